@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py — column-timesteps/s of the biogeophysics hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--size f02] [--impl reference]
+
+One "step" = one pass of the hot-path routines (clm_drv call order) over the
+rank's synthetic grid.  `value` is whole-job throughput with all state resident
+in HBM; `e2e` is the same step driven through the C ABI with HOST buffers
+(pinned), host<->device copies inside the timed region.  `roofline` is for the
+dominant kernel, `cpu_baseline` is the CPU oracle (C restatement of the
+reference, OpenMP over clumps) on a bounded sample of the same workload.
+Under torchrun each rank owns an equal, independent share (weak scaling); the
+path has no exchange step, so the only collectives are the timing reductions.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "column_timesteps_per_sec"
+UNIT = "column-steps/s"
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks line of B200_PROFILING.md, sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                t = [x.strip() for x in line.split(",")]
+                if len(t) < 9:
+                    continue
+                try:
+                    sm.append(float(t[1])); mx.append(float(t[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            hi = [s for s in sm if s >= 0.5 * max(sm)]
+            out["sm_mhz"] = float(np.median(hi))
+            out["sm_max_mhz"] = float(max(mx))
+            out["reasons"] = sorted(reasons)
+        return out
+
+
+def cpu_reference_run(size, steps, warmup, sample_gridcells, seed):
+    """The reference-arm / cpu_baseline measurement: oracle routines driven clump-parallel
+    (OpenMP over clumps like clm_driver.F90:525) on a bounded sample of the workload."""
+    from ctsm_b200 import abi, synthetic
+    from oracle import oracle
+    OL = oracle.lib()
+    nthreads = int(OL.oracle_num_threads())
+    sg, S = synthetic.make_case(sample_gridcells, seed=seed)
+    prm = abi.default_params()
+    clumps, keep = oracle.make_clumps(sg, nthreads * 4)
+    inout = [fs.name for g in ("soiltemperature", "soilwater") for fs in abi.FIELDS[g] if fs.intent != "IN"]
+    pristine = {k: S[k].copy() for k in set(inout)}
+    ft = abi.make_struct("soiltemperature", S, sg.bounds)
+    fw = abi.make_struct("soilwater", S, sg.bounds)
+    times = []
+    for it in range(warmup + steps):
+        for k, v in pristine.items():
+            S[k][...] = v
+        t0 = time.perf_counter()
+        rc = OL.oracle_step_clumps(C.byref(prm), len(clumps), clumps, C.byref(ft), C.byref(fw), 3)
+        t1 = time.perf_counter()
+        assert rc == 0
+        if it >= warmup:
+            times.append(t1 - t0)
+    tot = float(np.sum(times))
+    return {"value": sg.ncol * steps / tot, "ms_per_step": 1e3 * tot / steps, "cores": nthreads,
+            "columns": sg.ncol, "sample": "%d-gridcell (%d columns, %d patches) sample of the %s workload, %d steps, "
+            "C restatement of the reference (gcc -O2 -ffp-contract=off -fopenmp, one clump per task, %d threads)"
+            % (sg.ngrc, sg.ncol, sg.npatch, size, steps, nthreads)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", default="f02", help="tiny|f19|f09|f02 or a gridcell count (per GPU)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=20000, help="gridcells in the CPU baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    size = a.size if not a.size.isdigit() else int(a.size)
+    wl_name = "SoilTemperature+SoilWater one 1800 s step, %s-sized synthetic grid per GPU" % a.size
+    config = {"workload": wl_name, "grid": str(a.size), "routines": ["SoilTemperature", "SoilWater"],
+              "state": "restored from a pristine device snapshot before every step (untimed D2D copies)",
+              "l2": "inputs (GBs per step) exceed the 126 MB L2; no explicit flush", "parallelism": "clumps/gridcells sharded by rank, no collective"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(a.size, a.steps, a.warmup, a.cpu_sample, 20260101)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    from ctsm_b200 import abi, synthetic, driver
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; ctsm_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    prm = abi.default_params(device=local_rank)
+    ctx = driver.Context(prm)
+    sg, S = synthetic.make_case(size, seed=20260101 + 1000 * rank)
+    routines = driver.ROUTINES
+    names = sorted({fs.name for g in routines for fs in abi.FIELDS[g]})
+    D = {k: torch.from_numpy(S[k]).cuda() for k in names}
+    restore = sorted({fs.name for g in routines for fs in abi.FIELDS[g] if fs.intent != "IN"})
+    pristine = {k: D[k].clone() for k in restore}
+    hp = driver.HotPath(ctx, sg, D, abi.MEM_DEVICE, routines)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
+
+    def reset_state():
+        with torch.cuda.stream(stream):
+            for k, v in pristine.items():
+                D[k].copy_(v)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ncol = sg.ncol
+    for _ in range(a.warmup):
+        reset_state(); hp.step()
+    ctx.sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(routines) + 1)] for _ in range(a.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for it in range(a.steps):
+        reset_state()
+        ev[it][0].record(stream)
+        for i, g in enumerate(routines):
+            getattr(hp, {"soiltemperature": "SoilTemperature", "soilwater": "SoilWater"}[g])()
+            ev[it][i + 1].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ctx.sync()
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [ev[it][0].elapsed_time(ev[it][-1]) for it in range(a.steps)]
+    rt_ms = {g: float(np.mean([ev[it][i].elapsed_time(ev[it][i + 1]) for it in range(a.steps)])) for i, g in enumerate(routines)}
+    total_s = float(np.sum(step_ms)) / 1e3
+    t = torch.tensor([total_s], dtype=torch.float64, device="cuda")
+    cols = torch.tensor([float(ncol)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cols, op=dist.ReduceOp.SUM)
+    total_s, total_cols = float(t.item()), float(cols.item())
+    value = total_cols * a.steps / total_s
+
+    # roofline of the dominant kernel (per-routine event timing on the launching stream)
+    peak, peak_src = read_peaks()
+    dom = max(rt_ms, key=rt_ms.get)
+    ab = driver.algorithmic_bytes(sg, S, dom)
+    achieved = ab["bytes"] / (rt_ms[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": {"soiltemperature": "soiltemp_kernel", "soilwater": "soilwater_kernel"}[dom],
+                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "algorithmic_bytes_per_launch": ab["bytes"], "bytes_per_column": ab["bytes_per_column"],
+                "ms_per_launch": rt_ms[dom], "routine_ms": rt_ms}
+
+    # e2e: same step through the C ABI with pinned HOST buffers (H2D + kernels + D2H per step)
+    e2e = None
+    if not a.no_e2e:
+        H = {k: torch.from_numpy(S[k]).pin_memory() for k in names}
+        Hn = {k: v.numpy() for k, v in H.items()}
+        Hp = {k: S[k].copy() for k in restore}
+        hph = driver.HotPath(ctx, sg, Hn, abi.MEM_HOST, routines)
+        h2d, d2h = driver.staged_bytes(sg, routines, preserve_out=True)
+        e2e_steps = max(2, min(a.steps, 5))
+        ts = []
+        for it in range(1 + e2e_steps):
+            for k, v in Hp.items():
+                Hn[k][...] = v
+            barrier()
+            t0 = time.perf_counter()
+            hph.step()
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            if it >= 1:
+                ts.append(t1 - t0)
+        te = torch.tensor([float(np.sum(ts))], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_cols * e2e_steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+               "mode": "CTSM_MEM_HOST (all fields uploaded so that elements outside the filters are preserved)"}
+        del hph, H, Hn
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        r = cpu_reference_run(a.size, 3, 1, a.cpu_sample, 20260101)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * total_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": dict(config, columns_per_gpu=ncol, patches_per_gpu=sg.npatch),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "wall_s_timed_region": t_wall}
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

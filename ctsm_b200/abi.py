@@ -1,0 +1,253 @@
+"""ctypes binding of the C ABI in include/ctsm_b200.h.
+
+The field structs are generated from include/ctsm_b200_fields.def (the same
+X-macro table the C header and the CUDA library are generated from), so the
+three views cannot drift apart.
+
+Nothing in this module computes: it loads ``libctsm_b200.so`` (the CUDA
+library; there is no CPU fallback) and marshals pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEF_PATH = os.path.join(ROOT, "include", "ctsm_b200_fields.def")
+LIB_PATH = os.path.join(ROOT, "ctsm_b200", "lib", "libctsm_b200.so")
+
+NLEVSNO, NLEVGRND, NLEVSOI, NVEGWCS, NLEVCAN, MXPFT = 12, 25, 20, 4, 1, 78
+
+# LEV token -> (lower bound, number of levels); see ctsm_b200_fields.def header
+LEV = {
+    "L1": (1, 1),
+    "SNOSOI": (-NLEVSNO + 1, NLEVSNO + NLEVGRND),
+    "SNOSOI0": (-NLEVSNO, NLEVSNO + NLEVGRND + 1),
+    "GRND": (1, NLEVGRND),
+    "SOI": (1, NLEVSOI),
+    "SNO": (-NLEVSNO + 1, NLEVSNO),
+    "SNO1": (-NLEVSNO + 1, NLEVSNO + 1),
+    "VEGWCS": (1, NVEGWCS),
+    "CAN": (1, NLEVCAN),
+    "PFT": (0, MXPFT + 1),
+    "PFTVEGWCS": (0, (MXPFT + 1) * NVEGWCS),
+}
+
+MEM_DEVICE, MEM_HOST, MEM_HOST_NOPRESERVE = 0, 1, 3
+
+ISTSOIL, ISTCROP, ISTICE, ISTDLAK, ISTWET, ISTURB_MIN, ISTURB_MAX = 1, 2, 4, 5, 6, 7, 9
+
+
+class Bounds(C.Structure):
+    """decompMod.F90:60-68 bounds_type."""
+    _fields_ = [(n, C.c_int32) for n in (
+        "begg", "endg", "begl", "endl", "begc", "endc", "begp", "endp",
+        "begCohort", "endCohort", "level", "clump_index")]
+
+    def extent(self, sub: str) -> int:
+        b, e = SUB_BOUNDS[sub]
+        return getattr(self, e) - getattr(self, b) + 1
+
+    def beg(self, sub: str) -> int:
+        return getattr(self, SUB_BOUNDS[sub][0])
+
+    def copy(self) -> "Bounds":
+        o = Bounds()
+        C.memmove(C.byref(o), C.byref(self), C.sizeof(Bounds))
+        return o
+
+
+SUB_BOUNDS = {"GRC": ("begg", "endg"), "LUN": ("begl", "endl"), "COL": ("begc", "endc"),
+              "PATCH": ("begp", "endp"), "PFT": (None, None)}
+
+
+class Status(C.Structure):
+    _fields_ = [("code", C.c_int32), ("subgrid_level", C.c_int32), ("subgrid_index", C.c_int32),
+                ("info", C.c_int32), ("value", C.c_double), ("n_warnings", C.c_int32),
+                ("reserved", C.c_int32), ("msg", C.c_char * 160)]
+
+
+class Params(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32),
+                ("nlevsno", C.c_int32), ("nlevgrnd", C.c_int32), ("nlevsoi", C.c_int32),
+                ("dtime", C.c_double),
+                ("upper_boundary_condition", C.c_int32), ("lower_boundary_condition", C.c_int32),
+                ("flux_calculation", C.c_int32),
+                ("dtmin", C.c_double), ("verySmall", C.c_double), ("xTolerUpper", C.c_double),
+                ("xTolerLower", C.c_double), ("e_ice", C.c_double),
+                ("snow_thermal_cond_method", C.c_int32), ("snow_thermal_cond_glc_method", C.c_int32),
+                ("reserved_i", C.c_int32 * 8), ("reserved_d", C.c_double * 8)]
+
+
+def default_params(dtime: float = 1800.0, device: int = 0) -> Params:
+    """Python twin of ctsm_b200_default_params (clm6_0 namelist defaults,
+    namelist_defaults_ctsm.xml:471-488,511,254,556)."""
+    p = Params()
+    p.abi_version = 1
+    p.device = device
+    p.nlevsno, p.nlevgrnd, p.nlevsoi = NLEVSNO, NLEVGRND, NLEVSOI
+    p.dtime = dtime
+    p.upper_boundary_condition = 1
+    p.lower_boundary_condition = 2
+    p.flux_calculation = 1
+    p.dtmin, p.verySmall, p.xTolerUpper, p.xTolerLower = 60.0, 1.0e-8, 1.0e-1, 1.0e-2
+    p.e_ice = 6.0
+    p.snow_thermal_cond_method = 2
+    p.snow_thermal_cond_glc_method = 1
+    return p
+
+
+@dataclass(frozen=True)
+class FieldSpec:
+    name: str
+    ctype: str      # "double" | "int"
+    sub: str        # GRC | LUN | COL | PATCH | PFT
+    lev: str        # key of LEV
+    intent: str     # IN | OUT | INOUT
+    used_soil: int
+    used_snow: int
+    ref: str
+
+    @property
+    def dtype(self):
+        return np.float64 if self.ctype == "double" else np.int32
+
+    @property
+    def lo(self) -> int:
+        return LEV[self.lev][0]
+
+    @property
+    def nlev(self) -> int:
+        return LEV[self.lev][1]
+
+
+_F_RE = re.compile(r'CTSM_F\(\s*(\w+)\s*,\s*(\w+)\s*,\s*(\w+)\s*,\s*(\w+)\s*,\s*(\w+)\s*,'
+                   r'\s*(\d+)\s*,\s*(\d+)\s*,\s*"([^"]*)"\s*\)')
+
+
+def parse_fields(path: str = DEF_PATH) -> Dict[str, List[FieldSpec]]:
+    groups: Dict[str, List[FieldSpec]] = {}
+    cur: Optional[str] = None
+    with open(path) as fh:
+        for line in fh:
+            m = re.match(r"\s*#ifdef\s+CTSM_FIELDS_(\w+)", line)
+            if m:
+                cur = m.group(1).lower()
+                groups[cur] = []
+                continue
+            if re.match(r"\s*#endif", line):
+                cur = None
+                continue
+            m = _F_RE.search(line)
+            if m and cur is not None:
+                n, t, s, lv, it, us, usn, ref = m.groups()
+                groups[cur].append(FieldSpec(n, t, s, lv, it, int(us), int(usn), ref))
+    return groups
+
+
+FIELDS = parse_fields()
+
+
+def _make_struct(group: str):
+    flds = [("alloc", Bounds)]
+    for fs in FIELDS[group]:
+        flds.append((fs.name, C.POINTER(C.c_double if fs.ctype == "double" else C.c_int32)))
+    return type("ctsm_%s_fields_t" % group, (C.Structure,), {"_fields_": flds})
+
+
+STRUCTS = {g: _make_struct(g) for g in FIELDS}
+
+
+def _ptr(a, ctype):
+    """Raw pointer of a numpy array or a torch tensor (host or device)."""
+    if a is None:
+        return C.cast(None, C.POINTER(ctype))
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"], "field arrays must be contiguous (level-major, subgrid fastest)"
+        return a.ctypes.data_as(C.POINTER(ctype))
+    # torch tensor
+    assert a.is_contiguous()
+    return C.cast(a.data_ptr(), C.POINTER(ctype))
+
+
+def make_struct(group: str, arrays: dict, alloc: Bounds):
+    """Fill ctsm_<group>_fields_t from name -> array (numpy or torch).
+
+    Arrays are stored level-major: shape (nlev, n_subgrid) C-contiguous, which
+    is the Fortran (n_subgrid, nlev) column-major layout; 1-D fields have
+    shape (n_subgrid,).
+    """
+    st = STRUCTS[group]()
+    st.alloc = alloc
+    for fs in FIELDS[group]:
+        a = arrays[fs.name]
+        n = alloc.extent(fs.sub)
+        want = (n,) if fs.lev == "L1" else (fs.nlev, n)
+        assert tuple(a.shape) == want, "%s.%s: shape %s != %s" % (group, fs.name, tuple(a.shape), want)
+        kind = "float64" if fs.ctype == "double" else "int32"
+        assert str(a.dtype).endswith(kind), "%s.%s: dtype %s" % (group, fs.name, a.dtype)
+        setattr(st, fs.name, _ptr(a, C.c_double if fs.ctype == "double" else C.c_int32))
+    return st
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libctsm_b200.so (built in-tree by `make` / __graft_entry__.build()).
+
+    Fails loudly when the CUDA extension is missing: there is no CPU path.
+    """
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            "%s not found: build the CUDA library with `make` (or __graft_entry__.build()). "
+            "ctsm_b200 has no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32p, f64p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    L.ctsm_b200_default_params.argtypes = [C.POINTER(Params)]
+    L.ctsm_b200_default_params.restype = None
+    L.ctsm_b200_init.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    L.ctsm_b200_finalize.argtypes = [vp]
+    L.ctsm_b200_sync.argtypes = [vp, C.POINTER(Status)]
+    L.ctsm_b200_stream.argtypes = [vp]
+    L.ctsm_b200_stream.restype = vp
+    L.ctsm_b200_launch_count.argtypes = [vp]
+    L.ctsm_b200_launch_count.restype = C.c_int64
+    L.ctsm_b200_host_register.argtypes = [vp, C.c_uint64]
+    L.ctsm_b200_host_unregister.argtypes = [vp]
+    L.ctsm_b200_version.restype = C.c_char_p
+    L.ctsm_b200_tridiagonal.argtypes = [vp, C.POINTER(Bounds), C.c_int, C.c_int, i32p, C.c_int, i32p,
+                                        f64p, f64p, f64p, f64p, f64p, C.c_int]
+    L.ctsm_b200_banddiagonal.argtypes = [vp, C.POINTER(Bounds), C.c_int, C.c_int, i32p, i32p, C.c_int, i32p,
+                                         C.c_int, f64p, f64p, f64p, C.c_int, C.POINTER(Status)]
+    L.ctsm_b200_dgtsv_batch.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p,
+                                        f64p, f64p, f64p, f64p, f64p, C.c_int, C.POINTER(Status)]
+    L.ctsm_b200_soilwater.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p,
+                                      C.POINTER(STRUCTS["soilwater"]), C.c_int, C.POINTER(Status)]
+    L.ctsm_b200_soiltemperature.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p,
+                                            C.POINTER(STRUCTS["soiltemperature"]), C.c_int, C.POINTER(Status)]
+    for fn in ("init", "finalize", "sync", "host_register", "host_unregister", "tridiagonal", "banddiagonal",
+               "dgtsv_batch", "soilwater", "soiltemperature"):
+        getattr(L, "ctsm_b200_" + fn).restype = C.c_int
+    _lib = L
+    return L
+
+
+def i32p(a):
+    return _ptr(a, C.c_int32)
+
+
+def f64p(a):
+    return _ptr(a, C.c_double)

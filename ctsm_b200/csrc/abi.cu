@@ -1,0 +1,220 @@
+// abi.cu — lifecycle, status plumbing and host<->device staging of the C ABI
+// declared in include/ctsm_b200.h.  No compute here.
+#include "common.cuh"
+
+static const char* kVersion = "ctsm_b200 0.1.0 (sm_100a, fp64, -fmad=false)";
+
+extern "C" const char* ctsm_b200_version(void) { return kVersion; }
+
+extern "C" void ctsm_b200_default_params(ctsm_params_t* p) {
+  // clm6_0 defaults: bld/namelist_files/namelist_defaults_ctsm.xml:471-488 (soilwater_movement),
+  // :511 (nlevsno), :254 (20SL_8.5m), :556 (Sturm1997); e_ice is a parameter-file scalar.
+  memset(p, 0, sizeof *p);
+  p->abi_version = CTSM_B200_ABI_VERSION;
+  p->device = 0;
+  p->nlevsno = CTSM_NLEVSNO; p->nlevgrnd = CTSM_NLEVGRND; p->nlevsoi = CTSM_NLEVSOI;
+  p->dtime = 1800.0;
+  p->upper_boundary_condition = 1;
+  p->lower_boundary_condition = 2;
+  p->flux_calculation = 1;
+  p->dtmin = 60.0; p->verySmall = 1.e-8; p->xTolerUpper = 1.e-1; p->xTolerLower = 1.e-2;
+  p->e_ice = 6.0;
+  p->snow_thermal_cond_method = 2;
+  p->snow_thermal_cond_glc_method = 1;
+}
+
+extern "C" int ctsm_b200_init(const ctsm_params_t* p, ctsm_b200_ctx** out) {
+  if (!p || !out) return CTSM_ERR_BAD_ARG;
+  *out = nullptr;
+  if (p->abi_version != CTSM_B200_ABI_VERSION) return CTSM_ERR_BAD_ARG;
+  if (p->nlevsno != CTSM_NLEVSNO || p->nlevgrnd != CTSM_NLEVGRND || p->nlevsoi != CTSM_NLEVSOI) {
+    fprintf(stderr, "ctsm_b200_init: kernels are compiled for nlevsno=%d nlevgrnd=%d nlevsoi=%d\n", CTSM_NLEVSNO,
+            CTSM_NLEVGRND, CTSM_NLEVSOI);
+    return CTSM_ERR_BAD_ARG;
+  }
+  if (p->upper_boundary_condition != 1 || (p->lower_boundary_condition != 1 && p->lower_boundary_condition != 2))
+    return CTSM_ERR_BAD_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    fprintf(stderr, "ctsm_b200_init: no CUDA device (there is no CPU fallback)\n");
+    return CTSM_ERR_NO_DEVICE;
+  }
+  if (p->device < 0 || p->device >= ndev) return CTSM_ERR_BAD_ARG;
+  CUDA_TRY(cudaSetDevice(p->device));
+  ctsm_b200_ctx* ctx = new ctsm_b200_ctx();
+  ctx->prm = *p;
+  ctx->device = p->device;
+  ctx->launches = 0;
+  CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMalloc(&ctx->d_status, sizeof(DevStatus)));
+  CUDA_TRY(cudaMallocHost(&ctx->h_status, sizeof(DevStatus)));
+  DevStatus init; init.key = ~0ULL; init.n_warnings = 0; init.pad = 0;
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_status, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  *out = ctx;
+  return CTSM_OK;
+}
+
+extern "C" int ctsm_b200_finalize(ctsm_b200_ctx* ctx) {
+  if (!ctx) return CTSM_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->arena_fields.p); cudaFree(ctx->arena_filter0.p); cudaFree(ctx->arena_filter1.p);
+  cudaFree(ctx->arena_scratch.p); cudaFree(ctx->d_patchmask);
+  cudaFree(ctx->d_status); cudaFreeHost(ctx->h_status);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return CTSM_OK;
+}
+
+extern "C" void* ctsm_b200_stream(ctsm_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int64_t ctsm_b200_launch_count(const ctsm_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int ctsm_b200_host_register(void* ptr, uint64_t bytes) {
+  if (!ptr || !bytes) return CTSM_ERR_BAD_ARG;
+  CUDA_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return CTSM_OK;
+}
+extern "C" int ctsm_b200_host_unregister(void* ptr) {
+  if (!ptr) return CTSM_ERR_BAD_ARG;
+  CUDA_TRY(cudaHostUnregister(ptr));
+  return CTSM_OK;
+}
+
+static const char* message_for(int code) {
+  switch (code) {
+    case CTSM_ERR_DGBSV: return "BandDiagonal ERROR: dgbsv returned error code";
+    case CTSM_ERR_DGTSV: return "soilwater_moisture_form:: problem with the lapack solver";
+    case CTSM_ERR_FORC_HGT: return "CanopyFluxes: forcing height is below canopy height";
+    case CTSM_ERR_GS_NEG: return "PhotosynthesisHydraulicStress: negative stomatal conductance";
+    case CTSM_ERR_BRENT: return "brent_PHS: root must be bracketed";
+    case CTSM_ERR_QUADRATIC: return "quadratic solution error: b^2 - 4ac is negative";
+    case CTSM_ERR_URBAN: return "urban column in filter is outside the ctsm_b200 hot path";
+    case CTSM_ERR_BALANCE: return "BalanceCheck: balance error exceeds threshold";
+    default: return "";
+  }
+}
+
+void decode_status(const DevStatus& ds, ctsm_status_t* st) {
+  if (!st) return;
+  memset(st, 0, sizeof *st);
+  st->n_warnings = ds.n_warnings;
+  if (ds.key == ~0ULL) return;
+  st->subgrid_index = (int32_t)(ds.key >> 32);
+  st->code = (int32_t)((ds.key >> 24) & 0xff);
+  int info = (int)(ds.key & 0xffffff);
+  if (info & 0x800000) info |= ~0xffffff;   // sign-extend
+  st->info = info;
+  st->subgrid_level = (st->code == CTSM_ERR_FORC_HGT || st->code == CTSM_ERR_GS_NEG || st->code == CTSM_ERR_BRENT ||
+                       st->code == CTSM_ERR_QUADRATIC) ? CTSM_SUBGRID_PATCH : CTSM_SUBGRID_COLUMN;
+  snprintf(st->msg, sizeof st->msg, "%s", message_for(st->code));
+}
+
+extern "C" int ctsm_b200_sync(ctsm_b200_ctx* ctx, ctsm_status_t* st) {
+  if (!ctx) return CTSM_ERR_BAD_ARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  DevStatus got = *ctx->h_status;
+  if (got.key != ~0ULL || got.n_warnings != 0) {   // re-arm the record
+    DevStatus init; init.key = ~0ULL; init.n_warnings = 0; init.pad = 0;
+    *ctx->h_status = init;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_status, ctx->h_status, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  ctsm_status_t local;
+  decode_status(got, &local);
+  if (st) *st = local;
+  return local.code;
+}
+
+// DEVICE calls are asynchronous (status is collected by ctsm_b200_sync);
+// HOST calls are synchronous and return the status of this call.
+int finish_call(ctsm_b200_ctx* ctx, int mem, ctsm_status_t* st) {
+  if (mem == CTSM_MEM_DEVICE) {
+    if (st) memset(st, 0, sizeof *st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      fprintf(stderr, "ctsm_b200: launch error %s\n", cudaGetErrorString(e));
+      return CTSM_ERR_NO_DEVICE;
+    }
+    return CTSM_OK;
+  }
+  return ctsm_b200_sync(ctx, st);
+}
+
+int arena_reserve(ctsm_b200_ctx::Arena& a, size_t bytes) {
+  if (bytes <= a.cap) return CTSM_OK;
+  if (a.p) CUDA_TRY(cudaFree(a.p));
+  a.p = nullptr; a.cap = 0;
+  size_t want = bytes + bytes / 8 + 4096;
+  CUDA_TRY(cudaMalloc(&a.p, want));
+  a.cap = want;
+  return CTSM_OK;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int copy_range(void* dst, const void* src, int es, size_t ld, int nlev, size_t off, size_t ncall,
+                      cudaMemcpyKind kind, cudaStream_t s) {
+  if (ncall == 0) return CTSM_OK;
+  char* d = (char*)dst + off * es;
+  const char* h = (const char*)src + off * es;
+  if (ncall == ld) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)es * ld * nlev, kind, s));
+  } else {
+    CUDA_TRY(cudaMemcpy2DAsync(d, ld * es, h, ld * es, ncall * es, nlev, kind, s));
+  }
+  return CTSM_OK;
+}
+
+// Allocates the device mirrors (same layout and leading dimension as the host
+// arrays), points the device-side struct members at them and uploads IN/INOUT
+// (and, when preserve_out, OUT) fields over the call's bounds.
+int stage_begin(ctsm_b200_ctx* ctx, std::vector<StageField>& fl, const ctsm_bounds_t& alloc, const ctsm_bounds_t& call,
+                bool preserve_out) {
+  size_t total = 0;
+  for (auto& f : fl) {
+    if (!f.host_ptr) return CTSM_ERR_BAD_ARG;
+    const size_t ld = (size_t)(sub_end(alloc, f.sub) - sub_beg(alloc, f.sub) + 1);
+    total += align256((size_t)f.elem_size * ld * f.nlev);
+  }
+  int rc = arena_reserve(ctx->arena_fields, total);
+  if (rc) return rc;
+  size_t off = 0;
+  for (auto& f : fl) {
+    const size_t ld = (size_t)(sub_end(alloc, f.sub) - sub_beg(alloc, f.sub) + 1);
+    void* d = (char*)ctx->arena_fields.p + off;
+    *f.dev_slot = d;
+    off += align256((size_t)f.elem_size * ld * f.nlev);
+    if ((f.intent & INTENT_IN) || preserve_out) {
+      const size_t o = (size_t)(sub_beg(call, f.sub) - sub_beg(alloc, f.sub));
+      const size_t n = (size_t)(sub_end(call, f.sub) - sub_beg(call, f.sub) + 1);
+      rc = copy_range(d, f.host_ptr, f.elem_size, ld, f.nlev, o, n, cudaMemcpyHostToDevice, ctx->stream);
+      if (rc) return rc;
+    }
+  }
+  return CTSM_OK;
+}
+
+int stage_end(ctsm_b200_ctx* ctx, std::vector<StageField>& fl, const ctsm_bounds_t& alloc, const ctsm_bounds_t& call) {
+  for (auto& f : fl) {
+    if (!(f.intent & INTENT_OUT)) continue;
+    const size_t ld = (size_t)(sub_end(alloc, f.sub) - sub_beg(alloc, f.sub) + 1);
+    const size_t o = (size_t)(sub_beg(call, f.sub) - sub_beg(alloc, f.sub));
+    const size_t n = (size_t)(sub_end(call, f.sub) - sub_beg(call, f.sub) + 1);
+    int rc = copy_range(f.host_ptr, *f.dev_slot, f.elem_size, ld, f.nlev, o, n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (rc) return rc;
+  }
+  return CTSM_OK;
+}
+
+int stage_filter(ctsm_b200_ctx* ctx, ctsm_b200_ctx::Arena& a, const int32_t* host_filter, int numf,
+                 const int32_t** dev_filter) {
+  int rc = arena_reserve(a, sizeof(int32_t) * (size_t)(numf > 0 ? numf : 1));
+  if (rc) return rc;
+  if (numf > 0)
+    CUDA_TRY(cudaMemcpyAsync(a.p, host_filter, sizeof(int32_t) * (size_t)numf, cudaMemcpyHostToDevice, ctx->stream));
+  *dev_filter = (const int32_t*)a.p;
+  return CTSM_OK;
+}

@@ -1,0 +1,122 @@
+// common.cuh — shared declarations of the ctsm_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include "../../include/ctsm_b200.h"
+
+#define NLEVSNO CTSM_NLEVSNO
+#define NLEVGRND CTSM_NLEVGRND
+#define NLEVSOI CTSM_NLEVSOI
+#define SNOSOI_LO (-NLEVSNO + 1)
+#define SNOSOI0_LO (-NLEVSNO)
+
+// Physical constants: components/cdeps/share/shr_const_mod.F90:16-53 and
+// src/main/clm_varcon.F90:50-122.  Spelled exactly as the reference spells them
+// so the double-precision values are identical.
+namespace cst {
+constexpr double tfrz = 273.15;
+constexpr double denh2o = 1.000e3;
+constexpr double denice = 0.917e3;
+constexpr double cpliq = 4.188e3;
+constexpr double cpice = 2.11727e3;
+constexpr double hfus = 3.337e5;
+constexpr double hvap = 2.501e6;
+constexpr double sb = 5.67e-8;
+constexpr double grav = 9.80616;
+constexpr double tkair = 0.023;
+constexpr double tkice = 2.290;
+constexpr double tkwat = 0.57;
+constexpr double capr = 0.34;
+constexpr double cnfac = 0.5;
+constexpr double thk_bedrock = 3.0;
+constexpr double csol_bedrock = 2.0e6;
+constexpr double thin_sfclayer = 1.0e-6;   // SoilTemperatureMod.F90:84
+constexpr double m_to_mm = 1.e3;           // SoilWaterMovementMod.F90:65
+}  // namespace cst
+
+// Un-suffixed Fortran literals are REAL(4) constants promoted to double.
+#define R4(x) ((double)(float)(x))
+
+// Device-side "first failure" record (error convention).
+// key = subgrid index (32 bits, filters are ascending so the lowest index is the
+// first point the reference's loop would have reached) | code (8) | info (24).
+struct DevStatus {
+  unsigned long long key;
+  int n_warnings;
+  int pad;
+};
+
+__device__ __forceinline__ void report_failure(DevStatus* ds, int index, int code, int info) {
+  const unsigned long long key = ((unsigned long long)(uint32_t)index << 32) |
+                                 ((unsigned long long)(code & 0xff) << 24) | (unsigned long long)(info & 0xffffff);
+  atomicMin(&ds->key, key);
+}
+
+struct ctsm_b200_ctx {
+  ctsm_params_t prm;
+  int device;
+  cudaStream_t stream;
+  DevStatus* d_status;        // device
+  DevStatus* h_status;        // pinned host copy
+  int64_t launches;
+  // staging mirrors for CTSM_MEM_HOST calls: one grow-only device arena per purpose
+  struct Arena { void* p = nullptr; size_t cap = 0; };
+  Arena arena_fields, arena_filter0, arena_filter1, arena_scratch;
+  int32_t* d_patchmask = nullptr; size_t patchmask_cap = 0;
+};
+
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      fprintf(stderr, "ctsm_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__, __LINE__, \
+              cudaGetErrorString(_e));                                                       \
+      return CTSM_ERR_NO_DEVICE;                                                             \
+    }                                                                                        \
+  } while (0)
+
+// --- staging of field tables (abi.cu) -----------------------------------------
+enum SubLevel { SUB_GRC = 0, SUB_LUN = 1, SUB_COL = 2, SUB_PATCH = 3 };
+enum Intent { INTENT_IN = 1, INTENT_OUT = 2, INTENT_INOUT = 3 };
+struct LevShape { int lo; int n; };
+__host__ inline LevShape lev_shape(const char* lev) {
+  if (!strcmp(lev, "L1")) return {1, 1};
+  if (!strcmp(lev, "SNOSOI")) return {-NLEVSNO + 1, NLEVSNO + NLEVGRND};
+  if (!strcmp(lev, "SNOSOI0")) return {-NLEVSNO, NLEVSNO + NLEVGRND + 1};
+  if (!strcmp(lev, "GRND")) return {1, NLEVGRND};
+  if (!strcmp(lev, "SOI")) return {1, NLEVSOI};
+  if (!strcmp(lev, "SNO")) return {-NLEVSNO + 1, NLEVSNO};
+  if (!strcmp(lev, "SNO1")) return {-NLEVSNO + 1, NLEVSNO + 1};
+  if (!strcmp(lev, "VEGWCS")) return {1, CTSM_NVEGWCS};
+  return {1, 1};
+}
+
+struct StageField {
+  void** dev_slot;      // where the device pointer goes (member of the device-side field struct)
+  void* host_ptr;       // host array (element (alloc_beg, lev_lo))
+  int elem_size;
+  int sub;
+  int nlev;
+  int intent;
+};
+
+int arena_reserve(ctsm_b200_ctx::Arena& a, size_t bytes);
+int stage_begin(ctsm_b200_ctx* ctx, std::vector<StageField>& fl, const ctsm_bounds_t& alloc, const ctsm_bounds_t& call,
+                bool preserve_out);
+int stage_end(ctsm_b200_ctx* ctx, std::vector<StageField>& fl, const ctsm_bounds_t& alloc, const ctsm_bounds_t& call);
+int stage_filter(ctsm_b200_ctx* ctx, ctsm_b200_ctx::Arena& a, const int32_t* host_filter, int numf, const int32_t** dev_filter);
+int finish_call(ctsm_b200_ctx* ctx, int mem, ctsm_status_t* st);
+void decode_status(const DevStatus& ds, ctsm_status_t* st);
+
+static inline int sub_beg(const ctsm_bounds_t& b, int sub) {
+  return sub == SUB_GRC ? b.begg : sub == SUB_LUN ? b.begl : sub == SUB_COL ? b.begc : b.begp;
+}
+static inline int sub_end(const ctsm_bounds_t& b, int sub) {
+  return sub == SUB_GRC ? b.endg : sub == SUB_LUN ? b.endl : sub == SUB_COL ? b.endc : b.endp;
+}
+
+// launch geometry: grids sized in whole waves of the 148 SMs where the work allows
+static inline int grid_for(int n, int block) { return (n + block - 1) / block; }

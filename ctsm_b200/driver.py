@@ -1,0 +1,130 @@
+"""Host-side mirror of the hot-path call sites in clm_drv.
+
+Reference call order inside the clump loop (src/main/clm_driver.F90):
+    CanopyFluxes :766  ->  SoilTemperature :900  ->  HydrologyNoDrainage/SoilWater :950
+(+ BalanceCheck :1422 in the second clump loop).  This module owns a library
+context and the device-resident state and issues those calls through the C ABI
+(include/ctsm_b200.h).  It contains no arithmetic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, Optional
+
+import numpy as np
+
+from . import abi
+
+ROUTINES = ("soiltemperature", "soilwater")   # call order of the routines built so far
+
+
+class CtsmError(RuntimeError):
+    """Raised where the reference would call endrun()."""
+
+    def __init__(self, st: abi.Status, rc: int):
+        self.code, self.subgrid_level, self.subgrid_index, self.info = rc, st.subgrid_level, st.subgrid_index, st.info
+        super().__init__("ctsm_b200 rc=%d level=%d index=%d info=%d: %s" % (
+            rc, st.subgrid_level, st.subgrid_index, st.info, st.msg.decode()))
+
+
+class Context:
+    def __init__(self, prm: Optional[abi.Params] = None):
+        self.L = abi.lib()
+        self.prm = prm if prm is not None else abi.default_params()
+        self.h = C.c_void_p()
+        rc = self.L.ctsm_b200_init(C.byref(self.prm), C.byref(self.h))
+        if rc != 0:
+            raise RuntimeError("ctsm_b200_init failed (rc=%d): no usable CUDA device; there is no CPU fallback" % rc)
+
+    def close(self):
+        if self.h:
+            self.L.ctsm_b200_finalize(self.h)
+            self.h = C.c_void_p()
+
+    def sync(self) -> abi.Status:
+        st = abi.Status()
+        rc = self.L.ctsm_b200_sync(self.h, C.byref(st))
+        if rc != 0:
+            raise CtsmError(st, rc)
+        return st
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(self.L.ctsm_b200_stream(self.h) or 0)
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.ctsm_b200_launch_count(self.h))
+
+
+class HotPath:
+    """One rank's share of the grid: subgrid topology, filters and state arrays
+    (numpy = host-owned as in the Fortran model, torch = device-resident)."""
+
+    def __init__(self, ctx: Context, sg, arrays: Dict[str, object], mem: int, routines: Iterable[str] = ROUTINES):
+        self.ctx, self.sg, self.arrays, self.mem = ctx, sg, arrays, mem
+        self.routines = tuple(routines)
+        self.structs = {g: abi.make_struct(g, arrays, sg.bounds) for g in self.routines}
+        self.filters = dict(sg.filters)
+        if mem == abi.MEM_DEVICE:
+            import torch
+            self.filters = {k: torch.from_numpy(v).cuda() for k, v in sg.filters.items()}
+        self.nfilter = {k: len(v) for k, v in sg.filters.items()}
+
+    # -- individual routines (names and argument meaning follow the Fortran) ---------------
+    def SoilTemperature(self):
+        st = abi.Status()
+        rc = self.ctx.L.ctsm_b200_soiltemperature(
+            self.ctx.h, C.byref(self.sg.bounds), self.nfilter["nolakep"], abi.i32p(self.filters["nolakep"]),
+            self.nfilter["nolakec"], abi.i32p(self.filters["nolakec"]), C.byref(self.structs["soiltemperature"]),
+            self.mem, C.byref(st))
+        if rc != 0:
+            raise CtsmError(st, rc)
+
+    def SoilWater(self):
+        st = abi.Status()
+        rc = self.ctx.L.ctsm_b200_soilwater(
+            self.ctx.h, C.byref(self.sg.bounds), self.nfilter["hydrologyc"], abi.i32p(self.filters["hydrologyc"]),
+            C.byref(self.structs["soilwater"]), self.mem, C.byref(st))
+        if rc != 0:
+            raise CtsmError(st, rc)
+
+    def step(self):
+        for g in self.routines:
+            {"soiltemperature": self.SoilTemperature, "soilwater": self.SoilWater}[g]()
+
+
+def staged_bytes(sg, routines: Iterable[str], preserve_out: bool = True):
+    """Bytes a CTSM_MEM_HOST step moves over PCIe (fields + filters), from the field table."""
+    h2d = d2h = 0
+    for g in routines:
+        for fs in abi.FIELDS[g]:
+            n = sg.bounds.extent(fs.sub) * fs.nlev * (8 if fs.ctype == "double" else 4)
+            if fs.intent in ("IN", "INOUT") or preserve_out:
+                h2d += n
+            if fs.intent in ("OUT", "INOUT"):
+                d2h += n
+    h2d += 4 * (len(sg.filters["nolakec"]) + len(sg.filters["nolakep"]) + len(sg.filters["hydrologyc"]))
+    return h2d, d2h
+
+
+def algorithmic_bytes(sg, S, group: str) -> Dict[str, float]:
+    """Algorithmic bytes per launch of one routine, from the field table:
+    for every field, (levels >= 1 touched + active snow levels if touched) x element size x units in the
+    filter, counted once for IN or OUT and twice for INOUT."""
+    if group == "soilwater":
+        ncol = len(sg.filters["hydrologyc"]); cols = sg.filters["hydrologyc"] - 1
+        npat = 0; pats = np.zeros(0, dtype=np.int64)
+    else:
+        ncol = len(sg.filters["nolakec"]); cols = sg.filters["nolakec"] - 1
+        npat = len(sg.filters["nolakep"]); pats = sg.filters["nolakep"] - 1
+    snow_c = float(np.mean(-S["snl"][cols])) if ncol else 0.0
+    snow_p = float(np.mean(-S["snl"][sg.patch_column[pats] - 1])) if npat else 0.0
+    total = 0.0
+    for fs in abi.FIELDS[group]:
+        es = 8 if fs.ctype == "double" else 4
+        units, snow = (npat, snow_p) if fs.sub == "PATCH" else (ncol, snow_c)
+        lev = fs.used_soil + fs.used_snow * snow
+        mult = 2 if fs.intent == "INOUT" else 1
+        total += units * lev * es * mult
+    return {"bytes": total, "columns": ncol, "patches": npat, "bytes_per_column": total / max(ncol, 1)}

@@ -1,0 +1,204 @@
+/* ctsm_b200.h — C ABI of the B200-native CTSM biogeophysics hot path.
+ *
+ * Every entry point below is what a Fortran `bind(C)` interface in the host
+ * model binds (see INTEGRATION.md for the shim module).  Each one replaces one
+ * reference subroutine, cited as file:line relative to the CTSM checkout:
+ *
+ *   ctsm_b200_tridiagonal        src/biogeophys/TridiagonalMod.F90:23
+ *   ctsm_b200_banddiagonal       src/biogeophys/BandDiagonalMod.F90:29   (LAPACK dgbsv semantics)
+ *   ctsm_b200_dgtsv_batch        src/biogeophys/SoilWaterMovementMod.F90:1279-1299 (LAPACK dgtsv call site)
+ *   ctsm_b200_soilwater          src/biogeophys/SoilWaterMovementMod.F90:240  (moisture_form, :976)
+ *   ctsm_b200_soiltemperature    src/biogeophys/SoilTemperatureMod.F90:92
+ *   ctsm_b200_canopyfluxes       src/biogeophys/CanopyFluxesMod.F90:191  (+ PhotosynthesisMod.F90:2704 PHS)
+ *   ctsm_b200_set_exposedvegp_filter  src/main/filterMod.F90:595
+ *   ctsm_b200_balancecheck       src/biogeophys/BalanceCheckMod.F90:445,859
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary;
+ *   - all subgrid indices and filters are 1-based proc-local, exactly as the
+ *     Fortran passes them; arrays are column-major, subgrid index fastest;
+ *   - `mem` says where the pointers live: CTSM_MEM_DEVICE (device-resident
+ *     state, kernels launched on the context stream, asynchronous) or
+ *     CTSM_MEM_HOST (host arrays as the Fortran owns them: the library stages
+ *     them through its device mirrors, synchronous);
+ *   - return value 0 = success; nonzero = the reference would have called
+ *     endrun(); ctsm_status_t then carries the subgrid level/index and the
+ *     message text of the reference's abort site (abortutils.F90:68-97);
+ *   - there is no CPU fallback: every compute entry point returns
+ *     CTSM_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef CTSM_B200_H
+#define CTSM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTSM_B200_ABI_VERSION 1
+
+/* fixed vertical structure the kernels are compiled for (clm_varpar.F90:43-54,
+ * 290-292; namelist_defaults_ctsm.xml:254,511).  ctsm_b200_init refuses any
+ * other configuration. */
+#define CTSM_NLEVSNO 12
+#define CTSM_NLEVGRND 25
+#define CTSM_NLEVSOI 20
+#define CTSM_NVEGWCS 4
+#define CTSM_NLEVCAN 1
+#define CTSM_MXPFT 78
+
+/* decompMod.F90:60-68 */
+typedef struct ctsm_bounds_t {
+  int32_t begg, endg;
+  int32_t begl, endl;
+  int32_t begc, endc;
+  int32_t begp, endp;
+  int32_t begCohort, endCohort;
+  int32_t level;
+  int32_t clump_index;
+} ctsm_bounds_t;
+
+/* decompMod.F90:26-32 */
+enum { CTSM_SUBGRID_UNSPECIFIED = -1, CTSM_SUBGRID_LNDGRID = 0, CTSM_SUBGRID_GRIDCELL = 1,
+       CTSM_SUBGRID_LANDUNIT = 2, CTSM_SUBGRID_COLUMN = 3, CTSM_SUBGRID_PATCH = 4 };
+
+/* landunit_varcon.F90:19-30 */
+enum { CTSM_ISTSOIL = 1, CTSM_ISTCROP = 2, CTSM_ISTICE = 4, CTSM_ISTDLAK = 5, CTSM_ISTWET = 6,
+       CTSM_ISTURB_MIN = 7, CTSM_ISTURB_MAX = 9 };
+
+enum { CTSM_MEM_DEVICE = 0, CTSM_MEM_HOST = 1,
+       /* host arrays, but OUT fields are not uploaded first: elements outside
+        * the filter / active levels come back undefined */
+       CTSM_MEM_HOST_NOPRESERVE = 3 };
+
+enum {
+  CTSM_OK = 0,
+  CTSM_ERR_NO_DEVICE = 1,       /* no usable CUDA device / CUDA runtime error   */
+  CTSM_ERR_BAD_ARG = 2,         /* NULL pointer, bad bounds, unsupported config  */
+  CTSM_ERR_DGBSV = 10,          /* BandDiagonalMod.F90:200-213  "BandDiagonal ERROR: dgbsv returned error code" */
+  CTSM_ERR_DGTSV = 11,          /* SoilWaterMovementMod.F90:1295 "soilwater_moisture_form:: problem with the lapack solver" */
+  CTSM_ERR_FORC_HGT = 12,       /* CanopyFluxesMod.F90:997-1002  forcing height below canopy height */
+  CTSM_ERR_GS_NEG = 13,         /* PhotosynthesisMod.F90:3686-3690 negative stomatal conductance */
+  CTSM_ERR_BRENT = 14,          /* PhotosynthesisMod.F90:4134-4137 root must be bracketed for brent */
+  CTSM_ERR_QUADRATIC = 15,      /* quadraticMod.F90:42-58 */
+  CTSM_ERR_URBAN = 16,          /* urban column in filter: outside the hot path */
+  CTSM_ERR_BALANCE = 20         /* BalanceCheckMod.F90:640-659,1060-1114 thresholds exceeded */
+};
+
+typedef struct ctsm_status_t {
+  int32_t code;           /* CTSM_OK or CTSM_ERR_* of the FIRST (lowest-index) failing point */
+  int32_t subgrid_level;  /* CTSM_SUBGRID_* as passed to endrun(subgrid_level=) */
+  int32_t subgrid_index;  /* 1-based proc-local index as passed to endrun(subgrid_index=) */
+  int32_t info;           /* LAPACK info / iteration count / site-specific integer */
+  double  value;          /* offending value where the reference prints one */
+  int32_t n_warnings;     /* count of points where the reference only write(iulog)s */
+  int32_t reserved;
+  char    msg[160];       /* message text of the reference's endrun call */
+} ctsm_status_t;
+
+/* Scalars the reference reads from namelists / parameter files at init.
+ * Defaults (ctsm_b200_default_params) follow namelist_defaults_ctsm.xml for
+ * clm6_0 physics (SURVEY.md section 5 "Config / flag system"). */
+typedef struct ctsm_params_t {
+  int32_t abi_version;
+  int32_t device;                 /* CUDA device ordinal */
+  int32_t nlevsno, nlevgrnd, nlevsoi;
+  double  dtime;                  /* get_step_size_real() */
+  /* soilwater_movement_inparm, SoilWaterMovementMod.F90:104-236 */
+  int32_t upper_boundary_condition;  /* 1 = bc_flux (only supported value)        */
+  int32_t lower_boundary_condition;  /* 2 = bc_zero_flux, 1 = bc_flux             */
+  int32_t flux_calculation;          /* 1 = inexpensive, 42 = expensive           */
+  double  dtmin, verySmall, xTolerUpper, xTolerLower;
+  double  e_ice;                     /* params_inst%e_ice, SoilWaterMovementMod.F90:34 */
+  /* SoilTemperatureMod.F90:753-775 */
+  int32_t snow_thermal_cond_method;      /* 1 = Jordan1991, 2 = Sturm1997 */
+  int32_t snow_thermal_cond_glc_method;  /* 1 = Jordan1991, 2 = Sturm1997 */
+  int32_t reserved_i[8];
+  double  reserved_d[8];
+} ctsm_params_t;
+
+typedef struct ctsm_b200_ctx ctsm_b200_ctx;
+
+/* ---- field structs generated from ctsm_b200_fields.def ------------------- */
+#define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) ctype* name;
+typedef struct ctsm_soilwater_fields_t {
+  ctsm_bounds_t alloc;   /* lower/upper bounds the arrays were allocated with */
+#define CTSM_FIELDS_SOILWATER
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_SOILWATER
+} ctsm_soilwater_fields_t;
+
+typedef struct ctsm_soiltemperature_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_SOILTEMPERATURE
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_SOILTEMPERATURE
+} ctsm_soiltemperature_fields_t;
+#undef CTSM_F
+
+/* ---- lifecycle ------------------------------------------------------------ */
+void ctsm_b200_default_params(ctsm_params_t* p);
+int  ctsm_b200_init(const ctsm_params_t* p, ctsm_b200_ctx** ctx);
+int  ctsm_b200_finalize(ctsm_b200_ctx* ctx);
+/* wait for the context stream; fills *st from the device-side first-failure record */
+int  ctsm_b200_sync(ctsm_b200_ctx* ctx, ctsm_status_t* st);
+/* the cudaStream_t (as void*) all kernels of this context are launched on */
+void* ctsm_b200_stream(ctsm_b200_ctx* ctx);
+/* number of kernel launches issued by this context so far */
+int64_t ctsm_b200_launch_count(const ctsm_b200_ctx* ctx);
+/* page-lock a host array so that CTSM_MEM_HOST staging runs at full PCIe rate */
+int  ctsm_b200_host_register(void* ptr, uint64_t bytes);
+int  ctsm_b200_host_unregister(void* ptr);
+const char* ctsm_b200_version(void);
+
+/* ---- numerical primitives -------------------------------------------------- */
+
+/* Tridiagonal(bounds, lbj, ubj, jtop, numf, filter, a, b, c, r, u): TridiagonalMod.F90:23-91.
+ * a,b,c,r,u are (begc:endc, lbj:ubj); jtop is (begc:endc); filter(1:numf) holds
+ * column indices in [begc,endc].  Non-pivoting Thomas algorithm, only levels
+ * j >= jtop(ci) participate. */
+int ctsm_b200_tridiagonal(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int lbj, int ubj,
+                          const int32_t* jtop, int numf, const int32_t* filter,
+                          const double* a, const double* b, const double* c, const double* r,
+                          double* u, int mem);
+
+/* BandDiagonal(bounds, lbj, ubj, jtop, jbot, numf, filter, nband, b, r, u):
+ * BandDiagonalMod.F90:29-221.  b is (begc:endc, nband, lbj:ubj) with nband = 5;
+ * per column the rows jtop(ci)..jbot(ci) are solved with the semantics of
+ * LAPACK dgbsv(n, kl=2, ku=2, nrhs=1) (partial pivoting, dgbtf2 + dgbtrs).
+ * info != 0 is reported like the reference's endrun (CTSM_ERR_DGBSV). */
+int ctsm_b200_banddiagonal(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int lbj, int ubj,
+                           const int32_t* jtop, const int32_t* jbot, int numf, const int32_t* filter,
+                           int nband, const double* b, const double* r, double* u,
+                           int mem, ctsm_status_t* st);
+
+/* Batched LAPACK dgtsv(n, nrhs=1) as called at SoilWaterMovementMod.F90:1279-1299:
+ * for every filter column ci, n = nlayers(ci); dl = amx(ci,2:n), d = bmx(ci,1:n),
+ * du = cmx(ci,1:n-1), rhs = rmx(ci,1:n); x(ci,1:n) receives the solution.
+ * All 2-D arrays are (begc:endc, 1:nlev). */
+int ctsm_b200_dgtsv_batch(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int nlev,
+                          const int32_t* nlayers, int numf, const int32_t* filter,
+                          const double* amx, const double* bmx, const double* cmx, const double* rmx,
+                          double* x, int mem, ctsm_status_t* st);
+
+/* ---- physics ---------------------------------------------------------------- */
+
+/* SoilWater(bounds, num_hydrologyc, filter_hydrologyc, num_urbanc, filter_urbanc, ...):
+ * SoilWaterMovementMod.F90:240-243 with soilwater_movement_method = moisture_form (:976). */
+int ctsm_b200_soilwater(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
+                        int num_hydrologyc, const int32_t* filter_hydrologyc,
+                        const ctsm_soilwater_fields_t* f, int mem, ctsm_status_t* st);
+
+/* SoilTemperature(bounds, num_urbanl, filter_urbanl, num_urbanc, filter_urbanc,
+ *                 num_nolakep, filter_nolakep, num_nolakec, filter_nolakec, ...):
+ * SoilTemperatureMod.F90:92-95.  Urban filters must be empty (CTSM_ERR_URBAN). */
+int ctsm_b200_soiltemperature(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
+                              int num_nolakep, const int32_t* filter_nolakep,
+                              int num_nolakec, const int32_t* filter_nolakec,
+                              const ctsm_soiltemperature_fields_t* f, int mem, ctsm_status_t* st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTSM_B200_H */

@@ -1,0 +1,73 @@
+/* oracle.h — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C, gcc -O2 -ffp-contract=off like the reference's
+ * gnu.cmake:51-53 build) of the CTSM biogeophysics hot path.  Each function
+ * follows the Fortran routine it cites loop for loop (level-outer /
+ * filter-inner, full-size temporaries, one LAPACK call per column).
+ *
+ * Parity status: the reference cannot be compiled in this environment (no
+ * Fortran compiler, un-vendored submodules), and its own unit
+ * tests pin only plc/d1plc, quadratic, truncate_small_values and the
+ * BalanceCheck skip steps.  Those known answers are checked in
+ * tests/test_oracle_golden.py.  Everything else here is "PARITY UNPINNED": a
+ * restatement checked by analytic invariants (tests/test_oracle_*.py), not by
+ * reference outputs.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl
+ * reference) may call into this library.  The product (libctsm_b200.so) never
+ * links or loads it.
+ */
+#ifndef CTSM_ORACLE_H
+#define CTSM_ORACLE_H
+
+#include "../include/ctsm_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* LAPACK restatements (oracle_lapack.c) */
+void oracle_dgbsv(int n, int kl, int ku, int nrhs, double* ab, int ldab, int* ipiv, double* b, int ldb, int* info);
+void oracle_dgtsv(int n, int nrhs, double* dl, double* d, double* du, double* b, int ldb, int* info);
+
+/* TridiagonalMod.F90:23-91 */
+void oracle_tridiagonal(const ctsm_bounds_t* bounds, int lbj, int ubj, const int32_t* jtop, int numf,
+                        const int32_t* filter, const double* a, const double* b, const double* c,
+                        const double* r, double* u);
+/* BandDiagonalMod.F90:29-221; returns 0 or the first failing column's dgbsv info in st */
+int oracle_banddiagonal(const ctsm_bounds_t* bounds, int lbj, int ubj, const int32_t* jtop,
+                        const int32_t* jbot, int numf, const int32_t* filter, int nband,
+                        const double* b, const double* r, double* u, ctsm_status_t* st);
+/* SoilWaterMovementMod.F90:1279-1299 call shape */
+int oracle_dgtsv_batch(const ctsm_bounds_t* bounds, int nlev, const int32_t* nlayers, int numf,
+                       const int32_t* filter, const double* amx, const double* bmx, const double* cmx,
+                       const double* rmx, double* x, ctsm_status_t* st);
+
+/* SoilWaterMovementMod.F90:240 -> :976 */
+int oracle_soilwater(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_hydrologyc,
+                     const int32_t* filter_hydrologyc, const ctsm_soilwater_fields_t* f, ctsm_status_t* st);
+
+/* SoilTemperatureMod.F90:92 */
+int oracle_soiltemperature(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_nolakep,
+                           const int32_t* filter_nolakep, int num_nolakec, const int32_t* filter_nolakec,
+                           const ctsm_soiltemperature_fields_t* f, ctsm_status_t* st);
+
+/* one clump = what one OpenMP thread of clm_drv's clump loop owns (clm_driver.F90:525-527) */
+typedef struct oracle_clump_t {
+  ctsm_bounds_t bounds;
+  int32_t num_nolakep; const int32_t* filter_nolakep;
+  int32_t num_nolakec; const int32_t* filter_nolakec;
+  int32_t num_hydrologyc; const int32_t* filter_hydrologyc;
+  int32_t num_exposedvegp; const int32_t* filter_exposedvegp;
+} oracle_clump_t;
+/* which: bit 0 SoilTemperature, bit 1 SoilWater (call order of clm_drv) */
+int oracle_step_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump_t* clumps,
+                       const ctsm_soiltemperature_fields_t* ft, const ctsm_soilwater_fields_t* fw, int which);
+
+/* number of OpenMP threads the clump-loop drivers will use */
+int oracle_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

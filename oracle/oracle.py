@@ -1,0 +1,91 @@
+"""ctypes loader for the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs import this module; the
+product package ctsm_b200 never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+from ctsm_b200 import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "liboracle.so")
+_lib = None
+
+
+class Clump(C.Structure):
+    _fields_ = [("bounds", abi.Bounds),
+                ("num_nolakep", C.c_int32), ("filter_nolakep", C.POINTER(C.c_int32)),
+                ("num_nolakec", C.c_int32), ("filter_nolakec", C.POINTER(C.c_int32)),
+                ("num_hydrologyc", C.c_int32), ("filter_hydrologyc", C.POINTER(C.c_int32)),
+                ("num_exposedvegp", C.c_int32), ("filter_exposedvegp", C.POINTER(C.c_int32))]
+
+
+def make_clumps(sg, nclumps):
+    """Deal contiguous gridcell ranges to clumps (decompInitMod.F90:96-161 gives each clump whole
+    gridcells) and cut the proc-level filters at the clump bounds.  Returns (ctypes array, keepalive)."""
+    import numpy as np
+    ng = sg.ngrc
+    nclumps = max(1, min(nclumps, ng))
+    edges = np.linspace(0, ng, nclumps + 1).astype(np.int64)
+    arr = (Clump * nclumps)()
+    keep = []
+    for k in range(nclumps):
+        g0, g1 = int(edges[k]) + 1, int(edges[k + 1])
+        cols = np.nonzero((sg.col_gridcell >= g0) & (sg.col_gridcell <= g1))[0]
+        b = sg.bounds.copy()
+        b.begg, b.endg = g0, g1
+        b.begc, b.endc = int(cols[0]) + 1, int(cols[-1]) + 1
+        b.begl, b.endl = b.begc, b.endc
+        b.begp, b.endp = int(sg.col_patchi[cols[0]]), int(sg.col_patchf[cols[-1]])
+        b.level, b.clump_index = 2, k + 1
+        arr[k].bounds = b
+        for name, lo, hi in (("nolakep", b.begp, b.endp), ("nolakec", b.begc, b.endc),
+                             ("hydrologyc", b.begc, b.endc), ("exposedvegp", b.begp, b.endp)):
+            f = sg.filters.get(name)
+            if f is None:
+                f = np.zeros(0, dtype=np.int32)
+            sub = np.ascontiguousarray(f[(f >= lo) & (f <= hi)])
+            keep.append(sub)
+            setattr(arr[k], "num_" + name, len(sub))
+            setattr(arr[k], "filter_" + name, abi.i32p(sub))
+    return arr, keep
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(".c") or f.endswith(".h")]
+    srcs += [os.path.join(HERE, "..", "include", f) for f in ("ctsm_b200.h", "ctsm_b200_fields.def")]
+    stale = (not os.path.exists(LIB)) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-s", "-C", HERE, "liboracle.so"])
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(LIB)
+    i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    B, S, P = C.POINTER(abi.Bounds), C.POINTER(abi.Status), C.POINTER(abi.Params)
+    L.oracle_dgbsv.argtypes = [C.c_int] * 4 + [f64p, C.c_int, i32p, f64p, C.c_int, i32p]
+    L.oracle_dgbsv.restype = None
+    L.oracle_dgtsv.argtypes = [C.c_int, C.c_int, f64p, f64p, f64p, f64p, C.c_int, i32p]
+    L.oracle_dgtsv.restype = None
+    L.oracle_tridiagonal.argtypes = [B, C.c_int, C.c_int, i32p, C.c_int, i32p, f64p, f64p, f64p, f64p, f64p]
+    L.oracle_tridiagonal.restype = None
+    L.oracle_banddiagonal.argtypes = [B, C.c_int, C.c_int, i32p, i32p, C.c_int, i32p, C.c_int, f64p, f64p, f64p, S]
+    L.oracle_dgtsv_batch.argtypes = [B, C.c_int, i32p, C.c_int, i32p, f64p, f64p, f64p, f64p, f64p, S]
+    L.oracle_soilwater.argtypes = [P, B, C.c_int, i32p, C.POINTER(abi.STRUCTS["soilwater"]), S]
+    L.oracle_soiltemperature.argtypes = [P, B, C.c_int, i32p, C.c_int, i32p,
+                                         C.POINTER(abi.STRUCTS["soiltemperature"]), S]
+    L.oracle_num_threads.restype = C.c_int
+    L.oracle_step_clumps.argtypes = [P, C.c_int, C.POINTER(Clump), C.POINTER(abi.STRUCTS["soiltemperature"]),
+                                     C.POINTER(abi.STRUCTS["soilwater"]), C.c_int]
+    _lib = L
+    return L

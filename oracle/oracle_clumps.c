@@ -1,0 +1,32 @@
+/* oracle_clumps.c — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * The reference's CPU parallelism for the hot path: an OpenMP PARALLEL DO over
+ * clumps (src/main/clm_driver.F90:525-527, closes :1345), each thread calling
+ * the physics routines with its clump's bounds and filters.  This driver runs
+ * the oracle's routines the same way and is what bench.py times as the
+ * cpu_baseline ("port": C restatement, not gfortran — SURVEY.md F10).
+ */
+#include <stdlib.h>
+#include <string.h>
+#include "oracle.h"
+
+int oracle_step_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump_t* clumps,
+                       const ctsm_soiltemperature_fields_t* ft, const ctsm_soilwater_fields_t* fw, int which) {
+  int rc_all = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int nc = 0; nc < nclumps; ++nc) {
+    const oracle_clump_t* k = &clumps[nc];
+    ctsm_status_t st;
+    int rc = 0;
+    if ((which & 1) && ft)
+      rc = oracle_soiltemperature(prm, &k->bounds, k->num_nolakep, k->filter_nolakep, k->num_nolakec,
+                                  k->filter_nolakec, ft, &st);
+    if (!rc && (which & 2) && fw)
+      rc = oracle_soilwater(prm, &k->bounds, k->num_hydrologyc, k->filter_hydrologyc, fw, &st);
+    if (rc) {
+#pragma omp critical
+      rc_all = rc;
+    }
+  }
+  return rc_all;
+}

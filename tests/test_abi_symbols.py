@@ -1,0 +1,54 @@
+"""The C-ABI library must load (no GPU needed for that) and export every symbol
+include/ctsm_b200.h declares.  No compute call is made here."""
+import ctypes as C
+import os
+import re
+
+from ctsm_b200 import abi
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(abi.ROOT, "include", "ctsm_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(ctsm_b200_\w+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = abi.lib()
+    syms = _declared_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(L, s), "libctsm_b200.so does not export %s" % s
+
+
+def test_version_and_defaults_match_python_twin():
+    L = abi.lib()
+    assert b"sm_100a" in L.ctsm_b200_version()
+    p = abi.Params()
+    L.ctsm_b200_default_params(C.byref(p))
+    q = abi.default_params()
+    for name, _ in abi.Params._fields_:
+        if name.startswith("reserved"):
+            continue
+        assert getattr(p, name) == getattr(q, name), name
+
+
+def test_struct_layout_matches_def_table():
+    # one pointer per CTSM_F line + the alloc bounds
+    for g, specs in abi.FIELDS.items():
+        st = abi.STRUCTS[g]
+        assert C.sizeof(st) == C.sizeof(abi.Bounds) + 8 * len(specs)
+        names = [n for n, _ in st._fields_][1:]
+        assert names == [fs.name for fs in specs]
+
+
+def test_no_device_is_loud():
+    """Without a GPU the init call must fail with CTSM_ERR_NO_DEVICE, never fall back."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    L = abi.lib()
+    p = abi.default_params()
+    ctx = C.c_void_p()
+    assert L.ctsm_b200_init(C.byref(p), C.byref(ctx)) == 1
+    assert not ctx.value
