@@ -34,6 +34,7 @@ LEV = {
     "SNO1": (-NLEVSNO + 1, NLEVSNO + 1),
     "VEGWCS": (1, NVEGWCS),
     "CAN": (1, NLEVCAN),
+    "PHS2": (1, 2 * NLEVCAN),
     "PFT": (0, MXPFT + 1),
     "PFTVEGWCS": (0, (MXPFT + 1) * NVEGWCS),
 }
@@ -50,10 +51,14 @@ class Bounds(C.Structure):
         "begCohort", "endCohort", "level", "clump_index")]
 
     def extent(self, sub: str) -> int:
+        if sub == "PFT":
+            return MXPFT + 1
         b, e = SUB_BOUNDS[sub]
         return getattr(self, e) - getattr(self, b) + 1
 
     def beg(self, sub: str) -> int:
+        if sub == "PFT":
+            return 0
         return getattr(self, SUB_BOUNDS[sub][0])
 
     def copy(self) -> "Bounds":
@@ -81,24 +86,28 @@ class Params(C.Structure):
                 ("dtmin", C.c_double), ("verySmall", C.c_double), ("xTolerUpper", C.c_double),
                 ("xTolerLower", C.c_double), ("e_ice", C.c_double),
                 ("snow_thermal_cond_method", C.c_int32), ("snow_thermal_cond_glc_method", C.c_int32),
-                ("reserved_i", C.c_int32 * 8), ("reserved_d", C.c_double * 8)]
+                ("itmax_canopy_fluxes", C.c_int32), ("use_undercanopy_stability", C.c_int32),
+                ("use_biomass_heat_storage", C.c_int32), ("z0param_method", C.c_int32),
+                ("soil_resis_method", C.c_int32), ("use_hydrstress", C.c_int32), ("use_luna", C.c_int32),
+                ("stomatalcond_mtd", C.c_int32), ("light_inhibit", C.c_int32),
+                ("modifyphoto_and_lmr_forcrop", C.c_int32)] + [
+                (n, C.c_double) for n in (
+                    "lai_dl", "z_dl", "a_coef", "a_exp", "csoilc", "cv", "wind_min", "zetamaxstable", "leaf_mr_vcm",
+                    "act25", "fnr", "cp25_yr2000", "kc25_coef", "ko25_coef", "fnps", "theta_psii", "theta_ip",
+                    "vcmaxha", "jmaxha", "tpuha", "lmrha", "kcha", "koha", "cpha",
+                    "vcmaxhd", "jmaxhd", "tpuhd", "lmrhd", "lmrse",
+                    "tpu25ratio", "kp25ratio", "vcmaxse_sf", "jmaxse_sf", "tpuse_sf", "jmax25top_sf")] + [
+                ("balance_skip_steps", C.c_int32),
+                ("reserved_i", C.c_int32 * 7), ("reserved_d", C.c_double * 8)]
 
 
 def default_params(dtime: float = 1800.0, device: int = 0) -> Params:
-    """Python twin of ctsm_b200_default_params (clm6_0 namelist defaults,
-    namelist_defaults_ctsm.xml:471-488,511,254,556)."""
+    """ctsm_b200_default_params (clm6_0 namelist defaults, namelist_defaults_ctsm.xml) with dtime/device set.
+    Pure host code inside the library: works without a GPU."""
     p = Params()
-    p.abi_version = 1
+    lib().ctsm_b200_default_params(C.byref(p))
     p.device = device
-    p.nlevsno, p.nlevgrnd, p.nlevsoi = NLEVSNO, NLEVGRND, NLEVSOI
     p.dtime = dtime
-    p.upper_boundary_condition = 1
-    p.lower_boundary_condition = 2
-    p.flux_calculation = 1
-    p.dtmin, p.verySmall, p.xTolerUpper, p.xTolerLower = 60.0, 1.0e-8, 1.0e-1, 1.0e-2
-    p.e_ice = 6.0
-    p.snow_thermal_cond_method = 2
-    p.snow_thermal_cond_glc_method = 1
     return p
 
 
@@ -238,8 +247,12 @@ def lib():
                                       C.POINTER(STRUCTS["soilwater"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_soiltemperature.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p,
                                             C.POINTER(STRUCTS["soiltemperature"]), C.c_int, C.POINTER(Status)]
+    L.ctsm_b200_canopyfluxes.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p,
+                                         C.POINTER(STRUCTS["canopyfluxes"]), C.c_int, C.POINTER(Status)]
+    L.ctsm_b200_set_exposedvegp_filter.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, i32p, i32p, i32p, i32p, i32p,
+                                                   C.c_int]
     for fn in ("init", "finalize", "sync", "host_register", "host_unregister", "tridiagonal", "banddiagonal",
-               "dgtsv_batch", "soilwater", "soiltemperature"):
+               "dgtsv_batch", "soilwater", "soiltemperature", "canopyfluxes", "set_exposedvegp_filter"):
         getattr(L, "ctsm_b200_" + fn).restype = C.c_int
     _lib = L
     return L

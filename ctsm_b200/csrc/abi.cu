@@ -21,6 +21,31 @@ extern "C" void ctsm_b200_default_params(ctsm_params_t* p) {
   p->e_ice = 6.0;
   p->snow_thermal_cond_method = 2;
   p->snow_thermal_cond_glc_method = 1;
+  // canopyfluxes_inparm / clm6_0 switches: namelist_defaults_ctsm.xml:462,454,457,622,270,726,635,108,95,104,2182
+  p->itmax_canopy_fluxes = 40;
+  p->use_undercanopy_stability = 0;
+  p->use_biomass_heat_storage = 1;
+  p->z0param_method = 2;
+  p->soil_resis_method = 1;
+  p->use_hydrstress = 1;
+  p->use_luna = 1;
+  p->stomatalcond_mtd = 2;
+  p->light_inhibit = 1;
+  p->modifyphoto_and_lmr_forcrop = 1;
+  // parameter-file scalars: values documented inside the reference where available, otherwise
+  // synthetic choices (SURVEY.md Appendix D marks which)
+  p->lai_dl = 0.5; p->z_dl = 0.05; p->a_coef = 0.13; p->a_exp = 0.45; p->csoilc = 0.004; p->cv = 0.01;
+  p->wind_min = 1.0;
+  p->zetamaxstable = 2.0;
+  p->leaf_mr_vcm = 0.015;
+  p->act25 = 60.0; p->fnr = 7.16; p->cp25_yr2000 = 42.75e-6; p->kc25_coef = 404.9e-6; p->ko25_coef = 278.4e-3;
+  p->fnps = 0.15; p->theta_psii = 0.7; p->theta_ip = 0.95;
+  p->vcmaxha = 72000.0; p->jmaxha = 50000.0; p->tpuha = 72000.0; p->lmrha = 46390.0;
+  p->kcha = 79430.0; p->koha = 36380.0; p->cpha = 37830.0;
+  p->vcmaxhd = 200000.0; p->jmaxhd = 200000.0; p->tpuhd = 200000.0; p->lmrhd = 150650.0; p->lmrse = 490.0;
+  p->tpu25ratio = 0.167; p->kp25ratio = 20000.0;
+  p->vcmaxse_sf = 1.0; p->jmaxse_sf = 1.0; p->tpuse_sf = 1.0; p->jmax25top_sf = 1.0;
+  p->balance_skip_steps = -1;
 }
 
 extern "C" int ctsm_b200_init(const ctsm_params_t* p, ctsm_b200_ctx** out) {
@@ -32,6 +57,9 @@ extern "C" int ctsm_b200_init(const ctsm_params_t* p, ctsm_b200_ctx** out) {
             CTSM_NLEVGRND, CTSM_NLEVSOI);
     return CTSM_ERR_BAD_ARG;
   }
+  if (p->use_hydrstress != 1 || (p->z0param_method != 1 && p->z0param_method != 2) ||
+      (p->stomatalcond_mtd != 1 && p->stomatalcond_mtd != 2) || p->itmax_canopy_fluxes < 1)
+    return CTSM_ERR_BAD_ARG;
   if (p->upper_boundary_condition != 1 || (p->lower_boundary_condition != 1 && p->lower_boundary_condition != 2))
     return CTSM_ERR_BAD_ARG;
   int ndev = 0;
@@ -60,7 +88,7 @@ extern "C" int ctsm_b200_finalize(ctsm_b200_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->arena_fields.p); cudaFree(ctx->arena_filter0.p); cudaFree(ctx->arena_filter1.p);
-  cudaFree(ctx->arena_scratch.p); cudaFree(ctx->d_patchmask);
+  cudaFree(ctx->arena_scratch.p); cudaFree(ctx->arena_ints.p); cudaFree(ctx->d_patchmask);
   cudaFree(ctx->d_status); cudaFreeHost(ctx->h_status);
   cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -1,0 +1,1213 @@
+// canopy.cu — CanopyFluxes (+ PhotosynthesisHydraulicStress) on B200.
+//
+// Reference: src/biogeophys/CanopyFluxesMod.F90:191-1765 with
+//   FrictionVelocity / MoninObukIni   FrictionVelocityMod.F90:754-1209
+//   QSat                              QSatMod.F90:61-127
+//   calc_effective_soilporosity, calc_volumetric_h2oliq, calc_root_moist_stress
+//                                     SoilMoistStressMod.F90:70-514
+//   PhotosynthesisHydraulicStress     PhotosynthesisMod.F90:2704-3811 (callees in phs.cuh)
+//   TimeStepInit :1143, PhotosynthesisTotal :2065, truncate_small_values NumericsMod.F90:50
+//   setExposedvegpFilter              src/main/filterMod.F90:595-648
+//
+// B200 mapping.  The reference runs ~25 filter loops per ITERATION pass over clump-sized
+// scratch arrays and compacts the patch filter on the host side of every pass.  Here:
+//   canopy_colprep_kernel  one thread per column: eff_porosity / h2osoi_liqvol for columns that
+//                          own an exposed-vegetation patch (the reference writes them through a
+//                          duplicate-laden patch->column list; writes are idempotent);
+//   canopy_init_kernel     one thread per patch in bounds: TimeStepInit zeroing, rb1 = 0, and for
+//                          filter patches everything before the ITERATION loop, including the
+//                          iteration-invariant part of PHS (root-soil conductances: 20 pow per
+//                          patch, which the reference recomputes on every pass).  Builds the
+//                          active list with night patches packed from the front and day patches
+//                          from the back so that warps are (almost) homogeneous in the expensive
+//                          day/night branch of PHS;
+//   canopy_iter_kernel     one launch per ITERATION pass, persistent grid (multiple of the 148
+//                          SMs), one thread per still-unconverged patch.  Per-patch iteration
+//                          state lives in a compact structure-of-arrays workspace indexed by
+//                          filter position (coalesced); survivors are appended to the next active
+//                          list with __ballot_sync warp-aggregated atomics (order is irrelevant to
+//                          the numerics: patches are independent);
+//   canopy_final_kernel    one thread per filter patch: energy-balance check, stem temperature,
+//                          ground fluxes, 2 m diagnostics, longwave, dew update, totals.
+// Roofline: FP64 pipe / latency (hundreds of pow/exp/log per ~3 KB of patch traffic), not HBM
+// (SURVEY.md 8d); DESIGN.md section 4 has the algorithmic bytes.
+#include "phs.cuh"
+
+struct CanopyDev {
+#define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) ctype* name;
+#define CTSM_FIELDS_CANOPYFLUXES
+#include "../../include/ctsm_b200_fields.def"
+#undef CTSM_FIELDS_CANOPYFLUXES
+#undef CTSM_F
+};
+
+namespace {
+
+using phs::rgas;
+using phs::tfrz;
+using phs::spval;
+constexpr double rpi = 3.14159265358979323846;
+constexpr double sb = 5.67e-8, cpair = 1.00464e3, hvap = 2.501e6, vkc = 0.4, grav = 9.80616;
+constexpr double denice = 0.917e3, denh2o = 1.000e3, c_to_b = 2.0, tlsai_crit = 2.0, alpha_aero = 1.0;
+constexpr double c_water = 4.188e3, c_dry_biomass = 1400.0, nu_param = 1.5e-5, cd1_param = 7.5;
+constexpr int NPFT = CTSM_MXPFT + 1;
+
+// workspace slots (structure of arrays, one row of `stride` doubles per slot, indexed by filter position)
+enum Slot {
+  W_AIR, W_BIR, W_CIR, W_SA_LEAF, W_SA_STEM, W_SA_INT, W_FRS, W_CP_LEAF, W_CP_STEM, W_RSTEM, W_DAYL, W_UR, W_ZLDIS,
+  W_TL_INI, W_TS_INI, W_DEL, W_EFEB, W_EFE, W_OBUOLD, W_NMOZ, W_FM, W_EL, W_QSATL, W_QSATLDT, W_DELQ, W_DTH, W_DQH,
+  W_TLBEF, W_DT_VEG, W_TEMP1, W_TEMP2, W_TEMP12M, W_TEMP22M, W_WTG, W_WTA0, W_WTL0, W_WTSTEM0, W_WTAL, W_WTGQ, W_WTAQ0,
+  W_WTLQ0, W_WTALQ, W_LW_LEAF, W_LW_STEM, W_ERR, W_NSLOT
+};
+
+struct CanopyPrm {
+  double dtime;
+  int itmax, use_undercanopy_stability, use_biomass_heat_storage, z0param_method, soil_resis_method, use_luna,
+      medlyn, light_inhibit, modifyphoto_and_lmr_forcrop;
+  double lai_dl, z_dl, a_coef, a_exp, csoilc, cv, wind_min, zetamaxstable, leaf_mr_vcm;
+  double act25, fnr, cp25_yr2000, kc25_coef, ko25_coef, fnps, theta_psii, theta_ip;
+  double vcmaxha, jmaxha, tpuha, lmrha, kcha, koha, cpha, vcmaxhd, jmaxhd, tpuhd, lmrhd, lmrse;
+  double tpu25ratio, kp25ratio, vcmaxse_sf, jmaxse_sf, tpuse_sf, jmax25top_sf;
+};
+
+struct Geo {   // index bases / leading dimensions
+  int begp0, begc0, begg0, ldp, ldc;
+  int begp, endp, begc, endc;   // call bounds
+};
+
+struct Lists {          // device-side active lists
+  int* counts;          // [2*(itmax+3)]: per pass {night count, day count}
+  int* list_a;          // ping
+  int* list_b;          // pong
+  int* colflag;         // per column (alloc-based): owns an exposed-veg patch in this call
+  int n_warn_slot;
+};
+
+__device__ __forceinline__ double pow4(double t) { const double t2 = t * t; return t2 * t2; }
+__device__ __forceinline__ double pow3(double t) { return (t * t) * t; }
+
+// QSatMod.F90:61-127
+struct QS { double qs, es, qsdT; };
+__device__ __forceinline__ QS qsat(double T, double p, bool deriv) {
+  QS o;
+  const double td = fmin(100.0, fmax(-75.0, T - tfrz));
+  double es;
+  if (td >= 0.0)
+    es = 6.11213476 + td * (0.444007856 + td * (0.143064234e-01 + td * (0.264461437e-03 + td * (0.305903558e-05 + td * (0.196237241e-07 + td * (0.892344772e-10 + td * (-0.373208410e-12 + td * 0.209339997e-15)))))));
+  else
+    es = 6.11123516 + td * (0.503109514 + td * (0.188369801e-01 + td * (0.420547422e-03 + td * (0.614396778e-05 + td * (0.602780717e-07 + td * (0.387940929e-09 + td * (0.149436277e-11 + td * 0.262655803e-14)))))));
+  es = es * 100.0;
+  const double vp = 1.0 / (p - 0.378 * es);
+  const double vp1 = 0.622 * vp;
+  o.qs = es * vp1;
+  o.es = es;
+  o.qsdT = 0.0;
+  if (deriv) {
+    double d;
+    if (td >= 0.0)
+      d = 0.444017302 + td * (0.286064092e-01 + td * (0.794683137e-03 + td * (0.121211669e-04 + td * (0.103354611e-06 + td * (0.404125005e-09 + td * (-0.788037859e-12 + td * (-0.114596802e-13 + td * 0.381294516e-16)))))));
+    else
+      d = 0.503277922 + td * (0.377289173e-01 + td * (0.126801703e-02 + td * (0.249468427e-04 + td * (0.313703411e-06 + td * (0.257180651e-08 + td * (0.133268878e-10 + td * (0.394116744e-13 + td * 0.498070196e-16)))))));
+    d = d * 100.0;
+    const double vp2 = vp1 * vp;
+    o.qsdT = d * vp2 * p;
+  }
+  return o;
+}
+
+// FrictionVelocityMod.F90:1120-1155
+__device__ __forceinline__ double stab1(double zeta) {
+  const double chik2 = sqrt(1.0 - 16.0 * zeta);
+  const double chik = sqrt(chik2);
+  return 2.0 * log((1.0 + chik) * 0.5) + log((1.0 + chik2) * 0.5) - 2.0 * atan(chik) + rpi * 0.5;
+}
+__device__ __forceinline__ double stab2(double zeta) {
+  const double chik2 = sqrt(1.0 - 16.0 * zeta);
+  return 2.0 * log((1.0 + chik2) * 0.5);
+}
+// the four-regime log-law denominator shared by ustar / u10 (momentum) ...
+__device__ __forceinline__ double prof_m(double zldis, double zeta, double obu, double z0) {
+  const double zetam = 1.574;
+  if (zeta < -zetam)
+    return log(-zetam * obu / z0) - stab1(-zetam) + stab1(z0 / obu) + 1.14 * (pow(-zeta, 0.333) - pow(zetam, 0.333));
+  if (zeta < 0.0) return log(zldis / z0) - stab1(zeta) + stab1(z0 / obu);
+  if (zeta <= 1.0) return log(zldis / z0) + 5.0 * zeta - 5.0 * z0 / obu;
+  return log(obu / z0) + 5.0 - 5.0 * z0 / obu + (5.0 * log(zeta) + zeta - 1.0);
+}
+// ... and by temp1 / temp2 / temp12m / temp22m (scalars)
+__device__ __forceinline__ double prof_h(double zldis, double zeta, double obu, double z0) {
+  const double zetat = 0.465;
+  if (zeta < -zetat)
+    return log(-zetat * obu / z0) - stab2(-zetat) + stab2(z0 / obu) + 0.8 * (pow(zetat, -0.333) - pow(-zeta, -0.333));
+  if (zeta < 0.0) return log(zldis / z0) - stab2(zeta) + stab2(z0 / obu);
+  if (zeta <= 1.0) return log(zldis / z0) + 5.0 * zeta - 5.0 * z0 / obu;
+  return log(obu / z0) + 5.0 - 5.0 * z0 / obu + (5.0 * log(zeta) + zeta - 1.0);
+}
+
+struct FricOut { double ustar, temp1, temp2, temp12m, temp22m, fm, vds, u10_clm, u10; };
+// FrictionVelocity :842-1113 for one patch
+__device__ __forceinline__ FricOut friction_velocity(double hgt_u, double hgt_t, double hgt_q, double displa, double z0m,
+                                                     double z0h, double z0q, double obu, int iter, double ur, double um,
+                                                     double fm_prev) {
+  FricOut o;
+  double zldis = hgt_u - displa;
+  double zeta = zldis / obu;
+  o.ustar = vkc * um / prof_m(zldis, zeta, obu, z0m);
+  if (zeta < 0.0) o.vds = 2.e-3 * o.ustar * (1.0 + pow(300.0 / (-obu), 0.666));
+  else o.vds = 2.e-3 * o.ustar;
+  if (zldis - z0m <= 10.0) o.u10_clm = um;
+  else o.u10_clm = um - (o.ustar / vkc * prof_m(zldis, zeta, obu, 10.0 + z0m));
+  zldis = hgt_t - displa;
+  zeta = zldis / obu;
+  o.temp1 = vkc / prof_h(zldis, zeta, obu, z0h);
+  if (hgt_q == hgt_t && z0q == z0h) {
+    o.temp2 = o.temp1;
+  } else {
+    zldis = hgt_q - displa;
+    zeta = zldis / obu;
+    o.temp2 = vkc / prof_h(zldis, zeta, obu, z0q);
+  }
+  zldis = 2.0 + z0h;
+  zeta = zldis / obu;
+  o.temp12m = vkc / prof_h(zldis, zeta, obu, z0h);
+  if (z0q == z0h) {
+    o.temp22m = o.temp12m;
+  } else {
+    zldis = 2.0 + z0q;
+    zeta = zldis / obu;
+    o.temp22m = vkc / prof_h(zldis, zeta, obu, z0q);
+  }
+  zldis = hgt_u - displa;
+  zeta = zldis / obu;
+  double fmnew;
+  if (fmin(zeta, 1.0) < 0.0) {
+    const double t1 = pow(1.0 - 16.0 * fmin(zeta, 1.0), 0.25);
+    const double t2 = log((1.0 + t1 * t1) / 2.0);
+    const double t3 = log((1.0 + t1) / 2.0);
+    fmnew = 2.0 * t3 + t2 - 2.0 * atan(t1) + 1.5707963;
+  } else {
+    fmnew = -5.0 * fmin(zeta, 1.0);
+  }
+  o.fm = (iter == 1) ? fmnew : 0.5 * (fm_prev + fmnew);
+  double zeta10 = fmin(10.0 / obu, 1.0);
+  if (zeta == 0.0) zeta10 = 0.0;
+  double fm10;
+  if (zeta10 < 0.0) {
+    const double t1 = pow(1.0 - 16.0 * zeta10, 0.25);
+    const double t2 = log((1.0 + t1 * t1) / 2.0);
+    const double t3 = log((1.0 + t1) / 2.0);
+    fm10 = 2.0 * t3 + t2 - 2.0 * atan(t1) + 1.5707963;
+  } else {
+    fm10 = -5.0 * zeta10;
+  }
+  const double t4 = log(fmax(1.0, hgt_u / 10.0));
+  o.u10 = ur - o.ustar / vkc * (t4 - o.fm + fm10);
+  return o;
+}
+
+// statement functions PhotosynthesisMod.F90:2918-2920
+__device__ __forceinline__ double ft(double tl, double ha) { return exp(ha / (rgas * 1.e-3 * (tfrz + 25.0)) * (1.0 - (tfrz + 25.0) / tl)); }
+__device__ __forceinline__ double fth(double tl, double hd, double se, double sc) { return sc / (1.0 + exp((-hd + se * tl) / (rgas * 1.e-3 * tl))); }
+__device__ __forceinline__ double fth25(double hd, double se) { return 1.0 + exp((-hd + se * (tfrz + 25.0)) / (rgas * 1.e-3 * (tfrz + 25.0))); }
+
+#define PF(name) f.name[pp]
+#define PF2(name, j0) f.name[(size_t)(j0) * g.ldp + pp]           /* j0 = level - lower bound */
+#define CF(name) f.name[cc]
+#define CF2(name, j0) f.name[(size_t)(j0) * g.ldc + cc]
+#define WS(slot) ws[(size_t)(slot) * wstride + fi]
+
+// ---------------------------------------------------------------------------------------------
+__global__ void canopy_mark_kernel(CanopyDev f, Geo g, int fn, const int32_t* __restrict__ filterp, int* __restrict__ colflag,
+                                   int* __restrict__ fpos) {
+  const int fi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fi >= fn) return;
+  const int pp = filterp[fi] - g.begp0;
+  fpos[pp] = fi;
+  colflag[PF(column) - g.begc0] = 1;
+}
+
+// calc_effective_soilporosity :104-113, calc_volumetric_h2oliq :205-215 (jtop = 1)
+__global__ void __launch_bounds__(128)
+canopy_colprep_kernel(CanopyDev f, Geo g, const int* __restrict__ colflag) {
+  const int cc = (g.begc - g.begc0) + blockIdx.x * blockDim.x + threadIdx.x;
+  if (cc > g.endc - g.begc0) return;
+  if (!colflag[cc]) return;
+  for (int j = 1; j <= NLEVGRND; ++j) {
+    const double watsat = CF2(watsat, j - 1);
+    const double dz = CF2(dz, j - SNOSOI_LO);
+    const double vol_ice = fmin(watsat, CF2(h2osoi_ice, j - SNOSOI_LO) / (denice * dz));
+    const double eff = watsat - vol_ice;
+    CF2(eff_porosity, j - 1) = eff;
+    CF2(h2osoi_liqvol, j - SNOSOI_LO) = fmin(eff, CF2(h2osoi_liq, j - SNOSOI_LO) / (dz * denh2o));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// everything before the ITERATION loop (CanopyFluxesMod.F90:656-1023) + iteration-invariant PHS (:3063-3114)
+__global__ void __launch_bounds__(128)
+canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int* __restrict__ fpos, double* __restrict__ ws,
+                   int wstride, Lists L, DevStatus* ds) {
+  const int pp = (g.begp - g.begp0) + blockIdx.x * blockDim.x + threadIdx.x;
+  if (pp > g.endp - g.begp0) return;
+  // TimeStepInit :1158-1172 and rb1(begp:endp) = 0 (:830): every patch in bounds
+  if (!PF(patch_lakpoi)) {
+    PF(psnsun) = 0.0; PF(psnsun_wc) = 0.0; PF(psnsun_wj) = 0.0; PF(psnsun_wp) = 0.0;
+    PF(psnsha) = 0.0; PF(psnsha_wc) = 0.0; PF(psnsha_wj) = 0.0; PF(psnsha_wp) = 0.0;
+    PF(fpsn) = 0.0; PF(fpsn_wc) = 0.0; PF(fpsn_wj) = 0.0; PF(fpsn_wp) = 0.0;
+  }
+  PF(rb1) = 0.0;
+  const int fi = fpos[pp];
+  if (fi < 0) return;
+  const int cc = PF(column) - g.begc0;
+  const int gg = PF(gridcell) - g.begg0;
+  const int ivt = PF(itype);
+  const double elai = PF(elai), esai = PF(esai), htop = PF(htop);
+
+  PF(dhsdt_canopy) = 0.0;
+  // biomass heat storage :716-818
+  double frs, sa_leaf, sa_stem, sa_int, cp_leaf, cp_stem, rstem;
+  if (prm.use_biomass_heat_storage) {
+    const double fbw = f.pft_fbw[ivt], nstem = f.pft_nstem[ivt];
+    frs = (esai) / (elai + esai);
+    if (elai > 0.0) frs = 0.1 * frs;
+    const double dbh = f.pft_dbh[ivt];
+    sa_leaf = 2.0 * elai;
+    sa_stem = 1.0 * (nstem * (htop * rpi * dbh));
+    if (!(f.pft_is_tree[ivt] || f.pft_is_shrub[ivt]) || dbh < 0.05) {
+      frs = 0.0; sa_stem = 0.0; sa_leaf = sa_leaf + esai;
+    } else if (elai < 0.1) {
+      sa_leaf = sa_leaf + esai;
+    }
+    const double leaf_biomass = (1.e-3 * c_to_b / f.pft_slatop[ivt]) * fmax(0.01, 0.5 * sa_leaf) / (1.0 - fbw);
+    const double carea_stem = rpi * ((dbh * 0.5) * (dbh * 0.5));
+    const double stem_biomass = carea_stem * htop * 1.0 * nstem * f.pft_wood_density[ivt] / (1.0 - fbw);
+    PF(leaf_biomass) = leaf_biomass;
+    PF(stem_biomass) = stem_biomass;
+    sa_int = 0.0 * fmin(sa_leaf, sa_stem);
+    cp_leaf = leaf_biomass * (c_dry_biomass * (1.0 - fbw) + (fbw)*c_water);
+    cp_stem = 1.0 * (stem_biomass * (c_dry_biomass * (1.0 - fbw) + (fbw)*c_water));
+    rstem = f.pft_rstem_per_dbh[ivt] * dbh;
+  } else {
+    sa_leaf = (elai + esai); frs = 0.0; sa_stem = 0.0; sa_int = 0.0; cp_leaf = 0.0; cp_stem = 0.0; rstem = 0.0;
+  }
+  WS(W_FRS) = frs; WS(W_SA_LEAF) = sa_leaf; WS(W_SA_STEM) = sa_stem; WS(W_SA_INT) = sa_int;
+  WS(W_CP_LEAF) = cp_leaf; WS(W_CP_STEM) = cp_stem; WS(W_RSTEM) = rstem;
+  {
+    const double dayl = f.dayl[gg], mx = f.max_dayl[gg];
+    WS(W_DAYL) = fmin(1.0, fmax(0.01, (dayl * dayl) / (mx * mx)));      // :827
+  }
+
+  // calc_root_moist_stress_clm45default :377-431 (SMS btran, rresis, rootr)
+  {
+    const double smpsc = f.pft_smpsc[ivt], smpso = f.pft_smpso[ivt];
+    double btran = 0.0;
+    for (int j = 1; j <= NLEVGRND; ++j) {
+      const double liqvol = CF2(h2osoi_liqvol, j - SNOSOI_LO);
+      double rootr = 0.0;
+      if (!(liqvol <= 0.0 || CF2(t_soisno, j - SNOSOI_LO) <= tfrz - 2.0)) {
+        const double effp = CF2(eff_porosity, j - 1);
+        const double s_node = fmax(liqvol / effp, 0.01);
+        double smp_node = -CF2(sucsat, j - 1) * pow(s_node, -CF2(bsw, j - 1));
+        smp_node = fmax(smpsc, smp_node);
+        const double rresis = fmin((effp / CF2(watsat, j - 1)) * (smp_node - smpsc) / (smpso - smpsc), 1.0);
+        PF2(rresis, j - 1) = rresis;
+        rootr = PF2(rootfr, j - 1) * rresis;
+        btran = btran + fmax(rootr, 0.0);
+      }
+      PF2(rootr, j - 1) = rootr;
+    }
+    for (int j = 1; j <= NLEVGRND; ++j) {
+      if (btran > 0.0) PF2(rootr, j - 1) = PF2(rootr, j - 1) / btran;
+      else PF2(rootr, j - 1) = 0.0;
+    }
+    PF(btran) = btran;
+  }
+
+  // aerodynamic parameters :900-948
+  double displa, z0mv;
+  if (prm.z0param_method == 1) {
+    const double lt = fmin(elai + esai, tlsai_crit);
+    const double egvf = (1.0 - alpha_aero * exp(-lt)) / (1.0 - alpha_aero * exp(-tlsai_crit));
+    displa = egvf * PF(displa);
+    z0mv = exp(egvf * log(PF(z0mv)) + (1.0 - egvf) * log(CF(z0mg)));
+  } else {
+    double lt = fmax(1.e-5, elai + esai);
+    displa = htop * (1.0 - (1.0 - exp(-pow(cd1_param * lt, 0.5))) / pow(cd1_param * lt, 0.5));
+    lt = fmin(lt, f.pft_z0v_LAImax[ivt]);
+    const double zc = f.pft_z0v_c[ivt], cw = f.pft_z0v_cw[ivt];
+    const double ini = pow(f.pft_z0v_Cs[ivt] + f.pft_z0v_Cr[ivt] * lt * 0.5, -0.5) * zc * lt * 0.25;
+    double U = ini, delt = 2.0;
+    while (delt > 1.e-4) {
+      const double prev = U;
+      U = ini * exp(prev);
+      delt = fabs(U - prev);
+    }
+    U = 4.0 * U / lt / zc;
+    z0mv = htop * (1.0 - displa / htop) * exp(-vkc * U + log(cw) - 1.0 + 1.0 / cw);
+  }
+  PF(displa) = displa; PF(z0mv) = z0mv; PF(z0hv) = z0mv; PF(z0qv) = z0mv;
+  const double hgt_u = f.forc_hgt_u[gg] + z0mv + displa;
+  PF(forc_hgt_u_patch) = hgt_u;
+  PF(forc_hgt_t_patch) = f.forc_hgt_t[gg] + z0mv + displa;
+  PF(forc_hgt_q_patch) = f.forc_hgt_q[gg] + z0mv + displa;
+
+  // :951-995
+  const double emv = PF(emv), emg = CF(emg);
+  WS(W_AIR) = emv * (1.0 + (1.0 - emv) * (1.0 - emg)) * CF(forc_lwrad);
+  WS(W_BIR) = -(2.0 - emv * (1.0 - emg)) * emv * sb;
+  WS(W_CIR) = emv * emg * sb;
+  const double t_veg = PF(t_veg);
+  const QS q0 = qsat(t_veg, CF(forc_pbot), true);
+  WS(W_QSATL) = q0.qs; WS(W_EL) = q0.es; WS(W_QSATLDT) = q0.qsdT;
+  WS(W_NMOZ) = 0.0;
+  const double thm = PF(thm), forc_q = CF(forc_q);
+  const double taf = (CF(t_grnd) + thm) / 2.0;
+  const double qaf = (forc_q + CF(qg)) / 2.0;
+  PF(taf) = taf; PF(qaf) = qaf;
+  const double fu = f.forc_u[gg], fvv = f.forc_v[gg];
+  const double ur = fmax(prm.wind_min, sqrt(fu * fu + fvv * fvv));
+  const double dth = thm - taf, dqh = forc_q - qaf;
+  WS(W_UR) = ur; WS(W_DTH) = dth; WS(W_DQH) = dqh;
+  WS(W_DELQ) = CF(qg) - qaf;
+  const double dthv = dth * (1.0 + 0.61 * forc_q) + 0.61 * CF(forc_th) * dqh;
+  const double zldis = hgt_u - displa;
+  WS(W_ZLDIS) = zldis;
+  if (zldis < 0.0) report_failure(ds, pp + g.begp0, CTSM_ERR_FORC_HGT, 0);      // :990-1002
+
+  // MoninObukIni :1187-1207
+  {
+    const double thv = CF(thv);
+    double um;
+    if (dthv >= 0.0) um = fmax(ur, 0.1);
+    else um = sqrt(ur * ur + 0.5 * 0.5);
+    const double rib = grav * zldis * dthv / (thv * um * um);
+    double zeta;
+    if (rib >= 0.0) {
+      zeta = rib * log(zldis / z0mv) / (1.0 - 5.0 * fmin(rib, 0.19));
+      zeta = fmin(prm.zetamaxstable, fmax(zeta, 0.01));
+    } else {
+      zeta = rib * log(zldis / z0mv);
+      zeta = fmax(-100.0, fmin(zeta, -0.01));
+    }
+    PF(um) = um;
+    PF(obu) = zldis / zeta;
+  }
+  PF(num_iter) = 0.0;
+  WS(W_TL_INI) = t_veg;
+  WS(W_TS_INI) = PF(t_stem);
+  WS(W_DEL) = 0.0; WS(W_EFEB) = 0.0; WS(W_OBUOLD) = 0.0; WS(W_FM) = 0.0;
+  WS(W_WTLQ0) = 0.0; WS(W_WTALQ) = 0.0; WS(W_WTGQ) = 0.0; WS(W_WTAQ0) = 0.0;
+  PF(eflx_sh_stem) = 0.0;
+
+  // iteration-invariant part of PhotosynthesisHydraulicStress: root-soil interface conductance :3063-3114
+  {
+    const double froot_carbon = PF(froot_carbon), tsl = PF(tsai) + PF(tlai);
+    const double rr = f.pft_root_radius[ivt], rd = f.pft_root_density[ivt], frl = f.pft_froot_leaf[ivt], krmax = f.pft_krmax[ivt];
+    const double psi50r = f.pft_psi50[(size_t)phs::ROOT * NPFT + ivt], ckr = f.pft_ck[(size_t)phs::ROOT * NPFT + ivt];
+    for (int j = 1; j <= NLEVSOI; ++j) {
+      const double rootfr = PF2(rootfr, j - 1);
+      double rbd = c_to_b * froot_carbon * rootfr / CF2(dz, j - SNOSOI_LO);
+      rbd = fmax(c_to_b * 1.0, rbd);
+      const double area = rpi * (rr * rr);
+      const double rld = rbd / (rd * area);
+      const double rai = tsl * frl * rootfr;
+      const double r_soil = sqrt(1. / (rpi * rld));
+      double soil_c = fmin(CF2(hksat, j - 1), CF2(hk_l, j - 1)) / (1.e3 * r_soil);
+      const double fs = phs::plc(CF2(smp_l, j - 1), psi50r, ckr);
+      double root_c = (fs * rai * krmax) / (0.25 + CF2(z, j - SNOSOI_LO));
+      soil_c = fmax(soil_c, 1.e-16);
+      root_c = fmax(root_c, 1.e-16);
+      PF2(root_conductance, j - 1) = root_c;
+      PF2(soil_conductance, j - 1) = soil_c;
+      const double rs_resis = 1.0 / soil_c + 1.0 / root_c;
+      PF2(k_soil_root, j - 1) = (rai * rootfr > 0.0 && j > 1) ? 1.0 / rs_resis : 0.0;
+    }
+  }
+
+  // active list: night patches from the front, day patches from the back
+  const bool night = (PF2(parsun_z, 0) <= 0.0);
+  const unsigned act = __activemask();
+  const unsigned mnight = __ballot_sync(act, night);
+  const unsigned mine = night ? mnight : (act & ~mnight);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(mine) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(&L.counts[night ? 0 : 1], __popc(mine));
+  base = __shfl_sync(mine, base, leader);
+  const int rank = __popc(mine & ((1u << lane) - 1));
+  if (night) L.list_a[base + rank] = fi;
+  else L.list_a[fn - 1 - (base + rank)] = fi;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one ITERATION pass (CanopyFluxesMod.F90:1028-1457) for the still-active patches
+#define ITER_THREADS 64
+__global__ void __launch_bounds__(ITER_THREADS)
+canopy_iter_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef, const int32_t* __restrict__ filterp,
+                   double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in, int* __restrict__ list_out,
+                   DevStatus* ds) {
+  extern __shared__ double shm[];                       // [3][NLEVSOI][ITER_THREADS]
+  double* sk = shm + threadIdx.x;
+  double* sgv = shm + (size_t)NLEVSOI * ITER_THREADS + threadIdx.x;
+  double* ssv = shm + (size_t)2 * NLEVSOI * ITER_THREADS + threadIdx.x;
+  const int n_night = L.counts[2 * itlef], n_day = L.counts[2 * itlef + 1];
+  const int total = n_night + n_day;
+  const double dtime = prm.dtime;
+  for (int base = blockIdx.x * ITER_THREADS; base < total; base += gridDim.x * ITER_THREADS) {
+    const int t = base + threadIdx.x;
+    const bool live = t < total;
+    bool keep = false, night = false;
+    int fi = 0;
+    if (live) {
+      night = t < n_night;
+      fi = night ? list_in[t] : list_in[fn - 1 - (t - n_night)];
+      const int pp = filterp[fi] - g.begp0;
+      const int cc = PF(column) - g.begc0;
+      const int gg = PF(gridcell) - g.begg0;
+      const int ivt = PF(itype);
+      const double forc_pbot = CF(forc_pbot), forc_rho = CF(forc_rho), forc_q = CF(forc_q), t_grnd = CF(t_grnd);
+      const double thm = PF(thm), elai = PF(elai), esai = PF(esai), emv = PF(emv), htop = PF(htop);
+      const double laisun = PF(laisun), laisha = PF(laisha);
+      const double ur = WS(W_UR), zldis_u = WS(W_ZLDIS);
+      double t_veg = PF(t_veg);
+      const double t_stem = PF(t_stem);
+      double um = PF(um), obu = PF(obu), taf = PF(taf), qaf = PF(qaf);
+      const double displa = PF(displa), z0mv = PF(z0mv);
+
+      // FrictionVelocity :1033-1036
+      const FricOut fo = friction_velocity(PF(forc_hgt_u_patch), PF(forc_hgt_t_patch), PF(forc_hgt_q_patch), displa, z0mv,
+                                           z0mv, z0mv, obu, itlef + 1, ur, um, WS(W_FM));
+      const double ustar = fo.ustar, temp1 = fo.temp1, temp2 = fo.temp2;
+      PF(ustar) = ustar; PF(vds) = fo.vds; PF(u10_clm) = fo.u10_clm; PF(va) = um; PF(u10) = fo.u10; PF(fv) = ustar;
+      WS(W_FM) = fo.fm; WS(W_TEMP1) = temp1; WS(W_TEMP2) = temp2; WS(W_TEMP12M) = fo.temp12m; WS(W_TEMP22M) = fo.temp22m;
+
+      // :1038-1122
+      const double tlbef = t_veg;
+      const double del2 = WS(W_DEL);
+      const double ram1 = 1.0 / (ustar * ustar / um);
+      const double rah_a = 1.0 / (temp1 * ustar);
+      const double raw_a = 1.0 / (temp2 * ustar);
+      const double uaf = um * sqrt(1.0 / (ram1 * um));
+      const double uuc = fmin(0.4, (0.03 * um / ustar));
+      const double dleaf = f.pft_dleaf[ivt];
+      const double cfl = prm.cv / (sqrt(uaf) * sqrt(dleaf));
+      const double rb = 1.0 / (cfl * uaf);
+      const double w = exp(-(elai + esai));
+      const double csoilb = vkc / (prm.a_coef * pow(CF(z0mg) * uaf / nu_param, prm.a_exp));
+      const double ri = (grav * htop * (taf - t_grnd)) / (taf * (uaf * uaf));
+      double csoilcn;
+      if (prm.use_undercanopy_stability && (taf - t_grnd) > 0.0) {
+        const double ricsoilc = prm.csoilc / (1.00 + 0.5 * fmin(ri, 10.0));
+        csoilcn = csoilb * w + ricsoilc * (1.0 - w);
+      } else {
+        csoilcn = csoilb * w + prm.csoilc * (1.0 - w);
+      }
+      const double rah_b = prm.use_biomass_heat_storage ? 1.0 / (csoilcn * uuc) : 1.0 / (csoilcn * uaf);
+      const double raw_b = rah_b;
+      const double svpts = WS(W_EL);
+      const double eah = forc_pbot * qaf / 0.622;
+      PF(ram1) = ram1; PF(uaf) = uaf; PF(dleaf_patch) = dleaf; PF(rb1) = rb;
+      PF(rh_af) = eah / svpts;
+      PF(rah1) = rah_a; PF(raw1) = raw_a; PF(rah2) = rah_b; PF(raw2) = raw_b;
+      PF(vpd) = fmax((svpts - eah), 50.0) * 0.001;
+
+      // ---- PhotosynthesisHydraulicStress for this patch (:3118-3807) ----
+      const double qsatl = WS(W_QSATL);
+      bool bad_quad = false, notbracketed = false;
+      phs::PhsPatch P;
+      phs::Leaf Lf;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        P.psi50[s] = f.pft_psi50[(size_t)s * NPFT + ivt];
+        P.ck[s] = f.pft_ck[(size_t)s * NPFT + ivt];
+        P.kmax[s] = f.pft_kmax[(size_t)s * NPFT + ivt];
+      }
+      P.laisun = laisun; P.laisha = laisha; P.elai = elai; P.esai = esai; P.tsai = PF(tsai); P.htop = htop; P.fdry = PF(fdry);
+      P.forc_rho = forc_rho; P.forc_pbot = forc_pbot;
+      const double cfm = forc_pbot / (rgas * 1.e-3 * thm) * 1.e06;
+      P.cf = cfm;
+      P.qsatl = qsatl; P.qaf = qaf;
+      const double gb_mol = (1.0 / rb) * cfm;
+      P.gb_mol = gb_mol;
+      P.sk = sk; P.sg = sgv; P.ss = ssv; P.stride = ITER_THREADS;
+      {
+        double ksum = 0.0, ksmp = 0.0, ksmpg = 0.0, smpg = 0.0;
+        for (int j = 0; j < NLEVSOI; ++j) {
+          const double k = PF2(k_soil_root, j), sm = CF2(smp_l, j), gr = 1000.0 * CF2(z, j + 1 - SNOSOI_LO);
+          sk[j * ITER_THREADS] = k; sgv[j * ITER_THREADS] = gr; ssv[j * ITER_THREADS] = sm;
+          ksum += k; ksmp += k * sm; ksmpg += k * (sm - gr); smpg += sm - gr;
+        }
+        P.ksum = ksum; P.ksmp = ksmp; P.ksmpg = ksmpg; P.smpg_mean = smpg / NLEVSOI;
+      }
+      const bool c3 = ((int)nearbyint(f.pft_c3psn[ivt]) == 1);
+      const double crop = f.pft_crop[ivt];
+      Lf.c3 = c3; Lf.medlyn = prm.medlyn != 0;
+      Lf.qe = c3 ? 0.0 : 0.05;
+      Lf.bbb = c3 ? 10000.0 : 40000.0;
+      Lf.mbb = f.pft_mbbopt[ivt];
+      Lf.medint = f.pft_medlynintercept[ivt]; Lf.medslope = f.pft_medlynslope[ivt];
+      Lf.theta_cj = f.pft_theta_cj[ivt]; Lf.theta_ip = prm.theta_ip;
+      Lf.cair = f.forc_pco2[gg]; Lf.oair = f.forc_po2[gg];
+      {
+        const double kc25 = prm.kc25_coef * forc_pbot, ko25 = prm.ko25_coef * forc_pbot;
+        const double sco = 0.5 * 0.209 / prm.cp25_yr2000;
+        const double cp25 = 0.5 * Lf.oair / sco;
+        Lf.kc = kc25 * ft(t_veg, prm.kcha);
+        Lf.ko = ko25 * ft(t_veg, prm.koha);
+        Lf.cp = cp25 * ft(t_veg, prm.cpha);
+      }
+      PF(c3flag) = c3 ? 1 : 0; PF(qe) = Lf.qe; PF(kc) = Lf.kc; PF(ko) = Lf.ko; PF(cp) = Lf.cp; PF(gb_mol) = gb_mol;
+      const double t10 = PF(t_a10), dayl_factor = WS(W_DAYL);
+      const double lnc = fmin(1.0 / (f.pft_slatop[ivt] * f.pft_leafcn[ivt]), 10.0);
+      PF(lnca) = lnc;
+      double vcmax25top = lnc * f.pft_flnr[ivt] * prm.fnr * prm.act25 * dayl_factor;
+      vcmax25top = vcmax25top * f.pft_fnitr[ivt];
+      const double jmax25top = ((2.59 - 0.035 * fmin(fmax((t10 - tfrz), 11.0), 35.0)) * vcmax25top) * prm.jmax25top_sf;
+      const double tpu25top = prm.tpu25ratio * vcmax25top;
+      const double kp25top = prm.kp25ratio * vcmax25top;
+      PF(luvcmax25top) = vcmax25top; PF(lujmax25top) = jmax25top; PF(lutpu25top) = tpu25top;
+      const double lmr25top = c3 ? vcmax25top * prm.leaf_mr_vcm : vcmax25top * 0.025;
+      const int nrad = PF(nrad);
+      const double par_sun = PF2(parsun_z, 0), par_sha = PF2(parsha_z, 0);
+      Lf.par[0] = par_sun; Lf.par[1] = par_sha;
+      double jmax[2] = {0.0, 0.0};
+      Lf.vcmax[0] = Lf.vcmax[1] = Lf.tpu[0] = Lf.tpu[1] = Lf.kp[0] = Lf.kp[1] = 0.0;
+      double bsun = 0.0, bsha = 0.0, rs_z[2] = {0.0, 0.0}, psn_z[2] = {0.0, 0.0};
+      double wc_z[2] = {0.0, 0.0}, wj_z[2] = {0.0, 0.0}, wp_z[2] = {0.0, 0.0};
+      double qflx_tran_veg = PF(qflx_tran_veg);
+      if (nrad >= 1) {
+        const double ns[2] = {PF(vcmaxcintsun), PF(vcmaxcintsha)};
+        const bool luna = prm.use_luna && c3 && crop == 0.0;
+        const double vcmx25 = PF2(vcmx25_z, 0);
+        const double lmrc = fth25(prm.lmrhd, prm.lmrse);
+        const double tl_fac = fmin((0.2 * exp(3.218 * PF2(tlai_z, 0))), 1.0);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {                  // :3350-3374
+          double lmr25 = lmr25top * ns[s];
+          if (luna) lmr25 = prm.leaf_mr_vcm * vcmx25;
+          double lmr;
+          if (c3) {
+            lmr = lmr25 * ft(t_veg, prm.lmrha) * fth(t_veg, prm.lmrhd, prm.lmrse, lmrc);
+          } else {
+            lmr = lmr25 * pow(2.0, (t_veg - (tfrz + 25.0)) / 10.0);
+            lmr = lmr / (1.0 + exp(1.3 * (t_veg - (tfrz + 55.0))));
+          }
+          Lf.lmr[s] = lmr * tl_fac;
+        }
+        if (!(par_sun <= 0.0)) {                       // day :3393-3456
+          double v25[2], j25[2], t25[2];
+          if (luna) {
+            const double jmx25 = PF2(jmx25_z, 0);
+            v25[0] = v25[1] = vcmx25; j25[0] = j25[1] = jmx25;
+            t25[0] = prm.tpu25ratio * v25[0]; t25[1] = prm.tpu25ratio * v25[1];
+            if (ns[0] > 0.0) {
+              v25[1] = v25[0] * ns[1] / ns[0];
+              j25[1] = j25[0] * ns[1] / ns[0];
+              t25[1] = t25[0] * ns[1] / ns[0];
+            }
+          } else {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) { v25[s] = vcmax25top * ns[s]; j25[s] = jmax25top * ns[s]; t25[s] = tpu25top * ns[s]; }
+          }
+          const double tc = fmin(fmax((t10 - tfrz), 11.0), 35.0);
+          const double vcmaxse = (668.39 - 1.07 * tc) * prm.vcmaxse_sf;
+          const double jmaxse = (659.70 - 0.75 * tc) * prm.jmaxse_sf;
+          const double tpuse = (668.39 - 1.07 * tc) * prm.tpuse_sf;
+          const double vcmaxc = fth25(prm.vcmaxhd, vcmaxse), jmaxc = fth25(prm.jmaxhd, jmaxse), tpuc = fth25(prm.tpuhd, tpuse);
+          const double fv_ = ft(t_veg, prm.vcmaxha) , hv_ = fth(t_veg, prm.vcmaxhd, vcmaxse, vcmaxc);
+          const double fj_ = ft(t_veg, prm.jmaxha), hj_ = fth(t_veg, prm.jmaxhd, jmaxse, jmaxc);
+          const double ftp = ft(t_veg, prm.tpuha), htp = fth(t_veg, prm.tpuhd, tpuse, tpuc);
+          const double q10 = pow(2.0, (t_veg - (tfrz + 25.0)) / 10.0);
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            Lf.vcmax[s] = v25[s] * fv_ * hv_;
+            jmax[s] = j25[s] * fj_ * hj_;
+            Lf.tpu[s] = t25[s] * ftp * htp;
+            if (!c3) {
+              double v = v25[s] * q10;
+              v = v / (1.0 + exp(0.2 * ((tfrz + 15.0) - t_veg)));
+              v = v / (1.0 + exp(0.3 * (t_veg - (tfrz + 40.0))));
+              Lf.vcmax[s] = v;
+            }
+            Lf.kp[s] = (kp25top * ns[s]) * q10;
+          }
+        }
+        if (prm.light_inhibit && par_sun > 0.0) Lf.lmr[0] = Lf.lmr[0] * 0.67;      // :3461-3466
+        if (prm.light_inhibit && par_sha > 0.0) Lf.lmr[1] = Lf.lmr[1] * 0.67;
+        PF2(lmrsun_z, 0) = Lf.lmr[0]; PF2(lmrsha_z, 0) = Lf.lmr[1];
+        PF2(vcmax_z_phs, 0) = Lf.vcmax[0]; PF2(vcmax_z_phs, 1) = Lf.vcmax[1];
+        PF2(tpu_z_phs, 0) = Lf.tpu[0]; PF2(tpu_z_phs, 1) = Lf.tpu[1];
+        PF2(kp_z_phs, 0) = Lf.kp[0]; PF2(kp_z_phs, 1) = Lf.kp[1];
+
+        // leaf-level photosynthesis and stomatal conductance :3477-3714
+        const bool scale_an = (crop == 0.0 || !prm.modifyphoto_and_lmr_forcrop);
+        const int near_noon = f.near_local_noon[gg];
+        double xw[4];
+        phs::CiOut co;
+        double gs_mol[2], an[2], ci_z[2];
+        if (par_sun <= 0.0) {                          // night :3492-3547
+          xw[0] = 1.0; xw[1] = PF2(vegwp, 1); xw[2] = PF2(vegwp, 2); xw[3] = PF2(vegwp, 3);
+          const double gsmin = Lf.medlyn ? Lf.medint : Lf.bbb;
+          const phs::Stress st = phs::calcstress(P, xw, gsmin, gsmin, &qflx_tran_veg);
+          bsun = st.bsun; bsha = st.bsha;
+          const bool pd = f.local_time_lt_noon[gg] != 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { PF2(vegwp, i) = xw[i]; PF2(vegwp_pd, i) = pd ? xw[i] : spval; }
+          const double bb[2] = {bsun, bsha};
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            co.ac[s] = co.aj[s] = co.ap[s] = co.ag[s] = 0.0;
+            an[s] = scale_an ? 0.0 - bb[s] * Lf.lmr[s] : 0.0 - Lf.lmr[s];
+            rs_z[s] = fmin(2.e4, 1.0 / (fmax(bb[s] * gsmin, 1.0)) * cfm);
+            ci_z[s] = 0.0;
+            gs_mol[s] = cfm / rs_z[s];
+          }
+        } else {                                       // day :3549-3711
+          const double esat_tv = svpts;
+          const double ceair = fmin(eah, esat_tv);
+          if (!Lf.medlyn) Lf.rh_can = ceair / esat_tv;
+          else { Lf.rh_can = fmax((esat_tv - ceair), 50.0) * 0.001; PF(vpd_can) = Lf.rh_can; }
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const double qabs = 0.5 * (1.0 - prm.fnps) * Lf.par[s] * 4.6;
+            const phs::Quad q = phs::quadratic(prm.theta_psii, -(qabs + jmax[s]), qabs * jmax[s], &bad_quad);
+            Lf.je[s] = fmin(q.r1, q.r2);
+          }
+          const double vw[4] = {PF2(vegwp, 0), PF2(vegwp, 1), PF2(vegwp, 2), PF2(vegwp, 3)};
+          const phs::HybridOut h = phs::hybrid(P, Lf, vw, (c3 ? 0.7 : 0.4) * Lf.cair, co, &bad_quad, &notbracketed);
+          bsun = h.bsun; bsha = h.bsha;
+          qflx_tran_veg = h.tran;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { PF2(vegwp, i) = h.x[i]; PF2(vegwp_ln, i) = near_noon ? h.x[i] : spval; PF2(vegwp_pd, i) = spval; }
+          const double gsmin = Lf.medlyn ? Lf.medint : Lf.bbb;
+          const double bb[2] = {bsun, bsha};
+          gs_mol[0] = h.gs_sun; gs_mol[1] = h.gs_sha;
+          const double o3g[2] = {PF(o3coefgsun), PF(o3coefgsha)}, o3v[2] = {PF(o3coefvsun), PF(o3coefvsha)};
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            an[s] = co.an[s];
+            if (an[s] < 0.0) gs_mol[s] = fmax(bb[s] * gsmin, 1.0);
+            ci_z[s] = Lf.cair - an[s] * forc_pbot * (1.4 * gs_mol[s] + 1.6 * gb_mol) / (gb_mol * gs_mol[s]);
+            ci_z[s] = fmax(ci_z[s], 1.e-06);
+            const double gs = gs_mol[s] / cfm;
+            rs_z[s] = fmin(1.0 / gs, 2.e4);
+            rs_z[s] = rs_z[s] / o3g[s];
+            psn_z[s] = co.ag[s] * o3v[s];
+            if (co.ac[s] <= co.aj[s] && co.ac[s] <= co.ap[s]) wc_z[s] = psn_z[s];
+            else if (co.aj[s] < co.ac[s] && co.aj[s] <= co.ap[s]) wj_z[s] = psn_z[s];
+            else if (co.ap[s] < co.ac[s] && co.ap[s] < co.aj[s]) wp_z[s] = psn_z[s];
+          }
+          PF2(gs_mol_sun_ln, 0) = near_noon ? gs_mol[0] : spval;
+          PF2(gs_mol_sha_ln, 0) = near_noon ? gs_mol[1] : spval;
+          if (gs_mol[0] < 0.0 || gs_mol[1] < 0.0) report_failure(ds, pp + g.begp0, CTSM_ERR_GS_NEG, 0);
+        }
+        PF2(ac_phs, 0) = co.ac[0]; PF2(ac_phs, 1) = co.ac[1]; PF2(aj_phs, 0) = co.aj[0]; PF2(aj_phs, 1) = co.aj[1];
+        PF2(ap_phs, 0) = co.ap[0]; PF2(ap_phs, 1) = co.ap[1]; PF2(ag_phs, 0) = co.ag[0]; PF2(ag_phs, 1) = co.ag[1];
+        PF2(an_sun, 0) = an[0]; PF2(an_sha, 0) = an[1];
+        PF2(gs_mol_sun, 0) = gs_mol[0]; PF2(gs_mol_sha, 0) = gs_mol[1];
+        PF2(cisun_z, 0) = ci_z[0]; PF2(cisha_z, 0) = ci_z[1];
+        PF2(rssun_z, 0) = rs_z[0]; PF2(rssha_z, 0) = rs_z[1];
+        PF2(psnsun_z, 0) = psn_z[0]; PF2(psnsha_z, 0) = psn_z[1];
+      }
+      if (bad_quad) report_failure(ds, pp + g.begp0, CTSM_ERR_QUADRATIC, 0);
+      if (notbracketed) report_failure(ds, pp + g.begp0, CTSM_ERR_BRENT, 0);
+      // canopy sums :3724-3807 (nlevcan = 1)
+      double rssun, rssha, btran;
+      {
+        const bool scale_lmr = (crop == 0.0 && prm.modifyphoto_and_lmr_forcrop);
+        const double lz[2] = {nrad >= 1 ? PF2(laisun_z, 0) : 0.0, nrad >= 1 ? PF2(laisha_z, 0) : 0.0};
+        const double bb[2] = {bsun, bsha};
+        double psn[2], pwc[2], pwj[2], pwp[2], lmr[2], rs[2], lai[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          double a = 0.0, b_ = 0.0, c_ = 0.0, d_ = 0.0, e_ = 0.0, gsc = 0.0, ll = 0.0;
+          if (nrad >= 1) {
+            a = a + psn_z[s] * lz[s]; b_ = b_ + wc_z[s] * lz[s]; c_ = c_ + wj_z[s] * lz[s]; d_ = d_ + wp_z[s] * lz[s];
+            e_ = scale_lmr ? e_ + Lf.lmr[s] * lz[s] * bb[s] : e_ + Lf.lmr[s] * lz[s];
+            gsc = gsc + lz[s] / (rb + rs_z[s]);
+            ll = ll + lz[s];
+          }
+          lai[s] = ll;
+          if (ll > 0.0) { psn[s] = a / ll; pwc[s] = b_ / ll; pwj[s] = c_ / ll; pwp[s] = d_ / ll; lmr[s] = e_ / ll; rs[s] = ll / gsc - rb; }
+          else { psn[s] = 0.0; pwc[s] = 0.0; pwj[s] = 0.0; pwp[s] = 0.0; lmr[s] = 0.0; rs[s] = 0.0; }
+        }
+        PF(psnsun) = psn[0]; PF(psnsun_wc) = pwc[0]; PF(psnsun_wj) = pwj[0]; PF(psnsun_wp) = pwp[0]; PF(lmrsun) = lmr[0];
+        PF(psnsha) = psn[1]; PF(psnsha_wc) = pwc[1]; PF(psnsha_wj) = pwj[1]; PF(psnsha_wp) = pwp[1]; PF(lmrsha) = lmr[1];
+        rssun = rs[0]; rssha = rs[1];
+        PF(rssun) = rssun; PF(rssha) = rssha;
+        if (lai[1] + lai[0] > 0.0) btran = bsun * (lai[0] / (lai[0] + lai[1])) + bsha * (lai[1] / (lai[0] + lai[1]));
+        else btran = bsun;
+        PF(btran) = btran; PF(bsun) = bsun; PF(bsha) = bsha;
+        PF(qflx_tran_veg) = qflx_tran_veg;
+      }
+
+      // ---- leaf energy balance :1174-1435 ----
+      const double sa_leaf = WS(W_SA_LEAF), sa_stem = WS(W_SA_STEM), sa_int = WS(W_SA_INT), frs = WS(W_FRS);
+      const double cp_leaf = WS(W_CP_LEAF), rstem = WS(W_RSTEM), tl_ini = WS(W_TL_INI);
+      const double air = WS(W_AIR), bir = WS(W_BIR), cir = WS(W_CIR);
+      const double qsatldT = WS(W_QSATLDT);
+      const double fvn = (double)PF(frac_veg_nosno);
+      const double wta = 1.0 / rah_a;
+      const double wtl = sa_leaf / rb;
+      const double wtg = 1.0 / rah_b;
+      const double wtstem = sa_stem / (rstem + rb);
+      const double wtshi = 1.0 / (wta + wtl + wtstem + wtg);
+      const double wtl0 = wtl * wtshi, wtg0 = wtg * wtshi, wta0 = wta * wtshi, wtstem0 = wtstem * wtshi;
+      const double wtga = wta0 + wtg0 + wtstem0;
+      const double wtal = wta0 + wtl0 + wtstem0;
+      const double lw_stem = sa_int * emv * sb * pow4(t_stem);
+      double lw_leaf = sa_int * emv * sb * pow4(t_veg);
+      const double fdry = PF(fdry), fwet = PF(fwet);
+      double rppdry;
+      if (fdry > 0.0) rppdry = fdry * rb * (laisun / (rb + rssun) + laisha / (rb + rssha)) / elai;
+      else rppdry = 0.0;
+      double efpot = forc_rho * ((elai + esai) / rb) * (qsatl - qaf);
+      const double h2ocan = PF(liqcan) + PF(snocan);
+      double rpp;
+      if (efpot > 0.0) {
+        rpp = (btran > 0.0) ? rppdry + fwet : fwet;
+        rpp = fmin(rpp, (qflx_tran_veg + h2ocan / dtime) / efpot);
+      } else {
+        rpp = 1.0;
+      }
+      const double wtaq = fvn / raw_a;
+      const double wtlq = fvn * (elai + esai) / rb * rpp;
+      const double fsno_dl = CF(snow_depth) / prm.z_dl;
+      const double elai_dl = prm.lai_dl * (1.0 - fmin(fsno_dl, 1.0));
+      const double rdl = (1.0 - exp(-elai_dl)) / (0.004 * uaf);
+      double wtgq = WS(W_WTGQ);
+      if (WS(W_DELQ) < 0.0) {
+        wtgq = fvn / (raw_b + rdl);
+      } else {
+        if (prm.soil_resis_method == 0) wtgq = CF(soilbeta) * fvn / (raw_b + rdl);
+        if (prm.soil_resis_method == 1) wtgq = fvn / (raw_b + CF(soilresis));
+      }
+      const double wtsqi = 1.0 / (wtaq + wtlq + wtgq);
+      const double wtgq0 = wtgq * wtsqi, wtlq0 = wtlq * wtsqi, wtaq0 = wtaq * wtsqi;
+      const double wtgaq = wtaq0 + wtgq0;
+      const double wtalq = wtaq0 + wtlq0;
+      const double dc1 = forc_rho * cpair * wtl;
+      const double dc2 = hvap * forc_rho * wtlq;
+      const double qg = CF(qg);
+      const double efsh = dc1 * (wtga * t_veg - wtg0 * t_grnd - wta0 * thm - wtstem0 * t_stem);
+      double eflx_sh_stem = forc_rho * cpair * wtstem * ((wta0 + wtg0 + wtl0) * t_stem - wtg0 * t_grnd - wta0 * thm - wtl0 * t_veg);
+      double efe = dc2 * (wtgaq * qsatl - wtgq0 * qg - wtaq0 * forc_q);
+      const double efeb = WS(W_EFEB);
+      double erre = 0.0;
+      if (efe * efeb < 0.0) {
+        const double efeold = efe;
+        efe = 0.1 * efeold;
+        erre = efe - efeold;
+      }
+      const int snl = CF(snl);
+      const double frac_sno = CF(frac_sno_eff), frac_h2osfc = CF(frac_h2osfc);
+      const double lw_grnd = (frac_sno * pow4(CF2(t_soisno, snl + 1 - SNOSOI_LO)) + (1.0 - frac_sno - frac_h2osfc) * pow4(CF2(t_soisno, 1 - SNOSOI_LO))
+                              + frac_h2osfc * pow4(CF(t_h2osfc)));
+      const double sabv = PF(sabv);
+      const double tv3 = pow3(t_veg), tv4 = pow4(t_veg);
+      double dt_veg = ((1.0 - frs) * (sabv + air + bir * tv4 + cir * lw_grnd) - efsh - efe - lw_leaf + lw_stem - (cp_leaf / dtime) * (t_veg - tl_ini))
+                      / ((1.0 - frs) * (-4.0 * bir * tv3) + 4.0 * sa_int * emv * sb * tv3 + dc1 * wtga + dc2 * wtgaq * qsatldT + cp_leaf / dtime);
+      t_veg = tlbef + dt_veg;
+      const double dels = dt_veg;
+      const double del = fabs(dels);
+      double err = 0.0;
+      const double tb3 = pow3(tlbef);
+      if (del > 1.0) {
+        dt_veg = 1.0 * dels / del;
+        t_veg = tlbef + dt_veg;
+        err = (1.0 - frs) * (sabv + air + bir * tb3 * (tlbef + 4.0 * dt_veg) + cir * lw_grnd)
+              - sa_int * emv * sb * tb3 * (tlbef + 4.0 * dt_veg) + lw_stem - (efsh + dc1 * wtga * dt_veg)
+              - (efe + dc2 * wtgaq * qsatldT * dt_veg) - (cp_leaf / dtime) * (t_veg - tl_ini);
+      }
+      efpot = forc_rho * ((elai + esai) / rb) * (wtgaq * (qsatl + qsatldT * dt_veg) - wtgq0 * qg - wtaq0 * forc_q);
+      double qflx_evap_veg = rpp * efpot;
+      const double ecidif = fmax(0.0, qflx_evap_veg - qflx_tran_veg - h2ocan / dtime);
+      qflx_evap_veg = fmin(qflx_evap_veg, qflx_tran_veg + h2ocan / dtime);
+      PF(qflx_evap_veg) = qflx_evap_veg;
+      PF(eflx_sh_veg) = efsh + dc1 * wtga * dt_veg + err + erre + hvap * ecidif;
+      eflx_sh_stem = eflx_sh_stem + forc_rho * cpair * wtstem * (-wtl0 * dt_veg);
+      PF(eflx_sh_stem) = eflx_sh_stem;
+      lw_leaf = sa_int * emv * sb * tb3 * (tlbef + 4.0 * dt_veg);
+      const QS q1 = qsat(t_veg, forc_pbot, true);
+      taf = wtg0 * t_grnd + wta0 * thm + wtl0 * t_veg + wtstem0 * t_stem;
+      qaf = wtlq0 * q1.qs + wtgq0 * qg + forc_q * wtaq0;
+      const double dth = thm - taf, dqh = forc_q - qaf;
+      const double delq = wtalq * qg - wtlq0 * q1.qs - wtaq0 * forc_q;
+      const double tstar = temp1 * dth, qstar = temp2 * dqh;
+      const double thv = CF(thv);
+      const double thvstar = tstar * (1.0 + 0.61 * forc_q) + 0.61 * CF(forc_th) * qstar;
+      double zeta = zldis_u * vkc * grav * thvstar / ((ustar * ustar) * thv);
+      if (zeta >= 0.0) {
+        zeta = fmin(prm.zetamaxstable, fmax(zeta, 0.01));
+        um = fmax(ur, 0.1);
+      } else {
+        zeta = fmax(-100.0, fmin(zeta, -0.01));
+        double wc;
+        if (ustar * thvstar > 0.0) { wc = 0.0; atomicAdd(&ds->n_warnings, 1); }
+        else wc = 1.0 * pow(-grav * ustar * thvstar * 1000.0 / thv, 0.333);
+        um = sqrt(ur * ur + wc * wc);
+      }
+      obu = zldis_u / zeta;
+      double nmoz = WS(W_NMOZ);
+      const double obuold = WS(W_OBUOLD);
+      if (obuold * obu < 0.0) nmoz = nmoz + 1.0;
+      if (nmoz >= 4.0) obu = zldis_u / (-0.01);
+      PF(t_veg) = t_veg; PF(taf) = taf; PF(qaf) = qaf; PF(zeta) = zeta; PF(um) = um; PF(obu) = obu;
+      WS(W_NMOZ) = nmoz; WS(W_OBUOLD) = obu;
+      WS(W_QSATL) = q1.qs; WS(W_EL) = q1.es; WS(W_QSATLDT) = q1.qsdT;
+      WS(W_DTH) = dth; WS(W_DQH) = dqh; WS(W_DELQ) = delq; WS(W_TLBEF) = tlbef; WS(W_DT_VEG) = dt_veg; WS(W_DEL) = del;
+      WS(W_WTG) = wtg; WS(W_WTA0) = wta0; WS(W_WTL0) = wtl0; WS(W_WTSTEM0) = wtstem0; WS(W_WTAL) = wtal; WS(W_WTGQ) = wtgq;
+      WS(W_WTAQ0) = wtaq0; WS(W_WTLQ0) = wtlq0; WS(W_WTALQ) = wtalq; WS(W_LW_LEAF) = lw_leaf; WS(W_LW_STEM) = lw_stem;
+      WS(W_EFE) = efe; WS(W_ERR) = err;
+
+      // convergence :1439-1457
+      keep = true;
+      const int it1 = itlef + 1;
+      if (it1 > 2) {
+        const double dele = fabs(efe - efeb);
+        WS(W_EFEB) = efe;
+        const double det = fmax(del, del2);
+        PF(num_iter) = (double)it1;
+        keep = !(det < 0.01 && dele < 0.1);
+      }
+    }
+    // survivors -> next list (warp-aggregated)
+    const unsigned act = __activemask();
+    const unsigned mk = __ballot_sync(act, keep);
+    if (keep) {
+      const unsigned mnight = __ballot_sync(mk, night);
+      const unsigned mine = night ? mnight : (mk & ~mnight);
+      const int lane = threadIdx.x & 31;
+      const int leader = __ffs(mine) - 1;
+      int b0 = 0;
+      if (lane == leader) b0 = atomicAdd(&L.counts[2 * (itlef + 1) + (night ? 0 : 1)], __popc(mine));
+      b0 = __shfl_sync(mine, b0, leader);
+      const int rank = __popc(mine & ((1u << lane) - 1));
+      if (night) list_out[b0 + rank] = fi;
+      else list_out[fn - 1 - (b0 + rank)] = fi;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// after the ITERATION loop (CanopyFluxesMod.F90:1464-1760)
+__global__ void __launch_bounds__(128)
+canopy_final_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int32_t* __restrict__ filterp,
+                    const double* __restrict__ ws, int wstride, DevStatus* ds) {
+  const int fi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fi >= fn) return;
+  const int pp = filterp[fi] - g.begp0;
+  const int cc = PF(column) - g.begc0;
+  const int gg = PF(gridcell) - g.begg0;
+  const double dtime = prm.dtime;
+  const double forc_rho = CF(forc_rho), forc_q = CF(forc_q), t_grnd = CF(t_grnd), thm = PF(thm);
+  const double emv = PF(emv), emg = CF(emg), forc_lwrad = CF(forc_lwrad);
+  const int snl = CF(snl);
+  const double tsn = CF2(t_soisno, snl + 1 - SNOSOI_LO), ts1 = CF2(t_soisno, 1 - SNOSOI_LO), th2o = CF(t_h2osfc);
+  const double frac_sno = CF(frac_sno_eff), frac_h2osfc = CF(frac_h2osfc);
+  const double lw_grnd = (frac_sno * pow4(tsn) + (1.0 - frac_sno - frac_h2osfc) * pow4(ts1) + frac_h2osfc * pow4(th2o));
+  const double frs = WS(W_FRS), tb = WS(W_TLBEF), dt_veg = WS(W_DT_VEG), tsi = WS(W_TS_INI), tl_ini = WS(W_TL_INI);
+  const double air = WS(W_AIR), bir = WS(W_BIR), cir = WS(W_CIR), lw_leaf = WS(W_LW_LEAF), lw_stem = WS(W_LW_STEM);
+  const double cp_leaf = WS(W_CP_LEAF), cp_stem = WS(W_CP_STEM);
+  const double tb3 = pow3(tb), tsi3 = pow3(tsi), tsi4 = pow4(tsi);
+  const double sabv = PF(sabv), tv = PF(t_veg);
+  const double qflx_evap_veg = PF(qflx_evap_veg), qflx_tran_veg = PF(qflx_tran_veg);
+  const double err = (1.0 - frs) * (sabv + air + bir * tb3 * (tb + 4.0 * dt_veg) + cir * lw_grnd) - lw_leaf + lw_stem
+                     - PF(eflx_sh_veg) - hvap * qflx_evap_veg - ((tv - tl_ini) * cp_leaf / dtime);
+  double dt_stem = 0.0;
+  double tstem = PF(t_stem);
+  if (prm.use_biomass_heat_storage) {
+    if (PF(stem_biomass) > 0.0)
+      dt_stem = (frs * (sabv + air + bir * tsi4 + cir * lw_grnd) - PF(eflx_sh_stem) + lw_leaf - lw_stem)
+                / (cp_stem / dtime - frs * bir * 4.0 * tsi3);
+    PF(dhsdt_canopy) = dt_stem * cp_stem / dtime + (tv - tl_ini) * cp_leaf / dtime;
+    tstem = tstem + dt_stem;
+    PF(t_stem) = tstem;
+  }
+  const double wtal = WS(W_WTAL), wtl0 = WS(W_WTL0), wta0 = WS(W_WTA0), wtstem0 = WS(W_WTSTEM0), wtg = WS(W_WTG);
+  const double wtgq = WS(W_WTGQ), wtalq = WS(W_WTALQ), wtlq0 = WS(W_WTLQ0), wtaq0 = WS(W_WTAQ0), qsatl = WS(W_QSATL);
+  const double delt = wtal * t_grnd - wtl0 * tv - wta0 * thm - wtstem0 * tstem;
+  const double ram1 = PF(ram1);
+  PF(taux) = -forc_rho * f.forc_u[gg] / ram1;
+  PF(tauy) = -forc_rho * f.forc_v[gg] / ram1;
+  PF(eflx_sh_grnd) = cpair * forc_rho * wtg * delt;
+  PF(eflx_sh_snow) = cpair * forc_rho * wtg * (wtal * tsn - wtl0 * tv - wta0 * thm - wtstem0 * tstem);
+  PF(eflx_sh_soil) = cpair * forc_rho * wtg * (wtal * ts1 - wtl0 * tv - wta0 * thm - wtstem0 * tstem);
+  PF(eflx_sh_h2osfc) = cpair * forc_rho * wtg * (wtal * th2o - wtl0 * tv - wta0 * thm - wtstem0 * tstem);
+  PF(qflx_evap_soi) = forc_rho * wtgq * WS(W_DELQ);
+  PF(qflx_ev_snow) = forc_rho * wtgq * (wtalq * CF(qg_snow) - wtlq0 * qsatl - wtaq0 * forc_q);
+  PF(qflx_ev_soil) = forc_rho * wtgq * (wtalq * CF(qg_soil) - wtlq0 * qsatl - wtaq0 * forc_q);
+  PF(qflx_ev_h2osfc) = forc_rho * wtgq * (wtalq * CF(qg_h2osfc) - wtlq0 * qsatl - wtaq0 * forc_q);
+  const double temp1 = WS(W_TEMP1), temp2 = WS(W_TEMP2);
+  const double t_ref2m = thm + temp1 * WS(W_DTH) * (1.0 / WS(W_TEMP12M) - 1.0 / temp1);
+  PF(t_ref2m) = t_ref2m; PF(t_ref2m_r) = t_ref2m;
+  const double q_ref2m = forc_q + temp2 * WS(W_DQH) * (1.0 / WS(W_TEMP22M) - 1.0 / temp2);
+  PF(q_ref2m) = q_ref2m;
+  const QS q2 = qsat(t_ref2m, CF(forc_pbot), false);
+  const double rh = fmin(100.0, q_ref2m / q2.qs * 100.0);
+  PF(rh_ref2m) = rh; PF(rh_ref2m_r) = rh;
+  PF(vpd_ref2m) = q2.es * (1.0 - rh / 100.0);
+  PF(dlrad) = (1.0 - emv) * emg * forc_lwrad + emv * emg * sb * tb3 * (tb + 4.0 * dt_veg) * (1.0 - frs)
+              + emv * emg * sb * tsi3 * (tsi + 4.0 * dt_stem) * frs;
+  PF(ulrad) = ((1.0 - emg) * (1.0 - emv) * (1.0 - emv) * forc_lwrad
+               + emv * (1.0 + (1.0 - emg) * (1.0 - emv)) * sb * tb3 * (tb + 4.0 * dt_veg) * (1.0 - frs)
+               + emv * (1.0 + (1.0 - emg) * (1.0 - emv)) * sb * tsi3 * (tsi + 4.0 * dt_stem) * frs
+               + emg * (1.0 - emv) * sb * lw_grnd);
+  PF(t_skin) = emv * tv + (1.0 - emv) * sqrt(sqrt(lw_grnd));
+  const double cgrnds = PF(cgrnds) + cpair * forc_rho * wtg * wtal;
+  const double cgrndl = PF(cgrndl) + forc_rho * wtgq * wtalq * CF(dqgdT);
+  PF(cgrnds) = cgrnds; PF(cgrndl) = cgrndl;
+  PF(cgrnd) = cgrnds + cgrndl * CF(htvp);
+  // dew :1615-1641
+  double snocan = PF(snocan), liqcan = PF(liqcan);
+  const double base = snocan;
+  if (tv > tfrz) {
+    if ((qflx_evap_veg - qflx_tran_veg) * dtime > liqcan) snocan = fmax(0.0, snocan + liqcan + (qflx_tran_veg - qflx_evap_veg) * dtime);
+    liqcan = fmax(0.0, liqcan + (qflx_tran_veg - qflx_evap_veg) * dtime);
+  } else if (tv <= tfrz) {
+    if ((qflx_evap_veg - qflx_tran_veg) * dtime > snocan) liqcan = liqcan + snocan + (qflx_tran_veg - qflx_evap_veg) * dtime;
+    snocan = fmax(0.0, snocan + (qflx_tran_veg - qflx_evap_veg) * dtime);
+  }
+  if (fabs(snocan) < 1.e-10 * fabs(base)) snocan = 0.0;
+  PF(snocan) = snocan; PF(liqcan) = liqcan;
+  // PhotosynthesisTotal :2125-2131, iwue :1661-1676
+  const double laisun = PF(laisun), laisha = PF(laisha);
+  const double fpsn = PF(psnsun) * laisun + PF(psnsha) * laisha;
+  PF(fpsn) = fpsn;
+  PF(fpsn_wc) = PF(psnsun_wc) * laisun + PF(psnsha_wc) * laisha;
+  PF(fpsn_wj) = PF(psnsun_wj) * laisun + PF(psnsha_wj) * laisha;
+  PF(fpsn_wp) = PF(psnsun_wp) * laisun + PF(psnsha_wp) * laisha;
+  double iwue = spval;
+  if (f.near_local_noon[gg] && fpsn > 0.0) {
+    const double gs = 1.e-6 * (laisun * PF2(gs_mol_sun, 0) + laisha * PF2(gs_mol_sha, 0));
+    if (gs > 0.0) iwue = fpsn / gs;
+  }
+  PF(iwue_ln) = iwue;
+  if (fabs(err) > 0.1) atomicAdd(&ds->n_warnings, 1);       // :1746-1760
+}
+
+// ---------------------------------------------------------------------------------------------
+// setExposedvegpFilter (filterMod.F90:595-648): order-preserving two-way split
+#define SPLIT_BLOCK 256
+#define SPLIT_ITEMS 8
+__global__ void __launch_bounds__(SPLIT_BLOCK)
+split_count_kernel(int n, const int32_t* __restrict__ filt, const int32_t* __restrict__ fv, int begp, int* __restrict__ blockc) {
+  __shared__ int sh[SPLIT_BLOCK / 32];
+  const int base = blockIdx.x * SPLIT_BLOCK * SPLIT_ITEMS + threadIdx.x * SPLIT_ITEMS;
+  int c = 0;
+  for (int k = 0; k < SPLIT_ITEMS; ++k) {
+    const int i = base + k;
+    if (i < n && fv[filt[i] - begp] > 0) ++c;
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int k = 0; k < SPLIT_BLOCK / 32; ++k) s += sh[k];
+    blockc[blockIdx.x] = s;
+  }
+}
+__global__ void split_scan_kernel(int nblocks, int* __restrict__ blockc, int* __restrict__ total) {
+  // single block: exclusive scan of the per-block counts (nblocks is small: n / 2048)
+  __shared__ int carry;
+  __shared__ int sh[1024];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = (i < nblocks) ? blockc[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nblocks) blockc[i] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += sh[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(SPLIT_BLOCK)
+split_scatter_kernel(int n, const int32_t* __restrict__ filt, const int32_t* __restrict__ fv, int begp,
+                     const int* __restrict__ blockc, int32_t* __restrict__ out_yes, int32_t* __restrict__ out_no) {
+  __shared__ int sh[SPLIT_BLOCK];
+  const int base = blockIdx.x * SPLIT_BLOCK * SPLIT_ITEMS + threadIdx.x * SPLIT_ITEMS;
+  int c = 0;
+  int32_t v[SPLIT_ITEMS];
+  bool y[SPLIT_ITEMS];
+  for (int k = 0; k < SPLIT_ITEMS; ++k) {
+    const int i = base + k;
+    v[k] = (i < n) ? filt[i] : 0;
+    y[k] = (i < n) && fv[v[k] - begp] > 0;
+    if (y[k]) ++c;
+  }
+  sh[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 1; o < SPLIT_BLOCK; o <<= 1) {
+    const int t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  int yes_pos = blockc[blockIdx.x] + sh[threadIdx.x] - c;           // exposed entries before this thread
+  for (int k = 0; k < SPLIT_ITEMS; ++k) {
+    const int i = base + k;
+    if (i >= n) break;
+    if (y[k]) { out_yes[yes_pos] = v[k]; ++yes_pos; }
+    else out_no[i - yes_pos] = v[k];                                 // entries before i that are not exposed
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+static int reserve_ints(ctsm_b200_ctx::Arena& a, size_t n) { return arena_reserve(a, sizeof(int) * (n > 0 ? n : 1)); }
+
+extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_exposedvegp,
+                                      const int32_t* filter_exposedvegp, const ctsm_canopyfluxes_fields_t* hf, int mem,
+                                      ctsm_status_t* st) {
+  if (!ctx || !bounds || !hf || num_exposedvegp < 0 || (num_exposedvegp > 0 && !filter_exposedvegp)) return CTSM_ERR_BAD_ARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CanopyDev d;
+  const int32_t* dfilter = filter_exposedvegp;
+  std::vector<StageField> fl;
+#define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) \
+  d.name = hf->name;                                        \
+  fl.push_back(StageField{(void**)&d.name, (void*)hf->name, (int)sizeof(ctype), SUB_##sub, lev_shape(#lev).n, INTENT_##intent});
+#define CTSM_FIELDS_CANOPYFLUXES
+#include "../../include/ctsm_b200_fields.def"
+#undef CTSM_FIELDS_CANOPYFLUXES
+#undef CTSM_F
+  for (auto& s : fl) if (!s.host_ptr) return CTSM_ERR_BAD_ARG;
+  if (mem != CTSM_MEM_DEVICE) {
+    int rc = stage_begin(ctx, fl, hf->alloc, *bounds, mem == CTSM_MEM_HOST);
+    if (rc) return rc;
+    rc = stage_filter(ctx, ctx->arena_filter0, filter_exposedvegp, num_exposedvegp, &dfilter);
+    if (rc) return rc;
+  }
+  const ctsm_params_t& p = ctx->prm;
+  CanopyPrm cp;
+  cp.dtime = p.dtime; cp.itmax = p.itmax_canopy_fluxes; cp.use_undercanopy_stability = p.use_undercanopy_stability;
+  cp.use_biomass_heat_storage = p.use_biomass_heat_storage; cp.z0param_method = p.z0param_method;
+  cp.soil_resis_method = p.soil_resis_method; cp.use_luna = p.use_luna; cp.medlyn = (p.stomatalcond_mtd == 2);
+  cp.light_inhibit = p.light_inhibit; cp.modifyphoto_and_lmr_forcrop = p.modifyphoto_and_lmr_forcrop;
+  cp.lai_dl = p.lai_dl; cp.z_dl = p.z_dl; cp.a_coef = p.a_coef; cp.a_exp = p.a_exp; cp.csoilc = p.csoilc; cp.cv = p.cv;
+  cp.wind_min = p.wind_min; cp.zetamaxstable = p.zetamaxstable; cp.leaf_mr_vcm = p.leaf_mr_vcm;
+  cp.act25 = p.act25; cp.fnr = p.fnr; cp.cp25_yr2000 = p.cp25_yr2000; cp.kc25_coef = p.kc25_coef; cp.ko25_coef = p.ko25_coef;
+  cp.fnps = p.fnps; cp.theta_psii = p.theta_psii; cp.theta_ip = p.theta_ip;
+  cp.vcmaxha = p.vcmaxha; cp.jmaxha = p.jmaxha; cp.tpuha = p.tpuha; cp.lmrha = p.lmrha; cp.kcha = p.kcha; cp.koha = p.koha;
+  cp.cpha = p.cpha; cp.vcmaxhd = p.vcmaxhd; cp.jmaxhd = p.jmaxhd; cp.tpuhd = p.tpuhd; cp.lmrhd = p.lmrhd; cp.lmrse = p.lmrse;
+  cp.tpu25ratio = p.tpu25ratio; cp.kp25ratio = p.kp25ratio; cp.vcmaxse_sf = p.vcmaxse_sf; cp.jmaxse_sf = p.jmaxse_sf;
+  cp.tpuse_sf = p.tpuse_sf; cp.jmax25top_sf = p.jmax25top_sf;
+
+  Geo g;
+  g.begp0 = hf->alloc.begp; g.begc0 = hf->alloc.begc; g.begg0 = hf->alloc.begg;
+  g.ldp = hf->alloc.endp - hf->alloc.begp + 1; g.ldc = hf->alloc.endc - hf->alloc.begc + 1;
+  g.begp = bounds->begp; g.endp = bounds->endp; g.begc = bounds->begc; g.endc = bounds->endc;
+  const int fn = num_exposedvegp;
+  const int npb = g.endp - g.begp + 1, ncb = g.endc - g.begc + 1;
+  if (npb <= 0) return finish_call(ctx, mem, st);
+
+  // workspace: [W_NSLOT][wstride] doubles + int scratch {fpos[ldp], colflag[ldc], list_a[fn], list_b[fn], counts}
+  const int wstride = (fn + 31) & ~31;
+  const int npass = p.itmax_canopy_fluxes + 1;
+  const size_t n_counts = 2 * (size_t)(npass + 2);
+  int rc = arena_reserve(ctx->arena_scratch, sizeof(double) * (size_t)W_NSLOT * (size_t)(wstride > 0 ? wstride : 32));
+  if (rc) return rc;
+  rc = reserve_ints(ctx->arena_ints, (size_t)g.ldp + (size_t)g.ldc + 2 * (size_t)fn + n_counts + 64);
+  if (rc) return rc;
+  double* ws = (double*)ctx->arena_scratch.p;
+  int* ip = (int*)ctx->arena_ints.p;
+  int* fpos = ip; ip += g.ldp;
+  Lists L;
+  L.colflag = ip; ip += g.ldc;
+  L.list_a = ip; ip += fn;
+  L.list_b = ip; ip += fn;
+  L.counts = ip;
+  L.n_warn_slot = 0;
+  cudaStream_t s = ctx->stream;
+  CUDA_TRY(cudaMemsetAsync(fpos, 0xff, sizeof(int) * (size_t)g.ldp, s));
+  CUDA_TRY(cudaMemsetAsync(L.colflag, 0, sizeof(int) * (size_t)g.ldc, s));
+  CUDA_TRY(cudaMemsetAsync(L.counts, 0, sizeof(int) * n_counts, s));
+  if (fn > 0) {
+    canopy_mark_kernel<<<grid_for(fn, 256), 256, 0, s>>>(d, g, fn, dfilter, L.colflag, fpos);
+    canopy_colprep_kernel<<<grid_for(ncb, 128), 128, 0, s>>>(d, g, L.colflag);
+    ctx->launches += 2;
+  }
+  canopy_init_kernel<<<grid_for(npb, 128), 128, 0, s>>>(d, cp, g, fn, fpos, ws, wstride, L, ctx->d_status);
+  ctx->launches++;
+  if (fn > 0) {
+    const size_t shbytes = sizeof(double) * 3 * NLEVSOI * ITER_THREADS;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int gridmax = sms * 8;
+    int grid = grid_for(fn, ITER_THREADS);
+    if (grid > gridmax) grid = gridmax;
+    int *lin = L.list_a, *lout = L.list_b;
+    for (int itlef = 0; itlef < npass; ++itlef) {
+      canopy_iter_kernel<<<grid, ITER_THREADS, shbytes, s>>>(d, cp, g, fn, itlef, dfilter, ws, wstride, L, lin, lout,
+                                                             ctx->d_status);
+      ctx->launches++;
+      int* t = lin; lin = lout; lout = t;
+    }
+    canopy_final_kernel<<<grid_for(fn, 128), 128, 0, s>>>(d, cp, g, fn, dfilter, ws, wstride, ctx->d_status);
+    ctx->launches++;
+  }
+  if (mem != CTSM_MEM_DEVICE) {
+    rc = stage_end(ctx, fl, hf->alloc, *bounds);
+    if (rc) return rc;
+  }
+  return finish_call(ctx, mem, st);
+}
+
+extern "C" int ctsm_b200_set_exposedvegp_filter(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_nolakeurbanp,
+                                                const int32_t* filter_nolakeurbanp, const int32_t* frac_veg_nosno,
+                                                int32_t* filter_exposedvegp, int32_t* num_exposedvegp,
+                                                int32_t* filter_noexposedvegp, int32_t* num_noexposedvegp, int mem) {
+  if (!ctx || !bounds || num_nolakeurbanp < 0 || !frac_veg_nosno || !num_exposedvegp || !num_noexposedvegp ||
+      (num_nolakeurbanp > 0 && (!filter_nolakeurbanp || !filter_exposedvegp || !filter_noexposedvegp)))
+    return CTSM_ERR_BAD_ARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const int n = num_nolakeurbanp;
+  *num_exposedvegp = 0; *num_noexposedvegp = 0;
+  if (n == 0) return CTSM_OK;
+  cudaStream_t s = ctx->stream;
+  const int np = bounds->endp - bounds->begp + 1;
+  const int nblocks = grid_for(n, SPLIT_BLOCK * SPLIT_ITEMS);
+  const int32_t *dfilt = filter_nolakeurbanp, *dfv = frac_veg_nosno;
+  int32_t *dyes = filter_exposedvegp, *dno = filter_noexposedvegp;
+  int rc = reserve_ints(ctx->arena_ints, (size_t)nblocks + 8 + (mem != CTSM_MEM_DEVICE ? 3 * (size_t)n + (size_t)np : 0));
+  if (rc) return rc;
+  int* ip = (int*)ctx->arena_ints.p;
+  int* blockc = ip; ip += nblocks;
+  int* total = ip; ip += 8;
+  if (mem != CTSM_MEM_DEVICE) {
+    int32_t* a = ip; ip += n;
+    int32_t* b = ip; ip += n;
+    int32_t* c = ip; ip += n;
+    int32_t* e = ip; ip += np;
+    CUDA_TRY(cudaMemcpyAsync(a, filter_nolakeurbanp, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(e, frac_veg_nosno, sizeof(int32_t) * (size_t)np, cudaMemcpyHostToDevice, s));
+    dfilt = a; dyes = b; dno = c; dfv = e;
+  }
+  split_count_kernel<<<nblocks, SPLIT_BLOCK, 0, s>>>(n, dfilt, dfv, bounds->begp, blockc);
+  split_scan_kernel<<<1, 1024, 0, s>>>(nblocks, blockc, total);
+  split_scatter_kernel<<<nblocks, SPLIT_BLOCK, 0, s>>>(n, dfilt, dfv, bounds->begp, blockc, dyes, dno);
+  ctx->launches += 3;
+  int htotal = 0;
+  CUDA_TRY(cudaMemcpyAsync(&htotal, total, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  *num_exposedvegp = htotal;
+  *num_noexposedvegp = n - htotal;
+  if (mem != CTSM_MEM_DEVICE) {
+    if (htotal > 0) CUDA_TRY(cudaMemcpyAsync(filter_exposedvegp, dyes, sizeof(int32_t) * (size_t)htotal, cudaMemcpyDeviceToHost, s));
+    if (n - htotal > 0) CUDA_TRY(cudaMemcpyAsync(filter_noexposedvegp, dno, sizeof(int32_t) * (size_t)(n - htotal), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+  }
+  return CTSM_OK;
+}

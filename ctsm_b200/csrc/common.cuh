@@ -64,7 +64,7 @@ struct ctsm_b200_ctx {
   int64_t launches;
   // staging mirrors for CTSM_MEM_HOST calls: one grow-only device arena per purpose
   struct Arena { void* p = nullptr; size_t cap = 0; };
-  Arena arena_fields, arena_filter0, arena_filter1, arena_scratch;
+  Arena arena_fields, arena_filter0, arena_filter1, arena_scratch, arena_ints;
   int32_t* d_patchmask = nullptr; size_t patchmask_cap = 0;
 };
 
@@ -79,7 +79,7 @@ struct ctsm_b200_ctx {
   } while (0)
 
 // --- staging of field tables (abi.cu) -----------------------------------------
-enum SubLevel { SUB_GRC = 0, SUB_LUN = 1, SUB_COL = 2, SUB_PATCH = 3 };
+enum SubLevel { SUB_GRC = 0, SUB_LUN = 1, SUB_COL = 2, SUB_PATCH = 3, SUB_PFT = 4 };
 enum Intent { INTENT_IN = 1, INTENT_OUT = 2, INTENT_INOUT = 3 };
 struct LevShape { int lo; int n; };
 __host__ inline LevShape lev_shape(const char* lev) {
@@ -91,6 +91,8 @@ __host__ inline LevShape lev_shape(const char* lev) {
   if (!strcmp(lev, "SNO")) return {-NLEVSNO + 1, NLEVSNO};
   if (!strcmp(lev, "SNO1")) return {-NLEVSNO + 1, NLEVSNO + 1};
   if (!strcmp(lev, "VEGWCS")) return {1, CTSM_NVEGWCS};
+  if (!strcmp(lev, "CAN")) return {1, CTSM_NLEVCAN};
+  if (!strcmp(lev, "PHS2")) return {1, 2 * CTSM_NLEVCAN};
   return {1, 1};
 }
 
@@ -112,9 +114,11 @@ int finish_call(ctsm_b200_ctx* ctx, int mem, ctsm_status_t* st);
 void decode_status(const DevStatus& ds, ctsm_status_t* st);
 
 static inline int sub_beg(const ctsm_bounds_t& b, int sub) {
+  if (sub == SUB_PFT) return 0;
   return sub == SUB_GRC ? b.begg : sub == SUB_LUN ? b.begl : sub == SUB_COL ? b.begc : b.begp;
 }
 static inline int sub_end(const ctsm_bounds_t& b, int sub) {
+  if (sub == SUB_PFT) return CTSM_MXPFT;
   return sub == SUB_GRC ? b.endg : sub == SUB_LUN ? b.endl : sub == SUB_COL ? b.endc : b.endp;
 }
 

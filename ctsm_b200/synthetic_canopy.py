@@ -1,0 +1,208 @@
+"""Synthetic CanopyFluxes + PHS inputs on the subgrid and
+soil/snow state built by ctsm_b200.synthetic.
+
+Parameter values marked "external" in SURVEY.md Appendix D are synthetic choices, not CTSM
+parameter-file values (the production parameter file is not part of the reference checkout).
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import numpy as np
+
+from . import abi
+from .abi import NLEVSNO, NLEVGRND, NLEVSOI, ISTDLAK
+from .synthetic import (Subgrid, vertical_grid, build_subgrid, soil_state, GRID_SIZES, TFRZ, DENH2O)
+
+N_PFT_TABLE = abi.MXPFT + 1
+
+
+def _qsat_np(T, p):
+    """Vectorised QSat (QSatMod.F90:61-127); used only to build physically consistent synthetic forcing."""
+    a = [6.11213476, 0.444007856, 0.143064234e-01, 0.264461437e-03, 0.305903558e-05, 0.196237241e-07,
+         0.892344772e-10, -0.373208410e-12, 0.209339997e-15]
+    c = [6.11123516, 0.503109514, 0.188369801e-01, 0.420547422e-03, 0.614396778e-05, 0.602780717e-07,
+         0.387940929e-09, 0.149436277e-11, 0.262655803e-14]
+    td = np.clip(T - TFRZ, -75.0, 100.0)
+    ew = np.polyval(a[::-1], td)
+    ei = np.polyval(c[::-1], td)
+    es = np.where(td >= 0, ew, ei) * 100.0
+    return 0.622 * es / (p - 0.378 * es), es
+
+
+def pft_tables() -> Dict[str, np.ndarray]:
+    """Per-PFT parameter tables (index 0:mxpft).  psi50/ck follow PhotosynthesisMod.F90:929-934
+    (setParamsForTesting), root_radius/root_density the code comments at :2948-2949, dleaf the tech note;
+    everything else is a SYNTHETIC, physically plausible choice."""
+    n = N_PFT_TABLE
+    T = {}
+    tree = np.zeros(n, dtype=np.int32); tree[1:9] = 1
+    shrub = np.zeros(n, dtype=np.int32); shrub[9:12] = 1
+    c3 = np.ones(n); c3[14] = 0.0
+    T["pft_is_tree"], T["pft_is_shrub"], T["pft_c3psn"] = tree, shrub, c3
+    T["pft_crop"] = np.zeros(n)
+
+    def per(vals, default):
+        a = np.full(n, float(default))
+        a[:len(vals)] = vals
+        return a
+    T["pft_slatop"] = per([0.01, 0.010, 0.008, 0.024, 0.012, 0.012, 0.030, 0.030, 0.030, 0.012, 0.030, 0.030,
+                           0.030, 0.030, 0.030], 0.03)
+    T["pft_leafcn"] = per([25, 58, 58, 26, 30, 30, 23, 23, 23, 36, 23, 23, 28, 28, 35], 25)
+    T["pft_flnr"] = per([0.1, 0.051, 0.047, 0.055, 0.076, 0.076, 0.106, 0.106, 0.106, 0.033, 0.106, 0.106,
+                         0.137, 0.137, 0.090], 0.1)
+    T["pft_fnitr"] = per([1.0, 0.72, 0.78, 0.79, 0.83, 0.71, 0.66, 0.64, 0.70, 0.62, 0.60, 0.76, 0.68, 0.61, 0.64], 0.7)
+    T["pft_dleaf"] = np.full(n, 0.04)
+    T["pft_dbh"] = per([0.0, 0.30, 0.25, 0.25, 0.45, 0.35, 0.40, 0.30, 0.20, 0.04, 0.06, 0.03, 0.0, 0.0, 0.0], 0.0)
+    T["pft_fbw"] = np.full(n, 0.5)
+    T["pft_nstem"] = per([0.0, 0.08, 0.10, 0.10, 0.05, 0.06, 0.05, 0.08, 0.10, 0.5, 0.5, 0.5, 0.0, 0.0, 0.0], 0.0)
+    T["pft_rstem_per_dbh"] = np.full(n, 100.0)
+    T["pft_wood_density"] = per([0.0, 450, 450, 500, 600, 600, 600, 550, 500, 500, 500, 500, 0, 0, 0], 0.0)
+    T["pft_z0v_Cr"] = np.full(n, 0.35)
+    T["pft_z0v_Cs"] = np.full(n, 0.01)
+    T["pft_z0v_c"] = np.full(n, 0.09)
+    T["pft_z0v_cw"] = per([4.0] * 12 + [8.0, 8.0, 8.0], 4.0)
+    T["pft_z0v_LAImax"] = np.full(n, 6.0)
+    T["pft_smpso"] = per([-66000.0] * 12 + [-74000.0] * 3, -74000.0)
+    T["pft_smpsc"] = per([-255000.0] * 12 + [-275000.0] * 3, -275000.0)
+    T["pft_froot_leaf"] = per([0.0, 1.5, 1.5, 1.5, 1.0, 1.0, 1.0, 1.2, 1.2, 1.5, 1.5, 1.5, 2.0, 2.0, 2.0], 1.0)
+    T["pft_root_radius"] = np.full(n, 0.29e-3)
+    T["pft_root_density"] = np.full(n, 0.31e6)
+    T["pft_mbbopt"] = np.where(c3 > 0.5, 9.0, 4.0)
+    T["pft_medlynintercept"] = np.full(n, 100.0)
+    T["pft_medlynslope"] = per([2.0, 2.35, 2.35, 2.35, 4.12, 4.12, 4.45, 4.45, 4.45, 4.70, 4.70, 4.70,
+                                2.22, 5.25, 1.62], 4.0)
+    T["pft_krmax"] = per([1e-9, 2e-9, 2e-9, 2e-9, 4e-9, 3e-9, 4e-9, 3e-9, 2e-9, 2e-9, 2e-9, 2e-9, 3e-9, 3e-9, 3e-9], 2e-9)
+    T["pft_theta_cj"] = np.where(c3 > 0.5, 0.9393, 0.80)
+    T["pft_kmax"] = np.full((4, n), 2.0e-8)
+    psi = np.full(n, -340000.0); psi[1] = -150000.0; psi[2] = -530000.0; psi[3:13] = -400000.0; psi[0] = -150000.0
+    T["pft_psi50"] = np.repeat(psi[None, :], 4, axis=0).copy()
+    T["pft_ck"] = np.full((4, n), 3.95)
+    return T
+
+
+def canopy_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator, day_fraction: float = 0.5) -> None:
+    """Adds the fields of group `canopyfluxes` (ctsm_b200_fields.def) to S, consistent with the soil/snow state
+    already in S, and the exposedvegp / noexposedvegp filters to sg.filters."""
+    nc, npch, ng = sg.ncol, sg.npatch, sg.ngrc
+    g = lambda a, b, *sh: rng.uniform(a, b, size=sh)
+    lo = -NLEVSNO + 1
+    dzsoi, zisoi, zsoi = vertical_grid()
+    S.update(pft_tables())
+    # --- gridcell
+    S["dayl"] = g(30000.0, 50000.0, ng)
+    S["max_dayl"] = np.maximum(S["dayl"], g(45000.0, 55000.0, ng))
+    spd, ang = g(0.5, 12.0, ng), g(0.0, 2 * np.pi, ng)
+    S["forc_u"], S["forc_v"] = spd * np.cos(ang), spd * np.sin(ang)
+    S["forc_pco2"] = np.full(ng, 40.0) * g(0.95, 1.05, ng)
+    S["forc_po2"] = np.full(ng, 0.209 * 1.0e5)
+    for nm in ("forc_hgt_t", "forc_hgt_u", "forc_hgt_q"):
+        S[nm] = np.full(ng, 30.0)
+    S["near_local_noon"] = (rng.random(ng) < 1.0 / 12.0).astype(np.int32)
+    S["local_time_lt_noon"] = (rng.random(ng) < 0.5).astype(np.int32)
+    is_day_g = rng.random(ng) < day_fraction
+    # --- column
+    t1 = S["t_soisno"][1 - lo]
+    tg = S["t_grnd"]
+    forc_t = np.clip(tg + rng.normal(0.0, 3.0, nc), 235.0, 318.0)
+    pbot = g(85000.0, 101325.0, nc)
+    S["forc_pbot"] = pbot
+    S["forc_th"] = forc_t * (100000.0 / pbot) ** 0.286
+    S["forc_rho"] = pbot / (287.04 * forc_t)
+    qs_a, _ = _qsat_np(forc_t, pbot)
+    S["forc_q"] = g(0.2, 0.95, nc) * qs_a
+    S["thv"] = S["forc_th"] * (1.0 + 0.61 * S["forc_q"])
+    # forc_lwrad, emg, htvp, t_h2osfc, t_grnd, frac_*, snow_depth, snl are already in S (soil_state)
+    S["soilresis"] = 10.0 ** g(1.0, 3.3, nc)
+    S["soilbeta"] = g(0.1, 1.0, nc)
+    S["z0mg"] = np.where(S["frac_sno_eff"] > 0, 0.0024, 0.01)
+    topsn = np.take_along_axis(S["t_soisno"], (S["snl"] + 1 - lo)[None, :], axis=0)[0]
+    qgs, _ = _qsat_np(topsn, pbot); qgsoil, _ = _qsat_np(t1, pbot); qgh, _ = _qsat_np(S["t_h2osfc"], pbot)
+    hr = g(0.5, 1.0, nc)
+    S["qg_snow"], S["qg_soil"], S["qg_h2osfc"] = qgs, hr * qgsoil, qgh
+    fs, fh = S["frac_sno_eff"], S["frac_h2osfc"]
+    S["qg"] = fs * S["qg_snow"] + (1 - fs - fh) * S["qg_soil"] + fh * S["qg_h2osfc"]
+    qg1, _ = _qsat_np(tg + 0.5, pbot); qg0, _ = _qsat_np(tg - 0.5, pbot)
+    S["dqgdT"] = hr * (qg1 - qg0)
+    # soil hydraulic state as SoilWater left it (CH78): s = liq/(dz*1000*watsat)
+    soil = slice(NLEVSNO, NLEVSNO + NLEVGRND)
+    s_l = np.clip(S["h2osoi_liq"][soil] / (S["dz"][soil] * DENH2O * S["watsat"]), 0.01, 1.0)
+    S["smp_l"] = np.maximum(-S["sucsat"] * s_l ** (-S["bsw"]), -1.0e8)
+    S["hk_l"] = S["hksat"] * s_l ** (2.0 * S["bsw"] + 3.0)
+    S["h2osoi_liqvol"] = np.full((NLEVSNO + NLEVGRND, nc), 1.0e36)
+    # --- patch
+    pc = sg.patch_column - 1
+    pg = sg.patch_gridcell - 1
+    ivt = sg.patch_itype
+    S["gridcell"] = sg.patch_gridcell.copy()
+    S["itype"] = ivt.copy()
+    S["patch_lakpoi"] = (sg.col_lun_itype[pc] == ISTDLAK).astype(np.int32)
+    S["nrad"] = np.ones(npch, dtype=np.int32)
+    is_day = is_day_g[pg]
+    elai = g(0.1, 6.0, npch); esai = g(0.1, 1.0, npch)
+    S["elai"], S["esai"] = elai, esai
+    S["tlai"], S["tsai"] = elai * g(1.0, 1.2, npch), esai * g(1.0, 1.2, npch)
+    tree, shrub = S["pft_is_tree"][ivt] > 0, S["pft_is_shrub"][ivt] > 0
+    S["htop"] = np.where(tree, g(5.0, 35.0, npch), np.where(shrub, g(0.3, 2.0, npch), g(0.1, 1.0, npch)))
+    fsun = (1.0 - np.exp(-0.5 * elai)) / (0.5 * elai)
+    tiny_sun = rng.random(npch) < 0.02          # exercises the laisun ~ 0 (3x3) branch of calcstress
+    laisun = np.where(is_day, np.where(tiny_sun, 5.0e-4, fsun * elai), 0.0)
+    S["laisun"], S["laisha"] = laisun, elai - laisun
+    S["laisun_z"], S["laisha_z"] = S["laisun"][None, :].copy(), S["laisha"][None, :].copy()
+    S["tlai_z"] = S["tlai"][None, :].copy()
+    S["parsun_z"] = np.where(is_day, g(20.0, 300.0, npch), 0.0)[None, :]
+    S["parsha_z"] = np.where(is_day, g(5.0, 60.0, npch), 0.0)[None, :]
+    S["sabv"] = np.where(is_day, g(20.0, 400.0, npch), 0.0)
+    S["emv"] = 1.0 - np.exp(-(elai + esai))
+    fwet = np.where(rng.random(npch) < 0.5, g(0.0, 0.3, npch), 0.0)
+    S["fwet"], S["fdry"] = fwet, (1.0 - fwet) * elai / (elai + esai)
+    ft_p = forc_t[pc]
+    S["t_veg"] = ft_p + rng.normal(0.0, 2.0, npch)
+    S["t_stem"] = ft_p + rng.normal(0.0, 2.0, npch)
+    S["t_a10"] = ft_p + rng.normal(0.0, 3.0, npch)
+    S["vcmaxcintsun"] = np.where(is_day, g(0.3, 2.0, npch), 0.0)
+    S["vcmaxcintsha"] = g(0.3, 3.0, npch)
+    for nm in ("o3coefvsun", "o3coefgsun", "o3coefvsha", "o3coefgsha"):
+        S[nm] = np.ones(npch)
+    S["froot_carbon"] = g(50.0, 300.0, npch)
+    S["vcmx25_z"] = g(20.0, 80.0, npch)[None, :]
+    S["jmx25_z"] = S["vcmx25_z"] * g(1.6, 2.0, npch)[None, :]
+    beta_r = g(0.5, 2.5, npch)
+    rf = np.exp(-zsoi[1:NLEVGRND + 1][:, None] / beta_r[None, :])
+    rf[NLEVSOI:] = 0.0
+    S["rootfr"] = rf / rf.sum(0, keepdims=True)
+    S["displa"] = 0.67 * S["htop"]
+    S["z0mv"] = 0.1 * S["htop"]
+    S["thm"] = ft_p + 0.0098 * (30.0 + S["z0mv"] + S["displa"])
+    S["snocan"] = np.where(rng.random(npch) < 0.2, g(0.0, 2.0, npch), 0.0)
+    S["liqcan"] = np.where(rng.random(npch) < 0.3, g(0.0, 0.5, npch), 0.0)
+    S["cgrnds"], S["cgrndl"] = np.zeros(npch), np.zeros(npch)
+    S["qflx_tran_veg"] = g(0.0, 5.0e-5, npch)
+    wroot = -g(2.0e4, 1.0e5, npch)
+    wxyl = wroot - g(0.0, 2.0e4, npch) - 1000.0 * S["htop"]
+    S["vegwp"] = np.stack([wxyl - g(0.0, 2.0e4, npch), wxyl - g(0.0, 2.0e4, npch), wxyl, wroot])
+    # --- outputs: recognisable fill so untouched elements are visible
+    fill = 1.0e36
+    for fs_ in abi.FIELDS["canopyfluxes"]:
+        if fs_.name in S:
+            continue
+        n = sg.bounds.extent(fs_.sub)
+        shape = (n,) if fs_.lev == "L1" else (fs_.nlev, n)
+        S[fs_.name] = np.full(shape, fill) if fs_.ctype == "double" else np.full(shape, -9999, dtype=np.int32)
+    for k, v in list(S.items()):
+        S[k] = np.ascontiguousarray(v)
+    # filters (filterMod.F90:595-648)
+    nlu = sg.filters["nolakeurbanp"]
+    ex = S["frac_veg_nosno"][nlu - 1] > 0
+    sg.filters["exposedvegp"] = np.ascontiguousarray(nlu[ex])
+    sg.filters["noexposedvegp"] = np.ascontiguousarray(nlu[~ex])
+
+
+def make_full_case(size="tiny", seed: int = 20260101, special_every: int = 10, day_fraction: float = 0.5):
+    """Soil/snow state + canopy state on one subgrid (configs 3 and 4)."""
+    ngrc = GRID_SIZES[size] if isinstance(size, str) else int(size)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    sg = build_subgrid(ngrc, rng, special_every)
+    S = soil_state(sg, rng)
+    canopy_state(sg, S, rng, day_fraction)
+    return sg, S

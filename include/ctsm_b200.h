@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CTSM_B200_ABI_VERSION 1
+#define CTSM_B200_ABI_VERSION 2
 
 /* fixed vertical structure the kernels are compiled for (clm_varpar.F90:43-54,
  * 290-292; namelist_defaults_ctsm.xml:254,511).  ctsm_b200_init refuses any
@@ -114,7 +114,28 @@ typedef struct ctsm_params_t {
   /* SoilTemperatureMod.F90:753-775 */
   int32_t snow_thermal_cond_method;      /* 1 = Jordan1991, 2 = Sturm1997 */
   int32_t snow_thermal_cond_glc_method;  /* 1 = Jordan1991, 2 = Sturm1997 */
-  int32_t reserved_i[8];
+  /* canopyfluxes_inparm + CanopyFluxesMod params_inst (CanopyFluxesMod.F90:61-70,115-117,174-186) */
+  int32_t itmax_canopy_fluxes;          /* 40 */
+  int32_t use_undercanopy_stability;    /* 0 */
+  int32_t use_biomass_heat_storage;     /* 1 (clm6_0) */
+  int32_t z0param_method;               /* 1 = ZengWang2007, 2 = Meier2022 (clm6_0) */
+  int32_t soil_resis_method;            /* 0 = Lee-Pielke beta (do_soilevap_beta), 1 = SL14 (do_soil_resistance_sl14) */
+  int32_t use_hydrstress;               /* 1 (only supported value) */
+  int32_t use_luna;                     /* 1: vcmx25_z/jmx25_z inputs drive C3 non-crop vcmax (PhotosynthesisMod.F90:3353,3395) */
+  int32_t stomatalcond_mtd;             /* 1 = Ball-Berry1987, 2 = Medlyn2011 */
+  int32_t light_inhibit;                /* 1 */
+  int32_t modifyphoto_and_lmr_forcrop;  /* 1 */
+  double  lai_dl, z_dl, a_coef, a_exp, csoilc, cv, wind_min;
+  double  zetamaxstable;                /* frictionvel_inst%zetamaxstable: 0.5 or 2.0 */
+  double  leaf_mr_vcm;                  /* canopystate_inst%leaf_mr_vcm = 0.015 */
+  /* photo_params_type scalars, PhotosynthesisMod.F90:93-118 */
+  double  act25, fnr, cp25_yr2000, kc25_coef, ko25_coef, fnps, theta_psii, theta_ip;
+  double  vcmaxha, jmaxha, tpuha, lmrha, kcha, koha, cpha;
+  double  vcmaxhd, jmaxhd, tpuhd, lmrhd, lmrse;
+  double  tpu25ratio, kp25ratio, vcmaxse_sf, jmaxse_sf, tpuse_sf, jmax25top_sf;
+  /* BalanceCheckMod.F90:74-95 */
+  int32_t balance_skip_steps;           /* set by ctsm_b200_balancecheck_init */
+  int32_t reserved_i[7];
   double  reserved_d[8];
 } ctsm_params_t;
 
@@ -135,6 +156,13 @@ typedef struct ctsm_soiltemperature_fields_t {
 #include "ctsm_b200_fields.def"
 #undef CTSM_FIELDS_SOILTEMPERATURE
 } ctsm_soiltemperature_fields_t;
+
+typedef struct ctsm_canopyfluxes_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_CANOPYFLUXES
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_CANOPYFLUXES
+} ctsm_canopyfluxes_fields_t;
 #undef CTSM_F
 
 /* ---- lifecycle ------------------------------------------------------------ */
@@ -197,6 +225,26 @@ int ctsm_b200_soiltemperature(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
                               int num_nolakep, const int32_t* filter_nolakep,
                               int num_nolakec, const int32_t* filter_nolakec,
                               const ctsm_soiltemperature_fields_t* f, int mem, ctsm_status_t* st);
+
+/* CanopyFluxes(bounds, num_exposedvegp, filter_exposedvegp, ...): CanopyFluxesMod.F90:191-198
+ * with use_hydrstress=.true. (PhotosynthesisHydraulicStress, PhotosynthesisMod.F90:2704).
+ * Failures reported like the reference's endrun sites: CTSM_ERR_FORC_HGT (:997-1002),
+ * CTSM_ERR_GS_NEG, CTSM_ERR_BRENT, CTSM_ERR_QUADRATIC.  st->n_warnings counts patches
+ * whose canopy energy balance error exceeds 0.1 W/m2 (:1746-1760) plus ustar*thvstar>0
+ * occurrences (:1408-1423). */
+int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
+                           int num_exposedvegp, const int32_t* filter_exposedvegp,
+                           const ctsm_canopyfluxes_fields_t* f, int mem, ctsm_status_t* st);
+
+/* setExposedvegpFilter(bounds, frac_veg_nosno): filterMod.F90:595-648.  Order-preserving
+ * split of filter_nolakeurbanp into exposedvegp (frac_veg_nosno > 0) / noexposedvegp.
+ * Output lists must hold num_nolakeurbanp entries; counts are returned through the
+ * pointers (host memory in every mode; DEVICE mode synchronises to return them). */
+int ctsm_b200_set_exposedvegp_filter(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
+                                     int num_nolakeurbanp, const int32_t* filter_nolakeurbanp,
+                                     const int32_t* frac_veg_nosno /* (begp:endp) */,
+                                     int32_t* filter_exposedvegp, int32_t* num_exposedvegp,
+                                     int32_t* filter_noexposedvegp, int32_t* num_noexposedvegp, int mem);
 
 #ifdef __cplusplus
 }

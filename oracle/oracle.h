@@ -52,6 +52,21 @@ int oracle_soiltemperature(const ctsm_params_t* prm, const ctsm_bounds_t* bounds
                            const int32_t* filter_nolakep, int num_nolakec, const int32_t* filter_nolakec,
                            const ctsm_soiltemperature_fields_t* f, ctsm_status_t* st);
 
+/* CanopyFluxesMod.F90:191 (use_hydrstress) */
+int oracle_canopyfluxes(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_exposedvegp,
+                        const int32_t* filter_exposedvegp, const ctsm_canopyfluxes_fields_t* f, ctsm_status_t* st);
+/* filterMod.F90:595-648 */
+void oracle_set_exposedvegp_filter(const ctsm_bounds_t* bounds, int num_nolakeurbanp, const int32_t* nolakeurbanp,
+                                   const int32_t* frac_veg_nosno, int32_t* exposedvegp, int32_t* num_exposedvegp,
+                                   int32_t* noexposedvegp, int32_t* num_noexposedvegp);
+/* scalar pieces pinned by the reference's own unit tests (tests/test_oracle_golden.py) */
+void oracle_qsat(double T, double p, double* qs, double* es, double* qsdT);
+void oracle_moninobukini(double zetamaxstable, double ur, double thv, double dthv, double zldis, double z0m, double* um,
+                         double* obu);
+int oracle_quadratic(double a, double b, double c, double* r1, double* r2);
+double oracle_plc(double x, double psi50, double ck);
+double oracle_d1plc(double x, double psi50, double ck);
+
 /* one clump = what one OpenMP thread of clm_drv's clump loop owns (clm_driver.F90:525-527) */
 typedef struct oracle_clump_t {
   ctsm_bounds_t bounds;

@@ -84,6 +84,18 @@ def lib():
     L.oracle_soilwater.argtypes = [P, B, C.c_int, i32p, C.POINTER(abi.STRUCTS["soilwater"]), S]
     L.oracle_soiltemperature.argtypes = [P, B, C.c_int, i32p, C.c_int, i32p,
                                          C.POINTER(abi.STRUCTS["soiltemperature"]), S]
+    L.oracle_canopyfluxes.argtypes = [P, B, C.c_int, i32p, C.POINTER(abi.STRUCTS["canopyfluxes"]), S]
+    L.oracle_set_exposedvegp_filter.argtypes = [B, C.c_int, i32p, i32p, i32p, i32p, i32p, i32p]
+    L.oracle_set_exposedvegp_filter.restype = None
+    L.oracle_qsat.argtypes = [C.c_double, C.c_double, f64p, f64p, f64p]
+    L.oracle_qsat.restype = None
+    L.oracle_moninobukini.argtypes = [C.c_double] * 6 + [f64p, f64p]
+    L.oracle_moninobukini.restype = None
+    L.oracle_quadratic.argtypes = [C.c_double] * 3 + [f64p, f64p]
+    L.oracle_plc.argtypes = [C.c_double] * 3
+    L.oracle_plc.restype = C.c_double
+    L.oracle_d1plc.argtypes = [C.c_double] * 3
+    L.oracle_d1plc.restype = C.c_double
     L.oracle_num_threads.restype = C.c_int
     L.oracle_step_clumps.argtypes = [P, C.c_int, C.POINTER(Clump), C.POINTER(abi.STRUCTS["soiltemperature"]),
                                      C.POINTER(abi.STRUCTS["soilwater"]), C.c_int]
