@@ -1,16 +1,17 @@
 #!/usr/bin/env python
-"""bench.py — column-timesteps/s of the biogeophysics hot path on B200.
+"""bench.py — column-timesteps/s of the CTSM biogeophysics hot path on B200.
 
     python bench.py --gpus N --steps K --warmup W [--size f02] [--impl reference]
 
-One "step" = one pass of the hot-path routines (clm_drv call order) over the
-rank's synthetic grid.  `value` is whole-job throughput with all state resident
-in HBM; `e2e` is the same step driven through the C ABI with HOST buffers
-(pinned), host<->device copies inside the timed region.  `roofline` is for the
-dominant kernel, `cpu_baseline` is the CPU oracle (C restatement of the
-reference, OpenMP over clumps) on a bounded sample of the same workload.
-Under torchrun each rank owns an equal, independent share (weak scaling); the
-path has no exchange step, so the only collectives are the timing reductions.
+One "step" = one pass of the hot path in clm_drv call order (clm_driver.F90:766,900,950),
+CanopyFluxes (+PHS) -> SoilTemperature -> SoilWater, over the rank's synthetic grid (BASELINE.json
+config 4 on one GPU; `--size f09 --routines soiltemperature,soilwater` is config 2, `--routines
+canopyfluxes` config 3).  `value` is whole-job throughput with all state resident in HBM; `e2e` is
+the same step driven through the C ABI with pinned HOST buffers, host<->device copies inside the
+timed region.  `roofline` describes the dominant routine's kernels, `cpu_baseline` the CPU oracle
+(C restatement of the reference, OpenMP over clumps) on a bounded sample of the same workload.
+Under torchrun each rank owns an equal, independent grid (weak scaling); the path has no exchange
+step, so the only collectives are the timing reductions.
 """
 import argparse
 import ctypes as C
@@ -28,6 +29,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "column_timesteps_per_sec"
 UNIT = "column-steps/s"
+KERNEL_OF = {"canopyfluxes": "canopy_iter_kernel (all passes of one step)", "soiltemperature": "soiltemp_kernel",
+             "soilwater": "soilwater_kernel"}
+NAME_OF = {"canopyfluxes": "CanopyFluxes", "soiltemperature": "SoilTemperature", "soilwater": "SoilWater"}
 
 
 def read_peaks():
@@ -35,10 +39,10 @@ def read_peaks():
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            return float(d["hbm_gbs"]), "measured"
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         except Exception:
             pass
-    return 6650.0, "fallback"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -94,35 +98,44 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_run(size, steps, warmup, sample_gridcells, seed):
+def which_mask(routines):
+    return sum({"soiltemperature": 1, "soilwater": 2, "canopyfluxes": 4}[g] for g in routines)
+
+
+def cpu_reference_run(size_label, routines, steps, warmup, sample_gridcells, seed):
     """The reference-arm / cpu_baseline measurement: oracle routines driven clump-parallel
     (OpenMP over clumps like clm_driver.F90:525) on a bounded sample of the workload."""
-    from ctsm_b200 import abi, synthetic
+    from ctsm_b200 import abi, synthetic_canopy
     from oracle import oracle
     OL = oracle.lib()
     nthreads = int(OL.oracle_num_threads())
-    sg, S = synthetic.make_case(sample_gridcells, seed=seed)
+    sg, S = synthetic_canopy.make_full_case(sample_gridcells, seed=seed)
     prm = abi.default_params()
     clumps, keep = oracle.make_clumps(sg, nthreads * 4)
-    inout = [fs.name for g in ("soiltemperature", "soilwater") for fs in abi.FIELDS[g] if fs.intent != "IN"]
-    pristine = {k: S[k].copy() for k in set(inout)}
+    groups = ("canopyfluxes", "soiltemperature", "soilwater")
+    inout = {fs.name for g in groups for fs in abi.FIELDS[g] if fs.intent != "IN"}
+    pristine = {k: S[k].copy() for k in inout}
     ft = abi.make_struct("soiltemperature", S, sg.bounds)
     fw = abi.make_struct("soilwater", S, sg.bounds)
+    fc = abi.make_struct("canopyfluxes", S, sg.bounds)
     times = []
     for it in range(warmup + steps):
         for k, v in pristine.items():
             S[k][...] = v
         t0 = time.perf_counter()
-        rc = OL.oracle_step_clumps(C.byref(prm), len(clumps), clumps, C.byref(ft), C.byref(fw), 3)
+        rc = OL.oracle_step_clumps(C.byref(prm), len(clumps), clumps, C.byref(ft), C.byref(fw), C.byref(fc),
+                                   which_mask(routines))
         t1 = time.perf_counter()
-        assert rc == 0
+        assert rc == 0, "oracle step failed rc=%d" % rc
         if it >= warmup:
             times.append(t1 - t0)
     tot = float(np.sum(times))
-    return {"value": sg.ncol * steps / tot, "ms_per_step": 1e3 * tot / steps, "cores": nthreads,
-            "columns": sg.ncol, "sample": "%d-gridcell (%d columns, %d patches) sample of the %s workload, %d steps, "
-            "C restatement of the reference (gcc -O2 -ffp-contract=off -fopenmp, one clump per task, %d threads)"
-            % (sg.ngrc, sg.ncol, sg.npatch, size, steps, nthreads)}
+    return {"value": sg.ncol * steps / tot, "ms_per_step": 1e3 * tot / steps, "cores": nthreads, "columns": sg.ncol,
+            "sample": "%d-gridcell (%d columns, %d patches, %d exposed-veg patches) sample of the %s workload, %d steps of %s, "
+            "C restatement of the reference (gcc -O2 -ffp-contract=off -fopenmp, one clump per task, %d threads); "
+            "not gfortran: no Fortran compiler in the image" % (
+                sg.ngrc, sg.ncol, sg.npatch, len(sg.filters["exposedvegp"]), size_label, steps,
+                "+".join(NAME_OF[g] for g in routines), nthreads)}
 
 
 def main():
@@ -131,6 +144,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", default="f02", help="tiny|f19|f09|f02 or a gridcell count (per GPU)")
+    ap.add_argument("--routines", default="canopyfluxes,soiltemperature,soilwater")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=20000, help="gridcells in the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
@@ -141,15 +155,19 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     size = a.size if not a.size.isdigit() else int(a.size)
-    wl_name = "SoilTemperature+SoilWater one 1800 s step, %s-sized synthetic grid per GPU" % a.size
-    config = {"workload": wl_name, "grid": str(a.size), "routines": ["SoilTemperature", "SoilWater"],
+    routines = tuple(g for g in ("canopyfluxes", "soiltemperature", "soilwater") if g in a.routines.split(","))
+    wl_name = "%s one 1800 s step, %s-sized synthetic grid per GPU (15 patches per soil column)" % (
+        "->".join(NAME_OF[g] for g in routines), a.size)
+    config = {"workload": wl_name, "grid": str(a.size), "routines": [NAME_OF[g] for g in routines],
               "state": "restored from a pristine device snapshot before every step (untimed D2D copies)",
-              "l2": "inputs (GBs per step) exceed the 126 MB L2; no explicit flush", "parallelism": "clumps/gridcells sharded by rank, no collective"}
+              "l2": "per-step working set (GBs at f02) exceeds the 126 MB L2; the untimed state restore between steps "
+                    "streams >L2 bytes through the cache",
+              "parallelism": "gridcells/clumps sharded by rank, no data-path collective"}
 
     if a.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_run(a.size, a.steps, a.warmup, a.cpu_sample, 20260101)
+        r = cpu_reference_run(a.size, routines, a.steps, a.warmup, a.cpu_sample, 20260101)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -159,7 +177,7 @@ def main():
         return
 
     import torch
-    from ctsm_b200 import abi, synthetic, driver
+    from ctsm_b200 import abi, synthetic_canopy, driver
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; ctsm_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
@@ -170,8 +188,7 @@ def main():
 
     prm = abi.default_params(device=local_rank)
     ctx = driver.Context(prm)
-    sg, S = synthetic.make_case(size, seed=20260101 + 1000 * rank)
-    routines = driver.ROUTINES
+    sg, S = synthetic_canopy.make_full_case(size, seed=20260101 + 1000 * rank)
     names = sorted({fs.name for g in routines for fs in abi.FIELDS[g]})
     D = {k: torch.from_numpy(S[k]).cuda() for k in names}
     restore = sorted({fs.name for g in routines for fs in abi.FIELDS[g] if fs.intent != "IN"})
@@ -205,11 +222,11 @@ def main():
         reset_state()
         ev[it][0].record(stream)
         for i, g in enumerate(routines):
-            getattr(hp, {"soiltemperature": "SoilTemperature", "soilwater": "SoilWater"}[g])()
+            hp.call(g)
             ev[it][i + 1].record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    ctx.sync()
+    st = ctx.sync()
     launches = ctx.launches - launches0
     clocks = sampler.stop() if rank == 0 else None
     step_ms = [ev[it][0].elapsed_time(ev[it][-1]) for it in range(a.steps)]
@@ -223,15 +240,26 @@ def main():
     total_s, total_cols = float(t.item()), float(cols.item())
     value = total_cols * a.steps / total_s
 
-    # roofline of the dominant kernel (per-routine event timing on the launching stream)
+    # roofline of the dominant routine's kernels (event timing on the launching stream, this rank)
     peak, peak_src = read_peaks()
+    per_routine = {}
+    for g in routines:
+        ab = driver.algorithmic_bytes(sg, S, g)
+        per_routine[NAME_OF[g]] = {"ms": rt_ms[g], "algorithmic_bytes": ab["bytes"], "GBps": ab["bytes"] / (rt_ms[g] * 1e-3) / 1e9,
+                                   "frac_of_hbm_peak": ab["bytes"] / (rt_ms[g] * 1e-3) / 1e9 / peak,
+                                   "columns": ab["columns"], "patches": ab["patches"]}
     dom = max(rt_ms, key=rt_ms.get)
     ab = driver.algorithmic_bytes(sg, S, dom)
     achieved = ab["bytes"] / (rt_ms[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": {"soiltemperature": "soiltemp_kernel", "soilwater": "soilwater_kernel"}[dom],
-                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "algorithmic_bytes_per_launch": ab["bytes"], "bytes_per_column": ab["bytes_per_column"],
-                "ms_per_launch": rt_ms[dom], "routine_ms": rt_ms}
+    step_bytes = sum(v["algorithmic_bytes"] for v in per_routine.values())
+    roofline = {"bound": "hbm", "kernel": KERNEL_OF[dom], "achieved": achieved, "peak": peak, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": ab["bytes"], "ms_per_launch": rt_ms[dom],
+                "note": "CanopyFluxes+PHS is FP64-pipe/latency bound (hundreds of pow/exp/log per patch-pass), see DESIGN.md; "
+                        "the HBM fraction is reported because BASELINE.json asks for it",
+                "whole_step": {"algorithmic_bytes": step_bytes, "GBps": step_bytes / (float(np.mean(step_ms)) * 1e-3) / 1e9,
+                               "frac": step_bytes / (float(np.mean(step_ms)) * 1e-3) / 1e9 / peak},
+                "routines": per_routine}
 
     # e2e: same step through the C ABI with pinned HOST buffers (H2D + kernels + D2H per step)
     e2e = None
@@ -241,7 +269,7 @@ def main():
         Hp = {k: S[k].copy() for k in restore}
         hph = driver.HotPath(ctx, sg, Hn, abi.MEM_HOST, routines)
         h2d, d2h = driver.staged_bytes(sg, routines, preserve_out=True)
-        e2e_steps = max(2, min(a.steps, 5))
+        e2e_steps = max(2, min(a.steps, 3))
         ts = []
         for it in range(1 + e2e_steps):
             for k, v in Hp.items():
@@ -258,20 +286,24 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": total_cols * e2e_steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-               "mode": "CTSM_MEM_HOST (all fields uploaded so that elements outside the filters are preserved)"}
+               "mode": "CTSM_MEM_HOST: every routine uploads all of its fields (so that elements outside the filters are "
+                       "preserved) and downloads its OUT/INOUT fields; wall clock around the three C-ABI calls"}
         del hph, H, Hn
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
-        r = cpu_reference_run(a.size, 3, 1, a.cpu_sample, 20260101)
+        r = cpu_reference_run(a.size, routines, 3, 1, a.cpu_sample, 20260101)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     if rank == 0:
+        nit = S["num_iter"] if False else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1e3 * total_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": dict(config, columns_per_gpu=ncol, patches_per_gpu=sg.npatch),
+                "dtype": "f64", "data": "synthetic",
+                "config": dict(config, columns_per_gpu=ncol, patches_per_gpu=sg.npatch,
+                               exposedveg_patches_per_gpu=int(len(sg.filters["exposedvegp"]))),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "wall_s_timed_region": t_wall}
+                "warnings_in_timed_region": int(st.n_warnings), "wall_s_timed_region": t_wall}
         print(json.dumps(line))
     ctx.close()
     if dist is not None:

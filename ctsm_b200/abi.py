@@ -35,6 +35,7 @@ LEV = {
     "VEGWCS": (1, NVEGWCS),
     "CAN": (1, NLEVCAN),
     "PHS2": (1, 2 * NLEVCAN),
+    "NUMRAD": (1, 2),
     "PFT": (0, MXPFT + 1),
     "PFTVEGWCS": (0, (MXPFT + 1) * NVEGWCS),
 }
@@ -204,6 +205,13 @@ def make_struct(group: str, arrays: dict, alloc: Bounds):
     return st
 
 
+class BalanceReport(C.Structure):
+    """ctsm_balance_report_t"""
+    KINDS = ("errh2o_col", "errh2o_grc", "errh2osno", "errsol", "errlon", "errseb", "errsoi_col")
+    _fields_ = [("max_abs", C.c_double * 7), ("index", C.c_int32 * 7), ("warn", C.c_int32 * 7),
+                ("abort_kind", C.c_int32), ("skip_steps", C.c_int32)]
+
+
 class LibraryMissing(RuntimeError):
     pass
 
@@ -251,6 +259,13 @@ def lib():
                                          C.POINTER(STRUCTS["canopyfluxes"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_set_exposedvegp_filter.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, i32p, i32p, i32p, i32p, i32p,
                                                    C.c_int]
+    L.ctsm_b200_vert_tran_sink_hydstress.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p,
+                                                     C.POINTER(STRUCTS["plantsink"]), C.c_int, C.POINTER(Status)]
+    L.ctsm_b200_balancecheck_init.argtypes = [vp]
+    L.ctsm_b200_balancecheck.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.POINTER(STRUCTS["balancecheck"]),
+                                         C.c_int, C.c_int, C.POINTER(BalanceReport), C.POINTER(Status)]
+    for fn in ("vert_tran_sink_hydstress", "balancecheck_init", "balancecheck"):
+        getattr(L, "ctsm_b200_" + fn).restype = C.c_int
     for fn in ("init", "finalize", "sync", "host_register", "host_unregister", "tridiagonal", "banddiagonal",
                "dgtsv_batch", "soilwater", "soiltemperature", "canopyfluxes", "set_exposedvegp_filter"):
         getattr(L, "ctsm_b200_" + fn).restype = C.c_int

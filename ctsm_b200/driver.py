@@ -15,7 +15,8 @@ import numpy as np
 
 from . import abi
 
-ROUTINES = ("soiltemperature", "soilwater")   # call order of the routines built so far
+ROUTINES = ("canopyfluxes", "soiltemperature", "soilwater")   # clm_drv call order (clm_driver.F90:766,900,950)
+FILTER_OF = {"canopyfluxes": ("exposedvegp",), "soiltemperature": ("nolakep", "nolakec"), "soilwater": ("hydrologyc",)}
 
 
 class CtsmError(RuntimeError):
@@ -89,9 +90,20 @@ class HotPath:
         if rc != 0:
             raise CtsmError(st, rc)
 
+    def CanopyFluxes(self):
+        st = abi.Status()
+        rc = self.ctx.L.ctsm_b200_canopyfluxes(
+            self.ctx.h, C.byref(self.sg.bounds), self.nfilter["exposedvegp"], abi.i32p(self.filters["exposedvegp"]),
+            C.byref(self.structs["canopyfluxes"]), self.mem, C.byref(st))
+        if rc != 0:
+            raise CtsmError(st, rc)
+
+    def call(self, g):
+        {"canopyfluxes": self.CanopyFluxes, "soiltemperature": self.SoilTemperature, "soilwater": self.SoilWater}[g]()
+
     def step(self):
         for g in self.routines:
-            {"soiltemperature": self.SoilTemperature, "soilwater": self.SoilWater}[g]()
+            self.call(g)
 
 
 def staged_bytes(sg, routines: Iterable[str], preserve_out: bool = True):
@@ -104,7 +116,8 @@ def staged_bytes(sg, routines: Iterable[str], preserve_out: bool = True):
                 h2d += n
             if fs.intent in ("OUT", "INOUT"):
                 d2h += n
-    h2d += 4 * (len(sg.filters["nolakec"]) + len(sg.filters["nolakep"]) + len(sg.filters["hydrologyc"]))
+    for g in routines:
+        h2d += 4 * sum(len(sg.filters[k]) for k in FILTER_OF[g])
     return h2d, d2h
 
 
@@ -115,6 +128,9 @@ def algorithmic_bytes(sg, S, group: str) -> Dict[str, float]:
     if group == "soilwater":
         ncol = len(sg.filters["hydrologyc"]); cols = sg.filters["hydrologyc"] - 1
         npat = 0; pats = np.zeros(0, dtype=np.int64)
+    elif group == "canopyfluxes":
+        pats = sg.filters["exposedvegp"] - 1; npat = len(pats)
+        cols = np.unique(sg.patch_column[pats]) - 1; ncol = len(cols)      # each column counted once per step
     else:
         ncol = len(sg.filters["nolakec"]); cols = sg.filters["nolakec"] - 1
         npat = len(sg.filters["nolakep"]); pats = sg.filters["nolakep"] - 1
@@ -123,8 +139,11 @@ def algorithmic_bytes(sg, S, group: str) -> Dict[str, float]:
     total = 0.0
     for fs in abi.FIELDS[group]:
         es = 8 if fs.ctype == "double" else 4
+        if fs.sub in ("PFT", "GRC"):
+            continue          # parameter tables / per-gridcell scalars: negligible, shared by many units
         units, snow = (npat, snow_p) if fs.sub == "PATCH" else (ncol, snow_c)
         lev = fs.used_soil + fs.used_snow * snow
         mult = 2 if fs.intent == "INOUT" else 1
         total += units * lev * es * mult
-    return {"bytes": total, "columns": ncol, "patches": npat, "bytes_per_column": total / max(ncol, 1)}
+    return {"bytes": total, "columns": ncol, "patches": npat, "bytes_per_column": total / max(ncol, 1),
+            "bytes_per_patch": total / max(npat, 1)}

@@ -206,3 +206,86 @@ def make_full_case(size="tiny", seed: int = 20260101, special_every: int = 10, d
     S = soil_state(sg, rng)
     canopy_state(sg, S, rng, day_fraction)
     return sg, S
+
+
+def balance_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator, noise: float = 1.0e-11) -> None:
+    """Adds the fields of groups `balancecheck` and `plantsink`: budgets that close up to `noise`
+    (so the residuals are differences of O(1..100) operands, as in the model)."""
+    nc, npch, ng = sg.ncol, sg.npatch, sg.ngrc
+    g = lambda a, b, *sh: rng.uniform(a, b, size=sh)
+    dtime = 1800.0
+    first = np.searchsorted(sg.col_gridcell, np.arange(1, ng + 1), side="left")
+    last = np.searchsorted(sg.col_gridcell, np.arange(1, ng + 1), side="right") - 1
+    S["grc_coli"], S["grc_colf"] = (first + 1).astype(np.int32), (last + 1).astype(np.int32)
+    S["col_active"] = sg.col_active.astype(np.int32)
+    ncol_g = (last - first + 1)
+    S["wtgcell"] = (1.0 / ncol_g)[sg.col_gridcell - 1]
+    S["patch_active"] = sg.patch_active.astype(np.int32)
+    S["npatches"] = (sg.col_patchf - sg.col_patchi + 1).astype(np.int32)
+    colflux = ("forc_rain", "forc_snow", "qflx_flood", "qflx_sfc_irrig", "qflx_glcice_dyn_water_flux", "qflx_evap_tot",
+               "qflx_surf", "qflx_qrgwl", "qflx_drain", "qflx_drain_perched", "qflx_ice_runoff",
+               "qflx_snwcp_discarded_liq", "qflx_snwcp_discarded_ice")
+    sign = (1, 1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1, -1)
+    net = np.zeros(nc)
+    for nm, sgn in zip(colflux, sign):
+        S[nm] = g(0.0, 3.0e-4, nc) * (rng.random(nc) < 0.6)
+        net += sgn * S[nm]
+    S["begwb"] = g(500.0, 3000.0, nc)
+    S["endwb"] = S["begwb"] + net * dtime + rng.normal(0.0, noise, nc)
+    grcflux = ("forc_rain_grc", "forc_snow_grc", "forc_flood_grc", "qflx_sfc_irrig_grc", "qflx_evap_tot_grc",
+               "qflx_surf_grc", "qflx_qrgwl_grc", "qflx_drain_grc", "qflx_drain_perched_grc", "qflx_ice_runoff_grc")
+    gsign = (1, 1, 1, 1, -1, -1, -1, -1, -1, -1)
+    gnet = np.zeros(ng)
+    for nm, sgn in zip(grcflux, gsign):
+        S[nm] = g(0.0, 3.0e-4, ng)
+        gnet += sgn * S[nm]
+    agg = lambda a: np.add.reduceat(a * S["wtgcell"], first)
+    gnet += agg(S["qflx_glcice_dyn_water_flux"]) - agg(S["qflx_snwcp_discarded_liq"]) - agg(S["qflx_snwcp_discarded_ice"])
+    S["begwb_grc"] = g(500.0, 3000.0, ng)
+    S["endwb_grc"] = S["begwb_grc"] + gnet * dtime + rng.normal(0.0, noise, ng)
+    S["errh2o_grc"] = np.full(ng, 1.0e36)
+    for nm in ("qflx_prec_grnd", "qflx_soliddew_to_top_layer", "qflx_liqdew_to_top_layer", "qflx_solidevap_from_top_layer",
+               "qflx_liqevap_from_top_layer", "qflx_snwcp_ice", "qflx_snwcp_liq", "qflx_sl_top_soil",
+               "qflx_snow_grnd", "qflx_liq_grnd", "qflx_snow_h2osfc"):
+        S[nm] = g(0.0, 2.0e-4, nc) * (rng.random(nc) < 0.5)
+    lo = -NLEVSNO + 1
+    tot = S["h2osno_no_layers"].copy()
+    for j in range(lo, 1):
+        act = j >= S["snl"] + 1
+        tot += np.where(act, S["h2osoi_ice"][j - lo] + S["h2osoi_liq"][j - lo], 0.0)
+    fs = S["frac_sno_eff"]
+    h2ice = np.where(np.abs(S["qflx_h2osfc_to_ice"]) < 1e30, S["qflx_h2osfc_to_ice"], 0.0)
+    S["qflx_h2osfc_to_ice"] = h2ice
+    S["qflx_snow_drain"] = np.where(np.abs(S["qflx_snow_drain"]) < 1e30, S["qflx_snow_drain"], 0.0)
+    src = (S["qflx_snow_grnd"] - S["qflx_snow_h2osfc"]) + fs * (S["qflx_liq_grnd"] + S["qflx_soliddew_to_top_layer"]
+                                                               + S["qflx_liqdew_to_top_layer"]) + h2ice
+    snk = fs * (S["qflx_solidevap_from_top_layer"] + S["qflx_liqevap_from_top_layer"]) + S["qflx_snwcp_ice"] + S["qflx_snwcp_liq"] \
+        + S["qflx_snwcp_discarded_ice"] + S["qflx_snwcp_discarded_liq"] + S["qflx_snow_drain"] + S["qflx_sl_top_soil"]
+    lake = sg.col_lun_itype == ISTDLAK                       # BalanceCheckMod.F90:772-780
+    src = np.where(lake, S["qflx_snow_grnd"] + fs * (S["qflx_liq_grnd"] + S["qflx_soliddew_to_top_layer"]
+                                                     + S["qflx_liqdew_to_top_layer"]), src)
+    S["h2osno_old"] = tot - (src - snk) * dtime + rng.normal(0.0, noise, nc)
+    S["errsoi_col"] = rng.normal(0.0, 1.0e-7, nc)
+    S["forc_solad"] = g(0.0, 300.0, 2, nc)
+    S["forc_solai"] = g(0.0, 100.0, 2, ng)
+    pc, pg = sg.patch_column - 1, sg.patch_gridcell - 1
+    sol = S["forc_solad"][0, pc] + S["forc_solad"][1, pc] + S["forc_solai"][0, pg] + S["forc_solai"][1, pg]
+    S["fsr"] = sol * g(0.1, 0.4, npch)
+    S["fsa"] = sol - S["fsr"] + rng.normal(0.0, noise, npch)
+    S["eflx_lwrad_out"] = g(250.0, 480.0, npch)
+    S["eflx_lwrad_net"] = S["eflx_lwrad_out"] - S["forc_lwrad"][pc] + rng.normal(0.0, noise, npch)
+    S["eflx_sh_tot"] = rng.normal(30.0, 60.0, npch)
+    S["eflx_lh_tot"] = rng.normal(40.0, 60.0, npch)
+    sabg_chk = np.where(np.abs(S["sabg_chk"]) < 1e30, S["sabg_chk"], 0.0)
+    S["sabg_chk"] = sabg_chk
+    dh = np.where(np.abs(S["dhsdt_canopy"]) < 1e30, S["dhsdt_canopy"], 0.0)
+    S["dhsdt_canopy"] = dh
+    S["eflx_soil_grnd"] = S["sabv"] + sabg_chk + S["forc_lwrad"][pc] - S["eflx_lwrad_out"] - S["eflx_sh_tot"] - S["eflx_lh_tot"] \
+        - dh + rng.normal(0.0, noise, npch)
+    for nm in ("errh2o", "errh2osno", "snow_sources", "snow_sinks", "qflx_phs_neg"):
+        S[nm] = np.full(nc, 1.0e36)
+    for nm in ("errsol", "errlon", "errseb", "netrad", "qflx_hydr_redist"):
+        S[nm] = np.full(npch, 1.0e36)
+    S["k_soil_root"] = np.where(np.abs(S["k_soil_root"]) < 1e30, S["k_soil_root"], 0.0)
+    for k, v in list(S.items()):
+        S[k] = np.ascontiguousarray(v)

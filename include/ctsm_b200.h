@@ -163,7 +163,33 @@ typedef struct ctsm_canopyfluxes_fields_t {
 #include "ctsm_b200_fields.def"
 #undef CTSM_FIELDS_CANOPYFLUXES
 } ctsm_canopyfluxes_fields_t;
+
+typedef struct ctsm_plantsink_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_PLANTSINK
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_PLANTSINK
+} ctsm_plantsink_fields_t;
+
+typedef struct ctsm_balancecheck_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_BALANCECHECK
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_BALANCECHECK
+} ctsm_balancecheck_fields_t;
 #undef CTSM_F
+
+/* result of BalanceCheck / EnergyBalanceCheck: clump-local maxval / maxloc of each residual
+ * (BalanceCheckMod.F90:610,696,806,1009,1047,1066,1101) and the warning / abort decisions */
+enum { CTSM_BAL_H2O_COL = 0, CTSM_BAL_H2O_GRC = 1, CTSM_BAL_H2OSNO = 2, CTSM_BAL_SOL = 3, CTSM_BAL_LON = 4,
+       CTSM_BAL_SEB = 5, CTSM_BAL_SOI = 6, CTSM_BAL_NKIND = 7 };
+typedef struct ctsm_balance_report_t {
+  double  max_abs[CTSM_BAL_NKIND];   /* maxval(abs(err)) over the bounds */
+  int32_t index[CTSM_BAL_NKIND];     /* maxloc: lowest 1-based index attaining it (0 when nothing qualifies) */
+  int32_t warn[CTSM_BAL_NKIND];      /* the reference would write(iulog) a WARNING */
+  int32_t abort_kind;                /* first kind (in the reference's order of checks) that would endrun, or -1 */
+  int32_t skip_steps;
+} ctsm_balance_report_t;
 
 /* ---- lifecycle ------------------------------------------------------------ */
 void ctsm_b200_default_params(ctsm_params_t* p);
@@ -245,6 +271,24 @@ int ctsm_b200_set_exposedvegp_filter(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bo
                                      const int32_t* frac_veg_nosno /* (begp:endp) */,
                                      int32_t* filter_exposedvegp, int32_t* num_exposedvegp,
                                      int32_t* filter_noexposedvegp, int32_t* num_noexposedvegp, int mem);
+
+/* Compute_EffecRootFrac_And_VertTranSink_HydStress(bounds, num_filterc, filterc, ...):
+ * SoilWaterPlantSinkMod.F90:236-328 (the PHS sink term SoilWater consumes). */
+int ctsm_b200_vert_tran_sink_hydstress(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
+                                       int num_filterc, const int32_t* filterc,
+                                       const ctsm_plantsink_fields_t* f, int mem, ctsm_status_t* st);
+
+/* BalanceCheckInit(): BalanceCheckMod.F90:74-95; skip_steps = max(2, nint(3600/dtime)) + 1.  Returns skip_steps. */
+int ctsm_b200_balancecheck_init(ctsm_b200_ctx* ctx);
+
+/* BalanceCheck(bounds, num_allc, filter_allc, ...) including EnergyBalanceCheck:
+ * BalanceCheckMod.F90:445-857, 859-1119.  DAnstep = get_nstep_since_startup_or_lastDA_restart_or_pause().
+ * Synchronous (the reference decides on the host whether to endrun).  Returns CTSM_ERR_BALANCE and fills
+ * st like endrun(subgrid_index=, subgrid_level=) when a residual exceeds its abort threshold after the skip
+ * steps; CTSM_ERR_BAD_ARG when called before ctsm_b200_balancecheck_init (the reference aborts likewise). */
+int ctsm_b200_balancecheck(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_allc, const int32_t* filter_allc,
+                           const ctsm_balancecheck_fields_t* f, int DAnstep, int mem,
+                           ctsm_balance_report_t* report, ctsm_status_t* st);
 
 #ifdef __cplusplus
 }

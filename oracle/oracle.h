@@ -55,6 +55,15 @@ int oracle_soiltemperature(const ctsm_params_t* prm, const ctsm_bounds_t* bounds
 /* CanopyFluxesMod.F90:191 (use_hydrstress) */
 int oracle_canopyfluxes(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_exposedvegp,
                         const int32_t* filter_exposedvegp, const ctsm_canopyfluxes_fields_t* f, ctsm_status_t* st);
+/* BalanceCheckMod.F90:445-857 + EnergyBalanceCheck :859-1119 (prm->balance_skip_steps from BalanceCheckInit) */
+int oracle_balancecheck(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_allc, const int32_t* filter_allc,
+                        const ctsm_balancecheck_fields_t* f, int DAnstep, ctsm_balance_report_t* rep, ctsm_status_t* st);
+int oracle_balancecheck_skip_steps(double dtime);
+/* SoilWaterPlantSinkMod.F90:236-328 */
+int oracle_vert_tran_sink_hydstress(const ctsm_bounds_t* bounds, int num_filterc, const int32_t* filterc,
+                                    const ctsm_plantsink_fields_t* f);
+void oracle_truncate_small_values(int num_f, const int32_t* filter_f, int lb, const double* data_baseline, double* data,
+                                  double rel_epsilon);
 /* filterMod.F90:595-648 */
 void oracle_set_exposedvegp_filter(const ctsm_bounds_t* bounds, int num_nolakeurbanp, const int32_t* nolakeurbanp,
                                    const int32_t* frac_veg_nosno, int32_t* exposedvegp, int32_t* num_exposedvegp,
@@ -75,9 +84,10 @@ typedef struct oracle_clump_t {
   int32_t num_hydrologyc; const int32_t* filter_hydrologyc;
   int32_t num_exposedvegp; const int32_t* filter_exposedvegp;
 } oracle_clump_t;
-/* which: bit 0 SoilTemperature, bit 1 SoilWater (call order of clm_drv) */
+/* which: bit 2 CanopyFluxes, bit 0 SoilTemperature, bit 1 SoilWater; executed in clm_drv call order */
 int oracle_step_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump_t* clumps,
-                       const ctsm_soiltemperature_fields_t* ft, const ctsm_soilwater_fields_t* fw, int which);
+                       const ctsm_soiltemperature_fields_t* ft, const ctsm_soilwater_fields_t* fw,
+                       const ctsm_canopyfluxes_fields_t* fc, int which);
 
 /* number of OpenMP threads the clump-loop drivers will use */
 int oracle_num_threads(void);

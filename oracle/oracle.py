@@ -96,8 +96,12 @@ def lib():
     L.oracle_plc.restype = C.c_double
     L.oracle_d1plc.argtypes = [C.c_double] * 3
     L.oracle_d1plc.restype = C.c_double
+    L.oracle_balancecheck.argtypes = [P, B, C.c_int, i32p, C.POINTER(abi.STRUCTS["balancecheck"]), C.c_int,
+                                      C.POINTER(abi.BalanceReport), S]
+    L.oracle_balancecheck_skip_steps.argtypes = [C.c_double]
+    L.oracle_vert_tran_sink_hydstress.argtypes = [B, C.c_int, i32p, C.POINTER(abi.STRUCTS["plantsink"])]
     L.oracle_num_threads.restype = C.c_int
     L.oracle_step_clumps.argtypes = [P, C.c_int, C.POINTER(Clump), C.POINTER(abi.STRUCTS["soiltemperature"]),
-                                     C.POINTER(abi.STRUCTS["soilwater"]), C.c_int]
+                                     C.POINTER(abi.STRUCTS["soilwater"]), C.POINTER(abi.STRUCTS["canopyfluxes"]), C.c_int]
     _lib = L
     return L

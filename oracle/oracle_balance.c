@@ -1,0 +1,248 @@
+/* oracle_balance.c — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement of
+ *   BalanceCheck            src/biogeophys/BalanceCheckMod.F90:445-857
+ *   EnergyBalanceCheck      :859-1119
+ *   c2g_1d ('urbanf','unity' on non-urban landunits)   src/main/subgridAveMod.F90:761-818
+ *   CalculateTotalH2osno    src/biogeophys/WaterStateType.F90:887-896
+ *   Compute_EffecRootFrac_And_VertTranSink_HydStress   src/biogeophys/SoilWaterPlantSinkMod.F90:236-328
+ * for bulk water, non-urban landunits, use_hillslope_routing = .false..  The skip-step rule
+ * (BalanceCheckInit :74-95) is pinned by the reference's test_Balance.pf (tests/test_oracle_golden.py);
+ * the residual formulas are PARITY UNPINNED by the reference's tests.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "oracle.h"
+
+#define NLEVSNO CTSM_NLEVSNO
+#define NLEVSOI CTSM_NLEVSOI
+#define SNOSOI_LO (-NLEVSNO + 1)
+static const double spval = 1.e36;
+static const double error_thresh = 1.e-5, h2o_warning_thresh = 1.e-9, energy_warning_thresh = 1.e-7;
+
+/* maxval / maxloc over [lo,hi] with optional mask (mask==NULL: all); arrays are offset by base */
+static void maxabs(const double* a, int base, int lo, int hi, const int* mask_ok, double* mx, int* loc) {
+  *mx = 0.0; *loc = 0;
+  int any = 0;
+  for (int i = lo; i <= hi; ++i) {
+    if (mask_ok && !mask_ok[i - base]) continue;
+    const double v = fabs(a[i - base]);
+    if (!any || v > *mx) { *mx = v; *loc = i; any = 1; }
+  }
+  if (!any) { *mx = 0.0; *loc = 0; }
+}
+
+int oracle_balancecheck(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_allc, const int32_t* filter_allc,
+                        const ctsm_balancecheck_fields_t* f, int DAnstep, ctsm_balance_report_t* rep, ctsm_status_t* st) {
+  const int begc0 = f->alloc.begc, begp0 = f->alloc.begp, begg0 = f->alloc.begg;
+  const size_t ldc = (size_t)(f->alloc.endc - f->alloc.begc + 1), ldg = (size_t)(f->alloc.endg - f->alloc.begg + 1);
+  const double dtime = prm->dtime;
+  const int skip_steps = prm->balance_skip_steps;
+  memset(rep, 0, sizeof *rep);
+  if (st) memset(st, 0, sizeof *st);
+  rep->abort_kind = -1;
+  rep->skip_steps = skip_steps;
+  if (skip_steps <= 0) return CTSM_ERR_BAD_ARG;
+#define CC(name, c) (f->name[(c) - begc0])
+#define GG(name, g) (f->name[(g) - begg0])
+#define PP(name, p) (f->name[(p) - begp0])
+  const int nc = bounds->endc - bounds->begc + 1, ng = bounds->endg - bounds->begg + 1, np = bounds->endp - bounds->begp + 1;
+  double* h2osno_total = (double*)calloc((size_t)(nc > 0 ? nc : 1), sizeof(double));
+  double* gdyn = (double*)calloc((size_t)(ng > 0 ? ng : 1), sizeof(double));
+  double* gliq = (double*)calloc((size_t)(ng > 0 ? ng : 1), sizeof(double));
+  double* gice = (double*)calloc((size_t)(ng > 0 ? ng : 1), sizeof(double));
+  int* okmask = (int*)calloc((size_t)((np > nc ? np : nc) + 1), sizeof(int));
+  int abort_kind = -1, abort_index = 0, abort_level = 0;
+
+  for (int c = bounds->begc; c <= bounds->endc; ++c) {              /* :592-608 */
+    if (CC(col_active, c)) {
+      CC(errh2o, c) = CC(endwb, c) - CC(begwb, c)
+          - (CC(forc_rain, c) + CC(forc_snow, c) + CC(qflx_flood, c) + CC(qflx_sfc_irrig, c) + CC(qflx_glcice_dyn_water_flux, c)
+             - CC(qflx_evap_tot, c) - CC(qflx_surf, c) - CC(qflx_qrgwl, c) - CC(qflx_drain, c) - CC(qflx_drain_perched, c)
+             - CC(qflx_ice_runoff, c) - CC(qflx_snwcp_discarded_liq, c) - CC(qflx_snwcp_discarded_ice, c)) * dtime;
+    } else {
+      CC(errh2o, c) = 0.0;
+    }
+  }
+  maxabs(f->errh2o, begc0, bounds->begc, bounds->endc, NULL, &rep->max_abs[CTSM_BAL_H2O_COL], &rep->index[CTSM_BAL_H2O_COL]);
+  if (rep->max_abs[CTSM_BAL_H2O_COL] > h2o_warning_thresh) {         /* :612-660 */
+    rep->warn[CTSM_BAL_H2O_COL] = 1;
+    if (rep->max_abs[CTSM_BAL_H2O_COL] > error_thresh && DAnstep > skip_steps && abort_kind < 0) {
+      abort_kind = CTSM_BAL_H2O_COL; abort_index = rep->index[CTSM_BAL_H2O_COL]; abort_level = CTSM_SUBGRID_COLUMN;
+    }
+  }
+  /* c2g of three column fluxes, subgridAveMod.F90:791-812 (unity scales) */
+  const double* carr[3] = {f->qflx_glcice_dyn_water_flux, f->qflx_snwcp_discarded_liq, f->qflx_snwcp_discarded_ice};
+  double* garr[3] = {gdyn, gliq, gice};
+  for (int k = 0; k < 3; ++k) {
+    for (int g = bounds->begg; g <= bounds->endg; ++g) {
+      double sumwt = 0.0, acc = spval;
+      for (int c = GG(grc_coli, g); c <= GG(grc_colf, g); ++c) {
+        if (CC(col_active, c) && CC(wtgcell, c) != 0.0) {
+          if (carr[k][c - begc0] != spval) {
+            if (sumwt == 0.0) acc = 0.0;
+            acc = acc + carr[k][c - begc0] * 1.0 * 1.0 * CC(wtgcell, c);
+            sumwt = sumwt + CC(wtgcell, c);
+          }
+        }
+      }
+      if (!(sumwt > 1.0 + 1.e-6) && sumwt != 0.0) acc = acc / sumwt;
+      garr[k][g - bounds->begg] = acc;
+    }
+  }
+  for (int g = bounds->begg; g <= bounds->endg; ++g) {              /* :679-694 */
+    const int i = g - bounds->begg;
+    GG(errh2o_grc, g) = GG(endwb_grc, g) - GG(begwb_grc, g)
+        - (GG(forc_rain_grc, g) + GG(forc_snow_grc, g) + GG(forc_flood_grc, g) + GG(qflx_sfc_irrig_grc, g) + gdyn[i]
+           - GG(qflx_evap_tot_grc, g) - GG(qflx_surf_grc, g) - GG(qflx_qrgwl_grc, g) - GG(qflx_drain_grc, g)
+           - GG(qflx_drain_perched_grc, g) - GG(qflx_ice_runoff_grc, g) - gliq[i] - gice[i]) * dtime;
+  }
+  maxabs(f->errh2o_grc, begg0, bounds->begg, bounds->endg, NULL, &rep->max_abs[CTSM_BAL_H2O_GRC], &rep->index[CTSM_BAL_H2O_GRC]);
+  if (rep->max_abs[CTSM_BAL_H2O_GRC] > h2o_warning_thresh) {         /* :709-748 */
+    rep->warn[CTSM_BAL_H2O_GRC] = 1;
+    if (rep->max_abs[CTSM_BAL_H2O_GRC] > error_thresh && DAnstep > skip_steps && abort_kind < 0) {
+      abort_kind = CTSM_BAL_H2O_GRC; abort_index = rep->index[CTSM_BAL_H2O_GRC]; abort_level = CTSM_SUBGRID_GRIDCELL;
+    }
+  }
+  /* CalculateTotalH2osno over filter_allc, WaterStateType.F90:887-896 */
+  for (int fc = 0; fc < num_allc; ++fc) {
+    const int c = filter_allc[fc];
+    double t = CC(h2osno_no_layers, c);
+    for (int j = CC(snl, c) + 1; j <= 0; ++j)
+      t = t + f->h2osoi_ice[(size_t)(j - SNOSOI_LO) * ldc + (c - begc0)] + f->h2osoi_liq[(size_t)(j - SNOSOI_LO) * ldc + (c - begc0)];
+    h2osno_total[c - bounds->begc] = t;
+  }
+  for (int c = bounds->begc; c <= bounds->endc; ++c) {              /* :754-803 */
+    if (CC(col_active, c)) {
+      const int lt = CC(lun_itype, c);
+      if (CC(snl, c) < 0) {
+        double src = CC(qflx_prec_grnd, c) + CC(qflx_soliddew_to_top_layer, c) + CC(qflx_liqdew_to_top_layer, c);
+        double snk = CC(qflx_solidevap_from_top_layer, c) + CC(qflx_liqevap_from_top_layer, c) + CC(qflx_snow_drain, c)
+                     + CC(qflx_snwcp_ice, c) + CC(qflx_snwcp_liq, c) + CC(qflx_snwcp_discarded_ice, c)
+                     + CC(qflx_snwcp_discarded_liq, c) + CC(qflx_sl_top_soil, c);
+        if (lt == CTSM_ISTDLAK) {
+          src = CC(qflx_snow_grnd, c) + CC(frac_sno_eff, c) * (CC(qflx_liq_grnd, c) + CC(qflx_soliddew_to_top_layer, c)
+                                                                + CC(qflx_liqdew_to_top_layer, c));
+          snk = CC(frac_sno_eff, c) * (CC(qflx_solidevap_from_top_layer, c) + CC(qflx_liqevap_from_top_layer, c))
+                + CC(qflx_snwcp_ice, c) + CC(qflx_snwcp_liq, c) + CC(qflx_snwcp_discarded_ice, c)
+                + CC(qflx_snwcp_discarded_liq, c) + CC(qflx_snow_drain, c) + CC(qflx_sl_top_soil, c);
+        }
+        if (lt == CTSM_ISTSOIL || lt == CTSM_ISTCROP || lt == CTSM_ISTWET || lt == CTSM_ISTICE) {
+          src = (CC(qflx_snow_grnd, c) - CC(qflx_snow_h2osfc, c))
+                + CC(frac_sno_eff, c) * (CC(qflx_liq_grnd, c) + CC(qflx_soliddew_to_top_layer, c) + CC(qflx_liqdew_to_top_layer, c))
+                + CC(qflx_h2osfc_to_ice, c);
+          snk = CC(frac_sno_eff, c) * (CC(qflx_solidevap_from_top_layer, c) + CC(qflx_liqevap_from_top_layer, c))
+                + CC(qflx_snwcp_ice, c) + CC(qflx_snwcp_liq, c) + CC(qflx_snwcp_discarded_ice, c)
+                + CC(qflx_snwcp_discarded_liq, c) + CC(qflx_snow_drain, c) + CC(qflx_sl_top_soil, c);
+        }
+        CC(snow_sources, c) = src;
+        CC(snow_sinks, c) = snk;
+        CC(errh2osno, c) = (h2osno_total[c - bounds->begc] - CC(h2osno_old, c)) - (src - snk) * dtime;
+      } else {
+        CC(snow_sources, c) = 0.0;
+        CC(snow_sinks, c) = 0.0;
+        CC(errh2osno, c) = 0.0;
+      }
+    } else {
+      CC(errh2osno, c) = 0.0;
+    }
+  }
+  maxabs(f->errh2osno, begc0, bounds->begc, bounds->endc, NULL, &rep->max_abs[CTSM_BAL_H2OSNO], &rep->index[CTSM_BAL_H2OSNO]);
+  if (rep->max_abs[CTSM_BAL_H2OSNO] > h2o_warning_thresh) {          /* :808-847 */
+    rep->warn[CTSM_BAL_H2OSNO] = 1;
+    if (rep->max_abs[CTSM_BAL_H2OSNO] > error_thresh && DAnstep > skip_steps && abort_kind < 0) {
+      abort_kind = CTSM_BAL_H2OSNO; abort_index = rep->index[CTSM_BAL_H2OSNO]; abort_level = CTSM_SUBGRID_COLUMN;
+    }
+  }
+  /* EnergyBalanceCheck :962-1005 (non-urban) */
+  for (int p = bounds->begp; p <= bounds->endp; ++p) {
+    if (PP(patch_active, p)) {
+      const int c = PP(column, p), g = PP(gridcell, p);
+      PP(errsol, p) = PP(fsa, p) + PP(fsr, p)
+          - (f->forc_solad[c - begc0] + f->forc_solad[ldc + (c - begc0)] + f->forc_solai[g - begg0] + f->forc_solai[ldg + (g - begg0)]);
+      PP(errlon, p) = PP(eflx_lwrad_out, p) - PP(eflx_lwrad_net, p) - CC(forc_lwrad, c);
+      PP(errseb, p) = PP(sabv, p) + PP(sabg_chk, p) + CC(forc_lwrad, c) - PP(eflx_lwrad_out, p) - PP(eflx_sh_tot, p)
+                      - PP(eflx_lh_tot, p) - PP(eflx_soil_grnd, p) - PP(dhsdt_canopy, p);
+      PP(netrad, p) = PP(fsa, p) - PP(eflx_lwrad_net, p);
+    } else {
+      PP(errsol, p) = 0.0; PP(errlon, p) = 0.0; PP(errseb, p) = 0.0;
+    }
+  }
+  const int kinds[3] = {CTSM_BAL_SOL, CTSM_BAL_LON, CTSM_BAL_SEB};
+  const double* earr[3] = {f->errsol, f->errlon, f->errseb};
+  for (int k = 0; k < 3; ++k) {                                     /* :1009-1097 */
+    const int kd = kinds[k];
+    int* mask = NULL;
+    if (kd != CTSM_BAL_SEB) {
+      for (int p = bounds->begp; p <= bounds->endp; ++p) okmask[p - bounds->begp] = (earr[k][p - begp0] != spval);
+      mask = okmask;
+    }
+    /* maxabs takes base-relative mask: shift by using a temporary view */
+    double mx = 0.0; int loc = 0, any = 0;
+    for (int p = bounds->begp; p <= bounds->endp; ++p) {
+      if (mask && !mask[p - bounds->begp]) continue;
+      const double v = fabs(earr[k][p - begp0]);
+      if (!any || v > mx) { mx = v; loc = p; any = 1; }
+    }
+    rep->max_abs[kd] = mx; rep->index[kd] = loc;
+    if (mx > energy_warning_thresh && DAnstep > skip_steps) {
+      rep->warn[kd] = 1;
+      if (mx > error_thresh && abort_kind < 0) { abort_kind = kd; abort_index = loc; abort_level = CTSM_SUBGRID_PATCH; }
+    }
+  }
+  {                                                                 /* :1101-1114 */
+    double mx = 0.0; int loc = 0, any = 0;
+    for (int c = bounds->begc; c <= bounds->endc; ++c) {
+      if (!CC(col_active, c)) continue;
+      const double v = fabs(CC(errsoi_col, c));
+      if (!any || v > mx) { mx = v; loc = c; any = 1; }
+    }
+    rep->max_abs[CTSM_BAL_SOI] = mx; rep->index[CTSM_BAL_SOI] = loc;
+    if (mx > 1.0e-5) {
+      rep->warn[CTSM_BAL_SOI] = 1;
+      if (mx > 1.e-4 && DAnstep > skip_steps && abort_kind < 0) { abort_kind = CTSM_BAL_SOI; abort_index = loc; abort_level = CTSM_SUBGRID_COLUMN; }
+    }
+  }
+  rep->abort_kind = abort_kind;
+  free(h2osno_total); free(gdyn); free(gliq); free(gice); free(okmask);
+  if (abort_kind >= 0) {
+    if (st) { st->code = CTSM_ERR_BALANCE; st->subgrid_index = abort_index; st->subgrid_level = abort_level; st->info = abort_kind;
+              st->value = rep->max_abs[abort_kind]; }
+    return CTSM_ERR_BALANCE;
+  }
+  return 0;
+#undef CC
+#undef GG
+#undef PP
+}
+
+/* SoilWaterPlantSinkMod.F90:236-328 */
+int oracle_vert_tran_sink_hydstress(const ctsm_bounds_t* bounds, int num_filterc, const int32_t* filterc,
+                                    const ctsm_plantsink_fields_t* f) {
+  (void)bounds;
+  const int begc0 = f->alloc.begc, begp0 = f->alloc.begp;
+  const size_t ldc = (size_t)(f->alloc.endc - f->alloc.begc + 1), ldp = (size_t)(f->alloc.endp - f->alloc.begp + 1);
+  for (int fc = 0; fc < num_filterc; ++fc) {
+    const int c = filterc[fc];
+    f->qflx_phs_neg[c - begc0] = 0.0;
+    for (int j = 1; j <= NLEVSOI; ++j) {
+      const double grav2 = f->z[(size_t)(j - SNOSOI_LO) * ldc + (c - begc0)] * 1000.0;
+      double temp = 0.0;
+      for (int p = f->patchi[c - begc0]; p <= f->patchi[c - begc0] + f->npatches[c - begc0] - 1; ++p) {
+        if (j == 1) f->qflx_hydr_redist[p - begp0] = 0.0;
+        if (f->patch_active[p - begp0] && f->frac_veg_nosno[p - begp0] > 0) {
+          if (f->wtcol[p - begp0] > 0.0) {
+            const double patchflux = f->k_soil_root[(size_t)(j - 1) * ldp + (p - begp0)] *
+                                     (f->smp_l[(size_t)(j - 1) * ldc + (c - begc0)] - f->vegwp[(size_t)3 * ldp + (p - begp0)] - grav2);
+            if (patchflux < 0) f->qflx_hydr_redist[p - begp0] = f->qflx_hydr_redist[p - begp0] + patchflux;
+            temp = temp + patchflux * f->wtcol[p - begp0];
+          }
+        }
+      }
+      f->qflx_rootsoi[(size_t)(j - 1) * ldc + (c - begc0)] = temp;
+      if (temp < 0.0) f->qflx_phs_neg[c - begc0] = f->qflx_phs_neg[c - begc0] + temp;
+    }
+  }
+  return 0;
+}

@@ -11,14 +11,17 @@
 #include "oracle.h"
 
 int oracle_step_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump_t* clumps,
-                       const ctsm_soiltemperature_fields_t* ft, const ctsm_soilwater_fields_t* fw, int which) {
+                       const ctsm_soiltemperature_fields_t* ft, const ctsm_soilwater_fields_t* fw,
+                       const ctsm_canopyfluxes_fields_t* fc, int which) {
   int rc_all = 0;
 #pragma omp parallel for schedule(dynamic, 1)
   for (int nc = 0; nc < nclumps; ++nc) {
     const oracle_clump_t* k = &clumps[nc];
     ctsm_status_t st;
     int rc = 0;
-    if ((which & 1) && ft)
+    if ((which & 4) && fc)
+      rc = oracle_canopyfluxes(prm, &k->bounds, k->num_exposedvegp, k->filter_exposedvegp, fc, &st);
+    if (!rc && (which & 1) && ft)
       rc = oracle_soiltemperature(prm, &k->bounds, k->num_nolakep, k->filter_nolakep, k->num_nolakec,
                                   k->filter_nolakec, ft, &st);
     if (!rc && (which & 2) && fw)

@@ -140,6 +140,12 @@ static void getvegwp(const cf_ctx* x, int p, int c, double* xv, double gb_mol, d
 
 static const double tol_lai = .001;
 
+/* workload statistics for DESIGN.md / tools/phs_stats.py: [0] calcstress calls, [1] Newton iterations,
+ * [2] calcstress calls that hit itmax, [3] ci_func_PHS calls, [4] brent_PHS calls, [5] hybrid outer passes */
+long long oracle_phs_counters[8];
+static long long* per_patch_newton = 0;   /* optional (begp0:endp0) accumulator */
+void oracle_phs_set_patch_counter(long long* p) { per_patch_newton = p; }
+
 /* spacF :4898-4976 */
 static void spacF(const cf_ctx* x, int p, int c, const double* xv, double* f, double qflx_sun, double qflx_sha) {
   const double grav1 = P1(htop, p) * 1000.0;
@@ -256,8 +262,12 @@ static void calcstress(cf_ctx* x, int p, int c, double* xv, double* bsun, double
   getqflx(x, p, c, gb_mol, &gs0sun, &gs0sha, &qflx_sun, &qflx_sha, qsatl, qaf, 1);
   if ((laisun > tol_lai || laisha > tol_lai) && (qflx_sun > 0.0 || qflx_sha > 0.0)) {
     iter = 0;
+    oracle_phs_counters[0]++;
     for (;;) {
       iter = iter + 1;
+      oracle_phs_counters[1]++;
+      if (per_patch_newton) per_patch_newton[p - x->begp0]++;
+      if (iter > itmax) oracle_phs_counters[2]++;
       spacF(x, p, c, xv, f, qflx_sun, qflx_sha);
       if (sqrt(f[1] * f[1] + f[2] * f[2] + f[3] * f[3] + f[4] * f[4]) < tolf * (qflx_sun + qflx_sha)) { flag = 0; break; }
       if (iter > itmax) { flag = 0; break; }
@@ -350,6 +360,7 @@ static void ci_func_PHS(cf_ctx* x, const ci_args* a, double* xv, double cisun, d
   const double medint = PFT(pft_medlynintercept, ivt), medslope = PFT(pft_medlynslope, ivt);
   const double bbb = x->bbb[p - x->begp0], mbb = x->mbb[p - x->begp0];
 
+  oracle_phs_counters[3]++;
   if (bflag) calcstress(x, p, c, xv, bsun, bsha, gb_mol, gs0sun, gs0sha, a->qsatl, a->qaf);
 
   if (P1(c3flag, p)) {
@@ -475,6 +486,7 @@ static void brent_PHS(cf_ctx* x, const ci_args* ca, double* xsun, double x1sun, 
   for (int ph = 1; ph <= 2; ++ph)
     if ((fa[ph] > 0.0 && fb[ph] > 0.0) || (fa[ph] < 0.0 && fb[ph] < 0.0)) fail(x, CTSM_ERR_BRENT, ca->p);
   for (int ph = 1; ph <= 2; ++ph) { c[ph] = b[ph]; fc[ph] = fb[ph]; }
+  oracle_phs_counters[4]++;
   iter = 0;
   for (;;) {
     if (iter == itmax) break;
@@ -560,6 +572,7 @@ static void hybrid_PHS(cf_ctx* x, const ci_args* ca, double* x0sun, double* x0sh
   for (;;) {
     for (int i = 1; i <= 4; ++i) xv[i] = P2(vegwp, p, i, 1);
     *iter1 = *iter1 + 1;
+    oracle_phs_counters[5]++;
     *iter2 = 0;
     *x0sun = fmax(0.1, x1sun);
     x1sun = 0.99 * x1sun;
