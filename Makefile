@@ -5,12 +5,12 @@
 # multiply-add contraction would change results.
 NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS := -O3 -std=c++17 -lineinfo -fmad=false $(ARCH) -Xcompiler -fPIC -ccbin /usr/bin/g++
+NVCCFLAGS := -O3 -std=c++17 -lineinfo -fmad=false $(ARCH) -Xcompiler -fPIC -ccbin /usr/bin/g++ $(EXTRA)
 CSRC      := ctsm_b200/csrc
 CU        := $(wildcard $(CSRC)/*.cu)
 OBJ       := $(CU:.cu=.o)
 HDR       := $(wildcard $(CSRC)/*.cuh) include/ctsm_b200.h include/ctsm_b200_fields.def
-LIB       := ctsm_b200/lib/libctsm_b200.so
+LIB       ?= ctsm_b200/lib/libctsm_b200.so
 
 all: $(LIB) oracle
 

@@ -19,7 +19,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DEF_PATH = os.path.join(ROOT, "include", "ctsm_b200_fields.def")
-LIB_PATH = os.path.join(ROOT, "ctsm_b200", "lib", "libctsm_b200.so")
+LIB_PATH = os.environ.get("CTSM_B200_LIB", os.path.join(ROOT, "ctsm_b200", "lib", "libctsm_b200.so"))
 
 NLEVSNO, NLEVGRND, NLEVSOI, NVEGWCS, NLEVCAN, MXPFT = 12, 25, 20, 4, 1, 78
 

@@ -32,6 +32,7 @@
 // Roofline: FP64 pipe / latency (hundreds of pow/exp/log per ~3 KB of patch traffic), not HBM
 // (SURVEY.md 8d); DESIGN.md section 4 has the algorithmic bytes.
 #include "phs.cuh"
+#include <stdlib.h>
 
 struct CanopyDev {
 #define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) ctype* name;
@@ -46,6 +47,10 @@ namespace {
 using phs::rgas;
 using phs::tfrz;
 using phs::spval;
+using phs::pw;
+using phs::pw2;
+using phs::dexp;
+using phs::dlog;
 constexpr double rpi = 3.14159265358979323846;
 constexpr double sb = 5.67e-8, cpair = 1.00464e3, hvap = 2.501e6, vkc = 0.4, grav = 9.80616;
 constexpr double denice = 0.917e3, denh2o = 1.000e3, c_to_b = 2.0, tlsai_crit = 2.0, alpha_aero = 1.0;
@@ -75,20 +80,44 @@ struct Geo {   // index bases / leading dimensions
   int begp, endp, begc, endc;   // call bounds
 };
 
-struct Lists {          // device-side active lists
-  int* counts;          // [2*(itmax+3)]: per pass {night count, day count}
-  int* list_a;          // ping
+// Active lists.  NBIN = 2 x NCLASS bins: night patches in bins 0..NCLASS-1, day patches in the rest, each split by
+// the work the patch did in its previous pass (Newton iterations + ci evaluations; the work of consecutive passes of
+// one patch is strongly correlated), so that the 32 lanes of a warp carry patches of similar cost.  Every bin owns a
+// region of `cap` entries; thread slots are padded to whole warps per bin.
+#define NCLASS 4
+#define NBIN (2 * NCLASS)
+struct Lists {
+  int* counts;          // [npass + 2][NBIN]
+  int* list_a;          // ping: [NBIN][cap]
   int* list_b;          // pong
   int* colflag;         // per column (alloc-based): owns an exposed-veg patch in this call
-  int n_warn_slot;
+  int cap;
 };
+__device__ __forceinline__ int work_class(int work) {
+#ifdef NO_COST_BINS
+  return 0;
+#else
+  return work < 8 ? 0 : work < 24 ? 1 : work < 72 ? 2 : 3;
+#endif
+}
+
+// warp-aggregated append of `item` to bin `bin` of list (counts row `row`)
+__device__ __forceinline__ void bin_append(const Lists& L, int* list, int row, int bin, int item, unsigned group) {
+  const unsigned peers = __match_any_sync(group, bin);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(peers) - 1;
+  int b0 = 0;
+  if (lane == leader) b0 = atomicAdd(&L.counts[row * NBIN + bin], __popc(peers));
+  b0 = __shfl_sync(peers, b0, leader);
+  list[(size_t)bin * L.cap + b0 + __popc(peers & ((1u << lane) - 1))] = item;
+}
 
 __device__ __forceinline__ double pow4(double t) { const double t2 = t * t; return t2 * t2; }
 __device__ __forceinline__ double pow3(double t) { return (t * t) * t; }
 
 // QSatMod.F90:61-127
 struct QS { double qs, es, qsdT; };
-__device__ __forceinline__ QS qsat(double T, double p, bool deriv) {
+__device__ __noinline__ QS qsat(double T, double p, bool deriv) {
   QS o;
   const double td = fmin(100.0, fmax(-75.0, T - tfrz));
   double es;
@@ -116,44 +145,44 @@ __device__ __forceinline__ QS qsat(double T, double p, bool deriv) {
 }
 
 // FrictionVelocityMod.F90:1120-1155
-__device__ __forceinline__ double stab1(double zeta) {
+__device__ __noinline__ double stab1(double zeta) {
   const double chik2 = sqrt(1.0 - 16.0 * zeta);
   const double chik = sqrt(chik2);
-  return 2.0 * log((1.0 + chik) * 0.5) + log((1.0 + chik2) * 0.5) - 2.0 * atan(chik) + rpi * 0.5;
+  return 2.0 * dlog((1.0 + chik) * 0.5) + dlog((1.0 + chik2) * 0.5) - 2.0 * atan(chik) + rpi * 0.5;
 }
-__device__ __forceinline__ double stab2(double zeta) {
+__device__ __noinline__ double stab2(double zeta) {
   const double chik2 = sqrt(1.0 - 16.0 * zeta);
-  return 2.0 * log((1.0 + chik2) * 0.5);
+  return 2.0 * dlog((1.0 + chik2) * 0.5);
 }
 // the four-regime log-law denominator shared by ustar / u10 (momentum) ...
-__device__ __forceinline__ double prof_m(double zldis, double zeta, double obu, double z0) {
+__device__ __noinline__ double prof_m(double zldis, double zeta, double obu, double z0) {
   const double zetam = 1.574;
   if (zeta < -zetam)
-    return log(-zetam * obu / z0) - stab1(-zetam) + stab1(z0 / obu) + 1.14 * (pow(-zeta, 0.333) - pow(zetam, 0.333));
-  if (zeta < 0.0) return log(zldis / z0) - stab1(zeta) + stab1(z0 / obu);
-  if (zeta <= 1.0) return log(zldis / z0) + 5.0 * zeta - 5.0 * z0 / obu;
-  return log(obu / z0) + 5.0 - 5.0 * z0 / obu + (5.0 * log(zeta) + zeta - 1.0);
+    return dlog(-zetam * obu / z0) - stab1(-zetam) + stab1(z0 / obu) + 1.14 * (pw(-zeta, 0.333) - pw(zetam, 0.333));
+  if (zeta < 0.0) return dlog(zldis / z0) - stab1(zeta) + stab1(z0 / obu);
+  if (zeta <= 1.0) return dlog(zldis / z0) + 5.0 * zeta - 5.0 * z0 / obu;
+  return dlog(obu / z0) + 5.0 - 5.0 * z0 / obu + (5.0 * dlog(zeta) + zeta - 1.0);
 }
 // ... and by temp1 / temp2 / temp12m / temp22m (scalars)
-__device__ __forceinline__ double prof_h(double zldis, double zeta, double obu, double z0) {
+__device__ __noinline__ double prof_h(double zldis, double zeta, double obu, double z0) {
   const double zetat = 0.465;
   if (zeta < -zetat)
-    return log(-zetat * obu / z0) - stab2(-zetat) + stab2(z0 / obu) + 0.8 * (pow(zetat, -0.333) - pow(-zeta, -0.333));
-  if (zeta < 0.0) return log(zldis / z0) - stab2(zeta) + stab2(z0 / obu);
-  if (zeta <= 1.0) return log(zldis / z0) + 5.0 * zeta - 5.0 * z0 / obu;
-  return log(obu / z0) + 5.0 - 5.0 * z0 / obu + (5.0 * log(zeta) + zeta - 1.0);
+    return dlog(-zetat * obu / z0) - stab2(-zetat) + stab2(z0 / obu) + 0.8 * (pw(zetat, -0.333) - pw(-zeta, -0.333));
+  if (zeta < 0.0) return dlog(zldis / z0) - stab2(zeta) + stab2(z0 / obu);
+  if (zeta <= 1.0) return dlog(zldis / z0) + 5.0 * zeta - 5.0 * z0 / obu;
+  return dlog(obu / z0) + 5.0 - 5.0 * z0 / obu + (5.0 * dlog(zeta) + zeta - 1.0);
 }
 
 struct FricOut { double ustar, temp1, temp2, temp12m, temp22m, fm, vds, u10_clm, u10; };
 // FrictionVelocity :842-1113 for one patch
-__device__ __forceinline__ FricOut friction_velocity(double hgt_u, double hgt_t, double hgt_q, double displa, double z0m,
+__device__ __noinline__ FricOut friction_velocity(double hgt_u, double hgt_t, double hgt_q, double displa, double z0m,
                                                      double z0h, double z0q, double obu, int iter, double ur, double um,
                                                      double fm_prev) {
   FricOut o;
   double zldis = hgt_u - displa;
   double zeta = zldis / obu;
   o.ustar = vkc * um / prof_m(zldis, zeta, obu, z0m);
-  if (zeta < 0.0) o.vds = 2.e-3 * o.ustar * (1.0 + pow(300.0 / (-obu), 0.666));
+  if (zeta < 0.0) o.vds = 2.e-3 * o.ustar * (1.0 + pw(300.0 / (-obu), 0.666));
   else o.vds = 2.e-3 * o.ustar;
   if (zldis - z0m <= 10.0) o.u10_clm = um;
   else o.u10_clm = um - (o.ustar / vkc * prof_m(zldis, zeta, obu, 10.0 + z0m));
@@ -181,9 +210,9 @@ __device__ __forceinline__ FricOut friction_velocity(double hgt_u, double hgt_t,
   zeta = zldis / obu;
   double fmnew;
   if (fmin(zeta, 1.0) < 0.0) {
-    const double t1 = pow(1.0 - 16.0 * fmin(zeta, 1.0), 0.25);
-    const double t2 = log((1.0 + t1 * t1) / 2.0);
-    const double t3 = log((1.0 + t1) / 2.0);
+    const double t1 = pw(1.0 - 16.0 * fmin(zeta, 1.0), 0.25);
+    const double t2 = dlog((1.0 + t1 * t1) / 2.0);
+    const double t3 = dlog((1.0 + t1) / 2.0);
     fmnew = 2.0 * t3 + t2 - 2.0 * atan(t1) + 1.5707963;
   } else {
     fmnew = -5.0 * fmin(zeta, 1.0);
@@ -193,22 +222,22 @@ __device__ __forceinline__ FricOut friction_velocity(double hgt_u, double hgt_t,
   if (zeta == 0.0) zeta10 = 0.0;
   double fm10;
   if (zeta10 < 0.0) {
-    const double t1 = pow(1.0 - 16.0 * zeta10, 0.25);
-    const double t2 = log((1.0 + t1 * t1) / 2.0);
-    const double t3 = log((1.0 + t1) / 2.0);
+    const double t1 = pw(1.0 - 16.0 * zeta10, 0.25);
+    const double t2 = dlog((1.0 + t1 * t1) / 2.0);
+    const double t3 = dlog((1.0 + t1) / 2.0);
     fm10 = 2.0 * t3 + t2 - 2.0 * atan(t1) + 1.5707963;
   } else {
     fm10 = -5.0 * zeta10;
   }
-  const double t4 = log(fmax(1.0, hgt_u / 10.0));
+  const double t4 = dlog(fmax(1.0, hgt_u / 10.0));
   o.u10 = ur - o.ustar / vkc * (t4 - o.fm + fm10);
   return o;
 }
 
 // statement functions PhotosynthesisMod.F90:2918-2920
-__device__ __forceinline__ double ft(double tl, double ha) { return exp(ha / (rgas * 1.e-3 * (tfrz + 25.0)) * (1.0 - (tfrz + 25.0) / tl)); }
-__device__ __forceinline__ double fth(double tl, double hd, double se, double sc) { return sc / (1.0 + exp((-hd + se * tl) / (rgas * 1.e-3 * tl))); }
-__device__ __forceinline__ double fth25(double hd, double se) { return 1.0 + exp((-hd + se * (tfrz + 25.0)) / (rgas * 1.e-3 * (tfrz + 25.0))); }
+__device__ __forceinline__ double ft(double tl, double ha) { return dexp(ha / (rgas * 1.e-3 * (tfrz + 25.0)) * (1.0 - (tfrz + 25.0) / tl)); }
+__device__ __forceinline__ double fth(double tl, double hd, double se, double sc) { return sc / (1.0 + dexp((-hd + se * tl) / (rgas * 1.e-3 * tl))); }
+__device__ __forceinline__ double fth25(double hd, double se) { return 1.0 + dexp((-hd + se * (tfrz + 25.0)) / (rgas * 1.e-3 * (tfrz + 25.0))); }
 
 #define PF(name) f.name[pp]
 #define PF2(name, j0) f.name[(size_t)(j0) * g.ldp + pp]           /* j0 = level - lower bound */
@@ -307,7 +336,7 @@ canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int* __restr
       if (!(liqvol <= 0.0 || CF2(t_soisno, j - SNOSOI_LO) <= tfrz - 2.0)) {
         const double effp = CF2(eff_porosity, j - 1);
         const double s_node = fmax(liqvol / effp, 0.01);
-        double smp_node = -CF2(sucsat, j - 1) * pow(s_node, -CF2(bsw, j - 1));
+        double smp_node = -CF2(sucsat, j - 1) * pw(s_node, -CF2(bsw, j - 1));
         smp_node = fmax(smpsc, smp_node);
         const double rresis = fmin((effp / CF2(watsat, j - 1)) * (smp_node - smpsc) / (smpso - smpsc), 1.0);
         PF2(rresis, j - 1) = rresis;
@@ -327,23 +356,23 @@ canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int* __restr
   double displa, z0mv;
   if (prm.z0param_method == 1) {
     const double lt = fmin(elai + esai, tlsai_crit);
-    const double egvf = (1.0 - alpha_aero * exp(-lt)) / (1.0 - alpha_aero * exp(-tlsai_crit));
+    const double egvf = (1.0 - alpha_aero * dexp(-lt)) / (1.0 - alpha_aero * dexp(-tlsai_crit));
     displa = egvf * PF(displa);
-    z0mv = exp(egvf * log(PF(z0mv)) + (1.0 - egvf) * log(CF(z0mg)));
+    z0mv = dexp(egvf * dlog(PF(z0mv)) + (1.0 - egvf) * dlog(CF(z0mg)));
   } else {
     double lt = fmax(1.e-5, elai + esai);
-    displa = htop * (1.0 - (1.0 - exp(-pow(cd1_param * lt, 0.5))) / pow(cd1_param * lt, 0.5));
+    displa = htop * (1.0 - (1.0 - dexp(-pw(cd1_param * lt, 0.5))) / pw(cd1_param * lt, 0.5));
     lt = fmin(lt, f.pft_z0v_LAImax[ivt]);
     const double zc = f.pft_z0v_c[ivt], cw = f.pft_z0v_cw[ivt];
-    const double ini = pow(f.pft_z0v_Cs[ivt] + f.pft_z0v_Cr[ivt] * lt * 0.5, -0.5) * zc * lt * 0.25;
+    const double ini = pw(f.pft_z0v_Cs[ivt] + f.pft_z0v_Cr[ivt] * lt * 0.5, -0.5) * zc * lt * 0.25;
     double U = ini, delt = 2.0;
     while (delt > 1.e-4) {
       const double prev = U;
-      U = ini * exp(prev);
+      U = ini * dexp(prev);
       delt = fabs(U - prev);
     }
     U = 4.0 * U / lt / zc;
-    z0mv = htop * (1.0 - displa / htop) * exp(-vkc * U + log(cw) - 1.0 + 1.0 / cw);
+    z0mv = htop * (1.0 - displa / htop) * dexp(-vkc * U + dlog(cw) - 1.0 + 1.0 / cw);
   }
   PF(displa) = displa; PF(z0mv) = z0mv; PF(z0hv) = z0mv; PF(z0qv) = z0mv;
   const double hgt_u = f.forc_hgt_u[gg] + z0mv + displa;
@@ -383,10 +412,10 @@ canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int* __restr
     const double rib = grav * zldis * dthv / (thv * um * um);
     double zeta;
     if (rib >= 0.0) {
-      zeta = rib * log(zldis / z0mv) / (1.0 - 5.0 * fmin(rib, 0.19));
+      zeta = rib * dlog(zldis / z0mv) / (1.0 - 5.0 * fmin(rib, 0.19));
       zeta = fmin(prm.zetamaxstable, fmax(zeta, 0.01));
     } else {
-      zeta = rib * log(zldis / z0mv);
+      zeta = rib * dlog(zldis / z0mv);
       zeta = fmax(-100.0, fmin(zeta, -0.01));
     }
     PF(um) = um;
@@ -424,43 +453,45 @@ canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int* __restr
     }
   }
 
-  // active list: night patches from the front, day patches from the back
+  // first active list: no work history yet, one night bin and one day bin
   const bool night = (PF2(parsun_z, 0) <= 0.0);
-  const unsigned act = __activemask();
-  const unsigned mnight = __ballot_sync(act, night);
-  const unsigned mine = night ? mnight : (act & ~mnight);
-  const int lane = threadIdx.x & 31;
-  const int leader = __ffs(mine) - 1;
-  int base = 0;
-  if (lane == leader) base = atomicAdd(&L.counts[night ? 0 : 1], __popc(mine));
-  base = __shfl_sync(mine, base, leader);
-  const int rank = __popc(mine & ((1u << lane) - 1));
-  if (night) L.list_a[base + rank] = fi;
-  else L.list_a[fn - 1 - (base + rank)] = fi;
+  bin_append(L, L.list_a, 0, night ? 0 : NCLASS, fi, __activemask());
 }
 
 // ---------------------------------------------------------------------------------------------
 // one ITERATION pass (CanopyFluxesMod.F90:1028-1457) for the still-active patches
 #define ITER_THREADS 64
-__global__ void __launch_bounds__(ITER_THREADS)
-canopy_iter_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef, const int32_t* __restrict__ filterp,
+#ifndef ITER_MINBLOCKS
+#define ITER_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(ITER_THREADS, ITER_MINBLOCKS)
+canopy_iter_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, const int32_t* __restrict__ filterp,
                    double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in, int* __restrict__ list_out,
                    DevStatus* ds) {
   extern __shared__ double shm[];                       // [3][NLEVSOI][ITER_THREADS]
   double* sk = shm + threadIdx.x;
   double* sgv = shm + (size_t)NLEVSOI * ITER_THREADS + threadIdx.x;
   double* ssv = shm + (size_t)2 * NLEVSOI * ITER_THREADS + threadIdx.x;
-  const int n_night = L.counts[2 * itlef], n_day = L.counts[2 * itlef + 1];
-  const int total = n_night + n_day;
+  // thread slots: bins padded to whole warps
+  int off[NBIN + 1];
+  off[0] = 0;
+#pragma unroll
+  for (int b = 0; b < NBIN; ++b) off[b + 1] = off[b] + ((L.counts[itlef0 * NBIN + b] + 31) & ~31);
+  const int total = off[NBIN];
   const double dtime = prm.dtime;
   for (int base = blockIdx.x * ITER_THREADS; base < total; base += gridDim.x * ITER_THREADS) {
     const int t = base + threadIdx.x;
-    const bool live = t < total;
-    bool keep = false, night = false;
-    int fi = 0;
+    int bin = 0;
+#pragma unroll
+    for (int b = 1; b < NBIN; ++b) bin += (t >= off[b]) ? 1 : 0;
+    const int idx = t - off[bin];
+    const bool live = idx < L.counts[itlef0 * NBIN + bin];
+    bool keep = false;
+    const bool night = bin < NCLASS;
+    int fi = 0, work = 0;
+    if (live) fi = list_in[(size_t)bin * L.cap + idx];
     if (live) {
-      night = t < n_night;
-      fi = night ? list_in[t] : list_in[fn - 1 - (t - n_night)];
+      const int itlef = itlef0;
       const int pp = filterp[fi] - g.begp0;
       const int cc = PF(column) - g.begc0;
       const int gg = PF(gridcell) - g.begg0;
@@ -492,8 +523,8 @@ canopy_iter_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef, const i
       const double dleaf = f.pft_dleaf[ivt];
       const double cfl = prm.cv / (sqrt(uaf) * sqrt(dleaf));
       const double rb = 1.0 / (cfl * uaf);
-      const double w = exp(-(elai + esai));
-      const double csoilb = vkc / (prm.a_coef * pow(CF(z0mg) * uaf / nu_param, prm.a_exp));
+      const double w = dexp(-(elai + esai));
+      const double csoilb = vkc / (prm.a_coef * pw(CF(z0mg) * uaf / nu_param, prm.a_exp));
       const double ri = (grav * htop * (taf - t_grnd)) / (taf * (uaf * uaf));
       double csoilcn;
       if (prm.use_undercanopy_stability && (taf - t_grnd) > 0.0) {
@@ -529,7 +560,7 @@ canopy_iter_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef, const i
       P.qsatl = qsatl; P.qaf = qaf;
       const double gb_mol = (1.0 / rb) * cfm;
       P.gb_mol = gb_mol;
-      P.sk = sk; P.sg = sgv; P.ss = ssv; P.stride = ITER_THREADS;
+      P.sk = sk; P.sg = sgv; P.ss = ssv; P.stride = ITER_THREADS; P.work = &work;
       {
         double ksum = 0.0, ksmp = 0.0, ksmpg = 0.0, smpg = 0.0;
         for (int j = 0; j < NLEVSOI; ++j) {
@@ -580,7 +611,7 @@ canopy_iter_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef, const i
         const bool luna = prm.use_luna && c3 && crop == 0.0;
         const double vcmx25 = PF2(vcmx25_z, 0);
         const double lmrc = fth25(prm.lmrhd, prm.lmrse);
-        const double tl_fac = fmin((0.2 * exp(3.218 * PF2(tlai_z, 0))), 1.0);
+        const double tl_fac = fmin((0.2 * dexp(3.218 * PF2(tlai_z, 0))), 1.0);
 #pragma unroll
         for (int s = 0; s < 2; ++s) {                  // :3350-3374
           double lmr25 = lmr25top * ns[s];
@@ -589,8 +620,8 @@ canopy_iter_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef, const i
           if (c3) {
             lmr = lmr25 * ft(t_veg, prm.lmrha) * fth(t_veg, prm.lmrhd, prm.lmrse, lmrc);
           } else {
-            lmr = lmr25 * pow(2.0, (t_veg - (tfrz + 25.0)) / 10.0);
-            lmr = lmr / (1.0 + exp(1.3 * (t_veg - (tfrz + 55.0))));
+            lmr = lmr25 * pw2((t_veg - (tfrz + 25.0)) / 10.0);
+            lmr = lmr / (1.0 + dexp(1.3 * (t_veg - (tfrz + 55.0))));
           }
           Lf.lmr[s] = lmr * tl_fac;
         }
@@ -617,7 +648,7 @@ canopy_iter_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef, const i
           const double fv_ = ft(t_veg, prm.vcmaxha) , hv_ = fth(t_veg, prm.vcmaxhd, vcmaxse, vcmaxc);
           const double fj_ = ft(t_veg, prm.jmaxha), hj_ = fth(t_veg, prm.jmaxhd, jmaxse, jmaxc);
           const double ftp = ft(t_veg, prm.tpuha), htp = fth(t_veg, prm.tpuhd, tpuse, tpuc);
-          const double q10 = pow(2.0, (t_veg - (tfrz + 25.0)) / 10.0);
+          const double q10 = pw2((t_veg - (tfrz + 25.0)) / 10.0);
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
             Lf.vcmax[s] = v25[s] * fv_ * hv_;
@@ -625,8 +656,8 @@ canopy_iter_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef, const i
             Lf.tpu[s] = t25[s] * ftp * htp;
             if (!c3) {
               double v = v25[s] * q10;
-              v = v / (1.0 + exp(0.2 * ((tfrz + 15.0) - t_veg)));
-              v = v / (1.0 + exp(0.3 * (t_veg - (tfrz + 40.0))));
+              v = v / (1.0 + dexp(0.2 * ((tfrz + 15.0) - t_veg)));
+              v = v / (1.0 + dexp(0.3 * (t_veg - (tfrz + 40.0))));
               Lf.vcmax[s] = v;
             }
             Lf.kp[s] = (kp25top * ns[s]) * q10;
@@ -774,7 +805,7 @@ canopy_iter_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef, const i
       const double wtlq = fvn * (elai + esai) / rb * rpp;
       const double fsno_dl = CF(snow_depth) / prm.z_dl;
       const double elai_dl = prm.lai_dl * (1.0 - fmin(fsno_dl, 1.0));
-      const double rdl = (1.0 - exp(-elai_dl)) / (0.004 * uaf);
+      const double rdl = (1.0 - dexp(-elai_dl)) / (0.004 * uaf);
       double wtgq = WS(W_WTGQ);
       if (WS(W_DELQ) < 0.0) {
         wtgq = fvn / (raw_b + rdl);
@@ -844,7 +875,7 @@ canopy_iter_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef, const i
         zeta = fmax(-100.0, fmin(zeta, -0.01));
         double wc;
         if (ustar * thvstar > 0.0) { wc = 0.0; atomicAdd(&ds->n_warnings, 1); }
-        else wc = 1.0 * pow(-grav * ustar * thvstar * 1000.0 / thv, 0.333);
+        else wc = 1.0 * pw(-grav * ustar * thvstar * 1000.0 / thv, 0.333);
         um = sqrt(ur * ur + wc * wc);
       }
       obu = zldis_u / zeta;
@@ -871,21 +902,10 @@ canopy_iter_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef, const i
         keep = !(det < 0.01 && dele < 0.1);
       }
     }
-    // survivors -> next list (warp-aggregated)
+    // survivors -> bins of the next pass
     const unsigned act = __activemask();
     const unsigned mk = __ballot_sync(act, keep);
-    if (keep) {
-      const unsigned mnight = __ballot_sync(mk, night);
-      const unsigned mine = night ? mnight : (mk & ~mnight);
-      const int lane = threadIdx.x & 31;
-      const int leader = __ffs(mine) - 1;
-      int b0 = 0;
-      if (lane == leader) b0 = atomicAdd(&L.counts[2 * (itlef + 1) + (night ? 0 : 1)], __popc(mine));
-      b0 = __shfl_sync(mine, b0, leader);
-      const int rank = __popc(mine & ((1u << lane) - 1));
-      if (night) list_out[b0 + rank] = fi;
-      else list_out[fn - 1 - (b0 + rank)] = fi;
-    }
+    if (keep) bin_append(L, list_out, itlef0 + 1, (night ? 0 : NCLASS) + work_class(work), fi, mk);
   }
 }
 
@@ -1113,23 +1133,23 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   const int npb = g.endp - g.begp + 1, ncb = g.endc - g.begc + 1;
   if (npb <= 0) return finish_call(ctx, mem, st);
 
-  // workspace: [W_NSLOT][wstride] doubles + int scratch {fpos[ldp], colflag[ldc], list_a[fn], list_b[fn], counts}
+  // workspace: [W_NSLOT][wstride] doubles + int scratch {fpos[ldp], colflag[ldc], list_a/list_b[NBIN][fn], counts}
   const int wstride = (fn + 31) & ~31;
   const int npass = p.itmax_canopy_fluxes + 1;
-  const size_t n_counts = 2 * (size_t)(npass + 2);
+  const size_t n_counts = (size_t)NBIN * (size_t)(npass + 2);
   int rc = arena_reserve(ctx->arena_scratch, sizeof(double) * (size_t)W_NSLOT * (size_t)(wstride > 0 ? wstride : 32));
   if (rc) return rc;
-  rc = reserve_ints(ctx->arena_ints, (size_t)g.ldp + (size_t)g.ldc + 2 * (size_t)fn + n_counts + 64);
+  rc = reserve_ints(ctx->arena_ints, (size_t)g.ldp + (size_t)g.ldc + 2 * (size_t)NBIN * (size_t)fn + n_counts + 64);
   if (rc) return rc;
   double* ws = (double*)ctx->arena_scratch.p;
   int* ip = (int*)ctx->arena_ints.p;
   int* fpos = ip; ip += g.ldp;
   Lists L;
   L.colflag = ip; ip += g.ldc;
-  L.list_a = ip; ip += fn;
-  L.list_b = ip; ip += fn;
+  L.list_a = ip; ip += (size_t)NBIN * fn;
+  L.list_b = ip; ip += (size_t)NBIN * fn;
   L.counts = ip;
-  L.n_warn_slot = 0;
+  L.cap = fn;
   cudaStream_t s = ctx->stream;
   CUDA_TRY(cudaMemsetAsync(fpos, 0xff, sizeof(int) * (size_t)g.ldp, s));
   CUDA_TRY(cudaMemsetAsync(L.colflag, 0, sizeof(int) * (size_t)g.ldc, s));
@@ -1143,10 +1163,13 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   ctx->launches++;
   if (fn > 0) {
     const size_t shbytes = sizeof(double) * 3 * NLEVSOI * ITER_THREADS;
-    int sms = 148;
+    int sms = 148, occ = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    const int gridmax = sms * 8;
-    int grid = grid_for(fn, ITER_THREADS);
+    CUDA_TRY(cudaFuncSetAttribute(canopy_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shbytes));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, canopy_iter_kernel, ITER_THREADS, shbytes);
+    if (occ < 1) occ = 1;
+    const int gridmax = sms * occ * 2;                        // persistent grid: two waves of resident blocks
+    int grid = grid_for(fn + 32 * NBIN, ITER_THREADS);
     if (grid > gridmax) grid = gridmax;
     int *lin = L.list_a, *lout = L.list_b;
     for (int itlef = 0; itlef < npass; ++itlef) {

@@ -31,6 +31,28 @@ constexpr double tol_lai = .001;                     // :4543
 
 enum Seg { SUN = 0, SHA = 1, XYL = 2, ROOT = 3 };
 
+// Powers.  Every pow on this path has a positive base (ratios of potentials, -zeta, saturations), so
+// a**b = exp2(b*log2(a)) holds; libdevice's exp2/log2 (<= 1-2 ulp each) cost about a third of its
+// correctly-rounded-to-1-ulp pow, and the Newton solve of calcstress spends most of its instructions in the
+// eight powers of the Weibull curve.  The result differs from glibc's pow by a few ulp (|b*log2 a| <= ~50),
+// far inside the 1e-10 parity tolerance (tests/test_gpu_canopy.py); -DPHS_LIBM_POW restores pow().
+__device__ __forceinline__ double pw(double a, double b) {
+#ifdef PHS_LIBM_POW
+  return pow(a, b);
+#else
+  return exp2(b * log2(a));
+#endif
+}
+__device__ __forceinline__ double pw2(double b) {   // 2**b
+#ifdef PHS_LIBM_POW
+  return pow(2.0, b);
+#else
+  return exp2(b);
+#endif
+}
+__device__ __forceinline__ double dexp(double a) { return exp(a); }
+__device__ __forceinline__ double dlog(double a) { return log(a); }
+
 struct Quad { double r1, r2; };
 // quadraticMod.F90:17-74; *bad is set where the reference calls endrun
 __device__ __forceinline__ Quad quadratic(double a, double b, double c, bool* bad) {
@@ -50,10 +72,11 @@ __device__ __forceinline__ Quad quadratic(double a, double b, double c, bool* ba
 
 struct Weibull { double v, d; };   // plc and d1plc at one potential
 // plc :5186-5187, d1plc :5218-5220 (same pow / exp2 feeds both)
-__device__ __forceinline__ Weibull weibull(double x, double psi50, double ck, bool want_d) {
+__device__ __noinline__ Weibull weibull(double x, double psi50, double ck, bool want_d) {
   Weibull w;
-  const double t = pow(x / psi50, ck);
-  const double e = pow(2.0, -t);
+  const double r = x / psi50;
+  const double t = (r > 0.0) ? pw(r, ck) : pow(r, ck);
+  const double e = pw2(-t);
   w.d = want_d ? (-ck * 0.6931471805599453 * e * t / x) : 0.0;   // log(2._r8)
   w.v = (e < 0.005) ? 0.0 : e;
   return w;
@@ -74,6 +97,7 @@ struct PhsPatch {
   const double* sg;                      // shared: grav2
   const double* ss;                      // shared: smp
   int stride;
+  int* work;                             // per-pass work estimate of this patch (drives the cost bins of the next pass)
   __device__ __forceinline__ double K(int j) const { return sk[j * stride]; }
   __device__ __forceinline__ double G(int j) const { return sg[j * stride]; }
   __device__ __forceinline__ double S(int j) const { return ss[j * stride]; }
@@ -104,7 +128,7 @@ __device__ __forceinline__ void gs_from_qflx(const PhsPatch& P, double qsun, dou
 }
 
 // getvegwp :4979-5077.  x = {sun, sha, xyl, root}; returns soilflux.
-__device__ __forceinline__ double getvegwp(const PhsPatch& P, double* x, double gs_sun, double gs_sha) {
+__device__ __noinline__ double getvegwp(const PhsPatch& P, double* x, double gs_sun, double gs_sha) {
   double qsun, qsha;
   qflx_from_gs(P, gs_sun, gs_sha, qsun, qsha);
   const double grav1 = 1000.0 * P.htop;
@@ -143,6 +167,7 @@ __device__ __noinline__ Stress calcstress(const PhsPatch& P, double* x, double g
     const double tk = P.tsai * P.kmax[XYL] / P.htop;
     flag = false;
     for (int iter = 1;; ++iter) {
+      *P.work += 2;
       // segment conductance attenuation at x (shared by spacF :4951-4954 and spacA :4790-4799)
       const Weibull w1 = weibull(x[SUN], P.psi50[SUN], P.ck[SUN], true);
       const Weibull w2 = weibull(x[SHA], P.psi50[SHA], P.ck[SHA], true);
@@ -268,6 +293,7 @@ __device__ __noinline__ void ci_func(const PhsPatch& P, const Leaf& L, double ci
                                      double& fsun, double& fsha, double& gs_sun, double& gs_sha, CiOut& o, bool* bad) {
   const double ci[2] = {cisun, cisha};
   const double b[2] = {bsun, bsha};
+  *P.work += 1;
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     if (L.c3) {
@@ -377,7 +403,7 @@ __device__ __noinline__ void brent(const PhsPatch& P, const Leaf& L, double& xsu
 struct HybridOut { double bsun, bsha, gs_sun, gs_sha, tran; double x[4]; };
 
 // hybrid_PHS :3815-4064.  vegwp_in = canopystate_inst%vegwp_patch(p,:) at entry.
-__device__ __forceinline__ HybridOut hybrid(const PhsPatch& P, const Leaf& L, const double* vegwp_in, double ci0, CiOut& o,
+__device__ __noinline__ HybridOut hybrid(const PhsPatch& P, const Leaf& L, const double* vegwp_in, double ci0, CiOut& o,
                                             bool* bad, bool* notbracketed) {
   HybridOut h;
   double x[4];

@@ -56,6 +56,33 @@ def make_clumps(sg, nclumps):
     return arr, keep
 
 
+def clump_for_gridcells(sg, g0, g1):
+    """One clump covering the contiguous gridcell range [g0, g1] (1-based, inclusive)."""
+    import numpy as np
+    arr = (Clump * 1)()
+    keep = []
+    cols = np.nonzero((sg.col_gridcell >= g0) & (sg.col_gridcell <= g1))[0]
+    b = sg.bounds.copy()
+    b.begg, b.endg = g0, g1
+    b.begc, b.endc = int(cols[0]) + 1, int(cols[-1]) + 1
+    b.begl, b.endl = b.begc, b.endc
+    b.begp, b.endp = int(sg.col_patchi[cols[0]]), int(sg.col_patchf[cols[-1]])
+    b.level, b.clump_index = 2, 1
+    arr[0].bounds = b
+    for name, lo, hi in (("nolakep", b.begp, b.endp), ("nolakec", b.begc, b.endc),
+                         ("hydrologyc", b.begc, b.endc), ("exposedvegp", b.begp, b.endp)):
+        f = sg.filters.get(name)
+        sub = np.ascontiguousarray(f[(f >= lo) & (f <= hi)]) if f is not None else np.zeros(0, dtype=np.int32)
+        if len(sub) == 0:
+            sub = np.zeros(1, dtype=np.int32); n = 0
+        else:
+            n = len(sub)
+        keep.append(sub)
+        setattr(arr[0], "num_" + name, n)
+        setattr(arr[0], "filter_" + name, abi.i32p(sub))
+    return arr, keep
+
+
 def build(force: bool = False) -> str:
     srcs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(".c") or f.endswith(".h")]
     srcs += [os.path.join(HERE, "..", "include", f) for f in ("ctsm_b200.h", "ctsm_b200_fields.def")]

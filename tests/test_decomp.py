@@ -1,0 +1,100 @@
+"""Clump decomposition (decompInitMod.F90:96-161) and the world_size-2 gloo path of the multi-GPU layout:
+every gridcell is owned by exactly one rank, and running the oracle step per rank on its own clumps gives
+bit-identical results to the undecomposed run (the reference's ERP/PEM invariant)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from ctsm_b200 import decomp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("numg,npes,cpp", [(5500, 8, 1), (21000, 8, 4), (100, 2, 3), (7, 2, 2), (336000, 8, 16)])
+def test_partition_is_exact(numg, npes, cpp):
+    seen = np.zeros(numg + 1, dtype=np.int32)
+    for r in range(npes):
+        for cells in decomp.rank_gridcells(numg, npes, cpp, r):
+            assert np.all(np.diff(cells) > 0)
+            seen[cells] += 1
+    assert np.all(seen[1:] == 1)
+    # gridcells are dealt in nsegspc segments per clump when there are enough of them (:117-123)
+    cid = decomp.gridcell_to_clump(numg, npes * cpp)
+    if numg / (npes * cpp) >= 35:
+        nseg = 1 + int(np.sum(np.diff(cid) != 0))
+        assert abs(nseg - 35 * npes * cpp) <= npes * cpp
+    else:
+        assert np.array_equal(cid, (np.arange(numg) % (npes * cpp)) + 1)
+
+
+def _worker(rank, world, port, q):
+    import ctypes as C
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from ctsm_b200 import abi, synthetic_canopy
+    from oracle import oracle
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    OL = oracle.lib()
+    prm = abi.default_params()
+    sg, S = synthetic_canopy.make_full_case(48, seed=5)            # every rank builds the same global case
+    cells = decomp.rank_gridcells(sg.ngrc, world, 3, rank, nsegspc=2)
+    ft = abi.make_struct("soiltemperature", S, sg.bounds)
+    fw = abi.make_struct("soilwater", S, sg.bounds)
+    fc = abi.make_struct("canopyfluxes", S, sg.bounds)
+    touched = np.zeros(sg.ngrc + 1, dtype=bool)
+    for cl in cells:                                              # contiguous runs of gridcells = segments
+        if len(cl) == 0:
+            continue
+        runs = np.split(cl, np.nonzero(np.diff(cl) != 1)[0] + 1)
+        for run in runs:
+            sub = oracle.clump_for_gridcells(sg, int(run[0]), int(run[-1]))
+            arr, keep = sub
+            assert OL.oracle_step_clumps(C.byref(prm), 1, arr, C.byref(ft), C.byref(fw), C.byref(fc), 7) == 0
+            touched[run] = True
+    import torch
+    mx = torch.tensor([float(np.nanmax(np.where(touched[S["gridcell"]], np.where(S["t_veg"] < 1e30, S["t_veg"], 0), 0)))], dtype=torch.float64)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    got = decomp.reduce_balance_report([float(rank), 2.0], dist)
+    pmask = touched[S["gridcell"]]
+    cmask = touched[sg.col_gridcell]
+    q.put((rank, touched, {k: (S[k][..., pmask] if S[k].shape[-1] == sg.npatch else S[k][..., cmask])
+                           for k in ("t_veg", "num_iter", "t_soisno", "h2osoi_liq", "qflx_tran_veg", "t_grnd")}, float(mx), got))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_run_matches_single(oracle_lib):
+    import ctypes as C
+    import torch.multiprocessing as mp
+    from ctsm_b200 import abi, synthetic_canopy
+    from oracle import oracle
+    world, port = 2, 29000 + (os.getpid() % 2000)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process reference run
+    prm = abi.default_params()
+    sg, S = synthetic_canopy.make_full_case(48, seed=5)
+    arr, keep = oracle.make_clumps(sg, 1)
+    ft = abi.make_struct("soiltemperature", S, sg.bounds)
+    fw = abi.make_struct("soilwater", S, sg.bounds)
+    fc = abi.make_struct("canopyfluxes", S, sg.bounds)
+    assert oracle_lib.oracle_step_clumps(C.byref(prm), 1, arr, C.byref(ft), C.byref(fw), C.byref(fc), 7) == 0
+    owned = np.zeros(sg.ngrc + 1, dtype=np.int32)
+    for rank, touched, fields, mx, got in res:
+        owned += touched
+        pmask, cmask = touched[S["gridcell"]], touched[sg.col_gridcell]
+        for k, v in fields.items():
+            want = S[k][..., pmask] if S[k].shape[-1] == sg.npatch else S[k][..., cmask]
+            assert np.array_equal(v, want), (rank, k)             # bit-identical for any partition
+        assert got == [float(world - 1), 2.0]
+    assert np.all(owned[1:] == 1)
+    assert abs(res[0][3] - res[1][3]) == 0.0
