@@ -21,12 +21,12 @@
 //                          active list with night patches packed from the front and day patches
 //                          from the back so that warps are (almost) homogeneous in the expensive
 //                          day/night branch of PHS;
-//   canopy_iter_kernel     one launch per ITERATION pass, persistent grid (multiple of the 148
-//                          SMs), one thread per still-unconverged patch.  Per-patch iteration
-//                          state lives in a compact structure-of-arrays workspace indexed by
-//                          filter position (coalesced); survivors are appended to the next active
-//                          list with __ballot_sync warp-aggregated atomics (order is irrelevant to
-//                          the numerics: patches are independent);
+//   canopy_step_kernel / canopy_phs_kernel   two launches per ITERATION pass on persistent grids (multiples of the
+//                          148 SMs), one thread per still-unconverged patch (see the comment above the kernels).
+//                          Per-patch iteration state lives in a compact structure-of-arrays workspace indexed by
+//                          filter position (coalesced); survivors are appended to work-class bins of the next pass
+//                          with __match_any_sync warp-aggregated atomics (order is irrelevant to the numerics:
+//                          patches are independent);
 //   canopy_final_kernel    one thread per filter patch: energy-balance check, stem temperature,
 //                          ground fluxes, 2 m diagnostics, longwave, dew update, totals.
 // Roofline: FP64 pipe / latency (hundreds of pow/exp/log per ~3 KB of patch traffic), not HBM
@@ -62,7 +62,7 @@ enum Slot {
   W_AIR, W_BIR, W_CIR, W_SA_LEAF, W_SA_STEM, W_SA_INT, W_FRS, W_CP_LEAF, W_CP_STEM, W_RSTEM, W_DAYL, W_UR, W_ZLDIS,
   W_TL_INI, W_TS_INI, W_DEL, W_EFEB, W_EFE, W_OBUOLD, W_NMOZ, W_FM, W_EL, W_QSATL, W_QSATLDT, W_DELQ, W_DTH, W_DQH,
   W_TLBEF, W_DT_VEG, W_TEMP1, W_TEMP2, W_TEMP12M, W_TEMP22M, W_WTG, W_WTA0, W_WTL0, W_WTSTEM0, W_WTAL, W_WTGQ, W_WTAQ0,
-  W_WTLQ0, W_WTALQ, W_LW_LEAF, W_LW_STEM, W_ERR, W_NSLOT
+  W_WTLQ0, W_WTALQ, W_LW_LEAF, W_LW_STEM, W_ERR, W_JMAX0, W_JMAX1, W_WORK, W_NSLOT
 };
 
 struct CanopyPrm {
@@ -459,319 +459,58 @@ canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
-// one ITERATION pass (CanopyFluxesMod.F90:1028-1457) for the still-active patches
-#define ITER_THREADS 64
-#ifndef ITER_MINBLOCKS
-#define ITER_MINBLOCKS 4
-#endif
-__global__ void __launch_bounds__(ITER_THREADS, ITER_MINBLOCKS)
-canopy_iter_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, const int32_t* __restrict__ filterp,
-                   double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in, int* __restrict__ list_out,
-                   DevStatus* ds) {
-  extern __shared__ double shm[];                       // [3][NLEVSOI][ITER_THREADS]
-  double* sk = shm + threadIdx.x;
-  double* sgv = shm + (size_t)NLEVSOI * ITER_THREADS + threadIdx.x;
-  double* ssv = shm + (size_t)2 * NLEVSOI * ITER_THREADS + threadIdx.x;
+// ITERATION loop (CanopyFluxesMod.F90:1028-1457), split per pass into two kernels with different shapes:
+//   canopy_step_kernel  (uniform work, 128 threads): closes pass k-1 for every patch that ran it (leaf energy balance
+//                       :1174-1435, convergence test :1439-1457) and, for the survivors, opens pass k
+//                       (FrictionVelocity :1033, resistances :1038-1122, temperature-dependent leaf biochemistry
+//                       PhotosynthesisMod.F90:3118-3469); survivors are appended to the work-class bins of pass k;
+//   canopy_phs_kernel   (irregular work, 64 threads + shared root-zone vectors): the ci / plant-water-potential
+//                       solve of pass k (PhotosynthesisMod.F90:3477-3807) for the binned survivors.
+// Everything that crosses a kernel boundary lives in the patch fields it belongs to or in the SoA workspace.
+#define STEP_THREADS 128
+__global__ void __launch_bounds__(STEP_THREADS)
+canopy_step_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, int first, int last,
+                   const int32_t* __restrict__ filterp, double* __restrict__ ws, int wstride, Lists L,
+                   const int* __restrict__ list_in, int* __restrict__ list_out, DevStatus* ds) {
+  const int row = itlef0;
+  const double dtime = prm.dtime;
   // thread slots: bins padded to whole warps
   int off[NBIN + 1];
   off[0] = 0;
 #pragma unroll
-  for (int b = 0; b < NBIN; ++b) off[b + 1] = off[b] + ((L.counts[itlef0 * NBIN + b] + 31) & ~31);
+  for (int b = 0; b < NBIN; ++b) off[b + 1] = off[b] + ((L.counts[row * NBIN + b] + 31) & ~31);
   const int total = off[NBIN];
-  const double dtime = prm.dtime;
-  for (int base = blockIdx.x * ITER_THREADS; base < total; base += gridDim.x * ITER_THREADS) {
+  for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
     const int t = base + threadIdx.x;
     int bin = 0;
 #pragma unroll
     for (int b = 1; b < NBIN; ++b) bin += (t >= off[b]) ? 1 : 0;
     const int idx = t - off[bin];
-    const bool live = idx < L.counts[itlef0 * NBIN + bin];
-    bool keep = false;
+    const bool live = idx < L.counts[row * NBIN + bin];
     const bool night = bin < NCLASS;
-    int fi = 0, work = 0;
+    int fi = 0;
     if (live) fi = list_in[(size_t)bin * L.cap + idx];
+    bool keep = false;
     if (live) {
-      const int itlef = itlef0;
       const int pp = filterp[fi] - g.begp0;
       const int cc = PF(column) - g.begc0;
       const int gg = PF(gridcell) - g.begg0;
       const int ivt = PF(itype);
       const double forc_pbot = CF(forc_pbot), forc_rho = CF(forc_rho), forc_q = CF(forc_q), t_grnd = CF(t_grnd);
       const double thm = PF(thm), elai = PF(elai), esai = PF(esai), emv = PF(emv), htop = PF(htop);
-      const double laisun = PF(laisun), laisha = PF(laisha);
       const double ur = WS(W_UR), zldis_u = WS(W_ZLDIS);
-      double t_veg = PF(t_veg);
-      const double t_stem = PF(t_stem);
-      double um = PF(um), obu = PF(obu), taf = PF(taf), qaf = PF(qaf);
-      const double displa = PF(displa), z0mv = PF(z0mv);
-
-      // FrictionVelocity :1033-1036
-      const FricOut fo = friction_velocity(PF(forc_hgt_u_patch), PF(forc_hgt_t_patch), PF(forc_hgt_q_patch), displa, z0mv,
-                                           z0mv, z0mv, obu, itlef + 1, ur, um, WS(W_FM));
-      const double ustar = fo.ustar, temp1 = fo.temp1, temp2 = fo.temp2;
-      PF(ustar) = ustar; PF(vds) = fo.vds; PF(u10_clm) = fo.u10_clm; PF(va) = um; PF(u10) = fo.u10; PF(fv) = ustar;
-      WS(W_FM) = fo.fm; WS(W_TEMP1) = temp1; WS(W_TEMP2) = temp2; WS(W_TEMP12M) = fo.temp12m; WS(W_TEMP22M) = fo.temp22m;
-
-      // :1038-1122
-      const double tlbef = t_veg;
-      const double del2 = WS(W_DEL);
-      const double ram1 = 1.0 / (ustar * ustar / um);
-      const double rah_a = 1.0 / (temp1 * ustar);
-      const double raw_a = 1.0 / (temp2 * ustar);
-      const double uaf = um * sqrt(1.0 / (ram1 * um));
-      const double uuc = fmin(0.4, (0.03 * um / ustar));
-      const double dleaf = f.pft_dleaf[ivt];
-      const double cfl = prm.cv / (sqrt(uaf) * sqrt(dleaf));
-      const double rb = 1.0 / (cfl * uaf);
-      const double w = dexp(-(elai + esai));
-      const double csoilb = vkc / (prm.a_coef * pw(CF(z0mg) * uaf / nu_param, prm.a_exp));
-      const double ri = (grav * htop * (taf - t_grnd)) / (taf * (uaf * uaf));
-      double csoilcn;
-      if (prm.use_undercanopy_stability && (taf - t_grnd) > 0.0) {
-        const double ricsoilc = prm.csoilc / (1.00 + 0.5 * fmin(ri, 10.0));
-        csoilcn = csoilb * w + ricsoilc * (1.0 - w);
-      } else {
-        csoilcn = csoilb * w + prm.csoilc * (1.0 - w);
-      }
-      const double rah_b = prm.use_biomass_heat_storage ? 1.0 / (csoilcn * uuc) : 1.0 / (csoilcn * uaf);
-      const double raw_b = rah_b;
-      const double svpts = WS(W_EL);
-      const double eah = forc_pbot * qaf / 0.622;
-      PF(ram1) = ram1; PF(uaf) = uaf; PF(dleaf_patch) = dleaf; PF(rb1) = rb;
-      PF(rh_af) = eah / svpts;
-      PF(rah1) = rah_a; PF(raw1) = raw_a; PF(rah2) = rah_b; PF(raw2) = raw_b;
-      PF(vpd) = fmax((svpts - eah), 50.0) * 0.001;
-
-      // ---- PhotosynthesisHydraulicStress for this patch (:3118-3807) ----
-      const double qsatl = WS(W_QSATL);
-      bool bad_quad = false, notbracketed = false;
-      phs::PhsPatch P;
-      phs::Leaf Lf;
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        P.psi50[s] = f.pft_psi50[(size_t)s * NPFT + ivt];
-        P.ck[s] = f.pft_ck[(size_t)s * NPFT + ivt];
-        P.kmax[s] = f.pft_kmax[(size_t)s * NPFT + ivt];
-      }
-      P.laisun = laisun; P.laisha = laisha; P.elai = elai; P.esai = esai; P.tsai = PF(tsai); P.htop = htop; P.fdry = PF(fdry);
-      P.forc_rho = forc_rho; P.forc_pbot = forc_pbot;
-      const double cfm = forc_pbot / (rgas * 1.e-3 * thm) * 1.e06;
-      P.cf = cfm;
-      P.qsatl = qsatl; P.qaf = qaf;
-      const double gb_mol = (1.0 / rb) * cfm;
-      P.gb_mol = gb_mol;
-      P.sk = sk; P.sg = sgv; P.ss = ssv; P.stride = ITER_THREADS; P.work = &work;
-      {
-        double ksum = 0.0, ksmp = 0.0, ksmpg = 0.0, smpg = 0.0;
-        for (int j = 0; j < NLEVSOI; ++j) {
-          const double k = PF2(k_soil_root, j), sm = CF2(smp_l, j), gr = 1000.0 * CF2(z, j + 1 - SNOSOI_LO);
-          sk[j * ITER_THREADS] = k; sgv[j * ITER_THREADS] = gr; ssv[j * ITER_THREADS] = sm;
-          ksum += k; ksmp += k * sm; ksmpg += k * (sm - gr); smpg += sm - gr;
-        }
-        P.ksum = ksum; P.ksmp = ksmp; P.ksmpg = ksmpg; P.smpg_mean = smpg / NLEVSOI;
-      }
-      const bool c3 = ((int)nearbyint(f.pft_c3psn[ivt]) == 1);
-      const double crop = f.pft_crop[ivt];
-      Lf.c3 = c3; Lf.medlyn = prm.medlyn != 0;
-      Lf.qe = c3 ? 0.0 : 0.05;
-      Lf.bbb = c3 ? 10000.0 : 40000.0;
-      Lf.mbb = f.pft_mbbopt[ivt];
-      Lf.medint = f.pft_medlynintercept[ivt]; Lf.medslope = f.pft_medlynslope[ivt];
-      Lf.theta_cj = f.pft_theta_cj[ivt]; Lf.theta_ip = prm.theta_ip;
-      Lf.cair = f.forc_pco2[gg]; Lf.oair = f.forc_po2[gg];
-      {
-        const double kc25 = prm.kc25_coef * forc_pbot, ko25 = prm.ko25_coef * forc_pbot;
-        const double sco = 0.5 * 0.209 / prm.cp25_yr2000;
-        const double cp25 = 0.5 * Lf.oair / sco;
-        Lf.kc = kc25 * ft(t_veg, prm.kcha);
-        Lf.ko = ko25 * ft(t_veg, prm.koha);
-        Lf.cp = cp25 * ft(t_veg, prm.cpha);
-      }
-      PF(c3flag) = c3 ? 1 : 0; PF(qe) = Lf.qe; PF(kc) = Lf.kc; PF(ko) = Lf.ko; PF(cp) = Lf.cp; PF(gb_mol) = gb_mol;
-      const double t10 = PF(t_a10), dayl_factor = WS(W_DAYL);
-      const double lnc = fmin(1.0 / (f.pft_slatop[ivt] * f.pft_leafcn[ivt]), 10.0);
-      PF(lnca) = lnc;
-      double vcmax25top = lnc * f.pft_flnr[ivt] * prm.fnr * prm.act25 * dayl_factor;
-      vcmax25top = vcmax25top * f.pft_fnitr[ivt];
-      const double jmax25top = ((2.59 - 0.035 * fmin(fmax((t10 - tfrz), 11.0), 35.0)) * vcmax25top) * prm.jmax25top_sf;
-      const double tpu25top = prm.tpu25ratio * vcmax25top;
-      const double kp25top = prm.kp25ratio * vcmax25top;
-      PF(luvcmax25top) = vcmax25top; PF(lujmax25top) = jmax25top; PF(lutpu25top) = tpu25top;
-      const double lmr25top = c3 ? vcmax25top * prm.leaf_mr_vcm : vcmax25top * 0.025;
-      const int nrad = PF(nrad);
-      const double par_sun = PF2(parsun_z, 0), par_sha = PF2(parsha_z, 0);
-      Lf.par[0] = par_sun; Lf.par[1] = par_sha;
-      double jmax[2] = {0.0, 0.0};
-      Lf.vcmax[0] = Lf.vcmax[1] = Lf.tpu[0] = Lf.tpu[1] = Lf.kp[0] = Lf.kp[1] = 0.0;
-      double bsun = 0.0, bsha = 0.0, rs_z[2] = {0.0, 0.0}, psn_z[2] = {0.0, 0.0};
-      double wc_z[2] = {0.0, 0.0}, wj_z[2] = {0.0, 0.0}, wp_z[2] = {0.0, 0.0};
-      double qflx_tran_veg = PF(qflx_tran_veg);
-      if (nrad >= 1) {
-        const double ns[2] = {PF(vcmaxcintsun), PF(vcmaxcintsha)};
-        const bool luna = prm.use_luna && c3 && crop == 0.0;
-        const double vcmx25 = PF2(vcmx25_z, 0);
-        const double lmrc = fth25(prm.lmrhd, prm.lmrse);
-        const double tl_fac = fmin((0.2 * dexp(3.218 * PF2(tlai_z, 0))), 1.0);
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {                  // :3350-3374
-          double lmr25 = lmr25top * ns[s];
-          if (luna) lmr25 = prm.leaf_mr_vcm * vcmx25;
-          double lmr;
-          if (c3) {
-            lmr = lmr25 * ft(t_veg, prm.lmrha) * fth(t_veg, prm.lmrhd, prm.lmrse, lmrc);
-          } else {
-            lmr = lmr25 * pw2((t_veg - (tfrz + 25.0)) / 10.0);
-            lmr = lmr / (1.0 + dexp(1.3 * (t_veg - (tfrz + 55.0))));
-          }
-          Lf.lmr[s] = lmr * tl_fac;
-        }
-        if (!(par_sun <= 0.0)) {                       // day :3393-3456
-          double v25[2], j25[2], t25[2];
-          if (luna) {
-            const double jmx25 = PF2(jmx25_z, 0);
-            v25[0] = v25[1] = vcmx25; j25[0] = j25[1] = jmx25;
-            t25[0] = prm.tpu25ratio * v25[0]; t25[1] = prm.tpu25ratio * v25[1];
-            if (ns[0] > 0.0) {
-              v25[1] = v25[0] * ns[1] / ns[0];
-              j25[1] = j25[0] * ns[1] / ns[0];
-              t25[1] = t25[0] * ns[1] / ns[0];
-            }
-          } else {
-#pragma unroll
-            for (int s = 0; s < 2; ++s) { v25[s] = vcmax25top * ns[s]; j25[s] = jmax25top * ns[s]; t25[s] = tpu25top * ns[s]; }
-          }
-          const double tc = fmin(fmax((t10 - tfrz), 11.0), 35.0);
-          const double vcmaxse = (668.39 - 1.07 * tc) * prm.vcmaxse_sf;
-          const double jmaxse = (659.70 - 0.75 * tc) * prm.jmaxse_sf;
-          const double tpuse = (668.39 - 1.07 * tc) * prm.tpuse_sf;
-          const double vcmaxc = fth25(prm.vcmaxhd, vcmaxse), jmaxc = fth25(prm.jmaxhd, jmaxse), tpuc = fth25(prm.tpuhd, tpuse);
-          const double fv_ = ft(t_veg, prm.vcmaxha) , hv_ = fth(t_veg, prm.vcmaxhd, vcmaxse, vcmaxc);
-          const double fj_ = ft(t_veg, prm.jmaxha), hj_ = fth(t_veg, prm.jmaxhd, jmaxse, jmaxc);
-          const double ftp = ft(t_veg, prm.tpuha), htp = fth(t_veg, prm.tpuhd, tpuse, tpuc);
-          const double q10 = pw2((t_veg - (tfrz + 25.0)) / 10.0);
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            Lf.vcmax[s] = v25[s] * fv_ * hv_;
-            jmax[s] = j25[s] * fj_ * hj_;
-            Lf.tpu[s] = t25[s] * ftp * htp;
-            if (!c3) {
-              double v = v25[s] * q10;
-              v = v / (1.0 + dexp(0.2 * ((tfrz + 15.0) - t_veg)));
-              v = v / (1.0 + dexp(0.3 * (t_veg - (tfrz + 40.0))));
-              Lf.vcmax[s] = v;
-            }
-            Lf.kp[s] = (kp25top * ns[s]) * q10;
-          }
-        }
-        if (prm.light_inhibit && par_sun > 0.0) Lf.lmr[0] = Lf.lmr[0] * 0.67;      // :3461-3466
-        if (prm.light_inhibit && par_sha > 0.0) Lf.lmr[1] = Lf.lmr[1] * 0.67;
-        PF2(lmrsun_z, 0) = Lf.lmr[0]; PF2(lmrsha_z, 0) = Lf.lmr[1];
-        PF2(vcmax_z_phs, 0) = Lf.vcmax[0]; PF2(vcmax_z_phs, 1) = Lf.vcmax[1];
-        PF2(tpu_z_phs, 0) = Lf.tpu[0]; PF2(tpu_z_phs, 1) = Lf.tpu[1];
-        PF2(kp_z_phs, 0) = Lf.kp[0]; PF2(kp_z_phs, 1) = Lf.kp[1];
-
-        // leaf-level photosynthesis and stomatal conductance :3477-3714
-        const bool scale_an = (crop == 0.0 || !prm.modifyphoto_and_lmr_forcrop);
-        const int near_noon = f.near_local_noon[gg];
-        double xw[4];
-        phs::CiOut co;
-        double gs_mol[2], an[2], ci_z[2];
-        if (par_sun <= 0.0) {                          // night :3492-3547
-          xw[0] = 1.0; xw[1] = PF2(vegwp, 1); xw[2] = PF2(vegwp, 2); xw[3] = PF2(vegwp, 3);
-          const double gsmin = Lf.medlyn ? Lf.medint : Lf.bbb;
-          const phs::Stress st = phs::calcstress(P, xw, gsmin, gsmin, &qflx_tran_veg);
-          bsun = st.bsun; bsha = st.bsha;
-          const bool pd = f.local_time_lt_noon[gg] != 0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { PF2(vegwp, i) = xw[i]; PF2(vegwp_pd, i) = pd ? xw[i] : spval; }
-          const double bb[2] = {bsun, bsha};
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            co.ac[s] = co.aj[s] = co.ap[s] = co.ag[s] = 0.0;
-            an[s] = scale_an ? 0.0 - bb[s] * Lf.lmr[s] : 0.0 - Lf.lmr[s];
-            rs_z[s] = fmin(2.e4, 1.0 / (fmax(bb[s] * gsmin, 1.0)) * cfm);
-            ci_z[s] = 0.0;
-            gs_mol[s] = cfm / rs_z[s];
-          }
-        } else {                                       // day :3549-3711
-          const double esat_tv = svpts;
-          const double ceair = fmin(eah, esat_tv);
-          if (!Lf.medlyn) Lf.rh_can = ceair / esat_tv;
-          else { Lf.rh_can = fmax((esat_tv - ceair), 50.0) * 0.001; PF(vpd_can) = Lf.rh_can; }
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            const double qabs = 0.5 * (1.0 - prm.fnps) * Lf.par[s] * 4.6;
-            const phs::Quad q = phs::quadratic(prm.theta_psii, -(qabs + jmax[s]), qabs * jmax[s], &bad_quad);
-            Lf.je[s] = fmin(q.r1, q.r2);
-          }
-          const double vw[4] = {PF2(vegwp, 0), PF2(vegwp, 1), PF2(vegwp, 2), PF2(vegwp, 3)};
-          const phs::HybridOut h = phs::hybrid(P, Lf, vw, (c3 ? 0.7 : 0.4) * Lf.cair, co, &bad_quad, &notbracketed);
-          bsun = h.bsun; bsha = h.bsha;
-          qflx_tran_veg = h.tran;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { PF2(vegwp, i) = h.x[i]; PF2(vegwp_ln, i) = near_noon ? h.x[i] : spval; PF2(vegwp_pd, i) = spval; }
-          const double gsmin = Lf.medlyn ? Lf.medint : Lf.bbb;
-          const double bb[2] = {bsun, bsha};
-          gs_mol[0] = h.gs_sun; gs_mol[1] = h.gs_sha;
-          const double o3g[2] = {PF(o3coefgsun), PF(o3coefgsha)}, o3v[2] = {PF(o3coefvsun), PF(o3coefvsha)};
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            an[s] = co.an[s];
-            if (an[s] < 0.0) gs_mol[s] = fmax(bb[s] * gsmin, 1.0);
-            ci_z[s] = Lf.cair - an[s] * forc_pbot * (1.4 * gs_mol[s] + 1.6 * gb_mol) / (gb_mol * gs_mol[s]);
-            ci_z[s] = fmax(ci_z[s], 1.e-06);
-            const double gs = gs_mol[s] / cfm;
-            rs_z[s] = fmin(1.0 / gs, 2.e4);
-            rs_z[s] = rs_z[s] / o3g[s];
-            psn_z[s] = co.ag[s] * o3v[s];
-            if (co.ac[s] <= co.aj[s] && co.ac[s] <= co.ap[s]) wc_z[s] = psn_z[s];
-            else if (co.aj[s] < co.ac[s] && co.aj[s] <= co.ap[s]) wj_z[s] = psn_z[s];
-            else if (co.ap[s] < co.ac[s] && co.ap[s] < co.aj[s]) wp_z[s] = psn_z[s];
-          }
-          PF2(gs_mol_sun_ln, 0) = near_noon ? gs_mol[0] : spval;
-          PF2(gs_mol_sha_ln, 0) = near_noon ? gs_mol[1] : spval;
-          if (gs_mol[0] < 0.0 || gs_mol[1] < 0.0) report_failure(ds, pp + g.begp0, CTSM_ERR_GS_NEG, 0);
-        }
-        PF2(ac_phs, 0) = co.ac[0]; PF2(ac_phs, 1) = co.ac[1]; PF2(aj_phs, 0) = co.aj[0]; PF2(aj_phs, 1) = co.aj[1];
-        PF2(ap_phs, 0) = co.ap[0]; PF2(ap_phs, 1) = co.ap[1]; PF2(ag_phs, 0) = co.ag[0]; PF2(ag_phs, 1) = co.ag[1];
-        PF2(an_sun, 0) = an[0]; PF2(an_sha, 0) = an[1];
-        PF2(gs_mol_sun, 0) = gs_mol[0]; PF2(gs_mol_sha, 0) = gs_mol[1];
-        PF2(cisun_z, 0) = ci_z[0]; PF2(cisha_z, 0) = ci_z[1];
-        PF2(rssun_z, 0) = rs_z[0]; PF2(rssha_z, 0) = rs_z[1];
-        PF2(psnsun_z, 0) = psn_z[0]; PF2(psnsha_z, 0) = psn_z[1];
-      }
-      if (bad_quad) report_failure(ds, pp + g.begp0, CTSM_ERR_QUADRATIC, 0);
-      if (notbracketed) report_failure(ds, pp + g.begp0, CTSM_ERR_BRENT, 0);
-      // canopy sums :3724-3807 (nlevcan = 1)
-      double rssun, rssha, btran;
-      {
-        const bool scale_lmr = (crop == 0.0 && prm.modifyphoto_and_lmr_forcrop);
-        const double lz[2] = {nrad >= 1 ? PF2(laisun_z, 0) : 0.0, nrad >= 1 ? PF2(laisha_z, 0) : 0.0};
-        const double bb[2] = {bsun, bsha};
-        double psn[2], pwc[2], pwj[2], pwp[2], lmr[2], rs[2], lai[2];
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          double a = 0.0, b_ = 0.0, c_ = 0.0, d_ = 0.0, e_ = 0.0, gsc = 0.0, ll = 0.0;
-          if (nrad >= 1) {
-            a = a + psn_z[s] * lz[s]; b_ = b_ + wc_z[s] * lz[s]; c_ = c_ + wj_z[s] * lz[s]; d_ = d_ + wp_z[s] * lz[s];
-            e_ = scale_lmr ? e_ + Lf.lmr[s] * lz[s] * bb[s] : e_ + Lf.lmr[s] * lz[s];
-            gsc = gsc + lz[s] / (rb + rs_z[s]);
-            ll = ll + lz[s];
-          }
-          lai[s] = ll;
-          if (ll > 0.0) { psn[s] = a / ll; pwc[s] = b_ / ll; pwj[s] = c_ / ll; pwp[s] = d_ / ll; lmr[s] = e_ / ll; rs[s] = ll / gsc - rb; }
-          else { psn[s] = 0.0; pwc[s] = 0.0; pwj[s] = 0.0; pwp[s] = 0.0; lmr[s] = 0.0; rs[s] = 0.0; }
-        }
-        PF(psnsun) = psn[0]; PF(psnsun_wc) = pwc[0]; PF(psnsun_wj) = pwj[0]; PF(psnsun_wp) = pwp[0]; PF(lmrsun) = lmr[0];
-        PF(psnsha) = psn[1]; PF(psnsha_wc) = pwc[1]; PF(psnsha_wj) = pwj[1]; PF(psnsha_wp) = pwp[1]; PF(lmrsha) = lmr[1];
-        rssun = rs[0]; rssha = rs[1];
-        PF(rssun) = rssun; PF(rssha) = rssha;
-        if (lai[1] + lai[0] > 0.0) btran = bsun * (lai[0] / (lai[0] + lai[1])) + bsha * (lai[1] / (lai[0] + lai[1]));
-        else btran = bsun;
-        PF(btran) = btran; PF(bsun) = bsun; PF(bsha) = bsha;
-        PF(qflx_tran_veg) = qflx_tran_veg;
-      }
-
+      keep = true;
+      if (!first) {
+        // ---- close pass itlef0-1 ----
+        const double laisun = PF(laisun), laisha = PF(laisha);
+        double t_veg = PF(t_veg);
+        const double t_stem = PF(t_stem);
+        double um = PF(um), obu, taf, qaf = PF(qaf);
+        const double ustar = PF(ustar), temp1 = WS(W_TEMP1), temp2 = WS(W_TEMP2);
+        const double tlbef = t_veg, del2 = WS(W_DEL);
+        const double rah_a = PF(rah1), raw_a = PF(raw1), rah_b = PF(rah2), raw_b = rah_b, uaf = PF(uaf), rb = PF(rb1);
+        const double qsatl = WS(W_QSATL);
+        const double rssun = PF(rssun), rssha = PF(rssha), btran = PF(btran), qflx_tran_veg = PF(qflx_tran_veg);
       // ---- leaf energy balance :1174-1435 ----
       const double sa_leaf = WS(W_SA_LEAF), sa_stem = WS(W_SA_STEM), sa_int = WS(W_SA_INT), frs = WS(W_FRS);
       const double cp_leaf = WS(W_CP_LEAF), rstem = WS(W_RSTEM), tl_ini = WS(W_TL_INI);
@@ -893,7 +632,7 @@ canopy_iter_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, const 
 
       // convergence :1439-1457
       keep = true;
-      const int it1 = itlef + 1;
+      const int it1 = itlef0;
       if (it1 > 2) {
         const double dele = fabs(efe - efeb);
         WS(W_EFEB) = efe;
@@ -901,11 +640,355 @@ canopy_iter_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, const 
         PF(num_iter) = (double)it1;
         keep = !(det < 0.01 && dele < 0.1);
       }
+      }
+      if (keep && !last) {
+        // ---- open pass itlef0 ----
+        const double t_veg = PF(t_veg);
+        const double um = PF(um), obu = PF(obu), taf = PF(taf), qaf = PF(qaf);
+        const double displa = PF(displa), z0mv = PF(z0mv);
+        phs::Leaf Lf;
+
+      // FrictionVelocity :1033-1036
+      const FricOut fo = friction_velocity(PF(forc_hgt_u_patch), PF(forc_hgt_t_patch), PF(forc_hgt_q_patch), displa, z0mv,
+                                           z0mv, z0mv, obu, itlef0 + 1, ur, um, WS(W_FM));
+      const double ustar = fo.ustar, temp1 = fo.temp1, temp2 = fo.temp2;
+      PF(ustar) = ustar; PF(vds) = fo.vds; PF(u10_clm) = fo.u10_clm; PF(va) = um; PF(u10) = fo.u10; PF(fv) = ustar;
+      WS(W_FM) = fo.fm; WS(W_TEMP1) = temp1; WS(W_TEMP2) = temp2; WS(W_TEMP12M) = fo.temp12m; WS(W_TEMP22M) = fo.temp22m;
+
+      // :1038-1122
+      const double ram1 = 1.0 / (ustar * ustar / um);
+      const double rah_a = 1.0 / (temp1 * ustar);
+      const double raw_a = 1.0 / (temp2 * ustar);
+      const double uaf = um * sqrt(1.0 / (ram1 * um));
+      const double uuc = fmin(0.4, (0.03 * um / ustar));
+      const double dleaf = f.pft_dleaf[ivt];
+      const double cfl = prm.cv / (sqrt(uaf) * sqrt(dleaf));
+      const double rb = 1.0 / (cfl * uaf);
+      const double w = dexp(-(elai + esai));
+      const double csoilb = vkc / (prm.a_coef * pw(CF(z0mg) * uaf / nu_param, prm.a_exp));
+      const double ri = (grav * htop * (taf - t_grnd)) / (taf * (uaf * uaf));
+      double csoilcn;
+      if (prm.use_undercanopy_stability && (taf - t_grnd) > 0.0) {
+        const double ricsoilc = prm.csoilc / (1.00 + 0.5 * fmin(ri, 10.0));
+        csoilcn = csoilb * w + ricsoilc * (1.0 - w);
+      } else {
+        csoilcn = csoilb * w + prm.csoilc * (1.0 - w);
+      }
+      const double rah_b = prm.use_biomass_heat_storage ? 1.0 / (csoilcn * uuc) : 1.0 / (csoilcn * uaf);
+      const double raw_b = rah_b;
+      const double svpts = WS(W_EL);
+      const double eah = forc_pbot * qaf / 0.622;
+      PF(ram1) = ram1; PF(uaf) = uaf; PF(dleaf_patch) = dleaf; PF(rb1) = rb;
+      PF(rh_af) = eah / svpts;
+      PF(rah1) = rah_a; PF(raw1) = raw_a; PF(rah2) = rah_b; PF(raw2) = raw_b;
+      PF(vpd) = fmax((svpts - eah), 50.0) * 0.001;
+      const bool c3 = ((int)nearbyint(f.pft_c3psn[ivt]) == 1);
+      const double crop = f.pft_crop[ivt];
+      Lf.c3 = c3; Lf.medlyn = prm.medlyn != 0;
+      Lf.qe = c3 ? 0.0 : 0.05;
+      Lf.bbb = c3 ? 10000.0 : 40000.0;
+      Lf.mbb = f.pft_mbbopt[ivt];
+      Lf.medint = f.pft_medlynintercept[ivt]; Lf.medslope = f.pft_medlynslope[ivt];
+      Lf.theta_cj = f.pft_theta_cj[ivt]; Lf.theta_ip = prm.theta_ip;
+      Lf.cair = f.forc_pco2[gg]; Lf.oair = f.forc_po2[gg];
+      {
+        const double kc25 = prm.kc25_coef * forc_pbot, ko25 = prm.ko25_coef * forc_pbot;
+        const double sco = 0.5 * 0.209 / prm.cp25_yr2000;
+        const double cp25 = 0.5 * Lf.oair / sco;
+        Lf.kc = kc25 * ft(t_veg, prm.kcha);
+        Lf.ko = ko25 * ft(t_veg, prm.koha);
+        Lf.cp = cp25 * ft(t_veg, prm.cpha);
+      }
+      PF(c3flag) = c3 ? 1 : 0; PF(qe) = Lf.qe; PF(kc) = Lf.kc; PF(ko) = Lf.ko; PF(cp) = Lf.cp; PF(gb_mol) = (1.0 / rb) * (forc_pbot / (rgas * 1.e-3 * thm) * 1.e06);
+      const double t10 = PF(t_a10), dayl_factor = WS(W_DAYL);
+      const double lnc = fmin(1.0 / (f.pft_slatop[ivt] * f.pft_leafcn[ivt]), 10.0);
+      PF(lnca) = lnc;
+      double vcmax25top = lnc * f.pft_flnr[ivt] * prm.fnr * prm.act25 * dayl_factor;
+      vcmax25top = vcmax25top * f.pft_fnitr[ivt];
+      const double jmax25top = ((2.59 - 0.035 * fmin(fmax((t10 - tfrz), 11.0), 35.0)) * vcmax25top) * prm.jmax25top_sf;
+      const double tpu25top = prm.tpu25ratio * vcmax25top;
+      const double kp25top = prm.kp25ratio * vcmax25top;
+      PF(luvcmax25top) = vcmax25top; PF(lujmax25top) = jmax25top; PF(lutpu25top) = tpu25top;
+      const double lmr25top = c3 ? vcmax25top * prm.leaf_mr_vcm : vcmax25top * 0.025;
+      const int nrad = PF(nrad);
+      const double par_sun = PF2(parsun_z, 0), par_sha = PF2(parsha_z, 0);
+      Lf.par[0] = par_sun; Lf.par[1] = par_sha;
+      double jmax[2] = {0.0, 0.0};
+      Lf.vcmax[0] = Lf.vcmax[1] = Lf.tpu[0] = Lf.tpu[1] = Lf.kp[0] = Lf.kp[1] = 0.0;
+      if (nrad >= 1) {
+        const double ns[2] = {PF(vcmaxcintsun), PF(vcmaxcintsha)};
+        const bool luna = prm.use_luna && c3 && crop == 0.0;
+        const double vcmx25 = PF2(vcmx25_z, 0);
+        const double lmrc = fth25(prm.lmrhd, prm.lmrse);
+        const double tl_fac = fmin((0.2 * dexp(3.218 * PF2(tlai_z, 0))), 1.0);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {                  // :3350-3374
+          double lmr25 = lmr25top * ns[s];
+          if (luna) lmr25 = prm.leaf_mr_vcm * vcmx25;
+          double lmr;
+          if (c3) {
+            lmr = lmr25 * ft(t_veg, prm.lmrha) * fth(t_veg, prm.lmrhd, prm.lmrse, lmrc);
+          } else {
+            lmr = lmr25 * pw2((t_veg - (tfrz + 25.0)) / 10.0);
+            lmr = lmr / (1.0 + dexp(1.3 * (t_veg - (tfrz + 55.0))));
+          }
+          Lf.lmr[s] = lmr * tl_fac;
+        }
+        if (!(par_sun <= 0.0)) {                       // day :3393-3456
+          double v25[2], j25[2], t25[2];
+          if (luna) {
+            const double jmx25 = PF2(jmx25_z, 0);
+            v25[0] = v25[1] = vcmx25; j25[0] = j25[1] = jmx25;
+            t25[0] = prm.tpu25ratio * v25[0]; t25[1] = prm.tpu25ratio * v25[1];
+            if (ns[0] > 0.0) {
+              v25[1] = v25[0] * ns[1] / ns[0];
+              j25[1] = j25[0] * ns[1] / ns[0];
+              t25[1] = t25[0] * ns[1] / ns[0];
+            }
+          } else {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) { v25[s] = vcmax25top * ns[s]; j25[s] = jmax25top * ns[s]; t25[s] = tpu25top * ns[s]; }
+          }
+          const double tc = fmin(fmax((t10 - tfrz), 11.0), 35.0);
+          const double vcmaxse = (668.39 - 1.07 * tc) * prm.vcmaxse_sf;
+          const double jmaxse = (659.70 - 0.75 * tc) * prm.jmaxse_sf;
+          const double tpuse = (668.39 - 1.07 * tc) * prm.tpuse_sf;
+          const double vcmaxc = fth25(prm.vcmaxhd, vcmaxse), jmaxc = fth25(prm.jmaxhd, jmaxse), tpuc = fth25(prm.tpuhd, tpuse);
+          const double fv_ = ft(t_veg, prm.vcmaxha) , hv_ = fth(t_veg, prm.vcmaxhd, vcmaxse, vcmaxc);
+          const double fj_ = ft(t_veg, prm.jmaxha), hj_ = fth(t_veg, prm.jmaxhd, jmaxse, jmaxc);
+          const double ftp = ft(t_veg, prm.tpuha), htp = fth(t_veg, prm.tpuhd, tpuse, tpuc);
+          const double q10 = pw2((t_veg - (tfrz + 25.0)) / 10.0);
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            Lf.vcmax[s] = v25[s] * fv_ * hv_;
+            jmax[s] = j25[s] * fj_ * hj_;
+            Lf.tpu[s] = t25[s] * ftp * htp;
+            if (!c3) {
+              double v = v25[s] * q10;
+              v = v / (1.0 + dexp(0.2 * ((tfrz + 15.0) - t_veg)));
+              v = v / (1.0 + dexp(0.3 * (t_veg - (tfrz + 40.0))));
+              Lf.vcmax[s] = v;
+            }
+            Lf.kp[s] = (kp25top * ns[s]) * q10;
+          }
+        }
+        if (prm.light_inhibit && par_sun > 0.0) Lf.lmr[0] = Lf.lmr[0] * 0.67;      // :3461-3466
+        if (prm.light_inhibit && par_sha > 0.0) Lf.lmr[1] = Lf.lmr[1] * 0.67;
+        PF2(lmrsun_z, 0) = Lf.lmr[0]; PF2(lmrsha_z, 0) = Lf.lmr[1];
+        PF2(vcmax_z_phs, 0) = Lf.vcmax[0]; PF2(vcmax_z_phs, 1) = Lf.vcmax[1];
+        PF2(tpu_z_phs, 0) = Lf.tpu[0]; PF2(tpu_z_phs, 1) = Lf.tpu[1];
+        PF2(kp_z_phs, 0) = Lf.kp[0]; PF2(kp_z_phs, 1) = Lf.kp[1];
+        WS(W_JMAX0) = jmax[0]; WS(W_JMAX1) = jmax[1];
+        }
+      }
     }
-    // survivors -> bins of the next pass
+    // survivors -> work-class bins of pass itlef0 (work of the patch's previous PHS solve; none before the first)
+    const bool go = keep && !last;
     const unsigned act = __activemask();
-    const unsigned mk = __ballot_sync(act, keep);
-    if (keep) bin_append(L, list_out, itlef0 + 1, (night ? 0 : NCLASS) + work_class(work), fi, mk);
+    const unsigned mk = __ballot_sync(act, go);
+    if (go) {
+      const int wk = first ? 0 : (int)ws[(size_t)W_WORK * wstride + fi];
+      bin_append(L, list_out, row + 1, (night ? 0 : NCLASS) + work_class(wk), fi, mk);
+    }
+  }
+}
+
+#define ITER_THREADS 64
+#ifndef ITER_MINBLOCKS
+#define ITER_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(ITER_THREADS, ITER_MINBLOCKS)
+canopy_phs_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, const int32_t* __restrict__ filterp,
+                  double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in, DevStatus* ds) {
+  extern __shared__ double shm[];                       // [3][NLEVSOI][ITER_THREADS]
+  double* sk = shm + threadIdx.x;
+  double* sgv = shm + (size_t)NLEVSOI * ITER_THREADS + threadIdx.x;
+  double* ssv = shm + (size_t)2 * NLEVSOI * ITER_THREADS + threadIdx.x;
+  const int row = itlef0 + 1;
+  // thread slots: bins padded to whole warps
+  int off[NBIN + 1];
+  off[0] = 0;
+#pragma unroll
+  for (int b = 0; b < NBIN; ++b) off[b + 1] = off[b] + ((L.counts[row * NBIN + b] + 31) & ~31);
+  const int total = off[NBIN];
+  for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+    const int t = base + threadIdx.x;
+    int bin = 0;
+#pragma unroll
+    for (int b = 1; b < NBIN; ++b) bin += (t >= off[b]) ? 1 : 0;
+    const int idx = t - off[bin];
+    const bool live = idx < L.counts[row * NBIN + bin];
+    const bool night = bin < NCLASS;
+    int fi = 0;
+    if (live) fi = list_in[(size_t)bin * L.cap + idx];
+    (void)night;
+    if (live) {
+      int work = 0;
+      const int pp = filterp[fi] - g.begp0;
+      const int cc = PF(column) - g.begc0;
+      const int gg = PF(gridcell) - g.begg0;
+      const int ivt = PF(itype);
+      const double forc_pbot = CF(forc_pbot), forc_rho = CF(forc_rho);
+      const double thm = PF(thm), elai = PF(elai), esai = PF(esai), htop = PF(htop);
+      const double laisun = PF(laisun), laisha = PF(laisha);
+      const double qaf = PF(qaf), rb = PF(rb1);
+      const double svpts = WS(W_EL);
+      const double eah = forc_pbot * qaf / 0.622;
+      const double qsatl = WS(W_QSATL);
+      bool bad_quad = false, notbracketed = false;
+      phs::PhsPatch P;
+      phs::Leaf Lf;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        P.psi50[s] = f.pft_psi50[(size_t)s * NPFT + ivt];
+        P.ck[s] = f.pft_ck[(size_t)s * NPFT + ivt];
+        P.kmax[s] = f.pft_kmax[(size_t)s * NPFT + ivt];
+      }
+      P.laisun = laisun; P.laisha = laisha; P.elai = elai; P.esai = esai; P.tsai = PF(tsai); P.htop = htop; P.fdry = PF(fdry);
+      P.forc_rho = forc_rho; P.forc_pbot = forc_pbot;
+      const double cfm = forc_pbot / (rgas * 1.e-3 * thm) * 1.e06;
+      P.cf = cfm;
+      P.qsatl = qsatl; P.qaf = qaf;
+      const double gb_mol = (1.0 / rb) * cfm;
+      P.gb_mol = gb_mol;
+      P.sk = sk; P.sg = sgv; P.ss = ssv; P.stride = ITER_THREADS; P.work = &work;
+      {
+        double ksum = 0.0, ksmp = 0.0, ksmpg = 0.0, smpg = 0.0;
+        for (int j = 0; j < NLEVSOI; ++j) {
+          const double k = PF2(k_soil_root, j), sm = CF2(smp_l, j), gr = 1000.0 * CF2(z, j + 1 - SNOSOI_LO);
+          sk[j * ITER_THREADS] = k; sgv[j * ITER_THREADS] = gr; ssv[j * ITER_THREADS] = sm;
+          ksum += k; ksmp += k * sm; ksmpg += k * (sm - gr); smpg += sm - gr;
+        }
+        P.ksum = ksum; P.ksmp = ksmp; P.ksmpg = ksmpg; P.smpg_mean = smpg / NLEVSOI;
+      }
+      const bool c3 = ((int)nearbyint(f.pft_c3psn[ivt]) == 1);
+      const double crop = f.pft_crop[ivt];
+      Lf.c3 = c3; Lf.medlyn = prm.medlyn != 0;
+      Lf.qe = c3 ? 0.0 : 0.05;
+      Lf.bbb = c3 ? 10000.0 : 40000.0;
+      Lf.mbb = f.pft_mbbopt[ivt];
+      Lf.medint = f.pft_medlynintercept[ivt]; Lf.medslope = f.pft_medlynslope[ivt];
+      Lf.theta_cj = f.pft_theta_cj[ivt]; Lf.theta_ip = prm.theta_ip;
+      Lf.cair = f.forc_pco2[gg]; Lf.oair = f.forc_po2[gg];
+      Lf.kc = PF(kc); Lf.ko = PF(ko); Lf.cp = PF(cp);
+      const int nrad = PF(nrad);
+      const double par_sun = PF2(parsun_z, 0), par_sha = PF2(parsha_z, 0);
+      Lf.par[0] = par_sun; Lf.par[1] = par_sha;
+      double jmax[2] = {0.0, 0.0};
+      Lf.vcmax[0] = Lf.vcmax[1] = Lf.tpu[0] = Lf.tpu[1] = Lf.kp[0] = Lf.kp[1] = 0.0;
+      Lf.lmr[0] = Lf.lmr[1] = 0.0;
+      double bsun = 0.0, bsha = 0.0, rs_z[2] = {0.0, 0.0}, psn_z[2] = {0.0, 0.0};
+      double wc_z[2] = {0.0, 0.0}, wj_z[2] = {0.0, 0.0}, wp_z[2] = {0.0, 0.0};
+      double qflx_tran_veg = PF(qflx_tran_veg);
+      if (nrad >= 1) {
+        Lf.lmr[0] = PF2(lmrsun_z, 0); Lf.lmr[1] = PF2(lmrsha_z, 0);
+        Lf.vcmax[0] = PF2(vcmax_z_phs, 0); Lf.vcmax[1] = PF2(vcmax_z_phs, 1);
+        Lf.tpu[0] = PF2(tpu_z_phs, 0); Lf.tpu[1] = PF2(tpu_z_phs, 1);
+        Lf.kp[0] = PF2(kp_z_phs, 0); Lf.kp[1] = PF2(kp_z_phs, 1);
+        jmax[0] = WS(W_JMAX0); jmax[1] = WS(W_JMAX1);
+        // leaf-level photosynthesis and stomatal conductance :3477-3714
+        const bool scale_an = (crop == 0.0 || !prm.modifyphoto_and_lmr_forcrop);
+        const int near_noon = f.near_local_noon[gg];
+        double xw[4];
+        phs::CiOut co;
+        double gs_mol[2], an[2], ci_z[2];
+        if (par_sun <= 0.0) {                          // night :3492-3547
+          xw[0] = 1.0; xw[1] = PF2(vegwp, 1); xw[2] = PF2(vegwp, 2); xw[3] = PF2(vegwp, 3);
+          const double gsmin = Lf.medlyn ? Lf.medint : Lf.bbb;
+          const phs::Stress st = phs::calcstress(P, xw, gsmin, gsmin, &qflx_tran_veg);
+          bsun = st.bsun; bsha = st.bsha;
+          const bool pd = f.local_time_lt_noon[gg] != 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { PF2(vegwp, i) = xw[i]; PF2(vegwp_pd, i) = pd ? xw[i] : spval; }
+          const double bb[2] = {bsun, bsha};
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            co.ac[s] = co.aj[s] = co.ap[s] = co.ag[s] = 0.0;
+            an[s] = scale_an ? 0.0 - bb[s] * Lf.lmr[s] : 0.0 - Lf.lmr[s];
+            rs_z[s] = fmin(2.e4, 1.0 / (fmax(bb[s] * gsmin, 1.0)) * cfm);
+            ci_z[s] = 0.0;
+            gs_mol[s] = cfm / rs_z[s];
+          }
+        } else {                                       // day :3549-3711
+          const double esat_tv = svpts;
+          const double ceair = fmin(eah, esat_tv);
+          if (!Lf.medlyn) Lf.rh_can = ceair / esat_tv;
+          else { Lf.rh_can = fmax((esat_tv - ceair), 50.0) * 0.001; PF(vpd_can) = Lf.rh_can; }
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const double qabs = 0.5 * (1.0 - prm.fnps) * Lf.par[s] * 4.6;
+            const phs::Quad q = phs::quadratic(prm.theta_psii, -(qabs + jmax[s]), qabs * jmax[s], &bad_quad);
+            Lf.je[s] = fmin(q.r1, q.r2);
+          }
+          const double vw[4] = {PF2(vegwp, 0), PF2(vegwp, 1), PF2(vegwp, 2), PF2(vegwp, 3)};
+          const phs::HybridOut h = phs::hybrid(P, Lf, vw, (c3 ? 0.7 : 0.4) * Lf.cair, co, &bad_quad, &notbracketed);
+          bsun = h.bsun; bsha = h.bsha;
+          qflx_tran_veg = h.tran;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { PF2(vegwp, i) = h.x[i]; PF2(vegwp_ln, i) = near_noon ? h.x[i] : spval; PF2(vegwp_pd, i) = spval; }
+          const double gsmin = Lf.medlyn ? Lf.medint : Lf.bbb;
+          const double bb[2] = {bsun, bsha};
+          gs_mol[0] = h.gs_sun; gs_mol[1] = h.gs_sha;
+          const double o3g[2] = {PF(o3coefgsun), PF(o3coefgsha)}, o3v[2] = {PF(o3coefvsun), PF(o3coefvsha)};
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            an[s] = co.an[s];
+            if (an[s] < 0.0) gs_mol[s] = fmax(bb[s] * gsmin, 1.0);
+            ci_z[s] = Lf.cair - an[s] * forc_pbot * (1.4 * gs_mol[s] + 1.6 * gb_mol) / (gb_mol * gs_mol[s]);
+            ci_z[s] = fmax(ci_z[s], 1.e-06);
+            const double gs = gs_mol[s] / cfm;
+            rs_z[s] = fmin(1.0 / gs, 2.e4);
+            rs_z[s] = rs_z[s] / o3g[s];
+            psn_z[s] = co.ag[s] * o3v[s];
+            if (co.ac[s] <= co.aj[s] && co.ac[s] <= co.ap[s]) wc_z[s] = psn_z[s];
+            else if (co.aj[s] < co.ac[s] && co.aj[s] <= co.ap[s]) wj_z[s] = psn_z[s];
+            else if (co.ap[s] < co.ac[s] && co.ap[s] < co.aj[s]) wp_z[s] = psn_z[s];
+          }
+          PF2(gs_mol_sun_ln, 0) = near_noon ? gs_mol[0] : spval;
+          PF2(gs_mol_sha_ln, 0) = near_noon ? gs_mol[1] : spval;
+          if (gs_mol[0] < 0.0 || gs_mol[1] < 0.0) report_failure(ds, pp + g.begp0, CTSM_ERR_GS_NEG, 0);
+        }
+        PF2(ac_phs, 0) = co.ac[0]; PF2(ac_phs, 1) = co.ac[1]; PF2(aj_phs, 0) = co.aj[0]; PF2(aj_phs, 1) = co.aj[1];
+        PF2(ap_phs, 0) = co.ap[0]; PF2(ap_phs, 1) = co.ap[1]; PF2(ag_phs, 0) = co.ag[0]; PF2(ag_phs, 1) = co.ag[1];
+        PF2(an_sun, 0) = an[0]; PF2(an_sha, 0) = an[1];
+        PF2(gs_mol_sun, 0) = gs_mol[0]; PF2(gs_mol_sha, 0) = gs_mol[1];
+        PF2(cisun_z, 0) = ci_z[0]; PF2(cisha_z, 0) = ci_z[1];
+        PF2(rssun_z, 0) = rs_z[0]; PF2(rssha_z, 0) = rs_z[1];
+        PF2(psnsun_z, 0) = psn_z[0]; PF2(psnsha_z, 0) = psn_z[1];
+      }
+      if (bad_quad) report_failure(ds, pp + g.begp0, CTSM_ERR_QUADRATIC, 0);
+      if (notbracketed) report_failure(ds, pp + g.begp0, CTSM_ERR_BRENT, 0);
+      // canopy sums :3724-3807 (nlevcan = 1)
+      double rssun, rssha, btran;
+      {
+        const bool scale_lmr = (crop == 0.0 && prm.modifyphoto_and_lmr_forcrop);
+        const double lz[2] = {nrad >= 1 ? PF2(laisun_z, 0) : 0.0, nrad >= 1 ? PF2(laisha_z, 0) : 0.0};
+        const double bb[2] = {bsun, bsha};
+        double psn[2], pwc[2], pwj[2], pwp[2], lmr[2], rs[2], lai[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          double a = 0.0, b_ = 0.0, c_ = 0.0, d_ = 0.0, e_ = 0.0, gsc = 0.0, ll = 0.0;
+          if (nrad >= 1) {
+            a = a + psn_z[s] * lz[s]; b_ = b_ + wc_z[s] * lz[s]; c_ = c_ + wj_z[s] * lz[s]; d_ = d_ + wp_z[s] * lz[s];
+            e_ = scale_lmr ? e_ + Lf.lmr[s] * lz[s] * bb[s] : e_ + Lf.lmr[s] * lz[s];
+            gsc = gsc + lz[s] / (rb + rs_z[s]);
+            ll = ll + lz[s];
+          }
+          lai[s] = ll;
+          if (ll > 0.0) { psn[s] = a / ll; pwc[s] = b_ / ll; pwj[s] = c_ / ll; pwp[s] = d_ / ll; lmr[s] = e_ / ll; rs[s] = ll / gsc - rb; }
+          else { psn[s] = 0.0; pwc[s] = 0.0; pwj[s] = 0.0; pwp[s] = 0.0; lmr[s] = 0.0; rs[s] = 0.0; }
+        }
+        PF(psnsun) = psn[0]; PF(psnsun_wc) = pwc[0]; PF(psnsun_wj) = pwj[0]; PF(psnsun_wp) = pwp[0]; PF(lmrsun) = lmr[0];
+        PF(psnsha) = psn[1]; PF(psnsha_wc) = pwc[1]; PF(psnsha_wj) = pwj[1]; PF(psnsha_wp) = pwp[1]; PF(lmrsha) = lmr[1];
+        rssun = rs[0]; rssha = rs[1];
+        PF(rssun) = rssun; PF(rssha) = rssha;
+        if (lai[1] + lai[0] > 0.0) btran = bsun * (lai[0] / (lai[0] + lai[1])) + bsha * (lai[1] / (lai[0] + lai[1]));
+        else btran = bsun;
+        PF(btran) = btran; PF(bsun) = bsun; PF(bsha) = bsha;
+        PF(qflx_tran_veg) = qflx_tran_veg;
+      }
+      ws[(size_t)W_WORK * wstride + fi] = (double)work;
+    }
   }
 }
 
@@ -1163,19 +1246,28 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   ctx->launches++;
   if (fn > 0) {
     const size_t shbytes = sizeof(double) * 3 * NLEVSOI * ITER_THREADS;
-    int sms = 148, occ = 1;
+    int sms = 148, occ_p = 1, occ_s = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    CUDA_TRY(cudaFuncSetAttribute(canopy_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shbytes));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, canopy_iter_kernel, ITER_THREADS, shbytes);
-    if (occ < 1) occ = 1;
-    const int gridmax = sms * occ * 2;                        // persistent grid: two waves of resident blocks
-    int grid = grid_for(fn + 32 * NBIN, ITER_THREADS);
-    if (grid > gridmax) grid = gridmax;
+    CUDA_TRY(cudaFuncSetAttribute(canopy_phs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shbytes));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, canopy_phs_kernel, ITER_THREADS, shbytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, canopy_step_kernel, STEP_THREADS, 0);
+    if (occ_p < 1) occ_p = 1;
+    if (occ_s < 1) occ_s = 1;
+    // persistent grids: whole waves of resident blocks on the 148 SMs (the bins are padded to warps, hence + 32*NBIN)
+    int grid_p = grid_for(fn + 32 * NBIN, ITER_THREADS), grid_s = grid_for(fn + 32 * NBIN, STEP_THREADS);
+    if (grid_p > sms * occ_p * 2) grid_p = sms * occ_p * 2;
+    if (grid_s > sms * occ_s * 2) grid_s = sms * occ_s * 2;
     int *lin = L.list_a, *lout = L.list_b;
-    for (int itlef = 0; itlef < npass; ++itlef) {
-      canopy_iter_kernel<<<grid, ITER_THREADS, shbytes, s>>>(d, cp, g, fn, itlef, dfilter, ws, wstride, L, lin, lout,
-                                                             ctx->d_status);
+    // step(0, first) opens pass 0; phs(k) solves pass k; step(k+1) closes pass k and opens pass k+1; step(npass, last)
+    for (int itlef = 0; itlef <= npass; ++itlef) {
+      canopy_step_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, fn, itlef, itlef == 0, itlef == npass, dfilter, ws,
+                                                         wstride, L, lin, lout, ctx->d_status);
       ctx->launches++;
+      if (itlef < npass) {
+        canopy_phs_kernel<<<grid_p, ITER_THREADS, shbytes, s>>>(d, cp, g, fn, itlef, dfilter, ws, wstride, L, lout,
+                                                                ctx->d_status);
+        ctx->launches++;
+      }
       int* t = lin; lin = lout; lout = t;
     }
     canopy_final_kernel<<<grid_for(fn, 128), 128, 0, s>>>(d, cp, g, fn, dfilter, ws, wstride, ctx->d_status);
