@@ -62,7 +62,7 @@ enum Slot {
   W_AIR, W_BIR, W_CIR, W_SA_LEAF, W_SA_STEM, W_SA_INT, W_FRS, W_CP_LEAF, W_CP_STEM, W_RSTEM, W_DAYL, W_UR, W_ZLDIS,
   W_TL_INI, W_TS_INI, W_DEL, W_EFEB, W_EFE, W_OBUOLD, W_NMOZ, W_FM, W_EL, W_QSATL, W_QSATLDT, W_DELQ, W_DTH, W_DQH,
   W_TLBEF, W_DT_VEG, W_TEMP1, W_TEMP2, W_TEMP12M, W_TEMP22M, W_WTG, W_WTA0, W_WTL0, W_WTSTEM0, W_WTAL, W_WTGQ, W_WTAQ0,
-  W_WTLQ0, W_WTALQ, W_LW_LEAF, W_LW_STEM, W_ERR, W_JMAX0, W_JMAX1, W_WORK, W_NSLOT
+  W_WTLQ0, W_WTALQ, W_LW_LEAF, W_LW_STEM, W_ERR, W_NSLOT
 };
 
 struct CanopyPrm {
@@ -80,26 +80,50 @@ struct Geo {   // index bases / leading dimensions
   int begp, endp, begc, endc;   // call bounds
 };
 
-// Active lists.  NBIN = 2 x NCLASS bins: night patches in bins 0..NCLASS-1, day patches in the rest, each split by
-// the work the patch did in its previous pass (Newton iterations + ci evaluations; the work of consecutive passes of
-// one patch is strongly correlated), so that the 32 lanes of a warp carry patches of similar cost.  Every bin owns a
-// region of `cap` entries; thread slots are padded to whole warps per bin.
-#define NCLASS 4
-#define NBIN (2 * NCLASS)
+// Active lists of one ITERATION pass: bin 0 = night patches, bin 1 = day patches (they differ in what the pass does
+// for them); every bin owns a region of `cap` entries and thread slots are padded to whole warps per bin.
+#define NBIN 2
+#define BIN_NIGHT 0
+#define BIN_DAY 1
+// PHS task queues of one pass (hybrid_PHS has at most 4 outer passes, PhotosynthesisMod.F90:3896):
+//   ci queue i   (i = 0..3): day patches about to run outer pass i+1 of the ci solve; queue 0 is the day bin itself;
+//   newton queue i (i = 0..2): patches about to run calcstress before outer pass i+2 (queue 0 also holds the night
+//   patches, whose whole PHS solve is one calcstress).
+#define NQ_CI 4
+#define NQ_NT 3
+#define QROW (NBIN + 2 * (NQ_CI + NQ_NT))    // ints per pass: bin counts, queue counts, queue fetch heads
 struct Lists {
-  int* counts;          // [npass + 2][NBIN]
+  int* counts;          // [npass + 2][QROW]: {bin counts[NBIN], ci count[NQ_CI], nt count[NQ_NT], ci head[NQ_CI], nt head[NQ_NT]}
   int* list_a;          // ping: [NBIN][cap]
   int* list_b;          // pong
+  int* q_ci;            // [NQ_CI - 1][cap]  (ci queues 1..3)
+  int* q_nt;            // [NQ_NT][cap]
   int* colflag;         // per column (alloc-based): owns an exposed-veg patch in this call
   int cap;
+  __device__ __forceinline__ int* n_nt(int row, int i) const { return counts + (size_t)row * QROW + NBIN + NQ_CI + i; }
 };
-__device__ __forceinline__ int work_class(int work) {
-#ifdef NO_COST_BINS
-  return 0;
-#else
-  return work < 8 ? 0 : work < 24 ? 1 : work < 72 ? 2 : 3;
-#endif
-}
+
+// Everything the PHS task kernels need about one exposed-vegetation patch, as ONE contiguous record (array of
+// structures): the task kernels pick patches in queue order, i.e. scattered, so a record a lane can stream with
+// 16-byte loads beats the structure-of-arrays layout that suits the uniform kernels.
+struct alignas(128) PhsRec {
+  // constant during the call (canopy_init_kernel)
+  double psi50[4], ck[4], kmax[4];
+  double laisun, laisha, elai, esai, tsai, htop, fdry, forc_rho, forc_pbot, cf;
+  double ksum, ksmp, ksmpg, smpg_mean;
+  double K[NLEVSOI], G[NLEVSOI], S[NLEVSOI];       // k_soil_root(p,:), 1000 z(c,:), smp_l(c,:)
+  double qe, theta_cj, theta_ip, medint, medslope, bbb, mbb, cair, oair, par[2];
+  // per ITERATION pass (canopy_step_kernel)
+  double qsatl, qaf, gb_mol, rh_can, vcmax[2], tpu[2], kp[2], lmr[2], je[2], cp, kc, ko;
+  double x[4];                                      // vegwp at PHS entry (night: x[sun] = 1, the reference's sentinel)
+  double x1sun, x1sha, gs0sun, gs0sha, bsun, bsha, b0sun, b0sha;   // phs::HybridCarry
+  // results of the solve
+  double gs_sun, gs_sha, tran, xo[4];
+  phs::CiOut o;
+  phs::Brent br;                                    // brent_PHS state (rare: lives here, not in registers)
+  int iter1, flags, patch, pad;
+};
+enum { RF_C3 = 1, RF_MEDLYN = 2, RF_NIGHT = 4, RF_SOLVE = 8 };
 
 // warp-aggregated append of `item` to bin `bin` of list (counts row `row`)
 __device__ __forceinline__ void bin_append(const Lists& L, int* list, int row, int bin, int item, unsigned group) {
@@ -107,7 +131,7 @@ __device__ __forceinline__ void bin_append(const Lists& L, int* list, int row, i
   const int lane = threadIdx.x & 31;
   const int leader = __ffs(peers) - 1;
   int b0 = 0;
-  if (lane == leader) b0 = atomicAdd(&L.counts[row * NBIN + bin], __popc(peers));
+  if (lane == leader) b0 = atomicAdd(&L.counts[(size_t)row * QROW + bin], __popc(peers));
   b0 = __shfl_sync(peers, b0, leader);
   list[(size_t)bin * L.cap + b0 + __popc(peers & ((1u << lane) - 1))] = item;
 }
@@ -275,7 +299,7 @@ canopy_colprep_kernel(CanopyDev f, Geo g, const int* __restrict__ colflag) {
 // everything before the ITERATION loop (CanopyFluxesMod.F90:656-1023) + iteration-invariant PHS (:3063-3114)
 __global__ void __launch_bounds__(128)
 canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int* __restrict__ fpos, double* __restrict__ ws,
-                   int wstride, Lists L, DevStatus* ds) {
+                   int wstride, Lists L, PhsRec* __restrict__ rec, DevStatus* ds) {
   const int pp = (g.begp - g.begp0) + blockIdx.x * blockDim.x + threadIdx.x;
   if (pp > g.endp - g.begp0) return;
   // TimeStepInit :1158-1172 and rb1(begp:endp) = 0 (:830): every patch in bounds
@@ -428,11 +452,14 @@ canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int* __restr
   WS(W_WTLQ0) = 0.0; WS(W_WTALQ) = 0.0; WS(W_WTGQ) = 0.0; WS(W_WTAQ0) = 0.0;
   PF(eflx_sh_stem) = 0.0;
 
-  // iteration-invariant part of PhotosynthesisHydraulicStress: root-soil interface conductance :3063-3114
+  // iteration-invariant part of PhotosynthesisHydraulicStress: root-soil interface conductance :3063-3114, and the
+  // constant part of the patch's PHS record (segment parameters, leaf areas, root-zone vectors and their level sums)
+  PhsRec& R = rec[fi];
   {
     const double froot_carbon = PF(froot_carbon), tsl = PF(tsai) + PF(tlai);
     const double rr = f.pft_root_radius[ivt], rd = f.pft_root_density[ivt], frl = f.pft_froot_leaf[ivt], krmax = f.pft_krmax[ivt];
     const double psi50r = f.pft_psi50[(size_t)phs::ROOT * NPFT + ivt], ckr = f.pft_ck[(size_t)phs::ROOT * NPFT + ivt];
+    double ksum = 0.0, ksmp = 0.0, ksmpg = 0.0, smpg = 0.0;
     for (int j = 1; j <= NLEVSOI; ++j) {
       const double rootfr = PF2(rootfr, j - 1);
       double rbd = c_to_b * froot_carbon * rootfr / CF2(dz, j - SNOSOI_LO);
@@ -442,20 +469,50 @@ canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int* __restr
       const double rai = tsl * frl * rootfr;
       const double r_soil = sqrt(1. / (rpi * rld));
       double soil_c = fmin(CF2(hksat, j - 1), CF2(hk_l, j - 1)) / (1.e3 * r_soil);
-      const double fs = phs::plc(CF2(smp_l, j - 1), psi50r, ckr);
-      double root_c = (fs * rai * krmax) / (0.25 + CF2(z, j - SNOSOI_LO));
+      const double sm = CF2(smp_l, j - 1);
+      const double fs = phs::plc(sm, psi50r, ckr);
+      const double zj = CF2(z, j - SNOSOI_LO);
+      double root_c = (fs * rai * krmax) / (0.25 + zj);
       soil_c = fmax(soil_c, 1.e-16);
       root_c = fmax(root_c, 1.e-16);
       PF2(root_conductance, j - 1) = root_c;
       PF2(soil_conductance, j - 1) = soil_c;
       const double rs_resis = 1.0 / soil_c + 1.0 / root_c;
-      PF2(k_soil_root, j - 1) = (rai * rootfr > 0.0 && j > 1) ? 1.0 / rs_resis : 0.0;
+      const double k = (rai * rootfr > 0.0 && j > 1) ? 1.0 / rs_resis : 0.0;
+      PF2(k_soil_root, j - 1) = k;
+      const double gr = 1000.0 * zj;
+      R.K[j - 1] = k; R.G[j - 1] = gr; R.S[j - 1] = sm;
+      ksum += k; ksmp += k * sm; ksmpg += k * (sm - gr); smpg += sm - gr;
     }
+    R.ksum = ksum; R.ksmp = ksmp; R.ksmpg = ksmpg; R.smpg_mean = smpg / NLEVSOI;
+  }
+  const bool night = (PF2(parsun_z, 0) <= 0.0);
+  {
+#pragma unroll
+    for (int sgm = 0; sgm < 4; ++sgm) {
+      R.psi50[sgm] = f.pft_psi50[(size_t)sgm * NPFT + ivt];
+      R.ck[sgm] = f.pft_ck[(size_t)sgm * NPFT + ivt];
+      R.kmax[sgm] = f.pft_kmax[(size_t)sgm * NPFT + ivt];
+    }
+    const double forc_pbot = CF(forc_pbot);
+    R.laisun = PF(laisun); R.laisha = PF(laisha); R.elai = elai; R.esai = esai; R.tsai = PF(tsai); R.htop = htop; R.fdry = PF(fdry);
+    R.forc_rho = CF(forc_rho); R.forc_pbot = forc_pbot;
+    R.cf = forc_pbot / (rgas * 1.e-3 * thm) * 1.e06;
+    const bool c3 = ((int)nearbyint(f.pft_c3psn[ivt]) == 1);
+    R.qe = c3 ? 0.0 : 0.05;
+    R.bbb = c3 ? 10000.0 : 40000.0;
+    R.mbb = f.pft_mbbopt[ivt];
+    R.medint = f.pft_medlynintercept[ivt]; R.medslope = f.pft_medlynslope[ivt];
+    R.theta_cj = f.pft_theta_cj[ivt]; R.theta_ip = prm.theta_ip;
+    R.cair = f.forc_pco2[gg]; R.oair = f.forc_po2[gg];
+    R.par[0] = PF2(parsun_z, 0); R.par[1] = PF2(parsha_z, 0);
+    R.flags = (c3 ? RF_C3 : 0) | (prm.medlyn ? RF_MEDLYN : 0) | (night ? RF_NIGHT : 0);
+    R.patch = pp + g.begp0;
+    R.iter1 = 1;
   }
 
-  // first active list: no work history yet, one night bin and one day bin
-  const bool night = (PF2(parsun_z, 0) <= 0.0);
-  bin_append(L, L.list_a, 0, night ? 0 : NCLASS, fi, __activemask());
+  // first active list: night patches in bin 0, day patches in bin 1
+  bin_append(L, L.list_a, 0, night ? BIN_NIGHT : BIN_DAY, fi, __activemask());
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -471,14 +528,14 @@ canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int* __restr
 __global__ void __launch_bounds__(STEP_THREADS)
 canopy_step_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, int first, int last,
                    const int32_t* __restrict__ filterp, double* __restrict__ ws, int wstride, Lists L,
-                   const int* __restrict__ list_in, int* __restrict__ list_out, DevStatus* ds) {
+                   const int* __restrict__ list_in, int* __restrict__ list_out, PhsRec* __restrict__ rec, DevStatus* ds) {
   const int row = itlef0;
   const double dtime = prm.dtime;
   // thread slots: bins padded to whole warps
   int off[NBIN + 1];
   off[0] = 0;
 #pragma unroll
-  for (int b = 0; b < NBIN; ++b) off[b + 1] = off[b] + ((L.counts[row * NBIN + b] + 31) & ~31);
+  for (int b = 0; b < NBIN; ++b) off[b + 1] = off[b] + ((L.counts[(size_t)row * QROW + b] + 31) & ~31);
   const int total = off[NBIN];
   for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
     const int t = base + threadIdx.x;
@@ -486,11 +543,11 @@ canopy_step_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, int fi
 #pragma unroll
     for (int b = 1; b < NBIN; ++b) bin += (t >= off[b]) ? 1 : 0;
     const int idx = t - off[bin];
-    const bool live = idx < L.counts[row * NBIN + bin];
-    const bool night = bin < NCLASS;
+    const bool live = idx < L.counts[(size_t)row * QROW + bin];
+    const bool night = bin == BIN_NIGHT;
     int fi = 0;
     if (live) fi = list_in[(size_t)bin * L.cap + idx];
-    bool keep = false;
+    bool keep = false, solve = false;
     if (live) {
       const int pp = filterp[fi] - g.begp0;
       const int cc = PF(column) - g.begc0;
@@ -778,38 +835,255 @@ canopy_step_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, int fi
         PF2(vcmax_z_phs, 0) = Lf.vcmax[0]; PF2(vcmax_z_phs, 1) = Lf.vcmax[1];
         PF2(tpu_z_phs, 0) = Lf.tpu[0]; PF2(tpu_z_phs, 1) = Lf.tpu[1];
         PF2(kp_z_phs, 0) = Lf.kp[0]; PF2(kp_z_phs, 1) = Lf.kp[1];
-        WS(W_JMAX0) = jmax[0]; WS(W_JMAX1) = jmax[1];
+        }
+        // hand the patch to the PHS task kernels: the per-pass part of its record (PhotosynthesisMod.F90:3477-3585)
+        {
+          PhsRec& R = rec[fi];
+          const double cfm = forc_pbot / (rgas * 1.e-3 * thm) * 1.e06;
+          R.qsatl = WS(W_QSATL); R.qaf = qaf; R.gb_mol = (1.0 / rb) * cfm;
+          R.cp = Lf.cp; R.kc = Lf.kc; R.ko = Lf.ko;
+#pragma unroll
+          for (int s = 0; s < 2; ++s) { R.vcmax[s] = Lf.vcmax[s]; R.tpu[s] = Lf.tpu[s]; R.kp[s] = Lf.kp[s]; R.lmr[s] = (nrad >= 1) ? Lf.lmr[s] : 0.0; }
+          int flags = R.flags & ~RF_SOLVE;
+          if (nrad >= 1) {
+            flags |= RF_SOLVE;
+            solve = true;
+            const double gsmin = Lf.medlyn ? Lf.medint : Lf.bbb;
+            if (par_sun <= 0.0) {                        // night :3492-3496: one calcstress at the minimum conductance
+              R.x[0] = 1.0; R.x[1] = PF2(vegwp, 1); R.x[2] = PF2(vegwp, 2); R.x[3] = PF2(vegwp, 3);
+              R.gs0sun = gsmin; R.gs0sha = gsmin;
+            } else {                                     // day :3549-3585
+              const double ceair = fmin(eah, svpts);
+              double rh_can;
+              if (!Lf.medlyn) rh_can = ceair / svpts;
+              else { rh_can = fmax((svpts - ceair), 50.0) * 0.001; PF(vpd_can) = rh_can; }
+              R.rh_can = rh_can;
+              bool bad_quad = false;
+#pragma unroll
+              for (int s = 0; s < 2; ++s) {
+                const double qabs = 0.5 * (1.0 - prm.fnps) * Lf.par[s] * 4.6;
+                const phs::Quad q = phs::quadratic(prm.theta_psii, -(qabs + jmax[s]), qabs * jmax[s], &bad_quad);
+                R.je[s] = fmin(q.r1, q.r2);
+              }
+              if (bad_quad) report_failure(ds, pp + g.begp0, CTSM_ERR_QUADRATIC, 0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) R.x[i] = PF2(vegwp, i);
+              phs::HybridCarry H;
+              phs::hybrid_carry_init(H, (c3 ? 0.7 : 0.4) * Lf.cair);
+              R.x1sun = H.x1sun; R.x1sha = H.x1sha; R.gs0sun = H.gs0sun; R.gs0sha = H.gs0sha;
+              R.bsun = H.bsun; R.bsha = H.bsha; R.b0sun = H.b0sun; R.b0sha = H.b0sha;
+              R.iter1 = H.iter1;
+            }
+          }
+          R.flags = flags;
         }
       }
     }
-    // survivors -> work-class bins of pass itlef0 (work of the patch's previous PHS solve; none before the first)
+    // survivors -> night / day bin of pass itlef0; night patches that need a solve also enter newton queue 0
     const bool go = keep && !last;
     const unsigned act = __activemask();
     const unsigned mk = __ballot_sync(act, go);
-    if (go) {
-      const int wk = first ? 0 : (int)ws[(size_t)W_WORK * wstride + fi];
-      bin_append(L, list_out, row + 1, (night ? 0 : NCLASS) + work_class(wk), fi, mk);
+    if (go) bin_append(L, list_out, row + 1, night ? BIN_NIGHT : BIN_DAY, fi, mk);
+    const bool gq = go && night && solve;
+    const unsigned mq = __ballot_sync(act, gq);
+    if (gq) {
+      const int lane = threadIdx.x & 31;
+      const int leader = __ffs(mq) - 1;
+      int b0 = 0;
+      if (lane == leader) b0 = atomicAdd(L.n_nt(row + 1, 0), __popc(mq));
+      b0 = __shfl_sync(mq, b0, leader);
+      L.q_nt[b0 + __popc(mq & ((1u << lane) - 1))] = fi;
     }
   }
 }
 
-#define ITER_THREADS 64
-#ifndef ITER_MINBLOCKS
-#define ITER_MINBLOCKS 4
+// ---------------------------------------------------------------------------------------------
+// PHS task kernels.  A lane carries one task (one calcstress solve / one outer pass of the ci solve) from a queue
+// and is REFILLED from the queue when its task ends, so the 32 lanes of a warp stay busy although the tasks need
+// anything between 1 and 51 Newton iterations (2 and 26 ci_func evaluations).  All scheduling decisions are
+// warp-uniform (taken from ballots), so every __*_sync below is executed by the full warp.
+#define TASK_THREADS 64
+#ifndef NT_MINBLOCKS
+#define NT_MINBLOCKS 8
 #endif
-__global__ void __launch_bounds__(ITER_THREADS, ITER_MINBLOCKS)
-canopy_phs_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, const int32_t* __restrict__ filterp,
-                  double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in, DevStatus* ds) {
-  extern __shared__ double shm[];                       // [3][NLEVSOI][ITER_THREADS]
+#ifndef CI_MINBLOCKS
+#define CI_MINBLOCKS 6
+#endif
+#ifndef REFILL_MIN
+#define REFILL_MIN 4          // refill when at least this many lanes are idle (or nothing else is left to do)
+#endif
+#ifndef FIN_MIN
+#define FIN_MIN 4             // run the calcstress epilogue when at least this many lanes are waiting (for it or for work)
+#endif
+constexpr unsigned FULL = 0xffffffffu;
+
+enum LaneState { LS_IDLE = 0, LS_RUN = 1, LS_FIN = 2 };
+
+__device__ __forceinline__ void load_hydraulics(phs::PhsPatch& P, const PhsRec& R) {
+#pragma unroll
+  for (int s = 0; s < 4; ++s) { P.psi50[s] = R.psi50[s]; P.ck[s] = R.ck[s]; P.kmax[s] = R.kmax[s]; }
+  P.laisun = R.laisun; P.laisha = R.laisha; P.elai = R.elai; P.esai = R.esai; P.tsai = R.tsai; P.htop = R.htop; P.fdry = R.fdry;
+  P.forc_rho = R.forc_rho; P.forc_pbot = R.forc_pbot; P.cf = R.cf;
+  P.qsatl = R.qsatl; P.qaf = R.qaf; P.gb_mol = R.gb_mol;
+  P.ksum = R.ksum; P.ksmp = R.ksmp; P.ksmpg = R.ksmpg; P.smpg_mean = R.smpg_mean;
+}
+
+// push `item` of the lanes in `mask` (warp-uniform) to a queue
+__device__ __forceinline__ void queue_push(int* __restrict__ q, int* __restrict__ count, unsigned mask, bool mine, int item) {
+  if (mask == 0) return;
+  const int lane = threadIdx.x & 31;
+  int b0 = 0;
+  if (lane == 0) b0 = atomicAdd(count, __popc(mask));
+  b0 = __shfl_sync(FULL, b0, 0);
+  if (mine) q[b0 + __popc(mask & ((1u << lane) - 1))] = item;
+}
+
+// calcstress tasks (PhotosynthesisMod.F90:4490-4710).  Day patches return to the ci queue `q_out`; for night patches
+// the task is the whole solve (:3492-3547) and leaves potentials, stress factors and transpiration in the record.
+__global__ void __launch_bounds__(TASK_THREADS, NT_MINBLOCKS)
+phs_newton_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const int* __restrict__ n_in, int* __restrict__ head,
+                  int* __restrict__ q_out, int* __restrict__ n_out) {
+  extern __shared__ double shm[];                       // [2][NLEVSOI][TASK_THREADS]: k_soil_root, 1000 z
   double* sk = shm + threadIdx.x;
-  double* sgv = shm + (size_t)NLEVSOI * ITER_THREADS + threadIdx.x;
-  double* ssv = shm + (size_t)2 * NLEVSOI * ITER_THREADS + threadIdx.x;
+  double* sgv = shm + (size_t)NLEVSOI * TASK_THREADS + threadIdx.x;
+  const int n = *n_in;
+  const int lane = threadIdx.x & 31;
+  int st = LS_IDLE, fi = 0;
+  bool exhausted = (n <= 0);
+  phs::Newton N;
+  phs::PhsPatch P;                                      // only what newton_step reads stays live across iterations
+  P.sk = sk; P.sg = sgv; P.ss = sk; P.stride = TASK_THREADS;
+  for (;;) {
+    const unsigned idle = __ballot_sync(FULL, st == LS_IDLE);
+    const unsigned run = __ballot_sync(FULL, st == LS_RUN);
+    const unsigned fin = __ballot_sync(FULL, st == LS_FIN);
+    if (!exhausted && (__popc(idle) >= REFILL_MIN || (run | fin) == 0)) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(head, __popc(idle));
+      base = __shfl_sync(FULL, base, 0);
+      if (base + __popc(idle) >= n) exhausted = true;
+      if (st == LS_IDLE) {
+        const int my = base + __popc(idle & ((1u << lane) - 1));
+        if (my < n) {
+          fi = q_in[my];
+          const PhsRec& R = rec[fi];
+          load_hydraulics(P, R);
+#pragma unroll 4
+          for (int j = 0; j < NLEVSOI; ++j) { sk[j * TASK_THREADS] = R.K[j]; sgv[j * TASK_THREADS] = R.G[j]; }
+          const double xin[4] = {R.x[0], R.x[1], R.x[2], R.x[3]};
+          st = phs::newton_begin(N, P, xin, R.gs0sun, R.gs0sha) ? LS_RUN : LS_FIN;
+        }
+      }
+      continue;
+    }
+    if ((run | fin) == 0) break;
+    if (fin != 0 && (__popc(fin) + __popc(idle) >= FIN_MIN || run == 0)) {
+      bool day = false;
+      if (st == LS_FIN) {
+        PhsRec& R = rec[fi];
+        phs::PhsPatch Q;                                // full patch for the epilogue (getvegwp needs smp_l as well)
+        load_hydraulics(Q, R);
+        Q.sk = R.K; Q.sg = R.G; Q.ss = R.S; Q.stride = 1;
+        double tran = 0.0;
+        const phs::Stress so = phs::newton_finish(N, Q, R.gs0sun, R.gs0sha, &tran);
+        R.bsun = so.bsun; R.bsha = so.bsha;
+        if (R.flags & RF_NIGHT) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) R.xo[i] = N.x[i];
+          R.tran = tran;
+        } else {
+          day = true;
+        }
+        st = LS_IDLE;
+      }
+      const unsigned pm = __ballot_sync(FULL, day);
+      queue_push(q_out, n_out, pm, day, fi);
+      continue;
+    }
+    if (st == LS_RUN) {
+      if (!phs::newton_step(N, P)) st = LS_FIN;
+    }
+  }
+}
+
+// ci tasks: one outer pass of hybrid_PHS (:3925-4046) per task, one ci_func evaluation per scheduler round.
+__global__ void __launch_bounds__(TASK_THREADS, CI_MINBLOCKS)
+phs_ci_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const int* __restrict__ n_in, int* __restrict__ head,
+              int* __restrict__ q_out, int* __restrict__ n_out, DevStatus* ds) {
+  const int n = *n_in;
+  const int lane = threadIdx.x & 31;
+  int st = LS_IDLE, fi = 0;
+  bool exhausted = (n <= 0);
+  phs::CiLane C;
+  phs::Leaf L;
+  phs::PhsPatch P;                                      // ci_func reads gb_mol and forc_pbot only
+  bool bad = false, nb = false;
+  for (;;) {
+    const unsigned idle = __ballot_sync(FULL, st == LS_IDLE);
+    if (!exhausted && (__popc(idle) >= REFILL_MIN)) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(head, __popc(idle));
+      base = __shfl_sync(FULL, base, 0);
+      if (base + __popc(idle) >= n) exhausted = true;
+      if (st == LS_IDLE) {
+        const int my = base + __popc(idle & ((1u << lane) - 1));
+        if (my < n) {
+          fi = q_in[my];
+          const PhsRec& R = rec[fi];
+          if (R.flags & RF_SOLVE) {                     // (nrad < 1: nothing to solve, :3477)
+            P.gb_mol = R.gb_mol; P.forc_pbot = R.forc_pbot;
+            L.c3 = (R.flags & RF_C3) != 0; L.medlyn = (R.flags & RF_MEDLYN) != 0;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+              L.vcmax[s] = R.vcmax[s]; L.tpu[s] = R.tpu[s]; L.kp[s] = R.kp[s]; L.lmr[s] = R.lmr[s]; L.je[s] = R.je[s]; L.par[s] = R.par[s];
+            }
+            L.cp = R.cp; L.kc = R.kc; L.ko = R.ko; L.qe = R.qe; L.theta_cj = R.theta_cj; L.theta_ip = R.theta_ip;
+            L.medint = R.medint; L.medslope = R.medslope; L.bbb = R.bbb; L.mbb = R.mbb; L.cair = R.cair; L.oair = R.oair;
+            L.rh_can = R.rh_can;
+            phs::HybridCarry H;
+            H.x1sun = R.x1sun; H.x1sha = R.x1sha; H.bsun = R.bsun; H.bsha = R.bsha; H.b0sun = R.b0sun; H.b0sha = R.b0sha;
+            phs::ci_task_begin(C, H);
+            bad = false; nb = false;
+            st = LS_RUN;
+          }
+        }
+      }
+      continue;
+    }
+    if (idle == FULL) break;                            // nothing running and the queue is exhausted
+    bool push = false;
+    if (st == LS_RUN) {
+      PhsRec& R = rec[fi];
+      if (!phs::ci_step(C, R.br, P, L, &bad, &nb)) {
+        // bottom of the outer pass :4034-4046
+        phs::HybridCarry H;
+        H.gs0sun = R.gs0sun; H.gs0sha = R.gs0sha; H.iter1 = R.iter1;
+        const bool lastpass = phs::ci_task_end(C, H);
+        R.x1sun = H.x1sun; R.x1sha = H.x1sha; R.gs0sun = H.gs0sun; R.gs0sha = H.gs0sha;
+        R.b0sun = C.bsun; R.b0sha = C.bsha; R.iter1 = H.iter1;
+        R.gs_sun = C.gs_sun; R.gs_sha = C.gs_sha;
+        R.o = C.o;
+        if (bad) report_failure(ds, R.patch, CTSM_ERR_QUADRATIC, 0);
+        if (nb) report_failure(ds, R.patch, CTSM_ERR_BRENT, 0);
+        push = !lastpass;
+        st = LS_IDLE;
+      }
+    }
+    const unsigned pm = __ballot_sync(FULL, push);
+    queue_push(q_out, n_out, pm, push, fi);
+  }
+}
+
+// the part of PhotosynthesisHydraulicStress that follows the solve (:3497-3547 night, :3587-3714 day, canopy sums
+// :3724-3807), one thread per patch of the pass
+__global__ void __launch_bounds__(128)
+canopy_phs_end_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, const int32_t* __restrict__ filterp, Lists L,
+                      const int* __restrict__ list_in, PhsRec* __restrict__ rec, DevStatus* ds) {
   const int row = itlef0 + 1;
-  // thread slots: bins padded to whole warps
   int off[NBIN + 1];
   off[0] = 0;
 #pragma unroll
-  for (int b = 0; b < NBIN; ++b) off[b + 1] = off[b] + ((L.counts[row * NBIN + b] + 31) & ~31);
+  for (int b = 0; b < NBIN; ++b) off[b + 1] = off[b] + ((L.counts[(size_t)row * QROW + b] + 31) & ~31);
   const int total = off[NBIN];
   for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
     const int t = base + threadIdx.x;
@@ -817,177 +1091,109 @@ canopy_phs_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, const i
 #pragma unroll
     for (int b = 1; b < NBIN; ++b) bin += (t >= off[b]) ? 1 : 0;
     const int idx = t - off[bin];
-    const bool live = idx < L.counts[row * NBIN + bin];
-    const bool night = bin < NCLASS;
-    int fi = 0;
-    if (live) fi = list_in[(size_t)bin * L.cap + idx];
-    (void)night;
-    if (live) {
-      int work = 0;
-      const int pp = filterp[fi] - g.begp0;
-      const int cc = PF(column) - g.begc0;
-      const int gg = PF(gridcell) - g.begg0;
-      const int ivt = PF(itype);
-      const double forc_pbot = CF(forc_pbot), forc_rho = CF(forc_rho);
-      const double thm = PF(thm), elai = PF(elai), esai = PF(esai), htop = PF(htop);
-      const double laisun = PF(laisun), laisha = PF(laisha);
-      const double qaf = PF(qaf), rb = PF(rb1);
-      const double svpts = WS(W_EL);
-      const double eah = forc_pbot * qaf / 0.622;
-      const double qsatl = WS(W_QSATL);
-      bool bad_quad = false, notbracketed = false;
-      phs::PhsPatch P;
-      phs::Leaf Lf;
+    if (idx >= L.counts[(size_t)row * QROW + bin]) continue;
+    const int fi = list_in[(size_t)bin * L.cap + idx];
+    PhsRec& R = rec[fi];
+    const int pp = filterp[fi] - g.begp0;
+    const int gg = PF(gridcell) - g.begg0;
+    const int ivt = PF(itype);
+    const double forc_pbot = R.forc_pbot, cfm = R.cf, gb_mol = R.gb_mol, rb = PF(rb1);
+    const bool medlyn = (R.flags & RF_MEDLYN) != 0;
+    const double crop = f.pft_crop[ivt];
+    const int nrad = PF(nrad);
+    const double lmr_z[2] = {R.lmr[0], R.lmr[1]};
+    double bsun = 0.0, bsha = 0.0, rs_z[2] = {0.0, 0.0}, psn_z[2] = {0.0, 0.0};
+    double wc_z[2] = {0.0, 0.0}, wj_z[2] = {0.0, 0.0}, wp_z[2] = {0.0, 0.0};
+    double qflx_tran_veg = PF(qflx_tran_veg);
+    if (nrad >= 1) {
+      const bool scale_an = (crop == 0.0 || !prm.modifyphoto_and_lmr_forcrop);
+      const int near_noon = f.near_local_noon[gg];
+      const double gsmin = medlyn ? R.medint : R.bbb;
+      phs::CiOut co;
+      double gs_mol[2], an[2], ci_z[2];
+      bsun = R.bsun; bsha = R.bsha;
+      const double bb[2] = {bsun, bsha};
+      if (R.flags & RF_NIGHT) {                          // night :3497-3547
+        qflx_tran_veg = R.tran;
+        const bool pd = f.local_time_lt_noon[gg] != 0;
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        P.psi50[s] = f.pft_psi50[(size_t)s * NPFT + ivt];
-        P.ck[s] = f.pft_ck[(size_t)s * NPFT + ivt];
-        P.kmax[s] = f.pft_kmax[(size_t)s * NPFT + ivt];
-      }
-      P.laisun = laisun; P.laisha = laisha; P.elai = elai; P.esai = esai; P.tsai = PF(tsai); P.htop = htop; P.fdry = PF(fdry);
-      P.forc_rho = forc_rho; P.forc_pbot = forc_pbot;
-      const double cfm = forc_pbot / (rgas * 1.e-3 * thm) * 1.e06;
-      P.cf = cfm;
-      P.qsatl = qsatl; P.qaf = qaf;
-      const double gb_mol = (1.0 / rb) * cfm;
-      P.gb_mol = gb_mol;
-      P.sk = sk; P.sg = sgv; P.ss = ssv; P.stride = ITER_THREADS; P.work = &work;
-      {
-        double ksum = 0.0, ksmp = 0.0, ksmpg = 0.0, smpg = 0.0;
-        for (int j = 0; j < NLEVSOI; ++j) {
-          const double k = PF2(k_soil_root, j), sm = CF2(smp_l, j), gr = 1000.0 * CF2(z, j + 1 - SNOSOI_LO);
-          sk[j * ITER_THREADS] = k; sgv[j * ITER_THREADS] = gr; ssv[j * ITER_THREADS] = sm;
-          ksum += k; ksmp += k * sm; ksmpg += k * (sm - gr); smpg += sm - gr;
-        }
-        P.ksum = ksum; P.ksmp = ksmp; P.ksmpg = ksmpg; P.smpg_mean = smpg / NLEVSOI;
-      }
-      const bool c3 = ((int)nearbyint(f.pft_c3psn[ivt]) == 1);
-      const double crop = f.pft_crop[ivt];
-      Lf.c3 = c3; Lf.medlyn = prm.medlyn != 0;
-      Lf.qe = c3 ? 0.0 : 0.05;
-      Lf.bbb = c3 ? 10000.0 : 40000.0;
-      Lf.mbb = f.pft_mbbopt[ivt];
-      Lf.medint = f.pft_medlynintercept[ivt]; Lf.medslope = f.pft_medlynslope[ivt];
-      Lf.theta_cj = f.pft_theta_cj[ivt]; Lf.theta_ip = prm.theta_ip;
-      Lf.cair = f.forc_pco2[gg]; Lf.oair = f.forc_po2[gg];
-      Lf.kc = PF(kc); Lf.ko = PF(ko); Lf.cp = PF(cp);
-      const int nrad = PF(nrad);
-      const double par_sun = PF2(parsun_z, 0), par_sha = PF2(parsha_z, 0);
-      Lf.par[0] = par_sun; Lf.par[1] = par_sha;
-      double jmax[2] = {0.0, 0.0};
-      Lf.vcmax[0] = Lf.vcmax[1] = Lf.tpu[0] = Lf.tpu[1] = Lf.kp[0] = Lf.kp[1] = 0.0;
-      Lf.lmr[0] = Lf.lmr[1] = 0.0;
-      double bsun = 0.0, bsha = 0.0, rs_z[2] = {0.0, 0.0}, psn_z[2] = {0.0, 0.0};
-      double wc_z[2] = {0.0, 0.0}, wj_z[2] = {0.0, 0.0}, wp_z[2] = {0.0, 0.0};
-      double qflx_tran_veg = PF(qflx_tran_veg);
-      if (nrad >= 1) {
-        Lf.lmr[0] = PF2(lmrsun_z, 0); Lf.lmr[1] = PF2(lmrsha_z, 0);
-        Lf.vcmax[0] = PF2(vcmax_z_phs, 0); Lf.vcmax[1] = PF2(vcmax_z_phs, 1);
-        Lf.tpu[0] = PF2(tpu_z_phs, 0); Lf.tpu[1] = PF2(tpu_z_phs, 1);
-        Lf.kp[0] = PF2(kp_z_phs, 0); Lf.kp[1] = PF2(kp_z_phs, 1);
-        jmax[0] = WS(W_JMAX0); jmax[1] = WS(W_JMAX1);
-        // leaf-level photosynthesis and stomatal conductance :3477-3714
-        const bool scale_an = (crop == 0.0 || !prm.modifyphoto_and_lmr_forcrop);
-        const int near_noon = f.near_local_noon[gg];
-        double xw[4];
-        phs::CiOut co;
-        double gs_mol[2], an[2], ci_z[2];
-        if (par_sun <= 0.0) {                          // night :3492-3547
-          xw[0] = 1.0; xw[1] = PF2(vegwp, 1); xw[2] = PF2(vegwp, 2); xw[3] = PF2(vegwp, 3);
-          const double gsmin = Lf.medlyn ? Lf.medint : Lf.bbb;
-          const phs::Stress st = phs::calcstress(P, xw, gsmin, gsmin, &qflx_tran_veg);
-          bsun = st.bsun; bsha = st.bsha;
-          const bool pd = f.local_time_lt_noon[gg] != 0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { PF2(vegwp, i) = xw[i]; PF2(vegwp_pd, i) = pd ? xw[i] : spval; }
-          const double bb[2] = {bsun, bsha};
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            co.ac[s] = co.aj[s] = co.ap[s] = co.ag[s] = 0.0;
-            an[s] = scale_an ? 0.0 - bb[s] * Lf.lmr[s] : 0.0 - Lf.lmr[s];
-            rs_z[s] = fmin(2.e4, 1.0 / (fmax(bb[s] * gsmin, 1.0)) * cfm);
-            ci_z[s] = 0.0;
-            gs_mol[s] = cfm / rs_z[s];
-          }
-        } else {                                       // day :3549-3711
-          const double esat_tv = svpts;
-          const double ceair = fmin(eah, esat_tv);
-          if (!Lf.medlyn) Lf.rh_can = ceair / esat_tv;
-          else { Lf.rh_can = fmax((esat_tv - ceair), 50.0) * 0.001; PF(vpd_can) = Lf.rh_can; }
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            const double qabs = 0.5 * (1.0 - prm.fnps) * Lf.par[s] * 4.6;
-            const phs::Quad q = phs::quadratic(prm.theta_psii, -(qabs + jmax[s]), qabs * jmax[s], &bad_quad);
-            Lf.je[s] = fmin(q.r1, q.r2);
-          }
-          const double vw[4] = {PF2(vegwp, 0), PF2(vegwp, 1), PF2(vegwp, 2), PF2(vegwp, 3)};
-          const phs::HybridOut h = phs::hybrid(P, Lf, vw, (c3 ? 0.7 : 0.4) * Lf.cair, co, &bad_quad, &notbracketed);
-          bsun = h.bsun; bsha = h.bsha;
-          qflx_tran_veg = h.tran;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { PF2(vegwp, i) = h.x[i]; PF2(vegwp_ln, i) = near_noon ? h.x[i] : spval; PF2(vegwp_pd, i) = spval; }
-          const double gsmin = Lf.medlyn ? Lf.medint : Lf.bbb;
-          const double bb[2] = {bsun, bsha};
-          gs_mol[0] = h.gs_sun; gs_mol[1] = h.gs_sha;
-          const double o3g[2] = {PF(o3coefgsun), PF(o3coefgsha)}, o3v[2] = {PF(o3coefvsun), PF(o3coefvsha)};
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            an[s] = co.an[s];
-            if (an[s] < 0.0) gs_mol[s] = fmax(bb[s] * gsmin, 1.0);
-            ci_z[s] = Lf.cair - an[s] * forc_pbot * (1.4 * gs_mol[s] + 1.6 * gb_mol) / (gb_mol * gs_mol[s]);
-            ci_z[s] = fmax(ci_z[s], 1.e-06);
-            const double gs = gs_mol[s] / cfm;
-            rs_z[s] = fmin(1.0 / gs, 2.e4);
-            rs_z[s] = rs_z[s] / o3g[s];
-            psn_z[s] = co.ag[s] * o3v[s];
-            if (co.ac[s] <= co.aj[s] && co.ac[s] <= co.ap[s]) wc_z[s] = psn_z[s];
-            else if (co.aj[s] < co.ac[s] && co.aj[s] <= co.ap[s]) wj_z[s] = psn_z[s];
-            else if (co.ap[s] < co.ac[s] && co.ap[s] < co.aj[s]) wp_z[s] = psn_z[s];
-          }
-          PF2(gs_mol_sun_ln, 0) = near_noon ? gs_mol[0] : spval;
-          PF2(gs_mol_sha_ln, 0) = near_noon ? gs_mol[1] : spval;
-          if (gs_mol[0] < 0.0 || gs_mol[1] < 0.0) report_failure(ds, pp + g.begp0, CTSM_ERR_GS_NEG, 0);
-        }
-        PF2(ac_phs, 0) = co.ac[0]; PF2(ac_phs, 1) = co.ac[1]; PF2(aj_phs, 0) = co.aj[0]; PF2(aj_phs, 1) = co.aj[1];
-        PF2(ap_phs, 0) = co.ap[0]; PF2(ap_phs, 1) = co.ap[1]; PF2(ag_phs, 0) = co.ag[0]; PF2(ag_phs, 1) = co.ag[1];
-        PF2(an_sun, 0) = an[0]; PF2(an_sha, 0) = an[1];
-        PF2(gs_mol_sun, 0) = gs_mol[0]; PF2(gs_mol_sha, 0) = gs_mol[1];
-        PF2(cisun_z, 0) = ci_z[0]; PF2(cisha_z, 0) = ci_z[1];
-        PF2(rssun_z, 0) = rs_z[0]; PF2(rssha_z, 0) = rs_z[1];
-        PF2(psnsun_z, 0) = psn_z[0]; PF2(psnsha_z, 0) = psn_z[1];
-      }
-      if (bad_quad) report_failure(ds, pp + g.begp0, CTSM_ERR_QUADRATIC, 0);
-      if (notbracketed) report_failure(ds, pp + g.begp0, CTSM_ERR_BRENT, 0);
-      // canopy sums :3724-3807 (nlevcan = 1)
-      double rssun, rssha, btran;
-      {
-        const bool scale_lmr = (crop == 0.0 && prm.modifyphoto_and_lmr_forcrop);
-        const double lz[2] = {nrad >= 1 ? PF2(laisun_z, 0) : 0.0, nrad >= 1 ? PF2(laisha_z, 0) : 0.0};
-        const double bb[2] = {bsun, bsha};
-        double psn[2], pwc[2], pwj[2], pwp[2], lmr[2], rs[2], lai[2];
+        for (int i = 0; i < 4; ++i) { const double xi = R.xo[i]; PF2(vegwp, i) = xi; PF2(vegwp_pd, i) = pd ? xi : spval; }
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-          double a = 0.0, b_ = 0.0, c_ = 0.0, d_ = 0.0, e_ = 0.0, gsc = 0.0, ll = 0.0;
-          if (nrad >= 1) {
-            a = a + psn_z[s] * lz[s]; b_ = b_ + wc_z[s] * lz[s]; c_ = c_ + wj_z[s] * lz[s]; d_ = d_ + wp_z[s] * lz[s];
-            e_ = scale_lmr ? e_ + Lf.lmr[s] * lz[s] * bb[s] : e_ + Lf.lmr[s] * lz[s];
-            gsc = gsc + lz[s] / (rb + rs_z[s]);
-            ll = ll + lz[s];
-          }
-          lai[s] = ll;
-          if (ll > 0.0) { psn[s] = a / ll; pwc[s] = b_ / ll; pwj[s] = c_ / ll; pwp[s] = d_ / ll; lmr[s] = e_ / ll; rs[s] = ll / gsc - rb; }
-          else { psn[s] = 0.0; pwc[s] = 0.0; pwj[s] = 0.0; pwp[s] = 0.0; lmr[s] = 0.0; rs[s] = 0.0; }
+          co.ac[s] = co.aj[s] = co.ap[s] = co.ag[s] = 0.0;
+          an[s] = scale_an ? 0.0 - bb[s] * lmr_z[s] : 0.0 - lmr_z[s];
+          rs_z[s] = fmin(2.e4, 1.0 / (fmax(bb[s] * gsmin, 1.0)) * cfm);
+          ci_z[s] = 0.0;
+          gs_mol[s] = cfm / rs_z[s];
         }
-        PF(psnsun) = psn[0]; PF(psnsun_wc) = pwc[0]; PF(psnsun_wj) = pwj[0]; PF(psnsun_wp) = pwp[0]; PF(lmrsun) = lmr[0];
-        PF(psnsha) = psn[1]; PF(psnsha_wc) = pwc[1]; PF(psnsha_wj) = pwj[1]; PF(psnsha_wp) = pwp[1]; PF(lmrsha) = lmr[1];
-        rssun = rs[0]; rssha = rs[1];
-        PF(rssun) = rssun; PF(rssha) = rssha;
-        if (lai[1] + lai[0] > 0.0) btran = bsun * (lai[0] / (lai[0] + lai[1])) + bsha * (lai[1] / (lai[0] + lai[1]));
-        else btran = bsun;
-        PF(btran) = btran; PF(bsun) = bsun; PF(bsha) = bsha;
-        PF(qflx_tran_veg) = qflx_tran_veg;
+      } else {                                           // day :3587-3711
+        // hybrid_PHS epilogue :4048-4062: potentials and transpiration at the converged conductances
+        phs::PhsPatch Q;
+        load_hydraulics(Q, R);
+        Q.sk = R.K; Q.sg = R.G; Q.ss = R.S; Q.stride = 1;
+        double x[4];
+        double sf = phs::getvegwp(Q, x, R.gs_sun, R.gs_sha);
+        if (sf < 0.0) sf = 0.0;
+        qflx_tran_veg = sf;
+        co = R.o;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { PF2(vegwp, i) = x[i]; PF2(vegwp_ln, i) = near_noon ? x[i] : spval; PF2(vegwp_pd, i) = spval; }
+        gs_mol[0] = R.gs_sun; gs_mol[1] = R.gs_sha;
+        const double cair = R.cair;
+        const double o3g[2] = {PF(o3coefgsun), PF(o3coefgsha)}, o3v[2] = {PF(o3coefvsun), PF(o3coefvsha)};
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          an[s] = co.an[s];
+          if (an[s] < 0.0) gs_mol[s] = fmax(bb[s] * gsmin, 1.0);
+          ci_z[s] = cair - an[s] * forc_pbot * (1.4 * gs_mol[s] + 1.6 * gb_mol) / (gb_mol * gs_mol[s]);
+          ci_z[s] = fmax(ci_z[s], 1.e-06);
+          const double gs = gs_mol[s] / cfm;
+          rs_z[s] = fmin(1.0 / gs, 2.e4);
+          rs_z[s] = rs_z[s] / o3g[s];
+          psn_z[s] = co.ag[s] * o3v[s];
+          if (co.ac[s] <= co.aj[s] && co.ac[s] <= co.ap[s]) wc_z[s] = psn_z[s];
+          else if (co.aj[s] < co.ac[s] && co.aj[s] <= co.ap[s]) wj_z[s] = psn_z[s];
+          else if (co.ap[s] < co.ac[s] && co.ap[s] < co.aj[s]) wp_z[s] = psn_z[s];
+        }
+        PF2(gs_mol_sun_ln, 0) = near_noon ? gs_mol[0] : spval;
+        PF2(gs_mol_sha_ln, 0) = near_noon ? gs_mol[1] : spval;
+        if (gs_mol[0] < 0.0 || gs_mol[1] < 0.0) report_failure(ds, pp + g.begp0, CTSM_ERR_GS_NEG, 0);
       }
-      ws[(size_t)W_WORK * wstride + fi] = (double)work;
+      PF2(ac_phs, 0) = co.ac[0]; PF2(ac_phs, 1) = co.ac[1]; PF2(aj_phs, 0) = co.aj[0]; PF2(aj_phs, 1) = co.aj[1];
+      PF2(ap_phs, 0) = co.ap[0]; PF2(ap_phs, 1) = co.ap[1]; PF2(ag_phs, 0) = co.ag[0]; PF2(ag_phs, 1) = co.ag[1];
+      PF2(an_sun, 0) = an[0]; PF2(an_sha, 0) = an[1];
+      PF2(gs_mol_sun, 0) = gs_mol[0]; PF2(gs_mol_sha, 0) = gs_mol[1];
+      PF2(cisun_z, 0) = ci_z[0]; PF2(cisha_z, 0) = ci_z[1];
+      PF2(rssun_z, 0) = rs_z[0]; PF2(rssha_z, 0) = rs_z[1];
+      PF2(psnsun_z, 0) = psn_z[0]; PF2(psnsha_z, 0) = psn_z[1];
+    }
+    // canopy sums :3724-3807 (nlevcan = 1)
+    {
+      const bool scale_lmr = (crop == 0.0 && prm.modifyphoto_and_lmr_forcrop);
+      const double lz[2] = {nrad >= 1 ? PF2(laisun_z, 0) : 0.0, nrad >= 1 ? PF2(laisha_z, 0) : 0.0};
+      const double bb[2] = {bsun, bsha};
+      double psn[2], pwc[2], pwj[2], pwp[2], lmr[2], rs[2], lai[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        double a = 0.0, b_ = 0.0, c_ = 0.0, d_ = 0.0, e_ = 0.0, gsc = 0.0, ll = 0.0;
+        if (nrad >= 1) {
+          a = a + psn_z[s] * lz[s]; b_ = b_ + wc_z[s] * lz[s]; c_ = c_ + wj_z[s] * lz[s]; d_ = d_ + wp_z[s] * lz[s];
+          e_ = scale_lmr ? e_ + lmr_z[s] * lz[s] * bb[s] : e_ + lmr_z[s] * lz[s];
+          gsc = gsc + lz[s] / (rb + rs_z[s]);
+          ll = ll + lz[s];
+        }
+        lai[s] = ll;
+        if (ll > 0.0) { psn[s] = a / ll; pwc[s] = b_ / ll; pwj[s] = c_ / ll; pwp[s] = d_ / ll; lmr[s] = e_ / ll; rs[s] = ll / gsc - rb; }
+        else { psn[s] = 0.0; pwc[s] = 0.0; pwj[s] = 0.0; pwp[s] = 0.0; lmr[s] = 0.0; rs[s] = 0.0; }
+      }
+      PF(psnsun) = psn[0]; PF(psnsun_wc) = pwc[0]; PF(psnsun_wj) = pwj[0]; PF(psnsun_wp) = pwp[0]; PF(lmrsun) = lmr[0];
+      PF(psnsha) = psn[1]; PF(psnsha_wc) = pwc[1]; PF(psnsha_wj) = pwj[1]; PF(psnsha_wp) = pwp[1]; PF(lmrsha) = lmr[1];
+      PF(rssun) = rs[0]; PF(rssha) = rs[1];
+      double btran;
+      if (lai[1] + lai[0] > 0.0) btran = bsun * (lai[0] / (lai[0] + lai[1])) + bsha * (lai[1] / (lai[0] + lai[1]));
+      else btran = bsun;
+      PF(btran) = btran; PF(bsun) = bsun; PF(bsha) = bsha;
+      PF(qflx_tran_veg) = qflx_tran_veg;
     }
   }
 }
@@ -1216,21 +1422,27 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   const int npb = g.endp - g.begp + 1, ncb = g.endc - g.begc + 1;
   if (npb <= 0) return finish_call(ctx, mem, st);
 
-  // workspace: [W_NSLOT][wstride] doubles + int scratch {fpos[ldp], colflag[ldc], list_a/list_b[NBIN][fn], counts}
+  // workspace: [W_NSLOT][wstride] doubles, the PHS records [fn], and int scratch {fpos[ldp], colflag[ldc],
+  // list_a/list_b[NBIN][fn], ci queues 1..3 [fn], newton queues 0..2 [fn], counters}
   const int wstride = (fn + 31) & ~31;
   const int npass = p.itmax_canopy_fluxes + 1;
-  const size_t n_counts = (size_t)NBIN * (size_t)(npass + 2);
-  int rc = arena_reserve(ctx->arena_scratch, sizeof(double) * (size_t)W_NSLOT * (size_t)(wstride > 0 ? wstride : 32));
+  const size_t n_counts = (size_t)QROW * (size_t)(npass + 2);
+  const size_t ws_bytes = (sizeof(double) * (size_t)W_NSLOT * (size_t)(wstride > 0 ? wstride : 32) + 127) & ~(size_t)127;
+  int rc = arena_reserve(ctx->arena_scratch, ws_bytes + sizeof(PhsRec) * (size_t)(fn > 0 ? fn : 1));
   if (rc) return rc;
-  rc = reserve_ints(ctx->arena_ints, (size_t)g.ldp + (size_t)g.ldc + 2 * (size_t)NBIN * (size_t)fn + n_counts + 64);
+  const size_t nq = (size_t)(2 * NBIN + (NQ_CI - 1) + NQ_NT);
+  rc = reserve_ints(ctx->arena_ints, (size_t)g.ldp + (size_t)g.ldc + nq * (size_t)fn + n_counts + 64);
   if (rc) return rc;
   double* ws = (double*)ctx->arena_scratch.p;
+  PhsRec* rec = (PhsRec*)((char*)ctx->arena_scratch.p + ws_bytes);
   int* ip = (int*)ctx->arena_ints.p;
   int* fpos = ip; ip += g.ldp;
   Lists L;
   L.colflag = ip; ip += g.ldc;
   L.list_a = ip; ip += (size_t)NBIN * fn;
   L.list_b = ip; ip += (size_t)NBIN * fn;
+  L.q_ci = ip; ip += (size_t)(NQ_CI - 1) * fn;
+  L.q_nt = ip; ip += (size_t)NQ_NT * fn;
   L.counts = ip;
   L.cap = fn;
   cudaStream_t s = ctx->stream;
@@ -1242,30 +1454,55 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
     canopy_colprep_kernel<<<grid_for(ncb, 128), 128, 0, s>>>(d, g, L.colflag);
     ctx->launches += 2;
   }
-  canopy_init_kernel<<<grid_for(npb, 128), 128, 0, s>>>(d, cp, g, fn, fpos, ws, wstride, L, ctx->d_status);
+  canopy_init_kernel<<<grid_for(npb, 128), 128, 0, s>>>(d, cp, g, fn, fpos, ws, wstride, L, rec, ctx->d_status);
   ctx->launches++;
   if (fn > 0) {
-    const size_t shbytes = sizeof(double) * 3 * NLEVSOI * ITER_THREADS;
-    int sms = 148, occ_p = 1, occ_s = 1;
+    const size_t shbytes = sizeof(double) * 2 * NLEVSOI * TASK_THREADS;
+    int sms = 148, occ_n = 1, occ_c = 1, occ_s = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    CUDA_TRY(cudaFuncSetAttribute(canopy_phs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shbytes));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, canopy_phs_kernel, ITER_THREADS, shbytes);
+    CUDA_TRY(cudaFuncSetAttribute(phs_newton_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shbytes));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_n, phs_newton_kernel, TASK_THREADS, shbytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, phs_ci_kernel, TASK_THREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, canopy_step_kernel, STEP_THREADS, 0);
-    if (occ_p < 1) occ_p = 1;
+    if (occ_n < 1) occ_n = 1;
+    if (occ_c < 1) occ_c = 1;
     if (occ_s < 1) occ_s = 1;
-    // persistent grids: whole waves of resident blocks on the 148 SMs (the bins are padded to warps, hence + 32*NBIN)
-    int grid_p = grid_for(fn + 32 * NBIN, ITER_THREADS), grid_s = grid_for(fn + 32 * NBIN, STEP_THREADS);
-    if (grid_p > sms * occ_p * 2) grid_p = sms * occ_p * 2;
+    // persistent grids: whole waves of resident blocks on the 148 SMs
+    const int need_t = grid_for(fn, TASK_THREADS);
+    const int grid_n = need_t < sms * occ_n ? need_t : sms * occ_n;
+    const int grid_c = need_t < sms * occ_c ? need_t : sms * occ_c;
+    int grid_s = grid_for(fn + 32 * NBIN, STEP_THREADS);
     if (grid_s > sms * occ_s * 2) grid_s = sms * occ_s * 2;
     int *lin = L.list_a, *lout = L.list_b;
-    // step(0, first) opens pass 0; phs(k) solves pass k; step(k+1) closes pass k and opens pass k+1; step(npass, last)
+    const size_t cap = (size_t)fn;
+    // step(0, first) opens pass 0; the task kernels solve the PHS system of pass k; step(k+1) closes pass k and opens
+    // pass k+1; step(npass, last) only closes
     for (int itlef = 0; itlef <= npass; ++itlef) {
       canopy_step_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, fn, itlef, itlef == 0, itlef == npass, dfilter, ws,
-                                                         wstride, L, lin, lout, ctx->d_status);
+                                                         wstride, L, lin, lout, rec, ctx->d_status);
       ctx->launches++;
       if (itlef < npass) {
-        canopy_phs_kernel<<<grid_p, ITER_THREADS, shbytes, s>>>(d, cp, g, fn, itlef, dfilter, ws, wstride, L, lout,
-                                                                ctx->d_status);
+        const int row = itlef + 1;
+        int* crow = L.counts + (size_t)row * QROW;
+        int* n_ci = crow + NBIN;
+        int* n_nt = n_ci + NQ_CI;
+        int* h_ci = n_nt + NQ_NT;
+        int* h_nt = h_ci + NQ_CI;
+        for (int i = 0; i < NQ_CI; ++i) {
+          // ci queue 0 is the day bin of the pass list; ci queue i > 0 is filled by newton(i - 1)
+          const int* qin = (i == 0) ? lout + (size_t)BIN_DAY * cap : L.q_ci + (size_t)(i - 1) * cap;
+          const int* nin = (i == 0) ? crow + BIN_DAY : n_ci + i;
+          const int io = i < NQ_NT ? i : 0;               // the last outer pass never hands over to calcstress
+          phs_ci_kernel<<<grid_c, TASK_THREADS, 0, s>>>(rec, qin, nin, h_ci + i, L.q_nt + (size_t)io * cap, n_nt + io,
+                                                        ctx->d_status);
+          ctx->launches++;
+          if (i < NQ_NT) {
+            phs_newton_kernel<<<grid_n, TASK_THREADS, shbytes, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, h_nt + i,
+                                                                    L.q_ci + (size_t)i * cap, n_ci + i + 1);
+            ctx->launches++;
+          }
+        }
+        canopy_phs_end_kernel<<<grid_s, 128, 0, s>>>(d, cp, g, fn, itlef, dfilter, L, lout, rec, ctx->d_status);
         ctx->launches++;
       }
       int* t = lin; lin = lout; lout = t;
