@@ -47,10 +47,18 @@ namespace {
 using phs::rgas;
 using phs::tfrz;
 using phs::spval;
-using phs::pw;
-using phs::pw2;
-using phs::dexp;
-using phs::dlog;
+// Transcendentals of the uniform kernels (close / fric / leaf / init / final).  Out of line by default: the inlined
+// libdevice bodies were half of the 150 KB step kernel, and what bounds these kernels is instruction fetch, not the
+// call overhead (-DSTEP_MATH_INLINE restores inlining).  Same arithmetic as phs::pw / dexp / dlog.
+#ifdef STEP_MATH_INLINE
+#define SM_FN __device__ __forceinline__
+#else
+#define SM_FN __device__ __noinline__
+#endif
+SM_FN double pw(double a, double b) { return phs::pw(a, b); }
+SM_FN double pw2(double b) { return phs::pw2(b); }
+SM_FN double dexp(double a) { return exp(a); }
+SM_FN double dlog(double a) { return log(a); }
 constexpr double rpi = 3.14159265358979323846;
 constexpr double sb = 5.67e-8, cpair = 1.00464e3, hvap = 2.501e6, vkc = 0.4, grav = 9.80616;
 constexpr double denice = 0.917e3, denh2o = 1.000e3, c_to_b = 2.0, tlsai_crit = 2.0, alpha_aero = 1.0;
@@ -87,10 +95,11 @@ struct Geo {   // index bases / leading dimensions
 #define BIN_DAY 1
 // PHS task queues of one pass (hybrid_PHS has at most 4 outer passes, PhotosynthesisMod.F90:3896):
 //   ci queue i   (i = 0..3): day patches about to run outer pass i+1 of the ci solve; queue 0 is the day bin itself;
-//   newton queue i (i = 0..2): patches about to run calcstress before outer pass i+2 (queue 0 also holds the night
-//   patches, whose whole PHS solve is one calcstress).
+//   newton queue i (i = 0..3): patches that leave ci pass i+1: either on to calcstress before outer pass i+2, or, when
+//   the ci solve has ended, to the hybrid_PHS epilogue (getvegwp); queue 0 also holds the night patches, whose whole
+//   PHS solve is one calcstress.
 #define NQ_CI 4
-#define NQ_NT 3
+#define NQ_NT 4
 #define QROW (NBIN + 2 * (NQ_CI + NQ_NT))    // ints per pass: bin counts, queue counts, queue fetch heads
 struct Lists {
   int* counts;          // [npass + 2][QROW]: {bin counts[NBIN], ci count[NQ_CI], nt count[NQ_NT], ci head[NQ_CI], nt head[NQ_NT]}
@@ -111,7 +120,10 @@ struct alignas(128) PhsRec {
   double psi50[4], ck[4], kmax[4];
   double laisun, laisha, elai, esai, tsai, htop, fdry, forc_rho, forc_pbot, cf;
   double ksum, ksmp, ksmpg, smpg_mean;
-  double K[NLEVSOI], G[NLEVSOI], S[NLEVSOI];       // k_soil_root(p,:), 1000 z(c,:), smp_l(c,:)
+  double Kv[NLEVSOI], Gv[NLEVSOI], Sv[NLEVSOI];    // k_soil_root(p,:), 1000 z(c,:), smp_l(c,:)
+  __device__ __forceinline__ double K(int j) const { return Kv[j]; }
+  __device__ __forceinline__ double G(int j) const { return Gv[j]; }
+  __device__ __forceinline__ double S(int j) const { return Sv[j]; }
   double qe, theta_cj, theta_ip, medint, medslope, bbb, mbb, cair, oair, par[2];
   // per ITERATION pass (canopy_step_kernel)
   double qsatl, qaf, gb_mol, rh_can, vcmax[2], tpu[2], kp[2], lmr[2], je[2], cp, kc, ko;
@@ -123,7 +135,7 @@ struct alignas(128) PhsRec {
   phs::Brent br;                                    // brent_PHS state (rare: lives here, not in registers)
   int iter1, flags, patch, pad;
 };
-enum { RF_C3 = 1, RF_MEDLYN = 2, RF_NIGHT = 4, RF_SOLVE = 8 };
+enum { RF_C3 = 1, RF_MEDLYN = 2, RF_NIGHT = 4, RF_SOLVE = 8, RF_FINAL = 16 };
 
 // warp-aggregated append of `item` to bin `bin` of list (counts row `row`)
 __device__ __forceinline__ void bin_append(const Lists& L, int* list, int row, int bin, int item, unsigned group) {
@@ -481,7 +493,7 @@ canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int* __restr
       const double k = (rai * rootfr > 0.0 && j > 1) ? 1.0 / rs_resis : 0.0;
       PF2(k_soil_root, j - 1) = k;
       const double gr = 1000.0 * zj;
-      R.K[j - 1] = k; R.G[j - 1] = gr; R.S[j - 1] = sm;
+      R.Kv[j - 1] = k; R.Gv[j - 1] = gr; R.Sv[j - 1] = sm;
       ksum += k; ksmp += k * sm; ksmpg += k * (sm - gr); smpg += sm - gr;
     }
     R.ksum = ksum; R.ksmp = ksmp; R.ksmpg = ksmpg; R.smpg_mean = smpg / NLEVSOI;
@@ -516,47 +528,60 @@ canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
-// ITERATION loop (CanopyFluxesMod.F90:1028-1457), split per pass into two kernels with different shapes:
-//   canopy_step_kernel  (uniform work, 128 threads): closes pass k-1 for every patch that ran it (leaf energy balance
-//                       :1174-1435, convergence test :1439-1457) and, for the survivors, opens pass k
-//                       (FrictionVelocity :1033, resistances :1038-1122, temperature-dependent leaf biochemistry
-//                       PhotosynthesisMod.F90:3118-3469); survivors are appended to the work-class bins of pass k;
-//   canopy_phs_kernel   (irregular work, 64 threads + shared root-zone vectors): the ci / plant-water-potential
-//                       solve of pass k (PhotosynthesisMod.F90:3477-3807) for the binned survivors.
-// Everything that crosses a kernel boundary lives in the patch fields it belongs to or in the SoA workspace.
+// ITERATION loop (CanopyFluxesMod.F90:1028-1457).  One pass k is a chain of small kernels, each with a code footprint
+// that stays resident in the SM's instruction cache (a single fused "step" kernel was 150 KB of straight-line FP64
+// code and spent 3/4 of its cycles waiting for instruction lines, profiles/):
+//   canopy_close_kernel   closes pass k-1 for every patch that ran it (leaf energy balance :1174-1435, convergence test
+//                         :1439-1457) and appends the survivors to the night / day bin of pass k;
+//   canopy_fric_kernel    FrictionVelocity :1033 and the aerodynamic / leaf boundary-layer resistances :1038-1122;
+//   canopy_leaf_kernel    temperature-dependent leaf biochemistry (PhotosynthesisMod.F90:3118-3469) and the per-pass
+//                         part of the patch's PHS record;
+//   phs_ci_kernel / phs_newton_kernel   the ci / plant-water-potential solve (:3477-3807) as lane tasks;
+//   canopy_phs_end_kernel what follows the solve (:3587-3807).
+// Everything that crosses a kernel boundary lives in the patch fields it belongs to, in the SoA workspace or in the
+// PHS record.
 #define STEP_THREADS 128
-__global__ void __launch_bounds__(STEP_THREADS)
-canopy_step_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, int first, int last,
-                   const int32_t* __restrict__ filterp, double* __restrict__ ws, int wstride, Lists L,
-                   const int* __restrict__ list_in, int* __restrict__ list_out, PhsRec* __restrict__ rec, DevStatus* ds) {
-  const int row = itlef0;
-  const double dtime = prm.dtime;
-  // thread slots: bins padded to whole warps
-  int off[NBIN + 1];
+struct ListSlot { int fi; bool live, night; };
+// thread slots of one pass list: bins padded to whole warps
+__device__ __forceinline__ int list_offsets(const Lists& L, int row, int* off) {
   off[0] = 0;
 #pragma unroll
   for (int b = 0; b < NBIN; ++b) off[b + 1] = off[b] + ((L.counts[(size_t)row * QROW + b] + 31) & ~31);
-  const int total = off[NBIN];
-  for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
-    const int t = base + threadIdx.x;
-    int bin = 0;
+  return off[NBIN];
+}
+__device__ __forceinline__ ListSlot list_slot(const Lists& L, int row, const int* off, const int* __restrict__ list, int t) {
+  ListSlot sl;
+  int bin = 0;
 #pragma unroll
-    for (int b = 1; b < NBIN; ++b) bin += (t >= off[b]) ? 1 : 0;
-    const int idx = t - off[bin];
-    const bool live = idx < L.counts[(size_t)row * QROW + bin];
-    const bool night = bin == BIN_NIGHT;
-    int fi = 0;
-    if (live) fi = list_in[(size_t)bin * L.cap + idx];
+  for (int b = 1; b < NBIN; ++b) bin += (t >= off[b]) ? 1 : 0;
+  const int idx = t - off[bin];
+  sl.live = idx < L.counts[(size_t)row * QROW + bin];
+  sl.night = bin == BIN_NIGHT;
+  sl.fi = sl.live ? list[(size_t)bin * L.cap + idx] : 0;
+  return sl;
+}
+
+__global__ void __launch_bounds__(STEP_THREADS)
+canopy_close_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, int first, int last, const int32_t* __restrict__ filterp,
+                    double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in,
+                    int* __restrict__ list_out, DevStatus* ds) {
+  const int row = itlef0;
+  const double dtime = prm.dtime;
+  int off[NBIN + 1];
+  const int total = list_offsets(L, row, off);
+  for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+    const ListSlot sl = list_slot(L, row, off, list_in, base + threadIdx.x);
+    const int fi = sl.fi;
+    const bool live = sl.live, night = sl.night;
     bool keep = false, solve = false;
     if (live) {
       const int pp = filterp[fi] - g.begp0;
       const int cc = PF(column) - g.begc0;
-      const int gg = PF(gridcell) - g.begg0;
-      const int ivt = PF(itype);
       const double forc_pbot = CF(forc_pbot), forc_rho = CF(forc_rho), forc_q = CF(forc_q), t_grnd = CF(t_grnd);
-      const double thm = PF(thm), elai = PF(elai), esai = PF(esai), emv = PF(emv), htop = PF(htop);
+      const double thm = PF(thm), elai = PF(elai), esai = PF(esai), emv = PF(emv);
       const double ur = WS(W_UR), zldis_u = WS(W_ZLDIS);
       keep = true;
+      solve = PF(nrad) >= 1;
       if (!first) {
         // ---- close pass itlef0-1 ----
         const double laisun = PF(laisun), laisha = PF(laisha);
@@ -698,13 +723,44 @@ canopy_step_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, int fi
         keep = !(det < 0.01 && dele < 0.1);
       }
       }
-      if (keep && !last) {
-        // ---- open pass itlef0 ----
-        const double t_veg = PF(t_veg);
-        const double um = PF(um), obu = PF(obu), taf = PF(taf), qaf = PF(qaf);
-        const double displa = PF(displa), z0mv = PF(z0mv);
-        phs::Leaf Lf;
+    }
+    // survivors -> night / day bin of pass itlef0; night patches that need a solve also enter newton queue 0
+    const bool go = keep && !last;
+    const unsigned act = __activemask();
+    const unsigned mk = __ballot_sync(act, go);
+    if (go) bin_append(L, list_out, row + 1, night ? BIN_NIGHT : BIN_DAY, fi, mk);
+    const bool gq = go && night && solve;
+    const unsigned mq = __ballot_sync(act, gq);
+    if (gq) {
+      const int lane = threadIdx.x & 31;
+      const int leader = __ffs(mq) - 1;
+      int b0 = 0;
+      if (lane == leader) b0 = atomicAdd(L.n_nt(row + 1, 0), __popc(mq));
+      b0 = __shfl_sync(mq, b0, leader);
+      L.q_nt[b0 + __popc(mq & ((1u << lane) - 1))] = fi;
+    }
+  }
+}
 
+__global__ void __launch_bounds__(STEP_THREADS)
+canopy_fric_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, const int32_t* __restrict__ filterp,
+                   double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in) {
+  const int row = itlef0 + 1;
+  int off[NBIN + 1];
+  const int total = list_offsets(L, row, off);
+  for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+    const ListSlot sl = list_slot(L, row, off, list_in, base + threadIdx.x);
+    if (!sl.live) continue;
+    const int fi = sl.fi;
+    {
+      const int pp = filterp[fi] - g.begp0;
+      const int cc = PF(column) - g.begc0;
+      const int ivt = PF(itype);
+      const double forc_pbot = CF(forc_pbot), t_grnd = CF(t_grnd);
+      const double elai = PF(elai), esai = PF(esai), htop = PF(htop);
+      const double ur = WS(W_UR);
+      const double um = PF(um), obu = PF(obu), taf = PF(taf), qaf = PF(qaf);
+      const double displa = PF(displa), z0mv = PF(z0mv);
       // FrictionVelocity :1033-1036
       const FricOut fo = friction_velocity(PF(forc_hgt_u_patch), PF(forc_hgt_t_patch), PF(forc_hgt_q_patch), displa, z0mv,
                                            z0mv, z0mv, obu, itlef0 + 1, ur, um, WS(W_FM));
@@ -739,6 +795,32 @@ canopy_step_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, int fi
       PF(rh_af) = eah / svpts;
       PF(rah1) = rah_a; PF(raw1) = raw_a; PF(rah2) = rah_b; PF(raw2) = raw_b;
       PF(vpd) = fmax((svpts - eah), 50.0) * 0.001;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(STEP_THREADS)
+canopy_leaf_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, const int32_t* __restrict__ filterp,
+                   double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in, PhsRec* __restrict__ rec,
+                   DevStatus* ds) {
+  const int row = itlef0 + 1;
+  int off[NBIN + 1];
+  const int total = list_offsets(L, row, off);
+  for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+    const ListSlot sl = list_slot(L, row, off, list_in, base + threadIdx.x);
+    if (!sl.live) continue;
+    const int fi = sl.fi;
+    {
+      {
+      const int pp = filterp[fi] - g.begp0;
+      const int cc = PF(column) - g.begc0;
+      const int gg = PF(gridcell) - g.begg0;
+      const int ivt = PF(itype);
+      const double forc_pbot = CF(forc_pbot), thm = PF(thm);
+      const double t_veg = PF(t_veg), qaf = PF(qaf), rb = PF(rb1);
+      const double svpts = WS(W_EL);
+      const double eah = forc_pbot * qaf / 0.622;
+      phs::Leaf Lf;
       const bool c3 = ((int)nearbyint(f.pft_c3psn[ivt]) == 1);
       const double crop = f.pft_crop[ivt];
       Lf.c3 = c3; Lf.medlyn = prm.medlyn != 0;
@@ -844,10 +926,9 @@ canopy_step_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, int fi
           R.cp = Lf.cp; R.kc = Lf.kc; R.ko = Lf.ko;
 #pragma unroll
           for (int s = 0; s < 2; ++s) { R.vcmax[s] = Lf.vcmax[s]; R.tpu[s] = Lf.tpu[s]; R.kp[s] = Lf.kp[s]; R.lmr[s] = (nrad >= 1) ? Lf.lmr[s] : 0.0; }
-          int flags = R.flags & ~RF_SOLVE;
+          int flags = R.flags & ~(RF_SOLVE | RF_FINAL);
           if (nrad >= 1) {
             flags |= RF_SOLVE;
-            solve = true;
             const double gsmin = Lf.medlyn ? Lf.medint : Lf.bbb;
             if (par_sun <= 0.0) {                        // night :3492-3496: one calcstress at the minimum conductance
               R.x[0] = 1.0; R.x[1] = PF2(vegwp, 1); R.x[2] = PF2(vegwp, 2); R.x[3] = PF2(vegwp, 3);
@@ -879,21 +960,6 @@ canopy_step_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, int fi
         }
       }
     }
-    // survivors -> night / day bin of pass itlef0; night patches that need a solve also enter newton queue 0
-    const bool go = keep && !last;
-    const unsigned act = __activemask();
-    const unsigned mk = __ballot_sync(act, go);
-    if (go) bin_append(L, list_out, row + 1, night ? BIN_NIGHT : BIN_DAY, fi, mk);
-    const bool gq = go && night && solve;
-    const unsigned mq = __ballot_sync(act, gq);
-    if (gq) {
-      const int lane = threadIdx.x & 31;
-      const int leader = __ffs(mq) - 1;
-      int b0 = 0;
-      if (lane == leader) b0 = atomicAdd(L.n_nt(row + 1, 0), __popc(mq));
-      b0 = __shfl_sync(mq, b0, leader);
-      L.q_nt[b0 + __popc(mq & ((1u << lane) - 1))] = fi;
-    }
   }
 }
 
@@ -910,23 +976,14 @@ canopy_step_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, int fi
 #define CI_MINBLOCKS 6
 #endif
 #ifndef REFILL_MIN
-#define REFILL_MIN 4          // refill when at least this many lanes are idle (or nothing else is left to do)
+#define REFILL_MIN 8          // refill when at least this many lanes are idle (or nothing else is left to do)
 #endif
 #ifndef FIN_MIN
-#define FIN_MIN 4             // run the calcstress epilogue when at least this many lanes are waiting (for it or for work)
+#define FIN_MIN 16            // run the calcstress epilogue when at least this many lanes are waiting (for it or for work)
 #endif
 constexpr unsigned FULL = 0xffffffffu;
 
 enum LaneState { LS_IDLE = 0, LS_RUN = 1, LS_FIN = 2 };
-
-__device__ __forceinline__ void load_hydraulics(phs::PhsPatch& P, const PhsRec& R) {
-#pragma unroll
-  for (int s = 0; s < 4; ++s) { P.psi50[s] = R.psi50[s]; P.ck[s] = R.ck[s]; P.kmax[s] = R.kmax[s]; }
-  P.laisun = R.laisun; P.laisha = R.laisha; P.elai = R.elai; P.esai = R.esai; P.tsai = R.tsai; P.htop = R.htop; P.fdry = R.fdry;
-  P.forc_rho = R.forc_rho; P.forc_pbot = R.forc_pbot; P.cf = R.cf;
-  P.qsatl = R.qsatl; P.qaf = R.qaf; P.gb_mol = R.gb_mol;
-  P.ksum = R.ksum; P.ksmp = R.ksmp; P.ksmpg = R.ksmpg; P.smpg_mean = R.smpg_mean;
-}
 
 // push `item` of the lanes in `mask` (warp-uniform) to a queue
 __device__ __forceinline__ void queue_push(int* __restrict__ q, int* __restrict__ count, unsigned mask, bool mine, int item) {
@@ -951,8 +1008,8 @@ phs_newton_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const 
   int st = LS_IDLE, fi = 0;
   bool exhausted = (n <= 0);
   phs::Newton N;
-  phs::PhsPatch P;                                      // only what newton_step reads stays live across iterations
-  P.sk = sk; P.sg = sgv; P.ss = sk; P.stride = TASK_THREADS;
+  phs::NewtonCtx P;                                     // what newton_step reads: registers + shared root-zone vectors
+  P.sk = sk; P.sg = sgv; P.stride = TASK_THREADS;
   for (;;) {
     const unsigned idle = __ballot_sync(FULL, st == LS_IDLE);
     const unsigned run = __ballot_sync(FULL, st == LS_RUN);
@@ -967,11 +1024,17 @@ phs_newton_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const 
         if (my < n) {
           fi = q_in[my];
           const PhsRec& R = rec[fi];
-          load_hydraulics(P, R);
+          if (R.flags & RF_FINAL) {
+            st = LS_FIN;                                // the ci solve has ended: only the epilogue is left
+          } else {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { P.psi50[s] = R.psi50[s]; P.ck[s] = R.ck[s]; }
+            P.laisha = R.laisha; P.ksum = R.ksum; P.ksmp = R.ksmp;
 #pragma unroll 4
-          for (int j = 0; j < NLEVSOI; ++j) { sk[j * TASK_THREADS] = R.K[j]; sgv[j * TASK_THREADS] = R.G[j]; }
-          const double xin[4] = {R.x[0], R.x[1], R.x[2], R.x[3]};
-          st = phs::newton_begin(N, P, xin, R.gs0sun, R.gs0sha) ? LS_RUN : LS_FIN;
+            for (int j = 0; j < NLEVSOI; ++j) { sk[j * TASK_THREADS] = R.Kv[j]; sgv[j * TASK_THREADS] = R.Gv[j]; }
+            const double xin[4] = {R.x[0], R.x[1], R.x[2], R.x[3]};
+            st = phs::newton_begin(N, R, xin, R.gs0sun, R.gs0sha) ? LS_RUN : LS_FIN;
+          }
         }
       }
       continue;
@@ -980,19 +1043,26 @@ phs_newton_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const 
     if (fin != 0 && (__popc(fin) + __popc(idle) >= FIN_MIN || run == 0)) {
       bool day = false;
       if (st == LS_FIN) {
-        PhsRec& R = rec[fi];
-        phs::PhsPatch Q;                                // full patch for the epilogue (getvegwp needs smp_l as well)
-        load_hydraulics(Q, R);
-        Q.sk = R.K; Q.sg = R.G; Q.ss = R.S; Q.stride = 1;
-        double tran = 0.0;
-        const phs::Stress so = phs::newton_finish(N, Q, R.gs0sun, R.gs0sha, &tran);
-        R.bsun = so.bsun; R.bsha = so.bsha;
-        if (R.flags & RF_NIGHT) {
+        PhsRec& R = rec[fi];                            // the epilogues read the patch straight from its record
+        if (R.flags & RF_FINAL) {
+          // hybrid_PHS epilogue :4048-4062: potentials and transpiration at the converged conductances
+          double x[4];
+          double sf = phs::getvegwp(R, x, R.gs_sun, R.gs_sha);
+          if (sf < 0.0) sf = 0.0;
+          R.tran = sf;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) R.xo[i] = N.x[i];
-          R.tran = tran;
+          for (int i = 0; i < 4; ++i) R.xo[i] = x[i];
         } else {
-          day = true;
+          double tran = 0.0;
+          const phs::Stress so = phs::newton_finish(N, R, R.gs0sun, R.gs0sha, &tran);
+          R.bsun = so.bsun; R.bsha = so.bsha;
+          if (R.flags & RF_NIGHT) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) R.xo[i] = N.x[i];
+            R.tran = tran;
+          } else {
+            day = true;
+          }
         }
         st = LS_IDLE;
       }
@@ -1016,7 +1086,7 @@ phs_ci_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const int*
   bool exhausted = (n <= 0);
   phs::CiLane C;
   phs::Leaf L;
-  phs::PhsPatch P;                                      // ci_func reads gb_mol and forc_pbot only
+  struct { double gb_mol, forc_pbot; } P;               // all ci_func reads of the patch besides the leaf state
   bool bad = false, nb = false;
   for (;;) {
     const unsigned idle = __ballot_sync(FULL, st == LS_IDLE);
@@ -1065,7 +1135,8 @@ phs_ci_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const int*
         R.o = C.o;
         if (bad) report_failure(ds, R.patch, CTSM_ERR_QUADRATIC, 0);
         if (nb) report_failure(ds, R.patch, CTSM_ERR_BRENT, 0);
-        push = !lastpass;
+        if (lastpass) R.flags |= RF_FINAL;
+        push = true;
         st = LS_IDLE;
       }
     }
@@ -1127,17 +1198,10 @@ canopy_phs_end_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, con
           gs_mol[s] = cfm / rs_z[s];
         }
       } else {                                           // day :3587-3711
-        // hybrid_PHS epilogue :4048-4062: potentials and transpiration at the converged conductances
-        phs::PhsPatch Q;
-        load_hydraulics(Q, R);
-        Q.sk = R.K; Q.sg = R.G; Q.ss = R.S; Q.stride = 1;
-        double x[4];
-        double sf = phs::getvegwp(Q, x, R.gs_sun, R.gs_sha);
-        if (sf < 0.0) sf = 0.0;
-        qflx_tran_veg = sf;
+        qflx_tran_veg = R.tran;
         co = R.o;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { PF2(vegwp, i) = x[i]; PF2(vegwp_ln, i) = near_noon ? x[i] : spval; PF2(vegwp_pd, i) = spval; }
+        for (int i = 0; i < 4; ++i) { const double xi = R.xo[i]; PF2(vegwp, i) = xi; PF2(vegwp_ln, i) = near_noon ? xi : spval; PF2(vegwp_pd, i) = spval; }
         gs_mol[0] = R.gs_sun; gs_mol[1] = R.gs_sha;
         const double cair = R.cair;
         const double o3g[2] = {PF(o3coefgsun), PF(o3coefgsha)}, o3v[2] = {PF(o3coefvsun), PF(o3coefvsha)};
@@ -1463,7 +1527,7 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
     CUDA_TRY(cudaFuncSetAttribute(phs_newton_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shbytes));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_n, phs_newton_kernel, TASK_THREADS, shbytes);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, phs_ci_kernel, TASK_THREADS, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, canopy_step_kernel, STEP_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, canopy_close_kernel, STEP_THREADS, 0);
     if (occ_n < 1) occ_n = 1;
     if (occ_c < 1) occ_c = 1;
     if (occ_s < 1) occ_s = 1;
@@ -1475,13 +1539,16 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
     if (grid_s > sms * occ_s * 2) grid_s = sms * occ_s * 2;
     int *lin = L.list_a, *lout = L.list_b;
     const size_t cap = (size_t)fn;
-    // step(0, first) opens pass 0; the task kernels solve the PHS system of pass k; step(k+1) closes pass k and opens
-    // pass k+1; step(npass, last) only closes
+    // close(0, first) only builds the list of pass 0; fric/leaf(k) open pass k; the task kernels solve its PHS system;
+    // close(k+1) closes pass k; close(npass, last) only closes
     for (int itlef = 0; itlef <= npass; ++itlef) {
-      canopy_step_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, fn, itlef, itlef == 0, itlef == npass, dfilter, ws,
-                                                         wstride, L, lin, lout, rec, ctx->d_status);
+      canopy_close_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, itlef == 0, itlef == npass, dfilter, ws, wstride,
+                                                          L, lin, lout, ctx->d_status);
       ctx->launches++;
       if (itlef < npass) {
+        canopy_fric_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, dfilter, ws, wstride, L, lout);
+        canopy_leaf_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, dfilter, ws, wstride, L, lout, rec, ctx->d_status);
+        ctx->launches += 2;
         const int row = itlef + 1;
         int* crow = L.counts + (size_t)row * QROW;
         int* n_ci = crow + NBIN;
@@ -1492,15 +1559,13 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
           // ci queue 0 is the day bin of the pass list; ci queue i > 0 is filled by newton(i - 1)
           const int* qin = (i == 0) ? lout + (size_t)BIN_DAY * cap : L.q_ci + (size_t)(i - 1) * cap;
           const int* nin = (i == 0) ? crow + BIN_DAY : n_ci + i;
-          const int io = i < NQ_NT ? i : 0;               // the last outer pass never hands over to calcstress
-          phs_ci_kernel<<<grid_c, TASK_THREADS, 0, s>>>(rec, qin, nin, h_ci + i, L.q_nt + (size_t)io * cap, n_nt + io,
+          phs_ci_kernel<<<grid_c, TASK_THREADS, 0, s>>>(rec, qin, nin, h_ci + i, L.q_nt + (size_t)i * cap, n_nt + i,
                                                         ctx->d_status);
-          ctx->launches++;
-          if (i < NQ_NT) {
-            phs_newton_kernel<<<grid_n, TASK_THREADS, shbytes, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, h_nt + i,
-                                                                    L.q_ci + (size_t)i * cap, n_ci + i + 1);
-            ctx->launches++;
-          }
+          // newton(i): calcstress for the patches that go on to ci pass i + 1, epilogue for those that are done
+          const int io = i + 1 < NQ_CI ? i : 0;           // newton(3) holds epilogue tasks only and pushes nothing
+          phs_newton_kernel<<<grid_n, TASK_THREADS, shbytes, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, h_nt + i,
+                                                                  L.q_ci + (size_t)io * cap, n_ci + (i + 1 < NQ_CI ? i + 1 : 0));
+          ctx->launches += 2;
         }
         canopy_phs_end_kernel<<<grid_s, 128, 0, s>>>(d, cp, g, fn, itlef, dfilter, L, lout, rec, ctx->d_status);
         ctx->launches++;

@@ -76,16 +76,19 @@ PHS_INL Quad quadratic(double a, double b, double c, bool* bad) {
 }
 
 struct Weibull { double v, d; };   // plc and d1plc at one potential
+// x**ck for x <= 0 (never on a physical state: potentials and psi50 are negative); kept out of line
+PHS_FN double pow_nonpos(double r, double ck) { return pow(r, ck); }
 // plc :5186-5187, d1plc :5218-5220 (same pow / exp2 feeds both)
-PHS_FN Weibull weibull(double x, double psi50, double ck, bool want_d) {
+PHS_INL Weibull weibull_inl(double x, double psi50, double ck, bool want_d) {
   Weibull w;
   const double r = x / psi50;
-  const double t = (r > 0.0) ? pw(r, ck) : pow(r, ck);
+  const double t = (r > 0.0) ? pw(r, ck) : pow_nonpos(r, ck);
   const double e = pw2(-t);
   w.d = want_d ? (-ck * 0.6931471805599453 * e * t / x) : 0.0;   // log(2._r8)
   w.v = (e < 0.005) ? 0.0 : e;
   return w;
 }
+PHS_FN Weibull weibull(double x, double psi50, double ck, bool want_d) { return weibull_inl(x, psi50, ck, want_d); }
 PHS_INL double plc(double x, double psi50, double ck) { return weibull(x, psi50, ck, false).v; }
 
 // everything about one patch that the hydraulics needs, held in registers
@@ -107,8 +110,20 @@ struct PhsPatch {
   PHS_INL double S(int j) const { return ss[j * stride]; }
 };
 
+// what one Newton iteration reads of a patch (kept in registers / shared memory by the calcstress task kernel)
+struct NewtonCtx {
+  double psi50[4], ck[4];
+  double laisha, ksum, ksmp;
+  const double* sk;
+  const double* sg;
+  int stride;
+  PHS_INL double K(int j) const { return sk[j * stride]; }
+  PHS_INL double G(int j) const { return sg[j * stride]; }
+};
+
 // getqflx :5128-5146 (havegs = .true.)
-PHS_INL void qflx_from_gs(const PhsPatch& P, double gs_sun, double gs_sha, double& qsun, double& qsha) {
+template <class PT>
+PHS_INL void qflx_from_gs(const PT& P, double gs_sun, double gs_sha, double& qsun, double& qsha) {
   const double wtl = (P.elai + P.esai) * P.gb_mol;
   const double efpot = P.forc_rho * wtl * (P.qsatl - P.qaf);
   qsun = 0.0; qsha = 0.0;
@@ -124,7 +139,8 @@ PHS_INL void qflx_from_gs(const PhsPatch& P, double gs_sun, double gs_sha, doubl
   }
 }
 // getqflx :5148-5158 (havegs = .false.)
-PHS_INL void gs_from_qflx(const PhsPatch& P, double qsun, double qsha, double& gs_sun, double& gs_sha) {
+template <class PT>
+PHS_INL void gs_from_qflx(const PT& P, double qsun, double qsha, double& gs_sun, double& gs_sha) {
   const double wtl = (P.elai + P.esai) * P.gb_mol;
   const double efpot = P.forc_rho * wtl * (P.qsatl - P.qaf);
   gs_sun = (qsun > 0.0) ? P.gb_mol * qsun * P.cf * P.elai / (efpot * P.fdry * P.laisun - qsun * P.cf * P.elai) : 0.0;
@@ -132,7 +148,8 @@ PHS_INL void gs_from_qflx(const PhsPatch& P, double qsun, double qsha, double& g
 }
 
 // getvegwp :4979-5077.  x = {sun, sha, xyl, root}; returns soilflux.
-PHS_FN double getvegwp(const PhsPatch& P, double* x, double gs_sun, double gs_sha) {
+template <class PT>
+PHS_FN double getvegwp(const PT& P, double* x, double gs_sun, double gs_sha) {
   double qsun, qsha;
   qflx_from_gs(P, gs_sun, gs_sha, qsun, qsha);
   const double grav1 = 1000.0 * P.htop;
@@ -166,7 +183,8 @@ struct Newton {
 };
 
 // returns true when Newton iterations are needed (:4573-4575)
-PHS_INL bool newton_begin(Newton& N, const PhsPatch& P, const double* xin, double gs_sun_in, double gs_sha_in) {
+template <class PT>
+PHS_INL bool newton_begin(Newton& N, const PT& P, const double* xin, double gs_sun_in, double gs_sha_in) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) N.x[i] = xin[i];
   N.night = (N.x[SUN] > 0.0);                         // night sentinel :4563-4568
@@ -185,7 +203,8 @@ PHS_INL bool newton_begin(Newton& N, const PhsPatch& P, const double* xin, doubl
 }
 
 // one iteration of the loop :4579-4640; returns true while the iteration continues
-PHS_INL bool newton_step(Newton& N, const PhsPatch& P) {
+template <class PT>
+PHS_INL bool newton_step(Newton& N, const PT& P) {
   double* x = N.x;
   const double qsun = N.qsun, qsha = N.qsha, ls = N.ls, lh = N.lh, tk = N.tk, grav1 = N.grav1;
   const int iter = ++N.iter;
@@ -275,7 +294,8 @@ PHS_INL bool newton_step(Newton& N, const PhsPatch& P) {
 
 // :4642-4708.  On return N.x holds the potentials the reference leaves in x; *tran receives qflx_tran_veg when
 // night (else untouched).
-PHS_INL Stress newton_finish(Newton& N, const PhsPatch& P, double gs_sun_in, double gs_sha_in, double* tran) {
+template <class PT>
+PHS_INL Stress newton_finish(Newton& N, const PT& P, double gs_sun_in, double gs_sha_in, double* tran) {
   Stress out;
   double* x = N.x;
   out.night = N.night;
@@ -327,7 +347,8 @@ struct CiOut {   // what ci_func_PHS leaves in the photosyns arrays
 };
 
 // ci_func_PHS :4227-4486 minus the bflag/calcstress prologue (done by the caller).
-PHS_INL void ci_func(const PhsPatch& P, const Leaf& L, double cisun, double cisha, double bsun, double bsha,
+template <class PT>
+PHS_INL void ci_func(const PT& P, const Leaf& L, double cisun, double cisha, double bsun, double bsha,
                                      double& fsun, double& fsha, double& gs_sun, double& gs_sha, CiOut& o, bool* bad) {
   const double ci[2] = {cisun, cisha};
   const double b[2] = {bsun, bsha};
@@ -432,7 +453,8 @@ PHS_INL void ci_task_begin(CiLane& C, HybridCarry& H) {
 }
 
 // one ci_func evaluation + the control logic that follows it; returns true while the outer pass continues
-PHS_INL bool ci_step(CiLane& C, Brent& B, const PhsPatch& P, const Leaf& L, bool* bad, bool* notbracketed) {
+template <class PT>
+PHS_INL bool ci_step(CiLane& C, Brent& B, const PT& P, const Leaf& L, bool* bad, bool* notbracketed) {
   double fs, fh;
   ci_func(P, L, C.cs, C.ch, C.bsun, C.bsha, fs, fh, C.gs_sun, C.gs_sha, C.o, bad);
   bool top = false;

@@ -143,6 +143,7 @@ static const double tol_lai = .001;
 /* workload statistics for DESIGN.md / tools/phs_stats.py: [0] calcstress calls, [1] Newton iterations,
  * [2] calcstress calls that hit itmax, [3] ci_func_PHS calls, [4] brent_PHS calls, [5] hybrid outer passes */
 long long oracle_phs_counters[8];
+long long oracle_phs_newton_hist[2][64];   /* [night][Newton iterations of one calcstress call] (workload statistics) */
 static long long* per_patch_newton = 0;   /* optional (begp0:endp0) accumulator */
 void oracle_phs_set_patch_counter(long long* p) { per_patch_newton = p; }
 
@@ -305,8 +306,10 @@ static void calcstress(cf_ctx* x, int p, int c, double* xv, double* bsun, double
       if (xv[sun] > xv[xyl]) xv[sun] = xv[xyl];
       if (xv[sha] > xv[xyl]) xv[sha] = xv[xyl];
     }
+    oracle_phs_newton_hist[night][iter < 63 ? iter : 63]++;
   } else {
     flag = 1;
+    oracle_phs_newton_hist[night][0]++;
   }
   if (flag) {
     getvegwp(x, p, c, xv, gb_mol, &gs0sun, &gs0sha, qsatl, qaf, &soilflux);

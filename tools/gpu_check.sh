@@ -7,7 +7,7 @@ python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > $out/${tag}_pytest.log
 for v in "" "$@"; do
   lib=$PWD/ctsm_b200/lib/libctsm_b200${v:+_$v}.so
   [ -f $lib ] || continue
-  for size in f09 f02; do
+  for size in ${SIZES:-f02}; do
     CTSM_B200_LIB=$lib python bench.py --size $size --routines canopyfluxes --steps 3 --warmup 3 --no-e2e --no-cpu > $out/${tag}_bench_${size}_canopy${v:+_$v}.json 2>> $out/${tag}_err.log
   done
   CTSM_B200_LIB=$lib ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $out/${tag}_launches${v:+_$v}.csv \
