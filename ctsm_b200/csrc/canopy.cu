@@ -981,6 +981,7 @@ canopy_leaf_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, const int32_t*
 #ifndef FIN_MIN
 #define FIN_MIN 16            // run the calcstress epilogue when at least this many lanes are waiting (for it or for work)
 #endif
+#define QUAD_MAX 16384        // calcstress queues up to this size run four lanes per solve (phs_newton_quad_kernel)
 constexpr unsigned FULL = 0xffffffffu;
 
 enum LaneState { LS_IDLE = 0, LS_RUN = 1, LS_FIN = 2 };
@@ -1004,9 +1005,10 @@ phs_newton_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const 
   double* sk = shm + threadIdx.x;
   double* sgv = shm + (size_t)NLEVSOI * TASK_THREADS + threadIdx.x;
   const int n = *n_in;
+  if (n <= QUAD_MAX) return;                            // small queues: phs_newton_quad_kernel
   const int lane = threadIdx.x & 31;
   int st = LS_IDLE, fi = 0;
-  bool exhausted = (n <= 0);
+  bool exhausted = false;
   phs::Newton N;
   phs::NewtonCtx P;                                     // what newton_step reads: registers + shared root-zone vectors
   P.sk = sk; P.sg = sgv; P.stride = TASK_THREADS;
@@ -1072,6 +1074,73 @@ phs_newton_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const 
     }
     if (st == LS_RUN) {
       if (!phs::newton_step(N, P)) st = LS_FIN;
+    }
+  }
+}
+
+// Small calcstress queues (the late ITERATION passes: a few thousand hard patches, and every pass waits for the
+// slowest of them, 51 Newton iterations) are latency bound, so four lanes share one solve: each lane evaluates the
+// Weibull curve of one plant segment (60 % of the dependent chain of an iteration) and the quad exchanges them by
+// shuffle; everything else is computed redundantly, i.e. identically, by the four lanes.
+struct WeibullQuad {
+  unsigned qmask;
+  int sgm, base;
+  __device__ __forceinline__ void operator()(const double* x, const double* psi50, const double* ck, phs::Weibull* w) const {
+    double xs = x[0], ps = psi50[0], cs = ck[0];
+#pragma unroll
+    for (int s = 1; s < 4; ++s) if (sgm == s) { xs = x[s]; ps = psi50[s]; cs = ck[s]; }
+    const phs::Weibull mine = phs::weibull(xs, ps, cs, true);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      w[s].v = __shfl_sync(qmask, mine.v, base + s);
+      w[s].d = __shfl_sync(qmask, mine.d, base + s);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(128)
+phs_newton_quad_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const int* __restrict__ n_in,
+                       int* __restrict__ q_out, int* __restrict__ n_out) {
+  const int n = *n_in;
+  if (n <= 0 || n > QUAD_MAX) return;                   // large queues: phs_newton_kernel
+  const int lane = threadIdx.x & 31;
+  WeibullQuad wb;
+  wb.sgm = lane & 3; wb.base = lane & ~3; wb.qmask = 0xFu << wb.base;
+  const int quad = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, nquads = (gridDim.x * blockDim.x) >> 2;
+  for (int task = quad; task < n; task += nquads) {
+    const int fi = q_in[task];
+    PhsRec& R = rec[fi];
+    const int flags = R.flags;
+    const double gs0sun = R.gs0sun, gs0sha = R.gs0sha;
+    if (flags & RF_FINAL) {
+      double x[4];
+      double sf = phs::getvegwp(R, x, R.gs_sun, R.gs_sha);
+      if (sf < 0.0) sf = 0.0;
+      __syncwarp(wb.qmask);
+      if (wb.sgm == 0) {
+        R.tran = sf;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) R.xo[i] = x[i];
+      }
+      continue;
+    }
+    phs::Newton N;
+    const double xin[4] = {R.x[0], R.x[1], R.x[2], R.x[3]};
+    if (phs::newton_begin(N, R, xin, gs0sun, gs0sha)) {
+      while (phs::newton_step(N, R, wb)) {}
+    }
+    double tran = 0.0;
+    const phs::Stress so = phs::newton_finish(N, R, gs0sun, gs0sha, &tran);
+    __syncwarp(wb.qmask);
+    if (wb.sgm == 0) {
+      R.bsun = so.bsun; R.bsha = so.bsha;
+      if (flags & RF_NIGHT) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) R.xo[i] = N.x[i];
+        R.tran = tran;
+      } else {
+        q_out[atomicAdd(n_out, 1)] = fi;
+      }
     }
   }
 }
@@ -1146,83 +1215,69 @@ phs_ci_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const int*
 }
 
 // the part of PhotosynthesisHydraulicStress that follows the solve (:3497-3547 night, :3587-3714 day, canopy sums
-// :3724-3807), one thread per patch of the pass
-__global__ void __launch_bounds__(128)
-canopy_phs_end_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, const int32_t* __restrict__ filterp, Lists L,
-                      const int* __restrict__ list_in, PhsRec* __restrict__ rec, DevStatus* ds) {
-  const int row = itlef0 + 1;
-  int off[NBIN + 1];
-  off[0] = 0;
+// :3724-3807) for one patch.  Between passes only what the next pass reads is stored (ALL = false: vegwp, rssun, rssha,
+// btran, qflx_tran_veg); the patch's record keeps the state of its last pass, from which canopy_final_kernel writes the
+// full set of outputs once (ALL = true) - the reference overwrites them on every pass and the last one survives.
+template <bool ALL>
+__device__ __forceinline__ void phs_outputs(const CanopyDev& f, const CanopyPrm& prm, const Geo& g, const PhsRec& R, int pp,
+                                            DevStatus* ds) {
+  const int gg = PF(gridcell) - g.begg0;
+  const int ivt = PF(itype);
+  const double forc_pbot = R.forc_pbot, cfm = R.cf, gb_mol = R.gb_mol, rb = PF(rb1);
+  const bool medlyn = (R.flags & RF_MEDLYN) != 0;
+  const double crop = f.pft_crop[ivt];
+  const int nrad = PF(nrad);
+  const double lmr_z[2] = {R.lmr[0], R.lmr[1]};
+  double bsun = 0.0, bsha = 0.0, rs_z[2] = {0.0, 0.0}, psn_z[2] = {0.0, 0.0};
+  double wc_z[2] = {0.0, 0.0}, wj_z[2] = {0.0, 0.0}, wp_z[2] = {0.0, 0.0};
+  double qflx_tran_veg = PF(qflx_tran_veg);
+  if (nrad >= 1) {
+    const bool scale_an = (crop == 0.0 || !prm.modifyphoto_and_lmr_forcrop);
+    const int near_noon = f.near_local_noon[gg];
+    const double gsmin = medlyn ? R.medint : R.bbb;
+    phs::CiOut co;
+    double gs_mol[2], an[2], ci_z[2];
+    bsun = R.bsun; bsha = R.bsha;
+    const double bb[2] = {bsun, bsha};
+    if (R.flags & RF_NIGHT) {                          // night :3497-3547
+      qflx_tran_veg = R.tran;
+      const bool pd = f.local_time_lt_noon[gg] != 0;
 #pragma unroll
-  for (int b = 0; b < NBIN; ++b) off[b + 1] = off[b] + ((L.counts[(size_t)row * QROW + b] + 31) & ~31);
-  const int total = off[NBIN];
-  for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
-    const int t = base + threadIdx.x;
-    int bin = 0;
+      for (int i = 0; i < 4; ++i) { const double xi = R.xo[i]; PF2(vegwp, i) = xi; if (ALL) PF2(vegwp_pd, i) = pd ? xi : spval; }
 #pragma unroll
-    for (int b = 1; b < NBIN; ++b) bin += (t >= off[b]) ? 1 : 0;
-    const int idx = t - off[bin];
-    if (idx >= L.counts[(size_t)row * QROW + bin]) continue;
-    const int fi = list_in[(size_t)bin * L.cap + idx];
-    PhsRec& R = rec[fi];
-    const int pp = filterp[fi] - g.begp0;
-    const int gg = PF(gridcell) - g.begg0;
-    const int ivt = PF(itype);
-    const double forc_pbot = R.forc_pbot, cfm = R.cf, gb_mol = R.gb_mol, rb = PF(rb1);
-    const bool medlyn = (R.flags & RF_MEDLYN) != 0;
-    const double crop = f.pft_crop[ivt];
-    const int nrad = PF(nrad);
-    const double lmr_z[2] = {R.lmr[0], R.lmr[1]};
-    double bsun = 0.0, bsha = 0.0, rs_z[2] = {0.0, 0.0}, psn_z[2] = {0.0, 0.0};
-    double wc_z[2] = {0.0, 0.0}, wj_z[2] = {0.0, 0.0}, wp_z[2] = {0.0, 0.0};
-    double qflx_tran_veg = PF(qflx_tran_veg);
-    if (nrad >= 1) {
-      const bool scale_an = (crop == 0.0 || !prm.modifyphoto_and_lmr_forcrop);
-      const int near_noon = f.near_local_noon[gg];
-      const double gsmin = medlyn ? R.medint : R.bbb;
-      phs::CiOut co;
-      double gs_mol[2], an[2], ci_z[2];
-      bsun = R.bsun; bsha = R.bsha;
-      const double bb[2] = {bsun, bsha};
-      if (R.flags & RF_NIGHT) {                          // night :3497-3547
-        qflx_tran_veg = R.tran;
-        const bool pd = f.local_time_lt_noon[gg] != 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { const double xi = R.xo[i]; PF2(vegwp, i) = xi; PF2(vegwp_pd, i) = pd ? xi : spval; }
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          co.ac[s] = co.aj[s] = co.ap[s] = co.ag[s] = 0.0;
-          an[s] = scale_an ? 0.0 - bb[s] * lmr_z[s] : 0.0 - lmr_z[s];
-          rs_z[s] = fmin(2.e4, 1.0 / (fmax(bb[s] * gsmin, 1.0)) * cfm);
-          ci_z[s] = 0.0;
-          gs_mol[s] = cfm / rs_z[s];
-        }
-      } else {                                           // day :3587-3711
-        qflx_tran_veg = R.tran;
-        co = R.o;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { const double xi = R.xo[i]; PF2(vegwp, i) = xi; PF2(vegwp_ln, i) = near_noon ? xi : spval; PF2(vegwp_pd, i) = spval; }
-        gs_mol[0] = R.gs_sun; gs_mol[1] = R.gs_sha;
-        const double cair = R.cair;
-        const double o3g[2] = {PF(o3coefgsun), PF(o3coefgsha)}, o3v[2] = {PF(o3coefvsun), PF(o3coefvsha)};
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          an[s] = co.an[s];
-          if (an[s] < 0.0) gs_mol[s] = fmax(bb[s] * gsmin, 1.0);
-          ci_z[s] = cair - an[s] * forc_pbot * (1.4 * gs_mol[s] + 1.6 * gb_mol) / (gb_mol * gs_mol[s]);
-          ci_z[s] = fmax(ci_z[s], 1.e-06);
-          const double gs = gs_mol[s] / cfm;
-          rs_z[s] = fmin(1.0 / gs, 2.e4);
-          rs_z[s] = rs_z[s] / o3g[s];
-          psn_z[s] = co.ag[s] * o3v[s];
-          if (co.ac[s] <= co.aj[s] && co.ac[s] <= co.ap[s]) wc_z[s] = psn_z[s];
-          else if (co.aj[s] < co.ac[s] && co.aj[s] <= co.ap[s]) wj_z[s] = psn_z[s];
-          else if (co.ap[s] < co.ac[s] && co.ap[s] < co.aj[s]) wp_z[s] = psn_z[s];
-        }
-        PF2(gs_mol_sun_ln, 0) = near_noon ? gs_mol[0] : spval;
-        PF2(gs_mol_sha_ln, 0) = near_noon ? gs_mol[1] : spval;
-        if (gs_mol[0] < 0.0 || gs_mol[1] < 0.0) report_failure(ds, pp + g.begp0, CTSM_ERR_GS_NEG, 0);
+      for (int s = 0; s < 2; ++s) {
+        co.ac[s] = co.aj[s] = co.ap[s] = co.ag[s] = 0.0;
+        an[s] = scale_an ? 0.0 - bb[s] * lmr_z[s] : 0.0 - lmr_z[s];
+        rs_z[s] = fmin(2.e4, 1.0 / (fmax(bb[s] * gsmin, 1.0)) * cfm);
+        ci_z[s] = 0.0;
+        gs_mol[s] = cfm / rs_z[s];
       }
+    } else {                                           // day :3587-3711
+      qflx_tran_veg = R.tran;
+      co = R.o;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const double xi = R.xo[i]; PF2(vegwp, i) = xi; if (ALL) { PF2(vegwp_ln, i) = near_noon ? xi : spval; PF2(vegwp_pd, i) = spval; } }
+      gs_mol[0] = R.gs_sun; gs_mol[1] = R.gs_sha;
+      const double cair = R.cair;
+      const double o3g[2] = {PF(o3coefgsun), PF(o3coefgsha)}, o3v[2] = {PF(o3coefvsun), PF(o3coefvsha)};
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        an[s] = co.an[s];
+        if (an[s] < 0.0) gs_mol[s] = fmax(bb[s] * gsmin, 1.0);
+        ci_z[s] = cair - an[s] * forc_pbot * (1.4 * gs_mol[s] + 1.6 * gb_mol) / (gb_mol * gs_mol[s]);
+        ci_z[s] = fmax(ci_z[s], 1.e-06);
+        const double gs = gs_mol[s] / cfm;
+        rs_z[s] = fmin(1.0 / gs, 2.e4);
+        rs_z[s] = rs_z[s] / o3g[s];
+        psn_z[s] = co.ag[s] * o3v[s];
+        if (co.ac[s] <= co.aj[s] && co.ac[s] <= co.ap[s]) wc_z[s] = psn_z[s];
+        else if (co.aj[s] < co.ac[s] && co.aj[s] <= co.ap[s]) wj_z[s] = psn_z[s];
+        else if (co.ap[s] < co.ac[s] && co.ap[s] < co.aj[s]) wp_z[s] = psn_z[s];
+      }
+      if (ALL) { PF2(gs_mol_sun_ln, 0) = near_noon ? gs_mol[0] : spval; PF2(gs_mol_sha_ln, 0) = near_noon ? gs_mol[1] : spval; }
+      if (!ALL && (gs_mol[0] < 0.0 || gs_mol[1] < 0.0)) report_failure(ds, pp + g.begp0, CTSM_ERR_GS_NEG, 0);
+    }
+    if (ALL) {
       PF2(ac_phs, 0) = co.ac[0]; PF2(ac_phs, 1) = co.ac[1]; PF2(aj_phs, 0) = co.aj[0]; PF2(aj_phs, 1) = co.aj[1];
       PF2(ap_phs, 0) = co.ap[0]; PF2(ap_phs, 1) = co.ap[1]; PF2(ag_phs, 0) = co.ag[0]; PF2(ag_phs, 1) = co.ag[1];
       PF2(an_sun, 0) = an[0]; PF2(an_sha, 0) = an[1];
@@ -1231,34 +1286,50 @@ canopy_phs_end_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, con
       PF2(rssun_z, 0) = rs_z[0]; PF2(rssha_z, 0) = rs_z[1];
       PF2(psnsun_z, 0) = psn_z[0]; PF2(psnsha_z, 0) = psn_z[1];
     }
-    // canopy sums :3724-3807 (nlevcan = 1)
-    {
-      const bool scale_lmr = (crop == 0.0 && prm.modifyphoto_and_lmr_forcrop);
-      const double lz[2] = {nrad >= 1 ? PF2(laisun_z, 0) : 0.0, nrad >= 1 ? PF2(laisha_z, 0) : 0.0};
-      const double bb[2] = {bsun, bsha};
-      double psn[2], pwc[2], pwj[2], pwp[2], lmr[2], rs[2], lai[2];
+  }
+  // canopy sums :3724-3807 (nlevcan = 1)
+  {
+    const bool scale_lmr = (crop == 0.0 && prm.modifyphoto_and_lmr_forcrop);
+    const double lz[2] = {nrad >= 1 ? PF2(laisun_z, 0) : 0.0, nrad >= 1 ? PF2(laisha_z, 0) : 0.0};
+    const double bb[2] = {bsun, bsha};
+    double psn[2], pwc[2], pwj[2], pwp[2], lmr[2], rs[2], lai[2];
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        double a = 0.0, b_ = 0.0, c_ = 0.0, d_ = 0.0, e_ = 0.0, gsc = 0.0, ll = 0.0;
-        if (nrad >= 1) {
-          a = a + psn_z[s] * lz[s]; b_ = b_ + wc_z[s] * lz[s]; c_ = c_ + wj_z[s] * lz[s]; d_ = d_ + wp_z[s] * lz[s];
-          e_ = scale_lmr ? e_ + lmr_z[s] * lz[s] * bb[s] : e_ + lmr_z[s] * lz[s];
-          gsc = gsc + lz[s] / (rb + rs_z[s]);
-          ll = ll + lz[s];
-        }
-        lai[s] = ll;
-        if (ll > 0.0) { psn[s] = a / ll; pwc[s] = b_ / ll; pwj[s] = c_ / ll; pwp[s] = d_ / ll; lmr[s] = e_ / ll; rs[s] = ll / gsc - rb; }
-        else { psn[s] = 0.0; pwc[s] = 0.0; pwj[s] = 0.0; pwp[s] = 0.0; lmr[s] = 0.0; rs[s] = 0.0; }
+    for (int s = 0; s < 2; ++s) {
+      double a = 0.0, b_ = 0.0, c_ = 0.0, d_ = 0.0, e_ = 0.0, gsc = 0.0, ll = 0.0;
+      if (nrad >= 1) {
+        a = a + psn_z[s] * lz[s]; b_ = b_ + wc_z[s] * lz[s]; c_ = c_ + wj_z[s] * lz[s]; d_ = d_ + wp_z[s] * lz[s];
+        e_ = scale_lmr ? e_ + lmr_z[s] * lz[s] * bb[s] : e_ + lmr_z[s] * lz[s];
+        gsc = gsc + lz[s] / (rb + rs_z[s]);
+        ll = ll + lz[s];
       }
+      lai[s] = ll;
+      if (ll > 0.0) { psn[s] = a / ll; pwc[s] = b_ / ll; pwj[s] = c_ / ll; pwp[s] = d_ / ll; lmr[s] = e_ / ll; rs[s] = ll / gsc - rb; }
+      else { psn[s] = 0.0; pwc[s] = 0.0; pwj[s] = 0.0; pwp[s] = 0.0; lmr[s] = 0.0; rs[s] = 0.0; }
+    }
+    if (ALL) {
       PF(psnsun) = psn[0]; PF(psnsun_wc) = pwc[0]; PF(psnsun_wj) = pwj[0]; PF(psnsun_wp) = pwp[0]; PF(lmrsun) = lmr[0];
       PF(psnsha) = psn[1]; PF(psnsha_wc) = pwc[1]; PF(psnsha_wj) = pwj[1]; PF(psnsha_wp) = pwp[1]; PF(lmrsha) = lmr[1];
-      PF(rssun) = rs[0]; PF(rssha) = rs[1];
-      double btran;
-      if (lai[1] + lai[0] > 0.0) btran = bsun * (lai[0] / (lai[0] + lai[1])) + bsha * (lai[1] / (lai[0] + lai[1]));
-      else btran = bsun;
-      PF(btran) = btran; PF(bsun) = bsun; PF(bsha) = bsha;
-      PF(qflx_tran_veg) = qflx_tran_veg;
     }
+    PF(rssun) = rs[0]; PF(rssha) = rs[1];
+    double btran;
+    if (lai[1] + lai[0] > 0.0) btran = bsun * (lai[0] / (lai[0] + lai[1])) + bsha * (lai[1] / (lai[0] + lai[1]));
+    else btran = bsun;
+    PF(btran) = btran;
+    if (ALL) { PF(bsun) = bsun; PF(bsha) = bsha; }
+    PF(qflx_tran_veg) = qflx_tran_veg;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+canopy_phs_end_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, const int32_t* __restrict__ filterp, Lists L,
+                      const int* __restrict__ list_in, PhsRec* __restrict__ rec, DevStatus* ds) {
+  const int row = itlef0 + 1;
+  int off[NBIN + 1];
+  const int total = list_offsets(L, row, off);
+  for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+    const ListSlot sl = list_slot(L, row, off, list_in, base + threadIdx.x);
+    if (!sl.live) continue;
+    phs_outputs<false>(f, prm, g, rec[sl.fi], filterp[sl.fi] - g.begp0, ds);
   }
 }
 
@@ -1266,10 +1337,11 @@ canopy_phs_end_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, con
 // after the ITERATION loop (CanopyFluxesMod.F90:1464-1760)
 __global__ void __launch_bounds__(128)
 canopy_final_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int32_t* __restrict__ filterp,
-                    const double* __restrict__ ws, int wstride, DevStatus* ds) {
+                    const double* __restrict__ ws, int wstride, const PhsRec* __restrict__ rec, DevStatus* ds) {
   const int fi = blockIdx.x * blockDim.x + threadIdx.x;
   if (fi >= fn) return;
   const int pp = filterp[fi] - g.begp0;
+  phs_outputs<true>(f, prm, g, rec[fi], pp, ds);        // PHS outputs of the patch's last pass
   const int cc = PF(column) - g.begc0;
   const int gg = PF(gridcell) - g.begg0;
   const double dtime = prm.dtime;
@@ -1535,6 +1607,8 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
     const int need_t = grid_for(fn, TASK_THREADS);
     const int grid_n = need_t < sms * occ_n ? need_t : sms * occ_n;
     const int grid_c = need_t < sms * occ_c ? need_t : sms * occ_c;
+    const int need_q = grid_for((fn < QUAD_MAX ? fn : QUAD_MAX) * 4, 128);
+    const int grid_q = need_q < sms * 4 ? need_q : sms * 4;
     int grid_s = grid_for(fn + 32 * NBIN, STEP_THREADS);
     if (grid_s > sms * occ_s * 2) grid_s = sms * occ_s * 2;
     int *lin = L.list_a, *lout = L.list_b;
@@ -1565,14 +1639,16 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
           const int io = i + 1 < NQ_CI ? i : 0;           // newton(3) holds epilogue tasks only and pushes nothing
           phs_newton_kernel<<<grid_n, TASK_THREADS, shbytes, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, h_nt + i,
                                                                   L.q_ci + (size_t)io * cap, n_ci + (i + 1 < NQ_CI ? i + 1 : 0));
-          ctx->launches += 2;
+          phs_newton_quad_kernel<<<grid_q, 128, 0, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, L.q_ci + (size_t)io * cap,
+                                                        n_ci + (i + 1 < NQ_CI ? i + 1 : 0));
+          ctx->launches += 3;
         }
         canopy_phs_end_kernel<<<grid_s, 128, 0, s>>>(d, cp, g, fn, itlef, dfilter, L, lout, rec, ctx->d_status);
         ctx->launches++;
       }
       int* t = lin; lin = lout; lout = t;
     }
-    canopy_final_kernel<<<grid_for(fn, 128), 128, 0, s>>>(d, cp, g, fn, dfilter, ws, wstride, ctx->d_status);
+    canopy_final_kernel<<<grid_for(fn, 128), 128, 0, s>>>(d, cp, g, fn, dfilter, ws, wstride, rec, ctx->d_status);
     ctx->launches++;
   }
   if (mem != CTSM_MEM_DEVICE) {

@@ -203,16 +203,26 @@ PHS_INL bool newton_begin(Newton& N, const PT& P, const double* xin, double gs_s
 }
 
 // one iteration of the loop :4579-4640; returns true while the iteration continues
-template <class PT>
-PHS_INL bool newton_step(Newton& N, const PT& P) {
+// The Weibull curves of the four segments at the current potentials: one after the other in one lane (default), or
+// one segment per lane of a quad (canopy.cu, small queues, where the latency of a single solve is what matters).
+struct WeibullSerial {
+  PHS_INL void operator()(const double* x, const double* psi50, const double* ck, Weibull* w) const {
+    w[SUN] = weibull(x[SUN], psi50[SUN], ck[SUN], true);
+    w[SHA] = weibull(x[SHA], psi50[SHA], ck[SHA], true);
+    w[XYL] = weibull(x[XYL], psi50[XYL], ck[XYL], true);
+    w[ROOT] = weibull(x[ROOT], psi50[ROOT], ck[ROOT], true);
+  }
+};
+
+template <class PT, class WB = WeibullSerial>
+PHS_INL bool newton_step(Newton& N, const PT& P, const WB wb = WB()) {
   double* x = N.x;
   const double qsun = N.qsun, qsha = N.qsha, ls = N.ls, lh = N.lh, tk = N.tk, grav1 = N.grav1;
   const int iter = ++N.iter;
   // segment conductance attenuation at x (shared by spacF :4951-4954 and spacA :4790-4799)
-  const Weibull w1 = weibull(x[SUN], P.psi50[SUN], P.ck[SUN], true);
-  const Weibull w2 = weibull(x[SHA], P.psi50[SHA], P.ck[SHA], true);
-  const Weibull wx = weibull(x[XYL], P.psi50[XYL], P.ck[XYL], true);
-  const Weibull wr = weibull(x[ROOT], P.psi50[ROOT], P.ck[ROOT], true);
+  Weibull w4[4];
+  wb(x, P.psi50, P.ck, w4);
+  const Weibull w1 = w4[SUN], w2 = w4[SHA], wx = w4[XYL], wr = w4[ROOT];
   // spacF :4957-4972
   double f0 = qsun * w1.v - ls * wx.v * (x[XYL] - x[SUN]);
   double f1 = qsha * w2.v - lh * wx.v * (x[XYL] - x[SHA]);
