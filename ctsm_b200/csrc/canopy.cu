@@ -116,24 +116,28 @@ struct Lists {
 // structures): the task kernels pick patches in queue order, i.e. scattered, so a record a lane can stream with
 // 16-byte loads beats the structure-of-arrays layout that suits the uniform kernels.
 struct alignas(128) PhsRec {
-  // constant during the call (canopy_init_kernel)
-  double psi50[4], ck[4], kmax[4];
+  // --- what a calcstress task streams (first five 128-byte lines) ---
+  double psi50[4], ck[4], kmax[4];                  // constant during the call (canopy_init_kernel)
   double laisun, laisha, elai, esai, tsai, htop, fdry, forc_rho, forc_pbot, cf;
   double ksum, ksmp, ksmpg, smpg_mean;
-  double Kv[NLEVSOI], Gv[NLEVSOI], Sv[NLEVSOI];    // k_soil_root(p,:), 1000 z(c,:), smp_l(c,:)
+  double qsatl, qaf, gb_mol;                        // per ITERATION pass (canopy_leaf_kernel)
+  double x[4];                                      // vegwp at PHS entry (night: x[sun] = 1, the reference's sentinel)
+  double gs0sun, gs0sha;                            // conductances handed to calcstress (phs::HybridCarry)
+  int flags, iter1, patch, pad;
+  double Kv[NLEVSOI], Gv[NLEVSOI];                  // k_soil_root(p,:), 1000 z(c,:)
+  // --- what a ci task streams ---
+  double qe, theta_cj, theta_ip, medint, medslope, bbb, mbb, cair, oair, par[2];     // constant during the call
+  double rh_can, vcmax[2], tpu[2], kp[2], lmr[2], je[2], cp, kc, ko;                 // per pass
+  double x1sun, x1sha, bsun, bsha, b0sun, b0sha;    // rest of phs::HybridCarry
+  // --- results of the solve ---
+  double gs_sun, gs_sha, tran, xo[4];
+  phs::CiOut o;
+  // --- epilogues only ---
+  double Sv[NLEVSOI];                               // smp_l(c,:)
+  phs::Brent br;                                    // brent_PHS state (rare: lives here, not in registers)
   __device__ __forceinline__ double K(int j) const { return Kv[j]; }
   __device__ __forceinline__ double G(int j) const { return Gv[j]; }
   __device__ __forceinline__ double S(int j) const { return Sv[j]; }
-  double qe, theta_cj, theta_ip, medint, medslope, bbb, mbb, cair, oair, par[2];
-  // per ITERATION pass (canopy_step_kernel)
-  double qsatl, qaf, gb_mol, rh_can, vcmax[2], tpu[2], kp[2], lmr[2], je[2], cp, kc, ko;
-  double x[4];                                      // vegwp at PHS entry (night: x[sun] = 1, the reference's sentinel)
-  double x1sun, x1sha, gs0sun, gs0sha, bsun, bsha, b0sun, b0sha;   // phs::HybridCarry
-  // results of the solve
-  double gs_sun, gs_sha, tran, xo[4];
-  phs::CiOut o;
-  phs::Brent br;                                    // brent_PHS state (rare: lives here, not in registers)
-  int iter1, flags, patch, pad;
 };
 enum { RF_C3 = 1, RF_MEDLYN = 2, RF_NIGHT = 4, RF_SOLVE = 8, RF_FINAL = 16 };
 
@@ -282,12 +286,10 @@ __device__ __forceinline__ double fth25(double hd, double se) { return 1.0 + dex
 #define WS(slot) ws[(size_t)(slot) * wstride + fi]
 
 // ---------------------------------------------------------------------------------------------
-__global__ void canopy_mark_kernel(CanopyDev f, Geo g, int fn, const int32_t* __restrict__ filterp, int* __restrict__ colflag,
-                                   int* __restrict__ fpos) {
+__global__ void canopy_mark_kernel(CanopyDev f, Geo g, int fn, const int32_t* __restrict__ filterp, int* __restrict__ colflag) {
   const int fi = blockIdx.x * blockDim.x + threadIdx.x;
   if (fi >= fn) return;
   const int pp = filterp[fi] - g.begp0;
-  fpos[pp] = fi;
   colflag[PF(column) - g.begc0] = 1;
 }
 
@@ -310,19 +312,24 @@ canopy_colprep_kernel(CanopyDev f, Geo g, const int* __restrict__ colflag) {
 // ---------------------------------------------------------------------------------------------
 // everything before the ITERATION loop (CanopyFluxesMod.F90:656-1023) + iteration-invariant PHS (:3063-3114)
 __global__ void __launch_bounds__(128)
-canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int* __restrict__ fpos, double* __restrict__ ws,
-                   int wstride, Lists L, PhsRec* __restrict__ rec, DevStatus* ds) {
+canopy_zero_kernel(CanopyDev f, Geo g) {
+  // TimeStepInit :1158-1172 and rb1(begp:endp) = 0 (:830): every patch in bounds
   const int pp = (g.begp - g.begp0) + blockIdx.x * blockDim.x + threadIdx.x;
   if (pp > g.endp - g.begp0) return;
-  // TimeStepInit :1158-1172 and rb1(begp:endp) = 0 (:830): every patch in bounds
   if (!PF(patch_lakpoi)) {
     PF(psnsun) = 0.0; PF(psnsun_wc) = 0.0; PF(psnsun_wj) = 0.0; PF(psnsun_wp) = 0.0;
     PF(psnsha) = 0.0; PF(psnsha_wc) = 0.0; PF(psnsha_wj) = 0.0; PF(psnsha_wp) = 0.0;
     PF(fpsn) = 0.0; PF(fpsn_wc) = 0.0; PF(fpsn_wj) = 0.0; PF(fpsn_wp) = 0.0;
   }
   PF(rb1) = 0.0;
-  const int fi = fpos[pp];
-  if (fi < 0) return;
+}
+
+__global__ void __launch_bounds__(128)
+canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int32_t* __restrict__ filterp, double* __restrict__ ws,
+                   int wstride, Lists L, PhsRec* __restrict__ rec, DevStatus* ds) {
+  const int fi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fi >= fn) return;
+  const int pp = filterp[fi] - g.begp0;
   const int cc = PF(column) - g.begc0;
   const int gg = PF(gridcell) - g.begg0;
   const int ivt = PF(itype);
@@ -986,6 +993,7 @@ constexpr unsigned FULL = 0xffffffffu;
 
 enum LaneState { LS_IDLE = 0, LS_RUN = 1, LS_FIN = 2 };
 
+
 // push `item` of the lanes in `mask` (warp-uniform) to a queue
 __device__ __forceinline__ void queue_push(int* __restrict__ q, int* __restrict__ count, unsigned mask, bool mine, int item) {
   if (mask == 0) return;
@@ -1558,7 +1566,7 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   const int npb = g.endp - g.begp + 1, ncb = g.endc - g.begc + 1;
   if (npb <= 0) return finish_call(ctx, mem, st);
 
-  // workspace: [W_NSLOT][wstride] doubles, the PHS records [fn], and int scratch {fpos[ldp], colflag[ldc],
+  // workspace: [W_NSLOT][wstride] doubles, the PHS records [fn], and int scratch {colflag[ldc],
   // list_a/list_b[NBIN][fn], ci queues 1..3 [fn], newton queues 0..2 [fn], counters}
   const int wstride = (fn + 31) & ~31;
   const int npass = p.itmax_canopy_fluxes + 1;
@@ -1567,12 +1575,11 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   int rc = arena_reserve(ctx->arena_scratch, ws_bytes + sizeof(PhsRec) * (size_t)(fn > 0 ? fn : 1));
   if (rc) return rc;
   const size_t nq = (size_t)(2 * NBIN + (NQ_CI - 1) + NQ_NT);
-  rc = reserve_ints(ctx->arena_ints, (size_t)g.ldp + (size_t)g.ldc + nq * (size_t)fn + n_counts + 64);
+  rc = reserve_ints(ctx->arena_ints, (size_t)g.ldc + nq * (size_t)fn + n_counts + 64);
   if (rc) return rc;
   double* ws = (double*)ctx->arena_scratch.p;
   PhsRec* rec = (PhsRec*)((char*)ctx->arena_scratch.p + ws_bytes);
   int* ip = (int*)ctx->arena_ints.p;
-  int* fpos = ip; ip += g.ldp;
   Lists L;
   L.colflag = ip; ip += g.ldc;
   L.list_a = ip; ip += (size_t)NBIN * fn;
@@ -1582,17 +1589,18 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   L.counts = ip;
   L.cap = fn;
   cudaStream_t s = ctx->stream;
-  CUDA_TRY(cudaMemsetAsync(fpos, 0xff, sizeof(int) * (size_t)g.ldp, s));
   CUDA_TRY(cudaMemsetAsync(L.colflag, 0, sizeof(int) * (size_t)g.ldc, s));
   CUDA_TRY(cudaMemsetAsync(L.counts, 0, sizeof(int) * n_counts, s));
   if (fn > 0) {
-    canopy_mark_kernel<<<grid_for(fn, 256), 256, 0, s>>>(d, g, fn, dfilter, L.colflag, fpos);
+    canopy_mark_kernel<<<grid_for(fn, 256), 256, 0, s>>>(d, g, fn, dfilter, L.colflag);
     canopy_colprep_kernel<<<grid_for(ncb, 128), 128, 0, s>>>(d, g, L.colflag);
     ctx->launches += 2;
   }
-  canopy_init_kernel<<<grid_for(npb, 128), 128, 0, s>>>(d, cp, g, fn, fpos, ws, wstride, L, rec, ctx->d_status);
+  canopy_zero_kernel<<<grid_for(npb, 256), 256, 0, s>>>(d, g);
   ctx->launches++;
   if (fn > 0) {
+    canopy_init_kernel<<<grid_for(fn, 128), 128, 0, s>>>(d, cp, g, fn, dfilter, ws, wstride, L, rec, ctx->d_status);
+    ctx->launches++;
     const size_t shbytes = sizeof(double) * 2 * NLEVSOI * TASK_THREADS;
     int sms = 148, occ_n = 1, occ_c = 1, occ_s = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);

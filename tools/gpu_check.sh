@@ -10,7 +10,7 @@ for v in "" "$@"; do
   for size in ${SIZES:-f02}; do
     CTSM_B200_LIB=$lib python bench.py --size $size --routines canopyfluxes --steps 3 --warmup 3 --no-e2e --no-cpu > $out/${tag}_bench_${size}_canopy${v:+_$v}.json 2>> $out/${tag}_err.log
   done
-  CTSM_B200_LIB=$lib ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $out/${tag}_launches${v:+_$v}.csv \
+  CTSM_B200_LIB=$lib ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file $out/${tag}_launches${v:+_$v}.csv \
       python bench.py --routines canopyfluxes --steps 1 --warmup 3 --no-e2e --no-cpu > /dev/null 2>> $out/${tag}_err.log
 done
 python - <<PY
