@@ -159,13 +159,15 @@ extern "C" int ctsm_b200_sync(ctsm_b200_ctx* ctx, ctsm_status_t* st) {
 // DEVICE calls are asynchronous (status is collected by ctsm_b200_sync);
 // HOST calls are synchronous and return the status of this call.
 int finish_call(ctsm_b200_ctx* ctx, int mem, ctsm_status_t* st) {
+  // a kernel that failed to launch (bad configuration, missing image) must never pass silently
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    fprintf(stderr, "ctsm_b200: launch error %s\n", cudaGetErrorString(e));
+    if (st) memset(st, 0, sizeof *st);
+    return CTSM_ERR_NO_DEVICE;
+  }
   if (mem == CTSM_MEM_DEVICE) {
     if (st) memset(st, 0, sizeof *st);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
-      fprintf(stderr, "ctsm_b200: launch error %s\n", cudaGetErrorString(e));
-      return CTSM_ERR_NO_DEVICE;
-    }
     return CTSM_OK;
   }
   return ctsm_b200_sync(ctx, st);

@@ -1596,7 +1596,7 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
     canopy_colprep_kernel<<<grid_for(ncb, 128), 128, 0, s>>>(d, g, L.colflag);
     ctx->launches += 2;
   }
-  canopy_zero_kernel<<<grid_for(npb, 256), 256, 0, s>>>(d, g);
+  canopy_zero_kernel<<<grid_for(npb, 128), 128, 0, s>>>(d, g);
   ctx->launches++;
   if (fn > 0) {
     canopy_init_kernel<<<grid_for(fn, 128), 128, 0, s>>>(d, cp, g, fn, dfilter, ws, wstride, L, rec, ctx->d_status);
