@@ -9,28 +9,26 @@
 //   TimeStepInit :1143, PhotosynthesisTotal :2065, truncate_small_values NumericsMod.F90:50
 //   setExposedvegpFilter              src/main/filterMod.F90:595-648
 //
-// B200 mapping.  The reference runs ~25 filter loops per ITERATION pass over clump-sized
-// scratch arrays and compacts the patch filter on the host side of every pass.  Here:
-//   canopy_colprep_kernel  one thread per column: eff_porosity / h2osoi_liqvol for columns that
-//                          own an exposed-vegetation patch (the reference writes them through a
-//                          duplicate-laden patch->column list; writes are idempotent);
-//   canopy_init_kernel     one thread per patch in bounds: TimeStepInit zeroing, rb1 = 0, and for
-//                          filter patches everything before the ITERATION loop, including the
-//                          iteration-invariant part of PHS (root-soil conductances: 20 pow per
-//                          patch, which the reference recomputes on every pass).  Builds the
-//                          active list with night patches packed from the front and day patches
-//                          from the back so that warps are (almost) homogeneous in the expensive
-//                          day/night branch of PHS;
-//   canopy_step_kernel / canopy_phs_kernel   two launches per ITERATION pass on persistent grids (multiples of the
-//                          148 SMs), one thread per still-unconverged patch (see the comment above the kernels).
-//                          Per-patch iteration state lives in a compact structure-of-arrays workspace indexed by
-//                          filter position (coalesced); survivors are appended to work-class bins of the next pass
-//                          with __match_any_sync warp-aggregated atomics (order is irrelevant to the numerics:
-//                          patches are independent);
-//   canopy_final_kernel    one thread per filter patch: energy-balance check, stem temperature,
-//                          ground fluxes, 2 m diagnostics, longwave, dew update, totals.
-// Roofline: FP64 pipe / latency (hundreds of pow/exp/log per ~3 KB of patch traffic), not HBM
-// (SURVEY.md 8d); DESIGN.md section 4 has the algorithmic bytes.
+// B200 mapping.  The reference runs ~25 filter loops per ITERATION pass over clump-sized scratch arrays and compacts
+// the patch filter on the host side of every pass.  Here one call is a chain of small kernels on one stream:
+//   canopy_mark / colprep  eff_porosity / h2osoi_liqvol for the columns that own an exposed-vegetation patch (the
+//                          reference writes them through a duplicate-laden patch->column list; writes are idempotent);
+//   canopy_zero_kernel     TimeStepInit zeroing and rb1 = 0 for every patch in bounds;
+//   canopy_init_kernel     one thread per filter patch: everything before the ITERATION loop, the iteration-invariant
+//                          part of PHS (root-soil conductances: 20 pow per patch, which the reference recomputes on
+//                          every pass), the constant part of the patch's PHS record, and the first night / day list;
+//   per ITERATION pass k:  canopy_close_kernel (closes pass k-1, convergence test, survivors -> list of pass k),
+//                          canopy_fric_kernel, canopy_leaf_kernel (open pass k), then the PHS solve of pass k as lane
+//                          tasks with queue refill: phs_ci_kernel x4 interleaved with phs_newton_kernel /
+//                          phs_newton_quad_kernel x4, then canopy_phs_end_kernel (see the comments above the kernels);
+//   canopy_final_kernel    one thread per filter patch: PHS outputs of the patch's last pass, energy-balance check,
+//                          stem temperature, ground fluxes, 2 m diagnostics, longwave, dew update, totals.
+// Uniform kernels (one thread per listed patch) work on the Fortran arrays (patch index fastest: coalesced) and a
+// structure-of-arrays workspace indexed by filter position; the irregular task kernels work on one contiguous record per
+// patch (PhsRec).  Survivor lists are appended with warp-aggregated atomics: order is irrelevant to the numerics because
+// patches are independent.
+// Roofline: FP64 pipe / latency (hundreds of pow/exp/log per ~3 KB of patch traffic), not HBM;
+// DESIGN.md section 4 has the algorithmic bytes and the measured breakdown.
 #include "phs.cuh"
 #include <stdlib.h>
 
@@ -568,7 +566,10 @@ __device__ __forceinline__ ListSlot list_slot(const Lists& L, int row, const int
   return sl;
 }
 
-__global__ void __launch_bounds__(STEP_THREADS)
+#ifndef CLOSE_MINBLOCKS
+#define CLOSE_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(STEP_THREADS, CLOSE_MINBLOCKS)
 canopy_close_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, int first, int last, const int32_t* __restrict__ filterp,
                     double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in,
                     int* __restrict__ list_out, DevStatus* ds) {

@@ -7,17 +7,17 @@
 //   quadratic  src/utils/quadraticMod.F90:17-74
 //
 // B200 mapping (not the reference's call structure):
-//  * everything a patch needs is gathered ONCE into a register-resident PhsPatch
-//    (pft segment parameters, leaf areas, conversion factors) instead of being
-//    re-read through p/c/ivt indirection inside every callee;
-//  * the 20-level root-zone vectors k_soil_root(p,:), smp_l(c,:), 1000*z(c,:) are
-//    staged in shared memory ([level][thread], conflict-free) for the two sums that
-//    depend on the root potential; the level sums that do not depend on it
-//    (sum k, sum k*smp, sum k*(smp-grav2)) are formed once per call;
-//  * spacF and spacA are evaluated at the same potentials, so the vulnerability
-//    curve and its derivative are evaluated once per Newton step (Weibull: one
-//    pow + one exp2 per segment) and shared by both;
-//  * fmad is off (the reference is built with -ffp-contract=off).
+//  * the nested, data-dependent loops of the reference (hybrid -> calcstress Newton -> ci_func -> secant -> brent)
+//    are restated as two kinds of RESUMABLE TASKS - a calcstress solve (newton_begin / newton_step / newton_finish)
+//    and one outer pass of the ci solve (ci_task_begin / ci_step / ci_task_end) - so that the kernels in canopy.cu can
+//    advance 32 independent tasks per warp one step at a time and refill lanes whose task has ended;
+//  * the functions are templates over the "patch view" they read (registers + shared memory inside the Newton loop,
+//    the patch's global-memory record in prologues / epilogues): no copies through local memory;
+//  * spacF and spacA are evaluated at the same potentials, so the vulnerability curve and its derivative are
+//    evaluated once per Newton step (Weibull: one pow + one exp2 per segment) and shared by both; the level sums that
+//    do not depend on the root potential (sum k, sum k*smp, sum k*(smp-grav2)) are formed once per call;
+//  * fmad is off (the reference is built with -ffp-contract=off); the arithmetic and its order are the reference's,
+//    tests/host/phs_tasks_check.cu checks the task formulation bit for bit against the nested-loop one on the CPU.
 #pragma once
 #include "common.cuh"
 
