@@ -3,10 +3,10 @@
 
     python bench.py --gpus N --steps K --warmup W [--size f02] [--impl reference]
 
-One "step" = one pass of the hot path in clm_drv call order (clm_driver.F90:766,900,950),
-CanopyFluxes (+PHS) -> SoilTemperature -> SoilWater, over the rank's synthetic grid (BASELINE.json
-config 4 on one GPU; `--size f09 --routines soiltemperature,soilwater` is config 2, `--routines
-canopyfluxes` config 3).  `value` is whole-job throughput with all state resident in HBM; `e2e` is
+One "step" = one pass of the hot path in clm_drv call order (clm_driver.F90:766,900,950,1422),
+CanopyFluxes (+PHS) -> SoilTemperature -> root-water sink -> SoilWater -> BalanceCheck, over the rank's
+synthetic grid (BASELINE.json config 4 on one GPU; `--size f09 --routines soiltemperature,soilwater` is
+config 2, `--size f09 --routines canopyfluxes` config 3).  `value` is whole-job throughput with all state resident in HBM; `e2e` is
 the same step driven through the C ABI with pinned HOST buffers, host<->device copies inside the
 timed region.  `roofline` describes the dominant routine's kernels, `cpu_baseline` the CPU oracle
 (C restatement of the reference, OpenMP over clumps) on a bounded sample of the same workload.
@@ -29,9 +29,21 @@ sys.path.insert(0, ROOT)
 
 METRIC = "column_timesteps_per_sec"
 UNIT = "column-steps/s"
-KERNEL_OF = {"canopyfluxes": "canopy_iter_kernel (all passes of one step)", "soiltemperature": "soiltemp_kernel",
-             "soilwater": "soilwater_kernel"}
-NAME_OF = {"canopyfluxes": "CanopyFluxes", "soiltemperature": "SoilTemperature", "soilwater": "SoilWater"}
+ALL_ROUTINES = ("canopyfluxes", "soiltemperature", "plantsink", "soilwater", "balancecheck")   # clm_drv order
+KERNEL_OF = {"plantsink": "plantsink_kernel", "balancecheck": "balance_col/grc/patch/loc kernels",
+             "canopyfluxes": "CanopyFluxes kernel chain of one call (init, then per ITERATION pass close/fric/leaf, "
+                             "phs_ci x4, phs_newton x4, phs_end; final) - largest member: phs_newton_kernel",
+             "soiltemperature": "soiltemp_kernel", "soilwater": "soilwater_kernel"}
+NAME_OF = {"canopyfluxes": "CanopyFluxes", "soiltemperature": "SoilTemperature", "soilwater": "SoilWater",
+           "plantsink": "VertTranSink_HydStress", "balancecheck": "BalanceCheck"}
+
+
+def make_workload(size, seed):
+    """Synthetic subgrid + state of every routine of the step (SURVEY.md 8d generators)."""
+    from ctsm_b200 import synthetic_canopy
+    sg, S = synthetic_canopy.make_full_case(size, seed=seed)
+    synthetic_canopy.balance_state(sg, S, np.random.Generator(np.random.PCG64(seed + 1)), 1.0e-11)
+    return sg, S
 
 
 def read_peaks():
@@ -98,8 +110,22 @@ class ClockSampler:
         return out
 
 
+def read_traffic(routine, size):
+    """DRAM bytes per call of a routine's kernels, from the committed ncu launch list of the same command
+    (profiles/r01_traffic.json, written by tools/launch_summary.py output -> DESIGN.md section 4); None when the
+    workload differs from the profiled one."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        d = json.load(open(p))
+        if d.get("size") == str(size):
+            return d["dram_bytes_per_call"].get(routine)
+    except Exception:
+        pass
+    return None
+
+
 def which_mask(routines):
-    return sum({"soiltemperature": 1, "soilwater": 2, "canopyfluxes": 4}[g] for g in routines)
+    return sum({"soiltemperature": 1, "soilwater": 2, "canopyfluxes": 4, "plantsink": 8, "balancecheck": 16}[g] for g in routines)
 
 
 def cpu_reference_run(size_label, routines, steps, warmup, sample_gridcells, seed):
@@ -109,22 +135,24 @@ def cpu_reference_run(size_label, routines, steps, warmup, sample_gridcells, see
     from oracle import oracle
     OL = oracle.lib()
     nthreads = int(OL.oracle_num_threads())
-    sg, S = synthetic_canopy.make_full_case(sample_gridcells, seed=seed)
+    sg, S = make_workload(sample_gridcells, seed)
     prm = abi.default_params()
+    prm.balance_skip_steps = int(OL.oracle_balancecheck_skip_steps(prm.dtime))
     clumps, keep = oracle.make_clumps(sg, nthreads * 4)
-    groups = ("canopyfluxes", "soiltemperature", "soilwater")
-    inout = {fs.name for g in groups for fs in abi.FIELDS[g] if fs.intent != "IN"}
+    inout = {fs.name for g in ALL_ROUTINES for fs in abi.FIELDS[g] if fs.intent != "IN"}
     pristine = {k: S[k].copy() for k in inout}
     ft = abi.make_struct("soiltemperature", S, sg.bounds)
     fw = abi.make_struct("soilwater", S, sg.bounds)
     fc = abi.make_struct("canopyfluxes", S, sg.bounds)
+    fs_ = abi.make_struct("plantsink", S, sg.bounds)
+    fb = abi.make_struct("balancecheck", S, sg.bounds)
     times = []
     for it in range(warmup + steps):
         for k, v in pristine.items():
             S[k][...] = v
         t0 = time.perf_counter()
-        rc = OL.oracle_step_clumps(C.byref(prm), len(clumps), clumps, C.byref(ft), C.byref(fw), C.byref(fc),
-                                   which_mask(routines))
+        rc = OL.oracle_fullstep_clumps(C.byref(prm), len(clumps), clumps, C.byref(ft), C.byref(fw), C.byref(fc),
+                                       C.byref(fs_), C.byref(fb), 1, which_mask(routines))
         t1 = time.perf_counter()
         assert rc == 0, "oracle step failed rc=%d" % rc
         if it >= warmup:
@@ -144,7 +172,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", default="f02", help="tiny|f19|f09|f02 or a gridcell count (per GPU)")
-    ap.add_argument("--routines", default="canopyfluxes,soiltemperature,soilwater")
+    ap.add_argument("--routines", default=",".join(ALL_ROUTINES))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=20000, help="gridcells in the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
@@ -155,7 +183,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     size = a.size if not a.size.isdigit() else int(a.size)
-    routines = tuple(g for g in ("canopyfluxes", "soiltemperature", "soilwater") if g in a.routines.split(","))
+    routines = tuple(g for g in ALL_ROUTINES if g in a.routines.split(","))
     wl_name = "%s one 1800 s step, %s-sized synthetic grid per GPU (15 patches per soil column)" % (
         "->".join(NAME_OF[g] for g in routines), a.size)
     config = {"workload": wl_name, "grid": str(a.size), "routines": [NAME_OF[g] for g in routines],
@@ -188,7 +216,7 @@ def main():
 
     prm = abi.default_params(device=local_rank)
     ctx = driver.Context(prm)
-    sg, S = synthetic_canopy.make_full_case(size, seed=20260101 + 1000 * rank)
+    sg, S = make_workload(size, 20260101 + 1000 * rank)
     names = sorted({fs.name for g in routines for fs in abi.FIELDS[g]})
     D = {k: torch.from_numpy(S[k]).cuda() for k in names}
     restore = sorted({fs.name for g in routines for fs in abi.FIELDS[g] if fs.intent != "IN"})
@@ -253,10 +281,12 @@ def main():
     achieved = ab["bytes"] / (rt_ms[dom] * 1e-3) / 1e9
     step_bytes = sum(v["algorithmic_bytes"] for v in per_routine.values())
     roofline = {"bound": "hbm", "kernel": KERNEL_OF[dom], "achieved": achieved, "peak": peak, "peak_source": peak_src,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": read_traffic(NAME_OF[dom], a.size),
                 "algorithmic_bytes_per_launch": ab["bytes"], "ms_per_launch": rt_ms[dom],
-                "note": "CanopyFluxes+PHS is FP64-pipe/latency bound (hundreds of pow/exp/log per patch-pass), see DESIGN.md; "
-                        "the HBM fraction is reported because BASELINE.json asks for it",
+                "note": "a 'launch' is one call of the dominant routine (a chain of kernels, timed with CUDA events on the "
+                        "library's stream); CanopyFluxes+PHS is FP64-pipe/latency bound (hundreds of pow/exp/log per "
+                        "patch-pass, 7 passes per patch), see DESIGN.md section 4; the HBM fraction is reported because "
+                        "BASELINE.json asks for it",
                 "whole_step": {"algorithmic_bytes": step_bytes, "GBps": step_bytes / (float(np.mean(step_ms)) * 1e-3) / 1e9,
                                "frac": step_bytes / (float(np.mean(step_ms)) * 1e-3) / 1e9 / peak},
                 "routines": per_routine}

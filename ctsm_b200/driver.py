@@ -15,8 +15,11 @@ import numpy as np
 
 from . import abi
 
-ROUTINES = ("canopyfluxes", "soiltemperature", "soilwater")   # clm_drv call order (clm_driver.F90:766,900,950)
-FILTER_OF = {"canopyfluxes": ("exposedvegp",), "soiltemperature": ("nolakep", "nolakec"), "soilwater": ("hydrologyc",)}
+# clm_drv call order: CanopyFluxes clm_driver.F90:766, SoilTemperature :900, HydrologyNoDrainage :950 (root-water sink
+# HydrologyNoDrainageMod.F90:339, SoilWater :346), BalanceCheck :1422
+ROUTINES = ("canopyfluxes", "soiltemperature", "plantsink", "soilwater", "balancecheck")
+FILTER_OF = {"canopyfluxes": ("exposedvegp",), "soiltemperature": ("nolakep", "nolakec"), "plantsink": ("hydrologyc",),
+             "soilwater": ("hydrologyc",), "balancecheck": ("allc",)}
 
 
 class CtsmError(RuntimeError):
@@ -67,10 +70,19 @@ class HotPath:
         self.routines = tuple(routines)
         self.structs = {g: abi.make_struct(g, arrays, sg.bounds) for g in self.routines}
         self.filters = dict(sg.filters)
+        self.filters.setdefault("allc", np.arange(sg.bounds.begc, sg.bounds.endc + 1, dtype=np.int32))
+        # DAnstep: 1 = inside BalanceCheck's skip steps (BalanceCheckMod.F90:91,754): all residuals, maxima and warnings
+        # are computed, the abort is suppressed - the synthetic water/energy terms are not a closed budget after the step
+        self.danstep = 1
+        self.balance_report = abi.BalanceReport()
+        if "balancecheck" in self.routines:
+            self.ctx.L.ctsm_b200_balancecheck_init(self.ctx.h)
         if mem == abi.MEM_DEVICE:
             import torch
-            self.filters = {k: torch.from_numpy(v).cuda() for k, v in sg.filters.items()}
-        self.nfilter = {k: len(v) for k, v in sg.filters.items()}
+            self.nfilter = {k: len(v) for k, v in self.filters.items()}
+            self.filters = {k: torch.from_numpy(v).cuda() for k, v in self.filters.items()}
+        else:
+            self.nfilter = {k: len(v) for k, v in self.filters.items()}
 
     # -- individual routines (names and argument meaning follow the Fortran) ---------------
     def SoilTemperature(self):
@@ -98,8 +110,27 @@ class HotPath:
         if rc != 0:
             raise CtsmError(st, rc)
 
+    def VertTranSink(self):
+        """Compute_EffecRootFrac_And_VertTranSink_HydStress (SoilWaterPlantSinkMod.F90:236-328)"""
+        st = abi.Status()
+        rc = self.ctx.L.ctsm_b200_vert_tran_sink_hydstress(
+            self.ctx.h, C.byref(self.sg.bounds), self.nfilter["hydrologyc"], abi.i32p(self.filters["hydrologyc"]),
+            C.byref(self.structs["plantsink"]), self.mem, C.byref(st))
+        if rc != 0:
+            raise CtsmError(st, rc)
+
+    def BalanceCheck(self):
+        """BalanceCheck + EnergyBalanceCheck over all columns in bounds (BalanceCheckMod.F90:445,859)"""
+        st = abi.Status()
+        rc = self.ctx.L.ctsm_b200_balancecheck(
+            self.ctx.h, C.byref(self.sg.bounds), self.nfilter["allc"], abi.i32p(self.filters["allc"]),
+            C.byref(self.structs["balancecheck"]), self.danstep, self.mem, C.byref(self.balance_report), C.byref(st))
+        if rc != 0:
+            raise CtsmError(st, rc)
+
     def call(self, g):
-        {"canopyfluxes": self.CanopyFluxes, "soiltemperature": self.SoilTemperature, "soilwater": self.SoilWater}[g]()
+        {"canopyfluxes": self.CanopyFluxes, "soiltemperature": self.SoilTemperature, "soilwater": self.SoilWater,
+         "plantsink": self.VertTranSink, "balancecheck": self.BalanceCheck}[g]()
 
     def step(self):
         for g in self.routines:
@@ -117,7 +148,7 @@ def staged_bytes(sg, routines: Iterable[str], preserve_out: bool = True):
             if fs.intent in ("OUT", "INOUT"):
                 d2h += n
     for g in routines:
-        h2d += 4 * sum(len(sg.filters[k]) for k in FILTER_OF[g])
+        h2d += 4 * sum(len(sg.filters[k]) if k in sg.filters else sg.ncol for k in FILTER_OF[g])
     return h2d, d2h
 
 
@@ -128,6 +159,12 @@ def algorithmic_bytes(sg, S, group: str) -> Dict[str, float]:
     if group == "soilwater":
         ncol = len(sg.filters["hydrologyc"]); cols = sg.filters["hydrologyc"] - 1
         npat = 0; pats = np.zeros(0, dtype=np.int64)
+    elif group == "plantsink":
+        ncol = len(sg.filters["hydrologyc"]); cols = sg.filters["hydrologyc"] - 1
+        pats = np.nonzero(np.isin(sg.patch_column, sg.filters["hydrologyc"]))[0]; npat = len(pats)
+    elif group == "balancecheck":
+        ncol = sg.ncol; cols = np.arange(sg.ncol)
+        npat = sg.npatch; pats = np.arange(sg.npatch)
     elif group == "canopyfluxes":
         pats = sg.filters["exposedvegp"] - 1; npat = len(pats)
         cols = np.unique(sg.patch_column[pats]) - 1; ncol = len(cols)      # each column counted once per step

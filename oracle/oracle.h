@@ -88,6 +88,10 @@ typedef struct oracle_clump_t {
 int oracle_step_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump_t* clumps,
                        const ctsm_soiltemperature_fields_t* ft, const ctsm_soilwater_fields_t* fw,
                        const ctsm_canopyfluxes_fields_t* fc, int which);
+int oracle_fullstep_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump_t* clumps,
+                           const ctsm_soiltemperature_fields_t* ft, const ctsm_soilwater_fields_t* fw,
+                           const ctsm_canopyfluxes_fields_t* fc, const ctsm_plantsink_fields_t* fs,
+                           const ctsm_balancecheck_fields_t* fb, int DAnstep, int which);
 
 /* number of OpenMP threads the clump-loop drivers will use */
 int oracle_num_threads(void);

@@ -130,5 +130,9 @@ def lib():
     L.oracle_num_threads.restype = C.c_int
     L.oracle_step_clumps.argtypes = [P, C.c_int, C.POINTER(Clump), C.POINTER(abi.STRUCTS["soiltemperature"]),
                                      C.POINTER(abi.STRUCTS["soilwater"]), C.POINTER(abi.STRUCTS["canopyfluxes"]), C.c_int]
+    L.oracle_fullstep_clumps.argtypes = [P, C.c_int, C.POINTER(Clump), C.POINTER(abi.STRUCTS["soiltemperature"]),
+                                         C.POINTER(abi.STRUCTS["soilwater"]), C.POINTER(abi.STRUCTS["canopyfluxes"]),
+                                         C.POINTER(abi.STRUCTS["plantsink"]), C.POINTER(abi.STRUCTS["balancecheck"]),
+                                         C.c_int, C.c_int]
     _lib = L
     return L
