@@ -134,6 +134,8 @@ def cpu_reference_run(size_label, routines, steps, warmup, sample_gridcells, see
     from ctsm_b200 import abi, synthetic_canopy
     from oracle import oracle
     OL = oracle.lib()
+    # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which is not the reference's setup)
+    OL.oracle_set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     nthreads = int(OL.oracle_num_threads())
     sg, S = make_workload(sample_gridcells, seed)
     prm = abi.default_params()

@@ -85,6 +85,7 @@ typedef struct oracle_clump_t {
   int32_t num_exposedvegp; const int32_t* filter_exposedvegp;
 } oracle_clump_t;
 /* which: bit 2 CanopyFluxes, bit 0 SoilTemperature, bit 1 SoilWater; executed in clm_drv call order */
+void oracle_set_num_threads(int n);
 int oracle_step_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump_t* clumps,
                        const ctsm_soiltemperature_fields_t* ft, const ctsm_soilwater_fields_t* fw,
                        const ctsm_canopyfluxes_fields_t* fc, int which);

@@ -135,6 +135,9 @@ int oracle_dgtsv_batch(const ctsm_bounds_t* bounds, int nlev, const int32_t* nla
 #ifdef _OPENMP
 #include <omp.h>
 int oracle_num_threads(void) { return omp_get_max_threads(); }
+/* launchers such as torch.distributed.run export OMP_NUM_THREADS=1; the CPU arm must use the host cores it is given */
+void oracle_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 #else
 int oracle_num_threads(void) { return 1; }
+void oracle_set_num_threads(int n) { (void)n; }
 #endif

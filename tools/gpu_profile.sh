@@ -11,7 +11,7 @@ python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_refere
 python bench.py --size f09 --steps 5 --no-cpu > $out/${tag}_bench_f09.json 2>> $out/${tag}_bench_f02.err
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 12000 --csv \
     --log-file $out/${tag}_launches_f02.csv python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > $out/${tag}_b.log 2>&1
-python tools/launch_summary.py $out/${tag}_launches_f02.csv > $out/${tag}_launch_summary_f02.txt 2>&1
+python tools/launch_summary.py $out/${tag}_launches_f02.csv $out/${tag}_traffic.json f02 > $out/${tag}_launch_summary_f02.txt 2>&1
 gzip -f $out/${tag}_launches_f02.csv
 cap() {  # name regex skip count routines
   ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -f -o /tmp/$1 \

@@ -30,3 +30,16 @@ print("%-28s %9.1f %12.3f %7.1f%% %12.3f %12.3f" % ("TOTAL", sum(n.values()) / s
                                                   sum(rd.values()) / steps / 1e9, sum(wr.values()) / steps / 1e9))
 print("(ncu serialises launches and flushes caches between them: the SHARES are comparable with the event-timed step, the"
       " absolute times are not)")
+if len(sys.argv) > 3:
+    # DRAM bytes per call of each routine (bench.py roofline.traffic): tools/launch_summary.py CSV OUT.json SIZE
+    import json
+    routine_of = lambda k: ("SoilTemperature" if k in ("soiltemp_kernel", "patchmask_kernel") else "SoilWater" if k.startswith("soilwater")
+                            else "VertTranSink_HydStress" if k.startswith("plantsink") else "BalanceCheck" if k.startswith("balance")
+                            else "CanopyFluxes")
+    per = collections.defaultdict(float)
+    for k in t:
+        per[routine_of(k)] += (rd[k] + wr[k]) / steps
+    json.dump({"size": sys.argv[3], "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, summed over the "
+               "kernels of one call (mean of 4 steps of `bench.py --steps 1 --warmup 3`)", "dram_bytes_per_call": per},
+              open(sys.argv[2], "w"), indent=1)
+
