@@ -86,27 +86,27 @@ struct Geo {   // index bases / leading dimensions
   int begp, endp, begc, endc;   // call bounds
 };
 
-// Active lists of one ITERATION pass: bin 0 = night patches, bin 1 = day patches (they differ in what the pass does
-// for them); every bin owns a region of `cap` entries and thread slots are padded to whole warps per bin.
-#define NBIN 2
-#define BIN_NIGHT 0
-#define BIN_DAY 1
+// Active list of one ITERATION pass: ONE list in (roughly) ascending filter order.  Survivors are appended per warp, so a
+// warp's 32 entries stay a run of neighbouring patches and the uniform kernels read whole 32-byte sectors; splitting
+// the list into night / day bins (an earlier layout) halved the useful bytes per sector of kernels that are HBM bound.
+#define NBIN 1
 // PHS task queues of one pass (hybrid_PHS has at most 4 outer passes, PhotosynthesisMod.F90:3896):
-//   ci queue i   (i = 0..3): day patches about to run outer pass i+1 of the ci solve; queue 0 is the day bin itself;
+//   ci queue i   (i = 0..3): day patches about to run outer pass i+1 of the ci solve (queue 0 is filled by the close kernel);
 //   newton queue i (i = 0..3): patches that leave ci pass i+1: either on to calcstress before outer pass i+2, or, when
 //   the ci solve has ended, to the hybrid_PHS epilogue (getvegwp); queue 0 also holds the night patches, whose whole
 //   PHS solve is one calcstress.
 #define NQ_CI 4
 #define NQ_NT 4
-#define QROW (NBIN + 2 * (NQ_CI + NQ_NT))    // ints per pass: bin counts, queue counts, queue fetch heads
+#define QROW (NBIN + 2 * (NQ_CI + NQ_NT) + 1)   // ints per pass: list count, queue counts, queue fetch heads, a spare
 struct Lists {
   int* counts;          // [npass + 2][QROW]: {bin counts[NBIN], ci count[NQ_CI], nt count[NQ_NT], ci head[NQ_CI], nt head[NQ_NT]}
   int* list_a;          // ping: [NBIN][cap]
   int* list_b;          // pong
-  int* q_ci;            // [NQ_CI - 1][cap]  (ci queues 1..3)
+  int* q_ci;            // [NQ_CI][cap]
   int* q_nt;            // [NQ_NT][cap]
   int* colflag;         // per column (alloc-based): owns an exposed-veg patch in this call
   int cap;
+  __device__ __forceinline__ int* n_ci(int row, int i) const { return counts + (size_t)row * QROW + NBIN + i; }
   __device__ __forceinline__ int* n_nt(int row, int i) const { return counts + (size_t)row * QROW + NBIN + NQ_CI + i; }
 };
 
@@ -528,8 +528,8 @@ canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int32_t* __r
     R.iter1 = 1;
   }
 
-  // first active list: night patches in bin 0, day patches in bin 1
-  bin_append(L, L.list_a, 0, night ? BIN_NIGHT : BIN_DAY, fi, __activemask());
+  // first active list
+  bin_append(L, L.list_a, 0, 0, fi, __activemask());
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -546,7 +546,7 @@ canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int32_t* __r
 // Everything that crosses a kernel boundary lives in the patch fields it belongs to, in the SoA workspace or in the
 // PHS record.
 #define STEP_THREADS 128
-struct ListSlot { int fi; bool live, night; };
+struct ListSlot { int fi; bool live; };
 // thread slots of one pass list: bins padded to whole warps
 __device__ __forceinline__ int list_offsets(const Lists& L, int row, int* off) {
   off[0] = 0;
@@ -561,7 +561,6 @@ __device__ __forceinline__ ListSlot list_slot(const Lists& L, int row, const int
   for (int b = 1; b < NBIN; ++b) bin += (t >= off[b]) ? 1 : 0;
   const int idx = t - off[bin];
   sl.live = idx < L.counts[(size_t)row * QROW + bin];
-  sl.night = bin == BIN_NIGHT;
   sl.fi = sl.live ? list[(size_t)bin * L.cap + idx] : 0;
   return sl;
 }
@@ -580,8 +579,8 @@ canopy_close_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, int first, in
   for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
     const ListSlot sl = list_slot(L, row, off, list_in, base + threadIdx.x);
     const int fi = sl.fi;
-    const bool live = sl.live, night = sl.night;
-    bool keep = false, solve = false;
+    const bool live = sl.live;
+    bool keep = false, solve = false, night = false;
     if (live) {
       const int pp = filterp[fi] - g.begp0;
       const int cc = PF(column) - g.begc0;
@@ -590,6 +589,7 @@ canopy_close_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, int first, in
       const double ur = WS(W_UR), zldis_u = WS(W_ZLDIS);
       keep = true;
       solve = PF(nrad) >= 1;
+      night = (PF2(parsun_z, 0) <= 0.0);
       if (!first) {
         // ---- close pass itlef0-1 ----
         const double laisun = PF(laisun), laisha = PF(laisha);
@@ -732,20 +732,24 @@ canopy_close_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, int first, in
       }
       }
     }
-    // survivors -> night / day bin of pass itlef0; night patches that need a solve also enter newton queue 0
+    // survivors -> list of pass itlef0; those that need a PHS solve also enter their first task queue: night patches the
+    // calcstress queue 0 (their whole solve is one calcstress), day patches the ci queue 0
     const bool go = keep && !last;
     const unsigned act = __activemask();
     const unsigned mk = __ballot_sync(act, go);
-    if (go) bin_append(L, list_out, row + 1, night ? BIN_NIGHT : BIN_DAY, fi, mk);
-    const bool gq = go && night && solve;
-    const unsigned mq = __ballot_sync(act, gq);
-    if (gq) {
-      const int lane = threadIdx.x & 31;
-      const int leader = __ffs(mq) - 1;
-      int b0 = 0;
-      if (lane == leader) b0 = atomicAdd(L.n_nt(row + 1, 0), __popc(mq));
-      b0 = __shfl_sync(mq, b0, leader);
-      L.q_nt[b0 + __popc(mq & ((1u << lane) - 1))] = fi;
+    if (go) bin_append(L, list_out, row + 1, 0, fi, mk);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const bool gq = go && solve && (night == (q == 0));
+      const unsigned mq = __ballot_sync(act, gq);
+      if (gq) {
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(mq) - 1;
+        int b0 = 0;
+        if (lane == leader) b0 = atomicAdd(q == 0 ? L.n_nt(row + 1, 0) : L.n_ci(row + 1, 0), __popc(mq));
+        b0 = __shfl_sync(mq, b0, leader);
+        (q == 0 ? L.q_nt : L.q_ci)[b0 + __popc(mq & ((1u << lane) - 1))] = fi;
+      }
     }
   }
 }
@@ -1568,14 +1572,14 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   if (npb <= 0) return finish_call(ctx, mem, st);
 
   // workspace: [W_NSLOT][wstride] doubles, the PHS records [fn], and int scratch {colflag[ldc],
-  // list_a/list_b[NBIN][fn], ci queues 1..3 [fn], newton queues 0..2 [fn], counters}
+  // list_a/list_b[fn], ci queues 0..3 [fn], calcstress queues 0..3 [fn], counters}
   const int wstride = (fn + 31) & ~31;
   const int npass = p.itmax_canopy_fluxes + 1;
   const size_t n_counts = (size_t)QROW * (size_t)(npass + 2);
   const size_t ws_bytes = (sizeof(double) * (size_t)W_NSLOT * (size_t)(wstride > 0 ? wstride : 32) + 127) & ~(size_t)127;
   int rc = arena_reserve(ctx->arena_scratch, ws_bytes + sizeof(PhsRec) * (size_t)(fn > 0 ? fn : 1));
   if (rc) return rc;
-  const size_t nq = (size_t)(2 * NBIN + (NQ_CI - 1) + NQ_NT);
+  const size_t nq = (size_t)(2 * NBIN + NQ_CI + NQ_NT);
   rc = reserve_ints(ctx->arena_ints, (size_t)g.ldc + nq * (size_t)fn + n_counts + 64);
   if (rc) return rc;
   double* ws = (double*)ctx->arena_scratch.p;
@@ -1585,7 +1589,7 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   L.colflag = ip; ip += g.ldc;
   L.list_a = ip; ip += (size_t)NBIN * fn;
   L.list_b = ip; ip += (size_t)NBIN * fn;
-  L.q_ci = ip; ip += (size_t)(NQ_CI - 1) * fn;
+  L.q_ci = ip; ip += (size_t)NQ_CI * fn;
   L.q_nt = ip; ip += (size_t)NQ_NT * fn;
   L.counts = ip;
   L.cap = fn;
@@ -1638,18 +1642,17 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
         int* n_nt = n_ci + NQ_CI;
         int* h_ci = n_nt + NQ_NT;
         int* h_nt = h_ci + NQ_CI;
+        int* spare = h_nt + NQ_NT;
         for (int i = 0; i < NQ_CI; ++i) {
-          // ci queue 0 is the day bin of the pass list; ci queue i > 0 is filled by newton(i - 1)
-          const int* qin = (i == 0) ? lout + (size_t)BIN_DAY * cap : L.q_ci + (size_t)(i - 1) * cap;
-          const int* nin = (i == 0) ? crow + BIN_DAY : n_ci + i;
-          phs_ci_kernel<<<grid_c, TASK_THREADS, 0, s>>>(rec, qin, nin, h_ci + i, L.q_nt + (size_t)i * cap, n_nt + i,
-                                                        ctx->d_status);
-          // newton(i): calcstress for the patches that go on to ci pass i + 1, epilogue for those that are done
-          const int io = i + 1 < NQ_CI ? i : 0;           // newton(3) holds epilogue tasks only and pushes nothing
-          phs_newton_kernel<<<grid_n, TASK_THREADS, shbytes, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, h_nt + i,
-                                                                  L.q_ci + (size_t)io * cap, n_ci + (i + 1 < NQ_CI ? i + 1 : 0));
-          phs_newton_quad_kernel<<<grid_q, 128, 0, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, L.q_ci + (size_t)io * cap,
-                                                        n_ci + (i + 1 < NQ_CI ? i + 1 : 0));
+          // ci(i) hands every patch to calcstress queue i: on to outer pass i + 2, or (solve finished) to the epilogue
+          phs_ci_kernel<<<grid_c, TASK_THREADS, 0, s>>>(rec, L.q_ci + (size_t)i * cap, n_ci + i, h_ci + i,
+                                                        L.q_nt + (size_t)i * cap, n_nt + i, ctx->d_status);
+          // newton(i) feeds ci queue i + 1; newton(3) holds epilogue tasks only and pushes nothing
+          const bool lastq = (i + 1 == NQ_CI);
+          int* qo = L.q_ci + (size_t)(lastq ? 0 : i + 1) * cap;
+          int* no = lastq ? spare : n_ci + i + 1;
+          phs_newton_kernel<<<grid_n, TASK_THREADS, shbytes, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, h_nt + i, qo, no);
+          phs_newton_quad_kernel<<<grid_q, 128, 0, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, qo, no);
           ctx->launches += 3;
         }
         canopy_phs_end_kernel<<<grid_s, 128, 0, s>>>(d, cp, g, fn, itlef, dfilter, L, lout, rec, ctx->d_status);

@@ -13,7 +13,7 @@ steps = 4.0
 for r in rows[hi + 1:]:
     if len(r) <= mv:
         continue
-    name = r[kn].split("(")[0].split("::")[-1]
+    name = r[kn].split("(")[0].split("::")[-1].replace("void ", "").rstrip("<")
     v = float(r[mv].replace(",", "")) * scale.get(r[mu], 1.0)
     if r[mn] == "gpu__time_duration.sum":
         t[name] += v; n[name] += 1
@@ -33,7 +33,7 @@ print("(ncu serialises launches and flushes caches between them: the SHARES are 
 if len(sys.argv) > 3:
     # DRAM bytes per call of each routine (bench.py roofline.traffic): tools/launch_summary.py CSV OUT.json SIZE
     import json
-    routine_of = lambda k: ("SoilTemperature" if k in ("soiltemp_kernel", "patchmask_kernel") else "SoilWater" if k.startswith("soilwater")
+    routine_of = lambda k: ("SoilTemperature" if k in ("soiltemp_kernel", "patchmask_kernel") else "SoilWater" if "soilwater" in k
                             else "VertTranSink_HydStress" if k.startswith("plantsink") else "BalanceCheck" if k.startswith("balance")
                             else "CanopyFluxes")
     per = collections.defaultdict(float)
