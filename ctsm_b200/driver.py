@@ -15,11 +15,11 @@ import numpy as np
 
 from . import abi
 
-# clm_drv call order: CanopyFluxes clm_driver.F90:766, SoilTemperature :900, HydrologyNoDrainage :950 (root-water sink
-# HydrologyNoDrainageMod.F90:339, SoilWater :346), BalanceCheck :1422
-ROUTINES = ("canopyfluxes", "soiltemperature", "plantsink", "soilwater", "balancecheck")
-FILTER_OF = {"canopyfluxes": ("exposedvegp",), "soiltemperature": ("nolakep", "nolakec"), "plantsink": ("hydrologyc",),
-             "soilwater": ("hydrologyc",), "balancecheck": ("allc",)}
+# clm_drv call order: CanopyFluxes clm_driver.F90:766, SoilTemperature :900, SoilFluxes :921, HydrologyNoDrainage :950
+# (root-water sink HydrologyNoDrainageMod.F90:339, SoilWater :346), BalanceCheck :1422
+ROUTINES = ("canopyfluxes", "soiltemperature", "soilfluxes", "plantsink", "soilwater", "balancecheck")
+FILTER_OF = {"canopyfluxes": ("exposedvegp",), "soiltemperature": ("nolakep", "nolakec"), "soilfluxes": ("nolakep", "nolakec"),
+             "plantsink": ("hydrologyc",), "soilwater": ("hydrologyc",), "balancecheck": ("allc",)}
 
 
 class CtsmError(RuntimeError):
@@ -110,6 +110,16 @@ class HotPath:
         if rc != 0:
             raise CtsmError(st, rc)
 
+    def SoilFluxes(self):
+        """SoilFluxes (SoilFluxesMod.F90:37; the urban filters of the reference's dummy list are empty on this path)"""
+        st = abi.Status()
+        rc = self.ctx.L.ctsm_b200_soilfluxes(
+            self.ctx.h, C.byref(self.sg.bounds), self.nfilter["nolakec"], abi.i32p(self.filters["nolakec"]),
+            self.nfilter["nolakep"], abi.i32p(self.filters["nolakep"]), C.byref(self.structs["soilfluxes"]), self.mem,
+            C.byref(st))
+        if rc != 0:
+            raise CtsmError(st, rc)
+
     def VertTranSink(self):
         """Compute_EffecRootFrac_And_VertTranSink_HydStress (SoilWaterPlantSinkMod.F90:236-328)"""
         st = abi.Status()
@@ -130,7 +140,7 @@ class HotPath:
 
     def call(self, g):
         {"canopyfluxes": self.CanopyFluxes, "soiltemperature": self.SoilTemperature, "soilwater": self.SoilWater,
-         "plantsink": self.VertTranSink, "balancecheck": self.BalanceCheck}[g]()
+         "plantsink": self.VertTranSink, "balancecheck": self.BalanceCheck, "soilfluxes": self.SoilFluxes}[g]()
 
     def step(self):
         for g in self.routines:
@@ -162,6 +172,9 @@ def algorithmic_bytes(sg, S, group: str) -> Dict[str, float]:
     elif group == "plantsink":
         ncol = len(sg.filters["hydrologyc"]); cols = sg.filters["hydrologyc"] - 1
         pats = np.nonzero(np.isin(sg.patch_column, sg.filters["hydrologyc"]))[0]; npat = len(pats)
+    elif group == "soilfluxes":
+        ncol = len(sg.filters["nolakec"]); cols = sg.filters["nolakec"] - 1
+        npat = len(sg.filters["nolakep"]); pats = sg.filters["nolakep"] - 1
     elif group == "balancecheck":
         ncol = sg.ncol; cols = np.arange(sg.ncol)
         npat = sg.npatch; pats = np.arange(sg.npatch)

@@ -289,3 +289,37 @@ def balance_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generato
     S["k_soil_root"] = np.where(np.abs(S["k_soil_root"]) < 1e30, S["k_soil_root"], 0.0)
     for k, v in list(S.items()):
         S[k] = np.ascontiguousarray(v)
+
+
+def soilfluxes_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator) -> None:
+    """Adds the fields of group `soilfluxes` (SoilFluxesMod.F90:37).  t_ssbef / t_h2osfc_bef are the temperatures
+    SoilTemperature saves on entry (SoilTemperatureMod.F90:290-300): copies of the current state, so a step that
+    runs SoilTemperature first sees the true 'before' values.  Patch fluxes that CanopyFluxes leaves at spval on
+    patches without exposed vegetation get the values BareGroundFluxes would give them (zero canopy fluxes)."""
+    npch = sg.npatch
+    g = lambda a, b, *sh: rng.uniform(a, b, size=sh)
+    S["t_ssbef"] = S["t_soisno"].copy()
+    S["t_h2osfc_bef"] = S["t_h2osfc"].copy()
+    S["patch_active"] = sg.patch_active.astype(np.int32)
+    fill = {"eflx_sh_veg": 0.0, "eflx_sh_stem": 0.0, "qflx_evap_veg": 0.0, "qflx_tran_veg": 0.0, "ulrad": 0.0}
+    for nm, v in fill.items():
+        S[nm] = np.where(np.abs(S[nm]) < 1e30, S[nm], v)
+    for nm, (lo, hi) in {"dlrad": (0.0, 30.0), "cgrnds": (1.0, 12.0), "cgrndl": (1.0e-7, 4.0e-6), "t_skin": (250.0, 310.0)}.items():
+        S[nm] = np.where(np.abs(S[nm]) < 1e30, S[nm], g(lo, hi, npch))
+    for nm in ("xmf", "xmf_h2osfc", "c_h2osfc", "eflx_h2osfc_to_snow"):      # SoilTemperature outputs
+        if not np.all(np.abs(S[nm]) < 1e30):
+            S[nm] = np.where(np.abs(S[nm]) < 1e30, S[nm], 0.0 if nm != "c_h2osfc" else 1.0e-6)
+    if not np.all(np.abs(S["fact"]) < 1e30):
+        S["fact"] = np.where(np.abs(S["fact"]) < 1e30, S["fact"], g(1.0e-4, 5.0e-2, *S["fact"].shape))
+    for fs in abi_fields("soilfluxes"):
+        if fs.name not in S:
+            n = sg.ncol if fs.sub == "COL" else npch
+            S[fs.name] = np.full(n if fs.lev == "L1" else (fs.nlev, n), 1.0e36, dtype=fs.dtype)
+    for k, v in list(S.items()):
+        S[k] = np.ascontiguousarray(v)
+
+
+def abi_fields(group):
+    from . import abi
+    return abi.FIELDS[group]
+

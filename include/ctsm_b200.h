@@ -12,6 +12,7 @@
  *   ctsm_b200_canopyfluxes       src/biogeophys/CanopyFluxesMod.F90:191  (+ PhotosynthesisMod.F90:2704 PHS)
  *   ctsm_b200_set_exposedvegp_filter  src/main/filterMod.F90:595
  *   ctsm_b200_balancecheck       src/biogeophys/BalanceCheckMod.F90:445,859
+ *   ctsm_b200_soilfluxes         src/biogeophys/SoilFluxesMod.F90:37   (+ p2c, src/main/subgridAveMod.F90:292)
  *
  * Conventions:
  *   - plain pointers and sizes only; no C++/torch types cross this boundary;
@@ -171,6 +172,13 @@ typedef struct ctsm_plantsink_fields_t {
 #undef CTSM_FIELDS_PLANTSINK
 } ctsm_plantsink_fields_t;
 
+typedef struct ctsm_soilfluxes_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_SOILFLUXES
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_SOILFLUXES
+} ctsm_soilfluxes_fields_t;
+
 typedef struct ctsm_balancecheck_fields_t {
   ctsm_bounds_t alloc;
 #define CTSM_FIELDS_BALANCECHECK
@@ -277,6 +285,13 @@ int ctsm_b200_set_exposedvegp_filter(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bo
 int ctsm_b200_vert_tran_sink_hydstress(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
                                        int num_filterc, const int32_t* filterc,
                                        const ctsm_plantsink_fields_t* f, int mem, ctsm_status_t* st);
+
+/* SoilFluxes(bounds, num_urbanl, filter_urbanl, num_urbanp, filter_urbanp, num_nolakec, filter_nolakec, num_nolakep,
+ * filter_nolakep, ...): SoilFluxesMod.F90:37-521, call site clm_driver.F90:921.  The urban filters are not part of this
+ * hot path: a column of an urban landunit in filter_nolakec is refused with CTSM_ERR_URBAN. */
+int ctsm_b200_soilfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_nolakec, const int32_t* filter_nolakec,
+                         int num_nolakep, const int32_t* filter_nolakep, const ctsm_soilfluxes_fields_t* f, int mem,
+                         ctsm_status_t* st);
 
 /* BalanceCheckInit(): BalanceCheckMod.F90:74-95; skip_steps = max(2, nint(3600/dtime)) + 1.  Returns skip_steps. */
 int ctsm_b200_balancecheck_init(ctsm_b200_ctx* ctx);

@@ -36,12 +36,12 @@ int oracle_step_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump
 
 /* The full biogeophysics step of BASELINE.json config 4 in clm_drv order (clm_driver.F90:766, :900, :950 ->
  * HydrologyNoDrainageMod.F90:339,346, :1422): CanopyFluxes -> SoilTemperature -> root-water sink -> SoilWater ->
- * BalanceCheck over all columns of the clump.  `which` bits: 1 SoilTemperature, 2 SoilWater, 4 CanopyFluxes,
- * 8 plant sink, 16 BalanceCheck. */
+ * BalanceCheck over all columns of the clump (SoilFluxes, :921, between SoilTemperature and the sink).  `which` bits:
+ * 1 SoilTemperature, 2 SoilWater, 4 CanopyFluxes, 8 plant sink, 16 BalanceCheck, 32 SoilFluxes. */
 int oracle_fullstep_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump_t* clumps,
                            const ctsm_soiltemperature_fields_t* ft, const ctsm_soilwater_fields_t* fw,
                            const ctsm_canopyfluxes_fields_t* fc, const ctsm_plantsink_fields_t* fs,
-                           const ctsm_balancecheck_fields_t* fb, int DAnstep, int which) {
+                           const ctsm_balancecheck_fields_t* fb, const ctsm_soilfluxes_fields_t* fx, int DAnstep, int which) {
   int rc_all = 0;
 #pragma omp parallel for schedule(dynamic, 1)
   for (int nc = 0; nc < nclumps; ++nc) {
@@ -53,6 +53,8 @@ int oracle_fullstep_clumps(const ctsm_params_t* prm, int nclumps, const oracle_c
     if (!rc && (which & 1) && ft)
       rc = oracle_soiltemperature(prm, &k->bounds, k->num_nolakep, k->filter_nolakep, k->num_nolakec,
                                   k->filter_nolakec, ft, &st);
+    if (!rc && (which & 32) && fx)
+      rc = oracle_soilfluxes(prm, &k->bounds, k->num_nolakec, k->filter_nolakec, k->num_nolakep, k->filter_nolakep, fx, &st);
     if (!rc && (which & 8) && fs)
       rc = oracle_vert_tran_sink_hydstress(&k->bounds, k->num_hydrologyc, k->filter_hydrologyc, fs);
     if (!rc && (which & 2) && fw)
