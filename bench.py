@@ -321,7 +321,7 @@ def main():
         e2e = {"value": total_cols * e2e_steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                "mode": "CTSM_MEM_HOST: every routine uploads all of its fields (so that elements outside the filters are "
-                       "preserved) and downloads its OUT/INOUT fields; wall clock around the three C-ABI calls"}
+                       "preserved) and downloads its OUT/INOUT fields; wall clock around the C-ABI calls of one step"}
         del hph, H, Hn
 
     cpu = None
