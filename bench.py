@@ -4,7 +4,8 @@
     python bench.py --gpus N --steps K --warmup W [--size f02] [--impl reference]
 
 One "step" = one pass of the hot path in clm_drv call order (clm_driver.F90:766,900,921,950,1422),
-CanopyFluxes (+PHS) -> SoilTemperature -> SoilFluxes -> root-water sink -> SoilWater -> BalanceCheck, over the rank's
+CanopyFluxes (+PHS) -> SoilTemperature -> SoilFluxes -> clm_drv_patch2col -> root-water sink -> SoilWater -> BalanceCheck,
+over the rank's
 synthetic grid (BASELINE.json config 4 on one GPU; `--size f09 --routines soiltemperature,soilwater` is
 config 2, `--size f09 --routines canopyfluxes` config 3).  `value` is whole-job throughput with all state resident in HBM; `e2e` is
 the same step driven through the C ABI with pinned HOST buffers, host<->device copies inside the
@@ -29,13 +30,13 @@ sys.path.insert(0, ROOT)
 
 METRIC = "column_timesteps_per_sec"
 UNIT = "column-steps/s"
-ALL_ROUTINES = ("canopyfluxes", "soiltemperature", "soilfluxes", "plantsink", "soilwater", "balancecheck")   # clm_drv order
-KERNEL_OF = {"plantsink": "plantsink_kernel", "soilfluxes": "soilfluxes_patch_kernel + soilfluxes_p2c_kernel", "balancecheck": "balance_col/grc/patch/loc kernels",
+ALL_ROUTINES = ("canopyfluxes", "soiltemperature", "soilfluxes", "patch2col", "plantsink", "soilwater", "balancecheck")   # clm_drv order
+KERNEL_OF = {"plantsink": "plantsink_kernel", "soilfluxes": "soilfluxes_patch_kernel + soilfluxes_p2c_kernel", "patch2col": "patch2col_kernel<false/true>", "balancecheck": "balance_col/grc/patch/loc kernels",
              "canopyfluxes": "CanopyFluxes kernel chain of one call (init, then per ITERATION pass close/fric/leaf, "
                              "phs_ci x4, phs_newton x4, phs_end; final) - largest member: phs_newton_kernel",
              "soiltemperature": "soiltemp_kernel", "soilwater": "soilwater_kernel"}
 NAME_OF = {"canopyfluxes": "CanopyFluxes", "soiltemperature": "SoilTemperature", "soilwater": "SoilWater",
-           "plantsink": "VertTranSink_HydStress", "balancecheck": "BalanceCheck", "soilfluxes": "SoilFluxes"}
+           "plantsink": "VertTranSink_HydStress", "balancecheck": "BalanceCheck", "soilfluxes": "SoilFluxes", "patch2col": "clm_drv_patch2col"}
 
 
 def make_workload(size, seed):
@@ -126,7 +127,7 @@ def read_traffic(routine, size):
 
 
 def which_mask(routines):
-    return sum({"soiltemperature": 1, "soilwater": 2, "canopyfluxes": 4, "plantsink": 8, "balancecheck": 16, "soilfluxes": 32}[g] for g in routines)
+    return sum({"soiltemperature": 1, "soilwater": 2, "canopyfluxes": 4, "plantsink": 8, "balancecheck": 16, "soilfluxes": 32, "patch2col": 64}[g] for g in routines)
 
 
 def cpu_reference_run(size_label, routines, steps, warmup, sample_gridcells, seed):
@@ -150,13 +151,14 @@ def cpu_reference_run(size_label, routines, steps, warmup, sample_gridcells, see
     fs_ = abi.make_struct("plantsink", S, sg.bounds)
     fb = abi.make_struct("balancecheck", S, sg.bounds)
     fx = abi.make_struct("soilfluxes", S, sg.bounds)
+    f2c = abi.make_struct("patch2col", S, sg.bounds)
     times = []
     for it in range(warmup + steps):
         for k, v in pristine.items():
             S[k][...] = v
         t0 = time.perf_counter()
         rc = OL.oracle_fullstep_clumps(C.byref(prm), len(clumps), clumps, C.byref(ft), C.byref(fw), C.byref(fc),
-                                       C.byref(fs_), C.byref(fb), C.byref(fx), 1, which_mask(routines))
+                                       C.byref(fs_), C.byref(fb), C.byref(fx), C.byref(f2c), 1, which_mask(routines))
         t1 = time.perf_counter()
         assert rc == 0, "oracle step failed rc=%d" % rc
         if it >= warmup:

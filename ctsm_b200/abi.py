@@ -263,10 +263,12 @@ def lib():
                                                      C.POINTER(STRUCTS["plantsink"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_soilfluxes.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p,
                                        C.POINTER(STRUCTS["soilfluxes"]), C.c_int, C.POINTER(Status)]
+    L.ctsm_b200_patch2col.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p,
+                                      C.POINTER(STRUCTS["patch2col"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_balancecheck_init.argtypes = [vp]
     L.ctsm_b200_balancecheck.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.POINTER(STRUCTS["balancecheck"]),
                                          C.c_int, C.c_int, C.POINTER(BalanceReport), C.POINTER(Status)]
-    for fn in ("vert_tran_sink_hydstress", "balancecheck_init", "balancecheck", "soilfluxes"):
+    for fn in ("vert_tran_sink_hydstress", "balancecheck_init", "balancecheck", "soilfluxes", "patch2col"):
         getattr(L, "ctsm_b200_" + fn).restype = C.c_int
     for fn in ("init", "finalize", "sync", "host_register", "host_unregister", "tridiagonal", "banddiagonal",
                "dgtsv_batch", "soilwater", "soiltemperature", "canopyfluxes", "set_exposedvegp_filter"):

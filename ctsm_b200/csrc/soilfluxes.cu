@@ -15,6 +15,14 @@
 // serves the other 14 patches): DESIGN.md section 4.
 #include "common.cuh"
 
+struct Patch2ColDev {    // device-side view of ctsm_patch2col_fields_t
+#define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) ctype* name;
+#define CTSM_FIELDS_PATCH2COL
+#include "../../include/ctsm_b200_fields.def"
+#undef CTSM_FIELDS_PATCH2COL
+#undef CTSM_F
+};
+
 struct SoilFluxesDev {   // device-side view of ctsm_soilfluxes_fields_t
 #define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) ctype* name;
 #define CTSM_FIELDS_SOILFLUXES
@@ -150,7 +158,87 @@ soilfluxes_p2c_kernel(SoilFluxesDev f, int begc0, int begp0, int numc, const int
   }
   f.errsoi_col[cc] = s;
 }
+
+// clm_drv_patch2col (clm_driver.F90:1655-1739): the reference calls p2c eleven times, i.e. walks every column's patch
+// list eleven times; here one thread per column walks it once and forms all averages (each a separate accumulator in
+// ascending patch order = the reference's order).  ALLC = false: the ten averages over filter_nolakec; ALLC = true:
+// qflx_evap_soi over filter_allc (:1722-1724; it overrides the non-lake average, which is the same number there).
+template <bool ALLC>
+__global__ void __launch_bounds__(128)
+patch2col_kernel(Patch2ColDev f, int begc0, int begp0, int numc, const int32_t* __restrict__ filterc) {
+  const int fc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fc >= numc) return;
+  const int cc = filterc[fc] - begc0;
+  const int pi = f.patchi[cc], pf = f.patchf[cc];
+  double a[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) a[k] = 0.0;
+  for (int p1 = pi; p1 <= pf; ++p1) {
+    const int pp = p1 - begp0;
+    if (!f.patch_active[pp]) continue;
+    const double wt = f.wtcol[pp];
+    a[3] = a[3] + f.qflx_evap_soi[pp] * wt;
+    if (!ALLC) {
+      a[0] = a[0] + f.qflx_ev_snow[pp] * wt;
+      a[1] = a[1] + f.qflx_ev_soil[pp] * wt;
+      a[2] = a[2] + f.qflx_ev_h2osfc[pp] * wt;
+      a[4] = a[4] + f.qflx_evap_tot_patch[pp] * wt;
+      a[5] = a[5] + f.qflx_tran_veg[pp] * wt;
+      a[6] = a[6] + f.qflx_liqevap_from_top_layer_patch[pp] * wt;
+      a[7] = a[7] + f.qflx_liqdew_to_top_layer_patch[pp] * wt;
+      a[8] = a[8] + f.qflx_solidevap_from_top_layer_patch[pp] * wt;
+      a[9] = a[9] + f.qflx_soliddew_to_top_layer_patch[pp] * wt;
+    }
+  }
+  f.qflx_evap_soi_col[cc] = a[3];
+  if (!ALLC) {
+    f.qflx_ev_snow_col[cc] = a[0]; f.qflx_ev_soil_col[cc] = a[1]; f.qflx_ev_h2osfc_col[cc] = a[2];
+    f.qflx_evap_tot[cc] = a[4]; f.qflx_tran_veg_col[cc] = a[5]; f.qflx_liqevap_from_top_layer[cc] = a[6];
+    f.qflx_liqdew_to_top_layer[cc] = a[7]; f.qflx_solidevap_from_top_layer[cc] = a[8]; f.qflx_soliddew_to_top_layer[cc] = a[9];
+  }
+}
 }  // namespace
+
+extern "C" int ctsm_b200_patch2col(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_allc, const int32_t* filter_allc,
+                                   int num_nolakec, const int32_t* filter_nolakec, const ctsm_patch2col_fields_t* hf, int mem,
+                                   ctsm_status_t* st) {
+  if (!ctx || !bounds || !hf || num_allc < 0 || num_nolakec < 0 || (num_allc > 0 && !filter_allc) ||
+      (num_nolakec > 0 && !filter_nolakec))
+    return CTSM_ERR_BAD_ARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  Patch2ColDev d;
+  const int32_t *dfa = filter_allc, *dfc = filter_nolakec;
+  std::vector<StageField> fl;
+#define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) \
+  d.name = hf->name;                                        \
+  fl.push_back(StageField{(void**)&d.name, (void*)hf->name, (int)sizeof(ctype), SUB_##sub, lev_shape(#lev).n, INTENT_##intent});
+#define CTSM_FIELDS_PATCH2COL
+#include "../../include/ctsm_b200_fields.def"
+#undef CTSM_FIELDS_PATCH2COL
+#undef CTSM_F
+  for (auto& s : fl) if (!s.host_ptr) return CTSM_ERR_BAD_ARG;
+  if (mem != CTSM_MEM_DEVICE) {
+    int rc = stage_begin(ctx, fl, hf->alloc, *bounds, mem == CTSM_MEM_HOST);
+    if (rc) return rc;
+    rc = stage_filter(ctx, ctx->arena_filter0, filter_allc, num_allc, &dfa);
+    if (rc) return rc;
+    rc = stage_filter(ctx, ctx->arena_filter1, filter_nolakec, num_nolakec, &dfc);
+    if (rc) return rc;
+  }
+  if (num_nolakec > 0) {
+    patch2col_kernel<false><<<grid_for(num_nolakec, 128), 128, 0, ctx->stream>>>(d, hf->alloc.begc, hf->alloc.begp, num_nolakec, dfc);
+    ctx->launches++;
+  }
+  if (num_allc > 0) {
+    patch2col_kernel<true><<<grid_for(num_allc, 128), 128, 0, ctx->stream>>>(d, hf->alloc.begc, hf->alloc.begp, num_allc, dfa);
+    ctx->launches++;
+  }
+  if (mem != CTSM_MEM_DEVICE) {
+    int rc = stage_end(ctx, fl, hf->alloc, *bounds);
+    if (rc) return rc;
+  }
+  return finish_call(ctx, mem, st);
+}
 
 extern "C" int ctsm_b200_soilfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_nolakec,
                                     const int32_t* filter_nolakec, int num_nolakep, const int32_t* filter_nolakep,

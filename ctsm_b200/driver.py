@@ -15,11 +15,12 @@ import numpy as np
 
 from . import abi
 
-# clm_drv call order: CanopyFluxes clm_driver.F90:766, SoilTemperature :900, SoilFluxes :921, HydrologyNoDrainage :950
+# clm_drv call order: CanopyFluxes clm_driver.F90:766, SoilTemperature :900, SoilFluxes :921, clm_drv_patch2col :936,
+# HydrologyNoDrainage :950
 # (root-water sink HydrologyNoDrainageMod.F90:339, SoilWater :346), BalanceCheck :1422
-ROUTINES = ("canopyfluxes", "soiltemperature", "soilfluxes", "plantsink", "soilwater", "balancecheck")
+ROUTINES = ("canopyfluxes", "soiltemperature", "soilfluxes", "patch2col", "plantsink", "soilwater", "balancecheck")
 FILTER_OF = {"canopyfluxes": ("exposedvegp",), "soiltemperature": ("nolakep", "nolakec"), "soilfluxes": ("nolakep", "nolakec"),
-             "plantsink": ("hydrologyc",), "soilwater": ("hydrologyc",), "balancecheck": ("allc",)}
+             "patch2col": ("allc", "nolakec"), "plantsink": ("hydrologyc",), "soilwater": ("hydrologyc",), "balancecheck": ("allc",)}
 
 
 class CtsmError(RuntimeError):
@@ -120,6 +121,16 @@ class HotPath:
         if rc != 0:
             raise CtsmError(st, rc)
 
+    def Patch2Col(self):
+        """clm_drv_patch2col (clm_driver.F90:1655)"""
+        st = abi.Status()
+        rc = self.ctx.L.ctsm_b200_patch2col(
+            self.ctx.h, C.byref(self.sg.bounds), self.nfilter["allc"], abi.i32p(self.filters["allc"]),
+            self.nfilter["nolakec"], abi.i32p(self.filters["nolakec"]), C.byref(self.structs["patch2col"]), self.mem,
+            C.byref(st))
+        if rc != 0:
+            raise CtsmError(st, rc)
+
     def VertTranSink(self):
         """Compute_EffecRootFrac_And_VertTranSink_HydStress (SoilWaterPlantSinkMod.F90:236-328)"""
         st = abi.Status()
@@ -140,7 +151,7 @@ class HotPath:
 
     def call(self, g):
         {"canopyfluxes": self.CanopyFluxes, "soiltemperature": self.SoilTemperature, "soilwater": self.SoilWater,
-         "plantsink": self.VertTranSink, "balancecheck": self.BalanceCheck, "soilfluxes": self.SoilFluxes}[g]()
+         "plantsink": self.VertTranSink, "balancecheck": self.BalanceCheck, "soilfluxes": self.SoilFluxes, "patch2col": self.Patch2Col}[g]()
 
     def step(self):
         for g in self.routines:
@@ -172,6 +183,9 @@ def algorithmic_bytes(sg, S, group: str) -> Dict[str, float]:
     elif group == "plantsink":
         ncol = len(sg.filters["hydrologyc"]); cols = sg.filters["hydrologyc"] - 1
         pats = np.nonzero(np.isin(sg.patch_column, sg.filters["hydrologyc"]))[0]; npat = len(pats)
+    elif group == "patch2col":
+        ncol = sg.ncol; cols = np.arange(sg.ncol)
+        npat = len(sg.filters["nolakep"]); pats = sg.filters["nolakep"] - 1
     elif group == "soilfluxes":
         ncol = len(sg.filters["nolakec"]); cols = sg.filters["nolakec"] - 1
         npat = len(sg.filters["nolakep"]); pats = sg.filters["nolakep"] - 1

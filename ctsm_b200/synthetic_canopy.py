@@ -292,7 +292,7 @@ def balance_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generato
 
 
 def soilfluxes_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator) -> None:
-    """Adds the fields of group `soilfluxes` (SoilFluxesMod.F90:37).  t_ssbef / t_h2osfc_bef are the temperatures
+    """Adds the fields of groups `soilfluxes` (SoilFluxesMod.F90:37) and `patch2col` (clm_driver.F90:1655).  t_ssbef / t_h2osfc_bef are the temperatures
     SoilTemperature saves on entry (SoilTemperatureMod.F90:290-300): copies of the current state, so a step that
     runs SoilTemperature first sees the true 'before' values.  Patch fluxes that CanopyFluxes leaves at spval on
     patches without exposed vegetation get the values BareGroundFluxes would give them (zero canopy fluxes)."""
@@ -311,7 +311,7 @@ def soilfluxes_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Gener
             S[nm] = np.where(np.abs(S[nm]) < 1e30, S[nm], 0.0 if nm != "c_h2osfc" else 1.0e-6)
     if not np.all(np.abs(S["fact"]) < 1e30):
         S["fact"] = np.where(np.abs(S["fact"]) < 1e30, S["fact"], g(1.0e-4, 5.0e-2, *S["fact"].shape))
-    for fs in abi_fields("soilfluxes"):
+    for fs in list(abi_fields("soilfluxes")) + list(abi_fields("patch2col")):
         if fs.name not in S:
             n = sg.ncol if fs.sub == "COL" else npch
             S[fs.name] = np.full(n if fs.lev == "L1" else (fs.nlev, n), 1.0e36, dtype=fs.dtype)

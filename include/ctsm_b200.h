@@ -13,6 +13,7 @@
  *   ctsm_b200_set_exposedvegp_filter  src/main/filterMod.F90:595
  *   ctsm_b200_balancecheck       src/biogeophys/BalanceCheckMod.F90:445,859
  *   ctsm_b200_soilfluxes         src/biogeophys/SoilFluxesMod.F90:37   (+ p2c, src/main/subgridAveMod.F90:292)
+ *   ctsm_b200_patch2col          src/main/clm_driver.F90:1655          (clm_drv_patch2col)
  *
  * Conventions:
  *   - plain pointers and sizes only; no C++/torch types cross this boundary;
@@ -179,6 +180,13 @@ typedef struct ctsm_soilfluxes_fields_t {
 #undef CTSM_FIELDS_SOILFLUXES
 } ctsm_soilfluxes_fields_t;
 
+typedef struct ctsm_patch2col_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_PATCH2COL
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_PATCH2COL
+} ctsm_patch2col_fields_t;
+
 typedef struct ctsm_balancecheck_fields_t {
   ctsm_bounds_t alloc;
 #define CTSM_FIELDS_BALANCECHECK
@@ -292,6 +300,12 @@ int ctsm_b200_vert_tran_sink_hydstress(ctsm_b200_ctx* ctx, const ctsm_bounds_t* 
 int ctsm_b200_soilfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_nolakec, const int32_t* filter_nolakec,
                          int num_nolakep, const int32_t* filter_nolakep, const ctsm_soilfluxes_fields_t* f, int mem,
                          ctsm_status_t* st);
+
+/* clm_drv_patch2col(bounds, num_allc, filter_allc, num_nolakec, filter_nolakec, energyflux_inst, waterfluxbulk_inst):
+ * src/main/clm_driver.F90:1655-1739, call site :936. */
+int ctsm_b200_patch2col(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_allc, const int32_t* filter_allc,
+                        int num_nolakec, const int32_t* filter_nolakec, const ctsm_patch2col_fields_t* f, int mem,
+                        ctsm_status_t* st);
 
 /* BalanceCheckInit(): BalanceCheckMod.F90:74-95; skip_steps = max(2, nint(3600/dtime)) + 1.  Returns skip_steps. */
 int ctsm_b200_balancecheck_init(ctsm_b200_ctx* ctx);

@@ -88,6 +88,8 @@ typedef struct oracle_clump_t {
 /* oracle_soilfluxes.c (SoilFluxesMod.F90:37-521 + p2c) */
 int oracle_soilfluxes(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_nolakec, const int32_t* filter_nolakec,
                       int num_nolakep, const int32_t* filter_nolakep, const ctsm_soilfluxes_fields_t* f, ctsm_status_t* st);
+int oracle_patch2col(const ctsm_bounds_t* bounds, int num_allc, const int32_t* filter_allc, int num_nolakec,
+                     const int32_t* filter_nolakec, const ctsm_patch2col_fields_t* f);
 void oracle_set_num_threads(int n);
 int oracle_step_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump_t* clumps,
                        const ctsm_soiltemperature_fields_t* ft, const ctsm_soilwater_fields_t* fw,
@@ -95,7 +97,8 @@ int oracle_step_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump
 int oracle_fullstep_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump_t* clumps,
                            const ctsm_soiltemperature_fields_t* ft, const ctsm_soilwater_fields_t* fw,
                            const ctsm_canopyfluxes_fields_t* fc, const ctsm_plantsink_fields_t* fs,
-                           const ctsm_balancecheck_fields_t* fb, const ctsm_soilfluxes_fields_t* fx, int DAnstep, int which);
+                           const ctsm_balancecheck_fields_t* fb, const ctsm_soilfluxes_fields_t* fx,
+                           const ctsm_patch2col_fields_t* f2c, int DAnstep, int which);
 
 /* number of OpenMP threads the clump-loop drivers will use */
 int oracle_num_threads(void);

@@ -133,7 +133,9 @@ def lib():
     L.oracle_fullstep_clumps.argtypes = [P, C.c_int, C.POINTER(Clump), C.POINTER(abi.STRUCTS["soiltemperature"]),
                                          C.POINTER(abi.STRUCTS["soilwater"]), C.POINTER(abi.STRUCTS["canopyfluxes"]),
                                          C.POINTER(abi.STRUCTS["plantsink"]), C.POINTER(abi.STRUCTS["balancecheck"]),
-                                         C.POINTER(abi.STRUCTS["soilfluxes"]), C.c_int, C.c_int]
+                                         C.POINTER(abi.STRUCTS["soilfluxes"]), C.POINTER(abi.STRUCTS["patch2col"]),
+                                         C.c_int, C.c_int]
+    L.oracle_patch2col.argtypes = [B, C.c_int, i32p, C.c_int, i32p, C.POINTER(abi.STRUCTS["patch2col"])]
     L.oracle_soilfluxes.argtypes = [P, B, C.c_int, i32p, C.c_int, i32p, C.POINTER(abi.STRUCTS["soilfluxes"]), S]
     _lib = L
     return L

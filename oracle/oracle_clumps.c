@@ -37,11 +37,12 @@ int oracle_step_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump
 /* The full biogeophysics step of BASELINE.json config 4 in clm_drv order (clm_driver.F90:766, :900, :950 ->
  * HydrologyNoDrainageMod.F90:339,346, :1422): CanopyFluxes -> SoilTemperature -> root-water sink -> SoilWater ->
  * BalanceCheck over all columns of the clump (SoilFluxes, :921, between SoilTemperature and the sink).  `which` bits:
- * 1 SoilTemperature, 2 SoilWater, 4 CanopyFluxes, 8 plant sink, 16 BalanceCheck, 32 SoilFluxes. */
+ * 1 SoilTemperature, 2 SoilWater, 4 CanopyFluxes, 8 plant sink, 16 BalanceCheck, 32 SoilFluxes, 64 clm_drv_patch2col. */
 int oracle_fullstep_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump_t* clumps,
                            const ctsm_soiltemperature_fields_t* ft, const ctsm_soilwater_fields_t* fw,
                            const ctsm_canopyfluxes_fields_t* fc, const ctsm_plantsink_fields_t* fs,
-                           const ctsm_balancecheck_fields_t* fb, const ctsm_soilfluxes_fields_t* fx, int DAnstep, int which) {
+                           const ctsm_balancecheck_fields_t* fb, const ctsm_soilfluxes_fields_t* fx,
+                           const ctsm_patch2col_fields_t* f2c, int DAnstep, int which) {
   int rc_all = 0;
 #pragma omp parallel for schedule(dynamic, 1)
   for (int nc = 0; nc < nclumps; ++nc) {
@@ -55,6 +56,13 @@ int oracle_fullstep_clumps(const ctsm_params_t* prm, int nclumps, const oracle_c
                                   k->filter_nolakec, ft, &st);
     if (!rc && (which & 32) && fx)
       rc = oracle_soilfluxes(prm, &k->bounds, k->num_nolakec, k->filter_nolakec, k->num_nolakep, k->filter_nolakep, fx, &st);
+    if (!rc && (which & 64) && f2c) {                      /* clm_drv_patch2col, clm_driver.F90:936 */
+      const int n = k->bounds.endc - k->bounds.begc + 1;
+      int32_t* allc = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+      for (int i = 0; i < n; ++i) allc[i] = k->bounds.begc + i;
+      rc = oracle_patch2col(&k->bounds, n, allc, k->num_nolakec, k->filter_nolakec, f2c);
+      free(allc);
+    }
     if (!rc && (which & 8) && fs)
       rc = oracle_vert_tran_sink_hydstress(&k->bounds, k->num_hydrologyc, k->filter_hydrologyc, fs);
     if (!rc && (which & 2) && fw)

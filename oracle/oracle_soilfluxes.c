@@ -188,3 +188,32 @@ int oracle_soilfluxes(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int
 #undef TINC
 #undef TG0
 }
+
+/* clm_drv_patch2col: src/main/clm_driver.F90:1655-1739 with p2c_1d_filter (subgridAveMod.F90:312-318) */
+static void p2c_filter(const ctsm_patch2col_fields_t* f, int numfc, const int32_t* filterc, const double* parr, double* carr) {
+  const int begc0 = f->alloc.begc, begp0 = f->alloc.begp;
+  for (int fc = 0; fc < numfc; ++fc) {
+    const int c = filterc[fc];
+    carr[c - begc0] = 0.0;
+    for (int p = f->patchi[c - begc0]; p <= f->patchf[c - begc0]; ++p)
+      if (f->patch_active[p - begp0]) carr[c - begc0] = carr[c - begc0] + parr[p - begp0] * f->wtcol[p - begp0];
+  }
+}
+
+int oracle_patch2col(const ctsm_bounds_t* bounds, int num_allc, const int32_t* filter_allc, int num_nolakec,
+                     const int32_t* filter_nolakec, const ctsm_patch2col_fields_t* f) {
+  (void)bounds;
+  p2c_filter(f, num_nolakec, filter_nolakec, f->qflx_ev_snow, f->qflx_ev_snow_col);
+  p2c_filter(f, num_nolakec, filter_nolakec, f->qflx_ev_soil, f->qflx_ev_soil_col);
+  p2c_filter(f, num_nolakec, filter_nolakec, f->qflx_ev_h2osfc, f->qflx_ev_h2osfc_col);
+  p2c_filter(f, num_nolakec, filter_nolakec, f->qflx_evap_soi, f->qflx_evap_soi_col);
+  p2c_filter(f, num_nolakec, filter_nolakec, f->qflx_evap_tot_patch, f->qflx_evap_tot);
+  p2c_filter(f, num_nolakec, filter_nolakec, f->qflx_tran_veg, f->qflx_tran_veg_col);
+  p2c_filter(f, num_nolakec, filter_nolakec, f->qflx_liqevap_from_top_layer_patch, f->qflx_liqevap_from_top_layer);
+  p2c_filter(f, num_allc, filter_allc, f->qflx_evap_soi, f->qflx_evap_soi_col);
+  p2c_filter(f, num_nolakec, filter_nolakec, f->qflx_liqdew_to_top_layer_patch, f->qflx_liqdew_to_top_layer);
+  p2c_filter(f, num_nolakec, filter_nolakec, f->qflx_solidevap_from_top_layer_patch, f->qflx_solidevap_from_top_layer);
+  p2c_filter(f, num_nolakec, filter_nolakec, f->qflx_soliddew_to_top_layer_patch, f->qflx_soliddew_to_top_layer);
+  return 0;
+}
+

@@ -104,3 +104,33 @@ def test_soilfluxes_clump_bounds_and_urban_refusal(gpu_ctx, oracle_lib):
     rc = L.ctsm_b200_soilfluxes(ctx, C.byref(sg.bounds), len(fc), abi.i32p(fc), len(fp), abi.i32p(fp), C.byref(fb), abi.MEM_HOST,
                                 C.byref(st))
     assert rc == 16 and st.subgrid_index == c
+
+
+@pytest.mark.parametrize("mem", [abi.MEM_HOST, abi.MEM_DEVICE])
+def test_patch2col_matches_oracle_bitwise(gpu_ctx, oracle_lib, mem):
+    """clm_drv_patch2col (clm_driver.F90:1655): eleven p2c averages, same accumulation order, bit-identical."""
+    L, ctx, prm = gpu_ctx
+    sg, S = _case(oracle_lib, prm, 1500, 57)
+    assert _run_oracle(oracle_lib, prm, sg, S)[0] == 0            # SoilFluxes first: its outputs are what gets averaged
+    ref, got = copy_state(S), copy_state(S)
+    allc = np.arange(sg.bounds.begc, sg.bounds.endc + 1, dtype=np.int32)
+    fc = sg.filters["nolakec"]
+    fr = abi.make_struct("patch2col", ref, sg.bounds)
+    assert oracle_lib.oracle_patch2col(C.byref(sg.bounds), len(allc), abi.i32p(allc), len(fc), abi.i32p(fc), C.byref(fr)) == 0
+    st = abi.Status()
+    if mem == abi.MEM_DEVICE:
+        D = to_device(group_arrays(got, "patch2col"))
+        dflt = to_device({"a": allc, "c": fc})
+        f = abi.make_struct("patch2col", D, sg.bounds)
+        assert L.ctsm_b200_patch2col(ctx, C.byref(sg.bounds), len(allc), abi.i32p(dflt["a"]), len(fc), abi.i32p(dflt["c"]),
+                                     C.byref(f), mem, C.byref(st)) == 0
+        assert L.ctsm_b200_sync(ctx, C.byref(st)) == 0
+        for k, v in D.items():
+            got[k][...] = v.cpu().numpy()
+    else:
+        f = abi.make_struct("patch2col", got, sg.bounds)
+        assert L.ctsm_b200_patch2col(ctx, C.byref(sg.bounds), len(allc), abi.i32p(allc), len(fc), abi.i32p(fc), C.byref(f), mem,
+                                     C.byref(st)) == 0
+    for fs in abi.FIELDS["patch2col"]:
+        assert np.array_equal(got[fs.name], ref[fs.name], equal_nan=True), fs.name
+    assert np.abs(ref["qflx_evap_soi_col"][fc - 1]).max() > 0

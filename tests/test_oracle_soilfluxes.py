@@ -105,3 +105,24 @@ def test_soilfluxes_refuses_urban_columns():
     c = int(sg.filters["nolakec"][2])
     S["lun_itype"][c - 1] = 7
     assert _run(OL, prm, sg, S) == 16
+
+
+def test_patch2col_is_the_weighted_column_mean():
+    OL, prm, sg, S = _case(200, 77)
+    assert _run(OL, prm, sg, S) == 0
+    allc = np.arange(sg.bounds.begc, sg.bounds.endc + 1, dtype=np.int32)
+    fc = sg.filters["nolakec"]
+    f = abi.make_struct("patch2col", S, sg.bounds)
+    assert OL.oracle_patch2col(C.byref(sg.bounds), len(allc), abi.i32p(allc), len(fc), abi.i32p(fc), C.byref(f)) == 0
+    w = S["wtcol"] * S["patch_active"]
+    for pname, cname, flt in (("qflx_ev_snow", "qflx_ev_snow_col", fc), ("qflx_evap_tot_patch", "qflx_evap_tot", fc),
+                              ("qflx_liqdew_to_top_layer_patch", "qflx_liqdew_to_top_layer", fc),
+                              ("qflx_evap_soi", "qflx_evap_soi_col", allc)):
+        src = np.where(np.abs(S[pname]) < 1e30, S[pname], 0.0) * np.where(np.abs(S[pname]) < 1e30, w, 0.0)
+        for ci in (flt - 1)[:80]:
+            pi, pf = S["patchi"][ci] - 1, S["patchf"][ci]
+            act = S["patch_active"][pi:pf] != 0
+            if not np.all(np.abs(S[pname][pi:pf][act]) < 1e30):
+                continue
+            want = float(np.sum(src[pi:pf]))
+            assert abs(S[cname][ci] - want) <= 1e-14 * max(1.0, np.abs(src[pi:pf]).sum()) + 1e-300, (cname, ci)
