@@ -212,6 +212,25 @@ class BalanceReport(C.Structure):
                 ("abort_kind", C.c_int32), ("skip_steps", C.c_int32)]
 
 
+FILTER_NAMES = ("allc", "lakec", "nolakec", "bgc_soilc", "soilc", "hydrologyc", "urbanc", "nourbanc", "icec", "do_smb_c",
+                "lakep", "nolakep", "nolakeurbanp", "bgc_vegp", "soilp", "pcropp", "soilnopcropp", "urbanp", "nourbanp",
+                "urbanl", "nourbanl")            # CTSM_FLT_* order (filterMod.F90:29-115)
+FILTER_LEVEL = ("COL",) * 10 + ("PATCH",) * 9 + ("LUN",) * 2
+
+
+class FilterInputs(C.Structure):
+    """ctsm_filter_inputs_t"""
+    _ARRAYS = ("col_active", "col_landunit", "col_gridcell", "col_hydrologically_active", "lun_active", "lun_lakpoi",
+               "lun_urbpoi", "lun_itype", "patch_active", "patch_landunit", "patch_itype", "melt_replaced_by_ice_grc")
+    _fields_ = [("alloc", Bounds)] + [(n, C.POINTER(C.c_int32)) for n in _ARRAYS] + [
+        (n, C.c_int32) for n in ("include_inactive", "use_cn", "use_fates", "use_fates_bgc", "npcropmin", "npcropmax")]
+
+
+class Filters(C.Structure):
+    """ctsm_filters_t"""
+    _fields_ = [("list", C.POINTER(C.c_int32) * len(FILTER_NAMES)), ("num", C.c_int32 * len(FILTER_NAMES))]
+
+
 class LibraryMissing(RuntimeError):
     pass
 
@@ -263,6 +282,8 @@ def lib():
                                                      C.POINTER(STRUCTS["plantsink"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_soilfluxes.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p,
                                        C.POINTER(STRUCTS["soilfluxes"]), C.c_int, C.POINTER(Status)]
+    L.ctsm_b200_set_filters.argtypes = [vp, C.POINTER(Bounds), C.POINTER(FilterInputs), C.POINTER(Filters), C.c_int]
+    L.ctsm_b200_set_filters.restype = C.c_int
     L.ctsm_b200_patch2col.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p,
                                       C.POINTER(STRUCTS["patch2col"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_balancecheck_init.argtypes = [vp]

@@ -10,6 +10,7 @@
  *   ctsm_b200_soilwater          src/biogeophys/SoilWaterMovementMod.F90:240  (moisture_form, :976)
  *   ctsm_b200_soiltemperature    src/biogeophys/SoilTemperatureMod.F90:92
  *   ctsm_b200_canopyfluxes       src/biogeophys/CanopyFluxesMod.F90:191  (+ PhotosynthesisMod.F90:2704 PHS)
+ *   ctsm_b200_set_filters        src/main/filterMod.F90:303   (setFiltersOneGroup)
  *   ctsm_b200_set_exposedvegp_filter  src/main/filterMod.F90:595
  *   ctsm_b200_balancecheck       src/biogeophys/BalanceCheckMod.F90:445,859
  *   ctsm_b200_soilfluxes         src/biogeophys/SoilFluxesMod.F90:37   (+ p2c, src/main/subgridAveMod.F90:292)
@@ -207,6 +208,37 @@ typedef struct ctsm_balance_report_t {
   int32_t skip_steps;
 } ctsm_balance_report_t;
 
+/* setFiltersOneGroup (filterMod.F90:303-592): the index lists of `type clumpfilter` (filterMod.F90:29-115) that depend
+ * on subgrid type and "active" status only.  Every list is a stable, ascending-index compaction (bit-exact target).
+ * Lists the reference leaves empty under the given switches (bgc_soilc, bgc_vegp, pcropp, soilnopcropp) get num = 0. */
+enum { CTSM_FLT_ALLC = 0, CTSM_FLT_LAKEC, CTSM_FLT_NOLAKEC, CTSM_FLT_BGC_SOILC, CTSM_FLT_SOILC, CTSM_FLT_HYDROLOGYC,
+       CTSM_FLT_URBANC, CTSM_FLT_NOURBANC, CTSM_FLT_ICEC, CTSM_FLT_DO_SMB_C,                    /* column lists */
+       CTSM_FLT_LAKEP, CTSM_FLT_NOLAKEP, CTSM_FLT_NOLAKEURBANP, CTSM_FLT_BGC_VEGP, CTSM_FLT_SOILP, CTSM_FLT_PCROPP,
+       CTSM_FLT_SOILNOPCROPP, CTSM_FLT_URBANP, CTSM_FLT_NOURBANP,                              /* patch lists */
+       CTSM_FLT_URBANL, CTSM_FLT_NOURBANL,                                                     /* landunit lists */
+       CTSM_FLT_COUNT };
+typedef struct ctsm_filter_inputs_t {
+  ctsm_bounds_t alloc;                       /* bounds the arrays below are allocated with (lower bounds) */
+  const int32_t* col_active;                 /* col%active(begc:endc), 0/1 */
+  const int32_t* col_landunit;               /* col%landunit, 1-based proc-local landunit index */
+  const int32_t* col_gridcell;               /* col%gridcell */
+  const int32_t* col_hydrologically_active;  /* col%hydrologically_active */
+  const int32_t* lun_active;                 /* lun%active(begl:endl) */
+  const int32_t* lun_lakpoi;                 /* lun%lakpoi */
+  const int32_t* lun_urbpoi;                 /* lun%urbpoi */
+  const int32_t* lun_itype;                  /* lun%itype */
+  const int32_t* patch_active;               /* patch%active(begp:endp) */
+  const int32_t* patch_landunit;             /* patch%landunit */
+  const int32_t* patch_itype;                /* patch%itype */
+  const int32_t* melt_replaced_by_ice_grc;   /* glc_behavior%melt_replaced_by_ice_grc(begg:endg) */
+  int32_t include_inactive, use_cn, use_fates, use_fates_bgc;
+  int32_t npcropmin, npcropmax;              /* is_prognostic_crop (pftconMod.F90:1812-1825) */
+} ctsm_filter_inputs_t;
+typedef struct ctsm_filters_t {
+  int32_t* list[CTSM_FLT_COUNT];             /* each sized to the extent of its subgrid level in `bounds` */
+  int32_t  num[CTSM_FLT_COUNT];              /* out: list lengths (host memory in every mode) */
+} ctsm_filters_t;
+
 /* ---- lifecycle ------------------------------------------------------------ */
 void ctsm_b200_default_params(ctsm_params_t* p);
 int  ctsm_b200_init(const ctsm_params_t* p, ctsm_b200_ctx** ctx);
@@ -277,6 +309,11 @@ int ctsm_b200_soiltemperature(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
 int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
                            int num_exposedvegp, const int32_t* filter_exposedvegp,
                            const ctsm_canopyfluxes_fields_t* f, int mem, ctsm_status_t* st);
+
+/* setFiltersOneGroup(bounds, this_filter, include_inactive, glc_behavior): filterMod.F90:303.  Synchronous (the counts
+ * are returned to the host).  mem says where the input arrays and the output lists live. */
+int ctsm_b200_set_filters(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, const ctsm_filter_inputs_t* in,
+                          ctsm_filters_t* out, int mem);
 
 /* setExposedvegpFilter(bounds, frac_veg_nosno): filterMod.F90:595-648.  Order-preserving
  * split of filter_nolakeurbanp into exposedvegp (frac_veg_nosno > 0) / noexposedvegp.
