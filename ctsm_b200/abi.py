@@ -282,6 +282,9 @@ def lib():
                                                      C.POINTER(STRUCTS["plantsink"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_soilfluxes.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p,
                                        C.POINTER(STRUCTS["soilfluxes"]), C.c_int, C.POINTER(Status)]
+    L.ctsm_b200_begin_water_column_balance.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p,
+                                                       C.POINTER(STRUCTS["waterbalance"]), C.c_double, C.c_int, C.POINTER(Status)]
+    L.ctsm_b200_begin_water_column_balance.restype = C.c_int
     L.ctsm_b200_set_filters.argtypes = [vp, C.POINTER(Bounds), C.POINTER(FilterInputs), C.POINTER(Filters), C.c_int]
     L.ctsm_b200_set_filters.restype = C.c_int
     L.ctsm_b200_patch2col.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p,

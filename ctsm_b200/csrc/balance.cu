@@ -215,6 +215,97 @@ plantsink_kernel(PlantSinkDev f, int begc0, int ldc, int begp0, int ldp, int num
 }
 }  // namespace
 
+struct WaterBalanceDev {
+#define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) ctype* name;
+#define CTSM_FIELDS_WATERBALANCE
+#include "../../include/ctsm_b200_fields.def"
+#undef CTSM_FIELDS_WATERBALANCE
+#undef CTSM_F
+};
+
+namespace {
+// BeginWaterColumnBalanceSingle (BalanceCheckMod.F90:262-330) -> ComputeLiqIceMassNonLake (TotalWaterAndHeatMod.F90:200-326)
+// + AccumulateSoilLiqIceMassNonLake (:329-393) + CalculateTotalH2osno: one thread per non-lake column; level sums
+// ascending (the reference's level-outer / column-inner sweep visits a column's levels in that order), canopy water by
+// p2c over the column's contiguous patches.  HBM bound: 2 x 37 level reads + 25 excess-ice reads per column, coalesced.
+__global__ void __launch_bounds__(128)
+water_mass_kernel(WaterBalanceDev f, double aquifer_water_baseline, int begc0, int ldc_, int begp0, int numc,
+                  const int32_t* __restrict__ filterc, DevStatus* ds) {
+  const int fc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fc >= numc) return;
+  const int c1 = filterc[fc], cc = c1 - begc0;
+  const size_t ldc = (size_t)ldc_;
+  const int lt = f.lun_itype[cc];
+  if (lt >= CTSM_ISTURB_MIN && lt <= CTSM_ISTURB_MAX) { report_failure(ds, c1, CTSM_ERR_URBAN, 0); return; }
+  double liqcan_col = 0.0, snocan_col = 0.0;
+  const int pi = f.patchi[cc], pf = f.patchf[cc];
+  for (int p1 = pi; p1 <= pf; ++p1) {
+    const int pp = p1 - begp0;
+    if (f.patch_active[pp]) {
+      const double wt = f.wtcol[pp];
+      liqcan_col = liqcan_col + f.liqcan[pp] * wt;
+      snocan_col = snocan_col + f.snocan[pp] * wt;
+    }
+  }
+  double liquid_mass = 0.0, ice_mass = 0.0;
+  liquid_mass = liquid_mass + liqcan_col + f.total_plant_stored_h2o[cc];
+  ice_mass = ice_mass + snocan_col;
+  const double h2osno_no_layers = f.h2osno_no_layers[cc];
+  ice_mass = ice_mass + h2osno_no_layers;
+  const int snl = f.snl[cc];
+  double h2osno = h2osno_no_layers;
+  for (int j = snl + 1; j <= 0; ++j) {
+    const double liq = f.h2osoi_liq[(size_t)(j - SNOSOI_LO) * ldc + cc], ice = f.h2osoi_ice[(size_t)(j - SNOSOI_LO) * ldc + cc];
+    liquid_mass = liquid_mass + liq;
+    ice_mass = ice_mass + ice;
+    h2osno = h2osno + ice + liq;
+  }
+  if (f.col_hydrologically_active[cc]) liquid_mass = liquid_mass + (f.wa[cc] - aquifer_water_baseline);
+  liquid_mass = liquid_mass + f.h2osfc[cc];
+  for (int j = 1; j <= NLEVGRND; ++j) {
+    liquid_mass = liquid_mass + f.h2osoi_liq[(size_t)(j - SNOSOI_LO) * ldc + cc];
+    ice_mass = ice_mass + f.h2osoi_ice[(size_t)(j - SNOSOI_LO) * ldc + cc] + f.excess_ice[(size_t)(j - 1) * ldc + cc];
+  }
+  f.begwb[cc] = liquid_mass + ice_mass;
+  f.h2osno_old[cc] = h2osno;
+}
+}  // namespace
+
+extern "C" int ctsm_b200_begin_water_column_balance(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_nolakec,
+                                                    const int32_t* filter_nolakec, const ctsm_waterbalance_fields_t* hf,
+                                                    double aquifer_water_baseline, int mem, ctsm_status_t* st) {
+  if (!ctx || !bounds || !hf || num_nolakec < 0 || (num_nolakec > 0 && !filter_nolakec)) return CTSM_ERR_BAD_ARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  WaterBalanceDev d;
+  const int32_t* dfilter = filter_nolakec;
+  std::vector<StageField> fl;
+#define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) \
+  d.name = hf->name;                                        \
+  fl.push_back(StageField{(void**)&d.name, (void*)hf->name, (int)sizeof(ctype), SUB_##sub, lev_shape(#lev).n, INTENT_##intent});
+#define CTSM_FIELDS_WATERBALANCE
+#include "../../include/ctsm_b200_fields.def"
+#undef CTSM_FIELDS_WATERBALANCE
+#undef CTSM_F
+  for (auto& s : fl) if (!s.host_ptr) return CTSM_ERR_BAD_ARG;
+  if (mem != CTSM_MEM_DEVICE) {
+    int rc = stage_begin(ctx, fl, hf->alloc, *bounds, mem == CTSM_MEM_HOST);
+    if (rc) return rc;
+    rc = stage_filter(ctx, ctx->arena_filter0, filter_nolakec, num_nolakec, &dfilter);
+    if (rc) return rc;
+  }
+  if (num_nolakec > 0) {
+    water_mass_kernel<<<grid_for(num_nolakec, 128), 128, 0, ctx->stream>>>(
+        d, aquifer_water_baseline, hf->alloc.begc, hf->alloc.endc - hf->alloc.begc + 1, hf->alloc.begp, num_nolakec, dfilter,
+        ctx->d_status);
+    ctx->launches++;
+  }
+  if (mem != CTSM_MEM_DEVICE) {
+    int rc = stage_end(ctx, fl, hf->alloc, *bounds);
+    if (rc) return rc;
+  }
+  return finish_call(ctx, mem, st);
+}
+
 extern "C" int ctsm_b200_balancecheck_init(ctsm_b200_ctx* ctx) {
   if (!ctx) return -1;
   // BalanceCheckMod.F90:91: skip_steps = max(2, nint(skip_size/dtime)) + 1, skip_size = 3600 s (:56)

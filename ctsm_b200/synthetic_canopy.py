@@ -319,6 +319,24 @@ def soilfluxes_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Gener
         S[k] = np.ascontiguousarray(v)
 
 
+def waterbalance_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator) -> None:
+    """Adds the fields of group `waterbalance` (BeginWaterColumnBalance, BalanceCheckMod.F90:171)."""
+    nc = sg.ncol
+    S["wa"] = rng.uniform(4000.0, 5000.0, nc)
+    S["total_plant_stored_h2o"] = np.zeros(nc)
+    S["excess_ice"] = np.where(rng.random((25, nc)) < 0.05, rng.uniform(0.0, 30.0, (25, nc)), 0.0)
+    S["col_hydrologically_active"] = np.isin(sg.col_lun_itype, (1, 2)).astype(np.int32)
+    S["patch_active"] = sg.patch_active.astype(np.int32)
+    for nm in ("liqcan", "snocan"):
+        S[nm] = np.where(np.abs(S[nm]) < 1e30, S[nm], 0.0)
+    for fs in abi_fields("waterbalance"):
+        if fs.name not in S:
+            n = sg.ncol if fs.sub == "COL" else sg.npatch
+            S[fs.name] = np.full(n if fs.lev == "L1" else (fs.nlev, n), 1.0e36, dtype=fs.dtype)
+    for k, v in list(S.items()):
+        S[k] = np.ascontiguousarray(v)
+
+
 def abi_fields(group):
     from . import abi
     return abi.FIELDS[group]

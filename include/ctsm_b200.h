@@ -12,6 +12,7 @@
  *   ctsm_b200_canopyfluxes       src/biogeophys/CanopyFluxesMod.F90:191  (+ PhotosynthesisMod.F90:2704 PHS)
  *   ctsm_b200_set_filters        src/main/filterMod.F90:303   (setFiltersOneGroup)
  *   ctsm_b200_set_exposedvegp_filter  src/main/filterMod.F90:595
+ *   ctsm_b200_begin_water_column_balance  src/biogeophys/BalanceCheckMod.F90:171  (+ TotalWaterAndHeatMod.F90:92)
  *   ctsm_b200_balancecheck       src/biogeophys/BalanceCheckMod.F90:445,859
  *   ctsm_b200_soilfluxes         src/biogeophys/SoilFluxesMod.F90:37   (+ p2c, src/main/subgridAveMod.F90:292)
  *   ctsm_b200_patch2col          src/main/clm_driver.F90:1655          (clm_drv_patch2col)
@@ -188,6 +189,13 @@ typedef struct ctsm_patch2col_fields_t {
 #undef CTSM_FIELDS_PATCH2COL
 } ctsm_patch2col_fields_t;
 
+typedef struct ctsm_waterbalance_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_WATERBALANCE
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_WATERBALANCE
+} ctsm_waterbalance_fields_t;
+
 typedef struct ctsm_balancecheck_fields_t {
   ctsm_bounds_t alloc;
 #define CTSM_FIELDS_BALANCECHECK
@@ -343,6 +351,13 @@ int ctsm_b200_soilfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int nu
 int ctsm_b200_patch2col(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_allc, const int32_t* filter_allc,
                         int num_nolakec, const int32_t* filter_nolakec, const ctsm_patch2col_fields_t* f, int mem,
                         ctsm_status_t* st);
+
+/* BeginWaterColumnBalance(bounds, num_nolakec, filter_nolakec, num_lakec, filter_lakec, ...): BalanceCheckMod.F90:171,
+ * call site clm_driver.F90:414.  Bulk water, non-lake columns (the lake filter of the reference's dummy list is empty on
+ * this path), use_aquifer_layer = .false. (clm5/clm6 default).  aquifer_water_baseline: waterstate_inst scalar. */
+int ctsm_b200_begin_water_column_balance(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_nolakec,
+                                         const int32_t* filter_nolakec, const ctsm_waterbalance_fields_t* f,
+                                         double aquifer_water_baseline, int mem, ctsm_status_t* st);
 
 /* BalanceCheckInit(): BalanceCheckMod.F90:74-95; skip_steps = max(2, nint(3600/dtime)) + 1.  Returns skip_steps. */
 int ctsm_b200_balancecheck_init(ctsm_b200_ctx* ctx);

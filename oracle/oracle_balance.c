@@ -246,3 +246,50 @@ int oracle_vert_tran_sink_hydstress(const ctsm_bounds_t* bounds, int num_filterc
   }
   return 0;
 }
+
+/* BeginWaterColumnBalanceSingle (BalanceCheckMod.F90:262-330, use_aquifer_layer = .false.) =
+ * ComputeWaterMassNonLake -> ComputeLiqIceMassNonLake (TotalWaterAndHeatMod.F90:200-326, p2c of the canopy water,
+ * subtract_dynbal_baselines = .false.) -> AccumulateSoilLiqIceMassNonLake (:329-393, level-outer / column-inner, i.e.
+ * ascending levels per column) + CalculateTotalH2osno (WaterStateType.F90:887-896).  Non-urban columns. */
+int oracle_begin_water_column_balance(const ctsm_bounds_t* bounds, int num_nolakec, const int32_t* filter_nolakec,
+                                      const ctsm_waterbalance_fields_t* f, double aquifer_water_baseline, ctsm_status_t* st) {
+  (void)bounds;
+  const int begc0 = f->alloc.begc, begp0 = f->alloc.begp;
+  const size_t ldc = (size_t)(f->alloc.endc - f->alloc.begc + 1);
+  if (st) memset(st, 0, sizeof *st);
+  for (int fc = 0; fc < num_nolakec; ++fc) {
+    const int c = filter_nolakec[fc], cc = c - begc0;
+    const int lt = f->lun_itype[cc];
+    if (lt >= CTSM_ISTURB_MIN && lt <= CTSM_ISTURB_MAX) {
+      if (st) { st->code = CTSM_ERR_URBAN; st->subgrid_level = CTSM_SUBGRID_COLUMN; st->subgrid_index = c; }
+      return CTSM_ERR_URBAN;
+    }
+    double liqcan_col = 0.0, snocan_col = 0.0;                           /* p2c, subgridAveMod.F90:312-318 */
+    for (int p = f->patchi[cc]; p <= f->patchf[cc]; ++p)
+      if (f->patch_active[p - begp0]) liqcan_col = liqcan_col + f->liqcan[p - begp0] * f->wtcol[p - begp0];
+    for (int p = f->patchi[cc]; p <= f->patchf[cc]; ++p)
+      if (f->patch_active[p - begp0]) snocan_col = snocan_col + f->snocan[p - begp0] * f->wtcol[p - begp0];
+    double liquid_mass = 0.0, ice_mass = 0.0;
+    liquid_mass = liquid_mass + liqcan_col + f->total_plant_stored_h2o[cc];
+    ice_mass = ice_mass + snocan_col;
+    ice_mass = ice_mass + f->h2osno_no_layers[cc];
+    const int snl = f->snl[cc];
+    for (int j = snl + 1; j <= 0; ++j) {
+      liquid_mass = liquid_mass + f->h2osoi_liq[(size_t)(j - SNOSOI_LO) * ldc + cc];
+      ice_mass = ice_mass + f->h2osoi_ice[(size_t)(j - SNOSOI_LO) * ldc + cc];
+    }
+    if (f->col_hydrologically_active[cc]) liquid_mass = liquid_mass + (f->wa[cc] - aquifer_water_baseline);
+    liquid_mass = liquid_mass + f->h2osfc[cc];
+    for (int j = 1; j <= CTSM_NLEVGRND; ++j) {
+      liquid_mass = liquid_mass + f->h2osoi_liq[(size_t)(j - SNOSOI_LO) * ldc + cc];
+      ice_mass = ice_mass + f->h2osoi_ice[(size_t)(j - SNOSOI_LO) * ldc + cc] + f->excess_ice[(size_t)(j - 1) * ldc + cc];
+    }
+    f->begwb[cc] = liquid_mass + ice_mass;
+    double t = f->h2osno_no_layers[cc];
+    for (int j = snl + 1; j <= 0; ++j)
+      t = t + f->h2osoi_ice[(size_t)(j - SNOSOI_LO) * ldc + cc] + f->h2osoi_liq[(size_t)(j - SNOSOI_LO) * ldc + cc];
+    f->h2osno_old[cc] = t;
+  }
+  return 0;
+}
+
