@@ -29,6 +29,20 @@ def test_partition_is_exact(numg, npes, cpp):
         assert np.array_equal(cid, (np.arange(numg) % (npes * cpp)) + 1)
 
 
+# argument order of oracle_fullstep_clumps: the whole step of clm_drv (CanopyFluxes -> SoilTemperature -> SoilFluxes ->
+# clm_drv_patch2col -> root-water sink -> SoilWater -> BalanceCheck)
+STEP_GROUPS = ("soiltemperature", "soilwater", "canopyfluxes", "plantsink", "balancecheck", "soilfluxes", "patch2col")
+CHECKED = ("t_veg", "num_iter", "t_soisno", "h2osoi_liq", "qflx_tran_veg", "t_grnd", "eflx_soil_grnd", "errsoi_col",
+           "qflx_evap_soi_col", "qflx_rootsoi", "errh2o")
+
+
+def _global_case(synthetic_canopy):
+    sg, S = synthetic_canopy.make_full_case(48, seed=5)
+    synthetic_canopy.balance_state(sg, S, np.random.Generator(np.random.PCG64(6)), 1.0e-11)
+    synthetic_canopy.soilfluxes_state(sg, S, np.random.Generator(np.random.PCG64(7)))
+    return sg, S
+
+
 def _worker(rank, world, port, q):
     import ctypes as C
     import torch.distributed as dist
@@ -39,11 +53,10 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     OL = oracle.lib()
     prm = abi.default_params()
-    sg, S = synthetic_canopy.make_full_case(48, seed=5)            # every rank builds the same global case
+    sg, S = _global_case(synthetic_canopy)                        # every rank builds the same global case
     cells = decomp.rank_gridcells(sg.ngrc, world, 3, rank, nsegspc=2)
-    ft = abi.make_struct("soiltemperature", S, sg.bounds)
-    fw = abi.make_struct("soilwater", S, sg.bounds)
-    fc = abi.make_struct("canopyfluxes", S, sg.bounds)
+    prm.balance_skip_steps = int(OL.oracle_balancecheck_skip_steps(prm.dtime))
+    structs = [abi.make_struct(g, S, sg.bounds) for g in STEP_GROUPS]
     touched = np.zeros(sg.ngrc + 1, dtype=bool)
     for cl in cells:                                              # contiguous runs of gridcells = segments
         if len(cl) == 0:
@@ -52,7 +65,7 @@ def _worker(rank, world, port, q):
         for run in runs:
             sub = oracle.clump_for_gridcells(sg, int(run[0]), int(run[-1]))
             arr, keep = sub
-            assert OL.oracle_step_clumps(C.byref(prm), 1, arr, C.byref(ft), C.byref(fw), C.byref(fc), 7) == 0
+            assert OL.oracle_fullstep_clumps(C.byref(prm), 1, arr, *[C.byref(x) for x in structs], 1, 127) == 0
             touched[run] = True
     import torch
     mx = torch.tensor([float(np.nanmax(np.where(touched[S["gridcell"]], np.where(S["t_veg"] < 1e30, S["t_veg"], 0), 0)))], dtype=torch.float64)
@@ -61,7 +74,7 @@ def _worker(rank, world, port, q):
     pmask = touched[S["gridcell"]]
     cmask = touched[sg.col_gridcell]
     q.put((rank, touched, {k: (S[k][..., pmask] if S[k].shape[-1] == sg.npatch else S[k][..., cmask])
-                           for k in ("t_veg", "num_iter", "t_soisno", "h2osoi_liq", "qflx_tran_veg", "t_grnd")}, float(mx), got))
+                           for k in CHECKED}, float(mx), got))
     dist.destroy_process_group()
 
 
@@ -82,12 +95,11 @@ def test_two_rank_gloo_run_matches_single(oracle_lib):
         assert p.exitcode == 0
     # single-process reference run
     prm = abi.default_params()
-    sg, S = synthetic_canopy.make_full_case(48, seed=5)
+    prm.balance_skip_steps = int(oracle_lib.oracle_balancecheck_skip_steps(prm.dtime))
+    sg, S = _global_case(synthetic_canopy)
     arr, keep = oracle.make_clumps(sg, 1)
-    ft = abi.make_struct("soiltemperature", S, sg.bounds)
-    fw = abi.make_struct("soilwater", S, sg.bounds)
-    fc = abi.make_struct("canopyfluxes", S, sg.bounds)
-    assert oracle_lib.oracle_step_clumps(C.byref(prm), 1, arr, C.byref(ft), C.byref(fw), C.byref(fc), 7) == 0
+    structs = [abi.make_struct(g, S, sg.bounds) for g in STEP_GROUPS]
+    assert oracle_lib.oracle_fullstep_clumps(C.byref(prm), 1, arr, *[C.byref(x) for x in structs], 1, 127) == 0
     owned = np.zeros(sg.ngrc + 1, dtype=np.int32)
     for rank, touched, fields, mx, got in res:
         owned += touched
