@@ -33,7 +33,7 @@ print("(ncu serialises launches and flushes caches between them: the SHARES are 
 if len(sys.argv) > 3:
     # DRAM bytes per call of each routine (bench.py roofline.traffic): tools/launch_summary.py CSV OUT.json SIZE
     import json
-    routine_of = lambda k: ("SoilTemperature" if k in ("soiltemp_kernel", "patchmask_kernel") else "SoilWater" if "soilwater" in k else "SoilFluxes" if "soilfluxes" in k
+    routine_of = lambda k: ("SoilTemperature" if k in ("soiltemp_kernel", "patchmask_kernel") else "SoilWater" if "soilwater" in k else "SoilFluxes" if "soilfluxes" in k else "clm_drv_patch2col" if "patch2col" in k
                             else "VertTranSink_HydStress" if k.startswith("plantsink") else "BalanceCheck" if k.startswith("balance")
                             else "CanopyFluxes")
     per = collections.defaultdict(float)
