@@ -99,7 +99,7 @@ class Params(C.Structure):
                     "vcmaxhd", "jmaxhd", "tpuhd", "lmrhd", "lmrse",
                     "tpu25ratio", "kp25ratio", "vcmaxse_sf", "jmaxse_sf", "tpuse_sf", "jmax25top_sf")] + [
                 ("balance_skip_steps", C.c_int32),
-                ("reserved_i", C.c_int32 * 7), ("reserved_d", C.c_double * 8)]
+                ("npft_table", C.c_int32), ("reserved_i", C.c_int32 * 6), ("reserved_d", C.c_double * 8)]
 
 
 def default_params(dtime: float = 1800.0, device: int = 0) -> Params:
@@ -197,6 +197,9 @@ def make_struct(group: str, arrays: dict, alloc: Bounds):
     for fs in FIELDS[group]:
         a = arrays[fs.name]
         n = alloc.extent(fs.sub)
+        if fs.sub == "PFT":         # parameter tables: (mxpft+1) x members (ctsm_params_t::npft_table)
+            n = int(a.shape[-1])
+            assert n % (MXPFT + 1) == 0, "%s.%s: table length %d is not a multiple of mxpft+1" % (group, fs.name, n)
         want = (n,) if fs.lev == "L1" else (fs.nlev, n)
         assert tuple(a.shape) == want, "%s.%s: shape %s != %s" % (group, fs.name, tuple(a.shape), want)
         kind = "float64" if fs.ctype == "double" else "int32"

@@ -46,6 +46,7 @@ extern "C" void ctsm_b200_default_params(ctsm_params_t* p) {
   p->tpu25ratio = 0.167; p->kp25ratio = 20000.0;
   p->vcmaxse_sf = 1.0; p->jmaxse_sf = 1.0; p->tpuse_sf = 1.0; p->jmax25top_sf = 1.0;
   p->balance_skip_steps = -1;
+  p->npft_table = CTSM_MXPFT + 1;
 }
 
 extern "C" int ctsm_b200_init(const ctsm_params_t* p, ctsm_b200_ctx** out) {
@@ -60,6 +61,7 @@ extern "C" int ctsm_b200_init(const ctsm_params_t* p, ctsm_b200_ctx** out) {
   if (p->use_hydrstress != 1 || (p->z0param_method != 1 && p->z0param_method != 2) ||
       (p->stomatalcond_mtd != 1 && p->stomatalcond_mtd != 2) || p->itmax_canopy_fluxes < 1)
     return CTSM_ERR_BAD_ARG;
+  if (p->npft_table < CTSM_MXPFT + 1 || p->npft_table % (CTSM_MXPFT + 1) != 0) return CTSM_ERR_BAD_ARG;
   if (p->upper_boundary_condition != 1 || (p->lower_boundary_condition != 1 && p->lower_boundary_condition != 2))
     return CTSM_ERR_BAD_ARG;
   int ndev = 0;
@@ -206,20 +208,20 @@ int stage_begin(ctsm_b200_ctx* ctx, std::vector<StageField>& fl, const ctsm_boun
   size_t total = 0;
   for (auto& f : fl) {
     if (!f.host_ptr) return CTSM_ERR_BAD_ARG;
-    const size_t ld = (size_t)(sub_end(alloc, f.sub) - sub_beg(alloc, f.sub) + 1);
+    const size_t ld = (size_t)(sub_end(alloc, f.sub, ctx->prm.npft_table) - sub_beg(alloc, f.sub) + 1);
     total += align256((size_t)f.elem_size * ld * f.nlev);
   }
   int rc = arena_reserve(ctx->arena_fields, total);
   if (rc) return rc;
   size_t off = 0;
   for (auto& f : fl) {
-    const size_t ld = (size_t)(sub_end(alloc, f.sub) - sub_beg(alloc, f.sub) + 1);
+    const size_t ld = (size_t)(sub_end(alloc, f.sub, ctx->prm.npft_table) - sub_beg(alloc, f.sub) + 1);
     void* d = (char*)ctx->arena_fields.p + off;
     *f.dev_slot = d;
     off += align256((size_t)f.elem_size * ld * f.nlev);
     if ((f.intent & INTENT_IN) || preserve_out) {
       const size_t o = (size_t)(sub_beg(call, f.sub) - sub_beg(alloc, f.sub));
-      const size_t n = (size_t)(sub_end(call, f.sub) - sub_beg(call, f.sub) + 1);
+      const size_t n = (size_t)(sub_end(call, f.sub, ctx->prm.npft_table) - sub_beg(call, f.sub) + 1);
       rc = copy_range(d, f.host_ptr, f.elem_size, ld, f.nlev, o, n, cudaMemcpyHostToDevice, ctx->stream);
       if (rc) return rc;
     }
@@ -230,9 +232,9 @@ int stage_begin(ctsm_b200_ctx* ctx, std::vector<StageField>& fl, const ctsm_boun
 int stage_end(ctsm_b200_ctx* ctx, std::vector<StageField>& fl, const ctsm_bounds_t& alloc, const ctsm_bounds_t& call) {
   for (auto& f : fl) {
     if (!(f.intent & INTENT_OUT)) continue;
-    const size_t ld = (size_t)(sub_end(alloc, f.sub) - sub_beg(alloc, f.sub) + 1);
+    const size_t ld = (size_t)(sub_end(alloc, f.sub, ctx->prm.npft_table) - sub_beg(alloc, f.sub) + 1);
     const size_t o = (size_t)(sub_beg(call, f.sub) - sub_beg(alloc, f.sub));
-    const size_t n = (size_t)(sub_end(call, f.sub) - sub_beg(call, f.sub) + 1);
+    const size_t n = (size_t)(sub_end(call, f.sub, ctx->prm.npft_table) - sub_beg(call, f.sub) + 1);
     int rc = copy_range(f.host_ptr, *f.dev_slot, f.elem_size, ld, f.nlev, o, n, cudaMemcpyDeviceToHost, ctx->stream);
     if (rc) return rc;
   }

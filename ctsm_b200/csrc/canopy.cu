@@ -61,7 +61,6 @@ constexpr double rpi = 3.14159265358979323846;
 constexpr double sb = 5.67e-8, cpair = 1.00464e3, hvap = 2.501e6, vkc = 0.4, grav = 9.80616;
 constexpr double denice = 0.917e3, denh2o = 1.000e3, c_to_b = 2.0, tlsai_crit = 2.0, alpha_aero = 1.0;
 constexpr double c_water = 4.188e3, c_dry_biomass = 1400.0, nu_param = 1.5e-5, cd1_param = 7.5;
-constexpr int NPFT = CTSM_MXPFT + 1;
 
 // workspace slots (structure of arrays, one row of `stride` doubles per slot, indexed by filter position)
 enum Slot {
@@ -84,6 +83,7 @@ struct CanopyPrm {
 struct Geo {   // index bases / leading dimensions
   int begp0, begc0, begg0, ldp, ldc;
   int begp, endp, begc, endc;   // call bounds
+  int npft;                     // length of the PFT parameter tables (ctsm_params_t::npft_table)
 };
 
 // Active list of one ITERATION pass: ONE list in (roughly) ascending filter order.  Survivors are appended per warp, so a
@@ -475,7 +475,7 @@ canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int32_t* __r
   {
     const double froot_carbon = PF(froot_carbon), tsl = PF(tsai) + PF(tlai);
     const double rr = f.pft_root_radius[ivt], rd = f.pft_root_density[ivt], frl = f.pft_froot_leaf[ivt], krmax = f.pft_krmax[ivt];
-    const double psi50r = f.pft_psi50[(size_t)phs::ROOT * NPFT + ivt], ckr = f.pft_ck[(size_t)phs::ROOT * NPFT + ivt];
+    const double psi50r = f.pft_psi50[(size_t)phs::ROOT * g.npft + ivt], ckr = f.pft_ck[(size_t)phs::ROOT * g.npft + ivt];
     double ksum = 0.0, ksmp = 0.0, ksmpg = 0.0, smpg = 0.0;
     for (int j = 1; j <= NLEVSOI; ++j) {
       const double rootfr = PF2(rootfr, j - 1);
@@ -507,9 +507,9 @@ canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int32_t* __r
   {
 #pragma unroll
     for (int sgm = 0; sgm < 4; ++sgm) {
-      R.psi50[sgm] = f.pft_psi50[(size_t)sgm * NPFT + ivt];
-      R.ck[sgm] = f.pft_ck[(size_t)sgm * NPFT + ivt];
-      R.kmax[sgm] = f.pft_kmax[(size_t)sgm * NPFT + ivt];
+      R.psi50[sgm] = f.pft_psi50[(size_t)sgm * g.npft + ivt];
+      R.ck[sgm] = f.pft_ck[(size_t)sgm * g.npft + ivt];
+      R.kmax[sgm] = f.pft_kmax[(size_t)sgm * g.npft + ivt];
     }
     const double forc_pbot = CF(forc_pbot);
     R.laisun = PF(laisun); R.laisha = PF(laisha); R.elai = elai; R.esai = esai; R.tsai = PF(tsai); R.htop = htop; R.fdry = PF(fdry);
@@ -1567,6 +1567,7 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   g.begp0 = hf->alloc.begp; g.begc0 = hf->alloc.begc; g.begg0 = hf->alloc.begg;
   g.ldp = hf->alloc.endp - hf->alloc.begp + 1; g.ldc = hf->alloc.endc - hf->alloc.begc + 1;
   g.begp = bounds->begp; g.endp = bounds->endp; g.begc = bounds->begc; g.endc = bounds->endc;
+  g.npft = p.npft_table;
   const int fn = num_exposedvegp;
   const int npb = g.endp - g.begp + 1, ncb = g.endc - g.begc + 1;
   if (npb <= 0) return finish_call(ctx, mem, st);

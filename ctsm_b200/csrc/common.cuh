@@ -118,8 +118,8 @@ static inline int sub_beg(const ctsm_bounds_t& b, int sub) {
   if (sub == SUB_PFT) return 0;
   return sub == SUB_GRC ? b.begg : sub == SUB_LUN ? b.begl : sub == SUB_COL ? b.begc : b.begp;
 }
-static inline int sub_end(const ctsm_bounds_t& b, int sub) {
-  if (sub == SUB_PFT) return CTSM_MXPFT;
+static inline int sub_end(const ctsm_bounds_t& b, int sub, int npft_table) {
+  if (sub == SUB_PFT) return npft_table - 1;
   return sub == SUB_GRC ? b.endg : sub == SUB_LUN ? b.endl : sub == SUB_COL ? b.endc : b.endp;
 }
 

@@ -337,6 +337,31 @@ def waterbalance_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Gen
         S[k] = np.ascontiguousarray(v)
 
 
+def make_ensemble(sg: Subgrid, S: Dict[str, np.ndarray], nmember: int, rng: np.random.Generator, spread: float = 0.2):
+    """Perturbed-parameter ensemble through the PFT tables (BASELINE config 5): the grid is split into `nmember` equal
+    runs of gridcells, member m's patches get itype = m*(mxpft+1) + pft, and every pft_* table is extended to
+    nmember*(mxpft+1) entries with member m's copy of medlynslope, kmax, psi50, ck and krmax scaled by U(1-spread,
+    1+spread) factors (member 0 keeps the base table).  Returns the member index of every patch; run with
+    ctsm_params_t.npft_table = nmember*(mxpft+1)."""
+    npft = abi_mod().MXPFT + 1
+    member_g = np.minimum((np.arange(sg.ngrc) * nmember) // max(sg.ngrc, 1), nmember - 1)
+    member_p = member_g[sg.patch_gridcell - 1].astype(np.int32)
+    S["itype"] = (S["itype"] + member_p * npft).astype(np.int32)
+    perturbed = ("pft_medlynslope", "pft_kmax", "pft_psi50", "pft_ck", "pft_krmax")
+    for k in [k for k in S if k.startswith("pft_")]:
+        base = S[k]
+        reps = [base]
+        for m in range(1, nmember):
+            reps.append(base * rng.uniform(1.0 - spread, 1.0 + spread) if k in perturbed else base)
+        S[k] = np.ascontiguousarray(np.concatenate(reps, axis=-1).astype(base.dtype))
+    return member_p
+
+
+def abi_mod():
+    from . import abi
+    return abi
+
+
 def abi_fields(group):
     from . import abi
     return abi.FIELDS[group]

@@ -139,7 +139,11 @@ typedef struct ctsm_params_t {
   double  tpu25ratio, kp25ratio, vcmaxse_sf, jmaxse_sf, tpuse_sf, jmax25top_sf;
   /* BalanceCheckMod.F90:74-95 */
   int32_t balance_skip_steps;           /* set by ctsm_b200_balancecheck_init */
-  int32_t reserved_i[7];
+  int32_t npft_table;                   /* length of every PFT parameter table: (CTSM_MXPFT+1) x number of parameter-set
+                                         * members; patch%itype indexes the table directly, so a perturbed-parameter
+                                         * ensemble (BASELINE config 5) runs member m's patches with itype = m*(mxpft+1)+pft.
+                                         * Default CTSM_MXPFT+1 (one parameter set: pftcon as the reference holds it). */
+  int32_t reserved_i[6];
   double  reserved_d[8];
 } ctsm_params_t;
 

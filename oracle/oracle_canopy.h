@@ -9,7 +9,7 @@
 #define NLEVGRND CTSM_NLEVGRND
 #define NLEVSOI CTSM_NLEVSOI
 #define SNOSOI_LO (-NLEVSNO + 1)
-#define NPFT (CTSM_MXPFT + 1)
+#define NPFT (x->prm->npft_table)      /* runtime: (mxpft+1) x parameter-set members */
 
 /* shr_const_mod.F90:16-53, clm_varcon.F90:41-125 (spelled as the reference spells them) */
 static const double rpi = 3.14159265358979323846;
