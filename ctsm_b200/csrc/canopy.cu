@@ -990,6 +990,9 @@ canopy_leaf_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, const int32_t*
 #ifndef REFILL_MIN
 #define REFILL_MIN 8          // refill when at least this many lanes are idle (or nothing else is left to do)
 #endif
+#ifndef CI_REFILL_MIN
+#define CI_REFILL_MIN REFILL_MIN   // the same threshold serves the ci tasks (measured: 4 / 8 / 16 within 1 %)
+#endif
 #ifndef FIN_MIN
 #define FIN_MIN 16            // run the calcstress epilogue when at least this many lanes are waiting (for it or for work)
 #endif
@@ -1172,7 +1175,7 @@ phs_ci_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const int*
   bool bad = false, nb = false;
   for (;;) {
     const unsigned idle = __ballot_sync(FULL, st == LS_IDLE);
-    if (!exhausted && (__popc(idle) >= REFILL_MIN)) {
+    if (!exhausted && (__popc(idle) >= CI_REFILL_MIN)) {
       int base = 0;
       if (lane == 0) base = atomicAdd(head, __popc(idle));
       base = __shfl_sync(FULL, base, 0);
