@@ -1,0 +1,29 @@
+"""Regression fixture of the oracle itself (tests/golden/oracle_step_tiny.npz, written by make_oracle_golden.py): the
+seven-routine step on the 64-gridcell case must reproduce the frozen outputs.  This pins the ORACLE against accidental
+edits; it says nothing about parity with the reference (which cannot be built here)."""
+import importlib.util
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_oracle_step_reproduces_frozen_outputs():
+    spec = importlib.util.spec_from_file_location("make_oracle_golden", os.path.join(HERE, "golden", "make_oracle_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    got = mod.run()
+    want = np.load(os.path.join(HERE, "golden", "oracle_step_tiny.npz"))
+    assert set(want.files) == set(mod.FIELDS)
+    for k in mod.FIELDS:
+        a, b = got[k], want[k]
+        assert a.shape == b.shape, k
+        fin = np.abs(b.astype(float)) < 1e30
+        assert np.array_equal(fin, np.abs(a.astype(float)) < 1e30), k
+        if b.dtype.kind == "i":
+            assert np.array_equal(a, b), k
+            continue
+        # same compiler flags and libm give bit-identical results; the bound leaves room for a libm update only
+        scale = np.max(np.abs(b[fin])) if fin.any() else 1.0
+        assert np.all(np.abs(a[fin] - b[fin]) <= 1e-12 * np.maximum(np.abs(b[fin]), 1e-6 * scale)), k
