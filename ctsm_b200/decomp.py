@@ -37,6 +37,38 @@ def rank_gridcells(numg: int, npes: int, clump_pproc: int, rank: int, nsegspc: i
     return [np.nonzero(cid == n)[0].astype(np.int64) + 1 for n in mine]
 
 
+def balanced_slabs(cost_per_gridcell, nparts: int) -> np.ndarray:
+    """Contiguous gridcell slabs of (nearly) equal cost for the GPU layout of SURVEY.md 8e: the reference balances clumps
+    by gridcell COUNT (decompInitMod.F90:117-145), but the cost of the hot path is proportional to the number of
+    exposed-vegetation patches (CanopyFluxes is >90 % of the step), which varies by an order of magnitude between
+    gridcells of a real surface dataset.  Returns edges e (len nparts+1, e[0] = 0, e[-1] = numg): part k owns gridcells
+    e[k]+1 .. e[k+1] (1-based).  Slabs are contiguous so that each part's landunits, columns and patches are contiguous
+    index ranges (initGridCellsMod nests g > l > c > p) and every routine can be called with plain clump bounds.
+    Greedy prefix-sum cut: part k ends at the first gridcell where the running cost reaches (k+1)/nparts of the total;
+    the imbalance is bounded by the cost of one gridcell."""
+    c = np.asarray(cost_per_gridcell, dtype=np.float64)
+    numg = len(c)
+    nparts = max(1, int(nparts))
+    cum = np.concatenate([[0.0], np.cumsum(c)])
+    total = cum[-1]
+    edges = np.zeros(nparts + 1, dtype=np.int64)
+    edges[-1] = numg
+    for k in range(1, nparts):
+        if total > 0:
+            e = int(np.searchsorted(cum, total * k / nparts, side="left"))
+        else:
+            e = (numg * k) // nparts
+        edges[k] = min(max(e, edges[k - 1]), numg)
+    return edges
+
+
+def slab_imbalance(cost_per_gridcell, edges) -> float:
+    """max part cost / mean part cost (1.0 = perfect)."""
+    c = np.asarray(cost_per_gridcell, dtype=np.float64)
+    parts = np.array([c[edges[k]:edges[k + 1]].sum() for k in range(len(edges) - 1)])
+    return float(parts.max() / parts.mean()) if parts.mean() > 0 else 1.0
+
+
 def reduce_balance_report(max_abs, dist=None):
     """Global maxima of the per-rank BalanceCheck report (reporting diagnostic only; the reference has no
     such collective, BalanceCheckMod.F90 is clump-local).  `dist` is torch.distributed or None."""
