@@ -22,3 +22,12 @@ def test_fortran_shim_is_current_and_complete():
     for fn in set(re.findall(r"\b(ctsm_b200_\w+)\s*\(", hdr)):
         assert 'bind(C, name="%s")' % fn in committed, fn
     assert not [l for l in committed.splitlines() if len(l) > 132 and not l.lstrip().startswith("!")]
+    # the per-group c_loc blocks: one assignment (or one GATHER note) per table entry
+    fill = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_fortran_shim.py"), "--fill"], capture_output=True, text=True)
+    assert fill.returncode == 0, fill.stderr
+    inc = open(os.path.join(ROOT, "integration", "ctsm_b200_fill.inc")).read()
+    assert fill.stdout == inc, "integration/ctsm_b200_fill.inc is stale: rerun tools/gen_fortran_shim.py --fill"
+    for g, fields in abi.FIELDS.items():
+        block = re.search(r"#ifdef CTSM_FILL_%s\n(.*?)#undef" % g.upper(), inc, re.S).group(1)
+        n = len(re.findall(r"^  f%\w+ = c_loc", block, re.M)) + len(re.findall(r"^  ! GATHER", block, re.M))
+        assert n == len(fields), g
