@@ -58,3 +58,32 @@ def test_no_device_is_loud():
     ctx = C.c_void_p()
     assert L.ctsm_b200_init(C.byref(p), C.byref(ctx)) == 1
     assert not ctx.value
+
+
+def test_ctypes_mirrors_have_the_c_layout(tmp_path):
+    """sizeof / offsetof of every hand-written ctypes mirror against the C compiler's view of include/ctsm_b200.h."""
+    import subprocess
+    probes = {"ctsm_bounds_t": (abi.Bounds, ["begg", "endp", "clump_index"]),
+              "ctsm_status_t": (abi.Status, ["code", "value", "n_warnings", "msg"]),
+              "ctsm_params_t": (abi.Params, ["abi_version", "dtime", "e_ice", "itmax_canopy_fluxes", "lai_dl", "jmax25top_sf",
+                                             "balance_skip_steps", "npft_table", "reserved_i", "reserved_d"]),
+              "ctsm_balance_report_t": (abi.BalanceReport, ["max_abs", "index", "warn", "abort_kind", "skip_steps"]),
+              "ctsm_filter_inputs_t": (abi.FilterInputs, ["alloc", "col_active", "melt_replaced_by_ice_grc", "include_inactive",
+                                                          "npcropmax"]),
+              "ctsm_filters_t": (abi.Filters, ["list", "num"])}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ctsm_b200.h"', "int main(void) {"]
+    for cname, (_, members) in probes.items():
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for m in members:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, m, cname, m))
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = str(tmp_path / "probe")
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(abi.ROOT, "include"), str(src), "-o", exe])
+    out = dict(l.split() for l in subprocess.run([exe], capture_output=True, text=True).stdout.splitlines())
+    for cname, (ct, members) in probes.items():
+        assert C.sizeof(ct) == int(out[cname]), cname
+        for m in members:
+            assert getattr(ct, m).offset == int(out["%s.%s" % (cname, m)]), (cname, m)
+    assert len(abi.FILTER_NAMES) == C.sizeof(abi.Filters().num) // 4
