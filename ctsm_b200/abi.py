@@ -267,6 +267,11 @@ def lib():
     L.ctsm_b200_host_register.argtypes = [vp, C.c_uint64]
     L.ctsm_b200_host_unregister.argtypes = [vp]
     L.ctsm_b200_version.restype = C.c_char_p
+    L.ctsm_b200_last_cuda_error.restype = C.c_char_p
+    L.ctsm_b200_set_tuning.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.ctsm_b200_set_tuning.restype = C.c_int
+    L.ctsm_b200_canopy_round_stats.argtypes = [vp, i32p, i32p, C.c_int]
+    L.ctsm_b200_canopy_round_stats.restype = C.c_int
     L.ctsm_b200_tridiagonal.argtypes = [vp, C.POINTER(Bounds), C.c_int, C.c_int, i32p, C.c_int, i32p,
                                         f64p, f64p, f64p, f64p, f64p, C.c_int]
     L.ctsm_b200_banddiagonal.argtypes = [vp, C.POINTER(Bounds), C.c_int, C.c_int, i32p, i32p, C.c_int, i32p,

@@ -2,7 +2,20 @@
 // declared in include/ctsm_b200.h.  No compute here.
 #include "common.cuh"
 
-static const char* kVersion = "ctsm_b200 0.1.0 (sm_100a, fp64, -fmad=false)";
+#include <stdlib.h>
+
+static const char* kVersion = "ctsm_b200 0.2.0 (sm_100a, fp64, -fmad=false)";
+
+static char g_last_cuda_error[256] = "";
+int cuda_fail(cudaError_t e, const char* file, int line) {
+  snprintf(g_last_cuda_error, sizeof g_last_cuda_error, "%s at %s:%d: %s", cudaGetErrorName(e), file, line, cudaGetErrorString(e));
+  fprintf(stderr, "ctsm_b200: CUDA error %s\n", g_last_cuda_error);
+  (void)cudaGetLastError();      // clear the sticky launch-error slot where that is possible
+  if (e == cudaErrorMemoryAllocation) return CTSM_ERR_NOMEM;
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) return CTSM_ERR_NO_DEVICE;
+  return CTSM_ERR_CUDA;
+}
+extern "C" const char* ctsm_b200_last_cuda_error(void) { return g_last_cuda_error; }
 
 extern "C" const char* ctsm_b200_version(void) { return kVersion; }
 
@@ -20,7 +33,7 @@ extern "C" void ctsm_b200_default_params(ctsm_params_t* p) {
   p->dtmin = 60.0; p->verySmall = 1.e-8; p->xTolerUpper = 1.e-1; p->xTolerLower = 1.e-2;
   p->e_ice = 6.0;
   p->snow_thermal_cond_method = 2;
-  p->snow_thermal_cond_glc_method = 1;
+  p->snow_thermal_cond_glc_method = 2;   // clm6_0: Sturm1997 as well (namelist_defaults_ctsm.xml:559)
   // canopyfluxes_inparm / clm6_0 switches: namelist_defaults_ctsm.xml:462,454,457,622,270,726,635,108,95,104,2182
   p->itmax_canopy_fluxes = 40;
   p->use_undercanopy_stability = 0;
@@ -75,12 +88,25 @@ extern "C" int ctsm_b200_init(const ctsm_params_t* p, ctsm_b200_ctx** out) {
   ctx->prm = *p;
   ctx->device = p->device;
   ctx->launches = 0;
-  CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaMalloc(&ctx->d_status, sizeof(DevStatus)));
-  CUDA_TRY(cudaMallocHost(&ctx->h_status, sizeof(DevStatus)));
-  DevStatus init; init.key = ~0ULL; init.n_warnings = 0; init.pad = 0;
-  CUDA_TRY(cudaMemcpyAsync(ctx->d_status, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = nullptr; ctx->d_status = nullptr; ctx->h_status = nullptr;
+  if (const char* e = getenv("CTSM_B200_TAIL_MAX")) ctx->tune.tail_max = atoi(e);
+  if (const char* e = getenv("CTSM_B200_NT_BUDGET")) ctx->tune.nt_budget = atoi(e);
+  if (const char* e = getenv("CTSM_B200_TAIL_LANES")) ctx->tune.tail_lanes = atoi(e);
+  const int rc = [&]() -> int {
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc(&ctx->d_status, sizeof(DevStatus)));
+    CUDA_TRY(cudaMallocHost(&ctx->h_status, sizeof(DevStatus)));
+    DevStatus init; init.key = ~0ULL; init.n_warnings = 0; init.pad = 0;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_status, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return CTSM_OK;
+  }();
+  if (rc != CTSM_OK) {           // nothing of a half-built context survives
+    ctsm_b200_finalize(ctx);
+    return rc;
+  }
   *out = ctx;
   return CTSM_OK;
 }
@@ -88,12 +114,44 @@ extern "C" int ctsm_b200_init(const ctsm_params_t* p, ctsm_b200_ctx** out) {
 extern "C" int ctsm_b200_finalize(ctsm_b200_ctx* ctx) {
   if (!ctx) return CTSM_ERR_BAD_ARG;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
   cudaFree(ctx->arena_fields.p); cudaFree(ctx->arena_filter0.p); cudaFree(ctx->arena_filter1.p);
   cudaFree(ctx->arena_scratch.p); cudaFree(ctx->arena_ints.p); cudaFree(ctx->d_patchmask);
-  cudaFree(ctx->d_status); cudaFreeHost(ctx->h_status);
-  cudaStreamDestroy(ctx->stream);
+  cudaFree(ctx->d_status);
+  if (ctx->h_status) cudaFreeHost(ctx->h_status);
+  if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  for (auto e : ctx->ev_round) cudaEventDestroy(e);
+  for (auto e : ctx->ev_tail) cudaEventDestroy(e);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+  return CTSM_OK;
+}
+
+extern "C" int ctsm_b200_set_tuning(ctsm_b200_ctx* ctx, int tail_max, int nt_budget, int tail_lanes) {
+  if (!ctx) return CTSM_ERR_BAD_ARG;
+  if (tail_max >= 0) ctx->tune.tail_max = tail_max;
+  if (nt_budget >= 0) ctx->tune.nt_budget = nt_budget;
+  if (tail_lanes >= 0) ctx->tune.tail_lanes = tail_lanes;
+  return CTSM_OK;
+}
+
+// events and the pinned count buffer of CanopyFluxes' rounds (grown on first use, itmax is a run-time parameter)
+int ensure_round_events(ctsm_b200_ctx* ctx, int n) {
+  while ((int)ctx->ev_round.size() < n) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    ctx->ev_round.push_back(a);
+    CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    ctx->ev_tail.push_back(b);
+  }
+  if (ctx->h_counts_cap < n) {
+    if (ctx->h_counts) { CUDA_TRY(cudaStreamSynchronize(ctx->stream)); CUDA_TRY(cudaFreeHost(ctx->h_counts)); ctx->h_counts = nullptr; }
+    CUDA_TRY(cudaMallocHost(&ctx->h_counts, sizeof(int) * (size_t)n));
+    ctx->h_counts_cap = n;
+  }
   return CTSM_OK;
 }
 
@@ -164,9 +222,8 @@ int finish_call(ctsm_b200_ctx* ctx, int mem, ctsm_status_t* st) {
   // a kernel that failed to launch (bad configuration, missing image) must never pass silently
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
-    fprintf(stderr, "ctsm_b200: launch error %s\n", cudaGetErrorString(e));
     if (st) memset(st, 0, sizeof *st);
-    return CTSM_ERR_NO_DEVICE;
+    return cuda_fail(e, __FILE__, __LINE__);
   }
   if (mem == CTSM_MEM_DEVICE) {
     if (st) memset(st, 0, sizeof *st);
@@ -175,9 +232,15 @@ int finish_call(ctsm_b200_ctx* ctx, int mem, ctsm_status_t* st) {
   return ctsm_b200_sync(ctx, st);
 }
 
-int arena_reserve(ctsm_b200_ctx::Arena& a, size_t bytes) {
+// Grow-only arenas.  Growing replaces the allocation, so work that may still read the old one is drained first
+// (steady state never grows: the sizes of a model run do not change after the first step).
+int arena_reserve(ctsm_b200_ctx* ctx, ctsm_b200_ctx::Arena& a, size_t bytes) {
   if (bytes <= a.cap) return CTSM_OK;
-  if (a.p) CUDA_TRY(cudaFree(a.p));
+  if (a.p) {
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->stream2) CUDA_TRY(cudaStreamSynchronize(ctx->stream2));
+    CUDA_TRY(cudaFree(a.p));
+  }
   a.p = nullptr; a.cap = 0;
   size_t want = bytes + bytes / 8 + 4096;
   CUDA_TRY(cudaMalloc(&a.p, want));
@@ -211,7 +274,7 @@ int stage_begin(ctsm_b200_ctx* ctx, std::vector<StageField>& fl, const ctsm_boun
     const size_t ld = (size_t)(sub_end(alloc, f.sub, ctx->prm.npft_table) - sub_beg(alloc, f.sub) + 1);
     total += align256((size_t)f.elem_size * ld * f.nlev);
   }
-  int rc = arena_reserve(ctx->arena_fields, total);
+  int rc = arena_reserve(ctx, ctx->arena_fields, total);
   if (rc) return rc;
   size_t off = 0;
   for (auto& f : fl) {
@@ -243,7 +306,7 @@ int stage_end(ctsm_b200_ctx* ctx, std::vector<StageField>& fl, const ctsm_bounds
 
 int stage_filter(ctsm_b200_ctx* ctx, ctsm_b200_ctx::Arena& a, const int32_t* host_filter, int numf,
                  const int32_t** dev_filter) {
-  int rc = arena_reserve(a, sizeof(int32_t) * (size_t)(numf > 0 ? numf : 1));
+  int rc = arena_reserve(ctx, a, sizeof(int32_t) * (size_t)(numf > 0 ? numf : 1));
   if (rc) return rc;
   if (numf > 0)
     CUDA_TRY(cudaMemcpyAsync(a.p, host_filter, sizeof(int32_t) * (size_t)numf, cudaMemcpyHostToDevice, ctx->stream));

@@ -349,7 +349,7 @@ extern "C" int ctsm_b200_balancecheck(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   g.begc = bounds->begc; g.endc = bounds->endc; g.begp = bounds->begp; g.endp = bounds->endp;
   g.begg = bounds->begg; g.endg = bounds->endg;
   const int nc = g.endc - g.begc + 1, ng = g.endg - g.begg + 1, np = g.endp - g.begp + 1;
-  int rc = arena_reserve(ctx->arena_ints, sizeof(Red) + 64);
+  int rc = arena_reserve(ctx, ctx->arena_ints, sizeof(Red) + 64);
   if (rc) return rc;
   Red* red = (Red*)ctx->arena_ints.p;
   Red init;

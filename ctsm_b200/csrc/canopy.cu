@@ -105,6 +105,11 @@ struct Lists {
   int* q_ci;            // [NQ_CI][cap]
   int* q_nt;            // [NQ_NT][cap]
   int* colflag;         // per column (alloc-based): owns an exposed-veg patch in this call
+  int* ejected;         // [cap] per filter position: 1 once the patch has left the bulk rounds for the tail kernel
+  int* tail_list;       // [cap] ejected patches in ejection order: fi | TAIL_B (entry point, see canopy_tail_kernel)
+  int* tail_count;      // entries in tail_list so far
+  int* tail_end;        // [npass + 2] tail_count at the end of every bulk round (canopy_tail_mark_kernel)
+  int* tail_head;       // [npass + 2] fetch head of every round's tail kernel
   int cap;
   __device__ __forceinline__ int* n_ci(int row, int i) const { return counts + (size_t)row * QROW + NBIN + i; }
   __device__ __forceinline__ int* n_nt(int row, int i) const { return counts + (size_t)row * QROW + NBIN + NQ_CI + i; }
@@ -138,6 +143,9 @@ struct alignas(128) PhsRec {
   __device__ __forceinline__ double S(int j) const { return Sv[j]; }
 };
 enum { RF_C3 = 1, RF_MEDLYN = 2, RF_NIGHT = 4, RF_SOLVE = 8, RF_FINAL = 16 };
+// tail_list entry: filter position, plus TAIL_B when the patch was ejected in the middle of a pass (by a calcstress task
+// that exceeded its iteration budget): its fric / leaf part of the pass is done and its PHS solve restarts from scratch.
+#define TAIL_B (1 << 30)
 
 // warp-aggregated append of `item` to bin `bin` of list (counts row `row`)
 __device__ __forceinline__ void bin_append(const Lists& L, int* list, int row, int bin, int item, unsigned group) {
@@ -565,23 +573,20 @@ __device__ __forceinline__ ListSlot list_slot(const Lists& L, int row, const int
   return sl;
 }
 
-#ifndef CLOSE_MINBLOCKS
-#define CLOSE_MINBLOCKS 4
-#endif
-__global__ void __launch_bounds__(STEP_THREADS, CLOSE_MINBLOCKS)
-canopy_close_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, int first, int last, const int32_t* __restrict__ filterp,
-                    double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in,
-                    int* __restrict__ list_out, DevStatus* ds) {
-  const int row = itlef0;
+template <bool ALL>
+__device__ __forceinline__ void phs_outputs(const CanopyDev& f, const CanopyPrm& prm, const Geo& g, const PhsRec& R, int pp,
+                                            DevStatus* ds);
+
+struct CloseOut { bool keep, solve, night; };
+// closes pass itlef0-1 of one patch (leaf energy balance :1174-1435, convergence test :1439-1457); `first`: nothing to
+// close yet.  Shared by the bulk kernel (one thread per list entry) and the tail kernel (one thread per patch, all passes).
+__device__ __forceinline__ CloseOut close_body(const CanopyDev& f, const CanopyPrm& prm, const Geo& g, const int itlef0,
+                                               const bool first, const int fi, const int32_t* __restrict__ filterp,
+                                               double* __restrict__ ws, const int wstride, DevStatus* ds) {
   const double dtime = prm.dtime;
-  int off[NBIN + 1];
-  const int total = list_offsets(L, row, off);
-  for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
-    const ListSlot sl = list_slot(L, row, off, list_in, base + threadIdx.x);
-    const int fi = sl.fi;
-    const bool live = sl.live;
-    bool keep = false, solve = false, night = false;
-    if (live) {
+  bool keep = false, solve = false, night = false;
+  {
+    {
       const int pp = filterp[fi] - g.begp0;
       const int cc = PF(column) - g.begc0;
       const double forc_pbot = CF(forc_pbot), forc_rho = CF(forc_rho), forc_q = CF(forc_q), t_grnd = CF(t_grnd);
@@ -732,15 +737,57 @@ canopy_close_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, int first, in
       }
       }
     }
+  }
+  CloseOut o; o.keep = keep; o.solve = solve; o.night = night;
+  return o;
+}
+
+#ifndef CLOSE_MINBLOCKS
+#define CLOSE_MINBLOCKS 4
+#endif
+// Bulk round `itlef0`: (phs_outputs of pass itlef0-1, then) close pass itlef0-1 for every listed patch and append the
+// survivors to the list of pass itlef0 - or, once the list of this round is short (<= tail_max entries), EJECT them to
+// the round's tail list, where canopy_tail_kernel runs each patch through all its remaining passes (no more bulk rounds).
+__global__ void __launch_bounds__(STEP_THREADS, CLOSE_MINBLOCKS)
+canopy_close_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, int first, int last, const int32_t* __restrict__ filterp,
+                    double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in,
+                    int* __restrict__ list_out, PhsRec* __restrict__ rec, int tail_max, DevStatus* ds) {
+  const int row = itlef0;
+  int off[NBIN + 1];
+  const int total = list_offsets(L, row, off);
+  const bool to_tail = !first && !last && L.counts[(size_t)row * QROW] <= tail_max;
+  for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+    const ListSlot sl = list_slot(L, row, off, list_in, base + threadIdx.x);
+    const int fi = sl.fi;
+    const bool live = sl.live && !(L.ejected[fi]);     // ejected mid-pass by a task kernel: the tail kernel owns it now
+    CloseOut c; c.keep = false; c.solve = false; c.night = false;
+    if (live) {
+      if (!first) phs_outputs<false>(f, prm, g, rec[fi], filterp[fi] - g.begp0, ds);   // what follows the PHS solve of pass itlef0-1
+      c = close_body(f, prm, g, itlef0, first != 0, fi, filterp, ws, wstride, ds);
+    }
+    const bool go = c.keep && !last;
+    const unsigned act = __activemask();
     // survivors -> list of pass itlef0; those that need a PHS solve also enter their first task queue: night patches the
     // calcstress queue 0 (their whole solve is one calcstress), day patches the ci queue 0
-    const bool go = keep && !last;
-    const unsigned act = __activemask();
-    const unsigned mk = __ballot_sync(act, go);
-    if (go) bin_append(L, list_out, row + 1, 0, fi, mk);
+    {
+      const bool gt = go && to_tail;
+      const unsigned mt = __ballot_sync(act, gt);
+      if (gt) {
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(mt) - 1;
+        int b0 = 0;
+        if (lane == leader) b0 = atomicAdd(L.tail_count, __popc(mt));
+        b0 = __shfl_sync(mt, b0, leader);
+        L.tail_list[b0 + __popc(mt & ((1u << lane) - 1))] = fi;       // entry A: fric/leaf of pass itlef0 first
+        L.ejected[fi] = 1;
+      }
+    }
+    const bool gb = go && !to_tail;
+    const unsigned mk = __ballot_sync(act, gb);
+    if (gb) bin_append(L, list_out, row + 1, 0, fi, mk);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      const bool gq = go && solve && (night == (q == 0));
+      const bool gq = gb && c.solve && (c.night == (q == 0));
       const unsigned mq = __ballot_sync(act, gq);
       if (gq) {
         const int lane = threadIdx.x & 31;
@@ -754,16 +801,10 @@ canopy_close_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, int first, in
   }
 }
 
-__global__ void __launch_bounds__(STEP_THREADS)
-canopy_fric_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, const int32_t* __restrict__ filterp,
-                   double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in) {
-  const int row = itlef0 + 1;
-  int off[NBIN + 1];
-  const int total = list_offsets(L, row, off);
-  for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
-    const ListSlot sl = list_slot(L, row, off, list_in, base + threadIdx.x);
-    if (!sl.live) continue;
-    const int fi = sl.fi;
+// opens pass itlef0 of one patch, first half: FrictionVelocity and the aerodynamic / leaf boundary-layer resistances
+__device__ __forceinline__ void fric_body(const CanopyDev& f, const CanopyPrm& prm, const Geo& g, const int itlef0, const int fi,
+                                          const int32_t* __restrict__ filterp, double* __restrict__ ws, const int wstride) {
+  {
     {
       const int pp = filterp[fi] - g.begp0;
       const int cc = PF(column) - g.begc0;
@@ -812,16 +853,24 @@ canopy_fric_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, const int32_t*
 }
 
 __global__ void __launch_bounds__(STEP_THREADS)
-canopy_leaf_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, const int32_t* __restrict__ filterp,
-                   double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in, PhsRec* __restrict__ rec,
-                   DevStatus* ds) {
+canopy_fric_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, const int32_t* __restrict__ filterp,
+                   double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in) {
   const int row = itlef0 + 1;
   int off[NBIN + 1];
   const int total = list_offsets(L, row, off);
   for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
     const ListSlot sl = list_slot(L, row, off, list_in, base + threadIdx.x);
     if (!sl.live) continue;
-    const int fi = sl.fi;
+    fric_body(f, prm, g, itlef0, sl.fi, filterp, ws, wstride);
+  }
+}
+
+// opens pass itlef0 of one patch, second half: temperature-dependent leaf biochemistry and the per-pass part of the
+// patch's PHS record
+__device__ __forceinline__ void leaf_body(const CanopyDev& f, const CanopyPrm& prm, const Geo& g, const int itlef0, const int fi,
+                                          const int32_t* __restrict__ filterp, double* __restrict__ ws, const int wstride,
+                                          PhsRec* __restrict__ rec, DevStatus* ds) {
+  {
     {
       {
       const int pp = filterp[fi] - g.begp0;
@@ -975,6 +1024,20 @@ canopy_leaf_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, const int32_t*
   }
 }
 
+__global__ void __launch_bounds__(STEP_THREADS)
+canopy_leaf_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, const int32_t* __restrict__ filterp,
+                   double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in, PhsRec* __restrict__ rec,
+                   DevStatus* ds) {
+  const int row = itlef0 + 1;
+  int off[NBIN + 1];
+  const int total = list_offsets(L, row, off);
+  for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+    const ListSlot sl = list_slot(L, row, off, list_in, base + threadIdx.x);
+    if (!sl.live) continue;
+    leaf_body(f, prm, g, itlef0, sl.fi, filterp, ws, wstride, rec, ds);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // PHS task kernels.  A lane carries one task (one calcstress solve / one outer pass of the ci solve) from a queue
 // and is REFILLED from the queue when its task ends, so the 32 lanes of a warp stay busy although the tasks need
@@ -1016,7 +1079,7 @@ __device__ __forceinline__ void queue_push(int* __restrict__ q, int* __restrict_
 // the task is the whole solve (:3492-3547) and leaves potentials, stress factors and transpiration in the record.
 __global__ void __launch_bounds__(TASK_THREADS, NT_MINBLOCKS)
 phs_newton_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const int* __restrict__ n_in, int* __restrict__ head,
-                  int* __restrict__ q_out, int* __restrict__ n_out) {
+                  int* __restrict__ q_out, int* __restrict__ n_out, Lists L, int budget) {
   extern __shared__ double shm[];                       // [2][NLEVSOI][TASK_THREADS]: k_soil_root, 1000 z
   double* sk = shm + threadIdx.x;
   double* sgv = shm + (size_t)NLEVSOI * TASK_THREADS + threadIdx.x;
@@ -1088,8 +1151,15 @@ phs_newton_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const 
       queue_push(q_out, n_out, pm, day, fi);
       continue;
     }
+    bool ej = false;
     if (st == LS_RUN) {
       if (!phs::newton_step(N, P)) st = LS_FIN;
+      else if (N.iter >= budget) { ej = true; st = LS_IDLE; }     // a straggler: hand the patch to the tail kernel
+    }
+    const unsigned em = __ballot_sync(FULL, ej);
+    if (em) {
+      queue_push(L.tail_list, L.tail_count, em, ej, fi | TAIL_B);
+      if (ej) L.ejected[fi] = 1;
     }
   }
 }
@@ -1116,7 +1186,7 @@ struct WeibullQuad {
 
 __global__ void __launch_bounds__(128)
 phs_newton_quad_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const int* __restrict__ n_in,
-                       int* __restrict__ q_out, int* __restrict__ n_out) {
+                       int* __restrict__ q_out, int* __restrict__ n_out, Lists L, int budget) {
   const int n = *n_in;
   if (n <= 0 || n > QUAD_MAX) return;                   // large queues: phs_newton_kernel
   const int lane = threadIdx.x & 31;
@@ -1142,8 +1212,15 @@ phs_newton_quad_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, c
     }
     phs::Newton N;
     const double xin[4] = {R.x[0], R.x[1], R.x[2], R.x[3]};
+    bool ej = false;
     if (phs::newton_begin(N, R, xin, gs0sun, gs0sha)) {
-      while (phs::newton_step(N, R, wb)) {}
+      while (phs::newton_step(N, R, wb)) {
+        if (N.iter >= budget) { ej = true; break; }             // quad-uniform: the four lanes carry the same solve
+      }
+    }
+    if (ej) {
+      if (wb.sgm == 0) { L.tail_list[atomicAdd(L.tail_count, 1)] = fi | TAIL_B; L.ejected[fi] = 1; }
+      continue;
     }
     double tran = 0.0;
     const phs::Stress so = phs::newton_finish(N, R, gs0sun, gs0sha, &tran);
@@ -1161,6 +1238,40 @@ phs_newton_quad_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, c
   }
 }
 
+// what a ci task reads of its patch, and how one outer pass of hybrid_PHS starts from / ends in the patch's record
+// (shared by the ci task kernel and the nested solve of the tail kernel)
+struct CiPatch { double gb_mol, forc_pbot; };
+__device__ __forceinline__ void ci_load(const PhsRec& R, phs::Leaf& L, CiPatch& P) {
+  P.gb_mol = R.gb_mol; P.forc_pbot = R.forc_pbot;
+  L.c3 = (R.flags & RF_C3) != 0; L.medlyn = (R.flags & RF_MEDLYN) != 0;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    L.vcmax[s] = R.vcmax[s]; L.tpu[s] = R.tpu[s]; L.kp[s] = R.kp[s]; L.lmr[s] = R.lmr[s]; L.je[s] = R.je[s]; L.par[s] = R.par[s];
+  }
+  L.cp = R.cp; L.kc = R.kc; L.ko = R.ko; L.qe = R.qe; L.theta_cj = R.theta_cj; L.theta_ip = R.theta_ip;
+  L.medint = R.medint; L.medslope = R.medslope; L.bbb = R.bbb; L.mbb = R.mbb; L.cair = R.cair; L.oair = R.oair;
+  L.rh_can = R.rh_can;
+}
+__device__ __forceinline__ void ci_begin_from_record(const PhsRec& R, phs::CiLane& C) {
+  phs::HybridCarry H;
+  H.x1sun = R.x1sun; H.x1sha = R.x1sha; H.bsun = R.bsun; H.bsha = R.bsha; H.b0sun = R.b0sun; H.b0sha = R.b0sha;
+  phs::ci_task_begin(C, H);
+}
+// bottom of the outer pass :4034-4046; returns true when hybrid_PHS is finished (only its epilogue is left)
+__device__ __forceinline__ bool ci_end_to_record(PhsRec& R, const phs::CiLane& C, bool bad, bool nb, DevStatus* ds) {
+  phs::HybridCarry H;
+  H.gs0sun = R.gs0sun; H.gs0sha = R.gs0sha; H.iter1 = R.iter1;
+  const bool lastpass = phs::ci_task_end(C, H);
+  R.x1sun = H.x1sun; R.x1sha = H.x1sha; R.gs0sun = H.gs0sun; R.gs0sha = H.gs0sha;
+  R.b0sun = C.bsun; R.b0sha = C.bsha; R.iter1 = H.iter1;
+  R.gs_sun = C.gs_sun; R.gs_sha = C.gs_sha;
+  R.o = C.o;
+  if (bad) report_failure(ds, R.patch, CTSM_ERR_QUADRATIC, 0);
+  if (nb) report_failure(ds, R.patch, CTSM_ERR_BRENT, 0);
+  if (lastpass) R.flags |= RF_FINAL;
+  return lastpass;
+}
+
 // ci tasks: one outer pass of hybrid_PHS (:3925-4046) per task, one ci_func evaluation per scheduler round.
 __global__ void __launch_bounds__(TASK_THREADS, CI_MINBLOCKS)
 phs_ci_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const int* __restrict__ n_in, int* __restrict__ head,
@@ -1171,7 +1282,7 @@ phs_ci_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const int*
   bool exhausted = (n <= 0);
   phs::CiLane C;
   phs::Leaf L;
-  struct { double gb_mol, forc_pbot; } P;               // all ci_func reads of the patch besides the leaf state
+  CiPatch P;                                            // all ci_func reads of the patch besides the leaf state
   bool bad = false, nb = false;
   for (;;) {
     const unsigned idle = __ballot_sync(FULL, st == LS_IDLE);
@@ -1186,18 +1297,8 @@ phs_ci_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const int*
           fi = q_in[my];
           const PhsRec& R = rec[fi];
           if (R.flags & RF_SOLVE) {                     // (nrad < 1: nothing to solve, :3477)
-            P.gb_mol = R.gb_mol; P.forc_pbot = R.forc_pbot;
-            L.c3 = (R.flags & RF_C3) != 0; L.medlyn = (R.flags & RF_MEDLYN) != 0;
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-              L.vcmax[s] = R.vcmax[s]; L.tpu[s] = R.tpu[s]; L.kp[s] = R.kp[s]; L.lmr[s] = R.lmr[s]; L.je[s] = R.je[s]; L.par[s] = R.par[s];
-            }
-            L.cp = R.cp; L.kc = R.kc; L.ko = R.ko; L.qe = R.qe; L.theta_cj = R.theta_cj; L.theta_ip = R.theta_ip;
-            L.medint = R.medint; L.medslope = R.medslope; L.bbb = R.bbb; L.mbb = R.mbb; L.cair = R.cair; L.oair = R.oair;
-            L.rh_can = R.rh_can;
-            phs::HybridCarry H;
-            H.x1sun = R.x1sun; H.x1sha = R.x1sha; H.bsun = R.bsun; H.bsha = R.bsha; H.b0sun = R.b0sun; H.b0sha = R.b0sha;
-            phs::ci_task_begin(C, H);
+            ci_load(R, L, P);
+            ci_begin_from_record(R, C);
             bad = false; nb = false;
             st = LS_RUN;
           }
@@ -1210,17 +1311,7 @@ phs_ci_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const int*
     if (st == LS_RUN) {
       PhsRec& R = rec[fi];
       if (!phs::ci_step(C, R.br, P, L, &bad, &nb)) {
-        // bottom of the outer pass :4034-4046
-        phs::HybridCarry H;
-        H.gs0sun = R.gs0sun; H.gs0sha = R.gs0sha; H.iter1 = R.iter1;
-        const bool lastpass = phs::ci_task_end(C, H);
-        R.x1sun = H.x1sun; R.x1sha = H.x1sha; R.gs0sun = H.gs0sun; R.gs0sha = H.gs0sha;
-        R.b0sun = C.bsun; R.b0sha = C.bsha; R.iter1 = H.iter1;
-        R.gs_sun = C.gs_sun; R.gs_sha = C.gs_sha;
-        R.o = C.o;
-        if (bad) report_failure(ds, R.patch, CTSM_ERR_QUADRATIC, 0);
-        if (nb) report_failure(ds, R.patch, CTSM_ERR_BRENT, 0);
-        if (lastpass) R.flags |= RF_FINAL;
+        (void)ci_end_to_record(R, C, bad, nb, ds);
         push = true;
         st = LS_IDLE;
       }
@@ -1336,16 +1427,123 @@ __device__ __forceinline__ void phs_outputs(const CanopyDev& f, const CanopyPrm&
   }
 }
 
-__global__ void __launch_bounds__(128)
-canopy_phs_end_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, int itlef0, const int32_t* __restrict__ filterp, Lists L,
-                      const int* __restrict__ list_in, PhsRec* __restrict__ rec, DevStatus* ds) {
-  const int row = itlef0 + 1;
-  int off[NBIN + 1];
-  const int total = list_offsets(L, row, off);
-  for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
-    const ListSlot sl = list_slot(L, row, off, list_in, base + threadIdx.x);
-    if (!sl.live) continue;
-    phs_outputs<false>(f, prm, g, rec[sl.fi], filterp[sl.fi] - g.begp0, ds);
+// ---------------------------------------------------------------------------------------------
+// Tail of the ITERATION loop.  A bulk round is a chain of ~15 grid-wide kernels, each as long as its slowest task, so
+// rounds that serve a few thousand patches (the late passes: 1 % of the patches need more than 20 of the 41 passes) and
+// tasks that run far longer than the rest (0.5 % of the calcstress solves hit the 50-iteration cap) would set the pace
+// of the whole call.  Such patches are EJECTED from the bulk rounds - all survivors once a round's list is short
+// (canopy_close_kernel), single patches whose calcstress exceeds its budget (task kernels) - and one thread per patch
+// runs each through all of its remaining passes with the nested loops of the reference, concurrently with the bulk
+// rounds on a second stream.  Same device functions, same arithmetic, same order as the bulk kernels: results do not
+// depend on where a patch was ejected (tests/test_gpu_canopy.py compares bulk-only, tail-only and mixed runs bit for bit).
+
+// the PHS record of a day patch as canopy_leaf_kernel left it (start of hybrid_PHS :3893-3915)
+__device__ __forceinline__ void phs_restart(PhsRec& R) {
+  int flags = R.flags & ~RF_FINAL;
+  R.flags = flags;
+  if ((flags & RF_SOLVE) && !(flags & RF_NIGHT)) {
+    phs::HybridCarry H;
+    phs::hybrid_carry_init(H, ((flags & RF_C3) ? 0.7 : 0.4) * R.cair);
+    R.x1sun = H.x1sun; R.x1sha = H.x1sha; R.gs0sun = H.gs0sun; R.gs0sha = H.gs0sha;
+    R.bsun = H.bsun; R.bsha = H.bsha; R.b0sun = H.b0sun; R.b0sha = H.b0sha;
+    R.iter1 = H.iter1;
+  }
+}
+
+// calcstress :4490-4710 for one patch, straight from its record
+__device__ __noinline__ void calcstress_record(PhsRec& R) {
+  phs::Newton N;
+  const double xin[4] = {R.x[0], R.x[1], R.x[2], R.x[3]};
+  const double gs0sun = R.gs0sun, gs0sha = R.gs0sha;
+  if (phs::newton_begin(N, R, xin, gs0sun, gs0sha)) {
+    while (phs::newton_step(N, R)) {}
+  }
+  double tran = 0.0;
+  const phs::Stress so = phs::newton_finish(N, R, gs0sun, gs0sha, &tran);
+  R.bsun = so.bsun; R.bsha = so.bsha;
+  if (R.flags & RF_NIGHT) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) R.xo[i] = N.x[i];
+    R.tran = tran;
+  }
+}
+
+// the PHS solve of one pass for one patch (PhotosynthesisMod.F90:3477-3585 -> hybrid_PHS :3815-4064): the sequence the
+// task kernels spread over ci(1) -> calcstress -> ci(2) -> ... -> epilogue, as nested loops
+__device__ __noinline__ void phs_solve_nested(PhsRec& R, DevStatus* ds) {
+  const int flags = R.flags;
+  if (!(flags & RF_SOLVE)) return;                       // nrad < 1
+  if (flags & RF_NIGHT) { calcstress_record(R); return; }
+  phs::Leaf L;
+  CiPatch P;
+  ci_load(R, L, P);
+  for (;;) {
+    phs::CiLane C;
+    bool bad = false, nb = false;
+    ci_begin_from_record(R, C);
+    while (phs::ci_step(C, R.br, P, L, &bad, &nb)) {}
+    if (ci_end_to_record(R, C, bad, nb, ds)) break;
+    calcstress_record(R);
+  }
+  double x[4];                                           // hybrid_PHS epilogue :4048-4062
+  double sf = phs::getvegwp(R, x, R.gs_sun, R.gs_sha);
+  if (sf < 0.0) sf = 0.0;
+  R.tran = sf;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) R.xo[i] = x[i];
+}
+
+__device__ __noinline__ void fric_call(const CanopyDev& f, const CanopyPrm& prm, const Geo& g, int itlef0, int fi,
+                                       const int32_t* filterp, double* ws, int wstride) {
+  fric_body(f, prm, g, itlef0, fi, filterp, ws, wstride);
+}
+__device__ __noinline__ void leaf_call(const CanopyDev& f, const CanopyPrm& prm, const Geo& g, int itlef0, int fi,
+                                       const int32_t* filterp, double* ws, int wstride, PhsRec* rec, DevStatus* ds) {
+  leaf_body(f, prm, g, itlef0, fi, filterp, ws, wstride, rec, ds);
+}
+__device__ __noinline__ bool close_call(const CanopyDev& f, const CanopyPrm& prm, const Geo& g, int itlef0, int fi,
+                                        const int32_t* filterp, double* ws, int wstride, PhsRec* rec, DevStatus* ds) {
+  phs_outputs<false>(f, prm, g, rec[fi], filterp[fi] - g.begp0, ds);
+  return close_body(f, prm, g, itlef0, false, fi, filterp, ws, wstride, ds).keep;
+}
+
+// one thread: where the tail list stands at the end of bulk round `round`
+__global__ void canopy_tail_mark_kernel(Lists L, int round) { L.tail_end[round] = *L.tail_count; }
+
+#define TAIL_THREADS 64
+__global__ void __launch_bounds__(TAIL_THREADS)
+canopy_tail_kernel(CanopyDev f, CanopyPrm prm, Geo g, int round, int npass, const int32_t* __restrict__ filterp, double* ws,
+                   int wstride, Lists L, PhsRec* rec, int lanes, DevStatus* ds) {
+  const int beg = round > 0 ? L.tail_end[round - 1] : 0;
+  const int n = L.tail_end[round] - beg;
+  if (n <= 0) return;
+  const int lane = threadIdx.x & 31;
+  // a warp carries `lanes` patches (<= 32): every patch takes its own path through the nest, so fewer patches per warp
+  // trade idle lanes for less serialisation
+  for (;;) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&L.tail_head[round], lanes);
+    base = __shfl_sync(FULL, base, 0);
+    if (base >= n) break;
+    const int t = base + lane;
+    if (lane < lanes && t < n) {
+      const int e = L.tail_list[beg + t];
+      const int fi = e & ~TAIL_B;
+      int k = round;
+      bool open = !(e & TAIL_B);
+      if (!open) phs_restart(rec[fi]);
+      for (;;) {
+        if (open) {
+          fric_call(f, prm, g, k, fi, filterp, ws, wstride);
+          leaf_call(f, prm, g, k, fi, filterp, ws, wstride, rec, ds);
+        }
+        open = true;
+        phs_solve_nested(rec[fi], ds);
+        ++k;
+        if (!close_call(f, prm, g, k, fi, filterp, ws, wstride, rec, ds) || k == npass) break;
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -1527,7 +1725,7 @@ split_scatter_kernel(int n, const int32_t* __restrict__ filt, const int32_t* __r
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-static int reserve_ints(ctsm_b200_ctx::Arena& a, size_t n) { return arena_reserve(a, sizeof(int) * (n > 0 ? n : 1)); }
+static int reserve_ints(ctsm_b200_ctx* ctx, ctsm_b200_ctx::Arena& a, size_t n) { return arena_reserve(ctx, a, sizeof(int) * (n > 0 ? n : 1)); }
 
 extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_exposedvegp,
                                       const int32_t* filter_exposedvegp, const ctsm_canopyfluxes_fields_t* hf, int mem,
@@ -1576,15 +1774,20 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   if (npb <= 0) return finish_call(ctx, mem, st);
 
   // workspace: [W_NSLOT][wstride] doubles, the PHS records [fn], and int scratch {colflag[ldc],
-  // list_a/list_b[fn], ci queues 0..3 [fn], calcstress queues 0..3 [fn], counters}
+  // list_a/list_b[fn], ci queues 0..3 [fn], calcstress queues 0..3 [fn], ejected[fn], tail_list[fn], counters}
   const int wstride = (fn + 31) & ~31;
   const int npass = p.itmax_canopy_fluxes + 1;
+  {
+    const int rce = ensure_round_events(ctx, npass + 2);
+    if (rce) return rce;
+  }
   const size_t n_counts = (size_t)QROW * (size_t)(npass + 2);
+  const size_t n_tailc = 2 * (size_t)(npass + 2) + 2;        // tail_end[], tail_head[], tail_count
   const size_t ws_bytes = (sizeof(double) * (size_t)W_NSLOT * (size_t)(wstride > 0 ? wstride : 32) + 127) & ~(size_t)127;
-  int rc = arena_reserve(ctx->arena_scratch, ws_bytes + sizeof(PhsRec) * (size_t)(fn > 0 ? fn : 1));
+  int rc = arena_reserve(ctx, ctx->arena_scratch, ws_bytes + sizeof(PhsRec) * (size_t)(fn > 0 ? fn : 1));
   if (rc) return rc;
-  const size_t nq = (size_t)(2 * NBIN + NQ_CI + NQ_NT);
-  rc = reserve_ints(ctx->arena_ints, (size_t)g.ldc + nq * (size_t)fn + n_counts + 64);
+  const size_t nq = (size_t)(2 * NBIN + NQ_CI + NQ_NT + 2);
+  rc = reserve_ints(ctx, ctx->arena_ints, (size_t)g.ldc + nq * (size_t)fn + n_counts + n_tailc + 64);
   if (rc) return rc;
   double* ws = (double*)ctx->arena_scratch.p;
   PhsRec* rec = (PhsRec*)((char*)ctx->arena_scratch.p + ws_bytes);
@@ -1595,11 +1798,17 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   L.list_b = ip; ip += (size_t)NBIN * fn;
   L.q_ci = ip; ip += (size_t)NQ_CI * fn;
   L.q_nt = ip; ip += (size_t)NQ_NT * fn;
-  L.counts = ip;
+  L.tail_list = ip; ip += fn;
+  L.ejected = ip; ip += fn;                                  // zeroed together with the counters that follow it
+  L.counts = ip; ip += n_counts;
+  L.tail_end = ip; ip += npass + 2;
+  L.tail_head = ip; ip += npass + 2;
+  L.tail_count = ip; ip += 2;
   L.cap = fn;
+  ctx->dbg_counts = L.counts; ctx->dbg_tail_end = L.tail_end; ctx->dbg_npass = npass;
   cudaStream_t s = ctx->stream;
   CUDA_TRY(cudaMemsetAsync(L.colflag, 0, sizeof(int) * (size_t)g.ldc, s));
-  CUDA_TRY(cudaMemsetAsync(L.counts, 0, sizeof(int) * n_counts, s));
+  CUDA_TRY(cudaMemsetAsync(L.ejected, 0, sizeof(int) * ((size_t)fn + n_counts + n_tailc), s));
   if (fn > 0) {
     canopy_mark_kernel<<<grid_for(fn, 256), 256, 0, s>>>(d, g, fn, dfilter, L.colflag);
     canopy_colprep_kernel<<<grid_for(ncb, 128), 128, 0, s>>>(d, g, L.colflag);
@@ -1611,15 +1820,17 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
     canopy_init_kernel<<<grid_for(fn, 128), 128, 0, s>>>(d, cp, g, fn, dfilter, ws, wstride, L, rec, ctx->d_status);
     ctx->launches++;
     const size_t shbytes = sizeof(double) * 2 * NLEVSOI * TASK_THREADS;
-    int sms = 148, occ_n = 1, occ_c = 1, occ_s = 1;
+    int sms = 148, occ_n = 1, occ_c = 1, occ_s = 1, occ_t = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     CUDA_TRY(cudaFuncSetAttribute(phs_newton_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shbytes));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_n, phs_newton_kernel, TASK_THREADS, shbytes);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, phs_ci_kernel, TASK_THREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, canopy_close_kernel, STEP_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, canopy_tail_kernel, TAIL_THREADS, 0);
     if (occ_n < 1) occ_n = 1;
     if (occ_c < 1) occ_c = 1;
     if (occ_s < 1) occ_s = 1;
+    if (occ_t < 1) occ_t = 1;
     // persistent grids: whole waves of resident blocks on the 148 SMs
     const int need_t = grid_for(fn, TASK_THREADS);
     const int grid_n = need_t < sms * occ_n ? need_t : sms * occ_n;
@@ -1628,15 +1839,34 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
     const int grid_q = need_q < sms * 4 ? need_q : sms * 4;
     int grid_s = grid_for(fn + 32 * NBIN, STEP_THREADS);
     if (grid_s > sms * occ_s * 2) grid_s = sms * occ_s * 2;
+    // tail policy (ctsm_b200_set_tuning / CTSM_B200_TAIL_MAX, _NT_BUDGET, _TAIL_LANES): see canopy_tail_kernel
+    const int tail_max = ctx->tune.tail_max, nt_budget = ctx->tune.nt_budget > 0 ? ctx->tune.nt_budget : (1 << 30);
+    const int tail_lanes = ctx->tune.tail_lanes < 1 ? 1 : ctx->tune.tail_lanes > 32 ? 32 : ctx->tune.tail_lanes;
+    const bool use_tail = tail_max > 0 || ctx->tune.nt_budget > 0;
+    const int tail_cap = fn < tail_max + (fn >> 6) + 1024 ? fn : tail_max + (fn >> 6) + 1024;   // what one round is expected to eject
+    const int need_tail = grid_for(tail_cap, (TAIL_THREADS / 32) * tail_lanes);
+    const int grid_tail = need_tail < sms * occ_t ? need_tail : sms * occ_t;
+    cudaStream_t s2 = ctx->stream2;
     int *lin = L.list_a, *lout = L.list_b;
     const size_t cap = (size_t)fn;
     // close(0, first) only builds the list of pass 0; fric/leaf(k) open pass k; the task kernels solve its PHS system;
-    // close(k+1) closes pass k; close(npass, last) only closes
+    // close(k+1) closes pass k; close(npass, last) only closes.  The host stops issuing rounds once it has seen (two
+    // rounds late, through a pinned copy) that a round's list was empty.
+    int rounds = 0;
     for (int itlef = 0; itlef <= npass; ++itlef) {
+      if (itlef >= 2) {
+        // the host stays at most two rounds ahead of the device, so that it can stop when the lists have run empty
+        CUDA_TRY(cudaEventSynchronize(ctx->ev_round[itlef - 2]));
+        if (ctx->h_counts[itlef - 2] == 0) break;
+      }
       canopy_close_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, itlef == 0, itlef == npass, dfilter, ws, wstride,
-                                                          L, lin, lout, ctx->d_status);
+                                                          L, lin, lout, rec, tail_max, ctx->d_status);
       ctx->launches++;
+      rounds = itlef + 1;
       if (itlef < npass) {
+        // the list this round works on: copy its length to the host for the early exit above
+        CUDA_TRY(cudaMemcpyAsync(&ctx->h_counts[itlef], L.counts + (size_t)(itlef + 1) * QROW, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaEventRecord(ctx->ev_round[itlef], s));
         canopy_fric_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, dfilter, ws, wstride, L, lout);
         canopy_leaf_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, dfilter, ws, wstride, L, lout, rec, ctx->d_status);
         ctx->launches += 2;
@@ -1655,14 +1885,26 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
           const bool lastq = (i + 1 == NQ_CI);
           int* qo = L.q_ci + (size_t)(lastq ? 0 : i + 1) * cap;
           int* no = lastq ? spare : n_ci + i + 1;
-          phs_newton_kernel<<<grid_n, TASK_THREADS, shbytes, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, h_nt + i, qo, no);
-          phs_newton_quad_kernel<<<grid_q, 128, 0, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, qo, no);
+          phs_newton_kernel<<<grid_n, TASK_THREADS, shbytes, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, h_nt + i, qo, no, L, nt_budget);
+          phs_newton_quad_kernel<<<grid_q, 128, 0, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, qo, no, L, nt_budget);
           ctx->launches += 3;
         }
-        canopy_phs_end_kernel<<<grid_s, 128, 0, s>>>(d, cp, g, fn, itlef, dfilter, L, lout, rec, ctx->d_status);
-        ctx->launches++;
+        if (use_tail) {
+          // everything ejected during this round (survivors of a short list, calcstress stragglers) runs to completion
+          // on the second stream while the next bulk rounds proceed
+          canopy_tail_mark_kernel<<<1, 1, 0, s>>>(L, itlef);
+          CUDA_TRY(cudaEventRecord(ctx->ev_tail[itlef], s));
+          CUDA_TRY(cudaStreamWaitEvent(s2, ctx->ev_tail[itlef], 0));
+          canopy_tail_kernel<<<grid_tail, TAIL_THREADS, 0, s2>>>(d, cp, g, itlef, npass, dfilter, ws, wstride, L, rec, tail_lanes,
+                                                                ctx->d_status);
+          ctx->launches += 2;
+        }
       }
       int* t = lin; lin = lout; lout = t;
+    }
+    if (use_tail && rounds > 0) {
+      CUDA_TRY(cudaEventRecord(ctx->ev_join, s2));
+      CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_join, 0));
     }
     canopy_final_kernel<<<grid_for(fn, 128), 128, 0, s>>>(d, cp, g, fn, dfilter, ws, wstride, rec, ctx->d_status);
     ctx->launches++;
@@ -1672,6 +1914,20 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
     if (rc) return rc;
   }
   return finish_call(ctx, mem, st);
+}
+
+// list length and cumulative tail entries of every round of the last CanopyFluxes call (diagnostic; synchronises)
+extern "C" int ctsm_b200_canopy_round_stats(ctsm_b200_ctx* ctx, int32_t* list_len, int32_t* tail_end, int cap) {
+  if (!ctx || !list_len || !tail_end) return -1;
+  if (!ctx->dbg_counts) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  const int n = ctx->dbg_npass + 1 < cap ? ctx->dbg_npass + 1 : cap;
+  std::vector<int> c((size_t)QROW * (size_t)(n + 1)), t((size_t)n);
+  cudaMemcpy(c.data(), ctx->dbg_counts, sizeof(int) * c.size(), cudaMemcpyDeviceToHost);
+  cudaMemcpy(t.data(), ctx->dbg_tail_end, sizeof(int) * t.size(), cudaMemcpyDeviceToHost);
+  for (int r = 0; r < n; ++r) { list_len[r] = c[(size_t)(r + 1) * QROW]; tail_end[r] = t[r]; }
+  return n;
 }
 
 extern "C" int ctsm_b200_set_exposedvegp_filter(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_nolakeurbanp,
@@ -1690,7 +1946,7 @@ extern "C" int ctsm_b200_set_exposedvegp_filter(ctsm_b200_ctx* ctx, const ctsm_b
   const int nblocks = grid_for(n, SPLIT_BLOCK * SPLIT_ITEMS);
   const int32_t *dfilt = filter_nolakeurbanp, *dfv = frac_veg_nosno;
   int32_t *dyes = filter_exposedvegp, *dno = filter_noexposedvegp;
-  int rc = reserve_ints(ctx->arena_ints, (size_t)nblocks + 8 + (mem != CTSM_MEM_DEVICE ? 3 * (size_t)n + (size_t)np : 0));
+  int rc = reserve_ints(ctx, ctx->arena_ints, (size_t)nblocks + 8 + (mem != CTSM_MEM_DEVICE ? 3 * (size_t)n + (size_t)np : 0));
   if (rc) return rc;
   int* ip = (int*)ctx->arena_ints.p;
   int* blockc = ip; ip += nblocks;

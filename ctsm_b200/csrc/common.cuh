@@ -66,16 +66,22 @@ struct ctsm_b200_ctx {
   struct Arena { void* p = nullptr; size_t cap = 0; };
   Arena arena_fields, arena_filter0, arena_filter1, arena_scratch, arena_ints;
   int32_t* d_patchmask = nullptr; size_t patchmask_cap = 0;
+  // CanopyFluxes: second stream for the tail kernel, per-round events, pinned survivor counts (canopy.cu)
+  cudaStream_t stream2 = nullptr;
+  std::vector<cudaEvent_t> ev_round, ev_tail;
+  cudaEvent_t ev_join = nullptr;
+  int* h_counts = nullptr; int h_counts_cap = 0;
+  struct Tuning { int tail_max = 0, nt_budget = 0, tail_lanes = 1; } tune;
+  int* dbg_counts = nullptr; int* dbg_tail_end = nullptr; int dbg_npass = 0;
 };
+
+// records "name at file:line: text" for ctsm_b200_last_cuda_error() and maps the error to a CTSM_ERR_* code
+int cuda_fail(cudaError_t e, const char* file, int line);
 
 #define CUDA_TRY(expr)                                                                       \
   do {                                                                                       \
     cudaError_t _e = (expr);                                                                 \
-    if (_e != cudaSuccess) {                                                                 \
-      fprintf(stderr, "ctsm_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__, __LINE__, \
-              cudaGetErrorString(_e));                                                       \
-      return CTSM_ERR_NO_DEVICE;                                                             \
-    }                                                                                        \
+    if (_e != cudaSuccess) return cuda_fail(_e, __FILE__, __LINE__);                        \
   } while (0)
 
 // --- staging of field tables (abi.cu) -----------------------------------------
@@ -106,7 +112,8 @@ struct StageField {
   int intent;
 };
 
-int arena_reserve(ctsm_b200_ctx::Arena& a, size_t bytes);
+int arena_reserve(ctsm_b200_ctx* ctx, ctsm_b200_ctx::Arena& a, size_t bytes);
+int ensure_round_events(ctsm_b200_ctx* ctx, int n);
 int stage_begin(ctsm_b200_ctx* ctx, std::vector<StageField>& fl, const ctsm_bounds_t& alloc, const ctsm_bounds_t& call,
                 bool preserve_out);
 int stage_end(ctsm_b200_ctx* ctx, std::vector<StageField>& fl, const ctsm_bounds_t& alloc, const ctsm_bounds_t& call);

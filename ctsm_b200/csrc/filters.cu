@@ -156,7 +156,7 @@ extern "C" int ctsm_b200_set_filters(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bo
   // device scratch: mask[nmax], blockc[nblk_max], totals[CTSM_FLT_COUNT]; HOST mode adds input mirrors and one output list
   size_t ints = (size_t)nmax + (size_t)nblk_max + CTSM_FLT_COUNT + 64;
   if (mem != CTSM_MEM_DEVICE) ints += 4 * (size_t)ncol_a + 4 * (size_t)nlun_a + 3 * (size_t)npat_a + (size_t)ngrc_a + (size_t)nmax;
-  int rc = arena_reserve(ctx->arena_ints, sizeof(int32_t) * ints);
+  int rc = arena_reserve(ctx, ctx->arena_ints, sizeof(int32_t) * ints);
   if (rc) return rc;
   int32_t* ip = (int32_t*)ctx->arena_ints.p;
   uint32_t* mask = (uint32_t*)ip; ip += nmax;

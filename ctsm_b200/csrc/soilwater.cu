@@ -226,7 +226,7 @@ extern "C" int ctsm_b200_soilwater(ctsm_b200_ctx* ctx, const ctsm_bounds_t* boun
                  ctx->prm.e_ice, ctx->prm.lower_boundary_condition, ctx->prm.flux_calculation};
   if (p.flux_calculation != 1) return CTSM_ERR_BAD_ARG;
   if (num_hydrologyc > 0) {
-    int rc = arena_reserve(ctx->arena_ints, sizeof(int32_t) * ((size_t)num_hydrologyc + 64));
+    int rc = arena_reserve(ctx, ctx->arena_ints, sizeof(int32_t) * ((size_t)num_hydrologyc + 64));
     if (rc) return rc;
     int* nretry = (int*)ctx->arena_ints.p;
     int32_t* retry = (int32_t*)ctx->arena_ints.p + 64;

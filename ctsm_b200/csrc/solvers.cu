@@ -127,7 +127,7 @@ extern "C" int ctsm_b200_tridiagonal(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bo
   const double *da = a, *db = b, *dc = c, *dr = r;
   double* du = u;
   if (mem != CTSM_MEM_DEVICE) {
-    int rc = arena_reserve(ctx->arena_fields, 5 * (nb + 256) + sizeof(int32_t) * (size_t)ld + 256);
+    int rc = arena_reserve(ctx, ctx->arena_fields, 5 * (nb + 256) + sizeof(int32_t) * (size_t)ld + 256);
     if (rc) return rc;
     HostStage hs{ctx};
     da = (double*)hs.in(a, nb, true); db = (double*)hs.in(b, nb, true); dc = (double*)hs.in(c, nb, true);
@@ -160,7 +160,7 @@ extern "C" int ctsm_b200_banddiagonal(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   const double *db = b, *dr = r;
   double* du = u;
   if (mem != CTSM_MEM_DEVICE) {
-    int rc = arena_reserve(ctx->arena_fields, 7 * (nb + 256) + 2 * (sizeof(int32_t) * (size_t)ld + 256));
+    int rc = arena_reserve(ctx, ctx->arena_fields, 7 * (nb + 256) + 2 * (sizeof(int32_t) * (size_t)ld + 256));
     if (rc) return rc;
     HostStage hs{ctx};
     db = (double*)hs.in(b, 5 * nb, true); dr = (double*)hs.in(r, nb, true); du = (double*)hs.in(u, nb, true);
@@ -192,7 +192,7 @@ extern "C" int ctsm_b200_dgtsv_batch(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bo
   const double *da = amx, *db = bmx, *dc = cmx, *dr = rmx;
   double* dx = x;
   if (mem != CTSM_MEM_DEVICE) {
-    int rc = arena_reserve(ctx->arena_fields, 5 * (nb + 256) + sizeof(int32_t) * (size_t)ld + 256);
+    int rc = arena_reserve(ctx, ctx->arena_fields, 5 * (nb + 256) + sizeof(int32_t) * (size_t)ld + 256);
     if (rc) return rc;
     HostStage hs{ctx};
     da = (double*)hs.in(amx, nb, true); db = (double*)hs.in(bmx, nb, true); dc = (double*)hs.in(cmx, nb, true);

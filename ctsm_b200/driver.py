@@ -39,7 +39,13 @@ class Context:
         self.h = C.c_void_p()
         rc = self.L.ctsm_b200_init(C.byref(self.prm), C.byref(self.h))
         if rc != 0:
-            raise RuntimeError("ctsm_b200_init failed (rc=%d): no usable CUDA device; there is no CPU fallback" % rc)
+            why = {1: "no usable CUDA device; there is no CPU fallback", 2: "bad argument / unsupported configuration",
+                   3: "device memory allocation failed", 4: "CUDA runtime error"}.get(rc, "error")
+            raise RuntimeError("ctsm_b200_init failed (rc=%d): %s %s" % (rc, why, self.L.ctsm_b200_last_cuda_error().decode()))
+
+    def set_tuning(self, tail_max: int = -1, nt_budget: int = -1, tail_lanes: int = -1):
+        """Scheduling knobs of CanopyFluxes' ITERATION loop (include/ctsm_b200.h); results do not depend on them."""
+        self.L.ctsm_b200_set_tuning(self.h, tail_max, nt_budget, tail_lanes)
 
     def close(self):
         if self.h:

@@ -78,8 +78,10 @@ enum { CTSM_MEM_DEVICE = 0, CTSM_MEM_HOST = 1,
 
 enum {
   CTSM_OK = 0,
-  CTSM_ERR_NO_DEVICE = 1,       /* no usable CUDA device / CUDA runtime error   */
+  CTSM_ERR_NO_DEVICE = 1,       /* no usable CUDA device (there is no CPU fallback) */
   CTSM_ERR_BAD_ARG = 2,         /* NULL pointer, bad bounds, unsupported config  */
+  CTSM_ERR_NOMEM = 3,           /* device / pinned-host allocation failed (cudaErrorMemoryAllocation) */
+  CTSM_ERR_CUDA = 4,            /* any other CUDA runtime error; ctsm_b200_last_cuda_error() names it */
   CTSM_ERR_DGBSV = 10,          /* BandDiagonalMod.F90:200-213  "BandDiagonal ERROR: dgbsv returned error code" */
   CTSM_ERR_DGTSV = 11,          /* SoilWaterMovementMod.F90:1295 "soilwater_moisture_form:: problem with the lapack solver" */
   CTSM_ERR_FORC_HGT = 12,       /* CanopyFluxesMod.F90:997-1002  forcing height below canopy height */
@@ -261,6 +263,22 @@ int  ctsm_b200_sync(ctsm_b200_ctx* ctx, ctsm_status_t* st);
 void* ctsm_b200_stream(ctsm_b200_ctx* ctx);
 /* number of kernel launches issued by this context so far */
 int64_t ctsm_b200_launch_count(const ctsm_b200_ctx* ctx);
+/* "cudaErrorName at file:line: text" of the last CUDA runtime error this process's library calls met ("" if none) */
+const char* ctsm_b200_last_cuda_error(void);
+/* Scheduling knobs of CanopyFluxes' ITERATION loop (results do not depend on them; defaults come from the environment
+ * variables CTSM_B200_TAIL_MAX / CTSM_B200_NT_BUDGET / CTSM_B200_TAIL_LANES, else 0 / 0 / 1 = tail kernel off: on B200 the
+ * per-patch nested-loop kernel is instruction-fetch bound and only pays for calls of a few patches):
+ *   tail_max    once a pass has at most this many unconverged patches they all leave the list-driven bulk rounds and
+ *               one thread per patch runs each through its remaining passes (0: never);
+ *   nt_budget   a calcstress solve (PhotosynthesisMod.F90:4579) still running after this many Newton iterations sends
+ *               its patch to the same tail kernel (0: never);
+ *   tail_lanes  patches carried by one warp of the tail kernel (1..32).
+ * A negative argument keeps the current value. */
+int  ctsm_b200_set_tuning(ctsm_b200_ctx* ctx, int tail_max, int nt_budget, int tail_lanes);
+/* Diagnostic of the last ctsm_b200_canopyfluxes call (synchronises the stream): for every ITERATION round r < cap,
+ * list_len[r] = patches the round's list kernels served, tail_end[r] = patches handed to the tail kernel up to and
+ * including round r.  Returns the number of rounds written. */
+int  ctsm_b200_canopy_round_stats(ctsm_b200_ctx* ctx, int32_t* list_len, int32_t* tail_end, int cap);
 /* page-lock a host array so that CTSM_MEM_HOST staging runs at full PCIe rate */
 int  ctsm_b200_host_register(void* ptr, uint64_t bytes);
 int  ctsm_b200_host_unregister(void* ptr);

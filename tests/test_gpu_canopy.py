@@ -155,6 +155,46 @@ def test_canopyfluxes_is_bit_reproducible(gpu_ctx):
             assert np.array_equal(a[fs.name], b[fs.name], equal_nan=True), fs.name
 
 
+def _with_tuning(L, ctx, tail_max, nt_budget, tail_lanes):
+    assert L.ctsm_b200_set_tuning(ctx, tail_max, nt_budget, tail_lanes) == 0
+
+
+@pytest.mark.parametrize("mode", ["tail_after_round_8", "tail_from_round_1", "eject_every_newton", "lanes_32"])
+def test_canopyfluxes_schedules_agree_bit_for_bit(gpu_ctx, mode):
+    """Where a patch leaves the list-driven bulk rounds for the per-patch tail kernel is a scheduling decision
+    (ctsm_b200_set_tuning): bulk only, everything in the tail from pass 1 on, every calcstress solve longer than two
+    iterations ejected mid-pass, 32 patches per tail warp - all give the results of the default schedule bit for bit."""
+    L, ctx, prm = gpu_ctx
+    sg, S = synthetic_canopy.make_full_case(6000, seed=31)
+    a, b = copy_state(S), copy_state(S)
+    _with_tuning(L, ctx, 0, 0, 1)                      # the default: list-driven rounds only
+    assert run_gpu(L, ctx, sg, a, abi.MEM_DEVICE)[0] == 0
+    try:
+        _with_tuning(L, ctx, *{"tail_after_round_8": (32768, 16, 16), "tail_from_round_1": (1 << 30, 16, 8),
+                               "eject_every_newton": (4096, 2, 16), "lanes_32": (32768, 16, 32)}[mode])
+        assert run_gpu(L, ctx, sg, b, abi.MEM_DEVICE)[0] == 0
+    finally:
+        _with_tuning(L, ctx, 0, 0, 1)
+    for fs in abi.FIELDS["canopyfluxes"]:
+        if fs.intent != "IN":
+            assert np.array_equal(a[fs.name], b[fs.name], equal_nan=True), fs.name
+
+
+def test_canopyfluxes_tail_kernel_matches_oracle(gpu_ctx, oracle_lib):
+    """Every patch through the per-patch tail kernel from pass 1 on (the nested-loop formulation), against the oracle."""
+    L, ctx, prm = gpu_ctx
+    sg, S = synthetic_canopy.make_full_case(2000, seed=41)
+    ref, got = copy_state(S), copy_state(S)
+    rc_ref, _ = run_oracle(oracle_lib, prm, sg, ref)
+    _with_tuning(L, ctx, 1 << 30, 8, 4)
+    try:
+        rc, st = run_gpu(L, ctx, sg, got, abi.MEM_DEVICE)
+    finally:
+        _with_tuning(L, ctx, 0, 0, 1)
+    assert rc == rc_ref == 0, st.msg
+    compare(sg, got, ref, S)
+
+
 @pytest.mark.parametrize("variant", ["zengwang_bb_noluna", "night_only", "day_only", "no_biomass_beta"])
 def test_canopyfluxes_option_branches(oracle_lib, variant):
     """Namelist branches other than the clm6_0 defaults: ZengWang2007 z0, Ball-Berry, LUNA off,
