@@ -262,6 +262,8 @@ def lib():
     L.ctsm_b200_sync.argtypes = [vp, C.POINTER(Status)]
     L.ctsm_b200_stream.argtypes = [vp]
     L.ctsm_b200_stream.restype = vp
+    L.ctsm_b200_stream_of.argtypes = [vp, C.c_int]
+    L.ctsm_b200_stream_of.restype = vp
     L.ctsm_b200_launch_count.argtypes = [vp]
     L.ctsm_b200_launch_count.restype = C.c_int64
     L.ctsm_b200_host_register.argtypes = [vp, C.c_uint64]
@@ -270,6 +272,14 @@ def lib():
     L.ctsm_b200_last_cuda_error.restype = C.c_char_p
     L.ctsm_b200_set_tuning.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.ctsm_b200_set_tuning.restype = C.c_int
+    L.ctsm_b200_host_window_begin.argtypes = [vp]
+    L.ctsm_b200_host_window_begin.restype = C.c_int
+    L.ctsm_b200_host_window_end.argtypes = [vp, C.POINTER(Status)]
+    L.ctsm_b200_host_window_end.restype = C.c_int
+    L.ctsm_b200_host_window_bytes.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.ctsm_b200_host_window_bytes.restype = C.c_int
+    L.ctsm_b200_host_invalidate.argtypes = [vp, vp]
+    L.ctsm_b200_host_invalidate.restype = C.c_int
     L.ctsm_b200_canopy_round_stats.argtypes = [vp, i32p, i32p, C.c_int]
     L.ctsm_b200_canopy_round_stats.restype = C.c_int
     L.ctsm_b200_tridiagonal.argtypes = [vp, C.POINTER(Bounds), C.c_int, C.c_int, i32p, C.c_int, i32p,

@@ -121,6 +121,13 @@ extern "C" int ctsm_b200_finalize(ctsm_b200_ctx* ctx) {
   cudaFree(ctx->d_status);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  if (ctx->s_h2d) { cudaStreamSynchronize(ctx->s_h2d); cudaStreamDestroy(ctx->s_h2d); }
+  if (ctx->s_d2h) { cudaStreamSynchronize(ctx->s_d2h); cudaStreamDestroy(ctx->s_d2h); }
+  for (auto& kv : ctx->mirrors) cudaFree(kv.second.d);
+  for (auto& c : ctx->win_chunks) cudaFree(c.p);
+  for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+  for (auto q : ctx->bal_pinned) cudaFreeHost(q);
+  for (auto q : ctx->bal_dev) cudaFree(q);
   for (auto e : ctx->ev_round) cudaEventDestroy(e);
   for (auto e : ctx->ev_tail) cudaEventDestroy(e);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -156,6 +163,16 @@ int ensure_round_events(ctsm_b200_ctx* ctx, int n) {
 }
 
 extern "C" void* ctsm_b200_stream(ctsm_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" void* ctsm_b200_stream_of(ctsm_b200_ctx* ctx, int kind) {
+  if (!ctx) return nullptr;
+  switch (kind) {
+    case 0: return (void*)ctx->stream;
+    case 1: return (void*)ctx->stream2;
+    case 2: return (void*)ctx->s_h2d;
+    case 3: return (void*)ctx->s_d2h;
+    default: return nullptr;
+  }
+}
 extern "C" int64_t ctsm_b200_launch_count(const ctsm_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int ctsm_b200_host_register(void* ptr, uint64_t bytes) {
@@ -225,7 +242,7 @@ int finish_call(ctsm_b200_ctx* ctx, int mem, ctsm_status_t* st) {
     if (st) memset(st, 0, sizeof *st);
     return cuda_fail(e, __FILE__, __LINE__);
   }
-  if (mem == CTSM_MEM_DEVICE) {
+  if (mem == CTSM_MEM_DEVICE || ctx->window_open) {     // asynchronous: ctsm_b200_sync / ctsm_b200_host_window_end collect the status
     if (st) memset(st, 0, sizeof *st);
     return CTSM_OK;
   }
@@ -248,6 +265,95 @@ int arena_reserve(ctsm_b200_ctx* ctx, ctsm_b200_ctx::Arena& a, size_t bytes) {
   return CTSM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Resident window for CTSM_MEM_HOST callers.  Outside a window every HOST call is self-contained: upload all fields,
+// run, download, synchronise - 36 GB over PCIe for one f02 step, most of it repeated (fields shared by routines) or
+// only there so that values outside the filters survive the download.  Inside a window (one model step, or any run
+// of hot-path calls between which the host does not touch the arrays)
+//   * every host array has a persistent device mirror (created and filled once, at its first use ever);
+//   * a call uploads, on the H2D stream, only the index ranges of its IN / INOUT fields that are not yet fresh on
+//     the device in this window (uploaded or written by an earlier call), and never an OUT field;
+//   * calls return as soon as their work is queued; kernels wait for their uploads through an event, the D2H stream
+//     downloads a call's OUT / INOUT fields over its bounds as soon as its kernels are done - so uploads of the next
+//     clump, kernels of this one and downloads of the previous one overlap when the host calls clump after clump;
+//   * ctsm_b200_host_window_end waits for everything and returns the first failure, like ctsm_b200_sync.
+static void fresh_missing(const std::vector<std::pair<int, int>>& fresh, int b, int e, std::vector<std::pair<int, int>>& out) {
+  int cur = b;
+  for (const auto& iv : fresh) {
+    if (iv.second < cur) continue;
+    if (iv.first > e) break;
+    if (iv.first > cur) out.push_back({cur, iv.first - 1});
+    if (iv.second + 1 > cur) cur = iv.second + 1;
+    if (cur > e) break;
+  }
+  if (cur <= e) out.push_back({cur, e});
+}
+static void fresh_add(std::vector<std::pair<int, int>>& fresh, int b, int e) {
+  std::vector<std::pair<int, int>> out;
+  bool placed = false;
+  for (const auto& iv : fresh) {
+    if (iv.second + 1 < b) out.push_back(iv);
+    else if (iv.first > e + 1) { if (!placed) { out.push_back({b, e}); placed = true; } out.push_back(iv); }
+    else { if (iv.first < b) b = iv.first; if (iv.second > e) e = iv.second; }
+  }
+  if (!placed) out.push_back({b, e});
+  fresh.swap(out);
+}
+
+int window_event(ctsm_b200_ctx* ctx, cudaEvent_t* ev) {
+  if (ctx->ev_used == ctx->ev_pool.size()) {
+    cudaEvent_t e = nullptr;
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->ev_pool.push_back(e);
+  }
+  *ev = ctx->ev_pool[ctx->ev_used++];
+  return CTSM_OK;
+}
+
+extern "C" int ctsm_b200_host_window_begin(ctsm_b200_ctx* ctx) {
+  if (!ctx || ctx->window_open) return CTSM_ERR_BAD_ARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!ctx->s_h2d) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+  if (!ctx->s_d2h) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));          // whatever ran before the window is finished
+  for (auto& kv : ctx->mirrors) kv.second.fresh.clear();
+  ctx->ev_used = 0; ctx->win_chunk = 0; ctx->win_off = 0; ctx->win_h2d_bytes = 0; ctx->win_d2h_bytes = 0;
+  ctx->bal_pending.clear(); ctx->bal_pinned_used = 0;
+  ctx->window_open = true;
+  return CTSM_OK;
+}
+
+extern "C" int ctsm_b200_host_window_end(ctsm_b200_ctx* ctx, ctsm_status_t* st) {
+  if (!ctx || !ctx->window_open) return CTSM_ERR_BAD_ARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  ctx->window_open = false;
+  CUDA_TRY(cudaStreamSynchronize(ctx->s_h2d));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->s_d2h));
+  const int rc = ctsm_b200_sync(ctx, st);
+  const int rb = balance_finish_pending(ctx, rc == CTSM_OK ? st : nullptr);
+  return rc != CTSM_OK ? rc : rb;
+}
+
+extern "C" int ctsm_b200_host_window_bytes(const ctsm_b200_ctx* ctx, uint64_t* h2d, uint64_t* d2h) {
+  if (!ctx || !h2d || !d2h) return CTSM_ERR_BAD_ARG;
+  *h2d = ctx->win_h2d_bytes; *d2h = ctx->win_d2h_bytes;
+  return CTSM_OK;
+}
+
+extern "C" int ctsm_b200_host_invalidate(ctsm_b200_ctx* ctx, const void* host_ptr) {
+  if (!ctx || ctx->window_open) return CTSM_ERR_BAD_ARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!host_ptr) {
+    for (auto& kv : ctx->mirrors) CUDA_TRY(cudaFree(kv.second.d));
+    ctx->mirrors.clear();
+    return CTSM_OK;
+  }
+  auto it = ctx->mirrors.find(host_ptr);
+  if (it != ctx->mirrors.end()) { CUDA_TRY(cudaFree(it->second.d)); ctx->mirrors.erase(it); }
+  return CTSM_OK;
+}
+
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static int copy_range(void* dst, const void* src, int es, size_t ld, int nlev, size_t off, size_t ncall,
@@ -266,8 +372,52 @@ static int copy_range(void* dst, const void* src, int es, size_t ld, int nlev, s
 // Allocates the device mirrors (same layout and leading dimension as the host
 // arrays), points the device-side struct members at them and uploads IN/INOUT
 // (and, when preserve_out, OUT) fields over the call's bounds.
+static int stage_begin_window(ctsm_b200_ctx* ctx, std::vector<StageField>& fl, const ctsm_bounds_t& alloc, const ctsm_bounds_t& call) {
+  cudaStream_t up = ctx->s_h2d;
+  std::vector<std::pair<int, int>> need;
+  for (auto& f : fl) {
+    if (!f.host_ptr) return CTSM_ERR_BAD_ARG;
+    const int a0 = sub_beg(alloc, f.sub), a1 = sub_end(alloc, f.sub, ctx->prm.npft_table);
+    const size_t ld = (size_t)(a1 - a0 + 1);
+    const size_t bytes = (size_t)f.elem_size * ld * f.nlev;
+    ctsm_b200_ctx::Mirror& m = ctx->mirrors[f.host_ptr];
+    if (!m.d || m.bytes != bytes) {
+      // first use of this host array: create the mirror and fill it with the array as it stands (once; this is what
+      // keeps elements no routine writes - outside the filters - equal to the host's when the field is downloaded)
+      if (m.d) CUDA_TRY(cudaFree(m.d));
+      m.d = nullptr; m.fresh.clear();
+      CUDA_TRY(cudaMalloc(&m.d, bytes > 0 ? bytes : 8));
+      m.bytes = bytes;
+      CUDA_TRY(cudaMemcpyAsync(m.d, f.host_ptr, bytes, cudaMemcpyHostToDevice, up));
+      ctx->win_h2d_bytes += bytes;
+      m.fresh.push_back({a0, a1});
+    }
+    *f.dev_slot = m.d;
+    const int c0 = sub_beg(call, f.sub), c1 = sub_end(call, f.sub, ctx->prm.npft_table);
+    if (c1 < c0) continue;
+    if (f.intent & INTENT_IN) {
+      need.clear();
+      fresh_missing(m.fresh, c0, c1, need);
+      for (const auto& iv : need) {
+        const int rc = copy_range(m.d, f.host_ptr, f.elem_size, ld, f.nlev, (size_t)(iv.first - a0), (size_t)(iv.second - iv.first + 1),
+                                  cudaMemcpyHostToDevice, up);
+        if (rc) return rc;
+        ctx->win_h2d_bytes += (uint64_t)f.elem_size * (uint64_t)(iv.second - iv.first + 1) * (uint64_t)f.nlev;
+      }
+    }
+    fresh_add(m.fresh, c0, c1);
+  }
+  cudaEvent_t ev;
+  int rc = window_event(ctx, &ev);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(ev, up));
+  CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev, 0));
+  return CTSM_OK;
+}
+
 int stage_begin(ctsm_b200_ctx* ctx, std::vector<StageField>& fl, const ctsm_bounds_t& alloc, const ctsm_bounds_t& call,
                 bool preserve_out) {
+  if (ctx->window_open) return stage_begin_window(ctx, fl, alloc, call);
   size_t total = 0;
   for (auto& f : fl) {
     if (!f.host_ptr) return CTSM_ERR_BAD_ARG;
@@ -293,19 +443,56 @@ int stage_begin(ctsm_b200_ctx* ctx, std::vector<StageField>& fl, const ctsm_boun
 }
 
 int stage_end(ctsm_b200_ctx* ctx, std::vector<StageField>& fl, const ctsm_bounds_t& alloc, const ctsm_bounds_t& call) {
+  cudaStream_t down = ctx->stream;
+  if (ctx->window_open) {
+    cudaEvent_t ev;
+    int rc = window_event(ctx, &ev);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ev, ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_d2h, ev, 0));
+    down = ctx->s_d2h;
+  }
   for (auto& f : fl) {
     if (!(f.intent & INTENT_OUT)) continue;
     const size_t ld = (size_t)(sub_end(alloc, f.sub, ctx->prm.npft_table) - sub_beg(alloc, f.sub) + 1);
     const size_t o = (size_t)(sub_beg(call, f.sub) - sub_beg(alloc, f.sub));
     const size_t n = (size_t)(sub_end(call, f.sub, ctx->prm.npft_table) - sub_beg(call, f.sub) + 1);
-    int rc = copy_range(f.host_ptr, *f.dev_slot, f.elem_size, ld, f.nlev, o, n, cudaMemcpyDeviceToHost, ctx->stream);
+    int rc = copy_range(f.host_ptr, *f.dev_slot, f.elem_size, ld, f.nlev, o, n, cudaMemcpyDeviceToHost, down);
     if (rc) return rc;
+    if (ctx->window_open) ctx->win_d2h_bytes += (uint64_t)f.elem_size * (uint64_t)n * (uint64_t)f.nlev;
   }
+  return CTSM_OK;
+}
+
+// filters of the calls of a window live until the window ends (calls are asynchronous): bump allocation from chunks
+static int stage_filter_window(ctsm_b200_ctx* ctx, const int32_t* host_filter, int numf, const int32_t** dev_filter) {
+  const size_t bytes = align256(sizeof(int32_t) * (size_t)(numf > 0 ? numf : 1));
+  while (ctx->win_chunk < ctx->win_chunks.size() && ctx->win_off + bytes > ctx->win_chunks[ctx->win_chunk].cap) { ctx->win_chunk++; ctx->win_off = 0; }
+  if (ctx->win_chunk == ctx->win_chunks.size()) {
+    ctsm_b200_ctx::Arena c;
+    c.cap = bytes > ((size_t)64 << 20) ? bytes : ((size_t)64 << 20);
+    CUDA_TRY(cudaMalloc(&c.p, c.cap));
+    ctx->win_chunks.push_back(c);
+    ctx->win_off = 0;
+  }
+  char* d = (char*)ctx->win_chunks[ctx->win_chunk].p + ctx->win_off;
+  ctx->win_off += bytes;
+  if (numf > 0) {
+    CUDA_TRY(cudaMemcpyAsync(d, host_filter, sizeof(int32_t) * (size_t)numf, cudaMemcpyHostToDevice, ctx->s_h2d));
+    ctx->win_h2d_bytes += sizeof(int32_t) * (uint64_t)numf;
+    cudaEvent_t ev;
+    int rc = window_event(ctx, &ev);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ev, ctx->s_h2d));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev, 0));
+  }
+  *dev_filter = (const int32_t*)d;
   return CTSM_OK;
 }
 
 int stage_filter(ctsm_b200_ctx* ctx, ctsm_b200_ctx::Arena& a, const int32_t* host_filter, int numf,
                  const int32_t** dev_filter) {
+  if (ctx->window_open) return stage_filter_window(ctx, host_filter, numf, dev_filter);
   int rc = arena_reserve(ctx, a, sizeof(int32_t) * (size_t)(numf > 0 ? numf : 1));
   if (rc) return rc;
   if (numf > 0)

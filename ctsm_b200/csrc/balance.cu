@@ -315,62 +315,14 @@ extern "C" int ctsm_b200_balancecheck_init(ctsm_b200_ctx* ctx) {
   return ctx->prm.balance_skip_steps;
 }
 
-extern "C" int ctsm_b200_balancecheck(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_allc, const int32_t* filter_allc,
-                                      const ctsm_balancecheck_fields_t* hf, int DAnstep, int mem, ctsm_balance_report_t* rep,
-                                      ctsm_status_t* st) {
-  if (!ctx || !bounds || !hf || !rep || num_allc < 0) return CTSM_ERR_BAD_ARG;
-  memset(rep, 0, sizeof *rep);
-  rep->abort_kind = -1;
-  rep->skip_steps = ctx->prm.balance_skip_steps;
-  if (st) memset(st, 0, sizeof *st);
-  if (ctx->prm.balance_skip_steps <= 0) {
-    fprintf(stderr, "ctsm_b200_balancecheck called before ctsm_b200_balancecheck_init\n");   // GetBalanceCheckSkipSteps :117-128
-    return CTSM_ERR_BAD_ARG;
-  }
-  (void)filter_allc;   // allc = every column in bounds (filterMod.F90 allc); the kernels loop over the bounds
-  CUDA_TRY(cudaSetDevice(ctx->device));
-  BalanceDev d;
-  std::vector<StageField> fl;
-#define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) \
-  d.name = hf->name;                                        \
-  fl.push_back(StageField{(void**)&d.name, (void*)hf->name, (int)sizeof(ctype), SUB_##sub, lev_shape(#lev).n, INTENT_##intent});
-#define CTSM_FIELDS_BALANCECHECK
-#include "../../include/ctsm_b200_fields.def"
-#undef CTSM_FIELDS_BALANCECHECK
-#undef CTSM_F
-  for (auto& s : fl) if (!s.host_ptr) return CTSM_ERR_BAD_ARG;
-  if (mem != CTSM_MEM_DEVICE) {
-    int rc = stage_begin(ctx, fl, hf->alloc, *bounds, mem == CTSM_MEM_HOST);
-    if (rc) return rc;
-  }
-  BGeo g;
-  g.begc0 = hf->alloc.begc; g.begp0 = hf->alloc.begp; g.begg0 = hf->alloc.begg;
-  g.ldc = hf->alloc.endc - hf->alloc.begc + 1; g.ldg = hf->alloc.endg - hf->alloc.begg + 1;
-  g.begc = bounds->begc; g.endc = bounds->endc; g.begp = bounds->begp; g.endp = bounds->endp;
-  g.begg = bounds->begg; g.endg = bounds->endg;
-  const int nc = g.endc - g.begc + 1, ng = g.endg - g.begg + 1, np = g.endp - g.begp + 1;
-  int rc = arena_reserve(ctx, ctx->arena_ints, sizeof(Red) + 64);
-  if (rc) return rc;
-  Red* red = (Red*)ctx->arena_ints.p;
-  Red init;
-  for (int k = 0; k < CTSM_BAL_NKIND; ++k) { init.mx[k] = 0ULL; init.idx[k] = 0x7fffffff; }
-  init.pad = 0;
-  cudaStream_t s = ctx->stream;
-  CUDA_TRY(cudaMemcpyAsync(red, &init, sizeof init, cudaMemcpyHostToDevice, s));
-  const double dtime = ctx->prm.dtime;
-  if (nc > 0) balance_col_kernel<<<grid_for(nc, 256), 256, 0, s>>>(d, g, dtime, nullptr, red);
-  if (ng > 0) balance_grc_kernel<<<grid_for(ng, 256), 256, 0, s>>>(d, g, dtime, red);
-  if (np > 0) balance_patch_kernel<<<grid_for(np, 256), 256, 0, s>>>(d, g, red);
-  const int nmax = nc > np ? (nc > ng ? nc : ng) : (np > ng ? np : ng);
-  if (nmax > 0) balance_loc_kernel<<<grid_for(nmax, 256), 256, 0, s>>>(d, g, red);
-  ctx->launches += (nc > 0) + (ng > 0) + (np > 0) + (nmax > 0);
-  Red got;
-  CUDA_TRY(cudaMemcpyAsync(&got, red, sizeof got, cudaMemcpyDeviceToHost, s));
-  if (mem != CTSM_MEM_DEVICE) {
-    rc = stage_end(ctx, fl, hf->alloc, *bounds);
-    if (rc) return rc;
-  }
-  CUDA_TRY(cudaStreamSynchronize(s));
+__global__ void balance_init_kernel(Red* red) {
+  const int k = threadIdx.x;
+  if (k < CTSM_BAL_NKIND) { red->mx[k] = 0ULL; red->idx[k] = 0x7fffffff; }
+  if (k == 0) red->pad = 0;
+}
+
+// thresholds and the abort decision of BalanceCheck / EnergyBalanceCheck on the maxima the kernels left (host side)
+static int balance_decide(ctsm_b200_ctx* ctx, const Red& got, ctsm_balance_report_t* rep, int DAnstep, ctsm_status_t* st) {
   for (int k = 0; k < CTSM_BAL_NKIND; ++k) {
     long long b = (long long)got.mx[k];
     memcpy(&rep->max_abs[k], &b, sizeof(double));
@@ -416,6 +368,105 @@ extern "C" int ctsm_b200_balancecheck(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
     return CTSM_ERR_BALANCE;
   }
   return CTSM_OK;
+}
+
+extern "C" int ctsm_b200_balancecheck(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_allc, const int32_t* filter_allc,
+                                      const ctsm_balancecheck_fields_t* hf, int DAnstep, int mem, ctsm_balance_report_t* rep,
+                                      ctsm_status_t* st) {
+  if (!ctx || !bounds || !hf || !rep || num_allc < 0) return CTSM_ERR_BAD_ARG;
+  memset(rep, 0, sizeof *rep);
+  rep->abort_kind = -1;
+  rep->skip_steps = ctx->prm.balance_skip_steps;
+  if (st) memset(st, 0, sizeof *st);
+  if (ctx->prm.balance_skip_steps <= 0) {
+    fprintf(stderr, "ctsm_b200_balancecheck called before ctsm_b200_balancecheck_init\n");   // GetBalanceCheckSkipSteps :117-128
+    return CTSM_ERR_BAD_ARG;
+  }
+  (void)filter_allc;   // allc = every column in bounds (filterMod.F90 allc); the kernels loop over the bounds
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  BalanceDev d;
+  std::vector<StageField> fl;
+#define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) \
+  d.name = hf->name;                                        \
+  fl.push_back(StageField{(void**)&d.name, (void*)hf->name, (int)sizeof(ctype), SUB_##sub, lev_shape(#lev).n, INTENT_##intent});
+#define CTSM_FIELDS_BALANCECHECK
+#include "../../include/ctsm_b200_fields.def"
+#undef CTSM_FIELDS_BALANCECHECK
+#undef CTSM_F
+  for (auto& s : fl) if (!s.host_ptr) return CTSM_ERR_BAD_ARG;
+  if (mem != CTSM_MEM_DEVICE) {
+    int rc = stage_begin(ctx, fl, hf->alloc, *bounds, mem == CTSM_MEM_HOST);
+    if (rc) return rc;
+  }
+  BGeo g;
+  g.begc0 = hf->alloc.begc; g.begp0 = hf->alloc.begp; g.begg0 = hf->alloc.begg;
+  g.ldc = hf->alloc.endc - hf->alloc.begc + 1; g.ldg = hf->alloc.endg - hf->alloc.begg + 1;
+  g.begc = bounds->begc; g.endc = bounds->endc; g.begp = bounds->begp; g.endp = bounds->endp;
+  g.begg = bounds->begg; g.endg = bounds->endg;
+  const int nc = g.endc - g.begc + 1, ng = g.endg - g.begg + 1, np = g.endp - g.begp + 1;
+  int rc = arena_reserve(ctx, ctx->arena_ints, sizeof(Red) + 64);
+  if (rc) return rc;
+  Red* red = (Red*)ctx->arena_ints.p;
+  void* pinned_slot = nullptr;
+  if (ctx->window_open) {
+    // resident window: calls are asynchronous and arena_ints is reused by the next call, so the maxima of this call get
+    // their own device + pinned slot (pooled in the context)
+    if (ctx->bal_pinned_used == ctx->bal_pinned.size()) {
+      void *q = nullptr, *dq = nullptr;
+      CUDA_TRY(cudaMallocHost(&q, sizeof(Red)));
+      ctx->bal_pinned.push_back(q);
+      CUDA_TRY(cudaMalloc(&dq, sizeof(Red)));
+      ctx->bal_dev.push_back(dq);
+    }
+    red = (Red*)ctx->bal_dev[ctx->bal_pinned_used];
+    pinned_slot = ctx->bal_pinned[ctx->bal_pinned_used++];
+  }
+  cudaStream_t s = ctx->stream;
+  balance_init_kernel<<<1, 32, 0, s>>>(red);               // (no host->device copy: nothing on this stream may queue behind bulk DMA)
+  const double dtime = ctx->prm.dtime;
+  if (nc > 0) balance_col_kernel<<<grid_for(nc, 256), 256, 0, s>>>(d, g, dtime, nullptr, red);
+  if (ng > 0) balance_grc_kernel<<<grid_for(ng, 256), 256, 0, s>>>(d, g, dtime, red);
+  if (np > 0) balance_patch_kernel<<<grid_for(np, 256), 256, 0, s>>>(d, g, red);
+  const int nmax = nc > np ? (nc > ng ? nc : ng) : (np > ng ? np : ng);
+  if (nmax > 0) balance_loc_kernel<<<grid_for(nmax, 256), 256, 0, s>>>(d, g, red);
+  ctx->launches += (nc > 0) + (ng > 0) + (np > 0) + (nmax > 0);
+  if (ctx->window_open) {
+    // resident window: the call stays asynchronous; the maxima travel to the pinned slot on the download stream (a copy
+    // on the compute stream would queue behind the bulk downloads in the copy engine and stall the next kernels) and
+    // ctsm_b200_host_window_end takes the warn / abort decision (balance_finish_pending)
+    cudaEvent_t ev;
+    rc = window_event(ctx, &ev);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ev, s));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_d2h, ev, 0));
+    CUDA_TRY(cudaMemcpyAsync(pinned_slot, red, sizeof(Red), cudaMemcpyDeviceToHost, ctx->s_d2h));
+    ctx->bal_pending.push_back(ctsm_b200_ctx::BalPending{pinned_slot, rep, DAnstep});
+    rc = stage_end(ctx, fl, hf->alloc, *bounds);
+    if (rc) return rc;
+    return finish_call(ctx, mem, st);
+  }
+  Red got;
+  CUDA_TRY(cudaMemcpyAsync(&got, red, sizeof got, cudaMemcpyDeviceToHost, s));
+  if (mem != CTSM_MEM_DEVICE) {
+    rc = stage_end(ctx, fl, hf->alloc, *bounds);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return balance_decide(ctx, got, rep, DAnstep, st);
+}
+
+int balance_finish_pending(ctsm_b200_ctx* ctx, ctsm_status_t* st) {
+  int rc_all = CTSM_OK;
+  for (const auto& pnd : ctx->bal_pending) {
+    Red got;
+    memcpy(&got, pnd.pinned, sizeof got);
+    ctsm_status_t local;
+    memset(&local, 0, sizeof local);
+    const int rc = balance_decide(ctx, got, pnd.rep, pnd.DAnstep, &local);
+    if (rc != CTSM_OK && rc_all == CTSM_OK) { rc_all = rc; if (st) *st = local; }
+  }
+  ctx->bal_pending.clear();
+  return rc_all;
 }
 
 extern "C" int ctsm_b200_vert_tran_sink_hydstress(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_filterc,

@@ -1852,9 +1852,12 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
     // close(0, first) only builds the list of pass 0; fric/leaf(k) open pass k; the task kernels solve its PHS system;
     // close(k+1) closes pass k; close(npass, last) only closes.  The host stops issuing rounds once it has seen (two
     // rounds late, through a pinned copy) that a round's list was empty.
+    // Small calls only: a large filter practically always holds a patch that uses all itmax+1 passes (0.3 % of the
+    // synthetic patches do), and a host that waits on the device could not queue the next clump's uploads meanwhile.
+    const bool early_exit = fn <= 65536;
     int rounds = 0;
     for (int itlef = 0; itlef <= npass; ++itlef) {
-      if (itlef >= 2) {
+      if (itlef >= 2 && early_exit) {
         // the host stays at most two rounds ahead of the device, so that it can stop when the lists have run empty
         CUDA_TRY(cudaEventSynchronize(ctx->ev_round[itlef - 2]));
         if (ctx->h_counts[itlef - 2] == 0) break;
@@ -1865,8 +1868,10 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
       rounds = itlef + 1;
       if (itlef < npass) {
         // the list this round works on: copy its length to the host for the early exit above
-        CUDA_TRY(cudaMemcpyAsync(&ctx->h_counts[itlef], L.counts + (size_t)(itlef + 1) * QROW, sizeof(int), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaEventRecord(ctx->ev_round[itlef], s));
+        if (early_exit) {
+          CUDA_TRY(cudaMemcpyAsync(&ctx->h_counts[itlef], L.counts + (size_t)(itlef + 1) * QROW, sizeof(int), cudaMemcpyDeviceToHost, s));
+          CUDA_TRY(cudaEventRecord(ctx->ev_round[itlef], s));
+        }
         canopy_fric_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, dfilter, ws, wstride, L, lout);
         canopy_leaf_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, dfilter, ws, wstride, L, lout, rec, ctx->d_status);
         ctx->launches += 2;

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 #include <vector>
+#include <unordered_map>
+#include <utility>
 #include "../../include/ctsm_b200.h"
 
 #define NLEVSNO CTSM_NLEVSNO
@@ -73,6 +75,18 @@ struct ctsm_b200_ctx {
   int* h_counts = nullptr; int h_counts_cap = 0;
   struct Tuning { int tail_max = 0, nt_budget = 0, tail_lanes = 1; } tune;
   int* dbg_counts = nullptr; int* dbg_tail_end = nullptr; int dbg_npass = 0;
+  // CTSM_MEM_HOST resident window (abi.cu: ctsm_b200_host_window_begin / _end): persistent device mirrors keyed by the
+  // host array's base address, what is fresh on the device in the current window, copy streams, event pool
+  struct Mirror { void* d = nullptr; size_t bytes = 0; std::vector<std::pair<int, int>> fresh; };
+  std::unordered_map<const void*, Mirror> mirrors;
+  bool window_open = false;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+  std::vector<Arena> win_chunks; size_t win_chunk = 0, win_off = 0;      // filters of the window's calls
+  uint64_t win_h2d_bytes = 0, win_d2h_bytes = 0;
+  struct BalPending { void* pinned; ctsm_balance_report_t* rep; int DAnstep; };
+  std::vector<BalPending> bal_pending;
+  std::vector<void*> bal_pinned, bal_dev; size_t bal_pinned_used = 0;
 };
 
 // records "name at file:line: text" for ctsm_b200_last_cuda_error() and maps the error to a CTSM_ERR_* code
@@ -114,6 +128,9 @@ struct StageField {
 
 int arena_reserve(ctsm_b200_ctx* ctx, ctsm_b200_ctx::Arena& a, size_t bytes);
 int ensure_round_events(ctsm_b200_ctx* ctx, int n);
+int window_event(ctsm_b200_ctx* ctx, cudaEvent_t* ev);
+// balance.cu: thresholds / abort decision of the BalanceCheck calls issued inside a resident window
+int balance_finish_pending(ctsm_b200_ctx* ctx, ctsm_status_t* st);
 int stage_begin(ctsm_b200_ctx* ctx, std::vector<StageField>& fl, const ctsm_bounds_t& alloc, const ctsm_bounds_t& call,
                 bool preserve_out);
 int stage_end(ctsm_b200_ctx* ctx, std::vector<StageField>& fl, const ctsm_bounds_t& alloc, const ctsm_bounds_t& call);

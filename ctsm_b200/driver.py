@@ -68,34 +68,85 @@ class Context:
         return int(self.L.ctsm_b200_launch_count(self.h))
 
 
+def make_slabs(sg, nslab: int, cost: str = "exposedvegp"):
+    """Contiguous gridcell slabs (clump bounds + the rank-level filters cut at them), balanced by the number of
+    exposed-vegetation patches (decomp.balanced_slabs; decompInitMod.F90:137-161 gives clumps whole gridcells).
+    Returns [(Bounds, {filter name: int32 array})]."""
+    from . import decomp
+    ng = sg.ngrc
+    nslab = max(1, min(int(nslab), ng))
+    cost_g = np.zeros(ng, dtype=np.float64)
+    f = sg.filters.get(cost)
+    if f is not None and len(f):
+        gcell = sg.col_gridcell[sg.patch_column[f - 1] - 1]
+        np.add.at(cost_g, gcell - sg.bounds.begg, 1.0)
+    cost_g += 1.0e-3                                              # so that empty stretches are still dealt out
+    edges = decomp.balanced_slabs(cost_g, nslab)
+    out = []
+    for k in range(nslab):
+        g0, g1 = int(edges[k]) + sg.bounds.begg, int(edges[k + 1]) + sg.bounds.begg - 1
+        if g1 < g0:
+            continue
+        cols = np.nonzero((sg.col_gridcell >= g0) & (sg.col_gridcell <= g1))[0]
+        b = sg.bounds.copy()
+        b.begg, b.endg = g0, g1
+        b.begc, b.endc = int(cols[0]) + sg.bounds.begc, int(cols[-1]) + sg.bounds.begc
+        b.begl, b.endl = b.begc, b.endc                           # one landunit per column in the synthetic subgrid
+        b.begp, b.endp = int(sg.col_patchi[cols[0]]), int(sg.col_patchf[cols[-1]])
+        b.level, b.clump_index = 2, k + 1
+        fl = {}
+        for name, arr in sg.filters.items():
+            lo, hi = (b.begp, b.endp) if name.endswith("p") else (b.begc, b.endc)
+            fl[name] = np.ascontiguousarray(arr[(arr >= lo) & (arr <= hi)])
+        fl["allc"] = np.arange(b.begc, b.endc + 1, dtype=np.int32)
+        out.append((b, fl))
+    return out
+
+
 class HotPath:
     """One rank's share of the grid: subgrid topology, filters and state arrays
-    (numpy = host-owned as in the Fortran model, torch = device-resident)."""
+    (numpy = host-owned as in the Fortran model, torch = device-resident).
 
-    def __init__(self, ctx: Context, sg, arrays: Dict[str, object], mem: int, routines: Iterable[str] = ROUTINES):
+    nslab > 1 issues the step clump after clump (clm_drv's clump loop, clm_driver.F90:525) over nslab contiguous
+    slabs; with host-owned arrays and window=True the step runs inside a resident window
+    (ctsm_b200_host_window_begin/_end), where uploads, kernels and downloads of successive slabs overlap."""
+
+    def __init__(self, ctx: Context, sg, arrays: Dict[str, object], mem: int, routines: Iterable[str] = ROUTINES,
+                 nslab: int = 1, window: bool = False):
         self.ctx, self.sg, self.arrays, self.mem = ctx, sg, arrays, mem
         self.routines = tuple(routines)
+        self.window = bool(window) and mem != abi.MEM_DEVICE
         self.structs = {g: abi.make_struct(g, arrays, sg.bounds) for g in self.routines}
-        self.filters = dict(sg.filters)
-        self.filters.setdefault("allc", np.arange(sg.bounds.begc, sg.bounds.endc + 1, dtype=np.int32))
         # DAnstep: 1 = inside BalanceCheck's skip steps (BalanceCheckMod.F90:91,754): all residuals, maxima and warnings
         # are computed, the abort is suppressed - the synthetic water/energy terms are not a closed budget after the step
         self.danstep = 1
-        self.balance_report = abi.BalanceReport()
         if "balancecheck" in self.routines:
             self.ctx.L.ctsm_b200_balancecheck_init(self.ctx.h)
-        if mem == abi.MEM_DEVICE:
-            import torch
-            self.nfilter = {k: len(v) for k, v in self.filters.items()}
-            self.filters = {k: torch.from_numpy(v).cuda() for k, v in self.filters.items()}
+        if nslab > 1:
+            slabs = make_slabs(sg, nslab)
         else:
-            self.nfilter = {k: len(v) for k, v in self.filters.items()}
+            fl = dict(sg.filters)
+            fl.setdefault("allc", np.arange(sg.bounds.begc, sg.bounds.endc + 1, dtype=np.int32))
+            slabs = [(sg.bounds, fl)]
+        self.slabs = []
+        for b, fl in slabs:
+            nf = {k: len(v) for k, v in fl.items()}
+            if mem == abi.MEM_DEVICE:
+                import torch
+                fl = {k: torch.from_numpy(v if len(v) else np.zeros(1, np.int32)).cuda() for k, v in fl.items()}
+            else:
+                fl = {k: (v if len(v) else np.zeros(1, np.int32)) for k, v in fl.items()}
+            self.slabs.append((b, fl, nf, abi.BalanceReport()))
+        self._select(0)
+
+    def _select(self, k: int):
+        self.bounds, self.filters, self.nfilter, self.balance_report = self.slabs[k]
 
     # -- individual routines (names and argument meaning follow the Fortran) ---------------
     def SoilTemperature(self):
         st = abi.Status()
         rc = self.ctx.L.ctsm_b200_soiltemperature(
-            self.ctx.h, C.byref(self.sg.bounds), self.nfilter["nolakep"], abi.i32p(self.filters["nolakep"]),
+            self.ctx.h, C.byref(self.bounds), self.nfilter["nolakep"], abi.i32p(self.filters["nolakep"]),
             self.nfilter["nolakec"], abi.i32p(self.filters["nolakec"]), C.byref(self.structs["soiltemperature"]),
             self.mem, C.byref(st))
         if rc != 0:
@@ -104,7 +155,7 @@ class HotPath:
     def SoilWater(self):
         st = abi.Status()
         rc = self.ctx.L.ctsm_b200_soilwater(
-            self.ctx.h, C.byref(self.sg.bounds), self.nfilter["hydrologyc"], abi.i32p(self.filters["hydrologyc"]),
+            self.ctx.h, C.byref(self.bounds), self.nfilter["hydrologyc"], abi.i32p(self.filters["hydrologyc"]),
             C.byref(self.structs["soilwater"]), self.mem, C.byref(st))
         if rc != 0:
             raise CtsmError(st, rc)
@@ -112,7 +163,7 @@ class HotPath:
     def CanopyFluxes(self):
         st = abi.Status()
         rc = self.ctx.L.ctsm_b200_canopyfluxes(
-            self.ctx.h, C.byref(self.sg.bounds), self.nfilter["exposedvegp"], abi.i32p(self.filters["exposedvegp"]),
+            self.ctx.h, C.byref(self.bounds), self.nfilter["exposedvegp"], abi.i32p(self.filters["exposedvegp"]),
             C.byref(self.structs["canopyfluxes"]), self.mem, C.byref(st))
         if rc != 0:
             raise CtsmError(st, rc)
@@ -121,7 +172,7 @@ class HotPath:
         """SoilFluxes (SoilFluxesMod.F90:37; the urban filters of the reference's dummy list are empty on this path)"""
         st = abi.Status()
         rc = self.ctx.L.ctsm_b200_soilfluxes(
-            self.ctx.h, C.byref(self.sg.bounds), self.nfilter["nolakec"], abi.i32p(self.filters["nolakec"]),
+            self.ctx.h, C.byref(self.bounds), self.nfilter["nolakec"], abi.i32p(self.filters["nolakec"]),
             self.nfilter["nolakep"], abi.i32p(self.filters["nolakep"]), C.byref(self.structs["soilfluxes"]), self.mem,
             C.byref(st))
         if rc != 0:
@@ -131,7 +182,7 @@ class HotPath:
         """clm_drv_patch2col (clm_driver.F90:1655)"""
         st = abi.Status()
         rc = self.ctx.L.ctsm_b200_patch2col(
-            self.ctx.h, C.byref(self.sg.bounds), self.nfilter["allc"], abi.i32p(self.filters["allc"]),
+            self.ctx.h, C.byref(self.bounds), self.nfilter["allc"], abi.i32p(self.filters["allc"]),
             self.nfilter["nolakec"], abi.i32p(self.filters["nolakec"]), C.byref(self.structs["patch2col"]), self.mem,
             C.byref(st))
         if rc != 0:
@@ -141,7 +192,7 @@ class HotPath:
         """Compute_EffecRootFrac_And_VertTranSink_HydStress (SoilWaterPlantSinkMod.F90:236-328)"""
         st = abi.Status()
         rc = self.ctx.L.ctsm_b200_vert_tran_sink_hydstress(
-            self.ctx.h, C.byref(self.sg.bounds), self.nfilter["hydrologyc"], abi.i32p(self.filters["hydrologyc"]),
+            self.ctx.h, C.byref(self.bounds), self.nfilter["hydrologyc"], abi.i32p(self.filters["hydrologyc"]),
             C.byref(self.structs["plantsink"]), self.mem, C.byref(st))
         if rc != 0:
             raise CtsmError(st, rc)
@@ -150,7 +201,7 @@ class HotPath:
         """BalanceCheck + EnergyBalanceCheck over all columns in bounds (BalanceCheckMod.F90:445,859)"""
         st = abi.Status()
         rc = self.ctx.L.ctsm_b200_balancecheck(
-            self.ctx.h, C.byref(self.sg.bounds), self.nfilter["allc"], abi.i32p(self.filters["allc"]),
+            self.ctx.h, C.byref(self.bounds), self.nfilter["allc"], abi.i32p(self.filters["allc"]),
             C.byref(self.structs["balancecheck"]), self.danstep, self.mem, C.byref(self.balance_report), C.byref(st))
         if rc != 0:
             raise CtsmError(st, rc)
@@ -160,8 +211,28 @@ class HotPath:
          "plantsink": self.VertTranSink, "balancecheck": self.BalanceCheck, "soilfluxes": self.SoilFluxes, "patch2col": self.Patch2Col}[g]()
 
     def step(self):
-        for g in self.routines:
-            self.call(g)
+        if self.window:
+            rc = self.ctx.L.ctsm_b200_host_window_begin(self.ctx.h)
+            if rc != 0:
+                raise RuntimeError("ctsm_b200_host_window_begin rc=%d" % rc)
+        try:
+            for k in range(len(self.slabs)):
+                self._select(k)
+                for g in self.routines:
+                    self.call(g)
+        finally:
+            self._select(0)
+            if self.window:
+                st = abi.Status()
+                rc = self.ctx.L.ctsm_b200_host_window_end(self.ctx.h, C.byref(st))
+                if rc != 0:
+                    raise CtsmError(st, rc)
+
+    def window_bytes(self):
+        """(h2d, d2h) bytes the last resident window moved, counted by the library from the copies it issued."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self.ctx.L.ctsm_b200_host_window_bytes(self.ctx.h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
 
 
 def staged_bytes(sg, routines: Iterable[str], preserve_out: bool = True):

@@ -261,6 +261,9 @@ int  ctsm_b200_finalize(ctsm_b200_ctx* ctx);
 int  ctsm_b200_sync(ctsm_b200_ctx* ctx, ctsm_status_t* st);
 /* the cudaStream_t (as void*) all kernels of this context are launched on */
 void* ctsm_b200_stream(ctsm_b200_ctx* ctx);
+/* the context's other streams (for timelines): kind 0 = compute (same as ctsm_b200_stream), 1 = CanopyFluxes tail kernel,
+ * 2 = host-to-device copies of a resident window, 3 = device-to-host copies (2 and 3 exist after the first window) */
+void* ctsm_b200_stream_of(ctsm_b200_ctx* ctx, int kind);
 /* number of kernel launches issued by this context so far */
 int64_t ctsm_b200_launch_count(const ctsm_b200_ctx* ctx);
 /* "cudaErrorName at file:line: text" of the last CUDA runtime error this process's library calls met ("" if none) */
@@ -279,6 +282,21 @@ int  ctsm_b200_set_tuning(ctsm_b200_ctx* ctx, int tail_max, int nt_budget, int t
  * list_len[r] = patches the round's list kernels served, tail_end[r] = patches handed to the tail kernel up to and
  * including round r.  Returns the number of rounds written. */
 int  ctsm_b200_canopy_round_stats(ctsm_b200_ctx* ctx, int32_t* list_len, int32_t* tail_end, int cap);
+/* Resident window for CTSM_MEM_HOST callers (SURVEY.md 8b "Ownership": the library owns device mirrors keyed by host
+ * base address).  Between _begin and _end the host must not touch the arrays it passes to hot-path calls.  In the window
+ * every host array has a persistent device mirror (filled once, at its first use ever); a call uploads only the parts
+ * of its IN / INOUT fields that no earlier call of the window uploaded or produced, never an OUT field; calls return
+ * once their work is queued (status comes from _end); each call's OUT / INOUT fields are downloaded over its bounds
+ * as soon as its kernels finish.  Copies run on their own streams: when the host issues the step clump after clump
+ * (as clm_drv's clump loop does), uploads, kernels and downloads of successive clumps overlap.
+ * Contract: an array the window only writes (OUT) keeps, outside the filters, the values it had when its mirror was
+ * created or last downloaded; host code that changes such an array between windows calls ctsm_b200_host_invalidate.
+ * ctsm_b200_host_window_bytes reports the bytes the last (or current) window moved in each direction. */
+int  ctsm_b200_host_window_begin(ctsm_b200_ctx* ctx);
+int  ctsm_b200_host_window_end(ctsm_b200_ctx* ctx, ctsm_status_t* st);
+int  ctsm_b200_host_window_bytes(const ctsm_b200_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+/* drop the device mirror of one host array (NULL: of all); not inside a window */
+int  ctsm_b200_host_invalidate(ctsm_b200_ctx* ctx, const void* host_ptr);
 /* page-lock a host array so that CTSM_MEM_HOST staging runs at full PCIe rate */
 int  ctsm_b200_host_register(void* ptr, uint64_t bytes);
 int  ctsm_b200_host_unregister(void* ptr);

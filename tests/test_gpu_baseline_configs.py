@@ -35,7 +35,7 @@ def test_config3_canopyfluxes_f09(gpu_ctx, oracle_lib):
     L, ctx, prm = gpu_ctx
     sg, S = synthetic_canopy.make_full_case("f09", seed=20260103)
     fe = sg.filters["exposedvegp"]
-    assert sg.ngrc == 21000 and sg.npatch == 315000 and len(fe) > 140000
+    assert sg.ngrc == 21000 and sg.npatch >= 315000 and len(fe) > 140000
     ref, got = copy_state(S), copy_state(S)
     nth = _oracle_threads(oracle_lib)
     clumps, keep = oracle.make_clumps(sg, 4 * nth)
