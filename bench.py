@@ -182,7 +182,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=20000, help="gridcells in the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-slabs", type=int, default=4, help="gridcell slabs the e2e step is issued over (clump loop)")
+    ap.add_argument("--e2e-slabs", type=int, default=6, help="gridcell slabs the e2e step is issued over (clump loop)")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
