@@ -9,7 +9,7 @@ NVCCFLAGS := -O3 -std=c++17 -lineinfo -fmad=false $(ARCH) -Xcompiler -fPIC -ccbi
 CSRC      := ctsm_b200/csrc
 CU        := $(wildcard $(CSRC)/*.cu)
 OBJ       := $(CU:.cu=.o)
-HDR       := $(wildcard $(CSRC)/*.cuh) include/ctsm_b200.h include/ctsm_b200_fields.def
+HDR       := $(wildcard $(CSRC)/*.cuh) include/ctsm_b200.h include/ctsm_b200_fields.def include/ctsm_b200_defaults.h
 LIB       ?= ctsm_b200/lib/libctsm_b200.so
 
 all: $(LIB) oracle

@@ -11,8 +11,10 @@ config 2, `--size f09 --routines canopyfluxes` config 3).  `value` is whole-job 
 the same step driven through the C ABI with pinned HOST buffers, host<->device copies inside the
 timed region.  `roofline` describes the dominant routine's kernels, `cpu_baseline` the CPU oracle
 (C restatement of the reference, OpenMP over clumps) on a bounded sample of the same workload.
-Under torchrun each rank owns an equal, independent grid (weak scaling); the path has no exchange
-step, so the only collectives are the timing reductions.
+Under torchrun ONE grid of the named size is dealt to the ranks in contiguous gridcell slabs (clump decomposition,
+decompInitMod.F90:96-161; BASELINE.json config 4): strong scaling.  The path has no exchange step; the one collective in
+the timed region is the NCCL MAX-reduction of BalanceCheck's residual maxima on a side stream (`--scaling weak` gives
+every rank its own full-size grid instead).
 """
 import argparse
 import ctypes as C
@@ -140,7 +142,7 @@ def cpu_reference_run(size_label, routines, steps, warmup, sample_gridcells, see
     OL.oracle_set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     nthreads = int(OL.oracle_num_threads())
     sg, S = make_workload(sample_gridcells, seed)
-    prm = abi.default_params()
+    prm = oracle.default_params()          # from liboracle.so: this arm never loads the CUDA library
     prm.balance_skip_steps = int(OL.oracle_balancecheck_skip_steps(prm.dtime))
     clumps, keep = oracle.make_clumps(sg, nthreads * 4)
     inout = {fs.name for g in ALL_ROUTINES for fs in abi.FIELDS[g] if fs.intent != "IN"}
@@ -184,6 +186,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-slabs", type=int, default=6, help="gridcell slabs the e2e step is issued over (clump loop)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="under torchrun: strong = ONE grid of --size dealt to the ranks (default), weak = one grid of --size per rank")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -191,13 +195,23 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     size = a.size if not a.size.isdigit() else int(a.size)
     routines = tuple(g for g in ALL_ROUTINES if g in a.routines.split(","))
-    wl_name = "%s one 1800 s step, %s-sized synthetic grid per GPU (15 patches per soil column)" % (
-        "->".join(NAME_OF[g] for g in routines), a.size)
+    strong = a.scaling == "strong" or world == 1
+    if strong and world > 1:
+        from ctsm_b200 import synthetic
+        total_g = synthetic.GRID_SIZES[size] if isinstance(size, str) else int(size)
+        g0, g1 = rank * total_g // world, (rank + 1) * total_g // world      # contiguous slab of the one grid (clump range)
+        local_size = g1 - g0
+    else:
+        local_size = size
+    wl_name = "%s one 1800 s step, ONE %s-sized synthetic grid (15 patches per soil column)%s" % (
+        "->".join(NAME_OF[g] for g in routines), a.size,
+        "" if world == 1 else (" dealt to %d GPUs in contiguous gridcell slabs" % world if strong else " PER GPU (weak scaling)"))
     config = {"workload": wl_name, "grid": str(a.size), "routines": [NAME_OF[g] for g in routines],
               "state": "restored from a pristine device snapshot before every step (untimed D2D copies)",
               "l2": "per-step working set (GBs at f02) exceeds the 126 MB L2; the untimed state restore between steps "
                     "streams >L2 bytes through the cache",
-              "parallelism": "gridcells/clumps sharded by rank, no data-path collective"}
+              "parallelism": "gridcells/clumps sharded by rank (contiguous slabs), no data-path collective; NCCL all-reduce(MAX) of the "
+                             "7 BalanceCheck maxima per step on a side stream"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -205,7 +219,7 @@ def main():
         r = cpu_reference_run(a.size, routines, a.steps, a.warmup, a.cpu_sample, 20260101)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -223,12 +237,14 @@ def main():
 
     prm = abi.default_params(device=local_rank)
     ctx = driver.Context(prm)
-    sg, S = make_workload(size, 20260101 + 1000 * rank)
+    sg, S = make_workload(local_size, 20260101 + 1000 * rank)
     names = sorted({fs.name for g in routines for fs in abi.FIELDS[g]})
     D = {k: torch.from_numpy(S[k]).cuda() for k in names}
     restore = sorted({fs.name for g in routines for fs in abi.FIELDS[g] if fs.intent != "IN"})
     pristine = {k: D[k].clone() for k in restore}
     hp = driver.HotPath(ctx, sg, D, abi.MEM_DEVICE, routines)
+    if dist is not None and "balancecheck" in routines:
+        hp.enable_global_balance(dist)        # BalanceCheckMod's global water / energy figures: NCCL MAX on a side stream
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
 
     def reset_state():
@@ -343,12 +359,14 @@ def main():
     if rank == 0:
         nit = S["num_iter"] if False else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": 1e3 * total_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": 1e3 * total_s / a.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+                "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": dict(config, columns_per_gpu=ncol, patches_per_gpu=sg.npatch,
                                exposedveg_patches_per_gpu=int(len(sg.filters["exposedvegp"]))),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "warnings_in_timed_region": int(st.n_warnings), "wall_s_timed_region": t_wall}
+                "warnings_in_timed_region": int(st.n_warnings), "wall_s_timed_region": t_wall,
+                "balance_global_max": hp.global_balance(), "total_columns": int(total_cols)}
         print(json.dumps(line))
     ctx.close()
     if dist is not None:

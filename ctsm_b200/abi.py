@@ -280,6 +280,8 @@ def lib():
     L.ctsm_b200_host_window_bytes.restype = C.c_int
     L.ctsm_b200_host_invalidate.argtypes = [vp, vp]
     L.ctsm_b200_host_invalidate.restype = C.c_int
+    L.ctsm_b200_balance_device_maxima.argtypes = [vp]
+    L.ctsm_b200_balance_device_maxima.restype = vp
     L.ctsm_b200_canopy_round_stats.argtypes = [vp, i32p, i32p, C.c_int]
     L.ctsm_b200_canopy_round_stats.restype = C.c_int
     L.ctsm_b200_tridiagonal.argtypes = [vp, C.POINTER(Bounds), C.c_int, C.c_int, i32p, C.c_int, i32p,

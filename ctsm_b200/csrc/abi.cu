@@ -1,6 +1,7 @@
 // abi.cu — lifecycle, status plumbing and host<->device staging of the C ABI
 // declared in include/ctsm_b200.h.  No compute here.
 #include "common.cuh"
+#include "../../include/ctsm_b200_defaults.h"
 
 #include <stdlib.h>
 
@@ -19,48 +20,7 @@ extern "C" const char* ctsm_b200_last_cuda_error(void) { return g_last_cuda_erro
 
 extern "C" const char* ctsm_b200_version(void) { return kVersion; }
 
-extern "C" void ctsm_b200_default_params(ctsm_params_t* p) {
-  // clm6_0 defaults: bld/namelist_files/namelist_defaults_ctsm.xml:471-488 (soilwater_movement),
-  // :511 (nlevsno), :254 (20SL_8.5m), :556 (Sturm1997); e_ice is a parameter-file scalar.
-  memset(p, 0, sizeof *p);
-  p->abi_version = CTSM_B200_ABI_VERSION;
-  p->device = 0;
-  p->nlevsno = CTSM_NLEVSNO; p->nlevgrnd = CTSM_NLEVGRND; p->nlevsoi = CTSM_NLEVSOI;
-  p->dtime = 1800.0;
-  p->upper_boundary_condition = 1;
-  p->lower_boundary_condition = 2;
-  p->flux_calculation = 1;
-  p->dtmin = 60.0; p->verySmall = 1.e-8; p->xTolerUpper = 1.e-1; p->xTolerLower = 1.e-2;
-  p->e_ice = 6.0;
-  p->snow_thermal_cond_method = 2;
-  p->snow_thermal_cond_glc_method = 2;   // clm6_0: Sturm1997 as well (namelist_defaults_ctsm.xml:559)
-  // canopyfluxes_inparm / clm6_0 switches: namelist_defaults_ctsm.xml:462,454,457,622,270,726,635,108,95,104,2182
-  p->itmax_canopy_fluxes = 40;
-  p->use_undercanopy_stability = 0;
-  p->use_biomass_heat_storage = 1;
-  p->z0param_method = 2;
-  p->soil_resis_method = 1;
-  p->use_hydrstress = 1;
-  p->use_luna = 1;
-  p->stomatalcond_mtd = 2;
-  p->light_inhibit = 1;
-  p->modifyphoto_and_lmr_forcrop = 1;
-  // parameter-file scalars: values documented inside the reference where available, otherwise
-  // synthetic choices (SURVEY.md Appendix D marks which)
-  p->lai_dl = 0.5; p->z_dl = 0.05; p->a_coef = 0.13; p->a_exp = 0.45; p->csoilc = 0.004; p->cv = 0.01;
-  p->wind_min = 1.0;
-  p->zetamaxstable = 2.0;
-  p->leaf_mr_vcm = 0.015;
-  p->act25 = 60.0; p->fnr = 7.16; p->cp25_yr2000 = 42.75e-6; p->kc25_coef = 404.9e-6; p->ko25_coef = 278.4e-3;
-  p->fnps = 0.15; p->theta_psii = 0.7; p->theta_ip = 0.95;
-  p->vcmaxha = 72000.0; p->jmaxha = 50000.0; p->tpuha = 72000.0; p->lmrha = 46390.0;
-  p->kcha = 79430.0; p->koha = 36380.0; p->cpha = 37830.0;
-  p->vcmaxhd = 200000.0; p->jmaxhd = 200000.0; p->tpuhd = 200000.0; p->lmrhd = 150650.0; p->lmrse = 490.0;
-  p->tpu25ratio = 0.167; p->kp25ratio = 20000.0;
-  p->vcmaxse_sf = 1.0; p->jmaxse_sf = 1.0; p->tpuse_sf = 1.0; p->jmax25top_sf = 1.0;
-  p->balance_skip_steps = -1;
-  p->npft_table = CTSM_MXPFT + 1;
-}
+extern "C" void ctsm_b200_default_params(ctsm_params_t* p) { ctsm_default_params_fill(p); }
 
 extern "C" int ctsm_b200_init(const ctsm_params_t* p, ctsm_b200_ctx** out) {
   if (!p || !out) return CTSM_ERR_BAD_ARG;
@@ -230,6 +190,16 @@ extern "C" int ctsm_b200_sync(ctsm_b200_ctx* ctx, ctsm_status_t* st) {
   ctsm_status_t local;
   decode_status(got, &local);
   if (st) *st = local;
+  if (!ctx->window_open && !ctx->bal_pending.empty()) {      // BalanceCheck calls issued since the last synchronisation
+    ctsm_status_t bst;
+    memset(&bst, 0, sizeof bst);
+    const int rb = balance_finish_pending(ctx, &bst);
+    if (local.code == CTSM_OK && rb != CTSM_OK) {
+      bst.n_warnings = local.n_warnings;
+      if (st) *st = bst;
+      return rb;
+    }
+  }
   return local.code;
 }
 
@@ -326,13 +296,11 @@ extern "C" int ctsm_b200_host_window_begin(ctsm_b200_ctx* ctx) {
 extern "C" int ctsm_b200_host_window_end(ctsm_b200_ctx* ctx, ctsm_status_t* st) {
   if (!ctx || !ctx->window_open) return CTSM_ERR_BAD_ARG;
   CUDA_TRY(cudaSetDevice(ctx->device));
-  ctx->window_open = false;
   CUDA_TRY(cudaStreamSynchronize(ctx->s_h2d));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->s_d2h));
-  const int rc = ctsm_b200_sync(ctx, st);
-  const int rb = balance_finish_pending(ctx, rc == CTSM_OK ? st : nullptr);
-  return rc != CTSM_OK ? rc : rb;
+  ctx->window_open = false;
+  return ctsm_b200_sync(ctx, st);        // device-side first failure, then the deferred BalanceCheck decisions
 }
 
 extern "C" int ctsm_b200_host_window_bytes(const ctsm_b200_ctx* ctx, uint64_t* h2d, uint64_t* d2h) {

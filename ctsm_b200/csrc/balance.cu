@@ -408,9 +408,12 @@ extern "C" int ctsm_b200_balancecheck(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   if (rc) return rc;
   Red* red = (Red*)ctx->arena_ints.p;
   void* pinned_slot = nullptr;
-  if (ctx->window_open) {
-    // resident window: calls are asynchronous and arena_ints is reused by the next call, so the maxima of this call get
-    // their own device + pinned slot (pooled in the context)
+  // Deferred decision: with device-resident state, and for host arrays inside a resident window, the call is
+  // asynchronous; the warn / abort decision is taken when the host next synchronises (ctsm_b200_sync /
+  // ctsm_b200_host_window_end), which is where the reference's endrun would surface to the caller anyway.
+  const bool deferred = ctx->window_open || mem == CTSM_MEM_DEVICE;
+  if (deferred) {
+    // arena_ints is reused by the next call, so the maxima of this call get their own device + pinned slot (pooled)
     if (ctx->bal_pinned_used == ctx->bal_pinned.size()) {
       void *q = nullptr, *dq = nullptr;
       CUDA_TRY(cudaMallocHost(&q, sizeof(Red)));
@@ -430,19 +433,25 @@ extern "C" int ctsm_b200_balancecheck(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   const int nmax = nc > np ? (nc > ng ? nc : ng) : (np > ng ? np : ng);
   if (nmax > 0) balance_loc_kernel<<<grid_for(nmax, 256), 256, 0, s>>>(d, g, red);
   ctx->launches += (nc > 0) + (ng > 0) + (np > 0) + (nmax > 0);
-  if (ctx->window_open) {
-    // resident window: the call stays asynchronous; the maxima travel to the pinned slot on the download stream (a copy
-    // on the compute stream would queue behind the bulk downloads in the copy engine and stall the next kernels) and
-    // ctsm_b200_host_window_end takes the warn / abort decision (balance_finish_pending)
-    cudaEvent_t ev;
-    rc = window_event(ctx, &ev);
-    if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(ev, s));
-    CUDA_TRY(cudaStreamWaitEvent(ctx->s_d2h, ev, 0));
-    CUDA_TRY(cudaMemcpyAsync(pinned_slot, red, sizeof(Red), cudaMemcpyDeviceToHost, ctx->s_d2h));
+  if (deferred) {
+    ctx->bal_last_dev = red;
+    if (ctx->window_open) {
+      // the maxima travel to the pinned slot on the download stream (a copy on the compute stream would queue behind
+      // the bulk downloads in the copy engine and stall the next kernels)
+      cudaEvent_t ev;
+      rc = window_event(ctx, &ev);
+      if (rc) return rc;
+      CUDA_TRY(cudaEventRecord(ev, s));
+      CUDA_TRY(cudaStreamWaitEvent(ctx->s_d2h, ev, 0));
+      CUDA_TRY(cudaMemcpyAsync(pinned_slot, red, sizeof(Red), cudaMemcpyDeviceToHost, ctx->s_d2h));
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(pinned_slot, red, sizeof(Red), cudaMemcpyDeviceToHost, s));
+    }
     ctx->bal_pending.push_back(ctsm_b200_ctx::BalPending{pinned_slot, rep, DAnstep});
-    rc = stage_end(ctx, fl, hf->alloc, *bounds);
-    if (rc) return rc;
+    if (mem != CTSM_MEM_DEVICE) {
+      rc = stage_end(ctx, fl, hf->alloc, *bounds);
+      if (rc) return rc;
+    }
     return finish_call(ctx, mem, st);
   }
   Red got;
@@ -466,8 +475,12 @@ int balance_finish_pending(ctsm_b200_ctx* ctx, ctsm_status_t* st) {
     if (rc != CTSM_OK && rc_all == CTSM_OK) { rc_all = rc; if (st) *st = local; }
   }
   ctx->bal_pending.clear();
+  ctx->bal_pinned_used = 0;
   return rc_all;
 }
+
+// device address of the 7 maxima (|residual| as doubles, order CTSM_BAL_*) the last deferred BalanceCheck call left
+extern "C" void* ctsm_b200_balance_device_maxima(ctsm_b200_ctx* ctx) { return ctx ? ctx->bal_last_dev : nullptr; }
 
 extern "C" int ctsm_b200_vert_tran_sink_hydstress(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_filterc,
                                                   const int32_t* filterc, const ctsm_plantsink_fields_t* hf, int mem,

@@ -87,6 +87,7 @@ struct ctsm_b200_ctx {
   struct BalPending { void* pinned; ctsm_balance_report_t* rep; int DAnstep; };
   std::vector<BalPending> bal_pending;
   std::vector<void*> bal_pinned, bal_dev; size_t bal_pinned_used = 0;
+  void* bal_last_dev = nullptr;
 };
 
 // records "name at file:line: text" for ctsm_b200_last_cuda_error() and maps the error to a CTSM_ERR_* code

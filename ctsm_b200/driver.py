@@ -205,6 +205,44 @@ class HotPath:
             C.byref(self.structs["balancecheck"]), self.danstep, self.mem, C.byref(self.balance_report), C.byref(st))
         if rc != 0:
             raise CtsmError(st, rc)
+        if getattr(self, "_dist", None) is not None and self.mem == abi.MEM_DEVICE:
+            self._reduce_balance()
+
+    # -- the one collective of the path: global BalanceCheck figures (an addition, the reference is clump-local)
+    def enable_global_balance(self, dist):
+        """After every BalanceCheck call, MAX-reduce its 7 residual maxima over the ranks of `dist` (NCCL) on a side
+        stream, straight from the device slot the kernels wrote (ctsm_b200_balance_device_maxima): no host round trip,
+        nothing on the compute stream waits for it."""
+        import torch
+        self._dist = dist
+        self._side = torch.cuda.Stream()
+        self._gmax = torch.zeros(7, dtype=torch.float64, device="cuda")
+        self._ext = torch.cuda.ExternalStream(self.ctx.stream_ptr)
+
+    def _reduce_balance(self):
+        import torch
+
+        class _Dev:                      # the library's device slot as a CUDA array (7 doubles)
+            def __init__(self, ptr):
+                self.__cuda_array_interface__ = {"shape": (7,), "typestr": "<f8", "data": (int(ptr), True), "version": 2}
+
+        ptr = self.ctx.L.ctsm_b200_balance_device_maxima(self.ctx.h)
+        if not ptr:
+            return
+        src = torch.as_tensor(_Dev(ptr), device="cuda")
+        self._side.wait_stream(self._ext)
+        with torch.cuda.stream(self._side):
+            local = src.clone()
+            self._dist.all_reduce(local, op=self._dist.ReduceOp.MAX)
+            torch.maximum(self._gmax, local, out=self._gmax)
+
+    def global_balance(self):
+        """max |residual| over all ranks and all BalanceCheck calls since enable_global_balance (order CTSM_BAL_*)."""
+        if getattr(self, "_dist", None) is None:
+            return None
+        import torch
+        self._side.synchronize()
+        return [float(x) for x in self._gmax.cpu()]
 
     def call(self, g):
         {"canopyfluxes": self.CanopyFluxes, "soiltemperature": self.SoilTemperature, "soilwater": self.SoilWater,

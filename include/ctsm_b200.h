@@ -404,12 +404,19 @@ int ctsm_b200_balancecheck_init(ctsm_b200_ctx* ctx);
 
 /* BalanceCheck(bounds, num_allc, filter_allc, ...) including EnergyBalanceCheck:
  * BalanceCheckMod.F90:445-857, 859-1119.  DAnstep = get_nstep_since_startup_or_lastDA_restart_or_pause().
- * Synchronous (the reference decides on the host whether to endrun).  Returns CTSM_ERR_BALANCE and fills
- * st like endrun(subgrid_index=, subgrid_level=) when a residual exceeds its abort threshold after the skip
- * steps; CTSM_ERR_BAD_ARG when called before ctsm_b200_balancecheck_init (the reference aborts likewise). */
+ * CTSM_MEM_HOST outside a window: synchronous; returns CTSM_ERR_BALANCE and fills st like endrun(subgrid_index=,
+ * subgrid_level=) when a residual exceeds its abort threshold after the skip steps.  CTSM_MEM_DEVICE, and host arrays
+ * inside a resident window: asynchronous; *report (which must stay valid until then) is filled and the same decision
+ * is returned by the next ctsm_b200_sync / ctsm_b200_host_window_end.  CTSM_ERR_BAD_ARG when called before
+ * ctsm_b200_balancecheck_init (the reference aborts likewise). */
 int ctsm_b200_balancecheck(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_allc, const int32_t* filter_allc,
                            const ctsm_balancecheck_fields_t* f, int DAnstep, int mem,
                            ctsm_balance_report_t* report, ctsm_status_t* st);
+
+/* Device address of the 7 maxima (doubles, |residual|, order CTSM_BAL_*) the last asynchronous BalanceCheck call of this
+ * context left, valid in stream order on ctsm_b200_stream: lets a multi-GPU host reduce the global figures with NCCL
+ * (MAX over ranks) without a host round trip.  NULL before the first such call. */
+void* ctsm_b200_balance_device_maxima(ctsm_b200_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -95,6 +95,7 @@ int oracle_begin_water_column_balance(const ctsm_bounds_t* bounds, int num_nolak
 /* oracle_filters.c (filterMod.F90:303-592) */
 int oracle_set_filters(const ctsm_bounds_t* bounds, const ctsm_filter_inputs_t* in, ctsm_filters_t* out);
 void oracle_set_num_threads(int n);
+void oracle_default_params(ctsm_params_t* p);
 int oracle_step_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump_t* clumps,
                        const ctsm_soiltemperature_fields_t* ft, const ctsm_soilwater_fields_t* fw,
                        const ctsm_canopyfluxes_fields_t* fc, int which);

@@ -85,11 +85,18 @@ def clump_for_gridcells(sg, g0, g1):
 
 def build(force: bool = False) -> str:
     srcs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(".c") or f.endswith(".h")]
-    srcs += [os.path.join(HERE, "..", "include", f) for f in ("ctsm_b200.h", "ctsm_b200_fields.def")]
+    srcs += [os.path.join(HERE, "..", "include", f) for f in ("ctsm_b200.h", "ctsm_b200_fields.def", "ctsm_b200_defaults.h")]
     stale = (not os.path.exists(LIB)) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs)
     if force or stale:
         subprocess.check_call(["make", "-s", "-C", HERE, "liboracle.so"])
     return LIB
+
+
+def default_params():
+    """ctsm_params_t with the clm6_0 defaults, from the oracle library alone (does not load libctsm_b200.so)."""
+    p = abi.Params()
+    lib().oracle_default_params(C.byref(p))
+    return p
 
 
 def lib():
@@ -128,6 +135,8 @@ def lib():
     L.oracle_balancecheck_skip_steps.argtypes = [C.c_double]
     L.oracle_vert_tran_sink_hydstress.argtypes = [B, C.c_int, i32p, C.POINTER(abi.STRUCTS["plantsink"])]
     L.oracle_num_threads.restype = C.c_int
+    L.oracle_default_params.argtypes = [P]
+    L.oracle_default_params.restype = None
     L.oracle_step_clumps.argtypes = [P, C.c_int, C.POINTER(Clump), C.POINTER(abi.STRUCTS["soiltemperature"]),
                                      C.POINTER(abi.STRUCTS["soilwater"]), C.POINTER(abi.STRUCTS["canopyfluxes"]), C.c_int]
     L.oracle_fullstep_clumps.argtypes = [P, C.c_int, C.POINTER(Clump), C.POINTER(abi.STRUCTS["soiltemperature"]),

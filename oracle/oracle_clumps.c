@@ -9,6 +9,10 @@
 #include <stdlib.h>
 #include <string.h>
 #include "oracle.h"
+#include "../include/ctsm_b200_defaults.h"
+
+/* the clm6_0 defaults of ctsm_params_t (shared header), so that the CPU arm never needs the CUDA library */
+void oracle_default_params(ctsm_params_t* p) { ctsm_default_params_fill(p); }
 
 int oracle_step_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump_t* clumps,
                        const ctsm_soiltemperature_fields_t* ft, const ctsm_soilwater_fields_t* fw,

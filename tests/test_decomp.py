@@ -62,6 +62,26 @@ def test_cost_balanced_slabs():
     assert np.array_equal(decomp.balanced_slabs(np.zeros(10), 3), [0, 3, 6, 10])
 
 
+def test_driver_slabs_partition_the_subgrid_and_cut_the_filters():
+    """driver.make_slabs (what bench.py's e2e clump loop and the multi-GPU layout use): contiguous, exhaustive, whole
+    gridcells, filters cut at the bounds in order, balanced by exposed-vegetation patches."""
+    from ctsm_b200 import driver, synthetic_canopy
+    sg, S = synthetic_canopy.make_full_case(300, seed=9)
+    for k in (1, 2, 3, 7):
+        slabs = driver.make_slabs(sg, k)
+        assert len(slabs) == k
+        assert slabs[0][0].begg == sg.bounds.begg and slabs[-1][0].endg == sg.bounds.endg
+        for (b0, _), (b1, _) in zip(slabs[:-1], slabs[1:]):
+            assert (b1.begg, b1.begc, b1.begp) == (b0.endg + 1, b0.endc + 1, b0.endp + 1)
+        for name, f in sg.filters.items():
+            assert np.array_equal(np.concatenate([fl[name] for _, fl in slabs]), f), name
+        for b, fl in slabs:
+            assert np.all(sg.col_gridcell[b.begc - 1:b.endc] >= b.begg) and np.all(sg.col_gridcell[b.begc - 1:b.endc] <= b.endg)
+            assert np.array_equal(fl["allc"], np.arange(b.begc, b.endc + 1))
+        cost = [len(fl["exposedvegp"]) for _, fl in slabs]
+        assert max(cost) - min(cost) <= 30          # one gridcell holds at most 15 patches
+
+
 def _worker(rank, world, port, q):
     import ctypes as C
     import torch.distributed as dist
