@@ -224,7 +224,7 @@ class HotPath:
 
         class _Dev:                      # the library's device slot as a CUDA array (7 doubles)
             def __init__(self, ptr):
-                self.__cuda_array_interface__ = {"shape": (7,), "typestr": "<f8", "data": (int(ptr), True), "version": 2}
+                self.__cuda_array_interface__ = {"shape": (7,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
 
         ptr = self.ctx.L.ctsm_b200_balance_device_maxima(self.ctx.h)
         if not ptr:

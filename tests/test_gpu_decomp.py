@@ -26,6 +26,14 @@ def _global_case():
 
 
 def _worker(rank, world, port, mode, q):
+    try:
+        _worker_body(rank, world, port, mode, q)
+    except BaseException:                      # a dead worker must not leave the parent waiting on the queue
+        import traceback
+        q.put(("error", rank, traceback.format_exc()))
+
+
+def _worker_body(rank, world, port, mode, q):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -81,9 +89,11 @@ def test_two_rank_cuda_run_matches_single_rank_cuda_run(mode):
     procs = [mpc.Process(target=_worker, args=(r, world, port, mode, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in procs]
+    res = [q.get(timeout=240) for _ in procs]
+    for r in res:
+        assert r[0] != "error", r[2]
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=60)
         assert p.exitcode == 0
     # single-process CUDA run over the whole grid
     sg, S = _global_case()
