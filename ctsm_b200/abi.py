@@ -34,6 +34,7 @@ LEV = {
     "SNO1": (-NLEVSNO + 1, NLEVSNO + 1),
     "VEGWCS": (1, NVEGWCS),
     "CAN": (1, NLEVCAN),
+    "LAK": (1, 10),
     "PHS2": (1, 2 * NLEVCAN),
     "NUMRAD": (1, 2),
     "PFT": (0, MXPFT + 1),
@@ -302,8 +303,12 @@ def lib():
                                                      C.POINTER(STRUCTS["plantsink"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_soilfluxes.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p,
                                        C.POINTER(STRUCTS["soilfluxes"]), C.c_int, C.POINTER(Status)]
-    L.ctsm_b200_begin_water_column_balance.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p,
+    L.ctsm_b200_begin_water_column_balance.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p,
                                                        C.POINTER(STRUCTS["waterbalance"]), C.c_double, C.c_int, C.POINTER(Status)]
+    L.ctsm_b200_water_gridcell_balance.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p,
+                                                   C.POINTER(STRUCTS["watergridbalance"]), C.c_double, C.c_int, C.c_int,
+                                                   C.POINTER(Status)]
+    L.ctsm_b200_water_gridcell_balance.restype = C.c_int
     L.ctsm_b200_begin_water_column_balance.restype = C.c_int
     L.ctsm_b200_set_filters.argtypes = [vp, C.POINTER(Bounds), C.POINTER(FilterInputs), C.POINTER(Filters), C.c_int]
     L.ctsm_b200_set_filters.restype = C.c_int

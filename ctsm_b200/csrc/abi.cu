@@ -155,7 +155,7 @@ static const char* message_for(int code) {
     case CTSM_ERR_BRENT: return "brent_PHS: root must be bracketed";
     case CTSM_ERR_QUADRATIC: return "quadratic solution error: b^2 - 4ac is negative";
     case CTSM_ERR_URBAN: return "urban column in filter is outside the ctsm_b200 hot path";
-    case CTSM_ERR_BALANCE: return "BalanceCheck: balance error exceeds threshold";
+    case CTSM_ERR_BALANCE: return "BalanceCheck: balance error exceeds threshold / c2g: sumwt is greater than 1.0";
     default: return "";
   }
 }
@@ -170,7 +170,8 @@ void decode_status(const DevStatus& ds, ctsm_status_t* st) {
   int info = (int)(ds.key & 0xffffff);
   if (info & 0x800000) info |= ~0xffffff;   // sign-extend
   st->info = info;
-  st->subgrid_level = (st->code == CTSM_ERR_FORC_HGT || st->code == CTSM_ERR_GS_NEG || st->code == CTSM_ERR_BRENT ||
+  if (st->code == CTSM_ERR_BALANCE) st->subgrid_level = CTSM_SUBGRID_GRIDCELL;     /* device-side: the c2g weight check */
+  else st->subgrid_level = (st->code == CTSM_ERR_FORC_HGT || st->code == CTSM_ERR_GS_NEG || st->code == CTSM_ERR_BRENT ||
                        st->code == CTSM_ERR_QUADRATIC) ? CTSM_SUBGRID_PATCH : CTSM_SUBGRID_COLUMN;
   snprintf(st->msg, sizeof st->msg, "%s", message_for(st->code));
 }

@@ -222,21 +222,22 @@ struct WaterBalanceDev {
 #undef CTSM_FIELDS_WATERBALANCE
 #undef CTSM_F
 };
+struct WaterGridDev {
+#define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) ctype* name;
+#define CTSM_FIELDS_WATERGRIDBALANCE
+#include "../../include/ctsm_b200_fields.def"
+#undef CTSM_FIELDS_WATERGRIDBALANCE
+#undef CTSM_F
+};
 
 namespace {
-// BeginWaterColumnBalanceSingle (BalanceCheckMod.F90:262-330) -> ComputeLiqIceMassNonLake (TotalWaterAndHeatMod.F90:200-326)
-// + AccumulateSoilLiqIceMassNonLake (:329-393) + CalculateTotalH2osno: one thread per non-lake column; level sums
-// ascending (the reference's level-outer / column-inner sweep visits a column's levels in that order), canopy water by
-// p2c over the column's contiguous patches.  HBM bound: 2 x 37 level reads + 25 excess-ice reads per column, coalesced.
-__global__ void __launch_bounds__(128)
-water_mass_kernel(WaterBalanceDev f, double aquifer_water_baseline, int begc0, int ldc_, int begp0, int numc,
-                  const int32_t* __restrict__ filterc, DevStatus* ds) {
-  const int fc = blockIdx.x * blockDim.x + threadIdx.x;
-  if (fc >= numc) return;
-  const int c1 = filterc[fc], cc = c1 - begc0;
-  const size_t ldc = (size_t)ldc_;
-  const int lt = f.lun_itype[cc];
-  if (lt >= CTSM_ISTURB_MIN && lt <= CTSM_ISTURB_MAX) { report_failure(ds, c1, CTSM_ERR_URBAN, 0); return; }
+// ComputeLiqIceMassNonLake (TotalWaterAndHeatMod.F90:200-326) + AccumulateSoilLiqIceMassNonLake (:329-393) for one non-urban
+// column: level sums ascending (the reference's level-outer / column-inner sweep visits a column's levels in that order),
+// canopy water by p2c over the column's contiguous patches.  HBM bound: 2 x 37 level reads + 25 excess-ice reads per
+// column, coalesced.  F = WaterBalanceDev or WaterGridDev (same member names).
+template <class F>
+__device__ __forceinline__ void water_mass_nonlake(const F& f, int cc, size_t ldc, int begp0, double aquifer_water_baseline,
+                                                   double& liquid_mass, double& ice_mass) {
   double liqcan_col = 0.0, snocan_col = 0.0;
   const int pi = f.patchi[cc], pf = f.patchf[cc];
   for (int p1 = pi; p1 <= pf; ++p1) {
@@ -247,18 +248,14 @@ water_mass_kernel(WaterBalanceDev f, double aquifer_water_baseline, int begc0, i
       snocan_col = snocan_col + f.snocan[pp] * wt;
     }
   }
-  double liquid_mass = 0.0, ice_mass = 0.0;
+  liquid_mass = 0.0; ice_mass = 0.0;
   liquid_mass = liquid_mass + liqcan_col + f.total_plant_stored_h2o[cc];
   ice_mass = ice_mass + snocan_col;
-  const double h2osno_no_layers = f.h2osno_no_layers[cc];
-  ice_mass = ice_mass + h2osno_no_layers;
+  ice_mass = ice_mass + f.h2osno_no_layers[cc];
   const int snl = f.snl[cc];
-  double h2osno = h2osno_no_layers;
   for (int j = snl + 1; j <= 0; ++j) {
-    const double liq = f.h2osoi_liq[(size_t)(j - SNOSOI_LO) * ldc + cc], ice = f.h2osoi_ice[(size_t)(j - SNOSOI_LO) * ldc + cc];
-    liquid_mass = liquid_mass + liq;
-    ice_mass = ice_mass + ice;
-    h2osno = h2osno + ice + liq;
+    liquid_mass = liquid_mass + f.h2osoi_liq[(size_t)(j - SNOSOI_LO) * ldc + cc];
+    ice_mass = ice_mass + f.h2osoi_ice[(size_t)(j - SNOSOI_LO) * ldc + cc];
   }
   if (f.col_hydrologically_active[cc]) liquid_mass = liquid_mass + (f.wa[cc] - aquifer_water_baseline);
   liquid_mass = liquid_mass + f.h2osfc[cc];
@@ -266,18 +263,119 @@ water_mass_kernel(WaterBalanceDev f, double aquifer_water_baseline, int begc0, i
     liquid_mass = liquid_mass + f.h2osoi_liq[(size_t)(j - SNOSOI_LO) * ldc + cc];
     ice_mass = ice_mass + f.h2osoi_ice[(size_t)(j - SNOSOI_LO) * ldc + cc] + f.excess_ice[(size_t)(j - 1) * ldc + cc];
   }
+}
+// snow and soil layers of a lake column: ComputeLiqIceMassLake :449-462
+template <class F>
+__device__ __forceinline__ void water_mass_lake_layers(const F& f, int cc, size_t ldc, double& liquid_mass, double& ice_mass) {
+  ice_mass = ice_mass + f.h2osno_no_layers[cc];
+  const int snl = f.snl[cc];
+  for (int j = snl + 1; j <= 0; ++j) {
+    liquid_mass = liquid_mass + f.h2osoi_liq[(size_t)(j - SNOSOI_LO) * ldc + cc];
+    ice_mass = ice_mass + f.h2osoi_ice[(size_t)(j - SNOSOI_LO) * ldc + cc];
+  }
+  for (int j = 1; j <= NLEVGRND; ++j) {
+    liquid_mass = liquid_mass + f.h2osoi_liq[(size_t)(j - SNOSOI_LO) * ldc + cc];
+    ice_mass = ice_mass + f.h2osoi_ice[(size_t)(j - SNOSOI_LO) * ldc + cc];
+  }
+}
+template <class F>
+__device__ __forceinline__ double total_h2osno(const F& f, int cc, size_t ldc) {      // CalculateTotalH2osno, WaterStateType.F90:887-896
+  double t = f.h2osno_no_layers[cc];
+  const int snl = f.snl[cc];
+  for (int j = snl + 1; j <= 0; ++j)
+    t = t + f.h2osoi_ice[(size_t)(j - SNOSOI_LO) * ldc + cc] + f.h2osoi_liq[(size_t)(j - SNOSOI_LO) * ldc + cc];
+  return t;
+}
+
+// BeginWaterColumnBalanceSingle (BalanceCheckMod.F90:353-442): one thread per column of the non-lake filter, then of the lake filter
+__global__ void __launch_bounds__(128)
+water_mass_kernel(WaterBalanceDev f, double aquifer_water_baseline, int begc0, int ldc_, int begp0, int numc,
+                  const int32_t* __restrict__ filterc, int lake, DevStatus* ds) {
+  const int fc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fc >= numc) return;
+  const int c1 = filterc[fc], cc = c1 - begc0;
+  const size_t ldc = (size_t)ldc_;
+  double liquid_mass = 0.0, ice_mass = 0.0;
+  if (lake) {
+    water_mass_lake_layers(f, cc, ldc, liquid_mass, ice_mass);
+  } else {
+    const int lt = f.lun_itype[cc];
+    if (lt >= CTSM_ISTURB_MIN && lt <= CTSM_ISTURB_MAX) { report_failure(ds, c1, CTSM_ERR_URBAN, 0); return; }
+    water_mass_nonlake(f, cc, ldc, begp0, aquifer_water_baseline, liquid_mass, ice_mass);
+  }
   f.begwb[cc] = liquid_mass + ice_mass;
-  f.h2osno_old[cc] = h2osno;
+  f.h2osno_old[cc] = total_h2osno(f, cc, ldc);
+}
+
+// WaterGridcellBalanceSingle (BalanceCheckMod.F90:212-350), step 1: column water mass with the dynbal baselines subtracted
+// and, for lake columns, the lake water added (AccumulateLiqIceMassLake, TotalWaterAndHeatMod.F90:536-544)
+__global__ void __launch_bounds__(128)
+watergrid_col_kernel(WaterGridDev f, double aquifer_water_baseline, int begc0, int ldc_, int begp0, int begc_call, int numc,
+                     const int32_t* __restrict__ filterc, int lake, double* __restrict__ wb_col, DevStatus* ds) {
+  const int fc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fc >= numc) return;
+  const int c1 = filterc[fc], cc = c1 - begc0;
+  const size_t ldc = (size_t)ldc_;
+  double liquid_mass = 0.0, ice_mass = 0.0;
+  if (lake) {
+    liquid_mass = liquid_mass - f.dynbal_baseline_liq[cc];
+    ice_mass = ice_mass - f.dynbal_baseline_ice[cc];
+    for (int j = 1; j <= CTSM_NLEVLAK; ++j) {
+      const double dzl = f.dz_lake[(size_t)(j - 1) * ldc + cc], fr = f.lake_icefrac[(size_t)(j - 1) * ldc + cc];
+      const double h2olak_liq = dzl * cst::denh2o * (1 - fr) * 1.0;
+      const double h2olak_ice = dzl * cst::denh2o * fr * 1.0;
+      liquid_mass = liquid_mass + h2olak_liq;
+      ice_mass = ice_mass + h2olak_ice;
+    }
+    water_mass_lake_layers(f, cc, ldc, liquid_mass, ice_mass);
+  } else {
+    const int lt = f.lun_itype[cc];
+    if (lt >= CTSM_ISTURB_MIN && lt <= CTSM_ISTURB_MAX) { report_failure(ds, c1, CTSM_ERR_URBAN, 0); return; }
+    water_mass_nonlake(f, cc, ldc, begp0, aquifer_water_baseline, liquid_mass, ice_mass);
+    liquid_mass = liquid_mass - f.dynbal_baseline_liq[cc];
+    ice_mass = ice_mass - f.dynbal_baseline_ice[cc];
+  }
+  wb_col[c1 - begc_call] = liquid_mass + ice_mass;
+}
+// step 2: c2g (subgridAveMod.F90:791-816, scale factors 1 off the urban landunits), minus the dribblers' remainders
+__global__ void __launch_bounds__(128)
+watergrid_grc_kernel(WaterGridDev f, int begg0, int begc0, int begg, int endg, int begc, int endc, int flag_endwb,
+                     const double* __restrict__ wb_col, DevStatus* ds) {
+  const int g1 = begg + blockIdx.x * blockDim.x + threadIdx.x;
+  if (g1 > endg) return;
+  const int gg = g1 - begg0;
+  double garr = 1.0e36, sumwt = 0.0;
+  for (int c1 = f.grc_coli[gg]; c1 <= f.grc_colf[gg]; ++c1) {
+    if (c1 < begc || c1 > endc) continue;
+    const int cc = c1 - begc0;
+    const double wt = f.wtgcell[cc];
+    if (f.col_active[cc] && wt != 0.0) {
+      const double v = wb_col[c1 - begc];
+      if (v != 1.0e36) {
+        if (sumwt == 0.0) garr = 0.0;
+        garr = garr + v * 1.0 * 1.0 * wt;
+        sumwt = sumwt + wt;
+      }
+    }
+  }
+  if (sumwt > 1.0 + 1.e-6) report_failure(ds, g1, CTSM_ERR_BALANCE, 0);
+  else if (sumwt != 0.0) garr = garr / sumwt;
+  const double wb = garr - f.qflx_liq_dynbal_left_to_dribble[gg] - f.qflx_ice_dynbal_left_to_dribble[gg];
+  if (flag_endwb) f.endwb_grc[gg] = wb - 0.0;
+  else f.begwb_grc[gg] = wb;
 }
 }  // namespace
 
 extern "C" int ctsm_b200_begin_water_column_balance(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_nolakec,
-                                                    const int32_t* filter_nolakec, const ctsm_waterbalance_fields_t* hf,
-                                                    double aquifer_water_baseline, int mem, ctsm_status_t* st) {
-  if (!ctx || !bounds || !hf || num_nolakec < 0 || (num_nolakec > 0 && !filter_nolakec)) return CTSM_ERR_BAD_ARG;
+                                                    const int32_t* filter_nolakec, int num_lakec, const int32_t* filter_lakec,
+                                                    const ctsm_waterbalance_fields_t* hf, double aquifer_water_baseline, int mem,
+                                                    ctsm_status_t* st) {
+  if (!ctx || !bounds || !hf || num_nolakec < 0 || (num_nolakec > 0 && !filter_nolakec) || num_lakec < 0 ||
+      (num_lakec > 0 && !filter_lakec))
+    return CTSM_ERR_BAD_ARG;
   CUDA_TRY(cudaSetDevice(ctx->device));
   WaterBalanceDev d;
-  const int32_t* dfilter = filter_nolakec;
+  const int32_t *dfilter = filter_nolakec, *dlake = filter_lakec;
   std::vector<StageField> fl;
 #define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) \
   d.name = hf->name;                                        \
@@ -292,12 +390,71 @@ extern "C" int ctsm_b200_begin_water_column_balance(ctsm_b200_ctx* ctx, const ct
     if (rc) return rc;
     rc = stage_filter(ctx, ctx->arena_filter0, filter_nolakec, num_nolakec, &dfilter);
     if (rc) return rc;
+    rc = stage_filter(ctx, ctx->arena_filter1, filter_lakec, num_lakec, &dlake);
+    if (rc) return rc;
   }
+  const int begc0 = hf->alloc.begc, ldc = hf->alloc.endc - hf->alloc.begc + 1, begp0 = hf->alloc.begp;
   if (num_nolakec > 0) {
-    water_mass_kernel<<<grid_for(num_nolakec, 128), 128, 0, ctx->stream>>>(
-        d, aquifer_water_baseline, hf->alloc.begc, hf->alloc.endc - hf->alloc.begc + 1, hf->alloc.begp, num_nolakec, dfilter,
-        ctx->d_status);
+    water_mass_kernel<<<grid_for(num_nolakec, 128), 128, 0, ctx->stream>>>(d, aquifer_water_baseline, begc0, ldc, begp0,
+                                                                            num_nolakec, dfilter, 0, ctx->d_status);
     ctx->launches++;
+  }
+  if (num_lakec > 0) {
+    water_mass_kernel<<<grid_for(num_lakec, 128), 128, 0, ctx->stream>>>(d, aquifer_water_baseline, begc0, ldc, begp0,
+                                                                          num_lakec, dlake, 1, ctx->d_status);
+    ctx->launches++;
+  }
+  if (mem != CTSM_MEM_DEVICE) {
+    int rc = stage_end(ctx, fl, hf->alloc, *bounds);
+    if (rc) return rc;
+  }
+  return finish_call(ctx, mem, st);
+}
+
+extern "C" int ctsm_b200_water_gridcell_balance(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_nolakec,
+                                                const int32_t* filter_nolakec, int num_lakec, const int32_t* filter_lakec,
+                                                const ctsm_watergridbalance_fields_t* hf, double aquifer_water_baseline,
+                                                int flag_endwb, int mem, ctsm_status_t* st) {
+  if (!ctx || !bounds || !hf || num_nolakec < 0 || (num_nolakec > 0 && !filter_nolakec) || num_lakec < 0 ||
+      (num_lakec > 0 && !filter_lakec))
+    return CTSM_ERR_BAD_ARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  WaterGridDev d;
+  const int32_t *dfilter = filter_nolakec, *dlake = filter_lakec;
+  std::vector<StageField> fl;
+#define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) \
+  d.name = hf->name;                                        \
+  fl.push_back(StageField{(void**)&d.name, (void*)hf->name, (int)sizeof(ctype), SUB_##sub, lev_shape(#lev).n, INTENT_##intent});
+#define CTSM_FIELDS_WATERGRIDBALANCE
+#include "../../include/ctsm_b200_fields.def"
+#undef CTSM_FIELDS_WATERGRIDBALANCE
+#undef CTSM_F
+  for (auto& s : fl) if (!s.host_ptr) return CTSM_ERR_BAD_ARG;
+  if (mem != CTSM_MEM_DEVICE) {
+    int rc = stage_begin(ctx, fl, hf->alloc, *bounds, mem == CTSM_MEM_HOST);
+    if (rc) return rc;
+    rc = stage_filter(ctx, ctx->arena_filter0, filter_nolakec, num_nolakec, &dfilter);
+    if (rc) return rc;
+    rc = stage_filter(ctx, ctx->arena_filter1, filter_lakec, num_lakec, &dlake);
+    if (rc) return rc;
+  }
+  const int ncb = bounds->endc - bounds->begc + 1, ngb = bounds->endg - bounds->begg + 1;
+  if (ncb > 0 && ngb > 0) {
+    int rc = arena_reserve(ctx, ctx->arena_scratch, sizeof(double) * (size_t)ncb);
+    if (rc) return rc;
+    double* wb_col = (double*)ctx->arena_scratch.p;
+    cudaStream_t s = ctx->stream;
+    CUDA_TRY(cudaMemsetAsync(wb_col, 0, sizeof(double) * (size_t)ncb, s));      // columns in neither filter
+    const int begc0 = hf->alloc.begc, ldc = hf->alloc.endc - hf->alloc.begc + 1, begp0 = hf->alloc.begp;
+    if (num_nolakec > 0)
+      watergrid_col_kernel<<<grid_for(num_nolakec, 128), 128, 0, s>>>(d, aquifer_water_baseline, begc0, ldc, begp0, bounds->begc,
+                                                                      num_nolakec, dfilter, 0, wb_col, ctx->d_status);
+    if (num_lakec > 0)
+      watergrid_col_kernel<<<grid_for(num_lakec, 128), 128, 0, s>>>(d, aquifer_water_baseline, begc0, ldc, begp0, bounds->begc,
+                                                                    num_lakec, dlake, 1, wb_col, ctx->d_status);
+    watergrid_grc_kernel<<<grid_for(ngb, 128), 128, 0, s>>>(d, hf->alloc.begg, begc0, bounds->begg, bounds->endg, bounds->begc,
+                                                            bounds->endc, flag_endwb, wb_col, ctx->d_status);
+    ctx->launches += (num_nolakec > 0) + (num_lakec > 0) + 1;
   }
   if (mem != CTSM_MEM_DEVICE) {
     int rc = stage_end(ctx, fl, hf->alloc, *bounds);

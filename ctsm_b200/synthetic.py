@@ -137,6 +137,7 @@ def build_filters(sg: Subgrid) -> None:
     c1 = np.arange(1, sg.ncol + 1, dtype=np.int32)
     p1 = np.arange(1, sg.npatch + 1, dtype=np.int32)
     sg.filters["nolakec"] = c1[sg.col_active & ~lake_c]
+    sg.filters["lakec"] = c1[sg.col_active & lake_c]
     hyd = np.isin(sg.col_lun_itype, (ISTSOIL, abi.ISTCROP))
     sg.filters["hydrologyc"] = c1[sg.col_active & hyd]
     lake_p = lake_c[sg.patch_column - 1]

@@ -337,6 +337,31 @@ def waterbalance_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Gen
         S[k] = np.ascontiguousarray(v)
 
 
+def watergrid_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator) -> None:
+    """Adds the fields of group `watergridbalance` (WaterGridcellBalance, BalanceCheckMod.F90:132): lake geometry and ice
+    fraction, dynbal baselines, gridcell -> column ranges and weights, what the dynbal dribblers still hold."""
+    waterbalance_state(sg, S, rng)
+    nc, ng = sg.ncol, sg.ngrc
+    first = np.searchsorted(sg.col_gridcell, np.arange(1, ng + 1), side="left")
+    last = np.searchsorted(sg.col_gridcell, np.arange(1, ng + 1), side="right") - 1
+    S["grc_coli"], S["grc_colf"] = (first + 1).astype(np.int32), (last + 1).astype(np.int32)
+    S["col_active"] = sg.col_active.astype(np.int32)
+    w = rng.uniform(0.2, 1.0, nc)
+    tot = np.add.reduceat(w, first)
+    S["wtgcell"] = w / tot[sg.col_gridcell - 1]                    # column weights on the gridcell, summing to 1
+    S["dynbal_baseline_liq"] = rng.uniform(0.0, 50.0, nc) * (rng.random(nc) < 0.3)
+    S["dynbal_baseline_ice"] = rng.uniform(0.0, 20.0, nc) * (rng.random(nc) < 0.3)
+    S["dz_lake"] = np.ascontiguousarray(np.broadcast_to(np.array([0.1, 1.0, 2.0, 3.0, 4.0, 5.0, 7.0, 7.0, 10.45, 10.45])[:, None], (10, nc)).copy())
+    S["lake_icefrac"] = np.clip(rng.uniform(-0.5, 1.2, (10, nc)), 0.0, 1.0)
+    S["qflx_liq_dynbal_left_to_dribble"] = rng.uniform(-5.0, 5.0, ng) * (rng.random(ng) < 0.2)
+    S["qflx_ice_dynbal_left_to_dribble"] = rng.uniform(-1.0, 1.0, ng) * (rng.random(ng) < 0.2)
+    S["begwb_grc"] = np.full(ng, 1.0e36)
+    S["endwb_grc"] = np.full(ng, 1.0e36)
+    for k in ("grc_coli", "grc_colf", "col_active", "wtgcell", "dynbal_baseline_liq", "dynbal_baseline_ice", "dz_lake",
+              "lake_icefrac", "qflx_liq_dynbal_left_to_dribble", "qflx_ice_dynbal_left_to_dribble"):
+        S[k] = np.ascontiguousarray(S[k])
+
+
 def make_ensemble(sg: Subgrid, S: Dict[str, np.ndarray], nmember: int, rng: np.random.Generator, spread: float = 0.2):
     """Perturbed-parameter ensemble through the PFT tables (BASELINE config 5): the grid is split into `nmember` equal
     runs of gridcells, member m's patches get itype = m*(mxpft+1) + pft, and every pft_* table is extended to

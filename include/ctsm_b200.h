@@ -13,6 +13,7 @@
  *   ctsm_b200_set_filters        src/main/filterMod.F90:303   (setFiltersOneGroup)
  *   ctsm_b200_set_exposedvegp_filter  src/main/filterMod.F90:595
  *   ctsm_b200_begin_water_column_balance  src/biogeophys/BalanceCheckMod.F90:171  (+ TotalWaterAndHeatMod.F90:92)
+ *   ctsm_b200_water_gridcell_balance      src/biogeophys/BalanceCheckMod.F90:132  (+ TotalWaterAndHeatMod.F90:92,144)
  *   ctsm_b200_balancecheck       src/biogeophys/BalanceCheckMod.F90:445,859
  *   ctsm_b200_soilfluxes         src/biogeophys/SoilFluxesMod.F90:37   (+ p2c, src/main/subgridAveMod.F90:292)
  *   ctsm_b200_patch2col          src/main/clm_driver.F90:1655          (clm_drv_patch2col)
@@ -40,7 +41,7 @@
 extern "C" {
 #endif
 
-#define CTSM_B200_ABI_VERSION 2
+#define CTSM_B200_ABI_VERSION 3
 
 /* fixed vertical structure the kernels are compiled for (clm_varpar.F90:43-54,
  * 290-292; namelist_defaults_ctsm.xml:254,511).  ctsm_b200_init refuses any
@@ -50,6 +51,7 @@ extern "C" {
 #define CTSM_NLEVSOI 20
 #define CTSM_NVEGWCS 4
 #define CTSM_NLEVCAN 1
+#define CTSM_NLEVLAK 10
 #define CTSM_MXPFT 78
 
 /* decompMod.F90:60-68 */
@@ -201,6 +203,13 @@ typedef struct ctsm_waterbalance_fields_t {
 #include "ctsm_b200_fields.def"
 #undef CTSM_FIELDS_WATERBALANCE
 } ctsm_waterbalance_fields_t;
+
+typedef struct ctsm_watergridbalance_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_WATERGRIDBALANCE
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_WATERGRIDBALANCE
+} ctsm_watergridbalance_fields_t;
 
 typedef struct ctsm_balancecheck_fields_t {
   ctsm_bounds_t alloc;
@@ -393,11 +402,23 @@ int ctsm_b200_patch2col(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num
                         ctsm_status_t* st);
 
 /* BeginWaterColumnBalance(bounds, num_nolakec, filter_nolakec, num_lakec, filter_lakec, ...): BalanceCheckMod.F90:171,
- * call site clm_driver.F90:414.  Bulk water, non-lake columns (the lake filter of the reference's dummy list is empty on
- * this path), use_aquifer_layer = .false. (clm5/clm6 default).  aquifer_water_baseline: waterstate_inst scalar. */
+ * call site clm_driver.F90:414.  Bulk water, use_aquifer_layer = .false. (clm5/clm6 default).  Non-lake columns get
+ * ComputeWaterMassNonLake, lake columns ComputeWaterMassLake without the lake water itself (TotalWaterAndHeatMod.F90:144,
+ * 395-460: snow and soil layers only), both get h2osno_old.  aquifer_water_baseline: waterstate_inst scalar. */
 int ctsm_b200_begin_water_column_balance(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_nolakec,
-                                         const int32_t* filter_nolakec, const ctsm_waterbalance_fields_t* f,
-                                         double aquifer_water_baseline, int mem, ctsm_status_t* st);
+                                         const int32_t* filter_nolakec, int num_lakec, const int32_t* filter_lakec,
+                                         const ctsm_waterbalance_fields_t* f, double aquifer_water_baseline, int mem,
+                                         ctsm_status_t* st);
+
+/* WaterGridcellBalance(bounds, num_nolakec, filter_nolakec, num_lakec, filter_lakec, water_inst, lakestate_inst,
+ * use_aquifer_layer, flag): BalanceCheckMod.F90:132-350, call sites clm_driver.F90:331 ('begwb') and :1411 ('endwb').
+ * Bulk water, use_aquifer_layer = .false., hillslope routing off.  flag_endwb = 0 writes begwb_grc, 1 writes endwb_grc.
+ * The two dribbler amounts are inputs (the dribblers themselves belong to dynamic land cover, outside the hot path).
+ * c2g failure (sum of column weights > 1) is reported like the reference's endrun: CTSM_ERR_BALANCE at the gridcell. */
+int ctsm_b200_water_gridcell_balance(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_nolakec,
+                                     const int32_t* filter_nolakec, int num_lakec, const int32_t* filter_lakec,
+                                     const ctsm_watergridbalance_fields_t* f, double aquifer_water_baseline, int flag_endwb,
+                                     int mem, ctsm_status_t* st);
 
 /* BalanceCheckInit(): BalanceCheckMod.F90:74-95; skip_steps = max(2, nint(3600/dtime)) + 1.  Returns skip_steps. */
 int ctsm_b200_balancecheck_init(ctsm_b200_ctx* ctx);

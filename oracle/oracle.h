@@ -91,7 +91,11 @@ int oracle_soilfluxes(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int
 int oracle_patch2col(const ctsm_bounds_t* bounds, int num_allc, const int32_t* filter_allc, int num_nolakec,
                      const int32_t* filter_nolakec, const ctsm_patch2col_fields_t* f);
 int oracle_begin_water_column_balance(const ctsm_bounds_t* bounds, int num_nolakec, const int32_t* filter_nolakec,
+                                      int num_lakec, const int32_t* filter_lakec,
                                       const ctsm_waterbalance_fields_t* f, double aquifer_water_baseline, ctsm_status_t* st);
+int oracle_water_gridcell_balance(const ctsm_bounds_t* bounds, int num_nolakec, const int32_t* filter_nolakec, int num_lakec,
+                                  const int32_t* filter_lakec, const ctsm_watergridbalance_fields_t* f,
+                                  double aquifer_water_baseline, int flag_endwb, ctsm_status_t* st);
 /* oracle_filters.c (filterMod.F90:303-592) */
 int oracle_set_filters(const ctsm_bounds_t* bounds, const ctsm_filter_inputs_t* in, ctsm_filters_t* out);
 void oracle_set_num_threads(int n);

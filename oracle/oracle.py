@@ -144,7 +144,10 @@ def lib():
                                          C.POINTER(abi.STRUCTS["plantsink"]), C.POINTER(abi.STRUCTS["balancecheck"]),
                                          C.POINTER(abi.STRUCTS["soilfluxes"]), C.POINTER(abi.STRUCTS["patch2col"]),
                                          C.c_int, C.c_int]
-    L.oracle_begin_water_column_balance.argtypes = [B, C.c_int, i32p, C.POINTER(abi.STRUCTS["waterbalance"]), C.c_double, S]
+    L.oracle_begin_water_column_balance.argtypes = [B, C.c_int, i32p, C.c_int, i32p, C.POINTER(abi.STRUCTS["waterbalance"]),
+                                                    C.c_double, S]
+    L.oracle_water_gridcell_balance.argtypes = [B, C.c_int, i32p, C.c_int, i32p, C.POINTER(abi.STRUCTS["watergridbalance"]),
+                                                C.c_double, C.c_int, S]
     L.oracle_set_filters.argtypes = [B, C.POINTER(abi.FilterInputs), C.POINTER(abi.Filters)]
     L.oracle_patch2col.argtypes = [B, C.c_int, i32p, C.c_int, i32p, C.POINTER(abi.STRUCTS["patch2col"])]
     L.oracle_soilfluxes.argtypes = [P, B, C.c_int, i32p, C.c_int, i32p, C.POINTER(abi.STRUCTS["soilfluxes"]), S]

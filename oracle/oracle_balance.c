@@ -247,16 +247,71 @@ int oracle_vert_tran_sink_hydstress(const ctsm_bounds_t* bounds, int num_filterc
   return 0;
 }
 
-/* BeginWaterColumnBalanceSingle (BalanceCheckMod.F90:262-330, use_aquifer_layer = .false.) =
- * ComputeWaterMassNonLake -> ComputeLiqIceMassNonLake (TotalWaterAndHeatMod.F90:200-326, p2c of the canopy water,
- * subtract_dynbal_baselines = .false.) -> AccumulateSoilLiqIceMassNonLake (:329-393, level-outer / column-inner, i.e.
- * ascending levels per column) + CalculateTotalH2osno (WaterStateType.F90:887-896).  Non-urban columns. */
+/* ComputeLiqIceMassNonLake (TotalWaterAndHeatMod.F90:200-326) + AccumulateSoilLiqIceMassNonLake (:329-393, level-outer /
+ * column-inner, i.e. ascending levels per column) for one non-urban column; canopy water by p2c (subgridAveMod.F90:312-318). */
+#define WB_FIELDS(F) \
+  const int32_t *snl_ = (F)->snl, *hyd_ = (F)->col_hydrologically_active, *patchi_ = (F)->patchi, *patchf_ = (F)->patchf, \
+                *pact_ = (F)->patch_active; \
+  const double *liq_ = (F)->h2osoi_liq, *ice_ = (F)->h2osoi_ice, *exice_ = (F)->excess_ice, *h2osfc_ = (F)->h2osfc, \
+               *noly_ = (F)->h2osno_no_layers, *wa_ = (F)->wa, *tps_ = (F)->total_plant_stored_h2o, *wtcol_ = (F)->wtcol, \
+               *liqcan_ = (F)->liqcan, *snocan_ = (F)->snocan
+static void water_mass_nonlake(int cc, int begp0, size_t ldc, const int32_t* snl_, const int32_t* hyd_, const int32_t* patchi_,
+                               const int32_t* patchf_, const int32_t* pact_, const double* liq_, const double* ice_,
+                               const double* exice_, const double* h2osfc_, const double* noly_, const double* wa_,
+                               const double* tps_, const double* wtcol_, const double* liqcan_, const double* snocan_,
+                               double aquifer_water_baseline, double* liquid_out, double* ice_out) {
+  double liqcan_col = 0.0, snocan_col = 0.0;
+  for (int p = patchi_[cc]; p <= patchf_[cc]; ++p)
+    if (pact_[p - begp0]) liqcan_col = liqcan_col + liqcan_[p - begp0] * wtcol_[p - begp0];
+  for (int p = patchi_[cc]; p <= patchf_[cc]; ++p)
+    if (pact_[p - begp0]) snocan_col = snocan_col + snocan_[p - begp0] * wtcol_[p - begp0];
+  double liquid_mass = 0.0, ice_mass = 0.0;
+  liquid_mass = liquid_mass + liqcan_col + tps_[cc];
+  ice_mass = ice_mass + snocan_col;
+  ice_mass = ice_mass + noly_[cc];
+  const int snl = snl_[cc];
+  for (int j = snl + 1; j <= 0; ++j) {
+    liquid_mass = liquid_mass + liq_[(size_t)(j - SNOSOI_LO) * ldc + cc];
+    ice_mass = ice_mass + ice_[(size_t)(j - SNOSOI_LO) * ldc + cc];
+  }
+  if (hyd_[cc]) liquid_mass = liquid_mass + (wa_[cc] - aquifer_water_baseline);
+  liquid_mass = liquid_mass + h2osfc_[cc];
+  for (int j = 1; j <= CTSM_NLEVGRND; ++j) {
+    liquid_mass = liquid_mass + liq_[(size_t)(j - SNOSOI_LO) * ldc + cc];
+    ice_mass = ice_mass + ice_[(size_t)(j - SNOSOI_LO) * ldc + cc] + exice_[(size_t)(j - 1) * ldc + cc];
+  }
+  *liquid_out = liquid_mass; *ice_out = ice_mass;
+}
+/* snow and soil layers of a lake column: ComputeLiqIceMassLake :449-462 */
+static void water_mass_lake_layers(int cc, size_t ldc, const int32_t* snl_, const double* liq_, const double* ice_,
+                                   const double* noly_, double* liquid_mass, double* ice_mass) {
+  *ice_mass = *ice_mass + noly_[cc];
+  for (int j = snl_[cc] + 1; j <= 0; ++j) {
+    *liquid_mass = *liquid_mass + liq_[(size_t)(j - SNOSOI_LO) * ldc + cc];
+    *ice_mass = *ice_mass + ice_[(size_t)(j - SNOSOI_LO) * ldc + cc];
+  }
+  for (int j = 1; j <= CTSM_NLEVGRND; ++j) {
+    *liquid_mass = *liquid_mass + liq_[(size_t)(j - SNOSOI_LO) * ldc + cc];
+    *ice_mass = *ice_mass + ice_[(size_t)(j - SNOSOI_LO) * ldc + cc];
+  }
+}
+static double total_h2osno(int cc, size_t ldc, const int32_t* snl_, const double* liq_, const double* ice_, const double* noly_) {
+  double t = noly_[cc];                                                  /* CalculateTotalH2osno, WaterStateType.F90:887-896 */
+  for (int j = snl_[cc] + 1; j <= 0; ++j) t = t + ice_[(size_t)(j - SNOSOI_LO) * ldc + cc] + liq_[(size_t)(j - SNOSOI_LO) * ldc + cc];
+  return t;
+}
+
+/* BeginWaterColumnBalanceSingle (BalanceCheckMod.F90:353-442, use_aquifer_layer = .false.): ComputeWaterMassNonLake
+ * (subtract_dynbal_baselines = .false.), ComputeWaterMassLake (add_lake_water_and_subtract_dynbal_baselines = .false.),
+ * CalculateTotalH2osno over both filters.  Non-urban columns. */
 int oracle_begin_water_column_balance(const ctsm_bounds_t* bounds, int num_nolakec, const int32_t* filter_nolakec,
+                                      int num_lakec, const int32_t* filter_lakec,
                                       const ctsm_waterbalance_fields_t* f, double aquifer_water_baseline, ctsm_status_t* st) {
   (void)bounds;
   const int begc0 = f->alloc.begc, begp0 = f->alloc.begp;
   const size_t ldc = (size_t)(f->alloc.endc - f->alloc.begc + 1);
   if (st) memset(st, 0, sizeof *st);
+  WB_FIELDS(f);
   for (int fc = 0; fc < num_nolakec; ++fc) {
     const int c = filter_nolakec[fc], cc = c - begc0;
     const int lt = f->lun_itype[cc];
@@ -264,32 +319,90 @@ int oracle_begin_water_column_balance(const ctsm_bounds_t* bounds, int num_nolak
       if (st) { st->code = CTSM_ERR_URBAN; st->subgrid_level = CTSM_SUBGRID_COLUMN; st->subgrid_index = c; }
       return CTSM_ERR_URBAN;
     }
-    double liqcan_col = 0.0, snocan_col = 0.0;                           /* p2c, subgridAveMod.F90:312-318 */
-    for (int p = f->patchi[cc]; p <= f->patchf[cc]; ++p)
-      if (f->patch_active[p - begp0]) liqcan_col = liqcan_col + f->liqcan[p - begp0] * f->wtcol[p - begp0];
-    for (int p = f->patchi[cc]; p <= f->patchf[cc]; ++p)
-      if (f->patch_active[p - begp0]) snocan_col = snocan_col + f->snocan[p - begp0] * f->wtcol[p - begp0];
-    double liquid_mass = 0.0, ice_mass = 0.0;
-    liquid_mass = liquid_mass + liqcan_col + f->total_plant_stored_h2o[cc];
-    ice_mass = ice_mass + snocan_col;
-    ice_mass = ice_mass + f->h2osno_no_layers[cc];
-    const int snl = f->snl[cc];
-    for (int j = snl + 1; j <= 0; ++j) {
-      liquid_mass = liquid_mass + f->h2osoi_liq[(size_t)(j - SNOSOI_LO) * ldc + cc];
-      ice_mass = ice_mass + f->h2osoi_ice[(size_t)(j - SNOSOI_LO) * ldc + cc];
-    }
-    if (f->col_hydrologically_active[cc]) liquid_mass = liquid_mass + (f->wa[cc] - aquifer_water_baseline);
-    liquid_mass = liquid_mass + f->h2osfc[cc];
-    for (int j = 1; j <= CTSM_NLEVGRND; ++j) {
-      liquid_mass = liquid_mass + f->h2osoi_liq[(size_t)(j - SNOSOI_LO) * ldc + cc];
-      ice_mass = ice_mass + f->h2osoi_ice[(size_t)(j - SNOSOI_LO) * ldc + cc] + f->excess_ice[(size_t)(j - 1) * ldc + cc];
-    }
+    double liquid_mass, ice_mass;
+    water_mass_nonlake(cc, begp0, ldc, snl_, hyd_, patchi_, patchf_, pact_, liq_, ice_, exice_, h2osfc_, noly_, wa_, tps_, wtcol_,
+                       liqcan_, snocan_, aquifer_water_baseline, &liquid_mass, &ice_mass);
     f->begwb[cc] = liquid_mass + ice_mass;
-    double t = f->h2osno_no_layers[cc];
-    for (int j = snl + 1; j <= 0; ++j)
-      t = t + f->h2osoi_ice[(size_t)(j - SNOSOI_LO) * ldc + cc] + f->h2osoi_liq[(size_t)(j - SNOSOI_LO) * ldc + cc];
-    f->h2osno_old[cc] = t;
+    f->h2osno_old[cc] = total_h2osno(cc, ldc, snl_, liq_, ice_, noly_);
+  }
+  for (int fc = 0; fc < num_lakec; ++fc) {
+    const int cc = filter_lakec[fc] - begc0;
+    double liquid_mass = 0.0, ice_mass = 0.0;
+    water_mass_lake_layers(cc, ldc, snl_, liq_, ice_, noly_, &liquid_mass, &ice_mass);
+    f->begwb[cc] = liquid_mass + ice_mass;
+    f->h2osno_old[cc] = total_h2osno(cc, ldc, snl_, liq_, ice_, noly_);
   }
   return 0;
 }
 
+/* WaterGridcellBalanceSingle (BalanceCheckMod.F90:212-350): bulk water, use_aquifer_layer = .false., no hillslope routing */
+int oracle_water_gridcell_balance(const ctsm_bounds_t* bounds, int num_nolakec, const int32_t* filter_nolakec, int num_lakec,
+                                  const int32_t* filter_lakec, const ctsm_watergridbalance_fields_t* f,
+                                  double aquifer_water_baseline, int flag_endwb, ctsm_status_t* st) {
+  const int begc0 = f->alloc.begc, begp0 = f->alloc.begp, begg0 = f->alloc.begg;
+  const size_t ldc = (size_t)(f->alloc.endc - f->alloc.begc + 1);
+  if (st) memset(st, 0, sizeof *st);
+  WB_FIELDS(f);
+  const int ncb = bounds->endc - bounds->begc + 1;
+  double* wb_col = (double*)malloc(sizeof(double) * (size_t)(ncb > 0 ? ncb : 1));
+  for (int i = 0; i < ncb; ++i) wb_col[i] = 0.0;         /* the reference leaves columns outside both filters undefined */
+  for (int fc = 0; fc < num_nolakec; ++fc) {
+    const int c = filter_nolakec[fc], cc = c - begc0;
+    const int lt = f->lun_itype[cc];
+    if (lt >= CTSM_ISTURB_MIN && lt <= CTSM_ISTURB_MAX) {
+      if (st) { st->code = CTSM_ERR_URBAN; st->subgrid_level = CTSM_SUBGRID_COLUMN; st->subgrid_index = c; }
+      free(wb_col);
+      return CTSM_ERR_URBAN;
+    }
+    double liquid_mass, ice_mass;
+    water_mass_nonlake(cc, begp0, ldc, snl_, hyd_, patchi_, patchf_, pact_, liq_, ice_, exice_, h2osfc_, noly_, wa_, tps_, wtcol_,
+                       liqcan_, snocan_, aquifer_water_baseline, &liquid_mass, &ice_mass);
+    liquid_mass = liquid_mass - f->dynbal_baseline_liq[cc];             /* subtract_dynbal_baselines :316-322 */
+    ice_mass = ice_mass - f->dynbal_baseline_ice[cc];
+    wb_col[c - bounds->begc] = liquid_mass + ice_mass;
+  }
+  for (int fc = 0; fc < num_lakec; ++fc) {
+    const int c = filter_lakec[fc], cc = c - begc0;
+    double liquid_mass = 0.0, ice_mass = 0.0;
+    liquid_mass = liquid_mass - f->dynbal_baseline_liq[cc];             /* ComputeLiqIceMassLake :434-447 */
+    ice_mass = ice_mass - f->dynbal_baseline_ice[cc];
+    for (int j = 1; j <= CTSM_NLEVLAK; ++j) {                           /* AccumulateLiqIceMassLake :536-544, tracer_ratio = 1 */
+      const double dzl = f->dz_lake[(size_t)(j - 1) * ldc + cc], fr = f->lake_icefrac[(size_t)(j - 1) * ldc + cc];
+      const double h2olak_liq = dzl * 1.000e3 * (1 - fr) * 1.0;
+      const double h2olak_ice = dzl * 1.000e3 * fr * 1.0;
+      liquid_mass = liquid_mass + h2olak_liq;
+      ice_mass = ice_mass + h2olak_ice;
+    }
+    water_mass_lake_layers(cc, ldc, snl_, liq_, ice_, noly_, &liquid_mass, &ice_mass);
+    wb_col[c - bounds->begc] = liquid_mass + ice_mass;
+  }
+  /* c2g, subgridAveMod.F90:791-816 (scale factors 1 off the urban landunits) */
+  int rc = 0;
+  for (int g = bounds->begg; g <= bounds->endg; ++g) {
+    const int gg = g - begg0;
+    double garr = 1.0e36, sumwt = 0.0;
+    for (int c = f->grc_coli[gg]; c <= f->grc_colf[gg]; ++c) {
+      const int cc = c - begc0;
+      if (c < bounds->begc || c > bounds->endc) continue;
+      if (f->col_active[cc] && f->wtgcell[cc] != 0.0) {
+        const double v = wb_col[c - bounds->begc];
+        if (v != 1.0e36) {
+          if (sumwt == 0.0) garr = 0.0;
+          garr = garr + v * 1.0 * 1.0 * f->wtgcell[cc];
+          sumwt = sumwt + f->wtgcell[cc];
+        }
+      }
+    }
+    if (sumwt > 1.0 + 1.e-6) {
+      rc = CTSM_ERR_BALANCE;
+      if (st) { st->code = rc; st->subgrid_level = CTSM_SUBGRID_GRIDCELL; st->subgrid_index = g; }   /* the reference reports the last such g */
+    } else if (sumwt != 0.0) {
+      garr = garr / sumwt;
+    }
+    double wb = garr - f->qflx_liq_dynbal_left_to_dribble[gg] - f->qflx_ice_dynbal_left_to_dribble[gg];
+    if (flag_endwb) f->endwb_grc[gg] = wb - 0.0;                         /* wa_reset_nonconservation_gain_grc = 0 */
+    else f->begwb_grc[gg] = wb;
+  }
+  free(wb_col);
+  return rc;
+}
