@@ -17,6 +17,7 @@ int cuda_fail(cudaError_t e, const char* file, int line) {
   return CTSM_ERR_CUDA;
 }
 extern "C" const char* ctsm_b200_last_cuda_error(void) { return g_last_cuda_error; }
+static void free_member_params(ctsm_b200_ctx* ctx);
 
 extern "C" const char* ctsm_b200_version(void) { return kVersion; }
 
@@ -88,6 +89,7 @@ extern "C" int ctsm_b200_finalize(ctsm_b200_ctx* ctx) {
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   for (auto q : ctx->bal_pinned) cudaFreeHost(q);
   for (auto q : ctx->bal_dev) cudaFree(q);
+  free_member_params(ctx);
   for (auto e : ctx->ev_round) cudaEventDestroy(e);
   for (auto e : ctx->ev_tail) cudaEventDestroy(e);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -102,6 +104,42 @@ extern "C" int ctsm_b200_set_tuning(ctsm_b200_ctx* ctx, int tail_max, int nt_bud
   if (tail_max >= 0) ctx->tune.tail_max = tail_max;
   if (nt_budget >= 0) ctx->tune.nt_budget = nt_budget;
   if (tail_lanes >= 0) ctx->tune.tail_lanes = tail_lanes;
+  return CTSM_OK;
+}
+
+static void free_member_params(ctsm_b200_ctx* ctx) {
+  ctsm_b200_ctx::MemberPrm& m = ctx->member;
+  cudaFree(m.e_ice); cudaFree(m.csoilc); cudaFree(m.cv); cudaFree(m.a_coef); cudaFree(m.z_dl); cudaFree(m.col_member);
+  m = ctsm_b200_ctx::MemberPrm();
+}
+
+extern "C" int ctsm_b200_set_member_params(ctsm_b200_ctx* ctx, int nmember, const double* e_ice, const double* csoilc,
+                                           const double* cv, const double* a_coef, const double* z_dl,
+                                           const int32_t* col_member, int begc, int endc) {
+  if (!ctx || nmember < 0) return CTSM_ERR_BAD_ARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  free_member_params(ctx);
+  if (nmember == 0) return CTSM_OK;
+  if (nmember * (CTSM_MXPFT + 1) != ctx->prm.npft_table) return CTSM_ERR_BAD_ARG;      // same member count as the PFT tables
+  if (e_ice && (!col_member || endc < begc)) return CTSM_ERR_BAD_ARG;
+  ctsm_b200_ctx::MemberPrm& m = ctx->member;
+  m.n = nmember;
+  const double* src[5] = {e_ice, csoilc, cv, a_coef, z_dl};
+  double** dst[5] = {&m.e_ice, &m.csoilc, &m.cv, &m.a_coef, &m.z_dl};
+  for (int k = 0; k < 5; ++k) {
+    if (!src[k]) continue;
+    CUDA_TRY(cudaMalloc(dst[k], sizeof(double) * (size_t)nmember));
+    CUDA_TRY(cudaMemcpy(*dst[k], src[k], sizeof(double) * (size_t)nmember, cudaMemcpyHostToDevice));
+  }
+  if (col_member && endc >= begc) {
+    const size_t n = (size_t)(endc - begc + 1);
+    for (size_t i = 0; i < n; ++i)
+      if (col_member[i] < 0 || col_member[i] >= nmember) { free_member_params(ctx); return CTSM_ERR_BAD_ARG; }
+    CUDA_TRY(cudaMalloc(&m.col_member, sizeof(int32_t) * n));
+    CUDA_TRY(cudaMemcpy(m.col_member, col_member, sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+    m.begc = begc; m.endc = endc;
+  }
   return CTSM_OK;
 }
 

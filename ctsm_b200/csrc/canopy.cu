@@ -78,6 +78,8 @@ struct CanopyPrm {
   double act25, fnr, cp25_yr2000, kc25_coef, ko25_coef, fnps, theta_psii, theta_ip;
   double vcmaxha, jmaxha, tpuha, lmrha, kcha, koha, cpha, vcmaxhd, jmaxhd, tpuhd, lmrhd, lmrse;
   double tpu25ratio, kp25ratio, vcmaxse_sf, jmaxse_sf, tpuse_sf, jmax25top_sf;
+  // per-member values of scalar parameters (perturbed-parameter ensembles; NULL: the scalar above); member = itype / (mxpft+1)
+  const double *m_csoilc, *m_cv, *m_a_coef, *m_z_dl;
 };
 
 struct Geo {   // index bases / leading dimensions
@@ -637,7 +639,8 @@ __device__ __forceinline__ CloseOut close_body(const CanopyDev& f, const CanopyP
       }
       const double wtaq = fvn / raw_a;
       const double wtlq = fvn * (elai + esai) / rb * rpp;
-      const double fsno_dl = CF(snow_depth) / prm.z_dl;
+      const double z_dl = prm.m_z_dl ? prm.m_z_dl[PF(itype) / (CTSM_MXPFT + 1)] : prm.z_dl;
+      const double fsno_dl = CF(snow_depth) / z_dl;
       const double elai_dl = prm.lai_dl * (1.0 - fmin(fsno_dl, 1.0));
       const double rdl = (1.0 - dexp(-elai_dl)) / (0.004 * uaf);
       double wtgq = WS(W_WTGQ);
@@ -828,17 +831,20 @@ __device__ __forceinline__ void fric_body(const CanopyDev& f, const CanopyPrm& p
       const double uaf = um * sqrt(1.0 / (ram1 * um));
       const double uuc = fmin(0.4, (0.03 * um / ustar));
       const double dleaf = f.pft_dleaf[ivt];
-      const double cfl = prm.cv / (sqrt(uaf) * sqrt(dleaf));
+      const int mem_ = ivt / (CTSM_MXPFT + 1);
+      const double p_cv = prm.m_cv ? prm.m_cv[mem_] : prm.cv, p_a_coef = prm.m_a_coef ? prm.m_a_coef[mem_] : prm.a_coef;
+      const double p_csoilc = prm.m_csoilc ? prm.m_csoilc[mem_] : prm.csoilc;
+      const double cfl = p_cv / (sqrt(uaf) * sqrt(dleaf));
       const double rb = 1.0 / (cfl * uaf);
       const double w = dexp(-(elai + esai));
-      const double csoilb = vkc / (prm.a_coef * pw(CF(z0mg) * uaf / nu_param, prm.a_exp));
+      const double csoilb = vkc / (p_a_coef * pw(CF(z0mg) * uaf / nu_param, prm.a_exp));
       const double ri = (grav * htop * (taf - t_grnd)) / (taf * (uaf * uaf));
       double csoilcn;
       if (prm.use_undercanopy_stability && (taf - t_grnd) > 0.0) {
-        const double ricsoilc = prm.csoilc / (1.00 + 0.5 * fmin(ri, 10.0));
+        const double ricsoilc = p_csoilc / (1.00 + 0.5 * fmin(ri, 10.0));
         csoilcn = csoilb * w + ricsoilc * (1.0 - w);
       } else {
-        csoilcn = csoilb * w + prm.csoilc * (1.0 - w);
+        csoilcn = csoilb * w + p_csoilc * (1.0 - w);
       }
       const double rah_b = prm.use_biomass_heat_storage ? 1.0 / (csoilcn * uuc) : 1.0 / (csoilcn * uaf);
       const double raw_b = rah_b;
@@ -1763,6 +1769,7 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   cp.cpha = p.cpha; cp.vcmaxhd = p.vcmaxhd; cp.jmaxhd = p.jmaxhd; cp.tpuhd = p.tpuhd; cp.lmrhd = p.lmrhd; cp.lmrse = p.lmrse;
   cp.tpu25ratio = p.tpu25ratio; cp.kp25ratio = p.kp25ratio; cp.vcmaxse_sf = p.vcmaxse_sf; cp.jmaxse_sf = p.jmaxse_sf;
   cp.tpuse_sf = p.tpuse_sf; cp.jmax25top_sf = p.jmax25top_sf;
+  cp.m_csoilc = ctx->member.csoilc; cp.m_cv = ctx->member.cv; cp.m_a_coef = ctx->member.a_coef; cp.m_z_dl = ctx->member.z_dl;
 
   Geo g;
   g.begp0 = hf->alloc.begp; g.begc0 = hf->alloc.begc; g.begg0 = hf->alloc.begg;

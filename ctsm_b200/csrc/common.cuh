@@ -88,6 +88,12 @@ struct ctsm_b200_ctx {
   std::vector<BalPending> bal_pending;
   std::vector<void*> bal_pinned, bal_dev; size_t bal_pinned_used = 0;
   void* bal_last_dev = nullptr;
+  // perturbed-parameter ensembles: per-member values of the scalar parameters (device arrays, owned), ctsm_b200_set_member_params
+  struct MemberPrm {
+    int n = 0;
+    double *e_ice = nullptr, *csoilc = nullptr, *cv = nullptr, *a_coef = nullptr, *z_dl = nullptr;
+    int32_t* col_member = nullptr; int begc = 0, endc = -1;
+  } member;
 };
 
 // records "name at file:line: text" for ctsm_b200_last_cuda_error() and maps the error to a CTSM_ERR_* code

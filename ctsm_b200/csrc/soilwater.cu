@@ -31,6 +31,8 @@ struct SoilWaterDev {   // device-side view of ctsm_soilwater_fields_t
 struct SoilWaterPrm {
   double dtime, dtmin, verySmall, xTolerUpper, xTolerLower, e_ice;
   int lower_bc, flux_calculation;
+  // perturbed-parameter ensembles: e_ice per member, member of every column (NULL: the scalar above)
+  const double* m_e_ice; const int32_t* col_member; int member_begc;
 };
 
 template <int PASS>
@@ -44,6 +46,7 @@ soilwater_kernel(SoilWaterDev f, SoilWaterPrm prm, int begc0, int ldc, int numf_
   const int ci = c1 - begc0;
   const size_t ld = (size_t)ldc;
   const int n = f.nbedrock[ci];       // nlayers, :1184
+  const double e_ice = prm.m_e_ice ? prm.m_e_ice[prm.col_member[c1 - prm.member_begc]] : prm.e_ice;
 
   constexpr int N = NLEVSOI;
   double dz1000[N], watsat[N], bsw[N], sucsat[N], sink[N], ih[N], zden[N], liq[N];
@@ -68,10 +71,10 @@ soilwater_kernel(SoilWaterDev f, SoilWaterPrm prm, int begc0, int ldc, int numf_
       if (j < n - 1) {
         icef_n = f.icefrac[o1 + ld];
         z_n = f.z[os + ld];
-        imped = pow(10.0, -prm.e_ice * (0.5 * (icef_j + icef_n)));
+        imped = pow(10.0, -e_ice * (0.5 * (icef_j + icef_n)));
         zden[j] = cst::m_to_mm * (z_n - z_j);                      // den of :1710
       } else {
-        imped = pow(10.0, -prm.e_ice * icef_j);
+        imped = pow(10.0, -e_ice * icef_j);
         zden[j] = 0.0;
       }
       ih[j] = imped * f.hksat[o1];                                 // soil_hk: imped*hksat*s**(2b+3)
@@ -223,7 +226,9 @@ extern "C" int ctsm_b200_soilwater(ctsm_b200_ctx* ctx, const ctsm_bounds_t* boun
     if (rc) return rc;
   }
   SoilWaterPrm p{ctx->prm.dtime, ctx->prm.dtmin, ctx->prm.verySmall, ctx->prm.xTolerUpper, ctx->prm.xTolerLower,
-                 ctx->prm.e_ice, ctx->prm.lower_boundary_condition, ctx->prm.flux_calculation};
+                 ctx->prm.e_ice, ctx->prm.lower_boundary_condition, ctx->prm.flux_calculation,
+                 ctx->member.e_ice, ctx->member.col_member, ctx->member.begc};
+  if (p.m_e_ice && (bounds->begc < ctx->member.begc || bounds->endc > ctx->member.endc)) return CTSM_ERR_BAD_ARG;
   if (p.flux_calculation != 1) return CTSM_ERR_BAD_ARG;
   if (num_hydrologyc > 0) {
     int rc = arena_reserve(ctx, ctx->arena_ints, sizeof(int32_t) * ((size_t)num_hydrologyc + 64));

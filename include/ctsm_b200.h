@@ -277,6 +277,14 @@ void* ctsm_b200_stream_of(ctsm_b200_ctx* ctx, int kind);
 int64_t ctsm_b200_launch_count(const ctsm_b200_ctx* ctx);
 /* "cudaErrorName at file:line: text" of the last CUDA runtime error this process's library calls met ("" if none) */
 const char* ctsm_b200_last_cuda_error(void);
+/* Perturbed-parameter ensembles (BASELINE.json config 5: members batched as independent columns).  The PFT tables carry the
+ * members through ctsm_params_t.npft_table (patch%itype = member*(mxpft+1) + pft); this call does the same for the SCALAR
+ * parameters the survey lists: per-member values (host arrays of length nmember, NULL = keep the scalar of ctsm_params_t) of
+ * e_ice (SoilWaterMovementMod.F90:34), csoilc, cv, a_coef, z_dl (CanopyFluxesMod.F90:61-70).  A patch's member is
+ * itype / (mxpft+1); col_member(begc:endc) gives every column's member (0-based; needed for e_ice).  nmember must equal
+ * npft_table / (mxpft+1); nmember = 0 clears.  Synchronous, the arrays are copied. */
+int  ctsm_b200_set_member_params(ctsm_b200_ctx* ctx, int nmember, const double* e_ice, const double* csoilc, const double* cv,
+                                 const double* a_coef, const double* z_dl, const int32_t* col_member, int begc, int endc);
 /* Scheduling knobs of CanopyFluxes' ITERATION loop (results do not depend on them; defaults come from the environment
  * variables CTSM_B200_TAIL_MAX / CTSM_B200_NT_BUDGET / CTSM_B200_TAIL_LANES, else 0 / 0 / 1 = tail kernel off: on B200 the
  * per-patch nested-loop kernel is instruction-fetch bound and only pays for calls of a few patches):
