@@ -186,6 +186,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-slabs", type=int, default=6, help="gridcell slabs the e2e step is issued over (clump loop)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--members", type=int, default=1,
+                    help="perturbed-parameter ensemble (BASELINE config 5): this many parameter sets x the --size grid, batched "
+                         "as independent columns; dealt to the ranks under torchrun")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="under torchrun: strong = ONE grid of --size dealt to the ranks (default), weak = one grid of --size per rank")
     a = ap.parse_args()
@@ -196,15 +199,23 @@ def main():
     size = a.size if not a.size.isdigit() else int(a.size)
     routines = tuple(g for g in ALL_ROUTINES if g in a.routines.split(","))
     strong = a.scaling == "strong" or world == 1
+    from ctsm_b200 import synthetic
+    members_local = a.members
+    if a.members > 1:
+        if a.members % world != 0:
+            raise SystemExit("bench.py: --members must be a multiple of the number of ranks")
+        per_member_g = synthetic.GRID_SIZES[size] if isinstance(size, str) else int(size)
+        members_local = a.members // world if strong else a.members
+        size = per_member_g * a.members                     # the ensemble as ONE grid of independent columns
     if strong and world > 1:
-        from ctsm_b200 import synthetic
         total_g = synthetic.GRID_SIZES[size] if isinstance(size, str) else int(size)
         g0, g1 = rank * total_g // world, (rank + 1) * total_g // world      # contiguous slab of the one grid (clump range)
         local_size = g1 - g0
     else:
         local_size = size
-    wl_name = "%s one 1800 s step, ONE %s-sized synthetic grid (15 patches per soil column)%s" % (
-        "->".join(NAME_OF[g] for g in routines), a.size,
+    wl_name = "%s one 1800 s step, ONE %s synthetic grid (15 patches per soil column)%s" % (
+        "->".join(NAME_OF[g] for g in routines),
+        ("%s-sized" % a.size) if a.members == 1 else ("%d-member perturbed-parameter ensemble x %s-sized" % (a.members, a.size)),
         "" if world == 1 else (" dealt to %d GPUs in contiguous gridcell slabs" % world if strong else " PER GPU (weak scaling)"))
     config = {"workload": wl_name, "grid": str(a.size), "routines": [NAME_OF[g] for g in routines],
               "state": "restored from a pristine device snapshot before every step (untimed D2D copies)",
@@ -236,8 +247,18 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     prm = abi.default_params(device=local_rank)
-    ctx = driver.Context(prm)
     sg, S = make_workload(local_size, 20260101 + 1000 * rank)
+    if a.members > 1:
+        # config 5: members = contiguous gridcell ranges; PFT tables per member (medlynslope, kmax, psi50, ck, krmax perturbed)
+        # and per-member scalars e_ice, csoilc, cv, a_coef, z_dl
+        rngm = np.random.Generator(np.random.PCG64(20260105 + rank))
+        synthetic_canopy.make_ensemble(sg, S, members_local, rngm, spread=0.2)
+        prm.npft_table = members_local * (abi.MXPFT + 1)
+    ctx = driver.Context(prm)
+    if a.members > 1:
+        member_g = np.minimum((np.arange(sg.ngrc) * members_local) // sg.ngrc, members_local - 1)
+        scal = {k: getattr(prm, k) * rngm.uniform(0.8, 1.2, members_local) for k in ("e_ice", "csoilc", "cv", "a_coef", "z_dl")}
+        ctx.set_member_params(members_local, member_g[sg.col_gridcell - 1], sg.bounds.begc, sg.bounds.endc, **scal)
     names = sorted({fs.name for g in routines for fs in abi.FIELDS[g]})
     D = {k: torch.from_numpy(S[k]).cuda() for k in names}
     restore = sorted({fs.name for g in routines for fs in abi.FIELDS[g] if fs.intent != "IN"})
@@ -363,7 +384,8 @@ def main():
                 "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": dict(config, columns_per_gpu=ncol, patches_per_gpu=sg.npatch,
-                               exposedveg_patches_per_gpu=int(len(sg.filters["exposedvegp"]))),
+                               exposedveg_patches_per_gpu=int(len(sg.filters["exposedvegp"])), members=a.members,
+                               members_per_gpu=members_local),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "warnings_in_timed_region": int(st.n_warnings), "wall_s_timed_region": t_wall,
                 "balance_global_max": hp.global_balance(), "total_columns": int(total_cols)}

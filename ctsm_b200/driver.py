@@ -47,6 +47,16 @@ class Context:
         """Scheduling knobs of CanopyFluxes' ITERATION loop (include/ctsm_b200.h); results do not depend on them."""
         self.L.ctsm_b200_set_tuning(self.h, tail_max, nt_budget, tail_lanes)
 
+    def set_member_params(self, nmember, col_member, begc, endc, **tables):
+        """Per-member values of e_ice / csoilc / cv / a_coef / z_dl (ctsm_b200_set_member_params)."""
+        arr = {k: (np.ascontiguousarray(v, dtype=np.float64) if v is not None else None)
+               for k, v in ((k, tables.get(k)) for k in ("e_ice", "csoilc", "cv", "a_coef", "z_dl"))}
+        cm = np.ascontiguousarray(col_member, dtype=np.int32) if col_member is not None else None
+        rc = self.L.ctsm_b200_set_member_params(self.h, int(nmember), *[abi.f64p(arr[k]) for k in ("e_ice", "csoilc", "cv", "a_coef", "z_dl")],
+                                                abi.i32p(cm), int(begc), int(endc))
+        if rc != 0:
+            raise RuntimeError("ctsm_b200_set_member_params rc=%d" % rc)
+
     def close(self):
         if self.h:
             self.L.ctsm_b200_finalize(self.h)

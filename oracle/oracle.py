@@ -92,6 +92,18 @@ def build(force: bool = False) -> str:
     return LIB
 
 
+_pert = None
+
+
+def lib_perturbed():
+    """The conditioning probe (oracle_pert.h): same exports as lib(), CanopyFluxes / PHS libm results moved by one ulp."""
+    global _pert
+    if _pert is None:
+        subprocess.check_call(["make", "-s", "-C", HERE, "liboracle_pert.so"])
+        _pert = _bind(C.CDLL(os.path.join(HERE, "liboracle_pert.so")))
+    return _pert
+
+
 def default_params():
     """ctsm_params_t with the clm6_0 defaults, from the oracle library alone (does not load libctsm_b200.so)."""
     p = abi.Params()
@@ -104,7 +116,11 @@ def lib():
     if _lib is not None:
         return _lib
     build()
-    L = C.CDLL(LIB)
+    _lib = _bind(C.CDLL(LIB))
+    return _lib
+
+
+def _bind(L):
     i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
     B, S, P = C.POINTER(abi.Bounds), C.POINTER(abi.Status), C.POINTER(abi.Params)
     L.oracle_dgbsv.argtypes = [C.c_int] * 4 + [f64p, C.c_int, i32p, f64p, C.c_int, i32p]
@@ -135,6 +151,8 @@ def lib():
     L.oracle_balancecheck_skip_steps.argtypes = [C.c_double]
     L.oracle_vert_tran_sink_hydstress.argtypes = [B, C.c_int, i32p, C.POINTER(abi.STRUCTS["plantsink"])]
     L.oracle_num_threads.restype = C.c_int
+    L.oracle_set_pert_mode.argtypes = [C.c_int]
+    L.oracle_set_pert_mode.restype = None
     L.oracle_default_params.argtypes = [P]
     L.oracle_default_params.restype = None
     L.oracle_step_clumps.argtypes = [P, C.c_int, C.POINTER(Clump), C.POINTER(abi.STRUCTS["soiltemperature"]),
@@ -151,5 +169,4 @@ def lib():
     L.oracle_set_filters.argtypes = [B, C.POINTER(abi.FilterInputs), C.POINTER(abi.Filters)]
     L.oracle_patch2col.argtypes = [B, C.c_int, i32p, C.c_int, i32p, C.POINTER(abi.STRUCTS["patch2col"])]
     L.oracle_soilfluxes.argtypes = [P, B, C.c_int, i32p, C.c_int, i32p, C.POINTER(abi.STRUCTS["soilfluxes"]), S]
-    _lib = L
     return L

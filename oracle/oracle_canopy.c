@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "oracle_canopy.h"
+#include "oracle_pert.h"
 
 static const double sb = 5.67e-8, cpair = 1.00464e3, hvap = 2.501e6, vkc = 0.4, grav = 9.80616;
 static const double denice = 0.917e3, denh2o = 1.000e3, c_to_b = 2.0, tlsai_crit = 2.0, alpha_aero = 1.0;

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "oracle_canopy.h"
+#include "oracle_pert.h"
 
 static const double spval = 1.e36;
 static const double bbbopt_c3 = 10000.0, bbbopt_c4 = 40000.0;       /* :85-86 */
@@ -143,6 +144,8 @@ static const double tol_lai = .001;
 /* workload statistics for DESIGN.md / tools/phs_stats.py: [0] calcstress calls, [1] Newton iterations,
  * [2] calcstress calls that hit itmax, [3] ci_func_PHS calls, [4] brent_PHS calls, [5] hybrid outer passes */
 long long oracle_phs_counters[8];
+int oracle_pert_mode = 1;      /* oracle_pert.h; unused in the plain build */
+void oracle_set_pert_mode(int m) { oracle_pert_mode = m; }
 long long oracle_phs_newton_hist[2][64];   /* [night][Newton iterations of one calcstress call] (workload statistics) */
 static long long* per_patch_newton = 0;   /* optional (begp0:endp0) accumulator */
 void oracle_phs_set_patch_counter(long long* p) { per_patch_newton = p; }

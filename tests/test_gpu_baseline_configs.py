@@ -18,7 +18,7 @@ import pytest
 
 from ctsm_b200 import abi, driver, synthetic, synthetic_canopy
 from tests.util import relerr, to_device, copy_state, group_arrays
-from tests.test_gpu_canopy import compare as compare_canopy, run_gpu as run_gpu_canopy
+from tests.test_gpu_canopy import compare as compare_canopy, run_gpu as run_gpu_canopy, canopy_sensitivity, SENS_ILL
 from tests.test_gpu_soil import _run_oracle_soiltemp, _run_gpu_soiltemp, _compare as compare_group, _run_soilwater
 
 pytestmark = pytest.mark.gpu
@@ -36,14 +36,13 @@ def test_config3_canopyfluxes_f09(gpu_ctx, oracle_lib):
     sg, S = synthetic_canopy.make_full_case("f09", seed=20260103)
     fe = sg.filters["exposedvegp"]
     assert sg.ngrc == 21000 and sg.npatch >= 315000 and len(fe) > 140000
-    ref, got = copy_state(S), copy_state(S)
-    nth = _oracle_threads(oracle_lib)
-    clumps, keep = oracle.make_clumps(sg, 4 * nth)
-    fc = abi.make_struct("canopyfluxes", ref, sg.bounds)
-    assert oracle_lib.oracle_step_clumps(C.byref(prm), len(clumps), clumps, None, None, C.byref(fc), 4) == 0
+    got = copy_state(S)
+    ref, sens = canopy_sensitivity(sg, S, prm, _oracle_threads(oracle_lib))      # the oracle result + its measured conditioning
     rc, st = run_gpu_canopy(L, ctx, sg, got, abi.MEM_DEVICE)
     assert rc == 0, st.msg
-    worst, ntie = compare_canopy(sg, got, ref, S)
+    worst, ntie = compare_canopy(sg, got, ref, S, sens=sens)
+    print("f09 canopy: ill-conditioned patches (oracle moves > %g under 1-ulp libm noise): %d of %d, of which %d below the cap"
+          % (SENS_ILL, int((sens > SENS_ILL).sum()), len(fe), int(((sens > SENS_ILL) & (ref["num_iter"][fe - 1] < 41)).sum())))
     it = got["num_iter"][fe - 1]
     hist = np.bincount(it.astype(np.int64), minlength=42)
     print("f09 canopy: worst", sorted(worst.items(), key=lambda kv: -kv[1])[:4], "ties", ntie, "num_iter histogram", hist[3:].tolist())
@@ -104,12 +103,14 @@ def test_config4_full_step_f02_slab(gpu_ctx, oracle_lib):
     finally:
         ctx.close()
     # ---- compare ----
-    worst, ntie = compare_canopy(sg, got, ref, S)
-    # patches whose ITERATION did not converge (41 passes) or tied on the threshold carry a larger error into their
-    # column's soil state (SoilTemperature reads their fluxes): those columns are compared at 1e-4, the others at 1e-10
+    _, sens = canopy_sensitivity(sg, S, prm0, nth)
+    worst, ntie = compare_canopy(sg, got, ref, S, sens=sens)
+    # ill-conditioned patches (tests/test_gpu_canopy.py: the oracle itself moves under 1-ulp libm noise) carry a larger
+    # error into their column's soil state (SoilTemperature reads their fluxes): those columns are compared at 1e-3,
+    # all others at 1e-10
     fe0 = fe - 1
     loose_p = np.zeros(sg.npatch, dtype=bool)
-    loose_p[fe0[(ref["num_iter"][fe0] >= 41) | (got["num_iter"][fe0] != ref["num_iter"][fe0])]] = True
+    loose_p[fe0[(sens > SENS_ILL) | (got["num_iter"][fe0] != ref["num_iter"][fe0])]] = True
     loose_c = np.zeros(sg.ncol, dtype=bool)
     loose_c[S["column"][loose_p] - 1] = True
     loose_g = np.zeros(sg.ngrc, dtype=bool)

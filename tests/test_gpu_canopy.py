@@ -55,23 +55,77 @@ def run_gpu(L, ctx, sg, S, mem):
 LAGGING = ("cp", "kc", "ko", "lmrsun_z", "lmrsha_z", "rh_af", "vpd", "vpd_can", "vcmax_z_phs", "tpu_z_phs", "kp_z_phs", "gb_mol")
 
 
-def compare(sg, got, ref, init=None, lag_rtol=None):
+SENS_FIELDS = ("t_veg", "taf", "qaf", "qflx_tran_veg", "qflx_evap_veg", "eflx_sh_veg", "vegwp", "btran", "ustar", "t_ref2m")
+SENS_ILL = 1.0e-11          # a patch whose own oracle result moves by more than this under 1-ulp libm noise is ill-conditioned
+
+
+def canopy_sensitivity(sg, S, prm, nthreads=None):
+    """Per exposed-vegetation patch: how far the ORACLE's result moves when every libm result inside CanopyFluxes / PHS is
+    nudged by one unit in the last place (oracle/oracle_pert.h, two independent nudge patterns).  One ulp is what two correct
+    libms (glibc, libdevice) may disagree by, so this measures, patch by patch, what the ITERATION loop makes of legitimate
+    last-bit noise: ~1e-12 for the 99.98 % of patches that converge, up to 1e-6 for those still oscillating at the cap."""
+    import os
+    from oracle import oracle
+    OL, OP = oracle.lib(), oracle.lib_perturbed()
+    nth = nthreads or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 1)
+    clumps, keep = oracle.make_clumps(sg, 4 * nth)
+    fe = sg.filters["exposedvegp"] - 1
+
+    def run(L, mode):
+        X = copy_state(S)
+        L.oracle_set_num_threads(nth)
+        if mode:
+            L.oracle_set_pert_mode(mode)
+        fc = abi.make_struct("canopyfluxes", X, sg.bounds)
+        assert L.oracle_step_clumps(C.byref(prm), len(clumps), clumps, None, None, C.byref(fc), 4) == 0
+        return X
+
+    base = run(OL, 0)
+    sens = np.zeros(len(fe))
+    for mode in (1, 2):
+        pert = run(OP, mode)
+        for name in SENS_FIELDS:
+            a, b = pert[name][..., fe], base[name][..., fe]
+            scale = float(np.max(np.abs(b[np.abs(b) < 1e30]))) if np.any(np.abs(b) < 1e30) else 1.0
+            r = np.abs(a - b) / np.maximum(np.abs(b), 1e-3 * scale)
+            r = np.where(np.abs(b) < 1e30, r, 0.0)
+            sens = np.maximum(sens, r.max(axis=0) if r.ndim == 2 else r)
+        sens = np.where(pert["num_iter"][fe] != base["num_iter"][fe], np.inf, sens)      # the pass count itself is not stable
+    return base, sens
+
+
+def compare(sg, got, ref, init=None, lag_rtol=None, sens=None):
     fe = sg.filters["exposedvegp"] - 1
     ties = got["num_iter"][fe] != ref["num_iter"][fe]
     ntie = int(ties.sum())
     assert ntie <= max(1, int(MAX_TIE_FRACTION * len(fe))), "num_iter differs on %d of %d patches" % (ntie, len(fe))
     tie_p = np.zeros(sg.npatch, dtype=bool)
     tie_p[fe[ties]] = True
-    # Patches that exhaust the iteration cap (itmax_canopy_fluxes + 1 = 41 passes) have not converged in the
-    # reference either: their leaf temperature is still oscillating, and 41 passes of a non-contracting map
-    # amplify last-ulp libm differences (glibc vs libdevice pow/exp/log) to ~1e-7.  They are compared at
-    # CAP_RTOL on the prognostic outputs and excluded from the 1e-10 comparison; their number is bounded.
-    capped = (ref["num_iter"][fe] >= 41) & (ref["num_iter"][fe] < 1e30)
-    assert capped.sum() <= max(2, int(0.01 * len(fe))), "%d of %d patches hit the iteration cap" % (capped.sum(), len(fe))
-    for name in ("t_veg", "taf", "t_ref2m", "ustar", "eflx_sh_veg", "qflx_evap_veg"):
-        a, b = got[name][fe[capped]], ref[name][fe[capped]]
-        assert np.all(np.abs(a - b) <= CAP_RTOL * np.maximum(np.abs(b), 1.0)), (name, float(np.max(np.abs(a - b))))
-    tie_p[fe[capped]] = True
+    if sens is not None:
+        # Measured conditioning (canopy_sensitivity): patches whose oracle result is itself unstable under 1-ulp libm
+        # noise cannot be held to 1e-10 by ANY implementation with another libm.  They are held to the amplification
+        # the probe measured (x 1e4 head room: the GPU's libm differs by up to 2 ulp and in its own pattern), at least
+        # CAP_RTOL; every other patch - including slow convergers and capped ones that are stable - meets 1e-10.
+        ill = sens > SENS_ILL
+        assert ill.sum() <= max(2, int(1e-3 * len(fe))), "%d of %d patches are ill-conditioned" % (ill.sum(), len(fe))
+        assert not np.any(ties & ~ill), "num_iter differs on a well-conditioned patch"
+        for name in ("t_veg", "taf", "t_ref2m", "ustar", "eflx_sh_veg", "qflx_evap_veg"):
+            a, b = got[name][fe[ill]], ref[name][fe[ill]]
+            bound = np.maximum(CAP_RTOL, np.minimum(1e4 * sens[ill], 1e-1)) * np.maximum(np.abs(b), 1.0)
+            assert np.all(np.abs(a - b) <= bound), (name, float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0))))
+        tie_p[fe[ill]] = True
+    else:
+        # Patches that exhaust the iteration cap (itmax_canopy_fluxes + 1 = 41 passes) have not converged in the
+        # reference either: their leaf temperature is still oscillating, and 41 passes of a non-contracting map
+        # amplify last-ulp libm differences (glibc vs libdevice pow/exp/log) to ~1e-7 (measured: canopy_sensitivity).
+        # They are compared at CAP_RTOL on the prognostic outputs and excluded from the 1e-10 comparison; their number
+        # is bounded.
+        capped = (ref["num_iter"][fe] >= 41) & (ref["num_iter"][fe] < 1e30)
+        assert capped.sum() <= max(2, int(0.01 * len(fe))), "%d of %d patches hit the iteration cap" % (capped.sum(), len(fe))
+        for name in ("t_veg", "taf", "t_ref2m", "ustar", "eflx_sh_veg", "qflx_evap_veg"):
+            a, b = got[name][fe[capped]], ref[name][fe[capped]]
+            assert np.all(np.abs(a - b) <= CAP_RTOL * np.maximum(np.abs(b), 1.0)), (name, float(np.max(np.abs(a - b))))
+        tie_p[fe[capped]] = True
     tie_c = np.zeros(sg.ncol, dtype=bool)
     worst = {}
     for fs in abi.FIELDS["canopyfluxes"]:

@@ -110,14 +110,25 @@ def test_scalar_parameter_ensemble_matches_per_member_oracle_runs(oracle_lib):
         fc = abi.make_struct("canopyfluxes", ref, sg.bounds)
         assert oracle_lib.oracle_canopyfluxes(C.byref(pm), C.byref(k.bounds), k.num_exposedvegp, k.filter_exposedvegp, C.byref(fc),
                                               C.byref(st)) == 0
-        fwr = abi.make_struct("soilwater", ref, sg.bounds)
+    compare(sg, got, ref, S)
+    refw = copy_state(ref)                                           # SoilWater continues from the post-CanopyFluxes state
+    for m in range(nmem):
+        k = clumps[m]
+        pm = abi.default_params()
+        pm.e_ice = float(scal["e_ice"][m])
+        st = abi.Status()
+        fwr = abi.make_struct("soilwater", refw, sg.bounds)
         assert oracle_lib.oracle_soilwater(C.byref(pm), C.byref(k.bounds), k.num_hydrologyc, k.filter_hydrologyc, C.byref(fwr),
                                            C.byref(st)) == 0
-    compare(sg, got, ref, S)
     hc = fh - 1
-    assert np.array_equal(gotw["num_substeps"][hc], ref["num_substeps"][hc])
+    assert np.array_equal(gotw["num_substeps"][hc], refw["num_substeps"][hc])
     for name in ("h2osoi_liq", "smp_l", "hk_l", "qin", "qout"):
-        assert relerr(gotw[name][..., hc], ref[name][..., hc]) <= RTOL, name
+        assert relerr(gotw[name][..., hc], refw[name][..., hc]) <= RTOL, name
+    pe = abi.default_params()                                        # e_ice is felt: the base value gives other conductivities
+    plainw = copy_state(ref)
+    fwp = abi.make_struct("soilwater", plainw, sg.bounds)
+    assert oracle_lib.oracle_soilwater(C.byref(pe), C.byref(sg.bounds), len(fh), abi.i32p(fh), C.byref(fwp), C.byref(abi.Status())) == 0
+    assert np.mean(plainw["hk_l"][:5, hc] != refw["hk_l"][:5, hc]) > 0.2
     # the perturbation is felt: a run with the base scalars differs
     plain = copy_state(S)
     assert run_oracle(oracle_lib, prm, sg, plain)[0] == 0
