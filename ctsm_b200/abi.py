@@ -100,7 +100,8 @@ class Params(C.Structure):
                     "vcmaxhd", "jmaxhd", "tpuhd", "lmrhd", "lmrse",
                     "tpu25ratio", "kp25ratio", "vcmaxse_sf", "jmaxse_sf", "tpuse_sf", "jmax25top_sf")] + [
                 ("balance_skip_steps", C.c_int32),
-                ("npft_table", C.c_int32), ("reserved_i", C.c_int32 * 6), ("reserved_d", C.c_double * 8)]
+                ("npft_table", C.c_int32), ("calc_human_stress_indices", C.c_int32), ("reserved_i", C.c_int32 * 5),
+                ("reserved_d", C.c_double * 8)]
 
 
 def default_params(dtime: float = 1800.0, device: int = 0) -> Params:

@@ -35,6 +35,7 @@ extern "C" int ctsm_b200_init(const ctsm_params_t* p, ctsm_b200_ctx** out) {
   if (p->use_hydrstress != 1 || (p->z0param_method != 1 && p->z0param_method != 2) ||
       (p->stomatalcond_mtd != 1 && p->stomatalcond_mtd != 2) || p->itmax_canopy_fluxes < 1)
     return CTSM_ERR_BAD_ARG;
+  if (p->calc_human_stress_indices != 0 && p->calc_human_stress_indices != 1) return CTSM_ERR_BAD_ARG;
   if (p->npft_table < CTSM_MXPFT + 1 || p->npft_table % (CTSM_MXPFT + 1) != 0) return CTSM_ERR_BAD_ARG;
   if (p->upper_boundary_condition != 1 || (p->lower_boundary_condition != 1 && p->lower_boundary_condition != 2))
     return CTSM_ERR_BAD_ARG;
@@ -192,6 +193,7 @@ static const char* message_for(int code) {
     case CTSM_ERR_GS_NEG: return "PhotosynthesisHydraulicStress: negative stomatal conductance";
     case CTSM_ERR_BRENT: return "brent_PHS: root must be bracketed";
     case CTSM_ERR_QUADRATIC: return "quadratic solution error: b^2 - 4ac is negative";
+    case CTSM_ERR_RH: return "ERROR RH is negative / greater than a hundred (Wet_BulbS)";
     case CTSM_ERR_URBAN: return "urban column in filter is outside the ctsm_b200 hot path";
     case CTSM_ERR_BALANCE: return "BalanceCheck: balance error exceeds threshold / c2g: sumwt is greater than 1.0";
     default: return "";
@@ -210,7 +212,7 @@ void decode_status(const DevStatus& ds, ctsm_status_t* st) {
   st->info = info;
   if (st->code == CTSM_ERR_BALANCE) st->subgrid_level = CTSM_SUBGRID_GRIDCELL;     /* device-side: the c2g weight check */
   else st->subgrid_level = (st->code == CTSM_ERR_FORC_HGT || st->code == CTSM_ERR_GS_NEG || st->code == CTSM_ERR_BRENT ||
-                       st->code == CTSM_ERR_QUADRATIC) ? CTSM_SUBGRID_PATCH : CTSM_SUBGRID_COLUMN;
+                       st->code == CTSM_ERR_QUADRATIC || st->code == CTSM_ERR_RH) ? CTSM_SUBGRID_PATCH : CTSM_SUBGRID_COLUMN;
   snprintf(st->msg, sizeof st->msg, "%s", message_for(st->code));
 }
 

@@ -73,7 +73,7 @@ enum Slot {
 struct CanopyPrm {
   double dtime;
   int itmax, use_undercanopy_stability, use_biomass_heat_storage, z0param_method, soil_resis_method, use_luna,
-      medlyn, light_inhibit, modifyphoto_and_lmr_forcrop;
+      medlyn, light_inhibit, modifyphoto_and_lmr_forcrop, human_fast;
   double lai_dl, z_dl, a_coef, a_exp, csoilc, cv, wind_min, zetamaxstable, leaf_mr_vcm;
   double act25, fnr, cp25_yr2000, kc25_coef, ko25_coef, fnps, theta_psii, theta_ip;
   double vcmaxha, jmaxha, tpuha, lmrha, kcha, koha, cpha, vcmaxhd, jmaxhd, tpuhd, lmrhd, lmrse;
@@ -1612,6 +1612,36 @@ canopy_final_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int32_t* __
   const double rh = fmin(100.0, q_ref2m / q2.qs * 100.0);
   PF(rh_ref2m) = rh; PF(rh_ref2m_r) = rh;
   PF(vpd_ref2m) = q2.es * (1.0 - rh / 100.0);
+  if (prm.human_fast) {                                   // fast human stress indices :1550-1570 (HumanIndexMod.F90)
+    const double tc = t_ref2m - tfrz;                     // KtoC :1205
+    PF(tc_ref2m) = tc;
+    const double vap = (rh / 100.0) * q2.es;              // VaporPres :1243
+    PF(vap_ref2m) = vap;
+    if (rh < 0.0 || rh > 100.0) report_failure(ds, pp + g.begp0, CTSM_ERR_RH, 0);       // Wet_BulbS :1016-1022
+    const double wbt = tc * atan(0.151977 * sqrt(rh + 8.313659)) + atan(tc + rh) - atan(rh - 1.676331)
+                       + 0.00391838 * pow(rh, (3.0 / 2.0)) * atan(0.023101 * rh) - 4.686035;
+    PF(wbt_ref2m) = wbt; PF(wbt_ref2m_r) = wbt;
+    const double tf = (tc) * 9.0 / 5.0 + 32.0;            // HeatIndex :1039-1095
+    double hi;
+    if (tf < 68.0) hi = tf;
+    else hi = -42.379 + 2.04901523 * tf + 10.14333127 * rh + (-0.22475541 * tf * rh) + (-6.83783e-3 * (tf * tf))
+              + (-5.481717e-2 * (rh * rh)) + 1.22874e-3 * (tf * tf) * rh + 8.5282e-4 * tf * (rh * rh)
+              + (-1.99e-6 * (tf * tf) * (rh * rh));
+    hi = (hi - 32.0) * 5.0 / 9.0;
+    PF(nws_hi_ref2m) = hi; PF(nws_hi_ref2m_r) = hi;
+    const double at = tc + 3.30 * vap / 1000.0 - 0.70 * PF(u10_clm) - 4.0;              // AppTemp :555
+    PF(appar_temp_ref2m) = at; PF(appar_temp_ref2m_r) = at;
+    const double sw = 0.567 * (tc) + 0.393 * vap / 100.0 + 3.94;                        // swbgt :596
+    PF(swbgt_ref2m) = sw; PF(swbgt_ref2m_r) = sw;
+    const double hx = tc + ((5.0 / 9.0) * (vap / 100.0 - 10.0));                        // hmdex :637
+    PF(humidex_ref2m) = hx; PF(humidex_ref2m_r) = hx;
+    const double Tc = fmin(tc, 50.0);                                                   // dis_coiS :715-761
+    double rhl = fmin(rh, 99.0);
+    rhl = fmax(rhl, 5.0);
+    const double rh_min = Tc * (-2.27) + 27.7;
+    const double dc = (Tc < -20.0 || rhl < rh_min) ? Tc : 0.5 * wbt + 0.5 * Tc;
+    PF(discomf_index_ref2mS) = dc; PF(discomf_index_ref2mS_r) = dc;
+  }
   PF(dlrad) = (1.0 - emv) * emg * forc_lwrad + emv * emg * sb * tb3 * (tb + 4.0 * dt_veg) * (1.0 - frs)
               + emv * emg * sb * tsi3 * (tsi + 4.0 * dt_stem) * frs;
   PF(ulrad) = ((1.0 - emg) * (1.0 - emv) * (1.0 - emv) * forc_lwrad
@@ -1648,6 +1678,22 @@ canopy_final_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int32_t* __
     if (gs > 0.0) iwue = fpsn / gs;
   }
   PF(iwue_ln) = iwue;
+  if (prm.use_luna) {                                     // Acc24_Climate_LUNA, LunaMod.F90:695-724 (call :1704)
+    const double tvd = PF(t_veg_day);
+    if (tvd != spval) {                                   // not the first day
+      if (sabv > 0) { PF(t_veg_day) = tvd + tv; PF(ndaysteps) = PF(ndaysteps) + 1; }
+      else { PF(t_veg_night) = PF(t_veg_night) + tv; PF(nnightsteps) = PF(nnightsteps) + 1; }
+      if (PF(nrad) >= 1) {                                // nlevcan = 1
+        const double tlaii = PF2(laisun_z, 0) + PF2(laisha_z, 0);
+        if (tlaii > 0.0) {
+          const double TRad = PF2(parsun_z, 0);           // :715 overrides the lai-weighted mean of :714
+          PF2(par24d_z, 0) = PF2(par24d_z, 0) + dtime * TRad;
+          if (TRad > PF2(par24x_z, 0)) PF2(par24x_z, 0) = TRad;
+        }
+      }
+      PF(fpsn24) = PF(fpsn24) + dtime * fpsn;
+    }
+  }
   if (fabs(err) > 0.1) atomicAdd(&ds->n_warnings, 1);       // :1746-1760
 }
 
@@ -1761,6 +1807,7 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   cp.use_biomass_heat_storage = p.use_biomass_heat_storage; cp.z0param_method = p.z0param_method;
   cp.soil_resis_method = p.soil_resis_method; cp.use_luna = p.use_luna; cp.medlyn = (p.stomatalcond_mtd == 2);
   cp.light_inhibit = p.light_inhibit; cp.modifyphoto_and_lmr_forcrop = p.modifyphoto_and_lmr_forcrop;
+  cp.human_fast = (p.calc_human_stress_indices == 1);
   cp.lai_dl = p.lai_dl; cp.z_dl = p.z_dl; cp.a_coef = p.a_coef; cp.a_exp = p.a_exp; cp.csoilc = p.csoilc; cp.cv = p.cv;
   cp.wind_min = p.wind_min; cp.zetamaxstable = p.zetamaxstable; cp.leaf_mr_vcm = p.leaf_mr_vcm;
   cp.act25 = p.act25; cp.fnr = p.fnr; cp.cp25_yr2000 = p.cp25_yr2000; cp.kc25_coef = p.kc25_coef; cp.ko25_coef = p.ko25_coef;

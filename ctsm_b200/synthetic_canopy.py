@@ -181,6 +181,18 @@ def canopy_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator
     wroot = -g(2.0e4, 1.0e5, npch)
     wxyl = wroot - g(0.0, 2.0e4, npch) - 1000.0 * S["htop"]
     S["vegwp"] = np.stack([wxyl - g(0.0, 2.0e4, npch), wxyl - g(0.0, 2.0e4, npch), wxyl, wroot])
+    # --- LUNA daily accumulators (Acc24_Climate_LUNA): some patches on their first day (spval: nothing accumulates),
+    # the rest part-way through a day.  Own generator: the stream of `rng` stays what it was before these fields existed.
+    r2 = np.random.Generator(np.random.PCG64(977 + 31 * npch))
+    first_day = r2.random(npch) < 0.15
+    nday = r2.integers(0, 24, npch).astype(np.int32)
+    nnight = r2.integers(0, 24, npch).astype(np.int32)
+    S["t_veg_day"] = np.where(first_day, 1.0e36, nday * r2.uniform(270.0, 300.0, npch))
+    S["t_veg_night"] = np.where(first_day, 1.0e36, nnight * r2.uniform(265.0, 290.0, npch))
+    S["ndaysteps"], S["nnightsteps"] = nday, nnight
+    S["par24d_z"] = (nday * 1800.0 * r2.uniform(0.0, 150.0, npch))[None, :]
+    S["par24x_z"] = r2.uniform(0.0, 300.0, npch)[None, :]
+    S["fpsn24"] = nday * 1800.0 * r2.uniform(0.0, 10.0, npch)
     # --- outputs: recognisable fill so untouched elements are visible
     fill = 1.0e36
     for fs_ in abi.FIELDS["canopyfluxes"]:

@@ -91,6 +91,7 @@ enum {
   CTSM_ERR_BRENT = 14,          /* PhotosynthesisMod.F90:4134-4137 root must be bracketed for brent */
   CTSM_ERR_QUADRATIC = 15,      /* quadraticMod.F90:42-58 */
   CTSM_ERR_URBAN = 16,          /* urban column in filter: outside the hot path */
+  CTSM_ERR_RH = 17,             /* HumanIndexMod.F90:1016-1022 Wet_BulbS: 2 m relative humidity outside [0, 100] */
   CTSM_ERR_BALANCE = 20         /* BalanceCheckMod.F90:640-659,1060-1114 thresholds exceeded */
 };
 
@@ -147,7 +148,8 @@ typedef struct ctsm_params_t {
                                          * members; patch%itype indexes the table directly, so a perturbed-parameter
                                          * ensemble (BASELINE config 5) runs member m's patches with itype = m*(mxpft+1)+pft.
                                          * Default CTSM_MXPFT+1 (one parameter set: pftcon as the reference holds it). */
-  int32_t reserved_i[6];
+  int32_t calc_human_stress_indices;    /* 0 = NONE, 1 = FAST (clm5/clm6 default; HumanIndexMod.F90:496-547), ALL is not built */
+  int32_t reserved_i[5];
   double  reserved_d[8];
 } ctsm_params_t;
 

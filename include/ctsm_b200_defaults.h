@@ -47,6 +47,7 @@ static inline void ctsm_default_params_fill(ctsm_params_t* p) {
   p->vcmaxhd = 200000.0; p->jmaxhd = 200000.0; p->tpuhd = 200000.0; p->lmrhd = 150650.0; p->lmrse = 490.0;
   p->tpu25ratio = 0.167; p->kp25ratio = 20000.0;
   p->vcmaxse_sf = 1.0; p->jmaxse_sf = 1.0; p->tpuse_sf = 1.0; p->jmax25top_sf = 1.0;
+  p->calc_human_stress_indices = 1;      // FAST: namelist_defaults_ctsm.xml:235
   p->balance_skip_steps = -1;
   p->npft_table = CTSM_MXPFT + 1;
 }

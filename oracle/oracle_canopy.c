@@ -674,6 +674,42 @@ int oracle_canopyfluxes(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, i
     P1(rh_ref2m, p) = fmin(100.0, P1(q_ref2m, p) / qsat_ref2m * 100.0);
     P1(rh_ref2m_r, p) = P1(rh_ref2m, p);
     P1(vpd_ref2m, p) = e_ref2m * (1.0 - P1(rh_ref2m, p) / 100.0);
+    if (prm->calc_human_stress_indices == 1) {                          /* fast_human_stress_indices :1550-1570 */
+      const double rh = P1(rh_ref2m, p);
+      const double tc = P1(t_ref2m, p) - tfrz;                          /* KtoC, HumanIndexMod.F90:1205 */
+      P1(tc_ref2m, p) = tc;
+      const double vap = (rh / 100.0) * e_ref2m;                        /* VaporPres :1243 */
+      P1(vap_ref2m, p) = vap;
+      if ((rh < 0.0 || rh > 100.0) && !ctx.err_code) { ctx.err_code = CTSM_ERR_RH; ctx.err_index = p; }   /* Wet_BulbS :1016-1022 endrun */
+      const double wbt = tc * atan(0.151977 * sqrt(rh + 8.313659)) + atan(tc + rh) - atan(rh - 1.676331)
+                         + 0.00391838 * pow(rh, (3.0 / 2.0)) * atan(0.023101 * rh) - 4.686035;        /* :1024-1027 */
+      P1(wbt_ref2m, p) = wbt;
+      const double tf = (tc) * 9.0 / 5.0 + 32.0;                        /* HeatIndex :1039-1095 */
+      double hi;
+      if (tf < 68.0) hi = tf;
+      else hi = -42.379 + 2.04901523 * tf + 10.14333127 * rh + (-0.22475541 * tf * rh) + (-6.83783e-3 * (tf * tf))
+                + (-5.481717e-2 * (rh * rh)) + 1.22874e-3 * (tf * tf) * rh + 8.5282e-4 * tf * (rh * rh)
+                + (-1.99e-6 * (tf * tf) * (rh * rh));
+      hi = (hi - 32.0) * 5.0 / 9.0;
+      P1(nws_hi_ref2m, p) = hi;
+      P1(appar_temp_ref2m, p) = tc + 3.30 * vap / 1000.0 - 0.70 * P1(u10_clm, p) - 4.0;               /* AppTemp :555 */
+      P1(swbgt_ref2m, p) = 0.567 * (tc) + 0.393 * vap / 100.0 + 3.94;                                 /* swbgt :596 */
+      P1(humidex_ref2m, p) = tc + ((5.0 / 9.0) * (vap / 100.0 - 10.0));                               /* hmdex :637 */
+      {                                                                                               /* dis_coiS :715-761 */
+        const double Tc = fmin(tc, 50.0);
+        double rhl = fmin(rh, 99.0);
+        rhl = fmax(rhl, 5.0);
+        const double rh_min = Tc * (-2.27) + 27.7;
+        if (Tc < -20.0 || rhl < rh_min) P1(discomf_index_ref2mS, p) = Tc;
+        else P1(discomf_index_ref2mS, p) = 0.5 * wbt + 0.5 * Tc;
+      }
+      P1(wbt_ref2m_r, p) = P1(wbt_ref2m, p);
+      P1(nws_hi_ref2m_r, p) = P1(nws_hi_ref2m, p);
+      P1(appar_temp_ref2m_r, p) = P1(appar_temp_ref2m, p);
+      P1(swbgt_ref2m_r, p) = P1(swbgt_ref2m, p);
+      P1(humidex_ref2m_r, p) = P1(humidex_ref2m, p);
+      P1(discomf_index_ref2mS_r, p) = P1(discomf_index_ref2mS, p);
+    }
     P1(dlrad, p) = (1.0 - emv) * emg * forc_lwrad + emv * emg * sb * tb3 * (tb + 4.0 * A(dt_veg, p)) * (1.0 - frs)
                    + emv * emg * sb * tsi3 * (tsi + 4.0 * A(dt_stem, p)) * frs;
     P1(ulrad, p) = ((1.0 - emg) * (1.0 - emv) * (1.0 - emv) * forc_lwrad
@@ -709,6 +745,29 @@ int oracle_canopyfluxes(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, i
       else P1(iwue_ln, p) = spval;
     } else {
       P1(iwue_ln, p) = spval;
+    }
+  }
+  if (prm->use_luna) {                                                 /* Acc24_Climate_LUNA, LunaMod.F90:695-724 (call :1704) */
+    for (int f = 0; f < fn; ++f) {
+      const int p = filterp[f];
+      if (P1(t_veg_day, p) != spval) {                                 /* not the first day */
+        if (P1(sabv, p) > 0) {
+          P1(t_veg_day, p) = P1(t_veg_day, p) + P1(t_veg, p);
+          P1(ndaysteps, p) = P1(ndaysteps, p) + 1;
+        } else {
+          P1(t_veg_night, p) = P1(t_veg_night, p) + P1(t_veg, p);
+          P1(nnightsteps, p) = P1(nnightsteps, p) + 1;
+        }
+        for (int z = 1; z <= P1(nrad, p); ++z) {
+          const double tlaii = P2(laisun_z, p, z, 1) + P2(laisha_z, p, z, 1);
+          if (tlaii > 0.0) {
+            const double TRad = P2(parsun_z, p, z, 1);                 /* :715 overrides the lai-weighted mean of :714 */
+            P2(par24d_z, p, z, 1) = P2(par24d_z, p, z, 1) + dtime * TRad;
+            if (TRad > P2(par24x_z, p, z, 1)) P2(par24x_z, p, z, 1) = TRad;
+          }
+        }
+        P1(fpsn24, p) = P1(fpsn24, p) + dtime * P1(fpsn, p);
+      }
     }
   }
   for (int f = 0; f < fn; ++f) {                                       /* :1746-1760 */

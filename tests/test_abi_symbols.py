@@ -66,7 +66,7 @@ def test_ctypes_mirrors_have_the_c_layout(tmp_path):
     probes = {"ctsm_bounds_t": (abi.Bounds, ["begg", "endp", "clump_index"]),
               "ctsm_status_t": (abi.Status, ["code", "value", "n_warnings", "msg"]),
               "ctsm_params_t": (abi.Params, ["abi_version", "dtime", "e_ice", "itmax_canopy_fluxes", "lai_dl", "jmax25top_sf",
-                                             "balance_skip_steps", "npft_table", "reserved_i", "reserved_d"]),
+                                             "balance_skip_steps", "npft_table", "calc_human_stress_indices", "reserved_i", "reserved_d"]),
               "ctsm_balance_report_t": (abi.BalanceReport, ["max_abs", "index", "warn", "abort_kind", "skip_steps"]),
               "ctsm_filter_inputs_t": (abi.FilterInputs, ["alloc", "col_active", "melt_replaced_by_ice_grc", "include_inactive",
                                                           "npcropmax"]),

@@ -104,7 +104,7 @@ def test_config4_full_step_f02_slab(gpu_ctx, oracle_lib):
         ctx.close()
     # ---- compare ----
     _, sens = canopy_sensitivity(sg, S, prm0, nth)
-    worst, ntie = compare_canopy(sg, got, ref, S, sens=sens)
+    worst, ntie = compare_canopy(sg, got, ref, S, sens=sens, check_inputs=False)   # later routines update canopy inputs
     # ill-conditioned patches (tests/test_gpu_canopy.py: the oracle itself moves under 1-ulp libm noise) carry a larger
     # error into their column's soil state (SoilTemperature reads their fluxes): those columns are compared at 1e-3,
     # all others at 1e-10

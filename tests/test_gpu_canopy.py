@@ -94,7 +94,7 @@ def canopy_sensitivity(sg, S, prm, nthreads=None):
     return base, sens
 
 
-def compare(sg, got, ref, init=None, lag_rtol=None, sens=None):
+def compare(sg, got, ref, init=None, lag_rtol=None, sens=None, check_inputs=True):
     fe = sg.filters["exposedvegp"] - 1
     ties = got["num_iter"][fe] != ref["num_iter"][fe]
     ntie = int(ties.sum())
@@ -131,7 +131,8 @@ def compare(sg, got, ref, init=None, lag_rtol=None, sens=None):
     for fs in abi.FIELDS["canopyfluxes"]:
         a, b = got[fs.name], ref[fs.name]
         if fs.intent == "IN":
-            assert np.array_equal(a, b), "input %s was modified" % fs.name
+            if check_inputs:
+                assert np.array_equal(a, b), "input %s was modified" % fs.name
             continue
         skip = tie_p if fs.sub == "PATCH" else tie_c
         a, b = a[..., ~skip], b[..., ~skip]
@@ -155,7 +156,11 @@ def compare(sg, got, ref, init=None, lag_rtol=None, sens=None):
             op = 1800.0 * np.maximum(np.abs(ref["qflx_tran_veg"]), np.abs(ref["qflx_evap_veg"]))
             den = np.maximum(den, op[~skip][fin])
         if fs.name == "u10":
-            den = np.maximum(den, 0.1 * scale)       # ur - ustar/vkc*(...) : difference of O(ur) terms, can cross zero
+            # u10 = ur - ustar/vkc*(...) (FrictionVelocityMod.F90:1101): a difference of O(ur) terms that can cross zero; the
+            # error scale is that of its operands, ur and ur - u10
+            gi = ref["gridcell"] - 1
+            ur = np.maximum(1.0, np.sqrt(ref["forc_u"][gi] ** 2 + ref["forc_v"][gi] ** 2))
+            den = np.maximum(den, np.maximum(ur, np.abs(ur - b))[~skip][fin])
         if fs.name == "dhsdt_canopy":
             den = np.maximum(den, 1e-3 * scale)      # (t_veg - tl_ini)*cp_leaf/dtime cancels when the leaf barely moved
         if fs.name == "eflx_sh_stem":

@@ -43,6 +43,7 @@ def test_default_params_follow_clm6_0_namelist_defaults():
     assert p.modifyphoto_and_lmr_forcrop == _logical(GOLD["modifyphoto_and_lmr_forcrop"])
     assert p.zetamaxstable == _real(GOLD["zetamaxstable"])
     assert p.leaf_mr_vcm == _real(GOLD["leaf_mr_vcm"])
+    assert p.calc_human_stress_indices == {"NONE": 0, "FAST": 1, "ALL": 2}[GOLD["calc_human_stress_indices"]]
     assert p.nlevsno == int(GOLD["nlevsno"])
     assert GOLD["soil_layerstruct_predefined"] == "20SL_8.5m" and (p.nlevsoi, p.nlevgrnd) == (20, 25)
     assert int(GOLD["soilwater_movement_method"]) == 1      # moisture form + adaptive time stepping: the only one built

@@ -88,3 +88,66 @@ def test_qsat_and_moninobuk_sanity(oracle_lib):
     assert um.value == 3.0 and obu.value > 0      # stable
     oracle_lib.oracle_moninobukini(2.0, 3.0, 290.0, -1.5, 30.0, 0.5, C.byref(um), C.byref(obu))
     assert abs(um.value - np.sqrt(9.25)) < 1e-15 and obu.value < 0
+
+
+def test_fast_human_stress_indices_and_luna_accumulators_match_numpy(oracle_lib):
+    """the outputs CanopyFluxes writes under the default namelist besides the fluxes - HumanIndexMod's
+    FAST indices (CanopyFluxesMod.F90:1550-1583) and LUNA's daily accumulators (Acc24_Climate_LUNA, LunaMod.F90:695-724) -
+    restated independently in numpy from the oracle's own 2 m diagnostics."""
+    import ctypes as C
+    import numpy as np
+    from ctsm_b200 import abi, synthetic_canopy
+    from tests.util import copy_state
+    sg, S = synthetic_canopy.make_full_case(300, seed=17)
+    prm = abi.default_params()
+    R = copy_state(S)
+    st = abi.Status()
+    f = abi.make_struct("canopyfluxes", R, sg.bounds)
+    fe = sg.filters["exposedvegp"]
+    assert oracle_lib.oracle_canopyfluxes(C.byref(prm), C.byref(sg.bounds), len(fe), abi.i32p(fe), C.byref(f), C.byref(st)) == 0
+    p = fe - 1
+    tc = R["t_ref2m"][p] - 273.15
+    rh = R["rh_ref2m"][p]
+    es = R["vpd_ref2m"][p] / np.where(rh < 100.0, 1.0 - rh / 100.0, np.nan)           # e_ref2m from the vpd the routine wrote
+    ok = np.isfinite(es)
+    vap = R["vap_ref2m"][p]
+    assert np.allclose(vap[ok], rh[ok] / 100.0 * es[ok], rtol=1e-9)
+    assert np.array_equal(R["tc_ref2m"][p], tc)
+    wbt = tc * np.arctan(0.151977 * np.sqrt(rh + 8.313659)) + np.arctan(tc + rh) - np.arctan(rh - 1.676331) \
+        + 0.00391838 * rh ** 1.5 * np.arctan(0.023101 * rh) - 4.686035
+    assert np.allclose(R["wbt_ref2m"][p], wbt, rtol=1e-12, atol=1e-12)
+    tf = tc * 9.0 / 5.0 + 32.0
+    hi = np.where(tf < 68.0, tf, -42.379 + 2.04901523 * tf + 10.14333127 * rh - 0.22475541 * tf * rh - 6.83783e-3 * tf ** 2
+                  - 5.481717e-2 * rh ** 2 + 1.22874e-3 * tf ** 2 * rh + 8.5282e-4 * tf * rh ** 2 - 1.99e-6 * tf ** 2 * rh ** 2)
+    assert np.allclose(R["nws_hi_ref2m"][p], (hi - 32.0) * 5.0 / 9.0, rtol=1e-12, atol=1e-11)
+    assert np.allclose(R["appar_temp_ref2m"][p], tc + 3.3 * vap / 1000.0 - 0.7 * R["u10_clm"][p] - 4.0, rtol=1e-12, atol=1e-12)
+    assert np.allclose(R["swbgt_ref2m"][p], 0.567 * tc + 0.393 * vap / 100.0 + 3.94, rtol=1e-12, atol=1e-12)
+    assert np.allclose(R["humidex_ref2m"][p], tc + 5.0 / 9.0 * (vap / 100.0 - 10.0), rtol=1e-12, atol=1e-12)
+    Tc = np.minimum(tc, 50.0); rhl = np.clip(rh, 5.0, 99.0)
+    dc = np.where((Tc < -20.0) | (rhl < Tc * -2.27 + 27.7), Tc, 0.5 * wbt + 0.5 * Tc)
+    assert np.allclose(R["discomf_index_ref2mS"][p], dc, rtol=1e-12, atol=1e-12)
+    for k in ("wbt_ref2m", "nws_hi_ref2m", "appar_temp_ref2m", "swbgt_ref2m", "humidex_ref2m", "discomf_index_ref2mS"):
+        assert np.array_equal(R[k + "_r"][p], R[k][p])
+    # LUNA accumulators
+    live = S["t_veg_day"][p] != 1.0e36
+    day = S["sabv"][p] > 0
+    assert live.any() and (~live).any() and day.any() and (~day).any()
+    tv = R["t_veg"][p]
+    assert np.array_equal(R["t_veg_day"][p], np.where(live & day, S["t_veg_day"][p] + tv, S["t_veg_day"][p]))
+    assert np.array_equal(R["t_veg_night"][p], np.where(live & ~day, S["t_veg_night"][p] + tv, S["t_veg_night"][p]))
+    assert np.array_equal(R["ndaysteps"][p], S["ndaysteps"][p] + (live & day))
+    assert np.array_equal(R["nnightsteps"][p], S["nnightsteps"][p] + (live & ~day))
+    assert np.array_equal(R["fpsn24"][p], np.where(live, S["fpsn24"][p] + 1800.0 * R["fpsn"][p], S["fpsn24"][p]))
+    lai = (S["laisun_z"][0, p] + S["laisha_z"][0, p] > 0) & (S["nrad"][p] >= 1) & live
+    par = S["parsun_z"][0, p]
+    assert np.array_equal(R["par24d_z"][0, p], np.where(lai, S["par24d_z"][0, p] + 1800.0 * par, S["par24d_z"][0, p]))
+    assert np.array_equal(R["par24x_z"][0, p], np.where(lai & (par > S["par24x_z"][0, p]), par, S["par24x_z"][0, p]))
+    # patches outside the filter keep their fill / state
+    out = np.setdiff1d(np.arange(sg.npatch), p)
+    assert np.all(R["tc_ref2m"][out] == 1.0e36) and np.array_equal(R["fpsn24"][out], S["fpsn24"][out])
+    # NONE switches the indices off
+    prm.calc_human_stress_indices = 0
+    R0 = copy_state(S)
+    f0 = abi.make_struct("canopyfluxes", R0, sg.bounds)
+    assert oracle_lib.oracle_canopyfluxes(C.byref(prm), C.byref(sg.bounds), len(fe), abi.i32p(fe), C.byref(f0), C.byref(st)) == 0
+    assert np.all(R0["wbt_ref2m"] == 1.0e36) and np.array_equal(R0["t_veg"], R["t_veg"])

@@ -17,10 +17,9 @@ sg, S = synthetic_canopy.make_full_case(size, seed=seed)
 OL = oracle.lib()
 OL.oracle_set_num_threads(len(os.sched_getaffinity(0)))
 prm = abi.default_params()
-ref, got = copy_state(S), copy_state(S)
-clumps, keep = oracle.make_clumps(sg, 64)
-fc = abi.make_struct("canopyfluxes", ref, sg.bounds)
-assert OL.oracle_step_clumps(C.byref(prm), len(clumps), clumps, None, None, C.byref(fc), 4) == 0
+from tests.test_gpu_canopy import canopy_sensitivity
+got = copy_state(S)
+ref, sens = canopy_sensitivity(sg, S, prm)
 L = abi.lib()
 ctx = C.c_void_p()
 assert L.ctsm_b200_init(C.byref(prm), C.byref(ctx)) == 0
@@ -43,14 +42,16 @@ for lo, hi in ((3, 5), (6, 10), (11, 15), (16, 20), (21, 30), (31, 40), (41, 41)
         e = emax[m]
         print("num_iter %2d-%2d: %7d patches  max err %.2e  >1e-10: %5d  >1e-8: %4d  >1e-6: %3d" % (
             lo, hi, m.sum(), e.max(), (e > 1e-10).sum(), (e > 1e-8).sum(), (e > 1e-6).sum()))
-bad = np.nonzero((emax > 1e-10) & (ni_r < 41))[0]
-print("non-capped patches beyond 1e-10:", len(bad))
+print("ill-conditioned by the probe (sens > 1e-11):", int((sens > 1e-11).sum()), " GPU beyond 1e-10:", int((emax > 1e-10).sum()),
+      " beyond 1e-10 but NOT flagged:", int(((emax > 1e-10) & ~(sens > 1e-11)).sum()))
+bad = np.nonzero((emax > 1e-10) & ~(sens > 1e-11))[0]
+print("unflagged patches beyond 1e-10:", len(bad))
 order = bad[np.argsort(-emax[bad])][:25]
 night = S["parsun_z"][0, fe] <= 0
 for i in order:
     p = fe[i]
-    print("  p=%d ni=%d/%d night=%d emax=%.2e %s btran=%.4f/%.4f bsun %.4f/%.4f tran=%.3e/%.3e tveg=%.6f/%.6f vegwp_root=%.1f" % (
-        p + 1, ni_r[i], ni_g[i], night[i], emax[i], {k: "%.1e" % v[i] for k, v in errs.items()},
+    print("  p=%d sens=%.1e ni=%d/%d night=%d emax=%.2e %s btran=%.4f/%.4f bsun %.4f/%.4f tran=%.3e/%.3e tveg=%.6f/%.6f vegwp_root=%.1f" % (
+        p + 1, sens[i], ni_r[i], ni_g[i], night[i], emax[i], {k: "%.1e" % v[i] for k, v in errs.items()},
         ref["btran"][p], got["btran"][p], ref["bsun"][p], got["bsun"][p], ref["qflx_tran_veg"][p], got["qflx_tran_veg"][p],
         ref["t_veg"][p], got["t_veg"][p], ref["vegwp"][3, p]))
 L.ctsm_b200_finalize(ctx)
