@@ -274,7 +274,7 @@ def lib():
     L.ctsm_b200_last_cuda_error.restype = C.c_char_p
     L.ctsm_b200_set_member_params.argtypes = [vp, C.c_int, f64p, f64p, f64p, f64p, f64p, i32p, C.c_int, C.c_int]
     L.ctsm_b200_set_member_params.restype = C.c_int
-    L.ctsm_b200_set_tuning.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.ctsm_b200_set_tuning.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.ctsm_b200_set_tuning.restype = C.c_int
     L.ctsm_b200_host_window_begin.argtypes = [vp]
     L.ctsm_b200_host_window_begin.restype = C.c_int

@@ -54,6 +54,7 @@ extern "C" int ctsm_b200_init(const ctsm_params_t* p, ctsm_b200_ctx** out) {
   if (const char* e = getenv("CTSM_B200_TAIL_MAX")) ctx->tune.tail_max = atoi(e);
   if (const char* e = getenv("CTSM_B200_NT_BUDGET")) ctx->tune.nt_budget = atoi(e);
   if (const char* e = getenv("CTSM_B200_TAIL_LANES")) ctx->tune.tail_lanes = atoi(e);
+  if (const char* e = getenv("CTSM_B200_NT_SPLIT")) ctx->tune.nt_split = atoi(e);
   const int rc = [&]() -> int {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
@@ -100,8 +101,9 @@ extern "C" int ctsm_b200_finalize(ctsm_b200_ctx* ctx) {
   return CTSM_OK;
 }
 
-extern "C" int ctsm_b200_set_tuning(ctsm_b200_ctx* ctx, int tail_max, int nt_budget, int tail_lanes) {
+extern "C" int ctsm_b200_set_tuning(ctsm_b200_ctx* ctx, int tail_max, int nt_budget, int tail_lanes, int nt_split) {
   if (!ctx) return CTSM_ERR_BAD_ARG;
+  if (nt_split >= 0) ctx->tune.nt_split = nt_split;
   if (tail_max >= 0) ctx->tune.tail_max = tail_max;
   if (nt_budget >= 0) ctx->tune.nt_budget = nt_budget;
   if (tail_lanes >= 0) ctx->tune.tail_lanes = tail_lanes;

@@ -99,7 +99,8 @@ struct Geo {   // index bases / leading dimensions
 //   PHS solve is one calcstress.
 #define NQ_CI 4
 #define NQ_NT 4
-#define QROW (NBIN + 2 * (NQ_CI + NQ_NT) + 1)   // ints per pass: list count, queue counts, queue fetch heads, a spare
+#define QROW (NBIN + 2 * (NQ_CI + NQ_NT) + 1 + 2 * NQ_NT)   // ints per pass: list count, queue counts, queue fetch heads, a spare,
+                                                            // then per calcstress stage: runnable-solve count and fetch head (split path)
 struct Lists {
   int* counts;          // [npass + 2][QROW]: {bin counts[NBIN], ci count[NQ_CI], nt count[NQ_NT], ci head[NQ_CI], nt head[NQ_NT]}
   int* list_a;          // ping: [NBIN][cap]
@@ -1062,6 +1063,9 @@ canopy_leaf_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, const int32_t*
 #ifndef CI_REFILL_MIN
 #define CI_REFILL_MIN REFILL_MIN   // the same threshold serves the ci tasks (measured: 4 / 8 / 16 within 1 %)
 #endif
+#ifndef NT_SPLIT_REFILL
+#define NT_SPLIT_REFILL 8     // split path: refill the iterate kernel's lanes when this many are idle
+#endif
 #ifndef FIN_MIN
 #define FIN_MIN 16            // run the calcstress epilogue when at least this many lanes are waiting (for it or for work)
 #endif
@@ -1240,6 +1244,167 @@ phs_newton_quad_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, c
       } else {
         q_out[atomicAdd(n_out, 1)] = fi;
       }
+    }
+  }
+}
+
+// Split path for LARGE calcstress queues.  In phs_newton_kernel the prologue (newton_begin: getqflx, 25 % of a mean task)
+// and the epilogue (newton_finish: two Weibull curves, gs_from_qflx, for some a getvegwp with its 20-level sum; 40 %) run
+// for whichever lanes happen to wait, at 8..16 of 32 lanes.  They are uniform per task, so they get their own kernels with
+// one thread per queue entry (all lanes busy); the persistent kernel in between only iterates, and its refill is a
+// coalesced load of the 10-double solver state plus the patch's root-zone vectors.  Same functions, same arithmetic.
+struct NtState {          // structure of arrays over queue positions
+  double* v;              // [10][cap]: x[4], qsun, qsha, ls, lh, tk, grav1
+  int* w;                 // [cap]: iter | both << 8 | sha_only << 9 | night << 10 | flag << 11 | run << 12 | ejected << 13
+  int cap;
+};
+enum { NW_BOTH = 1 << 8, NW_SHA = 1 << 9, NW_NIGHT = 1 << 10, NW_FLAG = 1 << 11, NW_RUN = 1 << 12, NW_EJECT = 1 << 13 };
+__device__ __forceinline__ void nt_store(const NtState& S, int t, const phs::Newton& N, int extra) {
+  const size_t c = (size_t)S.cap;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) S.v[(size_t)i * c + t] = N.x[i];
+  S.v[4 * c + t] = N.qsun; S.v[5 * c + t] = N.qsha; S.v[6 * c + t] = N.ls; S.v[7 * c + t] = N.lh; S.v[8 * c + t] = N.tk;
+  S.v[9 * c + t] = N.grav1;
+  S.w[t] = (N.iter & 0xff) | (N.both ? NW_BOTH : 0) | (N.sha_only ? NW_SHA : 0) | (N.night ? NW_NIGHT : 0) | (N.flag ? NW_FLAG : 0) | extra;
+}
+__device__ __forceinline__ int nt_load(const NtState& S, int t, phs::Newton& N) {
+  const size_t c = (size_t)S.cap;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) N.x[i] = S.v[(size_t)i * c + t];
+  N.qsun = S.v[4 * c + t]; N.qsha = S.v[5 * c + t]; N.ls = S.v[6 * c + t]; N.lh = S.v[7 * c + t]; N.tk = S.v[8 * c + t];
+  N.grav1 = S.v[9 * c + t];
+  const int w = S.w[t];
+  N.iter = w & 0xff; N.both = (w & NW_BOTH) != 0; N.sha_only = (w & NW_SHA) != 0; N.night = (w & NW_NIGHT) != 0; N.flag = (w & NW_FLAG) != 0;
+  return w;
+}
+
+__global__ void __launch_bounds__(128)
+nt_begin_kernel(const PhsRec* __restrict__ rec, const int* __restrict__ q_in, const int* __restrict__ n_in, NtState S,
+                int* __restrict__ run_list, int* __restrict__ n_run) {
+  const int n = *n_in;
+  if (n <= QUAD_MAX) return;                            // small queues: phs_newton_quad_kernel
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const int t = base + threadIdx.x;
+    bool run = false;
+    if (t < n) {
+      const PhsRec& R = rec[q_in[t]];
+      if (!(R.flags & RF_FINAL)) {
+        phs::Newton N;
+        const double xin[4] = {R.x[0], R.x[1], R.x[2], R.x[3]};
+        run = phs::newton_begin(N, R, xin, R.gs0sun, R.gs0sha);
+        nt_store(S, t, N, run ? NW_RUN : 0);
+      }
+    }
+    const unsigned act = __activemask();
+    const unsigned m = __ballot_sync(act, run);
+    if (run) {
+      const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+      int b0 = 0;
+      if (lane == leader) b0 = atomicAdd(n_run, __popc(m));
+      b0 = __shfl_sync(m, b0, leader);
+      run_list[b0 + __popc(m & ((1u << lane) - 1))] = t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TASK_THREADS, NT_MINBLOCKS)
+nt_iter_kernel(const PhsRec* __restrict__ rec, const int* __restrict__ q_in, const int* __restrict__ n_in,
+               const int* __restrict__ run_list, const int* __restrict__ n_run, int* __restrict__ head, NtState S, Lists L,
+               int budget) {
+  extern __shared__ double shm[];                       // [2][NLEVSOI][TASK_THREADS]: k_soil_root, 1000 z
+  double* sk = shm + threadIdx.x;
+  double* sgv = shm + (size_t)NLEVSOI * TASK_THREADS + threadIdx.x;
+  if (*n_in <= QUAD_MAX) return;
+  const int n = *n_run;
+  const int lane = threadIdx.x & 31;
+  bool running = false, exhausted = (n <= 0);
+  int t = 0, fi = 0;
+  phs::Newton N;
+  phs::NewtonCtx P;
+  P.sk = sk; P.sg = sgv; P.stride = TASK_THREADS;
+  for (;;) {
+    const unsigned idle = __ballot_sync(FULL, !running);
+    if (!exhausted && (__popc(idle) >= NT_SPLIT_REFILL || idle == FULL)) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(head, __popc(idle));
+      base = __shfl_sync(FULL, base, 0);
+      if (base + __popc(idle) >= n) exhausted = true;
+      if (!running) {
+        const int my = base + __popc(idle & ((1u << lane) - 1));
+        if (my < n) {
+          t = run_list[my];
+          fi = q_in[t];
+          const PhsRec& R = rec[fi];
+          (void)nt_load(S, t, N);
+#pragma unroll
+          for (int s = 0; s < 4; ++s) { P.psi50[s] = R.psi50[s]; P.ck[s] = R.ck[s]; }
+          P.laisha = R.laisha; P.ksum = R.ksum; P.ksmp = R.ksmp;
+#pragma unroll 4
+          for (int j = 0; j < NLEVSOI; ++j) { sk[j * TASK_THREADS] = R.Kv[j]; sgv[j * TASK_THREADS] = R.Gv[j]; }
+          running = true;
+        }
+      }
+      continue;
+    }
+    if (idle == FULL) break;
+    bool ej = false;
+    if (running) {
+      bool more = phs::newton_step(N, P);
+      if (more && N.iter >= budget) { ej = true; more = false; }                  // a straggler: to the tail kernel
+      if (!more) { nt_store(S, t, N, ej ? NW_EJECT : 0); running = false; }
+    }
+    const unsigned em = __ballot_sync(FULL, ej);
+    if (em) {
+      queue_push(L.tail_list, L.tail_count, em, ej, fi | TAIL_B);
+      if (ej) L.ejected[fi] = 1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+nt_finish_kernel(PhsRec* __restrict__ rec, const int* __restrict__ q_in, const int* __restrict__ n_in, NtState S,
+                 int* __restrict__ q_out, int* __restrict__ n_out) {
+  const int n = *n_in;
+  if (n <= QUAD_MAX) return;
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const int t = base + threadIdx.x;
+    bool day = false;
+    int fi = 0;
+    if (t < n) {
+      fi = q_in[t];
+      PhsRec& R = rec[fi];
+      if (R.flags & RF_FINAL) {
+        double x[4];                                    // hybrid_PHS epilogue :4048-4062
+        double sf = phs::getvegwp(R, x, R.gs_sun, R.gs_sha);
+        if (sf < 0.0) sf = 0.0;
+        R.tran = sf;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) R.xo[i] = x[i];
+      } else {
+        phs::Newton N;
+        const int w = nt_load(S, t, N);
+        if (!(w & NW_EJECT)) {
+          double tran = 0.0;
+          const phs::Stress so = phs::newton_finish(N, R, R.gs0sun, R.gs0sha, &tran);
+          R.bsun = so.bsun; R.bsha = so.bsha;
+          if (R.flags & RF_NIGHT) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) R.xo[i] = N.x[i];
+            R.tran = tran;
+          } else {
+            day = true;
+          }
+        }
+      }
+    }
+    const unsigned act = __activemask();
+    const unsigned m = __ballot_sync(act, day);
+    if (day) {
+      const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+      int b0 = 0;
+      if (lane == leader) b0 = atomicAdd(n_out, __popc(m));
+      b0 = __shfl_sync(m, b0, leader);
+      q_out[b0 + __popc(m & ((1u << lane) - 1))] = fi;
     }
   }
 }
@@ -1838,13 +2003,21 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   const size_t n_counts = (size_t)QROW * (size_t)(npass + 2);
   const size_t n_tailc = 2 * (size_t)(npass + 2) + 2;        // tail_end[], tail_head[], tail_count
   const size_t ws_bytes = (sizeof(double) * (size_t)W_NSLOT * (size_t)(wstride > 0 ? wstride : 32) + 127) & ~(size_t)127;
-  int rc = arena_reserve(ctx, ctx->arena_scratch, ws_bytes + sizeof(PhsRec) * (size_t)(fn > 0 ? fn : 1));
+  const size_t rec_bytes = (sizeof(PhsRec) * (size_t)(fn > 0 ? fn : 1) + 127) & ~(size_t)127;
+  const bool nt_split = ctx->tune.nt_split != 0 && fn > QUAD_MAX;
+  const size_t nts_bytes = nt_split ? ((sizeof(double) * 10 + sizeof(int) * 2) * (size_t)fn + 256) : 0;   // NtState + run list
+  int rc = arena_reserve(ctx, ctx->arena_scratch, ws_bytes + rec_bytes + nts_bytes);
   if (rc) return rc;
   const size_t nq = (size_t)(2 * NBIN + NQ_CI + NQ_NT + 2);
   rc = reserve_ints(ctx, ctx->arena_ints, (size_t)g.ldc + nq * (size_t)fn + n_counts + n_tailc + 64);
   if (rc) return rc;
   double* ws = (double*)ctx->arena_scratch.p;
   PhsRec* rec = (PhsRec*)((char*)ctx->arena_scratch.p + ws_bytes);
+  NtState nts;
+  nts.v = (double*)((char*)ctx->arena_scratch.p + ws_bytes + rec_bytes);
+  nts.w = (int*)(nts.v + (size_t)10 * fn);
+  nts.cap = fn;
+  int* run_list = nts.w + fn;
   int* ip = (int*)ctx->arena_ints.p;
   Lists L;
   L.colflag = ip; ip += g.ldc;
@@ -1881,6 +2054,10 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, phs_ci_kernel, TASK_THREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, canopy_close_kernel, STEP_THREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, canopy_tail_kernel, TAIL_THREADS, 0);
+    int occ_i = 1;
+    CUDA_TRY(cudaFuncSetAttribute(nt_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shbytes));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_i, nt_iter_kernel, TASK_THREADS, shbytes);
+    if (occ_i < 1) occ_i = 1;
     if (occ_n < 1) occ_n = 1;
     if (occ_c < 1) occ_c = 1;
     if (occ_s < 1) occ_s = 1;
@@ -1889,6 +2066,9 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
     const int need_t = grid_for(fn, TASK_THREADS);
     const int grid_n = need_t < sms * occ_n ? need_t : sms * occ_n;
     const int grid_c = need_t < sms * occ_c ? need_t : sms * occ_c;
+    const int grid_i = need_t < sms * occ_i ? need_t : sms * occ_i;
+    const int need_u = grid_for(fn, 128);
+    const int grid_u = need_u < sms * 16 ? need_u : sms * 16;
     const int need_q = grid_for((fn < QUAD_MAX ? fn : QUAD_MAX) * 4, 128);
     const int grid_q = need_q < sms * 4 ? need_q : sms * 4;
     int grid_s = grid_for(fn + 32 * NBIN, STEP_THREADS);
@@ -1944,9 +2124,21 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
           const bool lastq = (i + 1 == NQ_CI);
           int* qo = L.q_ci + (size_t)(lastq ? 0 : i + 1) * cap;
           int* no = lastq ? spare : n_ci + i + 1;
-          phs_newton_kernel<<<grid_n, TASK_THREADS, shbytes, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, h_nt + i, qo, no, L, nt_budget);
+          if (nt_split) {
+            // large queues: prologue / iterations / epilogue as three kernels (see NtState); each exits at once on a small queue
+            int* n_run = spare + 1 + i;
+            int* h_run = spare + 1 + NQ_NT + i;
+            nt_begin_kernel<<<grid_u, 128, 0, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, nts, run_list, n_run);
+            nt_iter_kernel<<<grid_i, TASK_THREADS, shbytes, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, run_list, n_run, h_run, nts, L,
+                                                                 nt_budget);
+            nt_finish_kernel<<<grid_u, 128, 0, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, nts, qo, no);
+            ctx->launches += 3;
+          } else {
+            phs_newton_kernel<<<grid_n, TASK_THREADS, shbytes, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, h_nt + i, qo, no, L, nt_budget);
+            ctx->launches++;
+          }
           phs_newton_quad_kernel<<<grid_q, 128, 0, s>>>(rec, L.q_nt + (size_t)i * cap, n_nt + i, qo, no, L, nt_budget);
-          ctx->launches += 3;
+          ctx->launches += 2;
         }
         if (use_tail) {
           // everything ejected during this round (survivors of a short list, calcstress stragglers) runs to completion

@@ -43,9 +43,9 @@ class Context:
                    3: "device memory allocation failed", 4: "CUDA runtime error"}.get(rc, "error")
             raise RuntimeError("ctsm_b200_init failed (rc=%d): %s %s" % (rc, why, self.L.ctsm_b200_last_cuda_error().decode()))
 
-    def set_tuning(self, tail_max: int = -1, nt_budget: int = -1, tail_lanes: int = -1):
+    def set_tuning(self, tail_max: int = -1, nt_budget: int = -1, tail_lanes: int = -1, nt_split: int = -1):
         """Scheduling knobs of CanopyFluxes' ITERATION loop (include/ctsm_b200.h); results do not depend on them."""
-        self.L.ctsm_b200_set_tuning(self.h, tail_max, nt_budget, tail_lanes)
+        self.L.ctsm_b200_set_tuning(self.h, tail_max, nt_budget, tail_lanes, nt_split)
 
     def set_member_params(self, nmember, col_member, begc, endc, **tables):
         """Per-member values of e_ice / csoilc / cv / a_coef / z_dl (ctsm_b200_set_member_params)."""

@@ -294,9 +294,11 @@ int  ctsm_b200_set_member_params(ctsm_b200_ctx* ctx, int nmember, const double* 
  *               one thread per patch runs each through its remaining passes (0: never);
  *   nt_budget   a calcstress solve (PhotosynthesisMod.F90:4579) still running after this many Newton iterations sends
  *               its patch to the same tail kernel (0: never);
- *   tail_lanes  patches carried by one warp of the tail kernel (1..32).
+ *   tail_lanes  patches carried by one warp of the tail kernel (1..32);
+ *   nt_split    1 (default; CTSM_B200_NT_SPLIT): large calcstress queues run prologue / Newton iterations / epilogue as three
+ *               kernels, 0: as lane tasks of one persistent kernel.
  * A negative argument keeps the current value. */
-int  ctsm_b200_set_tuning(ctsm_b200_ctx* ctx, int tail_max, int nt_budget, int tail_lanes);
+int  ctsm_b200_set_tuning(ctsm_b200_ctx* ctx, int tail_max, int nt_budget, int tail_lanes, int nt_split);
 /* Diagnostic of the last ctsm_b200_canopyfluxes call (synchronises the stream): for every ITERATION round r < cap,
  * list_len[r] = patches the round's list kernels served, tail_end[r] = patches handed to the tail kernel up to and
  * including round r.  Returns the number of rounds written. */

@@ -232,15 +232,16 @@ def test_canopyfluxes_is_bit_reproducible(gpu_ctx):
             assert np.array_equal(a[fs.name], b[fs.name], equal_nan=True), fs.name
 
 
-def _with_tuning(L, ctx, tail_max, nt_budget, tail_lanes):
-    assert L.ctsm_b200_set_tuning(ctx, tail_max, nt_budget, tail_lanes) == 0
+def _with_tuning(L, ctx, tail_max, nt_budget, tail_lanes, nt_split=-1):
+    assert L.ctsm_b200_set_tuning(ctx, tail_max, nt_budget, tail_lanes, nt_split) == 0
 
 
-@pytest.mark.parametrize("mode", ["tail_after_round_8", "tail_from_round_1", "eject_every_newton", "lanes_32"])
+@pytest.mark.parametrize("mode", ["tail_after_round_8", "tail_from_round_1", "eject_every_newton", "lanes_32", "lane_task_newton",
+                                  "split_newton_with_budget"])
 def test_canopyfluxes_schedules_agree_bit_for_bit(gpu_ctx, mode):
-    """Where a patch leaves the list-driven bulk rounds for the per-patch tail kernel is a scheduling decision
-    (ctsm_b200_set_tuning): bulk only, everything in the tail from pass 1 on, every calcstress solve longer than two
-    iterations ejected mid-pass, 32 patches per tail warp - all give the results of the default schedule bit for bit."""
+    """Where a patch leaves the list-driven bulk rounds for the per-patch tail kernel, and whether large calcstress queues
+    run as lane tasks of one kernel or as prologue / iterations / epilogue kernels, are scheduling decisions
+    (ctsm_b200_set_tuning): all give the results of the default schedule bit for bit."""
     L, ctx, prm = gpu_ctx
     sg, S = synthetic_canopy.make_full_case(6000, seed=31)
     a, b = copy_state(S), copy_state(S)
@@ -248,10 +249,11 @@ def test_canopyfluxes_schedules_agree_bit_for_bit(gpu_ctx, mode):
     assert run_gpu(L, ctx, sg, a, abi.MEM_DEVICE)[0] == 0
     try:
         _with_tuning(L, ctx, *{"tail_after_round_8": (32768, 16, 16), "tail_from_round_1": (1 << 30, 16, 8),
-                               "eject_every_newton": (4096, 2, 16), "lanes_32": (32768, 16, 32)}[mode])
+                               "eject_every_newton": (4096, 2, 16, 0), "lanes_32": (32768, 16, 32),
+                               "lane_task_newton": (0, 0, 1, 0), "split_newton_with_budget": (4096, 6, 8, 1)}[mode])
         assert run_gpu(L, ctx, sg, b, abi.MEM_DEVICE)[0] == 0
     finally:
-        _with_tuning(L, ctx, 0, 0, 1)
+        _with_tuning(L, ctx, 0, 0, 1, 1)
     for fs in abi.FIELDS["canopyfluxes"]:
         if fs.intent != "IN":
             assert np.array_equal(a[fs.name], b[fs.name], equal_nan=True), fs.name

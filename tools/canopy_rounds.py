@@ -9,7 +9,7 @@ from ctsm_b200 import abi, driver, synthetic_canopy
 
 size = sys.argv[1] if len(sys.argv) > 1 else "f09"
 size = int(size) if size.isdigit() else size
-confs = [tuple(int(x) for x in a.split(",")) for a in sys.argv[2:]] or [(32768, 16, 16)]
+confs = [tuple(int(x) for x in a.split(",")) for a in sys.argv[2:]] or [(0, 0, 1, 1)]
 sg, S = synthetic_canopy.make_full_case(size, seed=20260101)
 ctx = driver.Context(abi.default_params())
 names = [fs.name for fs in abi.FIELDS["canopyfluxes"]]
@@ -32,7 +32,7 @@ for conf in confs:
         ts.append(e0.elapsed_time(e1)); nl = ctx.launches - l0
     ll, te = np.zeros(64, np.int32), np.zeros(64, np.int32)
     n = ctx.L.ctsm_b200_canopy_round_stats(ctx.h, abi.i32p(ll), abi.i32p(te), 64)
-    print("conf tail_max=%d nt_budget=%d lanes=%d: ms %s launches %d" % (conf + (["%.2f" % t for t in ts], nl)))
+    print("conf %s (tail_max, nt_budget, lanes, nt_split): ms %s launches %d" % (conf, ["%.2f" % t for t in ts], nl))
     print("  list_len", ll[:n].tolist())
     print("  tail_new", np.diff(np.concatenate([[0], te[:n]])).tolist())
 ctx.close()
