@@ -37,6 +37,7 @@ class Context:
         self.L = abi.lib()
         self.prm = prm if prm is not None else abi.default_params()
         self.h = C.c_void_p()
+        self._pending = []      # objects the library writes at the next synchronisation (deferred BalanceCheck reports)
         rc = self.L.ctsm_b200_init(C.byref(self.prm), C.byref(self.h))
         if rc != 0:
             why = {1: "no usable CUDA device; there is no CPU fallback", 2: "bad argument / unsupported configuration",
@@ -65,6 +66,7 @@ class Context:
     def sync(self) -> abi.Status:
         st = abi.Status()
         rc = self.L.ctsm_b200_sync(self.h, C.byref(st))
+        self._pending.clear()
         if rc != 0:
             raise CtsmError(st, rc)
         return st
@@ -210,6 +212,7 @@ class HotPath:
     def BalanceCheck(self):
         """BalanceCheck + EnergyBalanceCheck over all columns in bounds (BalanceCheckMod.F90:445,859)"""
         st = abi.Status()
+        self.ctx._pending.append(self.balance_report)        # filled at the next sync when the call is asynchronous
         rc = self.ctx.L.ctsm_b200_balancecheck(
             self.ctx.h, C.byref(self.bounds), self.nfilter["allc"], abi.i32p(self.filters["allc"]),
             C.byref(self.structs["balancecheck"]), self.danstep, self.mem, C.byref(self.balance_report), C.byref(st))
@@ -273,6 +276,7 @@ class HotPath:
             if self.window:
                 st = abi.Status()
                 rc = self.ctx.L.ctsm_b200_host_window_end(self.ctx.h, C.byref(st))
+                self.ctx._pending.clear()
                 if rc != 0:
                     raise CtsmError(st, rc)
 
