@@ -859,7 +859,13 @@ __device__ __forceinline__ void fric_body(const CanopyDev& f, const CanopyPrm& p
   }
 }
 
-__global__ void __launch_bounds__(STEP_THREADS)
+#ifndef FRIC_MINBLOCKS
+#define FRIC_MINBLOCKS 1
+#endif
+#ifndef LEAF_MINBLOCKS
+#define LEAF_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(STEP_THREADS, FRIC_MINBLOCKS)
 canopy_fric_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, const int32_t* __restrict__ filterp,
                    double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in) {
   const int row = itlef0 + 1;
@@ -1031,7 +1037,7 @@ __device__ __forceinline__ void leaf_body(const CanopyDev& f, const CanopyPrm& p
   }
 }
 
-__global__ void __launch_bounds__(STEP_THREADS)
+__global__ void __launch_bounds__(STEP_THREADS, LEAF_MINBLOCKS)
 canopy_leaf_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, const int32_t* __restrict__ filterp,
                    double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in, PhsRec* __restrict__ rec,
                    DevStatus* ds) {
