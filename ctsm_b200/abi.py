@@ -304,6 +304,8 @@ def lib():
                                                    C.c_int]
     L.ctsm_b200_vert_tran_sink_hydstress.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p,
                                                      C.POINTER(STRUCTS["plantsink"]), C.c_int, C.POINTER(Status)]
+    L.ctsm_b200_vert_tran_sink_default.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p,
+                                                     C.POINTER(STRUCTS["plantsinkdefault"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_soilfluxes.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p,
                                        C.POINTER(STRUCTS["soilfluxes"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_begin_water_column_balance.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p,
@@ -320,7 +322,7 @@ def lib():
     L.ctsm_b200_balancecheck_init.argtypes = [vp]
     L.ctsm_b200_balancecheck.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.POINTER(STRUCTS["balancecheck"]),
                                          C.c_int, C.c_int, C.POINTER(BalanceReport), C.POINTER(Status)]
-    for fn in ("vert_tran_sink_hydstress", "balancecheck_init", "balancecheck", "soilfluxes", "patch2col"):
+    for fn in ("vert_tran_sink_hydstress", "vert_tran_sink_default", "balancecheck_init", "balancecheck", "soilfluxes", "patch2col"):
         getattr(L, "ctsm_b200_" + fn).restype = C.c_int
     for fn in ("init", "finalize", "sync", "host_register", "host_unregister", "tridiagonal", "banddiagonal",
                "dgtsv_batch", "soilwater", "soiltemperature", "canopyfluxes", "set_exposedvegp_filter"):

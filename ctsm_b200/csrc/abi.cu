@@ -32,7 +32,7 @@ extern "C" int ctsm_b200_init(const ctsm_params_t* p, ctsm_b200_ctx** out) {
             CTSM_NLEVGRND, CTSM_NLEVSOI);
     return CTSM_ERR_BAD_ARG;
   }
-  if (p->use_hydrstress != 1 || (p->z0param_method != 1 && p->z0param_method != 2) ||
+  if ((p->use_hydrstress != 0 && p->use_hydrstress != 1) || (p->z0param_method != 1 && p->z0param_method != 2) ||
       (p->stomatalcond_mtd != 1 && p->stomatalcond_mtd != 2) || p->itmax_canopy_fluxes < 1)
     return CTSM_ERR_BAD_ARG;
   if (p->calc_human_stress_indices != 0 && p->calc_human_stress_indices != 1) return CTSM_ERR_BAD_ARG;

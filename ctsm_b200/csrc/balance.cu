@@ -24,6 +24,13 @@ struct BalanceDev {
 #undef CTSM_FIELDS_BALANCECHECK
 #undef CTSM_F
 };
+struct PlantSinkDefaultDev {
+#define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) ctype* name;
+#define CTSM_FIELDS_PLANTSINKDEFAULT
+#include "../../include/ctsm_b200_fields.def"
+#undef CTSM_FIELDS_PLANTSINKDEFAULT
+#undef CTSM_F
+};
 struct PlantSinkDev {
 #define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) ctype* name;
 #define CTSM_FIELDS_PLANTSINK
@@ -212,6 +219,32 @@ plantsink_kernel(PlantSinkDev f, int begc0, int ldc, int begp0, int ldp, int num
     if (temp < 0.0) neg = neg + temp;
   }
   f.qflx_phs_neg[cc] = neg;
+}
+
+// Compute_EffecRootFrac_And_VertTranSink_Default (SoilWaterPlantSinkMod.F90:332-424): one thread per column, its contiguous
+// patches inner and ascending (the reference's summation order).  Levels nlevsoi+1..nlevgrnd of rootr_col are not touched.
+__global__ void __launch_bounds__(128)
+plantsink_default_kernel(PlantSinkDefaultDev f, int begc0, int ldc, int begp0, int ldp, int numf, const int32_t* __restrict__ filterc) {
+  const int fc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fc >= numf) return;
+  const int cc = filterc[fc] - begc0;
+  const int pi = f.patchi[cc], pf = pi + f.npatches[cc] - 1;
+  double temp = 0.0;
+  for (int p1 = pi; p1 <= pf; ++p1) {
+    const int pp = p1 - begp0;
+    if (f.patch_active[pp]) temp = temp + f.qflx_tran_veg[pp] * f.wtcol[pp];
+  }
+  const double tran_col = f.qflx_tran_veg_col[cc];
+  for (int j = 1; j <= NLEVSOI; ++j) {
+    double r = 0.0;
+    for (int p1 = pi; p1 <= pf; ++p1) {
+      const int pp = p1 - begp0;
+      if (f.patch_active[pp]) r = r + f.rootr[(size_t)(j - 1) * ldp + pp] * f.qflx_tran_veg[pp] * f.wtcol[pp];
+    }
+    if (temp != 0.0) r = r / temp;
+    f.rootr_col[(size_t)(j - 1) * ldc + cc] = r;
+    f.qflx_rootsoi[(size_t)(j - 1) * ldc + cc] = r * tran_col;
+  }
 }
 }  // namespace
 
@@ -663,6 +696,41 @@ extern "C" int ctsm_b200_vert_tran_sink_hydstress(ctsm_b200_ctx* ctx, const ctsm
   }
   if (num_filterc > 0) {
     plantsink_kernel<<<grid_for(num_filterc, 128), 128, 0, ctx->stream>>>(
+        d, hf->alloc.begc, hf->alloc.endc - hf->alloc.begc + 1, hf->alloc.begp, hf->alloc.endp - hf->alloc.begp + 1,
+        num_filterc, dfilter);
+    ctx->launches++;
+  }
+  if (mem != CTSM_MEM_DEVICE) {
+    int rc = stage_end(ctx, fl, hf->alloc, *bounds);
+    if (rc) return rc;
+  }
+  return finish_call(ctx, mem, st);
+}
+
+extern "C" int ctsm_b200_vert_tran_sink_default(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_filterc,
+                                                  const int32_t* filterc, const ctsm_plantsinkdefault_fields_t* hf, int mem,
+                                                  ctsm_status_t* st) {
+  if (!ctx || !bounds || !hf || num_filterc < 0 || (num_filterc > 0 && !filterc)) return CTSM_ERR_BAD_ARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  PlantSinkDefaultDev d;
+  const int32_t* dfilter = filterc;
+  std::vector<StageField> fl;
+#define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) \
+  d.name = hf->name;                                        \
+  fl.push_back(StageField{(void**)&d.name, (void*)hf->name, (int)sizeof(ctype), SUB_##sub, lev_shape(#lev).n, INTENT_##intent});
+#define CTSM_FIELDS_PLANTSINKDEFAULT
+#include "../../include/ctsm_b200_fields.def"
+#undef CTSM_FIELDS_PLANTSINKDEFAULT
+#undef CTSM_F
+  for (auto& s : fl) if (!s.host_ptr) return CTSM_ERR_BAD_ARG;
+  if (mem != CTSM_MEM_DEVICE) {
+    int rc = stage_begin(ctx, fl, hf->alloc, *bounds, mem == CTSM_MEM_HOST);
+    if (rc) return rc;
+    rc = stage_filter(ctx, ctx->arena_filter0, filterc, num_filterc, &dfilter);
+    if (rc) return rc;
+  }
+  if (num_filterc > 0) {
+    plantsink_default_kernel<<<grid_for(num_filterc, 128), 128, 0, ctx->stream>>>(
         d, hf->alloc.begc, hf->alloc.endc - hf->alloc.begc + 1, hf->alloc.begp, hf->alloc.endp - hf->alloc.begp + 1,
         num_filterc, dfilter);
     ctx->launches++;

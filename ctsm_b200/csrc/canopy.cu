@@ -73,7 +73,7 @@ enum Slot {
 struct CanopyPrm {
   double dtime;
   int itmax, use_undercanopy_stability, use_biomass_heat_storage, z0param_method, soil_resis_method, use_luna,
-      medlyn, light_inhibit, modifyphoto_and_lmr_forcrop, human_fast;
+      medlyn, light_inhibit, modifyphoto_and_lmr_forcrop, human_fast, hydrstress;
   double lai_dl, z_dl, a_coef, a_exp, csoilc, cv, wind_min, zetamaxstable, leaf_mr_vcm;
   double act25, fnr, cp25_yr2000, kc25_coef, ko25_coef, fnps, theta_psii, theta_ip;
   double vcmaxha, jmaxha, tpuha, lmrha, kcha, koha, cpha, vcmaxhd, jmaxhd, tpuhd, lmrhd, lmrse;
@@ -483,7 +483,7 @@ canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int32_t* __r
   // iteration-invariant part of PhotosynthesisHydraulicStress: root-soil interface conductance :3063-3114, and the
   // constant part of the patch's PHS record (segment parameters, leaf areas, root-zone vectors and their level sums)
   PhsRec& R = rec[fi];
-  {
+  if (prm.hydrstress) {
     const double froot_carbon = PF(froot_carbon), tsl = PF(tsai) + PF(tlai);
     const double rr = f.pft_root_radius[ivt], rd = f.pft_root_density[ivt], frl = f.pft_froot_leaf[ivt], krmax = f.pft_krmax[ivt];
     const double psi50r = f.pft_psi50[(size_t)phs::ROOT * g.npft + ivt], ckr = f.pft_ck[(size_t)phs::ROOT * g.npft + ivt];
@@ -515,7 +515,7 @@ canopy_init_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int32_t* __r
     R.ksum = ksum; R.ksmp = ksmp; R.ksmpg = ksmpg; R.smpg_mean = smpg / NLEVSOI;
   }
   const bool night = (PF2(parsun_z, 0) <= 0.0);
-  {
+  if (prm.hydrstress) {
 #pragma unroll
     for (int sgm = 0; sgm < 4; ++sgm) {
       R.psi50[sgm] = f.pft_psi50[(size_t)sgm * g.npft + ivt];
@@ -632,11 +632,23 @@ __device__ __forceinline__ CloseOut close_body(const CanopyDev& f, const CanopyP
       double efpot = forc_rho * ((elai + esai) / rb) * (qsatl - qaf);
       const double h2ocan = PF(liqcan) + PF(snocan);
       double rpp;
-      if (efpot > 0.0) {
-        rpp = (btran > 0.0) ? rppdry + fwet : fwet;
-        rpp = fmin(rpp, (qflx_tran_veg + h2ocan / dtime) / efpot);
-      } else {
-        rpp = 1.0;
+      double tran = qflx_tran_veg;
+      if (prm.hydrstress) {                            // :1219-1230
+        if (efpot > 0.0) {
+          rpp = (btran > 0.0) ? rppdry + fwet : fwet;
+          rpp = fmin(rpp, (tran + h2ocan / dtime) / efpot);
+        } else {
+          rpp = 1.0;
+        }
+      } else {                                         // :1231-1248: transpiration follows the potential
+        if (efpot > 0.0) {
+          if (btran > 0.0) { tran = efpot * rppdry; rpp = rppdry + fwet; }
+          else { rpp = fwet; tran = 0.0; }
+          rpp = fmin(rpp, (tran + h2ocan / dtime) / efpot);
+        } else {
+          rpp = 1.0;
+          tran = 0.0;
+        }
       }
       const double wtaq = fvn / raw_a;
       const double wtlq = fvn * (elai + esai) / rb * rpp;
@@ -690,8 +702,12 @@ __device__ __forceinline__ CloseOut close_body(const CanopyDev& f, const CanopyP
       }
       efpot = forc_rho * ((elai + esai) / rb) * (wtgaq * (qsatl + qsatldT * dt_veg) - wtgq0 * qg - wtaq0 * forc_q);
       double qflx_evap_veg = rpp * efpot;
-      const double ecidif = fmax(0.0, qflx_evap_veg - qflx_tran_veg - h2ocan / dtime);
-      qflx_evap_veg = fmin(qflx_evap_veg, qflx_tran_veg + h2ocan / dtime);
+      if (!prm.hydrstress) {                           // :1357-1362
+        tran = (efpot > 0.0 && btran > 0.0) ? efpot * rppdry : 0.0;
+        PF(qflx_tran_veg) = tran;
+      }
+      const double ecidif = fmax(0.0, qflx_evap_veg - tran - h2ocan / dtime);
+      qflx_evap_veg = fmin(qflx_evap_veg, tran + h2ocan / dtime);
       PF(qflx_evap_veg) = qflx_evap_veg;
       PF(eflx_sh_veg) = efsh + dc1 * wtga * dt_veg + err + erre + hvap * ecidif;
       eflx_sh_stem = eflx_sh_stem + forc_rho * cpair * wtstem * (-wtl0 * dt_veg);
@@ -766,7 +782,7 @@ canopy_close_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, int first, in
     const bool live = sl.live && !(L.ejected[fi]);     // ejected mid-pass by a task kernel: the tail kernel owns it now
     CloseOut c; c.keep = false; c.solve = false; c.night = false;
     if (live) {
-      if (!first) phs_outputs<false>(f, prm, g, rec[fi], filterp[fi] - g.begp0, ds);   // what follows the PHS solve of pass itlef0-1
+      if (!first && prm.hydrstress) phs_outputs<false>(f, prm, g, rec[fi], filterp[fi] - g.begp0, ds);   // what follows the PHS solve of pass itlef0-1
       c = close_body(f, prm, g, itlef0, first != 0, fi, filterp, ws, wstride, ds);
     }
     const bool go = c.keep && !last;
@@ -791,7 +807,7 @@ canopy_close_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, int first, in
     if (gb) bin_append(L, list_out, row + 1, 0, fi, mk);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      const bool gq = gb && c.solve && (c.night == (q == 0));
+      const bool gq = gb && c.solve && (c.night == (q == 0)) && prm.hydrstress;
       const unsigned mq = __ballot_sync(act, gq);
       if (gq) {
         const int lane = threadIdx.x & 31;
@@ -1048,6 +1064,295 @@ canopy_leaf_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, const int32_t*
     const ListSlot sl = list_slot(L, row, off, list_in, base + threadIdx.x);
     if (!sl.live) continue;
     leaf_body(f, prm, g, itlef0, sl.fi, filterp, ws, wstride, rec, ds);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Photosynthesis WITHOUT plant hydraulic stress (use_hydrstress = .false., clm4_5 physics):
+// PhotosynthesisMod.F90 Photosynthesis :1243-2063, hybrid :2251-2400, brent :2403-2514, ci_func :2551-2701, called for the
+// sunlit and then the shaded leaves of every patch of the pass (CanopyFluxesMod.F90:1143-1166).  One thread per listed
+// patch runs both phases with the reference's nested loops: this is the secondary configuration, a single leaf per solve
+// has no calcstress and at most 40 + 20 ci_func evaluations, and the lists are the same survivor lists as on the PHS path.
+struct NoPhsLeaf {            // what ci_func reads (one phase of one patch)
+  bool c3, medlyn;
+  double vcmax, tpu, kp, cp, kc, ko, qe, je, par, lmr, theta_cj, theta_ip, medint, medslope, bbb, mbb, cair, oair, rh_can,
+      gb_mol, forc_pbot;
+};
+struct NoPhsOut { double ac, aj, ap, ag, an; };
+// ci_func :2551-2701
+__device__ __noinline__ double nophs_ci_func(const NoPhsLeaf& L, double ci, double& gs_mol, NoPhsOut& o, bool* bad) {
+  if (L.c3) {
+    o.ac = L.vcmax * fmax(ci - L.cp, 0.0) / (ci + L.kc * (1.0 + L.oair / L.ko));
+    o.aj = L.je * fmax(ci - L.cp, 0.0) / (4.0 * ci + 8.0 * L.cp);
+    o.ap = 3.0 * L.tpu;
+  } else {
+    o.ac = L.vcmax;
+    o.aj = L.qe * L.par * 4.6;
+    o.ap = L.kp * fmax(ci, 0.0) / L.forc_pbot;
+  }
+  phs::Quad q = phs::quadratic(L.theta_cj, -(o.ac + o.aj), o.ac * o.aj, bad);
+  const double ai = fmin(q.r1, q.r2);
+  q = phs::quadratic(L.theta_ip, -(ai + o.ap), ai * o.ap, bad);
+  o.ag = fmax(0.0, fmin(q.r1, q.r2));
+  o.an = o.ag - L.lmr;
+  if (o.an < 0.0) return 0.0;
+  double cs = L.cair - 1.4 / L.gb_mol * o.an * L.forc_pbot;
+  cs = fmax(cs, phs::max_cs);
+  if (L.medlyn) {
+    const double term = 1.6 * o.an / (cs / L.forc_pbot * 1.e06);
+    const double bq = -(2.0 * (L.medint * 1.e-06 + term) + ((L.medslope * term) * (L.medslope * term)) / (L.gb_mol * 1.e-06 * L.rh_can));
+    const double cq = L.medint * L.medint * 1.e-12 + (2.0 * L.medint * 1.e-06 + term * (1.0 - L.medslope * L.medslope / L.rh_can)) * term;
+    q = phs::quadratic(1.0, bq, cq, bad);
+    gs_mol = fmax(q.r1, q.r2) * 1.e06;
+  } else {
+    const double bq = cs * (L.gb_mol - L.bbb) - L.mbb * o.an * L.forc_pbot;
+    const double cq = -L.gb_mol * (cs * L.bbb + L.mbb * o.an * L.forc_pbot * L.rh_can);
+    q = phs::quadratic(cs, bq, cq, bad);
+    gs_mol = fmax(q.r1, q.r2);
+  }
+  return ci - L.cair + o.an * L.forc_pbot * (1.4 * gs_mol + 1.6 * L.gb_mol) / (L.gb_mol * gs_mol);
+}
+// brent :2403-2514
+__device__ __noinline__ double nophs_brent(const NoPhsLeaf& L, double x1, double x2, double f1, double f2, double tol, double& gs_mol,
+                                           NoPhsOut& o, bool* bad, bool* notbracketed) {
+  double a = x1, b = x2, fa = f1, fb = f2, c, fc, d = 0.0, e = 0.0;
+  if ((fa > 0.0 && fb > 0.0) || (fa < 0.0 && fb < 0.0)) *notbracketed = true;
+  c = b; fc = fb;
+  for (int iter = 0; iter < 20;) {
+    ++iter;
+    if ((fb > 0.0 && fc > 0.0) || (fb < 0.0 && fc < 0.0)) { c = a; fc = fa; d = b - a; e = d; }
+    if (fabs(fc) < fabs(fb)) { a = b; b = c; c = a; fa = fb; fb = fc; fc = fa; }
+    const double tol1 = 2.0 * 1.e-2 * fabs(b) + 0.5 * tol;
+    const double xm = 0.5 * (c - b);
+    if (fabs(xm) <= tol1 || fb == 0.0) return b;
+    if (fabs(e) >= tol1 && fabs(fa) > fabs(fb)) {
+      const double sv = fb / fa;
+      double pv, qv;
+      if (a == c) {
+        pv = 2.0 * xm * sv;
+        qv = 1.0 - sv;
+      } else {
+        qv = fa / fc;
+        const double rv = fb / fc;
+        pv = sv * (2.0 * xm * qv * (qv - rv) - (b - a) * (rv - 1.0));
+        qv = (qv - 1.0) * (rv - 1.0) * (sv - 1.0);
+      }
+      if (pv > 0.0) qv = -qv;
+      pv = fabs(pv);
+      if (2.0 * pv < fmin(3.0 * xm * qv - fabs(tol1 * qv), fabs(e * qv))) { e = d; d = pv / qv; }
+      else { d = xm; e = d; }
+    } else {
+      d = xm; e = d;
+    }
+    a = b; fa = fb;
+    if (fabs(d) > tol1) b = b + d;
+    else b = b + copysign(tol1, xm);
+    fb = nophs_ci_func(L, b, gs_mol, o, bad);
+    if (fb == 0.0) break;
+  }
+  return b;
+}
+// hybrid :2251-2400 (the caller does not use the ci it returns)
+__device__ __noinline__ void nophs_hybrid(const NoPhsLeaf& L, double x0, double& gs_mol, NoPhsOut& o, bool* bad, bool* notbracketed) {
+  double f0 = nophs_ci_func(L, x0, gs_mol, o, bad);
+  if (f0 == 0.0) return;
+  double minx = x0, minf = f0;
+  double x1 = x0 * 0.99;
+  double f1 = nophs_ci_func(L, x1, gs_mol, o, bad);
+  if (f1 == 0.0) return;
+  if (f1 < minf) { minx = x1; minf = f1; }
+  for (int iter = 0;;) {
+    ++iter;
+    const double dx = -f1 * (x1 - x0) / (f1 - f0);
+    const double x = x1 + dx;
+    const double tol = fabs(x) * 1.e-2;
+    if (fabs(dx) < tol) break;
+    x0 = x1; f0 = f1; x1 = x;
+    f1 = nophs_ci_func(L, x1, gs_mol, o, bad);
+    if (f1 < minf) { minx = x1; minf = f1; }
+    if (fabs(f1) <= 1.e-4) break;
+    if (f1 * f0 < 0.0) { (void)nophs_brent(L, x0, x1, f0, f1, tol, gs_mol, o, bad, notbracketed); break; }
+    if (iter > 40) { (void)nophs_ci_func(L, minx, gs_mol, o, bad); break; }
+  }
+}
+
+// Photosynthesis :1243-2063 for one patch, one phase (0 = sun, 1 = sha)
+__device__ __noinline__ void nophs_photosynthesis(const CanopyDev& f, const CanopyPrm& prm, const Geo& g, int pp, int phase,
+                                                  double esat_tv, double eair, double rb, double btran, double dayl_factor,
+                                                  DevStatus* ds) {
+  const int cc = PF(column) - g.begc0;
+  const int gg = PF(gridcell) - g.begg0;
+  const int ivt = PF(itype);
+  const bool medlyn = prm.medlyn != 0;
+  const double forc_pbot = CF(forc_pbot), t_veg = PF(t_veg), t10 = PF(t_a10);
+  const double cair = f.forc_pco2[gg], oair = f.forc_po2[gg];
+  const bool c3 = ((int)nearbyint(f.pft_c3psn[ivt]) == 1);
+  PF(c3flag) = c3 ? 1 : 0;
+  NoPhsLeaf L;
+  L.c3 = c3; L.medlyn = medlyn;
+  L.qe = c3 ? 0.0 : 0.05;
+  PF(qe) = L.qe;
+  L.bbb = 0.0; L.mbb = 0.0;
+  if (!medlyn) { L.bbb = fmax((c3 ? 10000.0 : 40000.0) * btran, 1.0); L.mbb = f.pft_mbbopt[ivt]; }      // :1462-1465
+  {
+    const double kc25 = prm.kc25_coef * forc_pbot, ko25 = prm.ko25_coef * forc_pbot;
+    const double sco = 0.5 * 0.209 / prm.cp25_yr2000;
+    const double cp25 = 0.5 * oair / sco;
+    L.kc = kc25 * ft(t_veg, prm.kcha);
+    L.ko = ko25 * ft(t_veg, prm.koha);
+    L.cp = cp25 * ft(t_veg, prm.cpha);
+    PF(kc) = L.kc; PF(ko) = L.ko; PF(cp) = L.cp;
+  }
+  const double lnc = 1.0 / (f.pft_slatop[ivt] * f.pft_leafcn[ivt]);                                     // :1514
+  PF(lnca) = lnc;
+  double vcmax25top = lnc * f.pft_flnr[ivt] * prm.fnr * prm.act25 * dayl_factor;
+  vcmax25top = vcmax25top * f.pft_fnitr[ivt];
+  const double jmax25top = ((2.59 - 0.035 * fmin(fmax((t10 - tfrz), 11.0), 35.0)) * vcmax25top) * prm.jmax25top_sf;
+  const double tpu25top = prm.tpu25ratio * vcmax25top;
+  const double kp25top = prm.kp25ratio * vcmax25top;
+  const double lmr25top = c3 ? vcmax25top * prm.leaf_mr_vcm : vcmax25top * 0.025;
+  const int nrad = PF(nrad);
+  const double par_z = phase == 0 ? PF2(parsun_z, 0) : PF2(parsha_z, 0);
+  const double lai_z = phase == 0 ? PF2(laisun_z, 0) : PF2(laisha_z, 0);
+  const double nscaler = phase == 0 ? PF(vcmaxcintsun) : PF(vcmaxcintsha);
+  const double cf = forc_pbot / (rgas * 1.e-3 * PF(thm)) * 1.e06;
+  const double gb_mol = (1.0 / rb) * cf;
+  PF(gb_mol) = gb_mol;
+  double lmr_z = 0.0, rs_z = 0.0, psn_z = 0.0, wc_z = 0.0, wj_z = 0.0, wp_z = 0.0;
+  if (nrad >= 1) {
+    const double crop = f.pft_crop[ivt];
+    const bool luna = prm.use_luna && c3 && crop == 0.0;
+    double lmr25 = lmr25top * nscaler;
+    if (luna) lmr25 = prm.leaf_mr_vcm * PF2(vcmx25_z, 0);
+    if (c3) {
+      lmr_z = lmr25 * ft(t_veg, prm.lmrha) * fth(t_veg, prm.lmrhd, prm.lmrse, fth25(prm.lmrhd, prm.lmrse));
+    } else {
+      lmr_z = lmr25 * pw2((t_veg - (tfrz + 25.0)) / 10.0);
+      lmr_z = lmr_z / (1.0 + dexp(1.3 * (t_veg - (tfrz + 55.0))));
+    }
+    double vcmax_z = 0.0, jmax_z = 0.0, tpu_z = 0.0, kp_z = 0.0;
+    if (!(par_z <= 0.0)) {
+      double vcmax25, jmax25, tpu25;
+      if (luna) {
+        vcmax25 = PF2(vcmx25_z, 0);
+        jmax25 = PF2(jmx25_z, 0);
+        tpu25 = prm.tpu25ratio * vcmax25;
+        if (phase == 1 && PF(vcmaxcintsun) > 0.0) {
+          const double a = PF(vcmaxcintsha), b = PF(vcmaxcintsun);
+          vcmax25 = vcmax25 * a / b; jmax25 = jmax25 * a / b; tpu25 = tpu25 * a / b;
+        }
+      } else {
+        vcmax25 = vcmax25top * nscaler; jmax25 = jmax25top * nscaler; tpu25 = tpu25top * nscaler;
+      }
+      const double kp25 = kp25top * nscaler;
+      const double tc = fmin(fmax((t10 - tfrz), 11.0), 35.0);
+      const double vcmaxse = (668.39 - 1.07 * tc) * prm.vcmaxse_sf;
+      const double jmaxse = (659.70 - 0.75 * tc) * prm.jmaxse_sf;
+      const double tpuse = (668.39 - 1.07 * tc) * prm.tpuse_sf;
+      const double vcmaxc = fth25(prm.vcmaxhd, vcmaxse), jmaxc = fth25(prm.jmaxhd, jmaxse), tpuc = fth25(prm.tpuhd, tpuse);
+      vcmax_z = vcmax25 * ft(t_veg, prm.vcmaxha) * fth(t_veg, prm.vcmaxhd, vcmaxse, vcmaxc);
+      jmax_z = jmax25 * ft(t_veg, prm.jmaxha) * fth(t_veg, prm.jmaxhd, jmaxse, jmaxc);
+      tpu_z = tpu25 * ft(t_veg, prm.tpuha) * fth(t_veg, prm.tpuhd, tpuse, tpuc);
+      if (!c3) {
+        vcmax_z = vcmax25 * pw2((t_veg - (tfrz + 25.0)) / 10.0);
+        vcmax_z = vcmax_z / (1.0 + dexp(0.2 * ((tfrz + 15.0) - t_veg)));
+        vcmax_z = vcmax_z / (1.0 + dexp(0.3 * (t_veg - (tfrz + 40.0))));
+      }
+      kp_z = kp25 * pw2((t_veg - (tfrz + 25.0)) / 10.0);
+    }
+    vcmax_z = vcmax_z * btran;                                                                          // :1745-1746
+    lmr_z = lmr_z * btran;
+    if (prm.light_inhibit && par_z > 0.0) lmr_z = lmr_z * 0.67;
+    PF2(vcmax_z, 0) = vcmax_z; PF2(tpu_z, 0) = tpu_z; PF2(kp_z, 0) = kp_z;
+    L.vcmax = vcmax_z; L.tpu = tpu_z; L.kp = kp_z; L.lmr = lmr_z; L.par = par_z;
+    L.theta_cj = f.pft_theta_cj[ivt]; L.theta_ip = prm.theta_ip;
+    L.medint = f.pft_medlynintercept[ivt]; L.medslope = f.pft_medlynslope[ivt];
+    L.cair = cair; L.oair = oair; L.gb_mol = gb_mol; L.forc_pbot = forc_pbot;
+    NoPhsOut o;
+    double ci_z, gs_sunsha;
+    if (par_z <= 0.0) {                                                                                 // night :1781-1815
+      o.ac = 0.0; o.aj = 0.0; o.ap = 0.0; o.ag = 0.0;
+      o.an = o.ag - lmr_z;
+      rs_z = fmin(2.e4, 1.0 / (medlyn ? L.medint : L.bbb) * cf);
+      ci_z = 0.0;
+      PF(rh_leaf) = 0.0;
+      gs_sunsha = cf / rs_z;
+    } else {                                                                                            // day :1817-2006
+      const double ceair = fmin(eair, esat_tv);
+      double rh_can;
+      if (!medlyn) rh_can = ceair / esat_tv;
+      else { rh_can = fmax((esat_tv - ceair), 50.0) * 0.001; PF(vpd_can) = rh_can; }
+      L.rh_can = rh_can;
+      bool bad = false, nb = false;
+      const double qabs = 0.5 * (1.0 - prm.fnps) * par_z * 4.6;
+      const phs::Quad q = phs::quadratic(prm.theta_psii, -(qabs + jmax_z), qabs * jmax_z, &bad);
+      L.je = fmin(q.r1, q.r2);
+      double gs_mol = PF2(gs_mol, 0);
+      nophs_hybrid(L, (c3 ? 0.7 : 0.4) * cair, gs_mol, o, &bad, &nb);
+      if (bad) report_failure(ds, pp + g.begp0, CTSM_ERR_QUADRATIC, 0);
+      if (nb) report_failure(ds, pp + g.begp0, CTSM_ERR_BRENT, 0);
+      if (o.an < 0.0) gs_mol = medlyn ? L.medint : L.bbb;
+      PF2(gs_mol, 0) = gs_mol;
+      gs_sunsha = gs_mol;
+      const int near_noon = f.near_local_noon[gg];
+      if (phase == 0) PF2(gs_mol_sun_ln, 0) = near_noon ? gs_mol : spval;
+      else PF2(gs_mol_sha_ln, 0) = near_noon ? gs_mol : spval;
+      double cs = cair - 1.4 / gb_mol * o.an * forc_pbot;
+      cs = fmax(cs, phs::max_cs);
+      ci_z = cair - o.an * forc_pbot * (1.4 * gs_mol + 1.6 * gb_mol) / (gb_mol * gs_mol);
+      ci_z = fmax(ci_z, 1.e-06);
+      const double gs = gs_mol / cf;
+      rs_z = fmin(1.0 / gs, 2.e4);
+      rs_z = rs_z / (phase == 0 ? PF(o3coefgsun) : PF(o3coefgsha));
+      psn_z = o.ag;
+      psn_z = psn_z * (phase == 0 ? PF(o3coefvsun) : PF(o3coefvsha));
+      if (o.ac <= o.aj && o.ac <= o.ap) wc_z = psn_z;
+      else if (o.aj < o.ac && o.aj <= o.ap) wj_z = psn_z;
+      else if (o.ap < o.ac && o.ap < o.aj) wp_z = psn_z;
+      if (gs_mol < 0.0) report_failure(ds, pp + g.begp0, CTSM_ERR_GS_NEG, 0);
+      if (!medlyn) {
+        const double hs = (gb_mol * ceair + gs_mol * esat_tv) / ((gb_mol + gs_mol) * esat_tv);
+        PF(rh_leaf) = hs;
+        const double gs_mol_err = L.mbb * fmax(o.an, 0.0) * hs / cs * forc_pbot + L.bbb;
+        if (fabs(gs_mol - gs_mol_err) > 1.e-01) atomicAdd(&ds->n_warnings, 1);
+      }
+    }
+    PF2(ac, 0) = o.ac; PF2(aj, 0) = o.aj; PF2(ap, 0) = o.ap; PF2(ag, 0) = o.ag; PF2(an, 0) = o.an;
+    if (phase == 0) { PF2(lmrsun_z, 0) = lmr_z; PF2(rssun_z, 0) = rs_z; PF2(cisun_z, 0) = ci_z; PF2(psnsun_z, 0) = psn_z; PF2(gs_mol_sun, 0) = gs_sunsha; }
+    else { PF2(lmrsha_z, 0) = lmr_z; PF2(rssha_z, 0) = rs_z; PF2(cisha_z, 0) = ci_z; PF2(psnsha_z, 0) = psn_z; PF2(gs_mol_sha, 0) = gs_sunsha; }
+  }
+  // canopy sums :2015-2058 (nlevcan = 1)
+  double psn = 0.0, pwc = 0.0, pwj = 0.0, pwp = 0.0, lmr = 0.0, rs = 0.0;
+  {
+    double psncan = 0.0, cwc = 0.0, cwj = 0.0, cwp = 0.0, lmrcan = 0.0, gscan = 0.0, laican = 0.0;
+    if (nrad >= 1) {
+      psncan = psncan + psn_z * lai_z; cwc = cwc + wc_z * lai_z; cwj = cwj + wj_z * lai_z; cwp = cwp + wp_z * lai_z;
+      lmrcan = lmrcan + lmr_z * lai_z;
+      gscan = gscan + lai_z / (rb + rs_z);
+      laican = laican + lai_z;
+    }
+    if (laican > 0.0) { psn = psncan / laican; pwc = cwc / laican; pwj = cwj / laican; pwp = cwp / laican; lmr = lmrcan / laican; rs = laican / gscan - rb; }
+  }
+  if (phase == 0) { PF(psnsun) = psn; PF(psnsun_wc) = pwc; PF(psnsun_wj) = pwj; PF(psnsun_wp) = pwp; PF(lmrsun) = lmr; PF(rssun) = rs; }
+  else { PF(psnsha) = psn; PF(psnsha_wc) = pwc; PF(psnsha_wj) = pwj; PF(psnsha_wp) = pwp; PF(lmrsha) = lmr; PF(rssha) = rs; }
+}
+
+__global__ void __launch_bounds__(STEP_THREADS)
+canopy_photosyn_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, const int32_t* __restrict__ filterp,
+                       double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in, DevStatus* ds) {
+  const int row = itlef0 + 1;
+  int off[NBIN + 1];
+  const int total = list_offsets(L, row, off);
+  for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+    const ListSlot sl = list_slot(L, row, off, list_in, base + threadIdx.x);
+    if (!sl.live) continue;
+    const int fi = sl.fi;
+    const int pp = filterp[fi] - g.begp0;
+    const int cc = PF(column) - g.begc0;
+    const double svpts = WS(W_EL), eah = CF(forc_pbot) * PF(qaf) / 0.622;
+    const double rb = PF(rb1), btran = PF(btran), dayl = WS(W_DAYL);
+    nophs_photosynthesis(f, prm, g, pp, 0, svpts, eah, rb, btran, dayl, ds);
+    nophs_photosynthesis(f, prm, g, pp, 1, svpts, eah, rb, btran, dayl, ds);
   }
 }
 
@@ -1680,7 +1985,7 @@ __device__ __noinline__ void leaf_call(const CanopyDev& f, const CanopyPrm& prm,
 }
 __device__ __noinline__ bool close_call(const CanopyDev& f, const CanopyPrm& prm, const Geo& g, int itlef0, int fi,
                                         const int32_t* filterp, double* ws, int wstride, PhsRec* rec, DevStatus* ds) {
-  phs_outputs<false>(f, prm, g, rec[fi], filterp[fi] - g.begp0, ds);
+  if (prm.hydrstress) phs_outputs<false>(f, prm, g, rec[fi], filterp[fi] - g.begp0, ds);
   return close_body(f, prm, g, itlef0, false, fi, filterp, ws, wstride, ds).keep;
 }
 
@@ -1732,7 +2037,7 @@ canopy_final_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int32_t* __
   const int fi = blockIdx.x * blockDim.x + threadIdx.x;
   if (fi >= fn) return;
   const int pp = filterp[fi] - g.begp0;
-  phs_outputs<true>(f, prm, g, rec[fi], pp, ds);        // PHS outputs of the patch's last pass
+  if (prm.hydrstress) phs_outputs<true>(f, prm, g, rec[fi], pp, ds);        // PHS outputs of the patch's last pass
   const int cc = PF(column) - g.begc0;
   const int gg = PF(gridcell) - g.begg0;
   const double dtime = prm.dtime;
@@ -1979,6 +2284,7 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
   cp.soil_resis_method = p.soil_resis_method; cp.use_luna = p.use_luna; cp.medlyn = (p.stomatalcond_mtd == 2);
   cp.light_inhibit = p.light_inhibit; cp.modifyphoto_and_lmr_forcrop = p.modifyphoto_and_lmr_forcrop;
   cp.human_fast = (p.calc_human_stress_indices == 1);
+  cp.hydrstress = p.use_hydrstress;
   cp.lai_dl = p.lai_dl; cp.z_dl = p.z_dl; cp.a_coef = p.a_coef; cp.a_exp = p.a_exp; cp.csoilc = p.csoilc; cp.cv = p.cv;
   cp.wind_min = p.wind_min; cp.zetamaxstable = p.zetamaxstable; cp.leaf_mr_vcm = p.leaf_mr_vcm;
   cp.act25 = p.act25; cp.fnr = p.fnr; cp.cp25_yr2000 = p.cp25_yr2000; cp.kc25_coef = p.kc25_coef; cp.ko25_coef = p.ko25_coef;
@@ -2113,6 +2419,13 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
           CUDA_TRY(cudaEventRecord(ctx->ev_round[itlef], s));
         }
         canopy_fric_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, dfilter, ws, wstride, L, lout);
+        if (!cp.hydrstress) {
+          // use_hydrstress = .false.: Photosynthesis for the sunlit, then the shaded leaves (no ci / calcstress task kernels)
+          canopy_photosyn_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, dfilter, ws, wstride, L, lout, ctx->d_status);
+          ctx->launches += 2;
+          int* t = lin; lin = lout; lout = t;
+          continue;
+        }
         canopy_leaf_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, dfilter, ws, wstride, L, lout, rec, ctx->d_status);
         ctx->launches += 2;
         const int row = itlef + 1;

@@ -128,7 +128,9 @@ class HotPath:
         self.ctx, self.sg, self.arrays, self.mem = ctx, sg, arrays, mem
         self.routines = tuple(routines)
         self.window = bool(window) and mem != abi.MEM_DEVICE
-        self.structs = {g: abi.make_struct(g, arrays, sg.bounds) for g in self.routines}
+        # the sink SoilWater consumes follows use_hydrstress (Compute_EffecRootFrac_And_VertTranSink, SoilWaterPlantSinkMod.F90:77-131)
+        self.group_of = {g: ("plantsinkdefault" if g == "plantsink" and not ctx.prm.use_hydrstress else g) for g in self.routines}
+        self.structs = {g: abi.make_struct(self.group_of[g], arrays, sg.bounds) for g in self.routines}
         # DAnstep: 1 = inside BalanceCheck's skip steps (BalanceCheckMod.F90:91,754): all residuals, maxima and warnings
         # are computed, the abort is suppressed - the synthetic water/energy terms are not a closed budget after the step
         self.danstep = 1
@@ -201,9 +203,11 @@ class HotPath:
             raise CtsmError(st, rc)
 
     def VertTranSink(self):
-        """Compute_EffecRootFrac_And_VertTranSink_HydStress (SoilWaterPlantSinkMod.F90:236-328)"""
+        """Compute_EffecRootFrac_And_VertTranSink (SoilWaterPlantSinkMod.F90:18-142): _HydStress (:236-328) with plant
+        hydraulic stress, _Default (:332-424) without"""
         st = abi.Status()
-        rc = self.ctx.L.ctsm_b200_vert_tran_sink_hydstress(
+        fn = self.ctx.L.ctsm_b200_vert_tran_sink_hydstress if self.ctx.prm.use_hydrstress else self.ctx.L.ctsm_b200_vert_tran_sink_default
+        rc = fn(
             self.ctx.h, C.byref(self.bounds), self.nfilter["hydrologyc"], abi.i32p(self.filters["hydrologyc"]),
             C.byref(self.structs["plantsink"]), self.mem, C.byref(st))
         if rc != 0:

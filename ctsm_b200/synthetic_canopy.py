@@ -323,12 +323,21 @@ def soilfluxes_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Gener
             S[nm] = np.where(np.abs(S[nm]) < 1e30, S[nm], 0.0 if nm != "c_h2osfc" else 1.0e-6)
     if not np.all(np.abs(S["fact"]) < 1e30):
         S["fact"] = np.where(np.abs(S["fact"]) < 1e30, S["fact"], g(1.0e-4, 5.0e-2, *S["fact"].shape))
-    for fs in list(abi_fields("soilfluxes")) + list(abi_fields("patch2col")):
-        if fs.name not in S:
+    for fs in list(abi_fields("soilfluxes")) + list(abi_fields("patch2col")) + list(abi_fields("plantsinkdefault")):
+        if fs.name not in S and fs.ctype == "double":       # (the topology integers come from balance_state)
             n = sg.ncol if fs.sub == "COL" else npch
             S[fs.name] = np.full(n if fs.lev == "L1" else (fs.nlev, n), 1.0e36, dtype=fs.dtype)
     for k, v in list(S.items()):
         S[k] = np.ascontiguousarray(v)
+
+
+def bare_ground_state(sg: Subgrid, S: Dict[str, np.ndarray]) -> None:
+    """What BareGroundFluxes leaves on patches without exposed vegetation (BareGroundFluxesMod.F90:294, :468): no effective
+    roots, no transpiration.  The default root-water sink (use_hydrstress = .false.) reads both on every patch."""
+    bare = np.ones(sg.npatch, dtype=bool)
+    bare[sg.filters["exposedvegp"] - 1] = False
+    S["rootr"][:, bare] = 0.0
+    S["qflx_tran_veg"][bare] = 0.0
 
 
 def waterbalance_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator) -> None:

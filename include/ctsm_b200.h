@@ -185,6 +185,13 @@ typedef struct ctsm_plantsink_fields_t {
 #undef CTSM_FIELDS_PLANTSINK
 } ctsm_plantsink_fields_t;
 
+typedef struct ctsm_plantsinkdefault_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_PLANTSINKDEFAULT
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_PLANTSINKDEFAULT
+} ctsm_plantsinkdefault_fields_t;
+
 typedef struct ctsm_soilfluxes_fields_t {
   ctsm_bounds_t alloc;
 #define CTSM_FIELDS_SOILFLUXES
@@ -399,6 +406,12 @@ int ctsm_b200_set_exposedvegp_filter(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bo
 int ctsm_b200_vert_tran_sink_hydstress(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
                                        int num_filterc, const int32_t* filterc,
                                        const ctsm_plantsink_fields_t* f, int mem, ctsm_status_t* st);
+
+/* Compute_EffecRootFrac_And_VertTranSink_Default(bounds, num_filterc, filterc, ...): SoilWaterPlantSinkMod.F90:332-424,
+ * what Compute_EffecRootFrac_And_VertTranSink (:18-142) calls for every column class when use_hydrstress = .false. */
+int ctsm_b200_vert_tran_sink_default(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
+                                     int num_filterc, const int32_t* filterc,
+                                     const ctsm_plantsinkdefault_fields_t* f, int mem, ctsm_status_t* st);
 
 /* SoilFluxes(bounds, num_urbanl, filter_urbanl, num_urbanp, filter_urbanp, num_nolakec, filter_nolakec, num_nolakep,
  * filter_nolakep, ...): SoilFluxesMod.F90:37-521, call site clm_driver.F90:921.  The urban filters are not part of this

@@ -62,6 +62,11 @@ int oracle_balancecheck_skip_steps(double dtime);
 /* SoilWaterPlantSinkMod.F90:236-328 */
 int oracle_vert_tran_sink_hydstress(const ctsm_bounds_t* bounds, int num_filterc, const int32_t* filterc,
                                     const ctsm_plantsink_fields_t* f);
+int oracle_vert_tran_sink_default(const ctsm_bounds_t* bounds, int num_filterc, const int32_t* filterc,
+                                  const ctsm_plantsinkdefault_fields_t* f);
+/* the field struct oracle_fullstep_clumps hands to the default sink when prm->use_hydrstress == 0 (its own plant-sink
+ * argument is the PHS struct); NULL = none */
+void oracle_set_plantsink_default(const ctsm_plantsinkdefault_fields_t* f);
 void oracle_truncate_small_values(int num_f, const int32_t* filter_f, int lb, const double* data_baseline, double* data,
                                   double rel_epsilon);
 /* filterMod.F90:595-648 */

@@ -150,6 +150,9 @@ def _bind(L):
                                       C.POINTER(abi.BalanceReport), S]
     L.oracle_balancecheck_skip_steps.argtypes = [C.c_double]
     L.oracle_vert_tran_sink_hydstress.argtypes = [B, C.c_int, i32p, C.POINTER(abi.STRUCTS["plantsink"])]
+    L.oracle_vert_tran_sink_default.argtypes = [B, C.c_int, i32p, C.POINTER(abi.STRUCTS["plantsinkdefault"])]
+    L.oracle_set_plantsink_default.argtypes = [C.POINTER(abi.STRUCTS["plantsinkdefault"])]
+    L.oracle_set_plantsink_default.restype = None
     L.oracle_num_threads.restype = C.c_int
     L.oracle_set_pert_mode.argtypes = [C.c_int]
     L.oracle_set_pert_mode.restype = None

@@ -247,6 +247,39 @@ int oracle_vert_tran_sink_hydstress(const ctsm_bounds_t* bounds, int num_filterc
   return 0;
 }
 
+/* SoilWaterPlantSinkMod.F90:332-424 (Compute_EffecRootFrac_And_VertTranSink_Default), loops as in the Fortran */
+int oracle_vert_tran_sink_default(const ctsm_bounds_t* bounds, int num_filterc, const int32_t* filterc,
+                                  const ctsm_plantsinkdefault_fields_t* f) {
+  const int begc0 = f->alloc.begc, begp0 = f->alloc.begp;
+  const size_t ldc = (size_t)(f->alloc.endc - f->alloc.begc + 1), ldp = (size_t)(f->alloc.endp - f->alloc.begp + 1);
+  const int nb = bounds->endc - bounds->begc + 1;
+  double* temp = (double*)calloc((size_t)(nb > 0 ? nb : 1), sizeof(double));      /* temp(bounds%begc:bounds%endc) = 0 */
+  for (int j = 1; j <= NLEVSOI; ++j)
+    for (int fc = 0; fc < num_filterc; ++fc) f->rootr_col[(size_t)(j - 1) * ldc + (filterc[fc] - begc0)] = 0.0;
+  for (int j = 1; j <= NLEVSOI; ++j)
+    for (int fc = 0; fc < num_filterc; ++fc) {
+      const int c = filterc[fc];
+      for (int p = f->patchi[c - begc0]; p <= f->patchi[c - begc0] + f->npatches[c - begc0] - 1; ++p)
+        if (f->patch_active[p - begp0])
+          f->rootr_col[(size_t)(j - 1) * ldc + (c - begc0)] = f->rootr_col[(size_t)(j - 1) * ldc + (c - begc0)] +
+              f->rootr[(size_t)(j - 1) * ldp + (p - begp0)] * f->qflx_tran_veg[p - begp0] * f->wtcol[p - begp0];
+    }
+  for (int fc = 0; fc < num_filterc; ++fc) {
+    const int c = filterc[fc];
+    for (int p = f->patchi[c - begc0]; p <= f->patchi[c - begc0] + f->npatches[c - begc0] - 1; ++p)
+      if (f->patch_active[p - begp0]) temp[c - bounds->begc] = temp[c - bounds->begc] + f->qflx_tran_veg[p - begp0] * f->wtcol[p - begp0];
+  }
+  for (int j = 1; j <= NLEVSOI; ++j)
+    for (int fc = 0; fc < num_filterc; ++fc) {
+      const int c = filterc[fc];
+      double* rc = &f->rootr_col[(size_t)(j - 1) * ldc + (c - begc0)];
+      if (temp[c - bounds->begc] != 0.0) *rc = *rc / temp[c - bounds->begc];
+      f->qflx_rootsoi[(size_t)(j - 1) * ldc + (c - begc0)] = *rc * f->qflx_tran_veg_col[c - begc0];
+    }
+  free(temp);
+  return 0;
+}
+
 /* ComputeLiqIceMassNonLake (TotalWaterAndHeatMod.F90:200-326) + AccumulateSoilLiqIceMassNonLake (:329-393, level-outer /
  * column-inner, i.e. ascending levels per column) for one non-urban column; canopy water by p2c (subgridAveMod.F90:312-318). */
 #define WB_FIELDS(F) \

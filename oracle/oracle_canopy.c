@@ -474,8 +474,13 @@ int oracle_canopyfluxes(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, i
       P1(vpd, p) = fmax((A(svpts, p) - A(eah, p)), 50.0) * 0.001;
     }
 
-    oracle_photosynthesis_hydraulic_stress(x, fn, filterp, svpts, eah, o2, co2, rb, bsun, bsha, btran, dayl_factor, qsatl,
-                                           fld->qaf);   /* :1134-1141 */
+    if (prm->use_hydrstress) {
+      oracle_photosynthesis_hydraulic_stress(x, fn, filterp, svpts, eah, o2, co2, rb, bsun, bsha, btran, dayl_factor, qsatl,
+                                             fld->qaf);   /* :1134-1141 */
+    } else {                                              /* :1143-1166: sunlit, then shaded leaves */
+      oracle_photosynthesis(x, fn, filterp, svpts, eah, o2, co2, rb, btran, dayl_factor, 0);
+      oracle_photosynthesis(x, fn, filterp, svpts, eah, o2, co2, rb, btran, dayl_factor, 1);
+    }
     if (ctx.err_code) goto done;
 
     for (int f = 0; f < fn; ++f) {                                     /* :1174-1435 */
@@ -505,12 +510,28 @@ int oracle_canopyfluxes(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, i
       double efpot = forc_rho * ((elai + esai) / A(rb, p)) * (A(qsatl, p) - P1(qaf, p));
       const double h2ocan = P1(liqcan, p) + P1(snocan, p);
       double rpp;
-      if (efpot > 0.0) {                                               /* use_hydrstress branch :1219-1230 */
-        if (A(btran, p) > btran0) rpp = rppdry + P1(fwet, p);
-        else rpp = P1(fwet, p);
-        rpp = fmin(rpp, (P1(qflx_tran_veg, p) + h2ocan / dtime) / efpot);
-      } else {
-        rpp = 1.0;
+      if (prm->use_hydrstress) {
+        if (efpot > 0.0) {                                             /* use_hydrstress branch :1219-1230 */
+          if (A(btran, p) > btran0) rpp = rppdry + P1(fwet, p);
+          else rpp = P1(fwet, p);
+          rpp = fmin(rpp, (P1(qflx_tran_veg, p) + h2ocan / dtime) / efpot);
+        } else {
+          rpp = 1.0;
+        }
+      } else {                                                         /* :1231-1248: transpiration follows the potential */
+        if (efpot > 0.0) {
+          if (A(btran, p) > btran0) {
+            P1(qflx_tran_veg, p) = efpot * rppdry;
+            rpp = rppdry + P1(fwet, p);
+          } else {
+            rpp = P1(fwet, p);
+            P1(qflx_tran_veg, p) = 0.0;
+          }
+          rpp = fmin(rpp, (P1(qflx_tran_veg, p) + h2ocan / dtime) / efpot);
+        } else {
+          rpp = 1.0;
+          P1(qflx_tran_veg, p) = 0.0;
+        }
       }
       const double wtaq = fvn / A(raw_a, p);
       const double wtlq = fvn * (elai + esai) / A(rb, p) * rpp;
@@ -569,7 +590,11 @@ int oracle_canopyfluxes(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, i
       efpot = forc_rho * ((elai + esai) / A(rb, p)) *
               (wtgaq * (A(qsatl, p) + A(qsatldT, p) * A(dt_veg, p)) - wtgq0 * C1(qg, c) - A(wtaq0, p) * forc_q);
       P1(qflx_evap_veg, p) = rpp * efpot;
-      const double ecidif = fmax(0.0, P1(qflx_evap_veg, p) - P1(qflx_tran_veg, p) - h2ocan / dtime);   /* :1353-1355 */
+      if (!prm->use_hydrstress) {                                      /* :1357-1362 */
+        if (efpot > 0.0 && A(btran, p) > btran0) P1(qflx_tran_veg, p) = efpot * rppdry;
+        else P1(qflx_tran_veg, p) = 0.0;
+      }
+      const double ecidif = fmax(0.0, P1(qflx_evap_veg, p) - P1(qflx_tran_veg, p) - h2ocan / dtime);   /* :1353-1355, :1363 */
       P1(qflx_evap_veg, p) = fmin(P1(qflx_evap_veg, p), P1(qflx_tran_veg, p) + h2ocan / dtime);
       P1(eflx_sh_veg, p) = efsh + dc1 * A(wtga, p) * A(dt_veg, p) + A(err, p) + erre + hvap * ecidif;
       P1(eflx_sh_stem, p) = P1(eflx_sh_stem, p) + forc_rho * cpair * wtstem * (-A(wtl0, p) * A(dt_veg, p));

@@ -44,4 +44,7 @@ void oracle_photosynthesis_hydraulic_stress(cf_ctx* x, int fn, const int32_t* fi
                                             const double* eair, const double* oair, const double* cair,
                                             const double* rb, double* bsun, double* bsha, double* btran,
                                             const double* dayl_factor, const double* qsatl, const double* qaf);
+void oracle_photosynthesis(cf_ctx* x, int fn, const int32_t* filterp, const double* esat_tv, const double* eair,
+                           const double* oair, const double* cair, const double* rb, const double* btran,
+                           const double* dayl_factor, int phase);
 #endif

@@ -42,6 +42,9 @@ int oracle_step_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump
  * HydrologyNoDrainageMod.F90:339,346, :1422): CanopyFluxes -> SoilTemperature -> root-water sink -> SoilWater ->
  * BalanceCheck over all columns of the clump (SoilFluxes, :921, between SoilTemperature and the sink).  `which` bits:
  * 1 SoilTemperature, 2 SoilWater, 4 CanopyFluxes, 8 plant sink, 16 BalanceCheck, 32 SoilFluxes, 64 clm_drv_patch2col. */
+static const ctsm_plantsinkdefault_fields_t* g_sink_default = NULL;
+void oracle_set_plantsink_default(const ctsm_plantsinkdefault_fields_t* f) { g_sink_default = f; }
+
 int oracle_fullstep_clumps(const ctsm_params_t* prm, int nclumps, const oracle_clump_t* clumps,
                            const ctsm_soiltemperature_fields_t* ft, const ctsm_soilwater_fields_t* fw,
                            const ctsm_canopyfluxes_fields_t* fc, const ctsm_plantsink_fields_t* fs,
@@ -67,7 +70,10 @@ int oracle_fullstep_clumps(const ctsm_params_t* prm, int nclumps, const oracle_c
       rc = oracle_patch2col(&k->bounds, n, allc, k->num_nolakec, k->filter_nolakec, f2c);
       free(allc);
     }
-    if (!rc && (which & 8) && fs)
+    if (!rc && (which & 8) && !prm->use_hydrstress) {
+      if (!g_sink_default) rc = CTSM_ERR_BAD_ARG;
+      else rc = oracle_vert_tran_sink_default(&k->bounds, k->num_hydrologyc, k->filter_hydrologyc, g_sink_default);
+    } else if (!rc && (which & 8) && fs)
       rc = oracle_vert_tran_sink_hydstress(&k->bounds, k->num_hydrologyc, k->filter_hydrologyc, fs);
     if (!rc && (which & 2) && fw)
       rc = oracle_soilwater(prm, &k->bounds, k->num_hydrologyc, k->filter_hydrologyc, fw, &st);

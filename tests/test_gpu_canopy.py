@@ -278,7 +278,8 @@ def test_canopyfluxes_tail_kernel_matches_oracle(gpu_ctx, oracle_lib):
     compare(sg, got, ref, S)
 
 
-@pytest.mark.parametrize("variant", ["zengwang_bb_noluna", "night_only", "day_only", "no_biomass_beta"])
+@pytest.mark.parametrize("variant", ["zengwang_bb_noluna", "night_only", "day_only", "no_biomass_beta", "nophs_medlyn",
+                                     "nophs_ballberry_noluna"])
 def test_canopyfluxes_option_branches(oracle_lib, variant):
     """Namelist branches other than the clm6_0 defaults: ZengWang2007 z0, Ball-Berry, LUNA off,
     biomass heat storage off, Lee-Pielke beta; all-night and all-day grids."""
@@ -291,6 +292,12 @@ def test_canopyfluxes_option_branches(oracle_lib, variant):
         day_fraction = 0.0
     elif variant == "day_only":
         day_fraction = 1.0
+    elif variant == "nophs_medlyn":
+        # soil-moisture-stress configuration: Photosynthesis for sunlit then shaded leaves, btran from
+        # calc_root_moist_stress, transpiration from the potential evaporation
+        prm.use_hydrstress = 0
+    elif variant == "nophs_ballberry_noluna":
+        prm.use_hydrstress, prm.stomatalcond_mtd, prm.use_luna = 0, 1, 0
     else:
         prm.use_biomass_heat_storage, prm.soil_resis_method, prm.use_undercanopy_stability = 0, 0, 1
     ctx = C.c_void_p()
