@@ -114,18 +114,22 @@ class ClockSampler:
         return out
 
 
-def read_traffic(routine, size):
-    """DRAM bytes per call of a routine's kernels, from the committed ncu launch list of the same command
-    (profiles/r01_traffic.json, written by tools/launch_summary.py output -> DESIGN.md section 4); None when the
-    workload differs from the profiled one."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        d = json.load(open(p))
-        if d.get("size") == str(size):
-            return d["dram_bytes_per_call"].get(routine)
-    except Exception:
-        pass
+def read_profile(size):
+    """The committed ncu launch-list summary of this command (tools/launch_summary.py -> profiles/r02_traffic.json): DRAM
+    bytes and FP64-pipe instructions per call of each routine.  None when the workload differs from the profiled one
+    (the counters are per launch of THAT grid)."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if d.get("size") == str(size):
+                d["file"] = "profiles/" + name
+                return d
+        except Exception:
+            continue
     return None
+
+
+FP64_LANES_PER_SM, N_SM = 64, 148          # B200: 148 SMs x 4 SMSPs x 16 FP64 lanes; a warp instruction holds an SMSP's pipe 2 cycles
 
 
 def which_mask(routines):
@@ -179,6 +183,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--under-profiler", action="store_true", help="run under ncu: allows --warmup < 3; the printed line is not a measurement")
     ap.add_argument("--size", default="f02", help="tiny|f19|f09|f02 or a gridcell count (per GPU)")
     ap.add_argument("--routines", default=",".join(ALL_ROUTINES))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -192,7 +197,8 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="under torchrun: strong = ONE grid of --size dealt to the ranks (default), weak = one grid of --size per rank")
     a = ap.parse_args()
-    a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+    # timing rule: at least 3 warm-up steps; --under-profiler (ncu launch lists, never a bench value) lifts it
+    a.warmup = max(a.warmup, 3) if (a.impl == "b200" and not a.under_profiler) else a.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -312,26 +318,51 @@ def main():
     total_s, total_cols = float(t.item()), float(cols.item())
     value = total_cols * a.steps / total_s
 
-    # roofline of the dominant routine's kernels (event timing on the launching stream, this rank)
+    # Rooflines (SURVEY.md 8d asks for both and for which one binds), per routine and for the dominant one.
+    #   hbm : algorithmic bytes of the field table / event-timed duration, against the measured copy bandwidth
+    #   fp64: FP64-pipe warp instructions of the call (committed ncu pass of this command, profiles/r02_traffic.json) x 32
+    #         thread slots / event-timed duration, against 148 SMs x 64 FP64 lanes x the SM clock sampled DURING this run.
+    #         The code is compiled -fmad=false (the reference's -ffp-contract=off), so one slot is one flop.
     peak, peak_src = read_peaks()
+    prof = read_profile(a.size) if (world == 1 and a.members == 1 and tuple(routines) == ALL_ROUTINES) else None
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    fp64_peak = N_SM * FP64_LANES_PER_SM * sm_mhz * 1e6 / 1e9          # G thread-slots / s
     per_routine = {}
     for g in routines:
         ab = driver.algorithmic_bytes(sg, S, g)
-        per_routine[NAME_OF[g]] = {"ms": rt_ms[g], "algorithmic_bytes": ab["bytes"], "GBps": ab["bytes"] / (rt_ms[g] * 1e-3) / 1e9,
-                                   "frac_of_hbm_peak": ab["bytes"] / (rt_ms[g] * 1e-3) / 1e9 / peak,
-                                   "columns": ab["columns"], "patches": ab["patches"]}
+        e = {"ms": rt_ms[g], "algorithmic_bytes": ab["bytes"], "GBps": ab["bytes"] / (rt_ms[g] * 1e-3) / 1e9,
+             "frac_of_hbm_peak": ab["bytes"] / (rt_ms[g] * 1e-3) / 1e9 / peak, "columns": ab["columns"], "patches": ab["patches"]}
+        if prof is not None and prof.get("fp64_warp_inst_per_call", {}).get(NAME_OF[g]):
+            w = prof["fp64_warp_inst_per_call"][NAME_OF[g]]
+            t = prof.get("fp64_thread_inst_per_call", {}).get(NAME_OF[g], 0.0)
+            e["fp64_Gslots_per_s"] = 32.0 * w / (rt_ms[g] * 1e-3) / 1e9
+            e["frac_of_fp64_peak"] = e["fp64_Gslots_per_s"] / fp64_peak
+            e["fp64_lanes_per_warp_inst"] = t / w if w else None
+            e["dram_traffic_bytes"] = prof["dram_bytes_per_call"].get(NAME_OF[g])
+        e["bound"] = "fp64" if e.get("frac_of_fp64_peak", 0.0) > e["frac_of_hbm_peak"] else "hbm"
+        per_routine[NAME_OF[g]] = e
     dom = max(rt_ms, key=rt_ms.get)
     ab = driver.algorithmic_bytes(sg, S, dom)
-    achieved = ab["bytes"] / (rt_ms[dom] * 1e-3) / 1e9
+    d = per_routine[NAME_OF[dom]]
     step_bytes = sum(v["algorithmic_bytes"] for v in per_routine.values())
-    roofline = {"bound": "hbm", "kernel": KERNEL_OF[dom], "achieved": achieved, "peak": peak, "peak_source": peak_src,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": read_traffic(NAME_OF[dom], a.size),
-                "algorithmic_bytes_per_launch": ab["bytes"], "ms_per_launch": rt_ms[dom],
-                "note": "a 'launch' is one call of the dominant routine (a chain of kernels, timed with CUDA events on the "
-                        "library's stream); CanopyFluxes+PHS is FP64-pipe/latency bound (hundreds of pow/exp/log per "
-                        "patch-pass, 7 passes per patch), see DESIGN.md section 4; the HBM fraction is reported because "
-                        "BASELINE.json asks for it; ncu (profiles/r01_ncu_*.txt): FP64 pipe 24 % busy in phs_newton_kernel, "
-                        "37 % in canopy_fric_kernel, issue slots 33 % / 52 %, 17 / 13 of 32 lanes active",
+    hbm = {"achieved": d["GBps"], "peak": peak, "unit": "GB/s", "frac": d["frac_of_hbm_peak"], "peak_source": peak_src,
+           "algorithmic_bytes_per_launch": ab["bytes"]}
+    fp64 = None
+    if "frac_of_fp64_peak" in d:
+        fp64 = {"achieved": d["fp64_Gslots_per_s"], "peak": fp64_peak, "unit": "G FP64 thread-slots/s", "frac": d["frac_of_fp64_peak"],
+                "peak_source": "148 SMs x 64 FP64 lanes x %.0f MHz (SM clock sampled under load in this run)" % sm_mhz,
+                "warp_instructions_per_launch": prof["fp64_warp_inst_per_call"][NAME_OF[dom]],
+                "lanes_per_warp_instruction": d["fp64_lanes_per_warp_inst"], "source": prof["file"]}
+    binds = fp64 if d["bound"] == "fp64" else hbm
+    roofline = {"bound": d["bound"], "kernel": KERNEL_OF[dom], "achieved": binds["achieved"], "peak": binds["peak"],
+                "peak_source": binds["peak_source"], "unit": binds["unit"], "frac": binds["frac"],
+                "traffic": prof["dram_bytes_per_call"].get(NAME_OF[dom]) if prof else None,
+                "algorithmic_bytes_per_launch": ab["bytes"], "ms_per_launch": rt_ms[dom], "hbm": hbm, "fp64": fp64,
+                "note": "a 'launch' is one call of the dominant routine (its chain of kernels, timed with CUDA events on the "
+                        "library's stream).  `bound` is the roofline the routine sits closer to; for CanopyFluxes + PHS that is "
+                        "the FP64 pipe (hundreds of exp/log/pow per patch-pass), but the ITERATION loop's 41 data-dependent "
+                        "rounds make it latency-bound below either roof (DESIGN.md section 4.1: the worst patch's Newton "
+                        "chain sets a floor per round).  fp64 is null when the workload is not the profiled one.",
                 "whole_step": {"algorithmic_bytes": step_bytes, "GBps": step_bytes / (float(np.mean(step_ms)) * 1e-3) / 1e9,
                                "frac": step_bytes / (float(np.mean(step_ms)) * 1e-3) / 1e9 / peak},
                 "routines": per_routine}
@@ -389,6 +420,8 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "warnings_in_timed_region": int(st.n_warnings), "wall_s_timed_region": t_wall,
                 "balance_global_max": hp.global_balance(), "total_columns": int(total_cols)}
+        if a.under_profiler:
+            line["under_profiler"] = True          # not a measurement
         print(json.dumps(line))
     ctx.close()
     if dist is not None:

@@ -23,7 +23,7 @@
 
 // Every function here is host+device: the device build is the product; the host build exists only so that
 // tests/host/phs_tasks_check.cu can run the task state machines against the direct formulation on the CPU.
-#define PHS_FN __host__ __device__ __noinline__
+#define PHS_FN static __host__ __device__ __noinline__
 #define PHS_INL __host__ __device__ __forceinline__
 
 namespace phs {

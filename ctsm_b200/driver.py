@@ -19,7 +19,11 @@ from . import abi
 # HydrologyNoDrainage :950
 # (root-water sink HydrologyNoDrainageMod.F90:339, SoilWater :346), BalanceCheck :1422
 ROUTINES = ("canopyfluxes", "soiltemperature", "soilfluxes", "patch2col", "plantsink", "soilwater", "balancecheck")
-FILTER_OF = {"canopyfluxes": ("exposedvegp",), "soiltemperature": ("nolakep", "nolakec"), "soilfluxes": ("nolakep", "nolakec"),
+# the routines clm_drv runs just before CanopyFluxes (clm_driver.F90:680, :702, :711); PRE_ROUTINES + ROUTINES
+# is the step from BiogeophysPreFluxCalcs to BalanceCheck
+PRE_ROUTINES = ("preflux", "surfacehumidity", "baregroundfluxes")
+FILTER_OF = {"preflux": ("nolakec", "nolakep"), "surfacehumidity": ("nolakec",), "baregroundfluxes": ("noexposedvegp",),
+             "canopyfluxes": ("exposedvegp",), "soiltemperature": ("nolakep", "nolakec"), "soilfluxes": ("nolakep", "nolakec"),
              "patch2col": ("allc", "nolakec"), "plantsink": ("hydrologyc",), "soilwater": ("hydrologyc",), "balancecheck": ("allc",)}
 
 
@@ -261,8 +265,37 @@ class HotPath:
         self._side.synchronize()
         return [float(x) for x in self._gmax.cpu()]
 
+    def BiogeophysPreFluxCalcs(self, time_flags: int = 0):
+        """BiogeophysPreFluxCalcs (BiogeophysPreFluxCalcsMod.F90:58-118); no urban columns"""
+        st = abi.Status()
+        rc = self.ctx.L.ctsm_b200_biogeophys_pre_flux_calcs(
+            self.ctx.h, C.byref(self.bounds), self.nfilter["nolakec"], abi.i32p(self.filters["nolakec"]),
+            self.nfilter["nolakep"], abi.i32p(self.filters["nolakep"]), 0, None, int(time_flags),
+            C.byref(self.structs["preflux"]), self.mem, C.byref(st))
+        if rc != 0:
+            raise CtsmError(st, rc)
+
+    def CalculateSurfaceHumidity(self):
+        """CalculateSurfaceHumidity (SurfaceHumidityMod.F90:41-239)"""
+        st = abi.Status()
+        rc = self.ctx.L.ctsm_b200_calculate_surface_humidity(
+            self.ctx.h, C.byref(self.bounds), self.nfilter["nolakec"], abi.i32p(self.filters["nolakec"]),
+            C.byref(self.structs["surfacehumidity"]), self.mem, C.byref(st))
+        if rc != 0:
+            raise CtsmError(st, rc)
+
+    def BareGroundFluxes(self):
+        """BareGroundFluxes (BareGroundFluxesMod.F90:63-529) over filter_noexposedvegp"""
+        st = abi.Status()
+        rc = self.ctx.L.ctsm_b200_bare_ground_fluxes(
+            self.ctx.h, C.byref(self.bounds), self.nfilter["noexposedvegp"], abi.i32p(self.filters["noexposedvegp"]),
+            C.byref(self.structs["baregroundfluxes"]), self.mem, C.byref(st))
+        if rc != 0:
+            raise CtsmError(st, rc)
+
     def call(self, g):
-        {"canopyfluxes": self.CanopyFluxes, "soiltemperature": self.SoilTemperature, "soilwater": self.SoilWater,
+        {"preflux": self.BiogeophysPreFluxCalcs, "surfacehumidity": self.CalculateSurfaceHumidity, "baregroundfluxes": self.BareGroundFluxes,
+         "canopyfluxes": self.CanopyFluxes, "soiltemperature": self.SoilTemperature, "soilwater": self.SoilWater,
          "plantsink": self.VertTranSink, "balancecheck": self.BalanceCheck, "soilfluxes": self.SoilFluxes, "patch2col": self.Patch2Col}[g]()
 
     def step(self):

@@ -340,6 +340,35 @@ def bare_ground_state(sg: Subgrid, S: Dict[str, np.ndarray]) -> None:
     S["qflx_tran_veg"][bare] = 0.0
 
 
+def preflux_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator) -> None:
+    """Inputs of BiogeophysPreFluxCalcs / CalculateSurfaceHumidity / BareGroundFluxes that the rest of the step does not
+    already carry: snow cover, air temperature, field capacity, the previous step's roughness
+    lengths and the ZengWang2007 PFT ratios.  Outputs start from spval."""
+    nc, npch = sg.ncol, sg.npatch
+    g = lambda lo, hi, *shape: rng.uniform(lo, hi, shape)
+    S["frac_sno"] = S["frac_sno_eff"].copy()                    # identical off urban landunits
+    S["forc_t"] = S["forc_th"] - g(0.0, 0.4, nc)                # forc_th = forc_t*(psrf/pbot)**cappa, slightly warmer
+    S["watfc"] = S["watsat"] * g(0.35, 0.8, *S["watsat"].shape)
+    S["smpmin"] = np.full(nc, -1.0e8)
+    S["z0m"] = g(0.01, 1.5, npch)                               # previous step (read where htop <= 1e-10)
+    for nm in ("z0hg", "z0qg", "beta", "zii", "dsl", "soilalpha"):
+        S[nm] = np.full(nc, 1.0e36)
+    for nm in ("z0mg_p", "z0hg_p", "z0qg_p", "kbm1"):
+        S[nm] = np.full(npch, 1.0e36)
+    nt = len(S["pft_z0v_LAImax"])
+    base = np.r_[0.0, rng.uniform(0.055, 0.12, abi_mod().MXPFT)]        # pftcon%z0mr / displar (noveg: 0)
+    S["pft_z0mr"] = np.tile(base, nt // len(base))
+    based = np.r_[0.0, rng.uniform(0.67, 0.68, abi_mod().MXPFT)]
+    S["pft_displar"] = np.tile(based, nt // len(based))
+    for grp in ("preflux", "surfacehumidity", "baregroundfluxes"):
+        for fs in abi_fields(grp):
+            if fs.name not in S and fs.ctype == "double":
+                n = {"COL": nc, "PATCH": npch, "GRC": sg.ngrc}[fs.sub]
+                S[fs.name] = np.full(n if fs.lev == "L1" else (fs.nlev, n), 1.0e36)
+    for k, v in list(S.items()):
+        S[k] = np.ascontiguousarray(v)
+
+
 def waterbalance_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator) -> None:
     """Adds the fields of group `waterbalance` (BeginWaterColumnBalance, BalanceCheckMod.F90:171)."""
     nc = sg.ncol

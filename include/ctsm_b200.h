@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define CTSM_B200_ABI_VERSION 3
+#define CTSM_B200_ABI_VERSION 4
 
 /* fixed vertical structure the kernels are compiled for (clm_varpar.F90:43-54,
  * 290-292; namelist_defaults_ctsm.xml:254,511).  ctsm_b200_init refuses any
@@ -149,8 +149,12 @@ typedef struct ctsm_params_t {
                                          * ensemble (BASELINE config 5) runs member m's patches with itype = m*(mxpft+1)+pft.
                                          * Default CTSM_MXPFT+1 (one parameter set: pftcon as the reference holds it). */
   int32_t calc_human_stress_indices;    /* 0 = NONE, 1 = FAST (clm5/clm6 default; HumanIndexMod.F90:496-547), ALL is not built */
-  int32_t reserved_i[5];
-  double  reserved_d[8];
+  /* BiogeophysPreFluxCalcs: FrictionVelocityMod.F90 (zlnd, zsno, zglc: parameter-file scalars), clm_varctl use_z0m_snowmelt,
+   * SurfaceResistanceMod.F90:35-36 (d_max, frac_sat_soil_dsl_init: parameter-file scalars) */
+  int32_t use_z0m_snowmelt;             /* 1 with Meier2022 (namelist_defaults_ctsm.xml:624) */
+  int32_t reserved_i[4];
+  double  zlnd, zsno, zglc, d_max, frac_sat_soil_dsl_init;
+  double  reserved_d[3];
 } ctsm_params_t;
 
 typedef struct ctsm_b200_ctx ctsm_b200_ctx;
@@ -191,6 +195,27 @@ typedef struct ctsm_plantsinkdefault_fields_t {
 #include "ctsm_b200_fields.def"
 #undef CTSM_FIELDS_PLANTSINKDEFAULT
 } ctsm_plantsinkdefault_fields_t;
+
+typedef struct ctsm_preflux_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_PREFLUX
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_PREFLUX
+} ctsm_preflux_fields_t;
+
+typedef struct ctsm_surfacehumidity_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_SURFACEHUMIDITY
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_SURFACEHUMIDITY
+} ctsm_surfacehumidity_fields_t;
+
+typedef struct ctsm_baregroundfluxes_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_BAREGROUNDFLUXES
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_BAREGROUNDFLUXES
+} ctsm_baregroundfluxes_fields_t;
 
 typedef struct ctsm_soilfluxes_fields_t {
   ctsm_bounds_t alloc;
@@ -406,6 +431,31 @@ int ctsm_b200_set_exposedvegp_filter(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bo
 int ctsm_b200_vert_tran_sink_hydstress(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
                                        int num_filterc, const int32_t* filterc,
                                        const ctsm_plantsink_fields_t* f, int mem, ctsm_status_t* st);
+
+/* BiogeophysPreFluxCalcs(bounds, num_nolakec, filter_nolakec, num_nolakep, filter_nolakep, num_urbanc, filter_urbanc, ...):
+ * BiogeophysPreFluxCalcsMod.F90:58-118, call site clm_driver.F90:680.  Runs SetZ0mDisp, SetRoughnessLengthsAndForcHeightsNonLake,
+ * CalcInitialTemperatureAndEnergyVars and calc_soilevap_resis.  num_urbanc must be 0 and no column of an urban landunit may
+ * be in filter_nolakec (CTSM_ERR_URBAN).  time_flags carries the clock tests of SetZ0mDisp (:174-184):
+ * bit 0 = is_first_step() .or. get_nstep() <= GetBalanceCheckSkipSteps()-1, bit 1 = is_beg_curr_year(). */
+#define CTSM_TIME_FIRST_STEPS 1
+#define CTSM_TIME_BEG_CURR_YEAR 2
+int ctsm_b200_biogeophys_pre_flux_calcs(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
+                                        int num_nolakec, const int32_t* filter_nolakec,
+                                        int num_nolakep, const int32_t* filter_nolakep,
+                                        int num_urbanc, const int32_t* filter_urbanc, int time_flags,
+                                        const ctsm_preflux_fields_t* f, int mem, ctsm_status_t* st);
+
+/* CalculateSurfaceHumidity(bounds, num_nolakec, filter_nolakec, ...): SurfaceHumidityMod.F90:41-239, call site
+ * clm_driver.F90:702.  Urban columns are refused (CTSM_ERR_URBAN). */
+int ctsm_b200_calculate_surface_humidity(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
+                                         int num_nolakec, const int32_t* filter_nolakec,
+                                         const ctsm_surfacehumidity_fields_t* f, int mem, ctsm_status_t* st);
+
+/* BareGroundFluxes(bounds, num_noexposedvegp, filter_noexposedvegp, ...): BareGroundFluxesMod.F90:63-529, call site
+ * clm_driver.F90:711.  use_lch4 = .false.; the human-stress indices follow ctsm_params_t.calc_human_stress_indices. */
+int ctsm_b200_bare_ground_fluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
+                                 int num_noexposedvegp, const int32_t* filter_noexposedvegp,
+                                 const ctsm_baregroundfluxes_fields_t* f, int mem, ctsm_status_t* st);
 
 /* Compute_EffecRootFrac_And_VertTranSink_Default(bounds, num_filterc, filterc, ...): SoilWaterPlantSinkMod.F90:332-424,
  * what Compute_EffecRootFrac_And_VertTranSink (:18-142) calls for every column class when use_hydrstress = .false. */

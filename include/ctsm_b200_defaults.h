@@ -48,6 +48,11 @@ static inline void ctsm_default_params_fill(ctsm_params_t* p) {
   p->tpu25ratio = 0.167; p->kp25ratio = 20000.0;
   p->vcmaxse_sf = 1.0; p->jmaxse_sf = 1.0; p->tpuse_sf = 1.0; p->jmax25top_sf = 1.0;
   p->calc_human_stress_indices = 1;      // FAST: namelist_defaults_ctsm.xml:235
+  // roughness lengths and the dry-surface-layer parameters are parameter-file scalars (the file is not in the source tree):
+  // the ctsm5.1+ parameter-file values are used (synthetic choice)
+  p->use_z0m_snowmelt = 1;                 // namelist_defaults_ctsm.xml:624 (z0param_method = Meier2022)
+  p->zlnd = 0.000775; p->zsno = 0.00085; p->zglc = 0.00230000005;
+  p->d_max = 15.0; p->frac_sat_soil_dsl_init = 0.8;
   p->balance_skip_steps = -1;
   p->npft_table = CTSM_MXPFT + 1;
 }

@@ -62,6 +62,14 @@ int oracle_balancecheck_skip_steps(double dtime);
 /* SoilWaterPlantSinkMod.F90:236-328 */
 int oracle_vert_tran_sink_hydstress(const ctsm_bounds_t* bounds, int num_filterc, const int32_t* filterc,
                                     const ctsm_plantsink_fields_t* f);
+/* oracle_preflux.c: the three routines before CanopyFluxes */
+int oracle_biogeophys_pre_flux_calcs(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_nolakec,
+                                     const int32_t* filter_nolakec, int num_nolakep, const int32_t* filter_nolakep,
+                                     int num_urbanc, int time_flags, const ctsm_preflux_fields_t* f, ctsm_status_t* st);
+int oracle_calculate_surface_humidity(const ctsm_bounds_t* bounds, int num_nolakec, const int32_t* filter_nolakec,
+                                      const ctsm_surfacehumidity_fields_t* f, ctsm_status_t* st);
+int oracle_bare_ground_fluxes(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_noexposedvegp,
+                              const int32_t* filter_noexposedvegp, const ctsm_baregroundfluxes_fields_t* f, ctsm_status_t* st);
 int oracle_vert_tran_sink_default(const ctsm_bounds_t* bounds, int num_filterc, const int32_t* filterc,
                                   const ctsm_plantsinkdefault_fields_t* f);
 /* the field struct oracle_fullstep_clumps hands to the default sink when prm->use_hydrstress == 0 (its own plant-sink

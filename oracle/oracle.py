@@ -150,6 +150,10 @@ def _bind(L):
                                       C.POINTER(abi.BalanceReport), S]
     L.oracle_balancecheck_skip_steps.argtypes = [C.c_double]
     L.oracle_vert_tran_sink_hydstress.argtypes = [B, C.c_int, i32p, C.POINTER(abi.STRUCTS["plantsink"])]
+    L.oracle_biogeophys_pre_flux_calcs.argtypes = [P, B, C.c_int, i32p, C.c_int, i32p, C.c_int, C.c_int,
+                                                   C.POINTER(abi.STRUCTS["preflux"]), C.POINTER(abi.Status)]
+    L.oracle_calculate_surface_humidity.argtypes = [B, C.c_int, i32p, C.POINTER(abi.STRUCTS["surfacehumidity"]), C.POINTER(abi.Status)]
+    L.oracle_bare_ground_fluxes.argtypes = [P, B, C.c_int, i32p, C.POINTER(abi.STRUCTS["baregroundfluxes"]), C.POINTER(abi.Status)]
     L.oracle_vert_tran_sink_default.argtypes = [B, C.c_int, i32p, C.POINTER(abi.STRUCTS["plantsinkdefault"])]
     L.oracle_set_plantsink_default.argtypes = [C.POINTER(abi.STRUCTS["plantsinkdefault"])]
     L.oracle_set_plantsink_default.restype = None

@@ -93,137 +93,148 @@ void oracle_moninobukini(double zetamaxstable, double ur, double thv, double dth
   *obu = zldis / zeta;
 }
 
-/* FrictionVelocity :754-1117, patch-level form (landunit_index absent).  Dummy arrays are (begp0:endp0). */
+/* FrictionVelocity :754-1117 for one point (patch-level form, landunit_index absent); o->fm carries fm(n) in and out */
+void oracle_friction_velocity_point(double hgt_u, double hgt_t, double hgt_q, double displa, double z0m, double z0h, double z0q,
+                                    double obu, int iter, double ur, double um, oracle_fricvel_t* o) {
+  const double zetam = 1.574, zetat = 0.465;
+  double zldis, zeta, tmp1, tmp2, tmp3, tmp4, fmnew, fm10, zeta10, vds_tmp;
+  /* wind profile */
+  zldis = hgt_u - displa;
+  zeta = zldis / obu;
+  if (zeta < -zetam) {
+    o->ustar = vkc * um / (log(-zetam * obu / z0m) - StabilityFunc1(-zetam) + StabilityFunc1(z0m / obu)
+                              + 1.14 * (pow(-zeta, 0.333) - pow(zetam, 0.333)));
+  } else if (zeta < 0.0) {
+    o->ustar = vkc * um / (log(zldis / z0m) - StabilityFunc1(zeta) + StabilityFunc1(z0m / obu));
+  } else if (zeta <= 1.0) {
+    o->ustar = vkc * um / (log(zldis / z0m) + 5.0 * zeta - 5.0 * z0m / obu);
+  } else {
+    o->ustar = vkc * um / (log(obu / z0m) + 5.0 - 5.0 * z0m / obu + (5.0 * log(zeta) + zeta - 1.0));
+  }
+  if (zeta < 0.0) vds_tmp = 2.e-3 * o->ustar * (1.0 + pow(300.0 / (-obu), 0.666));
+  else vds_tmp = 2.e-3 * o->ustar;
+  o->vds = vds_tmp;
+  /* 10-m wind */
+  if (zldis - z0m <= 10.0) {
+    o->u10_clm = um;
+  } else {
+    if (zeta < -zetam) {
+      o->u10_clm = um - (o->ustar / vkc * (log(-zetam * obu / (10.0 + z0m)) - StabilityFunc1(-zetam)
+                                                    + StabilityFunc1((10.0 + z0m) / obu)
+                                                    + 1.14 * (pow(-zeta, 0.333) - pow(zetam, 0.333))));
+    } else if (zeta < 0.0) {
+      o->u10_clm = um - (o->ustar / vkc * (log(zldis / (10.0 + z0m)) - StabilityFunc1(zeta)
+                                                    + StabilityFunc1((10.0 + z0m) / obu)));
+    } else if (zeta <= 1.0) {
+      o->u10_clm = um - (o->ustar / vkc * (log(zldis / (10.0 + z0m)) + 5.0 * zeta - 5.0 * (10.0 + z0m) / obu));
+    } else {
+      o->u10_clm = um - (o->ustar / vkc * (log(obu / (10.0 + z0m)) + 5.0 - 5.0 * (10.0 + z0m) / obu
+                                                    + (5.0 * log(zeta) + zeta - 1.0)));
+    }
+  }
+  o->va = um;
+  /* temperature profile */
+  zldis = hgt_t - displa;
+  zeta = zldis / obu;
+  if (zeta < -zetat) {
+    o->temp1 = vkc / (log(-zetat * obu / z0h) - StabilityFunc2(-zetat) + StabilityFunc2(z0h / obu)
+                      + 0.8 * (pow(zetat, -0.333) - pow(-zeta, -0.333)));
+  } else if (zeta < 0.0) {
+    o->temp1 = vkc / (log(zldis / z0h) - StabilityFunc2(zeta) + StabilityFunc2(z0h / obu));
+  } else if (zeta <= 1.0) {
+    o->temp1 = vkc / (log(zldis / z0h) + 5.0 * zeta - 5.0 * z0h / obu);
+  } else {
+    o->temp1 = vkc / (log(obu / z0h) + 5.0 - 5.0 * z0h / obu + (5.0 * log(zeta) + zeta - 1.0));
+  }
+  /* humidity profile */
+  if (hgt_q == hgt_t && z0q == z0h) {
+    o->temp2 = o->temp1;
+  } else {
+    zldis = hgt_q - displa;
+    zeta = zldis / obu;
+    if (zeta < -zetat) {
+      o->temp2 = vkc / (log(-zetat * obu / z0q) - StabilityFunc2(-zetat) + StabilityFunc2(z0q / obu)
+                        + 0.8 * (pow(zetat, -0.333) - pow(-zeta, -0.333)));
+    } else if (zeta < 0.0) {
+      o->temp2 = vkc / (log(zldis / z0q) - StabilityFunc2(zeta) + StabilityFunc2(z0q / obu));
+    } else if (zeta <= 1.0) {
+      o->temp2 = vkc / (log(zldis / z0q) + 5.0 * zeta - 5.0 * z0q / obu);
+    } else {
+      o->temp2 = vkc / (log(obu / z0q) + 5.0 - 5.0 * z0q / obu + (5.0 * log(zeta) + zeta - 1.0));
+    }
+  }
+  /* temperature profile applied at 2-m */
+  zldis = 2.0 + z0h;
+  zeta = zldis / obu;
+  if (zeta < -zetat) {
+    o->temp12m = vkc / (log(-zetat * obu / z0h) - StabilityFunc2(-zetat) + StabilityFunc2(z0h / obu)
+                        + 0.8 * (pow(zetat, -0.333) - pow(-zeta, -0.333)));
+  } else if (zeta < 0.0) {
+    o->temp12m = vkc / (log(zldis / z0h) - StabilityFunc2(zeta) + StabilityFunc2(z0h / obu));
+  } else if (zeta <= 1.0) {
+    o->temp12m = vkc / (log(zldis / z0h) + 5.0 * zeta - 5.0 * z0h / obu);
+  } else {
+    o->temp12m = vkc / (log(obu / z0h) + 5.0 - 5.0 * z0h / obu + (5.0 * log(zeta) + zeta - 1.0));
+  }
+  /* humidity profile applied at 2-m */
+  if (z0q == z0h) {
+    o->temp22m = o->temp12m;
+  } else {
+    zldis = 2.0 + z0q;
+    zeta = zldis / obu;
+    if (zeta < -zetat) {
+      o->temp22m = vkc / (log(-zetat * obu / z0q) - StabilityFunc2(-zetat) + StabilityFunc2(z0q / obu)
+                          + 0.8 * (pow(zetat, -0.333) - pow(-zeta, -0.333)));
+    } else if (zeta < 0.0) {
+      o->temp22m = vkc / (log(zldis / z0q) - StabilityFunc2(zeta) + StabilityFunc2(z0q / obu));
+    } else if (zeta <= 1.0) {
+      o->temp22m = vkc / (log(zldis / z0q) + 5.0 * zeta - 5.0 * z0q / obu);
+    } else {
+      o->temp22m = vkc / (log(obu / z0q) + 5.0 - 5.0 * z0q / obu + (5.0 * log(zeta) + zeta - 1.0));
+    }
+  }
+  /* 10-m wind for the dust model */
+  zldis = hgt_u - displa;
+  zeta = zldis / obu;
+  if (fmin(zeta, 1.0) < 0.0) {
+    tmp1 = pow(1.0 - 16.0 * fmin(zeta, 1.0), 0.25);
+    tmp2 = log((1.0 + tmp1 * tmp1) / 2.0);
+    tmp3 = log((1.0 + tmp1) / 2.0);
+    fmnew = 2.0 * tmp3 + tmp2 - 2.0 * atan(tmp1) + 1.5707963;
+  } else {
+    fmnew = -5.0 * fmin(zeta, 1.0);
+  }
+  if (iter == 1) o->fm = fmnew;
+  else o->fm = 0.5 * (o->fm + fmnew);
+  zeta10 = fmin(10.0 / obu, 1.0);
+  if (zeta == 0.0) zeta10 = 0.0;
+  if (zeta10 < 0.0) {
+    tmp1 = pow(1.0 - 16.0 * zeta10, 0.25);
+    tmp2 = log((1.0 + tmp1 * tmp1) / 2.0);
+    tmp3 = log((1.0 + tmp1) / 2.0);
+    fm10 = 2.0 * tmp3 + tmp2 - 2.0 * atan(tmp1) + 1.5707963;
+  } else {
+    fm10 = -5.0 * zeta10;
+  }
+  tmp4 = log(fmax(1.0, hgt_u / 10.0));
+  o->u10 = ur - o->ustar / vkc * (tmp4 - o->fm + fm10);
+  o->fv = o->ustar;
+}
+
+/* FrictionVelocity over a patch filter.  Dummy arrays are (begp0:endp0). */
 static void FrictionVelocity(cf_ctx* x, int fn, const int32_t* filtern, const double* displa, const double* z0m,
                              const double* z0h, const double* z0q, const double* obu, int iter, const double* ur,
                              const double* um, double* ustar, double* temp1, double* temp2, double* temp12m,
                              double* temp22m, double* fm) {
-  const double zetam = 1.574, zetat = 0.465;
   const int o = x->begp0;
   for (int f = 0; f < fn; ++f) {
     const int n = filtern[f], i = n - o;
-    double zldis, zeta, tmp1, tmp2, tmp3, tmp4, fmnew, fm10, zeta10, vds_tmp;
-    /* wind profile */
-    zldis = P1(forc_hgt_u_patch, n) - displa[i];
-    zeta = zldis / obu[i];
-    if (zeta < -zetam) {
-      ustar[i] = vkc * um[i] / (log(-zetam * obu[i] / z0m[i]) - StabilityFunc1(-zetam) + StabilityFunc1(z0m[i] / obu[i])
-                                + 1.14 * (pow(-zeta, 0.333) - pow(zetam, 0.333)));
-    } else if (zeta < 0.0) {
-      ustar[i] = vkc * um[i] / (log(zldis / z0m[i]) - StabilityFunc1(zeta) + StabilityFunc1(z0m[i] / obu[i]));
-    } else if (zeta <= 1.0) {
-      ustar[i] = vkc * um[i] / (log(zldis / z0m[i]) + 5.0 * zeta - 5.0 * z0m[i] / obu[i]);
-    } else {
-      ustar[i] = vkc * um[i] / (log(obu[i] / z0m[i]) + 5.0 - 5.0 * z0m[i] / obu[i] + (5.0 * log(zeta) + zeta - 1.0));
-    }
-    if (zeta < 0.0) vds_tmp = 2.e-3 * ustar[i] * (1.0 + pow(300.0 / (-obu[i]), 0.666));
-    else vds_tmp = 2.e-3 * ustar[i];
-    P1(vds, n) = vds_tmp;
-    /* 10-m wind */
-    if (zldis - z0m[i] <= 10.0) {
-      P1(u10_clm, n) = um[i];
-    } else {
-      if (zeta < -zetam) {
-        P1(u10_clm, n) = um[i] - (ustar[i] / vkc * (log(-zetam * obu[i] / (10.0 + z0m[i])) - StabilityFunc1(-zetam)
-                                                      + StabilityFunc1((10.0 + z0m[i]) / obu[i])
-                                                      + 1.14 * (pow(-zeta, 0.333) - pow(zetam, 0.333))));
-      } else if (zeta < 0.0) {
-        P1(u10_clm, n) = um[i] - (ustar[i] / vkc * (log(zldis / (10.0 + z0m[i])) - StabilityFunc1(zeta)
-                                                      + StabilityFunc1((10.0 + z0m[i]) / obu[i])));
-      } else if (zeta <= 1.0) {
-        P1(u10_clm, n) = um[i] - (ustar[i] / vkc * (log(zldis / (10.0 + z0m[i])) + 5.0 * zeta - 5.0 * (10.0 + z0m[i]) / obu[i]));
-      } else {
-        P1(u10_clm, n) = um[i] - (ustar[i] / vkc * (log(obu[i] / (10.0 + z0m[i])) + 5.0 - 5.0 * (10.0 + z0m[i]) / obu[i]
-                                                      + (5.0 * log(zeta) + zeta - 1.0)));
-      }
-    }
-    P1(va, n) = um[i];
-    /* temperature profile */
-    zldis = P1(forc_hgt_t_patch, n) - displa[i];
-    zeta = zldis / obu[i];
-    if (zeta < -zetat) {
-      temp1[i] = vkc / (log(-zetat * obu[i] / z0h[i]) - StabilityFunc2(-zetat) + StabilityFunc2(z0h[i] / obu[i])
-                        + 0.8 * (pow(zetat, -0.333) - pow(-zeta, -0.333)));
-    } else if (zeta < 0.0) {
-      temp1[i] = vkc / (log(zldis / z0h[i]) - StabilityFunc2(zeta) + StabilityFunc2(z0h[i] / obu[i]));
-    } else if (zeta <= 1.0) {
-      temp1[i] = vkc / (log(zldis / z0h[i]) + 5.0 * zeta - 5.0 * z0h[i] / obu[i]);
-    } else {
-      temp1[i] = vkc / (log(obu[i] / z0h[i]) + 5.0 - 5.0 * z0h[i] / obu[i] + (5.0 * log(zeta) + zeta - 1.0));
-    }
-    /* humidity profile */
-    if (P1(forc_hgt_q_patch, n) == P1(forc_hgt_t_patch, n) && z0q[i] == z0h[i]) {
-      temp2[i] = temp1[i];
-    } else {
-      zldis = P1(forc_hgt_q_patch, n) - displa[i];
-      zeta = zldis / obu[i];
-      if (zeta < -zetat) {
-        temp2[i] = vkc / (log(-zetat * obu[i] / z0q[i]) - StabilityFunc2(-zetat) + StabilityFunc2(z0q[i] / obu[i])
-                          + 0.8 * (pow(zetat, -0.333) - pow(-zeta, -0.333)));
-      } else if (zeta < 0.0) {
-        temp2[i] = vkc / (log(zldis / z0q[i]) - StabilityFunc2(zeta) + StabilityFunc2(z0q[i] / obu[i]));
-      } else if (zeta <= 1.0) {
-        temp2[i] = vkc / (log(zldis / z0q[i]) + 5.0 * zeta - 5.0 * z0q[i] / obu[i]);
-      } else {
-        temp2[i] = vkc / (log(obu[i] / z0q[i]) + 5.0 - 5.0 * z0q[i] / obu[i] + (5.0 * log(zeta) + zeta - 1.0));
-      }
-    }
-    /* temperature profile applied at 2-m */
-    zldis = 2.0 + z0h[i];
-    zeta = zldis / obu[i];
-    if (zeta < -zetat) {
-      temp12m[i] = vkc / (log(-zetat * obu[i] / z0h[i]) - StabilityFunc2(-zetat) + StabilityFunc2(z0h[i] / obu[i])
-                          + 0.8 * (pow(zetat, -0.333) - pow(-zeta, -0.333)));
-    } else if (zeta < 0.0) {
-      temp12m[i] = vkc / (log(zldis / z0h[i]) - StabilityFunc2(zeta) + StabilityFunc2(z0h[i] / obu[i]));
-    } else if (zeta <= 1.0) {
-      temp12m[i] = vkc / (log(zldis / z0h[i]) + 5.0 * zeta - 5.0 * z0h[i] / obu[i]);
-    } else {
-      temp12m[i] = vkc / (log(obu[i] / z0h[i]) + 5.0 - 5.0 * z0h[i] / obu[i] + (5.0 * log(zeta) + zeta - 1.0));
-    }
-    /* humidity profile applied at 2-m */
-    if (z0q[i] == z0h[i]) {
-      temp22m[i] = temp12m[i];
-    } else {
-      zldis = 2.0 + z0q[i];
-      zeta = zldis / obu[i];
-      if (zeta < -zetat) {
-        temp22m[i] = vkc / (log(-zetat * obu[i] / z0q[i]) - StabilityFunc2(-zetat) + StabilityFunc2(z0q[i] / obu[i])
-                            + 0.8 * (pow(zetat, -0.333) - pow(-zeta, -0.333)));
-      } else if (zeta < 0.0) {
-        temp22m[i] = vkc / (log(zldis / z0q[i]) - StabilityFunc2(zeta) + StabilityFunc2(z0q[i] / obu[i]));
-      } else if (zeta <= 1.0) {
-        temp22m[i] = vkc / (log(zldis / z0q[i]) + 5.0 * zeta - 5.0 * z0q[i] / obu[i]);
-      } else {
-        temp22m[i] = vkc / (log(obu[i] / z0q[i]) + 5.0 - 5.0 * z0q[i] / obu[i] + (5.0 * log(zeta) + zeta - 1.0));
-      }
-    }
-    /* 10-m wind for the dust model */
-    zldis = P1(forc_hgt_u_patch, n) - displa[i];
-    zeta = zldis / obu[i];
-    if (fmin(zeta, 1.0) < 0.0) {
-      tmp1 = pow(1.0 - 16.0 * fmin(zeta, 1.0), 0.25);
-      tmp2 = log((1.0 + tmp1 * tmp1) / 2.0);
-      tmp3 = log((1.0 + tmp1) / 2.0);
-      fmnew = 2.0 * tmp3 + tmp2 - 2.0 * atan(tmp1) + 1.5707963;
-    } else {
-      fmnew = -5.0 * fmin(zeta, 1.0);
-    }
-    if (iter == 1) fm[i] = fmnew;
-    else fm[i] = 0.5 * (fm[i] + fmnew);
-    zeta10 = fmin(10.0 / obu[i], 1.0);
-    if (zeta == 0.0) zeta10 = 0.0;
-    if (zeta10 < 0.0) {
-      tmp1 = pow(1.0 - 16.0 * zeta10, 0.25);
-      tmp2 = log((1.0 + tmp1 * tmp1) / 2.0);
-      tmp3 = log((1.0 + tmp1) / 2.0);
-      fm10 = 2.0 * tmp3 + tmp2 - 2.0 * atan(tmp1) + 1.5707963;
-    } else {
-      fm10 = -5.0 * zeta10;
-    }
-    tmp4 = log(fmax(1.0, P1(forc_hgt_u_patch, n) / 10.0));
-    P1(u10, n) = ur[i] - ustar[i] / vkc * (tmp4 - fm[i] + fm10);
-    P1(fv, n) = ustar[i];
+    oracle_fricvel_t r;
+    r.fm = fm[i];
+    oracle_friction_velocity_point(P1(forc_hgt_u_patch, n), P1(forc_hgt_t_patch, n), P1(forc_hgt_q_patch, n), displa[i], z0m[i],
+                                   z0h[i], z0q[i], obu[i], iter, ur[i], um[i], &r);
+    ustar[i] = r.ustar; temp1[i] = r.temp1; temp2[i] = r.temp2; temp12m[i] = r.temp12m; temp22m[i] = r.temp22m; fm[i] = r.fm;
+    P1(vds, n) = r.vds; P1(u10_clm, n) = r.u10_clm; P1(va, n) = r.va; P1(u10, n) = r.u10; P1(fv, n) = r.fv;
   }
 }
 

@@ -35,6 +35,13 @@ typedef struct cf_ctx {
 #define PFT(name, ivt) (x->f->name[(ivt)])
 #define PFTV(name, ivt, lvl) (x->f->name[(size_t)((lvl) - 1) * NPFT + (ivt)])
 
+/* outputs of FrictionVelocity for one point (FrictionVelocityMod.F90:754-1117) */
+typedef struct oracle_fricvel_t { double ustar, temp1, temp2, temp12m, temp22m, fm, vds, u10_clm, va, u10, fv; } oracle_fricvel_t;
+void oracle_friction_velocity_point(double hgt_u, double hgt_t, double hgt_q, double displa, double z0m, double z0h, double z0q,
+                                    double obu, int iter, double ur, double um, oracle_fricvel_t* o);
+void oracle_qsat(double T, double p, double* qs, double* es, double* qsdT);
+void oracle_moninobukini(double zetamaxstable, double ur, double thv, double dthv, double zldis, double z0m, double* um,
+                         double* obu);
 int oracle_quadratic(double a, double b, double c, double* r1, double* r2);
 double oracle_plc(double x, double psi50, double ck);
 double oracle_d1plc(double x, double psi50, double ck);

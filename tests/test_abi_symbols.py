@@ -32,7 +32,7 @@ def test_version_and_defaults_match_python_twin():
             continue
         assert getattr(p, name) == getattr(q, name), name
     # layout check of the ctypes mirror: first, middle and last members as ctsm_b200_default_params wrote them
-    assert (p.abi_version, p.nlevsno, p.nlevgrnd, p.nlevsoi) == (3, 12, 25, 20)
+    assert (p.abi_version, p.nlevsno, p.nlevgrnd, p.nlevsoi) == (4, 12, 25, 20)
     assert (p.dtmin, p.xTolerUpper, p.snow_thermal_cond_method) == (60.0, 0.1, 2)
     assert (p.itmax_canopy_fluxes, p.z0param_method, p.stomatalcond_mtd) == (40, 2, 2)
     assert (p.csoilc, p.zetamaxstable, p.lmrhd, p.jmax25top_sf, p.balance_skip_steps) == (0.004, 2.0, 150650.0, 1.0, -1)

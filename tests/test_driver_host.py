@@ -28,6 +28,20 @@ def test_step_order_is_clm_drv_order_and_every_routine_is_bound():
         abi.make_struct(g, S, sg.bounds)                           # every field of every group exists with the right shape
 
 
+def test_pre_flux_routines_are_bound_in_clm_drv_order():
+    assert driver.PRE_ROUTINES == ("preflux", "surfacehumidity", "baregroundfluxes")        # clm_driver.F90:680, 702, 711
+    L = abi.lib()
+    symbol = {"preflux": "ctsm_b200_biogeophys_pre_flux_calcs", "surfacehumidity": "ctsm_b200_calculate_surface_humidity",
+              "baregroundfluxes": "ctsm_b200_bare_ground_fluxes"}
+    sg, S = _case()
+    synthetic_canopy.preflux_state(sg, S, np.random.Generator(np.random.PCG64(6)))
+    for g in driver.PRE_ROUTINES:
+        assert g in abi.FIELDS and g in driver.FILTER_OF and hasattr(L, symbol[g])
+        abi.make_struct(g, S, sg.bounds)
+        for k in driver.FILTER_OF[g]:
+            assert k in sg.filters
+
+
 def test_algorithmic_bytes_follow_the_field_table():
     sg, S = _case()
     for g in driver.ROUTINES:

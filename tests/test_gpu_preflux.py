@@ -1,0 +1,118 @@
+"""GPU parity of the routines clm_drv runs just before CanopyFluxes - BiogeophysPreFluxCalcs,
+CalculateSurfaceHumidity, BareGroundFluxes - through the C ABI against the CPU oracle, chained as in clm_drv
+(clm_driver.F90:680-718).  Tolerance: 1e-10 relative (north_star); fields without transcendentals come out bit-identical."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from ctsm_b200 import abi
+from tests.util import copy_state, to_device, group_arrays
+from tests.test_oracle_preflux import case, run_preflux, run_humidity, run_bare
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+# results of +, -, *, /, min, max and copies only: identical bits expected
+EXACT = {"preflux": ("t_ssbef", "t_h2osfc_bef", "t_grnd", "emg", "htvp", "beta", "zii", "thv", "z0hg_p", "kbm1", "eflx_sh_tot",
+                     "cgrnd", "cgrnds", "cgrndl"),
+         "surfacehumidity": (), "baregroundfluxes": ("btran", "t_veg", "rssun", "rssha", "rootr", "rresis", "displa", "z0mv",
+                                                     "num_iter", "z0mg_p", "qflx_tran_veg")}
+
+
+def gpu_call(L, ctx, group, sg, S, mem, call):
+    st = abi.Status()
+    if mem == abi.MEM_DEVICE:
+        D = to_device(group_arrays(S, group))
+        f = abi.make_struct(group, D, sg.bounds)
+        flt = {k: to_device({"f": v})["f"] for k, v in sg.filters.items() if len(v)}
+        rc = call(f, flt, st)
+        assert rc == 0, st.msg
+        rc = L.ctsm_b200_sync(ctx, C.byref(st))
+        for k, v in D.items():
+            S[k][...] = v.cpu().numpy()
+    else:
+        f = abi.make_struct(group, S, sg.bounds)
+        rc = call(f, sg.filters, st)
+    return rc, st
+
+
+def compare(group, got, ref, worst):
+    for fs in abi.FIELDS[group]:
+        a, b = got[fs.name], ref[fs.name]
+        if fs.intent == "IN":
+            assert np.array_equal(a, b, equal_nan=True), "input %s was modified" % fs.name
+            continue
+        if fs.ctype == "int" or fs.name in EXACT[group]:
+            assert np.array_equal(a, b, equal_nan=True), "%s differs" % fs.name
+            continue
+        fin = np.abs(b) < 1e30
+        assert np.array_equal(fin, np.abs(a) < 1e30), "%s: fill pattern differs" % fs.name
+        if not fin.any():
+            continue
+        scale = float(np.max(np.abs(b[fin])))
+        e = float(np.max(np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), 1e-6 * scale + 1e-300)))
+        worst[group + "." + fs.name] = e
+        assert e <= RTOL, (group, fs.name, e)
+
+
+@pytest.mark.parametrize("mem", [abi.MEM_DEVICE, abi.MEM_HOST])
+@pytest.mark.parametrize("method,resis", [(2, 1), (1, 0)], ids=["meier2022_sl14", "zengwang2007_leepielke"])
+def test_preflux_chain_matches_oracle(oracle_lib, mem, method, resis):
+    L = abi.lib()
+    sg, S = case(6000, 501, wet_every=3)
+    S["htop"][sg.filters["nolakep"][::17] - 1] = 0.0
+    prm = abi.default_params()
+    prm.z0param_method, prm.soil_resis_method = method, resis
+    ref, got = copy_state(S), copy_state(S)
+    assert run_preflux(oracle_lib, prm, sg, ref) == 0
+    assert run_humidity(oracle_lib, sg, ref) == 0
+    assert run_bare(oracle_lib, prm, sg, ref) == 0
+    ctx = C.c_void_p()
+    assert L.ctsm_b200_init(C.byref(prm), C.byref(ctx)) == 0
+    worst = {}
+    try:
+        b = C.byref(sg.bounds)
+        n = {k: len(v) for k, v in sg.filters.items()}
+        rc, st = gpu_call(L, ctx, "preflux", sg, got, mem, lambda f, fl, st: L.ctsm_b200_biogeophys_pre_flux_calcs(
+            ctx, b, n["nolakec"], abi.i32p(fl["nolakec"]), n["nolakep"], abi.i32p(fl["nolakep"]), 0, None, 0, C.byref(f), mem, C.byref(st)))
+        assert rc == 0, st.msg
+        rc, st = gpu_call(L, ctx, "surfacehumidity", sg, got, mem, lambda f, fl, st: L.ctsm_b200_calculate_surface_humidity(
+            ctx, b, n["nolakec"], abi.i32p(fl["nolakec"]), C.byref(f), mem, C.byref(st)))
+        assert rc == 0, st.msg
+        rc, st = gpu_call(L, ctx, "baregroundfluxes", sg, got, mem, lambda f, fl, st: L.ctsm_b200_bare_ground_fluxes(
+            ctx, b, n["noexposedvegp"], abi.i32p(fl["noexposedvegp"]), C.byref(f), mem, C.byref(st)))
+        assert rc == 0, st.msg
+    finally:
+        L.ctsm_b200_finalize(ctx)
+    for g in ("preflux", "surfacehumidity", "baregroundfluxes"):
+        compare(g, got, ref, worst)
+    print("f2 chain worst:", sorted(worst.items(), key=lambda kv: -kv[1])[:6])
+    assert len(sg.filters["noexposedvegp"]) > 5000
+
+
+def test_preflux_refuses_urban_and_first_steps(oracle_lib):
+    L = abi.lib()
+    sg, S = case(300, 511)
+    prm = abi.default_params()
+    ctx = C.c_void_p()
+    assert L.ctsm_b200_init(C.byref(prm), C.byref(ctx)) == 0
+    try:
+        b = C.byref(sg.bounds)
+        fc, fp = sg.filters["nolakec"], sg.filters["nolakep"]
+        ref, got = copy_state(S), copy_state(S)
+        assert run_preflux(oracle_lib, prm, sg, ref, flags=1) == 0
+        st = abi.Status()
+        f = abi.make_struct("preflux", got, sg.bounds)
+        assert L.ctsm_b200_biogeophys_pre_flux_calcs(ctx, b, len(fc), abi.i32p(fc), len(fp), abi.i32p(fp), 0, None, 1, C.byref(f),
+                                                     abi.MEM_HOST, C.byref(st)) == 0
+        np.testing.assert_array_equal(got["z0m"], ref["z0m"])
+        np.testing.assert_array_equal(got["forc_hgt_u_patch"], ref["forc_hgt_u_patch"])
+        # an urban column filter, or a column of an urban landunit in filter_nolakec, is refused
+        assert L.ctsm_b200_biogeophys_pre_flux_calcs(ctx, b, len(fc), abi.i32p(fc), len(fp), abi.i32p(fp), 1, abi.i32p(fc), 0,
+                                                     C.byref(f), abi.MEM_HOST, C.byref(st)) == 16
+        got["lun_itype"][fc[5] - 1] = 8
+        rc = L.ctsm_b200_biogeophys_pre_flux_calcs(ctx, b, len(fc), abi.i32p(fc), len(fp), abi.i32p(fp), 0, None, 0, C.byref(f),
+                                                   abi.MEM_HOST, C.byref(st))
+        assert rc == 16 and st.subgrid_index == fc[5]
+    finally:
+        L.ctsm_b200_finalize(ctx)
