@@ -32,12 +32,16 @@ sys.path.insert(0, ROOT)
 
 METRIC = "column_timesteps_per_sec"
 UNIT = "column-steps/s"
+PRE_ROUTINES = ("preflux", "surfacehumidity", "baregroundfluxes")     # clm_driver.F90:680, 702, 711
 ALL_ROUTINES = ("canopyfluxes", "soiltemperature", "soilfluxes", "patch2col", "plantsink", "soilwater", "balancecheck")   # clm_drv order
 KERNEL_OF = {"plantsink": "plantsink_kernel", "soilfluxes": "soilfluxes_patch_kernel + soilfluxes_p2c_kernel", "patch2col": "patch2col_kernel<false/true>", "balancecheck": "balance_col/grc/patch/loc kernels",
              "canopyfluxes": "CanopyFluxes kernel chain of one call (init, then per ITERATION pass close/fric/leaf, "
                              "phs_ci x4, phs_newton x4, phs_end; final) - largest member: phs_newton_kernel",
              "soiltemperature": "soiltemp_kernel", "soilwater": "soilwater_kernel"}
-NAME_OF = {"canopyfluxes": "CanopyFluxes", "soiltemperature": "SoilTemperature", "soilwater": "SoilWater",
+KERNEL_OF.update({"preflux": "preflux_patch_a / preflux_col / preflux_patch_b kernels", "surfacehumidity": "surface_humidity_kernel",
+                  "baregroundfluxes": "bareground_kernel + bareground_colcopy_kernel"})
+NAME_OF = {"preflux": "BiogeophysPreFluxCalcs", "surfacehumidity": "CalculateSurfaceHumidity", "baregroundfluxes": "BareGroundFluxes",
+           "canopyfluxes": "CanopyFluxes", "soiltemperature": "SoilTemperature", "soilwater": "SoilWater",
            "plantsink": "VertTranSink_HydStress", "balancecheck": "BalanceCheck", "soilfluxes": "SoilFluxes", "patch2col": "clm_drv_patch2col"}
 
 
@@ -47,6 +51,7 @@ def make_workload(size, seed):
     sg, S = synthetic_canopy.make_full_case(size, seed=seed)
     synthetic_canopy.balance_state(sg, S, np.random.Generator(np.random.PCG64(seed + 1)), 1.0e-11)
     synthetic_canopy.soilfluxes_state(sg, S, np.random.Generator(np.random.PCG64(seed + 2)))
+    synthetic_canopy.preflux_state(sg, S, np.random.Generator(np.random.PCG64(seed + 3)))     # own generator: adds fields only
     return sg, S
 
 
@@ -133,7 +138,7 @@ FP64_LANES_PER_SM, N_SM = 64, 148          # B200: 148 SMs x 4 SMSPs x 16 FP64 l
 
 
 def which_mask(routines):
-    return sum({"soiltemperature": 1, "soilwater": 2, "canopyfluxes": 4, "plantsink": 8, "balancecheck": 16, "soilfluxes": 32, "patch2col": 64}[g] for g in routines)
+    return sum({"soiltemperature": 1, "soilwater": 2, "canopyfluxes": 4, "plantsink": 8, "balancecheck": 16, "soilfluxes": 32, "patch2col": 64}.get(g, 0) for g in routines)   # (the CPU arm times the seven-routine step)
 
 
 def cpu_reference_run(size_label, routines, steps, warmup, sample_gridcells, seed):
@@ -203,7 +208,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     size = a.size if not a.size.isdigit() else int(a.size)
-    routines = tuple(g for g in ALL_ROUTINES if g in a.routines.split(","))
+    # --routines names a subset of the step; "pre" (or the three names) adds the routines clm_drv runs before CanopyFluxes
+    want = a.routines.replace("pre,", ",".join(PRE_ROUTINES) + ",").split(",")
+    routines = tuple(g for g in PRE_ROUTINES + ALL_ROUTINES if g in want)
     strong = a.scaling == "strong" or world == 1
     from ctsm_b200 import synthetic
     members_local = a.members

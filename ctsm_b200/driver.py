@@ -358,6 +358,9 @@ def algorithmic_bytes(sg, S, group: str) -> Dict[str, float]:
     elif group == "balancecheck":
         ncol = sg.ncol; cols = np.arange(sg.ncol)
         npat = sg.npatch; pats = np.arange(sg.npatch)
+    elif group == "baregroundfluxes":
+        pats = sg.filters["noexposedvegp"] - 1; npat = len(pats)
+        cols = np.unique(sg.patch_column[pats]) - 1; ncol = len(cols)
     elif group == "canopyfluxes":
         pats = sg.filters["exposedvegp"] - 1; npat = len(pats)
         cols = np.unique(sg.patch_column[pats]) - 1; ncol = len(cols)      # each column counted once per step
