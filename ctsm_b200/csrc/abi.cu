@@ -55,6 +55,7 @@ extern "C" int ctsm_b200_init(const ctsm_params_t* p, ctsm_b200_ctx** out) {
   if (const char* e = getenv("CTSM_B200_NT_BUDGET")) ctx->tune.nt_budget = atoi(e);
   if (const char* e = getenv("CTSM_B200_TAIL_LANES")) ctx->tune.tail_lanes = atoi(e);
   if (const char* e = getenv("CTSM_B200_NT_SPLIT")) ctx->tune.nt_split = atoi(e);
+  if (const char* e = getenv("CTSM_B200_SOIL_STREAM")) ctx->tune.soil_stream = atoi(e);
   const int rc = [&]() -> int {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
@@ -98,6 +99,12 @@ extern "C" int ctsm_b200_finalize(ctsm_b200_ctx* ctx) {
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+  return CTSM_OK;
+}
+
+extern "C" int ctsm_b200_set_soil_tuning(ctsm_b200_ctx* ctx, int soil_stream) {
+  if (!ctx) return CTSM_ERR_BAD_ARG;
+  if (soil_stream >= 0) ctx->tune.soil_stream = soil_stream;
   return CTSM_OK;
 }
 

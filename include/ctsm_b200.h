@@ -331,6 +331,10 @@ int  ctsm_b200_set_member_params(ctsm_b200_ctx* ctx, int nmember, const double* 
  *               kernels, 0: as lane tasks of one persistent kernel.
  * A negative argument keeps the current value. */
 int  ctsm_b200_set_tuning(ctsm_b200_ctx* ctx, int tail_max, int nt_budget, int tail_lanes, int nt_split);
+/* SoilTemperature formulation (results are bit-identical): soil_stream 1 (default; CTSM_B200_SOIL_STREAM) streams the levels
+ * through registers and a coalesced scratch (soiltemp_stream_kernel), 0 keeps the per-thread level arrays (soiltemp_kernel);
+ * a negative value leaves the setting unchanged. */
+int  ctsm_b200_set_soil_tuning(ctsm_b200_ctx* ctx, int soil_stream);
 /* Diagnostic of the last ctsm_b200_canopyfluxes call (synchronises the stream): for every ITERATION round r < cap,
  * list_len[r] = patches the round's list kernels served, tail_end[r] = patches handed to the tail kernel up to and
  * including round r.  Returns the number of rounds written. */

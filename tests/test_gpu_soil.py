@@ -85,6 +85,24 @@ def test_soiltemperature_matches_oracle(gpu_ctx, oracle_lib, size, mem):
     print("worst rel err:", max(worst.values()), max(worst, key=worst.get))
 
 
+def test_soiltemperature_kernels_agree_bit_for_bit(gpu_ctx):
+    """The level-streaming kernel (default) and the per-thread-array kernel are two schedules of the same arithmetic:
+    every output, integer or real, must agree bit for bit (ctsm_b200_set_soil_tuning)."""
+    L, ctx, prm = gpu_ctx
+    sg, S = synthetic.make_case(20000, seed=77)
+    a, b = copy_state(S), copy_state(S)
+    try:
+        assert L.ctsm_b200_set_soil_tuning(ctx, 0) == 0
+        assert _run_gpu_soiltemp(L, ctx, sg, a, abi.MEM_DEVICE)[0] == 0
+        assert L.ctsm_b200_set_soil_tuning(ctx, 1) == 0
+        assert _run_gpu_soiltemp(L, ctx, sg, b, abi.MEM_DEVICE)[0] == 0
+    finally:
+        L.ctsm_b200_set_soil_tuning(ctx, 1)
+    for fs in abi.FIELDS["soiltemperature"]:
+        assert np.array_equal(a[fs.name], b[fs.name], equal_nan=True), fs.name
+    assert set(np.unique(b["imelt"])) >= {0, 1, 2}
+
+
 def test_soiltemperature_filter_subset_and_offset_bounds(gpu_ctx, oracle_lib):
     """Clump-style call: bounds are a sub-range of the allocation; columns outside keep their values."""
     L, ctx, prm = gpu_ctx
