@@ -33,7 +33,7 @@ for r in rows[hi + 1:]:
 
 
 def routine_of(k):
-    if k in ("soiltemp_kernel", "patchmask_kernel"):
+    if k.startswith("soiltemp") or k == "patchmask_kernel":
         return "SoilTemperature"
     if "soilwater" in k:
         return "SoilWater"
