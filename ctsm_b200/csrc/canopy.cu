@@ -734,11 +734,15 @@ __device__ __forceinline__ void fric_body(const CanopyDev& f, const CanopyPrm& p
   }
 }
 
+// Residency of the two uniform kernels that open a pass.  Measured at f02 on B200 (CanopyFluxes call, ms): unconstrained
+// (150 / 201 registers) 106.1; 4 blocks of 128 threads (128 registers, 16 warps per SM, no spills) 103.0; 5 blocks (96
+// registers, spills) 103.3; 80 / 64 registers 108.8 / 110.9.  Both kernels wait on HBM (long scoreboard): more warps help
+// until the spills start.
 #ifndef FRIC_MINBLOCKS
-#define FRIC_MINBLOCKS 1
+#define FRIC_MINBLOCKS 4
 #endif
 #ifndef LEAF_MINBLOCKS
-#define LEAF_MINBLOCKS 1
+#define LEAF_MINBLOCKS 4
 #endif
 __global__ void __launch_bounds__(STEP_THREADS, FRIC_MINBLOCKS)
 canopy_fric_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, const int32_t* __restrict__ filterp,
@@ -2257,15 +2261,19 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
     // close(0, first) only builds the list of pass 0; fric/leaf(k) open pass k; the task kernels solve its PHS system;
     // close(k+1) closes pass k; close(npass, last) only closes.  The host stops issuing rounds once it has seen (two
     // rounds late, through a pinned copy) that a round's list was empty.
-    // Small calls only: a large filter practically always holds a patch that uses all itmax+1 passes (0.3 % of the
-    // synthetic patches do), and a host that waits on the device could not queue the next clump's uploads meanwhile.
-    const bool early_exit = fn <= 65536;
+    // Inside a resident window only small calls do this: a host that waits on the device could not queue the next clump's
+    // uploads meanwhile (and a large filter practically always holds a patch that uses all itmax+1 passes).
+    const bool early_exit = fn <= 65536 || !ctx->window_open;
     int rounds = 0;
+    bool small_queues = false;      // every calcstress queue of the round is known to be below the split path's threshold
     for (int itlef = 0; itlef <= npass; ++itlef) {
       if (itlef >= 2 && early_exit) {
-        // the host stays at most two rounds ahead of the device, so that it can stop when the lists have run empty
+        // the host stays at most two rounds ahead of the device, so that it can stop when the lists have run empty and
+        // leave out the split-path kernels (three launches per calcstress stage that would return at once) when the list -
+        // an upper bound of every queue of the round, and lists only shrink - is below their threshold
         CUDA_TRY(cudaEventSynchronize(ctx->ev_round[itlef - 2]));
         if (ctx->h_counts[itlef - 2] == 0) break;
+        small_queues = ctx->h_counts[itlef - 2] <= QUAD_MAX;
       }
       canopy_close_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, itlef == 0, itlef == npass, dfilter, ws, wstride,
                                                           L, lin, lout, rec, tail_max, ctx->d_status);
@@ -2302,7 +2310,9 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
           const bool lastq = (i + 1 == NQ_CI);
           int* qo = L.q_ci + (size_t)(lastq ? 0 : i + 1) * cap;
           int* no = lastq ? spare : n_ci + i + 1;
-          if (nt_split) {
+          if (small_queues) {
+            // (nothing: the four-lane kernel below takes the whole queue)
+          } else if (nt_split) {
             // large queues: prologue / iterations / epilogue as three kernels (see NtState); each exits at once on a small queue
             int* n_run = spare + 1 + i;
             int* h_run = spare + 1 + NQ_NT + i;
