@@ -1852,6 +1852,56 @@ __device__ __noinline__ bool close_call(const CanopyDev& f, const CanopyPrm& prm
   return close_body(f, prm, g, itlef0, false, fi, filterp, ws, wstride, ds).keep;
 }
 
+// One launch instead of three for SHORT lists (late rounds: a few thousand patches, every kernel as long as one patch's
+// dependent chain): close pass itlef0-1 of a listed patch and, if it survives, open pass itlef0 for it (fric, leaf) in
+// the same thread.  Same functions as canopy_close / _fric / _leaf_kernel; patches are independent, so the order
+// "all close, all fric, all leaf" against "close, fric, leaf per patch" changes no operand.  PHS configuration only;
+// not used together with the tail kernel.
+__global__ void __launch_bounds__(STEP_THREADS)
+canopy_round_small_kernel(CanopyDev f, CanopyPrm prm, Geo g, int itlef0, const int32_t* __restrict__ filterp,
+                          double* __restrict__ ws, int wstride, Lists L, const int* __restrict__ list_in,
+                          int* __restrict__ list_out, PhsRec* __restrict__ rec, DevStatus* ds) {
+  const int row = itlef0;
+  int off[NBIN + 1];
+  const int total = list_offsets(L, row, off);
+  for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+    const ListSlot sl = list_slot(L, row, off, list_in, base + threadIdx.x);
+    const int fi = sl.fi;
+    const bool live = sl.live && !(L.ejected[fi]);
+    CloseOut c; c.keep = false; c.solve = false; c.night = false;
+    if (live) {
+      phs_outputs<false>(f, prm, g, rec[fi], filterp[fi] - g.begp0, ds);
+      c = close_body(f, prm, g, itlef0, false, fi, filterp, ws, wstride, ds);
+    }
+    const bool gb = c.keep;
+    const unsigned act = __activemask();
+    const unsigned mk = __ballot_sync(act, gb);
+    if (gb) bin_append(L, list_out, row + 1, 0, fi, mk);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const bool gq = gb && c.solve && (c.night == (q == 0));
+      const unsigned mq = __ballot_sync(act, gq);
+      if (gq) {
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(mq) - 1;
+        int b0 = 0;
+        if (lane == leader) b0 = atomicAdd(q == 0 ? L.n_nt(row + 1, 0) : L.n_ci(row + 1, 0), __popc(mq));
+        b0 = __shfl_sync(mq, b0, leader);
+        (q == 0 ? L.q_nt : L.q_ci)[b0 + __popc(mq & ((1u << lane) - 1))] = fi;
+      }
+    }
+    if (gb) {
+#ifdef ROUND_SMALL_CALLS
+      fric_call(f, prm, g, itlef0, fi, filterp, ws, wstride);
+      leaf_call(f, prm, g, itlef0, fi, filterp, ws, wstride, rec, ds);
+#else
+      fric_body(f, prm, g, itlef0, fi, filterp, ws, wstride);
+      leaf_body(f, prm, g, itlef0, fi, filterp, ws, wstride, rec, ds);
+#endif
+    }
+  }
+}
+
 // one thread: where the tail list stands at the end of bulk round `round`
 __global__ void canopy_tail_mark_kernel(Lists L, int round) { L.tail_end[round] = *L.tail_count; }
 
@@ -2275,8 +2325,13 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
         if (ctx->h_counts[itlef - 2] == 0) break;
         small_queues = ctx->h_counts[itlef - 2] <= QUAD_MAX;
       }
-      canopy_close_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, itlef == 0, itlef == npass, dfilter, ws, wstride,
-                                                          L, lin, lout, rec, tail_max, ctx->d_status);
+      // short lists of the PHS configuration: close + fric + leaf in one launch (canopy_round_small_kernel)
+      const bool fused_round = small_queues && cp.hydrstress && !use_tail && itlef > 0 && itlef < npass;
+      if (fused_round)
+        canopy_round_small_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, dfilter, ws, wstride, L, lin, lout, rec, ctx->d_status);
+      else
+        canopy_close_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, itlef == 0, itlef == npass, dfilter, ws, wstride,
+                                                            L, lin, lout, rec, tail_max, ctx->d_status);
       ctx->launches++;
       rounds = itlef + 1;
       if (itlef < npass) {
@@ -2285,7 +2340,7 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
           CUDA_TRY(cudaMemcpyAsync(&ctx->h_counts[itlef], L.counts + (size_t)(itlef + 1) * QROW, sizeof(int), cudaMemcpyDeviceToHost, s));
           CUDA_TRY(cudaEventRecord(ctx->ev_round[itlef], s));
         }
-        canopy_fric_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, dfilter, ws, wstride, L, lout);
+        if (!fused_round) canopy_fric_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, dfilter, ws, wstride, L, lout);
         if (!cp.hydrstress) {
           // use_hydrstress = .false.: Photosynthesis for the sunlit, then the shaded leaves (no ci / calcstress task kernels)
           canopy_photosyn_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, dfilter, ws, wstride, L, lout, ctx->d_status);
@@ -2293,8 +2348,10 @@ extern "C" int ctsm_b200_canopyfluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* b
           int* t = lin; lin = lout; lout = t;
           continue;
         }
-        canopy_leaf_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, dfilter, ws, wstride, L, lout, rec, ctx->d_status);
-        ctx->launches += 2;
+        if (!fused_round) {
+          canopy_leaf_kernel<<<grid_s, STEP_THREADS, 0, s>>>(d, cp, g, itlef, dfilter, ws, wstride, L, lout, rec, ctx->d_status);
+          ctx->launches += 2;
+        }
         const int row = itlef + 1;
         int* crow = L.counts + (size_t)row * QROW;
         int* n_ci = crow + NBIN;
