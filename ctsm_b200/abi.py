@@ -331,6 +331,7 @@ def lib():
     L.ctsm_b200_balancecheck.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.POINTER(STRUCTS["balancecheck"]),
                                          C.c_int, C.c_int, C.POINTER(BalanceReport), C.POINTER(Status)]
     L.ctsm_b200_set_soil_tuning.argtypes = [vp, C.c_int]
+    L.ctsm_b200_set_soilwater_tuning.argtypes = [vp, C.c_int]
     for fn in ("vert_tran_sink_hydstress", "vert_tran_sink_default", "biogeophys_pre_flux_calcs", "calculate_surface_humidity",
                "bare_ground_fluxes", "balancecheck_init", "balancecheck", "soilfluxes", "patch2col"):
         getattr(L, "ctsm_b200_" + fn).restype = C.c_int

@@ -56,6 +56,7 @@ extern "C" int ctsm_b200_init(const ctsm_params_t* p, ctsm_b200_ctx** out) {
   if (const char* e = getenv("CTSM_B200_TAIL_LANES")) ctx->tune.tail_lanes = atoi(e);
   if (const char* e = getenv("CTSM_B200_NT_SPLIT")) ctx->tune.nt_split = atoi(e);
   if (const char* e = getenv("CTSM_B200_SOIL_STREAM")) ctx->tune.soil_stream = atoi(e);
+  if (const char* e = getenv("CTSM_B200_SW_WARP")) ctx->tune.sw_warp = atoi(e);
   const int rc = [&]() -> int {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
@@ -105,6 +106,12 @@ extern "C" int ctsm_b200_finalize(ctsm_b200_ctx* ctx) {
 extern "C" int ctsm_b200_set_soil_tuning(ctsm_b200_ctx* ctx, int soil_stream) {
   if (!ctx) return CTSM_ERR_BAD_ARG;
   if (soil_stream >= 0) ctx->tune.soil_stream = soil_stream;
+  return CTSM_OK;
+}
+
+extern "C" int ctsm_b200_set_soilwater_tuning(ctsm_b200_ctx* ctx, int sw_warp) {
+  if (!ctx) return CTSM_ERR_BAD_ARG;
+  if (sw_warp >= 0) ctx->tune.sw_warp = sw_warp;
   return CTSM_OK;
 }
 

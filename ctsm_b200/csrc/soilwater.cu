@@ -202,6 +202,184 @@ soilwater_kernel(SoilWaterDev f, SoilWaterPrm prm, int begc0, int ldc, int numf_
   f.num_substeps[ci] = (double)nsubstep;
 }
 
+// PASS 2 with one WARP per queued column, lane j = soil level j + 1.  In soilwater_kernel<2> a thread walks its column's
+// sub-steps alone (3-40 attempts of 20 levels x 3 pow each): the launch lasts as long as the slowest column's serial
+// chain (2.4 ms at f02 for 9 % of the columns, 8 of 32 lanes busy).  Per sub-step everything except the pivoted
+// tridiagonal solve is independent per level, so the levels go across the lanes: retention curve, conductivities, fluxes,
+// derivatives and matrix rows per lane with the level below / above fetched by shuffle; the rows go to shared memory,
+// lane 0 runs the same dgtsv_solve, the error estimate is a warp maximum (exact).  Same expressions per level, same
+// operation order inside the solve and the over-saturation sweep: bit-identical to the one-thread form
+// (tests/test_gpu_soil.py::test_soilwater_retry_kernels_agree_bit_for_bit).
+#define SW_WARPS 4
+__global__ void __launch_bounds__(32 * SW_WARPS)
+soilwater_retry_warp_kernel(SoilWaterDev f, SoilWaterPrm prm, int begc0, int ldc, const int32_t* __restrict__ retry,
+                            const int* __restrict__ nretry, DevStatus* ds) {
+  constexpr int N = NLEVSOI;
+  __shared__ double sh[SW_WARPS][4][N];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* dl = sh[wib][0];
+  double* dd = sh[wib][1];
+  double* du = sh[wib][2];
+  double* bb = sh[wib][3];
+  const unsigned FULLM = 0xffffffffu;
+  const int numf = *nretry;
+  const int nwarps = gridDim.x * SW_WARPS;
+  const size_t ld = (size_t)ldc;
+  for (int w = blockIdx.x * SW_WARPS + wib; w < numf; w += nwarps) {
+    const int c1 = retry[w];
+    const int ci = c1 - begc0;
+    const int n = f.nbedrock[ci];
+    const double e_ice = prm.m_e_ice ? prm.m_e_ice[prm.col_member[c1 - prm.member_begc]] : prm.e_ice;
+    const int j = lane;
+    const bool on = j < n;
+    // ---- one-time loads of this lane's level (inactive lanes carry harmless values) ----
+    double dz1000 = 1.0, watsat = 1.0, bsw = 1.0, sucsat = 1.0, sink = 0.0, liq = 1.0, ih = 0.0, zden = 1.0;
+    if (on) {
+      const size_t o1 = (size_t)j * ld + ci;
+      const size_t os = (size_t)(j + 1 - SNOSOI_LO) * ld + ci;
+      dz1000 = cst::m_to_mm * f.dz[os];
+      watsat = f.watsat[o1];
+      bsw = f.bsw[o1];
+      sucsat = f.sucsat[o1];
+      sink = f.qflx_rootsoi[o1];
+      liq = f.h2osoi_liq[os];
+      const double icef_j = f.icefrac[o1], z_j = f.z[os];
+      double imped;
+      if (j < n - 1) {
+        const double icef_n = f.icefrac[o1 + ld], z_n = f.z[os + ld];
+        imped = pow(10.0, -e_ice * (0.5 * (icef_j + icef_n)));
+        zden = cst::m_to_mm * (z_n - z_j);
+      } else {
+        imped = pow(10.0, -e_ice * icef_j);
+        zden = 0.0;
+      }
+      ih = imped * f.hksat[o1];
+    }
+    const double watsat_n = __shfl_down_sync(FULLM, watsat, 1);
+    const double qflx_infl = f.qflx_infl[ci];
+    int nsubstep = 0;
+    double dtsub = prm.dtime, dtdone = 0.0, qcharge = 0.0;
+    double smp = 0.0, hk = 0.0, qout = 0.0, qin = 0.0;
+    bool failed = false;
+    for (;;) {
+      nsubstep = nsubstep + 1;
+      const double vwc = fmax(liq, 1.0e-6) / dz1000;
+      double s2 = vwc / watsat;
+      s2 = fmin(s2, 1.0);
+      s2 = fmax(0.01, s2);
+      const double sm = -sucsat * pow(s2, -bsw);
+      smp = sm;
+      const double dsmpdw = (-bsw * sm / s2) / watsat;
+      const double s2_n = __shfl_down_sync(FULLM, s2, 1);
+      const double smp_n = __shfl_down_sync(FULLM, sm, 1);
+      const double dsmpdw_n = __shfl_down_sync(FULLM, dsmpdw, 1);
+      double s1 = (j == n - 1) ? s2 : 0.5 * (s2 + s2_n);
+      s1 = fmin(s1, 1.0);
+      s1 = fmax(0.01, s1);
+      const double ex = 2.0 * bsw + 3.0;
+      const double hkj = ih * pow(s1, ex);
+      const double dhkds = ex * hkj / s1;
+      hk = hkj;
+      const double dt_dz = dtsub / dz1000;
+      double qo, dqodw1, dqodw2;
+      if (j < n - 1) {
+        const double dhkds1 = 0.5 * dhkds / watsat;
+        const double dhkds2 = 0.5 * dhkds / watsat_n;
+        const double num = (smp_n - sm);
+        const double den = zden;
+        qo = -hkj * num / den + hkj;
+        dqodw1 = (hkj * dsmpdw - dhkds1 * num) / den + dhkds1;
+        dqodw2 = (-hkj * dsmpdw_n - dhkds2 * num) / den + dhkds2;
+      } else {
+        if (prm.lower_bc == 1) { qo = hkj; dqodw1 = dhkds / watsat; }
+        else { qo = 0.0; dqodw1 = 0.0; }
+        dqodw2 = 0.0;
+      }
+      qout = qo;
+      double qin_j = __shfl_up_sync(FULLM, qo, 1);
+      double dqidw0 = __shfl_up_sync(FULLM, dqodw1, 1);
+      double dqidw1 = __shfl_up_sync(FULLM, dqodw2, 1);
+      if (j == 0) { qin_j = qflx_infl; dqidw0 = 0.0; dqidw1 = 0.0; }
+      qin = qin_j;
+      const double fluxNet = qin_j - qo - sink;
+      const double rmx = -fluxNet * dt_dz;
+      const double amx = (j == 0) ? 0.0 : dqidw0 * dt_dz;
+      const double bmx = -1.0 - (-dqidw1 + dqodw1) * dt_dz;
+      const double cmx = (j == n - 1) ? 0.0 : -dqodw2 * dt_dz;
+      __syncwarp();
+      if (on) {
+        if (j >= 1) dl[j - 1] = amx;          // dgtsv: dl(1:n-1) = amx(2:n)
+        dd[j] = bmx; du[j] = cmx; bb[j] = rmx;
+      }
+      __syncwarp();
+      int info = 0;
+      if (lane == 0) info = dgtsv_solve(n, dl, dd, du, bb);
+      info = __shfl_sync(FULLM, info, 0);
+      __syncwarp();
+      if (info != 0) {
+        if (lane == 0) report_failure(ds, c1, CTSM_ERR_DGTSV, info);
+        failed = true;
+        break;
+      }
+      const double dwat = on ? bb[j] : 0.0;
+      // error estimate :1307-1348
+      double e = -INFINITY;
+      if (on) {
+        const double fluxNet0 = dwat / dt_dz;
+        const double fluxNet1 = qin_j - qo - sink;
+        e = fabs(fluxNet1 - fluxNet0) * dtsub * 0.5;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) e = fmax(e, __shfl_xor_sync(FULLM, e, o));
+      const double errorMax = e;
+      if (errorMax > prm.xTolerUpper && dtsub > prm.dtmin) {   // :1349-1353
+        dtsub = fmax(dtsub / 2.0, prm.dtmin);
+        continue;
+      }
+      if (on) liq = liq + dwat * dz1000;                         // :1360-1362
+      double qcTemp = 0.0;                                       // :1365-1383
+      {
+        const double hk_b = __shfl_sync(FULLM, hkj, n - 1);
+        const double dh_b = __shfl_sync(FULLM, dhkds, n - 1);
+        const double dw_b = __shfl_sync(FULLM, dwat, n - 1);
+        if (prm.lower_bc == 1) qcTemp = hk_b + dh_b * dw_b;
+      }
+      qcharge = qcharge + qcTemp * (dtsub / prm.dtime);
+      dtdone = dtdone + dtsub;
+      if (fabs(prm.dtime - dtdone) < prm.verySmall) break;
+      if (errorMax < prm.xTolerLower) dtsub = dtsub * 2.0;
+      dtsub = fmin(dtsub, prm.dtime - dtdone);
+    }
+    if (failed) continue;
+    // :1406-1410 over-saturation moves upward (sequential recurrence: lane 0)
+    __syncwarp();
+    if (on) { dd[j] = liq; du[j] = (j >= 1) ? f.eff_porosity[(size_t)j * ld + ci] * dz1000 : 0.0; }
+    __syncwarp();
+    if (lane == 0) {
+      for (int q = n - 1; q >= 1; --q) {
+        const double cap = du[q];
+        const double over = fmax(dd[q] - cap, 0.0);
+        dd[q] = fmin(cap, dd[q]);
+        dd[q - 1] = dd[q - 1] + over;
+      }
+    }
+    __syncwarp();
+    if (on) {
+      const size_t o1 = (size_t)j * ld + ci;
+      f.h2osoi_liq[(size_t)(j + 1 - SNOSOI_LO) * ld + ci] = dd[j];
+      f.smp_l[o1] = smp;
+      f.hk_l[o1] = hk;
+      f.qin[o1] = qin;
+      f.qout[o1] = qout;
+    }
+    if (lane == 0) {
+      f.qcharge[ci] = qcharge;
+      f.num_substeps[ci] = (double)nsubstep;
+    }
+    __syncwarp();
+  }
+}
+
 extern "C" int ctsm_b200_soilwater(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_hydrologyc,
                                    const int32_t* filter_hydrologyc, const ctsm_soilwater_fields_t* hf, int mem,
                                    ctsm_status_t* st) {
@@ -240,8 +418,16 @@ extern "C" int ctsm_b200_soilwater(ctsm_b200_ctx* ctx, const ctsm_bounds_t* boun
     soilwater_kernel<1><<<grid_for(num_hydrologyc, 128), 128, 0, ctx->stream>>>(d, p, hf->alloc.begc, ldc, num_hydrologyc,
                                                                                 dfilter, retry, nretry, ctx->d_status);
     // the queue length is only known on the device: pass 2 is sized for the whole filter and exits early
-    soilwater_kernel<2><<<grid_for(num_hydrologyc, 128), 128, 0, ctx->stream>>>(d, p, hf->alloc.begc, ldc, num_hydrologyc,
-                                                                                dfilter, retry, nretry, ctx->d_status);
+    if (ctx->tune.sw_warp) {
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+      const int need = grid_for(num_hydrologyc, SW_WARPS);
+      soilwater_retry_warp_kernel<<<need < sms * 8 ? need : sms * 8, 32 * SW_WARPS, 0, ctx->stream>>>(d, p, hf->alloc.begc, ldc, retry,
+                                                                                                   nretry, ctx->d_status);
+    } else {
+      soilwater_kernel<2><<<grid_for(num_hydrologyc, 128), 128, 0, ctx->stream>>>(d, p, hf->alloc.begc, ldc, num_hydrologyc,
+                                                                                  dfilter, retry, nretry, ctx->d_status);
+    }
     ctx->launches += 2;
   }
   if (mem != CTSM_MEM_DEVICE) {

@@ -335,6 +335,10 @@ int  ctsm_b200_set_tuning(ctsm_b200_ctx* ctx, int tail_max, int nt_budget, int t
  * through registers and a coalesced scratch (soiltemp_stream_kernel), 0 keeps the per-thread level arrays (soiltemp_kernel);
  * a negative value leaves the setting unchanged. */
 int  ctsm_b200_set_soil_tuning(ctsm_b200_ctx* ctx, int soil_stream);
+/* SoilWater's second pass (the columns whose full time step was rejected): sw_warp 1 (default; CTSM_B200_SW_WARP) runs one warp
+ * per column with the soil levels across the lanes (soilwater_retry_warp_kernel), 0 one thread per column (soilwater_kernel<2>).
+ * Bit-identical results; a negative value leaves the setting unchanged. */
+int  ctsm_b200_set_soilwater_tuning(ctsm_b200_ctx* ctx, int sw_warp);
 /* Diagnostic of the last ctsm_b200_canopyfluxes call (synchronises the stream): for every ITERATION round r < cap,
  * list_len[r] = patches the round's list kernels served, tail_end[r] = patches handed to the tail kernel up to and
  * including round r.  Returns the number of rounds written. */

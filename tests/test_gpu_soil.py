@@ -155,6 +155,25 @@ def _run_soilwater(L_or, L, ctx, prm, sg, S, mem):
     return ref, got
 
 
+def test_soilwater_retry_kernels_agree_bit_for_bit(gpu_ctx, oracle_lib):
+    """SoilWater's second pass as one warp per column (levels across the lanes, default) and as one thread per column are two
+    schedules of the same arithmetic: every output agrees bit for bit (ctsm_b200_set_soilwater_tuning)."""
+    L, ctx, prm = gpu_ctx
+    sg, S = synthetic.make_case(20000, seed=79)
+    try:
+        assert L.ctsm_b200_set_soilwater_tuning(ctx, 0) == 0
+        _, a = _run_soilwater(oracle_lib, L, ctx, prm, sg, S, abi.MEM_DEVICE)
+        assert L.ctsm_b200_set_soilwater_tuning(ctx, 1) == 0
+        ref, b = _run_soilwater(oracle_lib, L, ctx, prm, sg, S, abi.MEM_DEVICE)
+    finally:
+        L.ctsm_b200_set_soilwater_tuning(ctx, 1)
+    for fs in abi.FIELDS["soilwater"]:
+        assert np.array_equal(a[fs.name], b[fs.name], equal_nan=True), fs.name
+    fh = sg.filters["hydrologyc"] - 1
+    assert (b["num_substeps"][fh] > 1).sum() > 500          # the second pass really ran
+    assert np.array_equal(b["num_substeps"][fh], ref["num_substeps"][fh])
+
+
 @pytest.mark.parametrize("size,mem", [("tiny", abi.MEM_HOST), (3000, abi.MEM_DEVICE)])
 def test_soilwater_matches_oracle(gpu_ctx, oracle_lib, size, mem):
     L, ctx, prm = gpu_ctx
