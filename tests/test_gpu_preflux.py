@@ -166,3 +166,44 @@ def test_step_from_preflux_to_balancecheck(oracle_lib):
     worst = compare_step_fields(sg, S, got, ref, loose_p, driver.ROUTINES[1:])
     print("ten-routine step: canopy worst", sorted(worst_c.items(), key=lambda kv: -kv[1])[:3], "ties", ntie,
           "rest worst", sorted(worst.items(), key=lambda kv: -kv[1])[:4])
+
+
+def test_preflux_routines_with_empty_filters_and_clump_bounds(oracle_lib):
+    """Empty filters are legal (a clump without non-lake columns) and write nothing; a call with one clump's bounds on
+    proc-sized arrays touches that clump only and gives the undecomposed result there."""
+    L = abi.lib()
+    sg, S = case(1200, 531, wet_every=3)
+    prm = abi.default_params()
+    ref = copy_state(S)
+    assert run_preflux(oracle_lib, prm, sg, ref) == 0
+    assert run_humidity(oracle_lib, sg, ref) == 0
+    assert run_bare(oracle_lib, prm, sg, ref) == 0
+    ctx = C.c_void_p()
+    assert L.ctsm_b200_init(C.byref(prm), C.byref(ctx)) == 0
+    try:
+        got = copy_state(S)
+        st = abi.Status()
+        b = C.byref(sg.bounds)
+        z = np.zeros(1, dtype=np.int32)
+        fpre = abi.make_struct("preflux", got, sg.bounds)
+        fhum = abi.make_struct("surfacehumidity", got, sg.bounds)
+        fbar = abi.make_struct("baregroundfluxes", got, sg.bounds)
+        assert L.ctsm_b200_biogeophys_pre_flux_calcs(ctx, b, 0, abi.i32p(z), 0, abi.i32p(z), 0, None, 0, C.byref(fpre), abi.MEM_HOST, C.byref(st)) == 0
+        assert L.ctsm_b200_calculate_surface_humidity(ctx, b, 0, abi.i32p(z), C.byref(fhum), abi.MEM_HOST, C.byref(st)) == 0
+        assert L.ctsm_b200_bare_ground_fluxes(ctx, b, 0, abi.i32p(z), C.byref(fbar), abi.MEM_HOST, C.byref(st)) == 0
+        for k in S:
+            assert np.array_equal(got[k], S[k], equal_nan=True), k
+        # clump by clump (bounds != alloc), host arrays
+        from ctsm_b200 import driver
+        for kb, fl in driver.make_slabs(sg, 5):
+            cb = C.byref(kb)
+            fc, fp, fb = fl["nolakec"], fl["nolakep"], fl["noexposedvegp"]
+            assert L.ctsm_b200_biogeophys_pre_flux_calcs(ctx, cb, len(fc), abi.i32p(fc), len(fp), abi.i32p(fp), 0, None, 0,
+                                                         C.byref(fpre), abi.MEM_HOST, C.byref(st)) == 0
+            assert L.ctsm_b200_calculate_surface_humidity(ctx, cb, len(fc), abi.i32p(fc), C.byref(fhum), abi.MEM_HOST, C.byref(st)) == 0
+            assert L.ctsm_b200_bare_ground_fluxes(ctx, cb, len(fb), abi.i32p(fb), C.byref(fbar), abi.MEM_HOST, C.byref(st)) == 0
+        worst = {}
+        for g in ("preflux", "surfacehumidity", "baregroundfluxes"):
+            compare(g, got, ref, worst)
+    finally:
+        L.ctsm_b200_finalize(ctx)

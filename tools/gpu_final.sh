@@ -1,29 +1,25 @@
 #!/bin/bash
-# tools/gpu_final.sh TAG: the round-end measurement pass on one B200: full GPU test suite, smoke, targeted ncu re-capture of the
-# SoilTemperature kernels (merged into profiles/<TAG>_traffic.json), then the bench lines.  Everything lands in gpurun_out/.
+# tools/gpu_final.sh TAG: the round-end measurement pass on one B200.
+#   1. ncu launch list of two f02 steps (time, DRAM bytes, FP64 pipe counters per launch) -> <TAG>_launches_f02.csv.gz,
+#      summarised by tools/launch_summary.py into <TAG>_launch_summary_f02.txt and <TAG>_traffic.json (also placed under
+#      profiles/ on the box, so that the bench lines below report roofline.traffic / roofline.fp64 from THIS tree);
+#   2. full GPU test suite and smoke;
+#   3. bench lines: default (f02), ten-routine step, f09, config-5 slice, CPU arm.
+# Everything lands in gpurun_out/; copy what is to be judged to profiles/.
 tag=${1:-r02}; out=gpurun_out; mkdir -p $out
+timeout 2400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_executed_pipe_fp64.sum,sm__thread_inst_executed_pipe_fp64_pred_on.sum,sm__pipe_fp64_cycles_active.sum \
+    --clock-control none -c 20000 --csv --log-file $out/${tag}_launches_f02.csv python bench.py --steps 1 --warmup 1 --under-profiler --no-e2e --no-cpu > $out/${tag}_b.log 2>&1
+python tools/launch_summary.py $out/${tag}_launches_f02.csv $out/${tag}_traffic.json f02 2 > $out/${tag}_launch_summary_f02.txt 2>&1
+cp $out/${tag}_traffic.json profiles/${tag}_traffic.json
+gzip -f $out/${tag}_launches_f02.csv
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -6 > $out/${tag}_pytest.log
 timeout 300 python __graft_entry__.py smoke > $out/${tag}_smoke.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_executed_pipe_fp64.sum,sm__thread_inst_executed_pipe_fp64_pred_on.sum,sm__pipe_fp64_cycles_active.sum \
-    --clock-control none -k regex:"soiltemp|patchmask" -c 8 --csv --log-file $out/${tag}_launches_soiltemp.csv \
-    python bench.py --routines soiltemperature --steps 1 --warmup 1 --under-profiler --no-e2e --no-cpu > $out/${tag}_b2.log 2>&1
-python tools/launch_summary.py $out/${tag}_launches_soiltemp.csv $out/${tag}_traffic_soiltemp.json f02 2 > $out/${tag}_launch_summary_soiltemp.txt 2>&1
-python - <<PY
-import json
-a = json.load(open("profiles/${tag}_traffic.json")); b = json.load(open("$out/${tag}_traffic_soiltemp.json"))
-for k, v in b.items():
-    if isinstance(v, dict) and "SoilTemperature" in v:
-        a[k]["SoilTemperature"] = v["SoilTemperature"]
-a["source"] += "; SoilTemperature re-captured after the level-streaming kernel (${tag}_launches_soiltemp.csv)"
-json.dump(a, open("profiles/${tag}_traffic.json", "w"), indent=1)
-json.dump(a, open("$out/${tag}_traffic.json", "w"), indent=1)
-PY
 timeout 600 python bench.py > $out/${tag}_bench_f02.json 2> $out/${tag}_bench_f02.err
 timeout 400 python bench.py --routines pre,canopyfluxes,soiltemperature,soilfluxes,patch2col,plantsink,soilwater,balancecheck --no-cpu > $out/${tag}_bench_f02_pre.json 2>> $out/${tag}_bench_f02.err
 timeout 300 python bench.py --size f09 --steps 5 --no-cpu > $out/${tag}_bench_f09.json 2>> $out/${tag}_bench_f02.err
 timeout 300 python bench.py --size f19 --members 32 --steps 5 --no-cpu > $out/${tag}_bench_f19x32.json 2>> $out/${tag}_bench_f02.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_reference.json 2>> $out/${tag}_bench_f02.err
-cat $out/${tag}_pytest.log $out/${tag}_smoke.log; cat $out/${tag}_launch_summary_soiltemp.txt | head -8; tail -3 $out/${tag}_bench_f02.err
+cat $out/${tag}_pytest.log $out/${tag}_smoke.log; head -34 $out/${tag}_launch_summary_f02.txt; tail -12 $out/${tag}_launch_summary_f02.txt; tail -3 $out/${tag}_bench_f02.err
 for f in f02 f02_pre f09 f19x32 reference; do python - <<PY
 import json
 try:
