@@ -101,9 +101,8 @@ class Params(C.Structure):
                     "tpu25ratio", "kp25ratio", "vcmaxse_sf", "jmaxse_sf", "tpuse_sf", "jmax25top_sf")] + [
                 ("balance_skip_steps", C.c_int32),
                 ("npft_table", C.c_int32), ("calc_human_stress_indices", C.c_int32), ("use_z0m_snowmelt", C.c_int32),
-                ("reserved_i", C.c_int32 * 4)] + [
-                (n, C.c_double) for n in ("zlnd", "zsno", "zglc", "d_max", "frac_sat_soil_dsl_init")] + [
-                ("reserved_d", C.c_double * 3)]
+                ("h2osfcflag", C.c_int32), ("crop_fsat_equals_zero", C.c_int32), ("reserved_i", C.c_int32 * 2)] + [
+                (n, C.c_double) for n in ("zlnd", "zsno", "zglc", "d_max", "frac_sat_soil_dsl_init", "fff", "pc", "mu")]
 
 
 def default_params(dtime: float = 1800.0, device: int = 0) -> Params:
@@ -312,6 +311,8 @@ def lib():
                                                        C.POINTER(STRUCTS["surfacehumidity"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_bare_ground_fluxes.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p,
                                                C.POINTER(STRUCTS["baregroundfluxes"]), C.c_int, C.POINTER(Status)]
+    L.ctsm_b200_hydrology_infiltration.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p, C.c_int, i32p,
+                                                   C.POINTER(STRUCTS["infiltration"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_vert_tran_sink_default.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p,
                                                      C.POINTER(STRUCTS["plantsinkdefault"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_soilfluxes.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p,
@@ -333,7 +334,7 @@ def lib():
     L.ctsm_b200_set_soil_tuning.argtypes = [vp, C.c_int]
     L.ctsm_b200_set_soilwater_tuning.argtypes = [vp, C.c_int]
     for fn in ("vert_tran_sink_hydstress", "vert_tran_sink_default", "biogeophys_pre_flux_calcs", "calculate_surface_humidity",
-               "bare_ground_fluxes", "balancecheck_init", "balancecheck", "soilfluxes", "patch2col"):
+               "bare_ground_fluxes", "hydrology_infiltration", "balancecheck_init", "balancecheck", "soilfluxes", "patch2col"):
         getattr(L, "ctsm_b200_" + fn).restype = C.c_int
     for fn in ("init", "finalize", "sync", "host_register", "host_unregister", "tridiagonal", "banddiagonal",
                "dgtsv_batch", "soilwater", "soiltemperature", "canopyfluxes", "set_exposedvegp_filter"):

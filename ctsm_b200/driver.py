@@ -22,9 +22,13 @@ ROUTINES = ("canopyfluxes", "soiltemperature", "soilfluxes", "patch2col", "plant
 # the routines clm_drv runs just before CanopyFluxes (clm_driver.F90:680, :702, :711); PRE_ROUTINES + ROUTINES
 # is the step from BiogeophysPreFluxCalcs to BalanceCheck
 PRE_ROUTINES = ("preflux", "surfacehumidity", "baregroundfluxes")
+# HydrologyNoDrainage's routines in front of the root-water sink (HydrologyNoDrainageMod.F90:297-337): with
+# them SoilWater's icefrac / eff_porosity / qflx_infl are produced on the device instead of being inputs
+HYDRO_ROUTINES = ("infiltration",)
+ROUTINES_HYDRO = ("canopyfluxes", "soiltemperature", "soilfluxes", "patch2col", "infiltration", "plantsink", "soilwater", "balancecheck")
 FILTER_OF = {"preflux": ("nolakec", "nolakep"), "surfacehumidity": ("nolakec",), "baregroundfluxes": ("noexposedvegp",),
              "canopyfluxes": ("exposedvegp",), "soiltemperature": ("nolakep", "nolakec"), "soilfluxes": ("nolakep", "nolakec"),
-             "patch2col": ("allc", "nolakec"), "plantsink": ("hydrologyc",), "soilwater": ("hydrologyc",), "balancecheck": ("allc",)}
+             "patch2col": ("allc", "nolakec"), "infiltration": ("nolakec", "hydrologyc"), "plantsink": ("hydrologyc",), "soilwater": ("hydrologyc",), "balancecheck": ("allc",)}
 
 
 class CtsmError(RuntimeError):
@@ -293,8 +297,18 @@ class HotPath:
         if rc != 0:
             raise CtsmError(st, rc)
 
+    def HydrologyInfiltration(self):
+        """SetSoilWaterFractions ... TotalSurfaceRunoff, the call sequence HydrologyNoDrainageMod.F90:297-337; no urban columns"""
+        st = abi.Status()
+        rc = self.ctx.L.ctsm_b200_hydrology_infiltration(
+            self.ctx.h, C.byref(self.bounds), self.nfilter["nolakec"], abi.i32p(self.filters["nolakec"]),
+            self.nfilter["hydrologyc"], abi.i32p(self.filters["hydrologyc"]), 0, None,
+            C.byref(self.structs["infiltration"]), self.mem, C.byref(st))
+        if rc != 0:
+            raise CtsmError(st, rc)
+
     def call(self, g):
-        {"preflux": self.BiogeophysPreFluxCalcs, "surfacehumidity": self.CalculateSurfaceHumidity, "baregroundfluxes": self.BareGroundFluxes,
+        {"infiltration": self.HydrologyInfiltration, "preflux": self.BiogeophysPreFluxCalcs, "surfacehumidity": self.CalculateSurfaceHumidity, "baregroundfluxes": self.BareGroundFluxes,
          "canopyfluxes": self.CanopyFluxes, "soiltemperature": self.SoilTemperature, "soilwater": self.SoilWater,
          "plantsink": self.VertTranSink, "balancecheck": self.BalanceCheck, "soilfluxes": self.SoilFluxes, "patch2col": self.Patch2Col}[g]()
 

@@ -412,6 +412,43 @@ def watergrid_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Genera
         S[k] = np.ascontiguousarray(S[k])
 
 
+def hydrology_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator) -> None:
+    """Inputs of the surface-water / infiltration chain of HydrologyNoDrainage (HydrologyNoDrainageMod.F90:297-337; SURVEY.md 8f
+    rank 3) that the rest of the step does not carry: flood water from the river model, water-table depths, surface-water
+    threshold and fractions, the rain + snow-melt flux reaching the soil.  Every branch of the chain is populated: perched
+    water table above / below the frost table, h2osfc above / below its threshold, h2osfc_partial driven negative (evaporation
+    larger than the store), infiltration excess, columns with and without snow layers.  Outputs start from spval."""
+    nc, ng = sg.ncol, sg.ngrc
+    g = lambda lo, hi, *shape: rng.uniform(lo, hi, shape)
+    S["col_gridcell"] = sg.col_gridcell.astype(np.int32)
+    S["forc_flood"] = g(0.0, 2.0e-4, ng) * (rng.random(ng) < 0.2)
+    S["topo_slope"] = g(0.05, 12.0, nc)                                  # degrees
+    S["wtfact"] = g(0.1, 0.7, nc)
+    S["zwt"] = g(0.3, 8.0, nc)
+    S["zwt_perched"] = g(0.1, 6.0, nc)
+    S["frost_table"] = g(0.1, 9.0, nc)
+    S["h2osfc_thresh"] = g(0.5, 12.0, nc)
+    S["h2osfc"] = np.where(rng.random(nc) < 0.5, g(0.0, 30.0, nc), 0.0)   # mm; half of the columns dry
+    S["frac_h2osfc"] = np.where(S["h2osfc"] > 0.0, g(0.01, 0.9, nc), 0.0)
+    S["frac_h2osfc_nosnow"] = np.minimum(1.0, S["frac_h2osfc"] * g(1.0, 1.3, nc))
+    wet = rng.random(nc) < 0.6
+    S["qflx_rain_plus_snomelt"] = np.where(wet, 10.0 ** g(-6.0, -2.3, nc), 0.0)     # up to ~18 mm/h: above qinmax on some columns
+    S["qflx_snow_h2osfc"] = np.where(rng.random(nc) < 0.2, g(0.0, 2.0e-5, nc), 0.0)
+    for nm in ("qflx_ev_soil_col", "qflx_ev_h2osfc_col", "qflx_liqevap_from_top_layer"):   # SoilFluxes outputs (spval before a step)
+        S[nm] = np.where(np.abs(S[nm]) < 1e30, S[nm], g(-1.0e-5, 6.0e-5, nc))
+    # evaporation that slightly over-empties the surface store (h2osfc_partial < 0, QflxH2osfcDrain's first branch): the deficit
+    # stays below a few per cent of the store, a strongly negative qflx_infl would make SoilWater's adaptive step ill-conditioned
+    big = (rng.random(nc) < 0.1) & (S["frac_h2osfc"] > 0.0)
+    S["qflx_ev_h2osfc_col"] = np.where(big, g(1.0, 1.05, nc) * S["h2osfc"] / (1800.0 * np.maximum(S["frac_h2osfc"], 1e-3))
+                                       + S["qflx_rain_plus_snomelt"] + 3.0e-4, S["qflx_ev_h2osfc_col"])
+    for fs in abi_fields("infiltration"):
+        if fs.name not in S and fs.ctype == "double":
+            n = {"COL": nc, "PATCH": sg.npatch, "GRC": ng}[fs.sub]
+            S[fs.name] = np.full(n if fs.lev == "L1" else (fs.nlev, n), 1.0e36)
+    for k, v in list(S.items()):
+        S[k] = np.ascontiguousarray(v)
+
+
 def make_ensemble(sg: Subgrid, S: Dict[str, np.ndarray], nmember: int, rng: np.random.Generator, spread: float = 0.2):
     """Perturbed-parameter ensemble through the PFT tables (BASELINE config 5): the grid is split into `nmember` equal
     runs of gridcells, member m's patches get itype = m*(mxpft+1) + pft, and every pft_* table is extended to

@@ -152,9 +152,13 @@ typedef struct ctsm_params_t {
   /* BiogeophysPreFluxCalcs: FrictionVelocityMod.F90 (zlnd, zsno, zglc: parameter-file scalars), clm_varctl use_z0m_snowmelt,
    * SurfaceResistanceMod.F90:35-36 (d_max, frac_sat_soil_dsl_init: parameter-file scalars) */
   int32_t use_z0m_snowmelt;             /* 1 with Meier2022 (namelist_defaults_ctsm.xml:624) */
-  int32_t reserved_i[4];
+  /* the infiltration chain: soilhydrology_inparm h2osfcflag (SoilHydrologyType.F90:352), crop_fsat_equals_zero
+   * (SaturatedExcessRunoffMod.F90), parameter-file scalars fff (SaturatedExcessRunoffMod.F90:56), pc, mu (SurfaceWaterMod.F90:42-43) */
+  int32_t h2osfcflag;                   /* 1 */
+  int32_t crop_fsat_equals_zero;        /* 0 */
+  int32_t reserved_i[2];
   double  zlnd, zsno, zglc, d_max, frac_sat_soil_dsl_init;
-  double  reserved_d[3];
+  double  fff, pc, mu;
 } ctsm_params_t;
 
 typedef struct ctsm_b200_ctx ctsm_b200_ctx;
@@ -216,6 +220,13 @@ typedef struct ctsm_baregroundfluxes_fields_t {
 #include "ctsm_b200_fields.def"
 #undef CTSM_FIELDS_BAREGROUNDFLUXES
 } ctsm_baregroundfluxes_fields_t;
+
+typedef struct ctsm_infiltration_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_INFILTRATION
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_INFILTRATION
+} ctsm_infiltration_fields_t;
 
 typedef struct ctsm_soilfluxes_fields_t {
   ctsm_bounds_t alloc;
@@ -464,6 +475,16 @@ int ctsm_b200_calculate_surface_humidity(ctsm_b200_ctx* ctx, const ctsm_bounds_t
 int ctsm_b200_bare_ground_fluxes(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
                                  int num_noexposedvegp, const int32_t* filter_noexposedvegp,
                                  const ctsm_baregroundfluxes_fields_t* f, int mem, ctsm_status_t* st);
+
+/* The call sequence HydrologyNoDrainageMod.F90:297-337 as one entry: SetSoilWaterFractions, SetFloodc (over filter_nolakec),
+ * SaturatedExcessRunoff, SetQflxInputs, InfiltrationExcessRunoff, RouteInfiltrationExcess, UpdateH2osfc, Infiltration,
+ * TotalSurfaceRunoff (over filter_hydrologyc).  fsat_method = TOPModel, qinmax_method = hksat (the clm5 / clm6 defaults);
+ * num_urbanc must be 0 and urban columns in the filters are refused (CTSM_ERR_URBAN). */
+int ctsm_b200_hydrology_infiltration(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
+                                     int num_nolakec, const int32_t* filter_nolakec,
+                                     int num_hydrologyc, const int32_t* filter_hydrologyc,
+                                     int num_urbanc, const int32_t* filter_urbanc,
+                                     const ctsm_infiltration_fields_t* f, int mem, ctsm_status_t* st);
 
 /* Compute_EffecRootFrac_And_VertTranSink_Default(bounds, num_filterc, filterc, ...): SoilWaterPlantSinkMod.F90:332-424,
  * what Compute_EffecRootFrac_And_VertTranSink (:18-142) calls for every column class when use_hydrstress = .false. */

@@ -53,6 +53,9 @@ static inline void ctsm_default_params_fill(ctsm_params_t* p) {
   p->use_z0m_snowmelt = 1;                 // namelist_defaults_ctsm.xml:624 (z0param_method = Meier2022)
   p->zlnd = 0.000775; p->zsno = 0.00085; p->zglc = 0.00230000005;
   p->d_max = 15.0; p->frac_sat_soil_dsl_init = 0.8;
+  p->h2osfcflag = 1;                       // SoilHydrologyType.F90:352-360
+  p->crop_fsat_equals_zero = 0;            // namelist_defaults_ctsm.xml (saturated_excess_runoff_inparm)
+  p->fff = 0.5; p->pc = 0.4; p->mu = 0.13889;   // parameter-file scalars (clm5 technical note values; synthetic choice)
   p->balance_skip_steps = -1;
   p->npft_table = CTSM_MXPFT + 1;
 }

@@ -70,6 +70,10 @@ int oracle_calculate_surface_humidity(const ctsm_bounds_t* bounds, int num_nolak
                                       const ctsm_surfacehumidity_fields_t* f, ctsm_status_t* st);
 int oracle_bare_ground_fluxes(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_noexposedvegp,
                               const int32_t* filter_noexposedvegp, const ctsm_baregroundfluxes_fields_t* f, ctsm_status_t* st);
+/* oracle_hydrology.c: the infiltration chain of HydrologyNoDrainage (first part) */
+int oracle_hydrology_infiltration(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_nolakec,
+                                  const int32_t* filter_nolakec, int num_hydrologyc, const int32_t* filter_hydrologyc,
+                                  int num_urbanc, const ctsm_infiltration_fields_t* f, ctsm_status_t* st);
 int oracle_vert_tran_sink_default(const ctsm_bounds_t* bounds, int num_filterc, const int32_t* filterc,
                                   const ctsm_plantsinkdefault_fields_t* f);
 /* the field struct oracle_fullstep_clumps hands to the default sink when prm->use_hydrstress == 0 (its own plant-sink

@@ -154,6 +154,8 @@ def _bind(L):
                                                    C.POINTER(abi.STRUCTS["preflux"]), C.POINTER(abi.Status)]
     L.oracle_calculate_surface_humidity.argtypes = [B, C.c_int, i32p, C.POINTER(abi.STRUCTS["surfacehumidity"]), C.POINTER(abi.Status)]
     L.oracle_bare_ground_fluxes.argtypes = [P, B, C.c_int, i32p, C.POINTER(abi.STRUCTS["baregroundfluxes"]), C.POINTER(abi.Status)]
+    L.oracle_hydrology_infiltration.argtypes = [P, B, C.c_int, i32p, C.c_int, i32p, C.c_int, C.POINTER(abi.STRUCTS["infiltration"]),
+                                                C.POINTER(abi.Status)]
     L.oracle_vert_tran_sink_default.argtypes = [B, C.c_int, i32p, C.POINTER(abi.STRUCTS["plantsinkdefault"])]
     L.oracle_set_plantsink_default.argtypes = [C.POINTER(abi.STRUCTS["plantsinkdefault"])]
     L.oracle_set_plantsink_default.restype = None

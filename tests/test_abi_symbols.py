@@ -36,7 +36,7 @@ def test_version_and_defaults_match_python_twin():
     assert (p.dtmin, p.xTolerUpper, p.snow_thermal_cond_method) == (60.0, 0.1, 2)
     assert (p.itmax_canopy_fluxes, p.z0param_method, p.stomatalcond_mtd) == (40, 2, 2)
     assert (p.csoilc, p.zetamaxstable, p.lmrhd, p.jmax25top_sf, p.balance_skip_steps) == (0.004, 2.0, 150650.0, 1.0, -1)
-    assert all(v == 0 for v in p.reserved_i) and all(v == 0.0 for v in p.reserved_d)
+    assert all(v == 0 for v in p.reserved_i) and (p.fff, p.pc, p.mu, p.h2osfcflag) == (0.5, 0.4, 0.13889, 1)
 
 
 def test_struct_layout_matches_def_table():
@@ -66,7 +66,7 @@ def test_ctypes_mirrors_have_the_c_layout(tmp_path):
     probes = {"ctsm_bounds_t": (abi.Bounds, ["begg", "endp", "clump_index"]),
               "ctsm_status_t": (abi.Status, ["code", "value", "n_warnings", "msg"]),
               "ctsm_params_t": (abi.Params, ["abi_version", "dtime", "e_ice", "itmax_canopy_fluxes", "lai_dl", "jmax25top_sf",
-                                             "balance_skip_steps", "npft_table", "calc_human_stress_indices", "reserved_i", "reserved_d"]),
+                                             "balance_skip_steps", "npft_table", "calc_human_stress_indices", "reserved_i", "fff", "mu"]),
               "ctsm_balance_report_t": (abi.BalanceReport, ["max_abs", "index", "warn", "abort_kind", "skip_steps"]),
               "ctsm_filter_inputs_t": (abi.FilterInputs, ["alloc", "col_active", "melt_replaced_by_ice_grc", "include_inactive",
                                                           "npcropmax"]),
