@@ -37,6 +37,7 @@ LEV = {
     "LAK": (1, 10),
     "PHS2": (1, 2 * NLEVCAN),
     "NUMRAD": (1, 2),
+    "AER": (1, 14),
     "PFT": (0, MXPFT + 1),
     "PFTVEGWCS": (0, (MXPFT + 1) * NVEGWCS),
 }
@@ -102,7 +103,15 @@ class Params(C.Structure):
                 ("balance_skip_steps", C.c_int32),
                 ("npft_table", C.c_int32), ("calc_human_stress_indices", C.c_int32), ("use_z0m_snowmelt", C.c_int32),
                 ("h2osfcflag", C.c_int32), ("crop_fsat_equals_zero", C.c_int32), ("reserved_i", C.c_int32 * 2)] + [
-                (n, C.c_double) for n in ("zlnd", "zsno", "zglc", "d_max", "frac_sat_soil_dsl_init", "fff", "pc", "mu")]
+                (n, C.c_double) for n in ("zlnd", "zsno", "zglc", "d_max", "frac_sat_soil_dsl_init", "fff", "pc", "mu")] + [
+                (n, C.c_int32) for n in ("snow_overburden_compaction_method", "wind_dependent_snow_density", "use_subgrid_fluxes",
+                                         "snicar_use_aerosol")] + [
+                (n, C.c_double) for n in (
+                    "snow_dzmin_1", "snow_dzmin_2", "snow_dzmax_l_1", "snow_dzmax_l_2", "snow_dzmax_u_1", "snow_dzmax_u_2",
+                    "overburden_compress_Tfactor", "int_snow_max", "wimp", "ssi", "drift_gs", "eta0_anderson", "eta0_vionnet",
+                    "rho_max", "tau_ref", "ceta", "snw_rds_min", "upplim_destruct_metamorph", "scvng_fct_mlt_sf",
+                    "scvng_fct_mlt_bcphi", "scvng_fct_mlt_bcpho", "scvng_fct_mlt_dst1", "scvng_fct_mlt_dst2", "scvng_fct_mlt_dst3",
+                    "scvng_fct_mlt_dst4")]
 
 
 def default_params(dtime: float = 1800.0, device: int = 0) -> Params:
@@ -313,6 +322,10 @@ def lib():
                                                C.POINTER(STRUCTS["baregroundfluxes"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_hydrology_infiltration.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p, C.c_int, i32p,
                                                    C.POINTER(STRUCTS["infiltration"]), C.c_int, C.POINTER(Status)]
+    L.ctsm_b200_build_snow_filter.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, i32p, C.c_int, C.c_int, i32p, i32p, i32p, i32p, C.c_int]
+    L.ctsm_b200_snow_water.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p, C.POINTER(STRUCTS["snowwater"]), C.c_int,
+                                       C.POINTER(Status)]
+    L.ctsm_b200_snow_layers.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.POINTER(STRUCTS["snowlayers"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_vert_tran_sink_default.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p,
                                                      C.POINTER(STRUCTS["plantsinkdefault"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_soilfluxes.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p,
@@ -334,7 +347,7 @@ def lib():
     L.ctsm_b200_set_soil_tuning.argtypes = [vp, C.c_int]
     L.ctsm_b200_set_soilwater_tuning.argtypes = [vp, C.c_int]
     for fn in ("vert_tran_sink_hydstress", "vert_tran_sink_default", "biogeophys_pre_flux_calcs", "calculate_surface_humidity",
-               "bare_ground_fluxes", "hydrology_infiltration", "balancecheck_init", "balancecheck", "soilfluxes", "patch2col"):
+               "bare_ground_fluxes", "hydrology_infiltration", "build_snow_filter", "snow_water", "snow_layers", "balancecheck_init", "balancecheck", "soilfluxes", "patch2col"):
         getattr(L, "ctsm_b200_" + fn).restype = C.c_int
     for fn in ("init", "finalize", "sync", "host_register", "host_unregister", "tridiagonal", "banddiagonal",
                "dgtsv_batch", "soilwater", "soiltemperature", "canopyfluxes", "set_exposedvegp_filter"):

@@ -209,6 +209,7 @@ static const char* message_for(int code) {
     case CTSM_ERR_GS_NEG: return "PhotosynthesisHydraulicStress: negative stomatal conductance";
     case CTSM_ERR_BRENT: return "brent_PHS: root must be bracketed";
     case CTSM_ERR_QUADRATIC: return "quadratic solution error: b^2 - 4ac is negative";
+    case CTSM_ERR_SNOW_NEGATIVE: return "In UpdateState_TopLayerFluxes, h2osoi_ice has gone significantly negative";
     case CTSM_ERR_RH: return "ERROR RH is negative / greater than a hundred (Wet_BulbS)";
     case CTSM_ERR_URBAN: return "urban column in filter is outside the ctsm_b200 hot path";
     case CTSM_ERR_BALANCE: return "BalanceCheck: balance error exceeds threshold / c2g: sumwt is greater than 1.0";
@@ -230,6 +231,8 @@ void decode_status(const DevStatus& ds, ctsm_status_t* st) {
   else st->subgrid_level = (st->code == CTSM_ERR_FORC_HGT || st->code == CTSM_ERR_GS_NEG || st->code == CTSM_ERR_BRENT ||
                        st->code == CTSM_ERR_QUADRATIC || st->code == CTSM_ERR_RH) ? CTSM_SUBGRID_PATCH : CTSM_SUBGRID_COLUMN;
   snprintf(st->msg, sizeof st->msg, "%s", message_for(st->code));
+  if (st->code == CTSM_ERR_SNOW_NEGATIVE && info == 1)
+    snprintf(st->msg, sizeof st->msg, "In UpdateState_TopLayerFluxes, h2osoi_liq has gone significantly negative");
 }
 
 extern "C" int ctsm_b200_sync(ctsm_b200_ctx* ctx, ctsm_status_t* st) {

@@ -2091,13 +2091,13 @@ canopy_final_kernel(CanopyDev f, CanopyPrm prm, Geo g, int fn, const int32_t* __
 #define SPLIT_BLOCK 256
 #define SPLIT_ITEMS 8
 __global__ void __launch_bounds__(SPLIT_BLOCK)
-split_count_kernel(int n, const int32_t* __restrict__ filt, const int32_t* __restrict__ fv, int begp, int* __restrict__ blockc) {
+split_count_kernel(int n, const int32_t* __restrict__ filt, const int32_t* __restrict__ fv, int begp, int sign, int* __restrict__ blockc) {
   __shared__ int sh[SPLIT_BLOCK / 32];
   const int base = blockIdx.x * SPLIT_BLOCK * SPLIT_ITEMS + threadIdx.x * SPLIT_ITEMS;
   int c = 0;
   for (int k = 0; k < SPLIT_ITEMS; ++k) {
     const int i = base + k;
-    if (i < n && fv[filt[i] - begp] > 0) ++c;
+    if (i < n && sign * fv[filt[i] - begp] > 0) ++c;
   }
   for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
@@ -2133,7 +2133,7 @@ __global__ void split_scan_kernel(int nblocks, int* __restrict__ blockc, int* __
   if (threadIdx.x == 0) *total = carry;
 }
 __global__ void __launch_bounds__(SPLIT_BLOCK)
-split_scatter_kernel(int n, const int32_t* __restrict__ filt, const int32_t* __restrict__ fv, int begp,
+split_scatter_kernel(int n, const int32_t* __restrict__ filt, const int32_t* __restrict__ fv, int begp, int sign,
                      const int* __restrict__ blockc, int32_t* __restrict__ out_yes, int32_t* __restrict__ out_no) {
   __shared__ int sh[SPLIT_BLOCK];
   const int base = blockIdx.x * SPLIT_BLOCK * SPLIT_ITEMS + threadIdx.x * SPLIT_ITEMS;
@@ -2143,7 +2143,7 @@ split_scatter_kernel(int n, const int32_t* __restrict__ filt, const int32_t* __r
   for (int k = 0; k < SPLIT_ITEMS; ++k) {
     const int i = base + k;
     v[k] = (i < n) ? filt[i] : 0;
-    y[k] = (i < n) && fv[v[k] - begp] > 0;
+    y[k] = (i < n) && sign * fv[v[k] - begp] > 0;
     if (y[k]) ++c;
   }
   sh[threadIdx.x] = c;
@@ -2426,11 +2426,33 @@ extern "C" int ctsm_b200_canopy_round_stats(ctsm_b200_ctx* ctx, int32_t* list_le
   return n;
 }
 
+// order-preserving split of a filter by the sign of an integer flag array (flag(beg:end), sign * flag > 0 goes to `yes`)
+static int split_filter(ctsm_b200_ctx* ctx, int beg, int end, int sign, int num_nolakeurbanp, const int32_t* filter_nolakeurbanp,
+                        const int32_t* frac_veg_nosno, int32_t* filter_exposedvegp, int32_t* num_exposedvegp,
+                        int32_t* filter_noexposedvegp, int32_t* num_noexposedvegp, int mem);
+
 extern "C" int ctsm_b200_set_exposedvegp_filter(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_nolakeurbanp,
                                                 const int32_t* filter_nolakeurbanp, const int32_t* frac_veg_nosno,
                                                 int32_t* filter_exposedvegp, int32_t* num_exposedvegp,
                                                 int32_t* filter_noexposedvegp, int32_t* num_noexposedvegp, int mem) {
-  if (!ctx || !bounds || num_nolakeurbanp < 0 || !frac_veg_nosno || !num_exposedvegp || !num_noexposedvegp ||
+  if (!bounds) return CTSM_ERR_BAD_ARG;
+  return split_filter(ctx, bounds->begp, bounds->endp, 1, num_nolakeurbanp, filter_nolakeurbanp, frac_veg_nosno, filter_exposedvegp,
+                      num_exposedvegp, filter_noexposedvegp, num_noexposedvegp, mem);
+}
+
+// BuildSnowFilter, SnowHydrologyMod.F90:3975-4010: snowc where col%snl < 0
+extern "C" int ctsm_b200_build_snow_filter(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_nolakec, const int32_t* filter_nolakec,
+                                           const int32_t* snl, int alloc_begc, int alloc_endc, int32_t* filter_snowc, int32_t* num_snowc,
+                                           int32_t* filter_nosnowc, int32_t* num_nosnowc, int mem) {
+  if (!bounds || alloc_endc < alloc_begc) return CTSM_ERR_BAD_ARG;
+  return split_filter(ctx, alloc_begc, alloc_endc, -1, num_nolakec, filter_nolakec, snl, filter_snowc, num_snowc, filter_nosnowc,
+                      num_nosnowc, mem);
+}
+
+static int split_filter(ctsm_b200_ctx* ctx, int beg, int end, int sign, int num_nolakeurbanp, const int32_t* filter_nolakeurbanp,
+                        const int32_t* frac_veg_nosno, int32_t* filter_exposedvegp, int32_t* num_exposedvegp,
+                        int32_t* filter_noexposedvegp, int32_t* num_noexposedvegp, int mem) {
+  if (!ctx || num_nolakeurbanp < 0 || !frac_veg_nosno || !num_exposedvegp || !num_noexposedvegp ||
       (num_nolakeurbanp > 0 && (!filter_nolakeurbanp || !filter_exposedvegp || !filter_noexposedvegp)))
     return CTSM_ERR_BAD_ARG;
   CUDA_TRY(cudaSetDevice(ctx->device));
@@ -2438,7 +2460,7 @@ extern "C" int ctsm_b200_set_exposedvegp_filter(ctsm_b200_ctx* ctx, const ctsm_b
   *num_exposedvegp = 0; *num_noexposedvegp = 0;
   if (n == 0) return CTSM_OK;
   cudaStream_t s = ctx->stream;
-  const int np = bounds->endp - bounds->begp + 1;
+  const int np = end - beg + 1;
   const int nblocks = grid_for(n, SPLIT_BLOCK * SPLIT_ITEMS);
   const int32_t *dfilt = filter_nolakeurbanp, *dfv = frac_veg_nosno;
   int32_t *dyes = filter_exposedvegp, *dno = filter_noexposedvegp;
@@ -2456,9 +2478,9 @@ extern "C" int ctsm_b200_set_exposedvegp_filter(ctsm_b200_ctx* ctx, const ctsm_b
     CUDA_TRY(cudaMemcpyAsync(e, frac_veg_nosno, sizeof(int32_t) * (size_t)np, cudaMemcpyHostToDevice, s));
     dfilt = a; dyes = b; dno = c; dfv = e;
   }
-  split_count_kernel<<<nblocks, SPLIT_BLOCK, 0, s>>>(n, dfilt, dfv, bounds->begp, blockc);
+  split_count_kernel<<<nblocks, SPLIT_BLOCK, 0, s>>>(n, dfilt, dfv, beg, sign, blockc);
   split_scan_kernel<<<1, 1024, 0, s>>>(nblocks, blockc, total);
-  split_scatter_kernel<<<nblocks, SPLIT_BLOCK, 0, s>>>(n, dfilt, dfv, bounds->begp, blockc, dyes, dno);
+  split_scatter_kernel<<<nblocks, SPLIT_BLOCK, 0, s>>>(n, dfilt, dfv, beg, sign, blockc, dyes, dno);
   ctx->launches += 3;
   int htotal = 0;
   CUDA_TRY(cudaMemcpyAsync(&htotal, total, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -121,6 +121,7 @@ __host__ inline LevShape lev_shape(const char* lev) {
   if (!strcmp(lev, "CAN")) return {1, CTSM_NLEVCAN};
   if (!strcmp(lev, "LAK")) return {1, CTSM_NLEVLAK};
   if (!strcmp(lev, "NUMRAD")) return {1, 2};
+  if (!strcmp(lev, "AER")) return {1, 14};
   if (!strcmp(lev, "PHS2")) return {1, 2 * CTSM_NLEVCAN};
   return {1, 1};
 }

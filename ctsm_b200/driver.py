@@ -24,11 +24,15 @@ ROUTINES = ("canopyfluxes", "soiltemperature", "soilfluxes", "patch2col", "plant
 PRE_ROUTINES = ("preflux", "surfacehumidity", "baregroundfluxes")
 # HydrologyNoDrainage's routines in front of the root-water sink (HydrologyNoDrainageMod.F90:297-337): with
 # them SoilWater's icefrac / eff_porosity / qflx_infl are produced on the device instead of being inputs
-HYDRO_ROUTINES = ("infiltration",)
-ROUTINES_HYDRO = ("canopyfluxes", "soiltemperature", "soilfluxes", "patch2col", "infiltration", "plantsink", "soilwater", "balancecheck")
+HYDRO_ROUTINES = ("snowwater", "infiltration", "snowlayers")
+# HydrologyNoDrainage as far as it is built (HydrologyNoDrainageMod.F90:279-402): BuildSnowFilter, SnowWater, the infiltration chain,
+# the root-water sink, SoilWater, SnowCompaction / CombineSnowLayers / DivideSnowLayers / ZeroEmptySnowLayers, BuildSnowFilter
+ROUTINES_HYDRO = ("canopyfluxes", "soiltemperature", "soilfluxes", "patch2col", "snowwater", "infiltration", "plantsink", "soilwater",
+                  "snowlayers", "balancecheck")
 FILTER_OF = {"preflux": ("nolakec", "nolakep"), "surfacehumidity": ("nolakec",), "baregroundfluxes": ("noexposedvegp",),
              "canopyfluxes": ("exposedvegp",), "soiltemperature": ("nolakep", "nolakec"), "soilfluxes": ("nolakep", "nolakec"),
-             "patch2col": ("allc", "nolakec"), "infiltration": ("nolakec", "hydrologyc"), "plantsink": ("hydrologyc",), "soilwater": ("hydrologyc",), "balancecheck": ("allc",)}
+             "patch2col": ("allc", "nolakec"), "infiltration": ("nolakec", "hydrologyc"), "plantsink": ("hydrologyc",),
+             "snowwater": ("nolakec",), "snowlayers": ("nolakec",), "soilwater": ("hydrologyc",), "balancecheck": ("allc",)}
 
 
 class CtsmError(RuntimeError):
@@ -307,8 +311,53 @@ class HotPath:
         if rc != 0:
             raise CtsmError(st, rc)
 
+    def BuildSnowFilter(self):
+        """BuildSnowFilter (SnowHydrologyMod.F90:3975): filter_snowc / filter_nosnowc of the current clump from col%snl, kept on the
+        side the arrays live on; returns the two lists as numpy arrays"""
+        n = self.nfilter["nolakec"]
+        na, nb = C.c_int32(0), C.c_int32(0)
+        snl = self.arrays["snl"]
+        if self.mem == abi.MEM_DEVICE:
+            import torch
+            a = torch.zeros(max(n, 1), dtype=torch.int32, device="cuda")
+            b = torch.zeros(max(n, 1), dtype=torch.int32, device="cuda")
+        else:
+            a, b = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+        rc = self.ctx.L.ctsm_b200_build_snow_filter(
+            self.ctx.h, C.byref(self.bounds), n, abi.i32p(self.filters["nolakec"]), abi.i32p(snl), self.sg.bounds.begc,
+            self.sg.bounds.endc, abi.i32p(a), C.byref(na), abi.i32p(b), C.byref(nb), abi.MEM_DEVICE if self.mem == abi.MEM_DEVICE else abi.MEM_HOST)
+        if rc != 0:
+            raise RuntimeError("ctsm_b200_build_snow_filter rc=%d" % rc)
+        self.filters["snowc"], self.filters["nosnowc"] = a, b
+        self.nfilter["snowc"], self.nfilter["nosnowc"] = int(na.value), int(nb.value)
+        to_np = (lambda t, k: t[:k].cpu().numpy()) if self.mem == abi.MEM_DEVICE else (lambda t, k: t[:k].copy())
+        return to_np(a, na.value), to_np(b, nb.value)
+
+    def SnowWater(self):
+        """BuildSnowFilter + SnowWater, HydrologyNoDrainageMod.F90:279-285 (SnowHydrologyMod.F90:1015)"""
+        self.BuildSnowFilter()
+        st = abi.Status()
+        rc = self.ctx.L.ctsm_b200_snow_water(
+            self.ctx.h, C.byref(self.bounds), self.nfilter["snowc"], abi.i32p(self.filters["snowc"]), self.nfilter["nosnowc"],
+            abi.i32p(self.filters["nosnowc"]), C.byref(self.structs["snowwater"]), self.mem, C.byref(st))
+        if rc != 0:
+            raise CtsmError(st, rc)
+
+    def SnowLayers(self):
+        """SnowCompaction, CombineSnowLayers, DivideSnowLayers, ZeroEmptySnowLayers over the snow filter built at the start of
+        HydrologyNoDrainage (HydrologyNoDrainageMod.F90:381-399)"""
+        if "snowc" not in self.filters:
+            self.BuildSnowFilter()
+        st = abi.Status()
+        rc = self.ctx.L.ctsm_b200_snow_layers(
+            self.ctx.h, C.byref(self.bounds), self.nfilter["snowc"], abi.i32p(self.filters["snowc"]),
+            C.byref(self.structs["snowlayers"]), self.mem, C.byref(st))
+        if rc != 0:
+            raise CtsmError(st, rc)
+        self.filters.pop("snowc", None)            # snl has changed: the next user rebuilds the filter (:402)
+
     def call(self, g):
-        {"infiltration": self.HydrologyInfiltration, "preflux": self.BiogeophysPreFluxCalcs, "surfacehumidity": self.CalculateSurfaceHumidity, "baregroundfluxes": self.BareGroundFluxes,
+        {"snowwater": self.SnowWater, "snowlayers": self.SnowLayers, "infiltration": self.HydrologyInfiltration, "preflux": self.BiogeophysPreFluxCalcs, "surfacehumidity": self.CalculateSurfaceHumidity, "baregroundfluxes": self.BareGroundFluxes,
          "canopyfluxes": self.CanopyFluxes, "soiltemperature": self.SoilTemperature, "soilwater": self.SoilWater,
          "plantsink": self.VertTranSink, "balancecheck": self.BalanceCheck, "soilfluxes": self.SoilFluxes, "patch2col": self.Patch2Col}[g]()
 

@@ -449,6 +449,78 @@ def hydrology_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Genera
         S[k] = np.ascontiguousarray(v)
 
 
+def snow_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator) -> None:
+    """Inputs of the snow routines of HydrologyNoDrainage (SnowWater, SnowCompaction, CombineSnowLayers, DivideSnowLayers;
+    SURVEY.md 8f rank 3) that the rest of the step does not carry: aerosol masses and deposition, grain radii, the snow water
+    before melt, melt flags, wind.  The layer structure soil_state draws (thickness 0.01 - 0.3 m in any order, density
+    80 - 450 kg/m3) already violates the thickness limits in most columns, so combination and subdivision both run; on top of
+    that: layers with almost no ice (<= 0.01 kg/m2: merged downwards, the bottom one into the soil), very light layers
+    (< 50 kg/m3), one-layer packs thin enough to disappear, saturated (immobile) layers."""
+    nc, ng = sg.ncol, sg.ngrc
+    nsno = 12
+    g = lambda lo, hi, *shape: rng.uniform(lo, hi, shape)
+    snl = S["snl"]
+    lev = np.arange(-nsno + 1, 1)[:, None]
+    act = lev >= (snl + 1)[None, :]
+    S["col_gridcell"] = sg.col_gridcell.astype(np.int32)
+    ice, liq, dz = S["h2osoi_ice"], S["h2osoi_liq"], S["dz"]
+    snowc = np.nonzero(snl < 0)[0]
+    pick = lambda frac: snowc[rng.random(len(snowc)) < frac]
+    for c in pick(0.12):                                      # an almost ice-free layer somewhere in the pack
+        j = int(rng.integers(snl[c] + 1, 1))
+        ice[j + nsno - 1, c] = rng.uniform(0.0, 0.01)
+        liq[j + nsno - 1, c] = rng.uniform(0.0, 0.3)
+    for c in pick(0.08):                                      # a very light layer
+        j = int(rng.integers(snl[c] + 1, 1))
+        ice[j + nsno - 1, c] = dz[j + nsno - 1, c] * rng.uniform(15.0, 45.0)
+    for c in pick(0.06):                                      # a saturated layer (void <= 0.001)
+        j = int(rng.integers(snl[c] + 1, 1))
+        ice[j + nsno - 1, c] = dz[j + nsno - 1, c] * S["frac_sno_eff"][c] * 900.0
+        liq[j + nsno - 1, c] = dz[j + nsno - 1, c] * S["frac_sno_eff"][c] * 30.0
+    one = snowc[(snl[snowc] == -1)]
+    for c in one[rng.random(len(one)) < 0.4]:                 # a pack about to disappear
+        dz[nsno - 1, c] = rng.uniform(0.004, 0.02)
+        ice[nsno - 1, c] = dz[nsno - 1, c] * rng.uniform(60.0, 300.0)
+        S["zi"][nsno - 1, c] = -dz[nsno - 1, c]
+        S["z"][nsno - 1, c] = -0.5 * dz[nsno - 1, c]
+    wx = ice[:nsno] + liq[:nsno]
+    S["swe_old"] = np.where(act, wx * g(0.9, 1.3, nsno, nc), 0.0)
+    fio = np.zeros_like(ice)
+    fio[:nsno] = np.where(act, ice[:nsno] / np.maximum(wx, 1e-30) * g(1.0, 1.1, nsno, nc), 0.0).clip(0.0, 1.0)
+    S["frac_iceold"] = fio
+    im = np.where(np.abs(S["imelt"]) < 3, S["imelt"], 0).astype(np.int32)
+    im[:nsno] = np.where(act & (rng.random((nsno, nc)) < 0.4), 1, 0)
+    S["imelt"] = im
+    S["n_melt"] = 200.0 / np.maximum(10.0, g(5.0, 600.0, nc))
+    S["forc_wind"] = g(0.3, 18.0, ng)
+    S["snw_rds"] = np.where(act, g(54.526, 1500.0, nsno, nc), 0.0)
+    for a in ("bcphi", "bcpho", "ocphi", "ocpho", "dst1", "dst2", "dst3", "dst4"):
+        S["mss_" + a] = np.where(act, 10.0 ** g(-9.0, -5.0, nsno, nc), 0.0)
+    S["forc_aer"] = 10.0 ** g(-14.0, -10.0, 14, ng)
+    S["int_snow"] = np.maximum(S["int_snow"], (wx * act).sum(0) * g(1.0, 1.5, nc))
+    # column water fluxes at the snow surface (SoilFluxes outputs: spval before a step); evaporation kept below the top layer's store
+    top = np.clip(snl + nsno, 0, nsno - 1)
+    ice_top, liq_top = ice[top, np.arange(nc)], liq[top, np.arange(nc)]
+    fs = np.maximum(S["frac_sno_eff"], 1e-3)
+    S["qflx_soliddew_to_top_layer"] = np.where(rng.random(nc) < 0.3, g(0.0, 2.0e-5, nc), 0.0)
+    S["qflx_liqdew_to_top_layer"] = np.where(rng.random(nc) < 0.3, g(0.0, 2.0e-5, nc), 0.0)
+    S["qflx_solidevap_from_top_layer"] = np.minimum(np.where(rng.random(nc) < 0.5, g(0.0, 4.0e-5, nc), 0.0), 0.5 * ice_top / (1800.0 * fs))
+    S["qflx_liqevap_from_top_layer"] = np.minimum(np.where(rng.random(nc) < 0.5, g(0.0, 4.0e-5, nc), 0.0), 0.5 * liq_top / (1800.0 * fs))
+    exact = snowc[rng.random(len(snowc)) < 0.05]              # sublimation that removes the top layer's ice to rounding (truncated to 0)
+    S["qflx_solidevap_from_top_layer"][exact] = ice_top[exact] / (1800.0 * S["frac_sno_eff"][exact])
+    S["qflx_soliddew_to_top_layer"][exact] = 0.0
+    S["qflx_liq_grnd"] = np.where(rng.random(nc) < 0.4, 10.0 ** g(-6.0, -3.3, nc), 0.0)
+    S["qflx_snomelt"] = np.where(rng.random(nc) < 0.4, g(0.0, 3.0e-4, nc), 0.0)
+    S["qflx_snow_drain"] = np.where(snl < 0, S["qflx_snomelt"], 1.0e36)       # (SoilTemperature leaves the melt here on snow columns)
+    for grp in ("snowwater", "snowlayers"):
+        for fs_ in abi_fields(grp):
+            if fs_.name not in S and fs_.ctype == "double":
+                n = {"COL": nc, "PATCH": sg.npatch, "GRC": ng}[fs_.sub]
+                S[fs_.name] = np.full(n if fs_.lev == "L1" else (fs_.nlev, n), 1.0e36)
+    for k, v in list(S.items()):
+        S[k] = np.ascontiguousarray(v)
+
+
 def make_ensemble(sg: Subgrid, S: Dict[str, np.ndarray], nmember: int, rng: np.random.Generator, spread: float = 0.2):
     """Perturbed-parameter ensemble through the PFT tables (BASELINE config 5): the grid is split into `nmember` equal
     runs of gridcells, member m's patches get itype = m*(mxpft+1) + pft, and every pft_* table is extended to

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define CTSM_B200_ABI_VERSION 4
+#define CTSM_B200_ABI_VERSION 5
 
 /* fixed vertical structure the kernels are compiled for (clm_varpar.F90:43-54,
  * 290-292; namelist_defaults_ctsm.xml:254,511).  ctsm_b200_init refuses any
@@ -91,6 +91,7 @@ enum {
   CTSM_ERR_BRENT = 14,          /* PhotosynthesisMod.F90:4134-4137 root must be bracketed for brent */
   CTSM_ERR_QUADRATIC = 15,      /* quadraticMod.F90:42-58 */
   CTSM_ERR_URBAN = 16,          /* urban column in filter: outside the hot path */
+  CTSM_ERR_SNOW_NEGATIVE = 18,  /* SnowHydrologyMod.F90:1244-1287 UpdateState_TopLayerFluxes: top-layer ice / liquid significantly negative */
   CTSM_ERR_RH = 17,             /* HumanIndexMod.F90:1016-1022 Wet_BulbS: 2 m relative humidity outside [0, 100] */
   CTSM_ERR_BALANCE = 20         /* BalanceCheckMod.F90:640-659,1060-1114 thresholds exceeded */
 };
@@ -159,6 +160,17 @@ typedef struct ctsm_params_t {
   int32_t reserved_i[2];
   double  zlnd, zsno, zglc, d_max, frac_sat_soil_dsl_init;
   double  fff, pc, mu;
+  /* the snow routines of HydrologyNoDrainage (SnowHydrologyMod.F90): clm_snowhydrology_inparm :188-283 (namelist), params_inst
+   * :70-91 (parameter file), scf_swenson_lawrence_2012_inparm int_snow_max, clm_varctl use_subgrid_fluxes */
+  int32_t snow_overburden_compaction_method;  /* 1 = Anderson1976, 2 = Vionnet2012 (clm5 / clm6) */
+  int32_t wind_dependent_snow_density;        /* 1 */
+  int32_t use_subgrid_fluxes;                 /* 1 */
+  int32_t snicar_use_aerosol;                 /* 1: AerosolFluxes deposits forc_aer on the top snow layer (AerosolMod.F90:754) */
+  double  snow_dzmin_1, snow_dzmin_2, snow_dzmax_l_1, snow_dzmax_l_2, snow_dzmax_u_1, snow_dzmax_u_2;
+  double  overburden_compress_Tfactor, int_snow_max;
+  double  wimp, ssi, drift_gs, eta0_anderson, eta0_vionnet, rho_max, tau_ref, ceta, snw_rds_min, upplim_destruct_metamorph;
+  double  scvng_fct_mlt_sf, scvng_fct_mlt_bcphi, scvng_fct_mlt_bcpho, scvng_fct_mlt_dst1, scvng_fct_mlt_dst2,
+          scvng_fct_mlt_dst3, scvng_fct_mlt_dst4;
 } ctsm_params_t;
 
 typedef struct ctsm_b200_ctx ctsm_b200_ctx;
@@ -227,6 +239,20 @@ typedef struct ctsm_infiltration_fields_t {
 #include "ctsm_b200_fields.def"
 #undef CTSM_FIELDS_INFILTRATION
 } ctsm_infiltration_fields_t;
+
+typedef struct ctsm_snowwater_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_SNOWWATER
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_SNOWWATER
+} ctsm_snowwater_fields_t;
+
+typedef struct ctsm_snowlayers_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_SNOWLAYERS
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_SNOWLAYERS
+} ctsm_snowlayers_fields_t;
 
 typedef struct ctsm_soilfluxes_fields_t {
   ctsm_bounds_t alloc;
@@ -485,6 +511,27 @@ int ctsm_b200_hydrology_infiltration(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bo
                                      int num_hydrologyc, const int32_t* filter_hydrologyc,
                                      int num_urbanc, const int32_t* filter_urbanc,
                                      const ctsm_infiltration_fields_t* f, int mem, ctsm_status_t* st);
+
+/* BuildSnowFilter(bounds, num_nolakec, filter_nolakec, num_snowc, filter_snowc, num_nosnowc, filter_nosnowc):
+ * SnowHydrologyMod.F90:3975-4010, called at HydrologyNoDrainageMod.F90:279 and :402.  Order-preserving split of filter_nolakec
+ * by col%snl < 0.  snl is the (alloc_begc : ...) array; output lists must hold num_nolakec entries; counts come back through
+ * host pointers in every mode (DEVICE mode synchronises to return them). */
+int ctsm_b200_build_snow_filter(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_nolakec, const int32_t* filter_nolakec,
+                                const int32_t* snl, int alloc_begc, int alloc_endc,
+                                int32_t* filter_snowc, int32_t* num_snowc, int32_t* filter_nosnowc, int32_t* num_nosnowc, int mem);
+
+/* SnowWater(bounds, num_snowc, filter_snowc, num_nosnowc, filter_nosnowc, atm2lnd_inst, aerosol_inst, water_inst):
+ * SnowHydrologyMod.F90:1015-1165.  Fails with CTSM_ERR_SNOW_NEGATIVE where the reference calls endrun
+ * ("h2osoi_ice / h2osoi_liq has gone significantly negative", :1244-1287). */
+int ctsm_b200_snow_water(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_snowc, const int32_t* filter_snowc,
+                         int num_nosnowc, const int32_t* filter_nosnowc, const ctsm_snowwater_fields_t* f, int mem,
+                         ctsm_status_t* st);
+
+/* SnowCompaction, CombineSnowLayers, DivideSnowLayers(is_lake = .false.), ZeroEmptySnowLayers over filter_snowc: the call
+ * sequence HydrologyNoDrainageMod.F90:381-399 (SnowHydrologyMod.F90:1870, :2083, :2510, :2898).  Lake and urban columns in the
+ * filter are refused (CTSM_ERR_URBAN / CTSM_ERR_BAD_ARG). */
+int ctsm_b200_snow_layers(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_snowc, const int32_t* filter_snowc,
+                          const ctsm_snowlayers_fields_t* f, int mem, ctsm_status_t* st);
 
 /* Compute_EffecRootFrac_And_VertTranSink_Default(bounds, num_filterc, filterc, ...): SoilWaterPlantSinkMod.F90:332-424,
  * what Compute_EffecRootFrac_And_VertTranSink (:18-142) calls for every column class when use_hydrstress = .false. */

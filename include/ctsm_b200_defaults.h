@@ -56,6 +56,16 @@ static inline void ctsm_default_params_fill(ctsm_params_t* p) {
   p->h2osfcflag = 1;                       // SoilHydrologyType.F90:352-360
   p->crop_fsat_equals_zero = 0;            // namelist_defaults_ctsm.xml (saturated_excess_runoff_inparm)
   p->fff = 0.5; p->pc = 0.4; p->mu = 0.13889;   // parameter-file scalars (clm5 technical note values; synthetic choice)
+  // snow: namelist_defaults_ctsm.xml:521-544, 694 (clm6_0); parameter-file scalars: the ctsm5.1+ parameter-file values
+  // (synthetic choice; scavenging factors as in Flanner et al. 2007 / SnowHydrologyMod.F90:131-132)
+  p->snow_overburden_compaction_method = 2; p->wind_dependent_snow_density = 1; p->use_subgrid_fluxes = 1; p->snicar_use_aerosol = 1;
+  p->snow_dzmin_1 = 0.010; p->snow_dzmin_2 = 0.015; p->snow_dzmax_l_1 = 0.03; p->snow_dzmax_l_2 = 0.07;
+  p->snow_dzmax_u_1 = 0.02; p->snow_dzmax_u_2 = 0.05;
+  p->overburden_compress_Tfactor = 0.08; p->int_snow_max = 2000.0;
+  p->wimp = 0.05; p->ssi = 0.033; p->drift_gs = 0.35e-3; p->eta0_anderson = 9.0e5; p->eta0_vionnet = 7.62237e6;
+  p->rho_max = 350.0; p->tau_ref = 172800.0; p->ceta = 250.0; p->snw_rds_min = 54.526; p->upplim_destruct_metamorph = 175.0;
+  p->scvng_fct_mlt_sf = 1.0; p->scvng_fct_mlt_bcphi = 0.20; p->scvng_fct_mlt_bcpho = 0.03;
+  p->scvng_fct_mlt_dst1 = 0.02; p->scvng_fct_mlt_dst2 = 0.02; p->scvng_fct_mlt_dst3 = 0.01; p->scvng_fct_mlt_dst4 = 0.01;
   p->balance_skip_steps = -1;
   p->npft_table = CTSM_MXPFT + 1;
 }

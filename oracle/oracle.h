@@ -74,6 +74,14 @@ int oracle_bare_ground_fluxes(const ctsm_params_t* prm, const ctsm_bounds_t* bou
 int oracle_hydrology_infiltration(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_nolakec,
                                   const int32_t* filter_nolakec, int num_hydrologyc, const int32_t* filter_hydrologyc,
                                   int num_urbanc, const ctsm_infiltration_fields_t* f, ctsm_status_t* st);
+/* oracle_snow.c: the snow routines of HydrologyNoDrainage */
+void oracle_snow_dz_limits(const ctsm_params_t* prm, double* dzmin, double* dzmax_l, double* dzmax_u);
+void oracle_build_snow_filter(int num_nolakec, const int32_t* filter_nolakec, const int32_t* snl, int begc0,
+                              int32_t* filter_snowc, int32_t* num_snowc, int32_t* filter_nosnowc, int32_t* num_nosnowc);
+int oracle_snow_water(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_snowc, const int32_t* filter_snowc,
+                      int num_nosnowc, const int32_t* filter_nosnowc, const ctsm_snowwater_fields_t* f, ctsm_status_t* st);
+int oracle_snow_layers(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_snowc, const int32_t* filter_snowc,
+                       const ctsm_snowlayers_fields_t* f, ctsm_status_t* st);
 int oracle_vert_tran_sink_default(const ctsm_bounds_t* bounds, int num_filterc, const int32_t* filterc,
                                   const ctsm_plantsinkdefault_fields_t* f);
 /* the field struct oracle_fullstep_clumps hands to the default sink when prm->use_hydrstress == 0 (its own plant-sink

@@ -156,6 +156,13 @@ def _bind(L):
     L.oracle_bare_ground_fluxes.argtypes = [P, B, C.c_int, i32p, C.POINTER(abi.STRUCTS["baregroundfluxes"]), C.POINTER(abi.Status)]
     L.oracle_hydrology_infiltration.argtypes = [P, B, C.c_int, i32p, C.c_int, i32p, C.c_int, C.POINTER(abi.STRUCTS["infiltration"]),
                                                 C.POINTER(abi.Status)]
+    dp = C.POINTER(C.c_double)
+    L.oracle_snow_dz_limits.argtypes = [P, dp, dp, dp]
+    L.oracle_snow_dz_limits.restype = None
+    L.oracle_build_snow_filter.argtypes = [C.c_int, i32p, i32p, C.c_int, i32p, i32p, i32p, i32p]
+    L.oracle_build_snow_filter.restype = None
+    L.oracle_snow_water.argtypes = [P, B, C.c_int, i32p, C.c_int, i32p, C.POINTER(abi.STRUCTS["snowwater"]), C.POINTER(abi.Status)]
+    L.oracle_snow_layers.argtypes = [P, B, C.c_int, i32p, C.POINTER(abi.STRUCTS["snowlayers"]), C.POINTER(abi.Status)]
     L.oracle_vert_tran_sink_default.argtypes = [B, C.c_int, i32p, C.POINTER(abi.STRUCTS["plantsinkdefault"])]
     L.oracle_set_plantsink_default.argtypes = [C.POINTER(abi.STRUCTS["plantsinkdefault"])]
     L.oracle_set_plantsink_default.restype = None

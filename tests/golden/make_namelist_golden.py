@@ -27,7 +27,10 @@ VARS = ["upper_boundary_condition", "lower_boundary_condition", "flux_calculatio
         "xTolerLower", "snow_thermal_cond_method", "snow_thermal_cond_glc_method", "itmax_canopy_fluxes",
         "use_undercanopy_stability", "use_biomass_heat_storage", "z0param_method", "soil_resis_method", "use_hydrstress",
         "use_luna", "stomatalcond_method", "light_inhibit", "modifyphoto_and_lmr_forcrop", "zetamaxstable", "leaf_mr_vcm",
-        "soilwater_movement_method", "nlevsno", "soil_layerstruct_predefined", "calc_human_stress_indices"]
+        "soilwater_movement_method", "nlevsno", "soil_layerstruct_predefined", "calc_human_stress_indices",
+        "snow_dzmin_1", "snow_dzmin_2", "snow_dzmax_l_1", "snow_dzmax_l_2", "snow_dzmax_u_1", "snow_dzmax_u_2", "int_snow_max",
+        "wind_dependent_snow_density", "snow_overburden_compaction_method", "overburden_compress_tfactor", "use_subgrid_fluxes",
+        "snow_cover_fraction_method", "snicar_use_aerosol"]
 
 
 def resolve(text, var):

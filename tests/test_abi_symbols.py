@@ -32,7 +32,7 @@ def test_version_and_defaults_match_python_twin():
             continue
         assert getattr(p, name) == getattr(q, name), name
     # layout check of the ctypes mirror: first, middle and last members as ctsm_b200_default_params wrote them
-    assert (p.abi_version, p.nlevsno, p.nlevgrnd, p.nlevsoi) == (4, 12, 25, 20)
+    assert (p.abi_version, p.nlevsno, p.nlevgrnd, p.nlevsoi) == (5, 12, 25, 20)
     assert (p.dtmin, p.xTolerUpper, p.snow_thermal_cond_method) == (60.0, 0.1, 2)
     assert (p.itmax_canopy_fluxes, p.z0param_method, p.stomatalcond_mtd) == (40, 2, 2)
     assert (p.csoilc, p.zetamaxstable, p.lmrhd, p.jmax25top_sf, p.balance_skip_steps) == (0.004, 2.0, 150650.0, 1.0, -1)
@@ -66,7 +66,7 @@ def test_ctypes_mirrors_have_the_c_layout(tmp_path):
     probes = {"ctsm_bounds_t": (abi.Bounds, ["begg", "endp", "clump_index"]),
               "ctsm_status_t": (abi.Status, ["code", "value", "n_warnings", "msg"]),
               "ctsm_params_t": (abi.Params, ["abi_version", "dtime", "e_ice", "itmax_canopy_fluxes", "lai_dl", "jmax25top_sf",
-                                             "balance_skip_steps", "npft_table", "calc_human_stress_indices", "reserved_i", "fff", "mu"]),
+                                             "balance_skip_steps", "npft_table", "calc_human_stress_indices", "reserved_i", "fff", "mu", "snicar_use_aerosol", "snow_dzmin_1", "scvng_fct_mlt_dst4"]),
               "ctsm_balance_report_t": (abi.BalanceReport, ["max_abs", "index", "warn", "abort_kind", "skip_steps"]),
               "ctsm_filter_inputs_t": (abi.FilterInputs, ["alloc", "col_active", "melt_replaced_by_ice_grc", "include_inactive",
                                                           "npcropmax"]),

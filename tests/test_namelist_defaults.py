@@ -47,3 +47,17 @@ def test_default_params_follow_clm6_0_namelist_defaults():
     assert p.nlevsno == int(GOLD["nlevsno"])
     assert GOLD["soil_layerstruct_predefined"] == "20SL_8.5m" and (p.nlevsoi, p.nlevgrnd) == (20, 25)
     assert int(GOLD["soilwater_movement_method"]) == 1      # moisture form + adaptive time stepping: the only one built
+
+
+def test_snow_defaults_follow_clm6_0_namelist_defaults():
+    L = abi.lib()
+    p = abi.Params()
+    L.ctsm_b200_default_params(C.byref(p))
+    for nm in ("snow_dzmin_1", "snow_dzmin_2", "snow_dzmax_l_1", "snow_dzmax_l_2", "snow_dzmax_u_1", "snow_dzmax_u_2", "int_snow_max"):
+        assert getattr(p, nm) == _real(GOLD[nm]), nm
+    assert p.overburden_compress_Tfactor == _real(GOLD["overburden_compress_tfactor"])
+    assert p.wind_dependent_snow_density == _logical(GOLD["wind_dependent_snow_density"])
+    assert p.use_subgrid_fluxes == _logical(GOLD["use_subgrid_fluxes"])
+    assert p.snicar_use_aerosol == _logical(GOLD["snicar_use_aerosol"])
+    assert p.snow_overburden_compaction_method == {"Anderson1976": 1, "Vionnet2012": 2}[GOLD["snow_overburden_compaction_method"].strip("'")]
+    assert GOLD["snow_cover_fraction_method"] == "SwensonLawrence2012"      # FracSnowDuringMelt: the only method built
