@@ -326,6 +326,10 @@ def lib():
     L.ctsm_b200_snow_water.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p, C.POINTER(STRUCTS["snowwater"]), C.c_int,
                                        C.POINTER(Status)]
     L.ctsm_b200_snow_layers.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.POINTER(STRUCTS["snowlayers"]), C.c_int, C.POINTER(Status)]
+    L.ctsm_b200_water_table.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p, C.POINTER(STRUCTS["watertable"]), C.c_int,
+                                        C.POINTER(Status)]
+    L.ctsm_b200_hydrology_diagnostics.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p, C.c_int, i32p, C.c_int, i32p, C.c_int,
+                                                  i32p, C.POINTER(STRUCTS["hydrodiag"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_vert_tran_sink_default.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p,
                                                      C.POINTER(STRUCTS["plantsinkdefault"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_soilfluxes.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p,
@@ -347,7 +351,7 @@ def lib():
     L.ctsm_b200_set_soil_tuning.argtypes = [vp, C.c_int]
     L.ctsm_b200_set_soilwater_tuning.argtypes = [vp, C.c_int]
     for fn in ("vert_tran_sink_hydstress", "vert_tran_sink_default", "biogeophys_pre_flux_calcs", "calculate_surface_humidity",
-               "bare_ground_fluxes", "hydrology_infiltration", "build_snow_filter", "snow_water", "snow_layers", "balancecheck_init", "balancecheck", "soilfluxes", "patch2col"):
+               "bare_ground_fluxes", "hydrology_infiltration", "build_snow_filter", "snow_water", "snow_layers", "water_table", "hydrology_diagnostics", "balancecheck_init", "balancecheck", "soilfluxes", "patch2col"):
         getattr(L, "ctsm_b200_" + fn).restype = C.c_int
     for fn in ("init", "finalize", "sync", "host_register", "host_unregister", "tridiagonal", "banddiagonal",
                "dgtsv_batch", "soilwater", "soiltemperature", "canopyfluxes", "set_exposedvegp_filter"):

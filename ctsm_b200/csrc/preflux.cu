@@ -603,183 +603,3 @@ extern "C" int ctsm_b200_bare_ground_fluxes(ctsm_b200_ctx* ctx, const ctsm_bound
   }
   return finish_call(ctx, mem, st);
 }
-
-// ---------------------------------------------------------------------------------------------------------------------
-// The surface-water / infiltration chain of HydrologyNoDrainage (HydrologyNoDrainageMod.F90:297-337; SURVEY.md 8f rank 3,
-// first part): nine small per-column routines of the reference, none of which reads another column, fused into one
-// thread-per-column kernel (every intermediate stays in registers and is also stored, because all of them are history /
-// balance fields of the reference).  HBM-bound: ~0.9 KB per hydrology column.
-struct InfilDev {
-#define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) ctype* name;
-#define CTSM_FIELDS_INFILTRATION
-#include "../../include/ctsm_b200_fields.def"
-#undef CTSM_FIELDS_INFILTRATION
-#undef CTSM_F
-};
-
-namespace {
-struct InfilPrm { double dtime, fff, pc, mu, e_ice; int h2osfcflag, crop_fsat_equals_zero; };
-
-// SetFloodc, SoilHydrologyMod.F90:282-291
-__global__ void __launch_bounds__(256)
-floodc_kernel(InfilDev f, int begc0, int begg0, int numf, const int32_t* __restrict__ filterc, DevStatus* ds) {
-  const int fc = blockIdx.x * blockDim.x + threadIdx.x;
-  if (fc >= numf) return;
-  const int c1 = filterc[fc];
-  const int cc = c1 - begc0;
-  if (is_urban(f.lun_itype[cc])) { report_failure(ds, c1, CTSM_ERR_URBAN, 0); return; }
-  f.qflx_floodc[cc] = f.forc_flood[f.col_gridcell[cc] - begg0];
-}
-
-// truncate_small_values, NumericsMod.F90:50
-__device__ __forceinline__ double truncate_small(double data, double baseline) {
-  return (fabs(data) < 1.e-13 * fabs(baseline)) ? 0.0 : data;
-}
-
-__global__ void __launch_bounds__(256)
-infiltration_kernel(InfilDev f, InfilPrm prm, int begc0, int ldc_, int numf, const int32_t* __restrict__ filterc, DevStatus* ds) {
-  const int fc = blockIdx.x * blockDim.x + threadIdx.x;
-  if (fc >= numf) return;
-  const int c1 = filterc[fc];
-  const int cc = c1 - begc0;
-  const size_t ldc = (size_t)ldc_;
-  const int lt = f.lun_itype[cc];
-  if (is_urban(lt)) { report_failure(ds, c1, CTSM_ERR_URBAN, 0); return; }
-  const double dtime = prm.dtime;
-  // SetSoilWaterFractions :239-252 (excess_ice = 0); the three top-level ice fractions feed qinmax below
-  double qmin = 0.0;
-#pragma unroll 4
-  for (int j = 1; j <= CTSM_NLEVSOI; ++j) {
-    const size_t o1 = (size_t)(j - 1) * ldc + cc, os = (size_t)(j - SNO_LO) * ldc + cc;
-    const double watsat = f.watsat[o1];
-    const double dz_ext = f.dz[os] + 0.0 / denice;
-    const double vol_ice = fmin(watsat, (f.h2osoi_ice[os] + 0.0) / (dz_ext * denice));
-    f.eff_porosity[o1] = fmax(0.01, watsat - vol_ice);
-    const double icefrac = fmin(1.0, vol_ice / watsat);
-    f.icefrac[o1] = icefrac;
-    if (j <= 3) {                                                            // ComputeQinmaxHksat :296-300
-      const double v = pow(10.0, -prm.e_ice * (icefrac)) * f.hksat[o1];
-      if (j == 1 || v < qmin) qmin = v;
-    }
-  }
-  // SaturatedExcessRunoff: ComputeFsatTopmodel :344-356
-  const double frost_table = f.frost_table[cc], zwt = f.zwt[cc], zwt_perched = f.zwt_perched[cc];
-  double fsat;
-  if (frost_table > zwt_perched && frost_table <= zwt) fsat = f.wtfact[cc] * dexp(-0.5 * prm.fff * zwt_perched);
-  else fsat = f.wtfact[cc] * dexp(-0.5 * prm.fff * zwt);
-  if (prm.crop_fsat_equals_zero && lt == CTSM_ISTCROP) fsat = 0.0;
-  f.fsat[cc] = fsat; f.fcov[cc] = fsat;
-  const double rain = f.qflx_rain_plus_snomelt[cc];
-  const double qflx_sat_excess_surf = fsat * rain;
-  f.qflx_sat_excess_surf[cc] = qflx_sat_excess_surf;
-  // SetQflxInputs :339-362
-  const double frac_h2osfc = f.frac_h2osfc[cc];
-  const double qflx_top_soil = rain + f.qflx_snow_h2osfc[cc] + f.qflx_floodc[cc];
-  f.qflx_top_soil[cc] = qflx_top_soil;
-  double fsno, qflx_evap;
-  if (f.snl[cc] >= 0) { fsno = 0.0; qflx_evap = f.qflx_liqevap_from_top_layer[cc]; }
-  else { fsno = f.frac_sno_eff[cc]; qflx_evap = f.qflx_ev_soil_col[cc]; }
-  double qflx_in_soil = (1.0 - frac_h2osfc) * (qflx_top_soil - qflx_sat_excess_surf);
-  double qflx_top_soil_to_h2osfc = frac_h2osfc * (qflx_top_soil - qflx_sat_excess_surf);
-  qflx_in_soil = qflx_in_soil - (1.0 - fsno - frac_h2osfc) * qflx_evap;
-  qflx_top_soil_to_h2osfc = qflx_top_soil_to_h2osfc - frac_h2osfc * f.qflx_ev_h2osfc_col[cc];
-  f.qflx_in_soil[cc] = qflx_in_soil; f.qflx_top_soil_to_h2osfc[cc] = qflx_top_soil_to_h2osfc;
-  // InfiltrationExcessRunoff :253-259
-  const double qinmax = (1.0 - fsat) * qmin;
-  f.qinmax[cc] = qinmax;
-  const double qflx_infl_excess = fmax(0.0, (qflx_in_soil - (1.0 - frac_h2osfc) * qinmax));
-  f.qflx_infl_excess[cc] = qflx_infl_excess;
-  // RouteInfiltrationExcess :399-419
-  double qflx_in_soil_limited, qflx_in_h2osfc, qflx_infl_excess_surf;
-  if (lt == CTSM_ISTSOIL || lt == CTSM_ISTCROP) {
-    qflx_in_soil_limited = qflx_in_soil - qflx_infl_excess;
-    if (prm.h2osfcflag != 0) { qflx_in_h2osfc = qflx_top_soil_to_h2osfc + qflx_infl_excess; qflx_infl_excess_surf = 0.0; }
-    else { qflx_in_h2osfc = qflx_top_soil_to_h2osfc; qflx_infl_excess_surf = qflx_infl_excess; }
-  } else {
-    qflx_in_soil_limited = qflx_in_soil; qflx_in_h2osfc = 0.0; qflx_infl_excess_surf = 0.0;
-  }
-  f.qflx_in_soil_limited[cc] = qflx_in_soil_limited; f.qflx_in_h2osfc[cc] = qflx_in_h2osfc;
-  f.qflx_infl_excess_surf[cc] = qflx_infl_excess_surf;
-  // UpdateH2osfc, SurfaceWaterMod.F90:345-556
-  const double h2osfc0 = f.h2osfc[cc], thresh = f.h2osfc_thresh[cc];
-  double frac_infclust = 0.0;
-  if (prm.h2osfcflag == 1) {
-    const double fn = f.frac_h2osfc_nosnow[cc];
-    if (fn <= prm.pc) frac_infclust = 0.0;
-    else frac_infclust = pow(fn - prm.pc, prm.mu);
-  }
-  double qflx_h2osfc_surf;
-  if (h2osfc0 > thresh && prm.h2osfcflag != 0) {
-    const double k_wet = 1.0e-4 * sin((rpi / 180.0) * f.topo_slope[cc]);
-    qflx_h2osfc_surf = k_wet * frac_infclust * (h2osfc0 - thresh);
-    qflx_h2osfc_surf = fmin(qflx_h2osfc_surf, (h2osfc0 - thresh) / dtime);
-  } else {
-    qflx_h2osfc_surf = 0.0;
-  }
-  if (qflx_h2osfc_surf < 1.0e-8) qflx_h2osfc_surf = 0.0;
-  f.qflx_h2osfc_surf[cc] = qflx_h2osfc_surf;
-  double h2osfc_partial = h2osfc0 + (qflx_in_h2osfc - qflx_h2osfc_surf) * dtime;
-  h2osfc_partial = truncate_small(h2osfc_partial, h2osfc0);
-  double qflx_h2osfc_drain;
-  if (h2osfc_partial < 0.0) {
-    qflx_h2osfc_drain = h2osfc_partial / dtime;
-  } else {
-    qflx_h2osfc_drain = fmin(frac_h2osfc * qinmax, h2osfc_partial / dtime);
-    if (prm.h2osfcflag == 0) qflx_h2osfc_drain = fmax(0.0, h2osfc_partial / dtime);
-  }
-  f.qflx_h2osfc_drain[cc] = qflx_h2osfc_drain;
-  double h2osfc = h2osfc_partial - qflx_h2osfc_drain * dtime;
-  h2osfc = truncate_small(h2osfc, h2osfc_partial);
-  f.h2osfc[cc] = h2osfc;
-  // Infiltration :450-453, TotalSurfaceRunoff :511-515
-  f.qflx_infl[cc] = qflx_in_soil_limited + qflx_h2osfc_drain;
-  f.qflx_surf[cc] = qflx_sat_excess_surf + qflx_infl_excess_surf + qflx_h2osfc_surf;
-}
-}  // namespace
-
-extern "C" int ctsm_b200_hydrology_infiltration(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_nolakec,
-                                                const int32_t* filter_nolakec, int num_hydrologyc,
-                                                const int32_t* filter_hydrologyc, int num_urbanc, const int32_t* filter_urbanc,
-                                                const ctsm_infiltration_fields_t* hf, int mem, ctsm_status_t* st) {
-  (void)filter_urbanc;
-  if (!ctx || !bounds || !hf || num_nolakec < 0 || num_hydrologyc < 0 || (num_nolakec > 0 && !filter_nolakec) ||
-      (num_hydrologyc > 0 && !filter_hydrologyc))
-    return CTSM_ERR_BAD_ARG;
-  if (num_urbanc != 0) return CTSM_ERR_URBAN;
-  CUDA_TRY(cudaSetDevice(ctx->device));
-  InfilDev d;
-  const int32_t *dfn = filter_nolakec, *dfh = filter_hydrologyc;
-  std::vector<StageField> fl;
-#define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) \
-  d.name = hf->name;                                        \
-  fl.push_back(StageField{(void**)&d.name, (void*)hf->name, (int)sizeof(ctype), SUB_##sub, lev_shape(#lev).n, INTENT_##intent});
-#define CTSM_FIELDS_INFILTRATION
-#include "../../include/ctsm_b200_fields.def"
-#undef CTSM_FIELDS_INFILTRATION
-#undef CTSM_F
-  for (auto& s : fl) if (!s.host_ptr) return CTSM_ERR_BAD_ARG;
-  if (mem != CTSM_MEM_DEVICE) {
-    int rc = stage_begin(ctx, fl, hf->alloc, *bounds, mem == CTSM_MEM_HOST);
-    if (rc) return rc;
-    rc = stage_filter(ctx, ctx->arena_filter0, filter_nolakec, num_nolakec, &dfn);
-    if (rc) return rc;
-    rc = stage_filter(ctx, ctx->arena_filter1, filter_hydrologyc, num_hydrologyc, &dfh);
-    if (rc) return rc;
-  }
-  const InfilPrm prm{ctx->prm.dtime, ctx->prm.fff, ctx->prm.pc, ctx->prm.mu, ctx->prm.e_ice, ctx->prm.h2osfcflag,
-                     ctx->prm.crop_fsat_equals_zero};
-  if (num_nolakec > 0) {
-    floodc_kernel<<<grid_for(num_nolakec, 256), 256, 0, ctx->stream>>>(d, hf->alloc.begc, hf->alloc.begg, num_nolakec, dfn, ctx->d_status);
-    ctx->launches++;
-  }
-  if (num_hydrologyc > 0) {
-    infiltration_kernel<<<grid_for(num_hydrologyc, 256), 256, 0, ctx->stream>>>(d, prm, hf->alloc.begc, hf->alloc.endc - hf->alloc.begc + 1,
-                                                                                num_hydrologyc, dfh, ctx->d_status);
-    ctx->launches++;
-  }
-  if (mem != CTSM_MEM_DEVICE) {
-    int rc = stage_end(ctx, fl, hf->alloc, *bounds);
-    if (rc) return rc;
-  }
-  return finish_call(ctx, mem, st);
-}

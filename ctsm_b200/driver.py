@@ -24,15 +24,17 @@ ROUTINES = ("canopyfluxes", "soiltemperature", "soilfluxes", "patch2col", "plant
 PRE_ROUTINES = ("preflux", "surfacehumidity", "baregroundfluxes")
 # HydrologyNoDrainage's routines in front of the root-water sink (HydrologyNoDrainageMod.F90:297-337): with
 # them SoilWater's icefrac / eff_porosity / qflx_infl are produced on the device instead of being inputs
-HYDRO_ROUTINES = ("snowwater", "infiltration", "snowlayers")
-# HydrologyNoDrainage as far as it is built (HydrologyNoDrainageMod.F90:279-402): BuildSnowFilter, SnowWater, the infiltration chain,
-# the root-water sink, SoilWater, SnowCompaction / CombineSnowLayers / DivideSnowLayers / ZeroEmptySnowLayers, BuildSnowFilter
+HYDRO_ROUTINES = ("snowwater", "infiltration", "watertable", "snowlayers", "hydrodiag")
+# HydrologyNoDrainage as far as it is built (HydrologyNoDrainageMod.F90:279-757): BuildSnowFilter, SnowWater, the infiltration chain,
+# the root-water sink, SoilWater, PerchedWaterTable / ThetaBasedWaterTable / RenewCondensation, SnowCompaction / CombineSnowLayers /
+# DivideSnowLayers / ZeroEmptySnowLayers, BuildSnowFilter, the closing diagnostics (everything except SnowCapping)
 ROUTINES_HYDRO = ("canopyfluxes", "soiltemperature", "soilfluxes", "patch2col", "snowwater", "infiltration", "plantsink", "soilwater",
-                  "snowlayers", "balancecheck")
+                  "watertable", "snowlayers", "hydrodiag", "balancecheck")
 FILTER_OF = {"preflux": ("nolakec", "nolakep"), "surfacehumidity": ("nolakec",), "baregroundfluxes": ("noexposedvegp",),
              "canopyfluxes": ("exposedvegp",), "soiltemperature": ("nolakep", "nolakec"), "soilfluxes": ("nolakep", "nolakec"),
              "patch2col": ("allc", "nolakec"), "infiltration": ("nolakec", "hydrologyc"), "plantsink": ("hydrologyc",),
-             "snowwater": ("nolakec",), "snowlayers": ("nolakec",), "soilwater": ("hydrologyc",), "balancecheck": ("allc",)}
+             "snowwater": ("nolakec",), "snowlayers": ("nolakec",), "watertable": ("hydrologyc",),
+             "hydrodiag": ("nolakec", "hydrologyc"), "soilwater": ("hydrologyc",), "balancecheck": ("allc",)}
 
 
 class CtsmError(RuntimeError):
@@ -356,8 +358,30 @@ class HotPath:
             raise CtsmError(st, rc)
         self.filters.pop("snowc", None)            # snl has changed: the next user rebuilds the filter (:402)
 
+    def WaterTable(self):
+        """PerchedWaterTable, ThetaBasedWaterTable, RenewCondensation (HydrologyNoDrainageMod.F90:359-373)"""
+        st = abi.Status()
+        rc = self.ctx.L.ctsm_b200_water_table(
+            self.ctx.h, C.byref(self.bounds), self.nfilter["hydrologyc"], abi.i32p(self.filters["hydrologyc"]), 0, None,
+            C.byref(self.structs["watertable"]), self.mem, C.byref(st))
+        if rc != 0:
+            raise CtsmError(st, rc)
+
+    def HydrologyDiagnostics(self):
+        """BuildSnowFilter (:402) + the diagnostics that close HydrologyNoDrainage (:420-757)"""
+        if "snowc" not in self.filters:
+            self.BuildSnowFilter()
+        st = abi.Status()
+        rc = self.ctx.L.ctsm_b200_hydrology_diagnostics(
+            self.ctx.h, C.byref(self.bounds), self.nfilter["nolakec"], abi.i32p(self.filters["nolakec"]),
+            self.nfilter["snowc"], abi.i32p(self.filters["snowc"]), self.nfilter["nosnowc"], abi.i32p(self.filters["nosnowc"]),
+            self.nfilter["hydrologyc"], abi.i32p(self.filters["hydrologyc"]), 0, None,
+            C.byref(self.structs["hydrodiag"]), self.mem, C.byref(st))
+        if rc != 0:
+            raise CtsmError(st, rc)
+
     def call(self, g):
-        {"snowwater": self.SnowWater, "snowlayers": self.SnowLayers, "infiltration": self.HydrologyInfiltration, "preflux": self.BiogeophysPreFluxCalcs, "surfacehumidity": self.CalculateSurfaceHumidity, "baregroundfluxes": self.BareGroundFluxes,
+        {"watertable": self.WaterTable, "hydrodiag": self.HydrologyDiagnostics, "snowwater": self.SnowWater, "snowlayers": self.SnowLayers, "infiltration": self.HydrologyInfiltration, "preflux": self.BiogeophysPreFluxCalcs, "surfacehumidity": self.CalculateSurfaceHumidity, "baregroundfluxes": self.BareGroundFluxes,
          "canopyfluxes": self.CanopyFluxes, "soiltemperature": self.SoilTemperature, "soilwater": self.SoilWater,
          "plantsink": self.VertTranSink, "balancecheck": self.BalanceCheck, "soilfluxes": self.SoilFluxes, "patch2col": self.Patch2Col}[g]()
 

@@ -521,6 +521,37 @@ def snow_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator) 
         S[k] = np.ascontiguousarray(v)
 
 
+def watertable_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator) -> None:
+    """Inputs of PerchedWaterTable / ThetaBasedWaterTable / RenewCondensation and of the diagnostics that close HydrologyNoDrainage
+    (SURVEY.md 8f rank 3).  A third of the columns get nearly saturated layers below a random depth, so that the water tables are
+    found by interpolation between layers (perched above a frozen layer, and the theta-based one above bedrock); a few per cent
+    lose exactly their top-layer ice to sublimation (truncated to zero by RenewCondensation)."""
+    nc = sg.ncol
+    g = lambda lo, hi, *shape: rng.uniform(lo, hi, shape)
+    lo = 11                                                     # row of soil level 1 in SNOSOI arrays is lo + 1
+    dz, liq, ice = S["dz"], S["h2osoi_liq"], S["h2osoi_ice"]
+    wet = np.nonzero(rng.random(nc) < 0.35)[0]
+    ktop = rng.integers(2, 16, size=len(wet))
+    for c, k0 in zip(wet, ktop):
+        for k in range(int(k0), 21):
+            ratio = rng.uniform(0.91, 0.995)
+            need = ratio * S["watsat"][k - 1, c] - ice[lo + k, c] / (dz[lo + k, c] * 917.0)
+            if need > 0.0:
+                liq[lo + k, c] = need * dz[lo + k, c] * 1000.0
+    S["h2osoi_vol"] = g(0.05, 0.5, 25, nc)
+    S["snow_persistence"] = g(0.0, 1.0e6, nc)
+    nosnow = np.nonzero(S["snl"] == 0)[0]
+    exact = nosnow[rng.random(len(nosnow)) < 0.05]
+    S["qflx_soliddew_to_top_layer"][exact] = 0.0
+    S["qflx_solidevap_from_top_layer"][exact] = ice[lo + 1, exact] / (1800.0 * (1.0 - S["frac_h2osfc"][exact]))
+    for grp in ("watertable", "hydrodiag"):
+        for fs_ in abi_fields(grp):
+            if fs_.name not in S and fs_.ctype == "double":
+                S[fs_.name] = np.full(nc if fs_.lev == "L1" else (fs_.nlev, nc), 1.0e36)
+    for k, v in list(S.items()):
+        S[k] = np.ascontiguousarray(v)
+
+
 def make_ensemble(sg: Subgrid, S: Dict[str, np.ndarray], nmember: int, rng: np.random.Generator, spread: float = 0.2):
     """Perturbed-parameter ensemble through the PFT tables (BASELINE config 5): the grid is split into `nmember` equal
     runs of gridcells, member m's patches get itype = m*(mxpft+1) + pft, and every pft_* table is extended to

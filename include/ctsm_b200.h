@@ -254,6 +254,20 @@ typedef struct ctsm_snowlayers_fields_t {
 #undef CTSM_FIELDS_SNOWLAYERS
 } ctsm_snowlayers_fields_t;
 
+typedef struct ctsm_watertable_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_WATERTABLE
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_WATERTABLE
+} ctsm_watertable_fields_t;
+
+typedef struct ctsm_hydrodiag_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_HYDRODIAG
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_HYDRODIAG
+} ctsm_hydrodiag_fields_t;
+
 typedef struct ctsm_soilfluxes_fields_t {
   ctsm_bounds_t alloc;
 #define CTSM_FIELDS_SOILFLUXES
@@ -532,6 +546,19 @@ int ctsm_b200_snow_water(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int nu
  * filter are refused (CTSM_ERR_URBAN / CTSM_ERR_BAD_ARG). */
 int ctsm_b200_snow_layers(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_snowc, const int32_t* filter_snowc,
                           const ctsm_snowlayers_fields_t* f, int mem, ctsm_status_t* st);
+
+/* PerchedWaterTable, ThetaBasedWaterTable, RenewCondensation over filter_hydrologyc: the call sequence
+ * HydrologyNoDrainageMod.F90:359-373 (use_aquifer_layer = .false.; SoilHydrologyMod.F90:1525, :1933, :2569).  num_urbanc must be 0.
+ * Fails with CTSM_ERR_SNOW_NEGATIVE (info = 2) where RenewCondensation calls endrun ("h2osoi_ice has gone significantly negative"). */
+int ctsm_b200_water_table(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_hydrologyc, const int32_t* filter_hydrologyc,
+                          int num_urbanc, const int32_t* filter_urbanc, const ctsm_watertable_fields_t* f, int mem, ctsm_status_t* st);
+
+/* The column diagnostics HydrologyNoDrainage computes inline after its second BuildSnowFilter (HydrologyNoDrainageMod.F90:420-757).
+ * filter_snowc / filter_nosnowc are the new snow filters; num_urbanc must be 0. */
+int ctsm_b200_hydrology_diagnostics(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_nolakec, const int32_t* filter_nolakec,
+                                    int num_snowc, const int32_t* filter_snowc, int num_nosnowc, const int32_t* filter_nosnowc,
+                                    int num_hydrologyc, const int32_t* filter_hydrologyc, int num_urbanc, const int32_t* filter_urbanc,
+                                    const ctsm_hydrodiag_fields_t* f, int mem, ctsm_status_t* st);
 
 /* Compute_EffecRootFrac_And_VertTranSink_Default(bounds, num_filterc, filterc, ...): SoilWaterPlantSinkMod.F90:332-424,
  * what Compute_EffecRootFrac_And_VertTranSink (:18-142) calls for every column class when use_hydrstress = .false. */

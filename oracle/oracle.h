@@ -74,6 +74,12 @@ int oracle_bare_ground_fluxes(const ctsm_params_t* prm, const ctsm_bounds_t* bou
 int oracle_hydrology_infiltration(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_nolakec,
                                   const int32_t* filter_nolakec, int num_hydrologyc, const int32_t* filter_hydrologyc,
                                   int num_urbanc, const ctsm_infiltration_fields_t* f, ctsm_status_t* st);
+int oracle_water_table(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_hydrologyc, const int32_t* filter_hydrologyc,
+                       int num_urbanc, const ctsm_watertable_fields_t* f, ctsm_status_t* st);
+int oracle_hydrology_diagnostics(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_nolakec, const int32_t* filter_nolakec,
+                                 int num_snowc, const int32_t* filter_snowc, int num_nosnowc, const int32_t* filter_nosnowc,
+                                 int num_hydrologyc, const int32_t* filter_hydrologyc, int num_urbanc,
+                                 const ctsm_hydrodiag_fields_t* f, ctsm_status_t* st);
 /* oracle_snow.c: the snow routines of HydrologyNoDrainage */
 void oracle_snow_dz_limits(const ctsm_params_t* prm, double* dzmin, double* dzmax_l, double* dzmax_u);
 void oracle_build_snow_filter(int num_nolakec, const int32_t* filter_nolakec, const int32_t* snl, int begc0,

@@ -163,6 +163,9 @@ def _bind(L):
     L.oracle_build_snow_filter.restype = None
     L.oracle_snow_water.argtypes = [P, B, C.c_int, i32p, C.c_int, i32p, C.POINTER(abi.STRUCTS["snowwater"]), C.POINTER(abi.Status)]
     L.oracle_snow_layers.argtypes = [P, B, C.c_int, i32p, C.POINTER(abi.STRUCTS["snowlayers"]), C.POINTER(abi.Status)]
+    L.oracle_water_table.argtypes = [P, B, C.c_int, i32p, C.c_int, C.POINTER(abi.STRUCTS["watertable"]), C.POINTER(abi.Status)]
+    L.oracle_hydrology_diagnostics.argtypes = [P, B, C.c_int, i32p, C.c_int, i32p, C.c_int, i32p, C.c_int, i32p, C.c_int,
+                                               C.POINTER(abi.STRUCTS["hydrodiag"]), C.POINTER(abi.Status)]
     L.oracle_vert_tran_sink_default.argtypes = [B, C.c_int, i32p, C.POINTER(abi.STRUCTS["plantsinkdefault"])]
     L.oracle_set_plantsink_default.argtypes = [C.POINTER(abi.STRUCTS["plantsinkdefault"])]
     L.oracle_set_plantsink_default.restype = None

@@ -137,3 +137,164 @@ def test_step_with_infiltration_feeds_soilwater(oracle_lib):
     worst = compare_step_fields(sg, S, got, ref, np.zeros(sg.npatch, dtype=bool), routines)
     assert np.array_equal(got["num_substeps"], ref["num_substeps"])
     print("infiltration -> sink -> SoilWater worst:", sorted(worst.items(), key=lambda kv: -kv[1])[:4])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# PerchedWaterTable / ThetaBasedWaterTable / RenewCondensation, the closing diagnostics, and HydrologyNoDrainage as a whole
+from tests.test_oracle_hydrology import wt_case, run_water_table, run_diagnostics   # noqa: E402
+
+
+def _gpu(L, ctx, group, sg, S, mem, filters, call):
+    st = abi.Status()
+    z = np.zeros(1, dtype=np.int32)
+    filters = [f if len(f) else z for f in filters]
+    if mem == abi.MEM_DEVICE:
+        D = to_device(group_arrays(S, group))
+        f = abi.make_struct(group, D, sg.bounds)
+        rc = call(f, [to_device({"f": v})["f"] for v in filters], st)
+        if rc == 0:
+            rc = L.ctsm_b200_sync(ctx, C.byref(st))
+        for k, v in D.items():
+            S[k][...] = v.cpu().numpy()
+    else:
+        f = abi.make_struct(group, S, sg.bounds)
+        rc = call(f, filters, st)
+    return rc, st
+
+
+def gpu_water_table(L, ctx, sg, S, mem, fh, bounds=None):
+    b = C.byref(bounds if bounds is not None else sg.bounds)
+    return _gpu(L, ctx, "watertable", sg, S, mem, [fh], lambda f, fl, st: L.ctsm_b200_water_table(
+        ctx, b, len(fh), abi.i32p(fl[0]), 0, None, C.byref(f), mem, C.byref(st)))
+
+
+def gpu_diagnostics(L, ctx, sg, S, mem, fn, fs, fns, fh, bounds=None):
+    b = C.byref(bounds if bounds is not None else sg.bounds)
+    return _gpu(L, ctx, "hydrodiag", sg, S, mem, [fn, fs, fns, fh], lambda f, fl, st: L.ctsm_b200_hydrology_diagnostics(
+        ctx, b, len(fn), abi.i32p(fl[0]), len(fs), abi.i32p(fl[1]), len(fns), abi.i32p(fl[2]), len(fh), abi.i32p(fl[3]), 0, None,
+        C.byref(f), mem, C.byref(st)))
+
+
+@pytest.mark.parametrize("mem", [abi.MEM_DEVICE, abi.MEM_HOST])
+def test_water_table_bit_exact(oracle_lib, mem):
+    """no transcendentals in the three routines: every field identical to the oracle's, bit for bit"""
+    L = abi.lib()
+    sg, S = wt_case(6000, 731)
+    prm = abi.default_params()
+    ref, got = copy_state(S), copy_state(S)
+    rc, st = run_water_table(oracle_lib, prm, sg, ref)
+    assert rc == 0
+    fh = sg.filters["hydrologyc"]
+    ctx = C.c_void_p()
+    assert L.ctsm_b200_init(C.byref(prm), C.byref(ctx)) == 0
+    try:
+        if mem == abi.MEM_HOST:                                  # clump by clump, bounds != alloc
+            for kb, fl in driver.make_slabs(sg, 3):
+                rc, st = gpu_water_table(L, ctx, sg, got, mem, fl["hydrologyc"], bounds=kb)
+                assert rc == 0, st.msg
+        else:
+            rc, st = gpu_water_table(L, ctx, sg, got, mem, fh)
+            assert rc == 0, st.msg
+        for f in abi.FIELDS["watertable"]:
+            assert np.array_equal(got[f.name], ref[f.name], equal_nan=True), f.name
+        bad = copy_state(S)
+        bare = fh[S["snl"][fh - 1] == 0]
+        bad["qflx_solidevap_from_top_layer"][bare[5] - 1] = 10.0
+        rc, st = gpu_water_table(L, ctx, sg, bad, mem, fh)
+        assert rc == 18 and st.subgrid_index == bare[5] and b"RenewCondensation" in st.msg
+        rc, st = gpu_water_table(L, ctx, sg, copy_state(S), mem, fh[:0])
+        assert rc == 0
+    finally:
+        L.ctsm_b200_finalize(ctx)
+    assert (ref["zwt_perched"][fh - 1] != ref["frost_table"][fh - 1]).sum() > 100
+
+
+@pytest.mark.parametrize("mem", [abi.MEM_DEVICE, abi.MEM_HOST])
+def test_hydrology_diagnostics_match_oracle(oracle_lib, mem):
+    from tests.test_oracle_snow import snow_filters
+    L = abi.lib()
+    sg, S = wt_case(6000, 741)
+    S["dz"][12, ::7] = 0.1
+    prm = abi.default_params()
+    fs, fns = snow_filters(oracle_lib, sg, S)
+    fn, fh = sg.filters["nolakec"], sg.filters["hydrologyc"]
+    ref, got = copy_state(S), copy_state(S)
+    rc, st = run_diagnostics(oracle_lib, prm, sg, ref, fs, fns)
+    assert rc == 0
+    ctx = C.c_void_p()
+    assert L.ctsm_b200_init(C.byref(prm), C.byref(ctx)) == 0
+    try:
+        if mem == abi.MEM_HOST:
+            for kb, fl in driver.make_slabs(sg, 3):
+                cut = lambda a: a[(a >= kb.begc) & (a <= kb.endc)]
+                rc, st = gpu_diagnostics(L, ctx, sg, got, mem, fl["nolakec"], cut(fs), cut(fns), fl["hydrologyc"], bounds=kb)
+                assert rc == 0, st.msg
+        else:
+            rc, st = gpu_diagnostics(L, ctx, sg, got, mem, fn, fs, fns, fh)
+            assert rc == 0, st.msg
+    finally:
+        L.ctsm_b200_finalize(ctx)
+    worst = {}
+    for f in abi.FIELDS["hydrodiag"]:
+        a, b = got[f.name], ref[f.name]
+        if f.intent == "IN":
+            assert np.array_equal(a, S[f.name], equal_nan=True), f.name
+        elif f.name in ("soilpsi", "smp_l", "wf", "wf2"):        # pow
+            fin = np.abs(b) < 1e30
+            assert np.array_equal(fin, np.abs(a) < 1e30), f.name
+            worst[f.name] = float(np.max(np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), 1e-300)))
+            assert worst[f.name] <= RTOL, (f.name, worst[f.name])
+        else:
+            assert np.array_equal(a, b, equal_nan=True), f.name
+    print("hydrology diagnostics worst:", worst)
+
+
+def test_hydrology_no_drainage_device_resident(oracle_lib):
+    """HydrologyNoDrainage as far as it is built, in the reference's order (HydrologyNoDrainageMod.F90:279-757): BuildSnowFilter,
+    SnowWater, infiltration chain, root-water sink, SoilWater, water tables + RenewCondensation, snow-layer update, BuildSnowFilter,
+    diagnostics - device-resident through driver.HotPath against the same sequence of the oracle."""
+    import torch
+    from tests.test_oracle_snow import snow_filters, run_snow_water, run_snow_layers
+    sg, S = wt_case(3000, 751)
+    prm = abi.default_params()
+    fh = sg.filters["hydrologyc"]
+    ref = copy_state(S)
+    fs, fns = snow_filters(oracle_lib, sg, ref)
+    st = abi.Status()
+    assert run_snow_water(oracle_lib, prm, sg, ref, fs, fns)[0] == 0
+    assert run_infiltration(oracle_lib, prm, sg, ref) == 0
+    fsk = abi.make_struct("plantsink", ref, sg.bounds)
+    assert oracle_lib.oracle_vert_tran_sink_hydstress(C.byref(sg.bounds), len(fh), abi.i32p(fh), C.byref(fsk)) == 0
+    fw = abi.make_struct("soilwater", ref, sg.bounds)
+    assert oracle_lib.oracle_soilwater(C.byref(prm), C.byref(sg.bounds), len(fh), abi.i32p(fh), C.byref(fw), C.byref(st)) == 0
+    assert run_water_table(oracle_lib, prm, sg, ref)[0] == 0
+    assert run_snow_layers(oracle_lib, prm, sg, ref, fs)[0] == 0
+    fs2, fns2 = snow_filters(oracle_lib, sg, ref)
+    assert run_diagnostics(oracle_lib, prm, sg, ref, fs2, fns2)[0] == 0
+    routines = ("snowwater", "infiltration", "plantsink", "soilwater", "watertable", "snowlayers", "hydrodiag")
+    ctx = driver.Context(prm)
+    try:
+        names = sorted({f.name for g in routines for f in abi.FIELDS[g]})
+        D = {k: torch.from_numpy(np.ascontiguousarray(S[k])).cuda() for k in names}
+        driver.HotPath(ctx, sg, D, abi.MEM_DEVICE, routines).step()
+        ctx.sync()
+        got = {k: (D[k].cpu().numpy() if k in D else S[k]) for k in S}
+    finally:
+        ctx.close()
+    assert np.array_equal(got["snl"], ref["snl"]) and np.array_equal(got["num_substeps"], ref["num_substeps"])
+    worst = {}
+    for g in routines:
+        for f in abi.FIELDS[g]:
+            if f.intent == "IN" or f.ctype == "int":
+                continue
+            a, b = got[f.name], ref[f.name]
+            fin = np.abs(b) < 1e30
+            assert np.array_equal(fin, np.abs(a) < 1e30), f.name
+            if not fin.any():
+                continue
+            scale = float(np.max(np.abs(b[fin])))
+            e = float(np.max(np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), 1e-6 * scale + 1e-300)))
+            worst[f.name] = max(worst.get(f.name, 0.0), e)
+    bad = {k: v for k, v in worst.items() if not v <= RTOL}
+    print("HydrologyNoDrainage worst:", sorted(worst.items(), key=lambda kv: -kv[1])[:6])
+    assert not bad, bad
