@@ -34,24 +34,42 @@ METRIC = "column_timesteps_per_sec"
 UNIT = "column-steps/s"
 PRE_ROUTINES = ("preflux", "surfacehumidity", "baregroundfluxes")     # clm_driver.F90:680, 702, 711
 ALL_ROUTINES = ("canopyfluxes", "soiltemperature", "soilfluxes", "patch2col", "plantsink", "soilwater", "balancecheck")   # clm_drv order
+# the rest of HydrologyNoDrainage around the sink and SoilWater (HydrologyNoDrainageMod.F90:279-757): `--routines hydro,...`
+HYDRO_ROUTINES = ("snowwater", "infiltration", "watertable", "snowcapping", "snowlayers", "hydrodiag")
+FULL_ORDER = PRE_ROUTINES + ("canopyfluxes", "soiltemperature", "soilfluxes", "patch2col", "snowwater", "infiltration", "plantsink", "soilwater",
+                             "watertable", "snowcapping", "snowlayers", "hydrodiag", "balancecheck")
 KERNEL_OF = {"plantsink": "plantsink_kernel", "soilfluxes": "soilfluxes_patch_kernel + soilfluxes_p2c_kernel", "patch2col": "patch2col_kernel<false/true>", "balancecheck": "balance_col/grc/patch/loc kernels",
              "canopyfluxes": "CanopyFluxes kernel chain of one call (init, then per ITERATION pass close/fric/leaf, "
                              "phs_ci x4, phs_newton x4, phs_end; final) - largest member: phs_newton_kernel",
              "soiltemperature": "soiltemp_kernel", "soilwater": "soilwater_kernel"}
 KERNEL_OF.update({"preflux": "preflux_patch_a / preflux_col / preflux_patch_b kernels", "surfacehumidity": "surface_humidity_kernel",
                   "baregroundfluxes": "bareground_kernel + bareground_colcopy_kernel"})
-NAME_OF = {"preflux": "BiogeophysPreFluxCalcs", "surfacehumidity": "CalculateSurfaceHumidity", "baregroundfluxes": "BareGroundFluxes",
+KERNEL_OF.update({"snowwater": "aerosol_dep_kernel + snow_water_kernel", "infiltration": "floodc_kernel + infiltration_kernel",
+                  "watertable": "water_table_kernel", "snowcapping": "snow_capping_init_kernel + snow_capping_kernel",
+                  "snowlayers": "snow_layers_kernel", "hydrodiag": "hydrodiag_nolake / snowdp / snow / soil kernels"})
+NAME_OF = {"snowwater": "BuildSnowFilter+SnowWater", "infiltration": "SetSoilWaterFractions..TotalSurfaceRunoff",
+           "watertable": "PerchedWaterTable+ThetaBasedWaterTable+RenewCondensation", "snowcapping": "SnowCapping",
+           "snowlayers": "SnowCompaction+CombineSnowLayers+DivideSnowLayers+ZeroEmptySnowLayers",
+           "hydrodiag": "BuildSnowFilter+HydrologyNoDrainage diagnostics",
+           "preflux": "BiogeophysPreFluxCalcs", "surfacehumidity": "CalculateSurfaceHumidity", "baregroundfluxes": "BareGroundFluxes",
            "canopyfluxes": "CanopyFluxes", "soiltemperature": "SoilTemperature", "soilwater": "SoilWater",
            "plantsink": "VertTranSink_HydStress", "balancecheck": "BalanceCheck", "soilfluxes": "SoilFluxes", "patch2col": "clm_drv_patch2col"}
 
 
-def make_workload(size, seed):
+def make_workload(size, seed, hydro=False):
     """Synthetic subgrid + state of every routine of the step (SURVEY.md 8d generators)."""
     from ctsm_b200 import synthetic_canopy
     sg, S = synthetic_canopy.make_full_case(size, seed=seed)
     synthetic_canopy.balance_state(sg, S, np.random.Generator(np.random.PCG64(seed + 1)), 1.0e-11)
     synthetic_canopy.soilfluxes_state(sg, S, np.random.Generator(np.random.PCG64(seed + 2)))
     synthetic_canopy.preflux_state(sg, S, np.random.Generator(np.random.PCG64(seed + 3)))     # own generator: adds fields only
+    if hydro:                                               # inputs of the HydrologyNoDrainage routines (own generators as well)
+        synthetic_canopy.hydrology_state(sg, S, np.random.Generator(np.random.PCG64(seed + 4)))
+        synthetic_canopy.snow_state(sg, S, np.random.Generator(np.random.PCG64(seed + 5)))
+        synthetic_canopy.watertable_state(sg, S, np.random.Generator(np.random.PCG64(seed + 6)), saturate=False)
+        S["topo"] = np.random.Generator(np.random.PCG64(seed + 7)).uniform(0.0, 3000.0, sg.ncol)
+        for k in ("qflx_snwcp_ice", "qflx_snwcp_liq", "qflx_snwcp_discarded_ice", "qflx_snwcp_discarded_liq"):
+            S[k] = np.full(sg.ncol, 1.0e36)
     return sg, S
 
 
@@ -212,8 +230,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     size = a.size if not a.size.isdigit() else int(a.size)
     # --routines names a subset of the step; "pre" (or the three names) adds the routines clm_drv runs before CanopyFluxes
-    want = a.routines.replace("pre,", ",".join(PRE_ROUTINES) + ",").split(",")
-    routines = tuple(g for g in PRE_ROUTINES + ALL_ROUTINES if g in want)
+    want = a.routines.replace("pre,", ",".join(PRE_ROUTINES) + ",").replace("hydro,", ",".join(HYDRO_ROUTINES) + ",").split(",")
+    routines = tuple(g for g in FULL_ORDER if g in want)
     strong = a.scaling == "strong" or world == 1
     from ctsm_b200 import synthetic
     members_local = a.members
@@ -263,7 +281,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     prm = abi.default_params(device=local_rank)
-    sg, S = make_workload(local_size, 20260101 + 1000 * rank)
+    sg, S = make_workload(local_size, 20260101 + 1000 * rank, hydro=any(g in HYDRO_ROUTINES for g in routines))
     if a.members > 1:
         # config 5: members = contiguous gridcell ranges; PFT tables per member (medlynslope, kmax, psi50, ck, krmax perturbed)
         # and per-member scalars e_ice, csoilc, cv, a_coef, z_dl

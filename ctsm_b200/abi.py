@@ -111,7 +111,8 @@ class Params(C.Structure):
                     "overburden_compress_Tfactor", "int_snow_max", "wimp", "ssi", "drift_gs", "eta0_anderson", "eta0_vionnet",
                     "rho_max", "tau_ref", "ceta", "snw_rds_min", "upplim_destruct_metamorph", "scvng_fct_mlt_sf",
                     "scvng_fct_mlt_bcphi", "scvng_fct_mlt_bcpho", "scvng_fct_mlt_dst1", "scvng_fct_mlt_dst2", "scvng_fct_mlt_dst3",
-                    "scvng_fct_mlt_dst4")]
+                    "scvng_fct_mlt_dst4", "h2osno_max", "reset_snow_glc_ela")] + [
+                ("reset_snow", C.c_int32), ("reset_snow_glc", C.c_int32)]
 
 
 def default_params(dtime: float = 1800.0, device: int = 0) -> Params:
@@ -325,6 +326,8 @@ def lib():
     L.ctsm_b200_build_snow_filter.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, i32p, C.c_int, C.c_int, i32p, i32p, i32p, i32p, C.c_int]
     L.ctsm_b200_snow_water.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p, C.POINTER(STRUCTS["snowwater"]), C.c_int,
                                        C.POINTER(Status)]
+    L.ctsm_b200_snow_capping.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p, C.POINTER(STRUCTS["snowcapping"]), C.c_int, C.c_int,
+                                         C.POINTER(Status)]
     L.ctsm_b200_snow_layers.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.POINTER(STRUCTS["snowlayers"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_water_table.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p, C.POINTER(STRUCTS["watertable"]), C.c_int,
                                         C.POINTER(Status)]
@@ -351,7 +354,7 @@ def lib():
     L.ctsm_b200_set_soil_tuning.argtypes = [vp, C.c_int]
     L.ctsm_b200_set_soilwater_tuning.argtypes = [vp, C.c_int]
     for fn in ("vert_tran_sink_hydstress", "vert_tran_sink_default", "biogeophys_pre_flux_calcs", "calculate_surface_humidity",
-               "bare_ground_fluxes", "hydrology_infiltration", "build_snow_filter", "snow_water", "snow_layers", "water_table", "hydrology_diagnostics", "balancecheck_init", "balancecheck", "soilfluxes", "patch2col"):
+               "bare_ground_fluxes", "hydrology_infiltration", "build_snow_filter", "snow_water", "snow_capping", "snow_layers", "water_table", "hydrology_diagnostics", "balancecheck_init", "balancecheck", "soilfluxes", "patch2col"):
         getattr(L, "ctsm_b200_" + fn).restype = C.c_int
     for fn in ("init", "finalize", "sync", "host_register", "host_unregister", "tridiagonal", "banddiagonal",
                "dgtsv_batch", "soilwater", "soiltemperature", "canopyfluxes", "set_exposedvegp_filter"):

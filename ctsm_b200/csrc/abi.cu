@@ -231,6 +231,8 @@ void decode_status(const DevStatus& ds, ctsm_status_t* st) {
   else st->subgrid_level = (st->code == CTSM_ERR_FORC_HGT || st->code == CTSM_ERR_GS_NEG || st->code == CTSM_ERR_BRENT ||
                        st->code == CTSM_ERR_QUADRATIC || st->code == CTSM_ERR_RH) ? CTSM_SUBGRID_PATCH : CTSM_SUBGRID_COLUMN;
   snprintf(st->msg, sizeof st->msg, "%s", message_for(st->code));
+  if (st->code == CTSM_ERR_SNOW_NEGATIVE && info == 3)
+    snprintf(st->msg, sizeof st->msg, "ERROR: capping procedure failed (negative mass remaining)");
   if (st->code == CTSM_ERR_SNOW_NEGATIVE && info == 2)
     snprintf(st->msg, sizeof st->msg, "In RenewCondensation, h2osoi_ice has gone significantly negative");
   if (st->code == CTSM_ERR_SNOW_NEGATIVE && info == 1)

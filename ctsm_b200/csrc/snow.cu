@@ -36,6 +36,14 @@ struct SnowLayersDev {
 #undef CTSM_F
 };
 
+struct SnowCappingDev {
+#define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) ctype* name;
+#define CTSM_FIELDS_SNOWCAPPING
+#include "../../include/ctsm_b200_fields.def"
+#undef CTSM_FIELDS_SNOWCAPPING
+#undef CTSM_F
+};
+
 namespace {
 using namespace cst;
 constexpr int NS = CTSM_NLEVSNO;
@@ -176,6 +184,67 @@ snow_water_kernel(SnowWaterDev f, SnowGeo geo, SnowWaterPrm prm, int num_snowc, 
   f.int_snow[cc] = f.int_snow[cc] + fse * (q_sdew + q_ldew + q_liq_grnd) * dtime;
   f.qflx_snow_drain[cc] = f.qflx_snow_drain[cc] + q;
   f.qflx_rain_plus_snomelt[cc] = q + (1.0 - fse) * q_liq_grnd;
+#undef OFF
+}
+
+// SnowCapping :3121-3247.  Two launches: the four capping fluxes are zeroed over filter_initc (InitFlux_SnowCapping), then one
+// thread per snow column sums its pack (CalculateTotalH2osno), finds the excess (SnowCappingExcess) and, where there is one,
+// removes it from the bottom layer (fluxes, state, thickness at constant ice density, aerosol masses).
+struct SnowCapPrm { double dtime, h2osno_max, reset_snow_glc_ela; int reset_snow, reset_snow_glc, reset_active; };
+
+__global__ void __launch_bounds__(256)
+snow_capping_init_kernel(SnowCappingDev f, int begc0, int numf, const int32_t* __restrict__ filterc) {
+  const int fc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fc >= numf) return;
+  const int cc = filterc[fc] - begc0;
+  f.qflx_snwcp_ice[cc] = 0.0; f.qflx_snwcp_liq[cc] = 0.0; f.qflx_snwcp_discarded_ice[cc] = 0.0; f.qflx_snwcp_discarded_liq[cc] = 0.0;
+}
+
+__global__ void __launch_bounds__(128)
+snow_capping_kernel(SnowCappingDev f, SnowCapPrm prm, int begc0, int ldc_, int numf, const int32_t* __restrict__ filterc, DevStatus* ds) {
+  const int fc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fc >= numf) return;
+  const int c1 = filterc[fc];
+  const int cc = c1 - begc0;
+  const size_t ldc = (size_t)ldc_;
+#define OFF(j) ((size_t)((j) - SLO) * ldc + cc)
+  const int snl = f.snl[cc], lt = f.lun_itype[cc];
+  double h2osno = f.h2osno_no_layers[cc];
+  double ice0 = 0.0, liq0 = 0.0;
+  for (int j = snl + 1; j <= 0; ++j) {
+    ice0 = f.h2osoi_ice[OFF(j)]; liq0 = f.h2osoi_liq[OFF(j)];
+    h2osno = h2osno + ice0 + liq0;
+  }
+  double excess = 0.0;
+  bool apply_runoff = false;
+  if (h2osno > prm.h2osno_max) { excess = h2osno - prm.h2osno_max; apply_runoff = true; }
+  if (prm.reset_active) {                                                          // :3457-3471, reset_snow_h2osno = 35 mm
+    if ((lt != CTSM_ISTICE) && prm.reset_snow && (h2osno > 35.0)) { excess = h2osno - 35.0; apply_runoff = false; }
+    else if ((lt == CTSM_ISTICE) && prm.reset_snow_glc && (h2osno > 35.0) && (f.topo[cc] <= prm.reset_snow_glc_ela)) {
+      excess = h2osno - 35.0; apply_runoff = false;
+    }
+  }
+  if (!(excess > 0.0)) return;
+  // (ice0, liq0) = the bottom layer, the last one the loop read
+  const double dz0 = f.dz[OFF(0)];
+  const double rho_orig_bottom = ice0 / dz0;
+  const double mss_snow_bottom_lyr = ice0 + liq0;
+  const double mss_snwcp_tot = fmin(excess, mss_snow_bottom_lyr * (1.0 - 1.e-3));
+  const double icefrac = ice0 / mss_snow_bottom_lyr;
+  const double snwcp_flux_ice = mss_snwcp_tot / prm.dtime * icefrac;
+  const double snwcp_flux_liq = mss_snwcp_tot / prm.dtime * (1.0 - icefrac);
+  double q_ice = 0.0, q_liq = 0.0, qd_ice = 0.0, qd_liq = 0.0;
+  if (apply_runoff) { q_ice = snwcp_flux_ice; q_liq = snwcp_flux_liq; f.qflx_snwcp_ice[cc] = q_ice; f.qflx_snwcp_liq[cc] = q_liq; }
+  else { qd_ice = snwcp_flux_ice; qd_liq = snwcp_flux_liq; f.qflx_snwcp_discarded_ice[cc] = qd_ice; f.qflx_snwcp_discarded_liq[cc] = qd_liq; }
+  const double frac_adjust = (mss_snow_bottom_lyr - mss_snwcp_tot) / mss_snow_bottom_lyr;
+  const double ice1 = ice0 - (q_ice + qd_ice) * prm.dtime;
+  const double liq1 = liq0 - (q_liq + qd_liq) * prm.dtime;
+  f.h2osoi_ice[OFF(0)] = ice1; f.h2osoi_liq[OFF(0)] = liq1;
+  if (ice1 < 0.0 || liq1 < 0.0) { report_failure(ds, c1, CTSM_ERR_SNOW_NEGATIVE, 3); return; }
+  if (rho_orig_bottom > 1.0) f.dz[OFF(0)] = ice1 / rho_orig_bottom;
+  double* const mss[8] = {f.mss_bcphi, f.mss_bcpho, f.mss_ocphi, f.mss_ocpho, f.mss_dst1, f.mss_dst2, f.mss_dst3, f.mss_dst4};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) mss[k][OFF(0)] = mss[k][OFF(0)] * frac_adjust;
 #undef OFF
 }
 
@@ -593,6 +662,51 @@ extern "C" int ctsm_b200_snow_layers(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bo
   prm.method = p.snow_overburden_compaction_method; prm.wind = p.wind_dependent_snow_density; prm.subgrid = p.use_subgrid_fluxes;
   if (num_snowc > 0) {
     snow_layers_kernel<<<grid_for(num_snowc, 128), 128, 0, ctx->stream>>>(d, geo, prm, num_snowc, dfs, ctx->d_status);
+    ctx->launches++;
+  }
+  if (mem != CTSM_MEM_DEVICE) {
+    int rc = stage_end(ctx, fl, hf->alloc, *bounds);
+    if (rc) return rc;
+  }
+  return finish_call(ctx, mem, st);
+}
+
+extern "C" int ctsm_b200_snow_capping(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_initc, const int32_t* filter_initc,
+                                      int num_snowc, const int32_t* filter_snowc, const ctsm_snowcapping_fields_t* hf, int nstep,
+                                      int mem, ctsm_status_t* st) {
+  if (!ctx || !bounds || !hf || num_initc < 0 || num_snowc < 0 || (num_initc > 0 && !filter_initc) || (num_snowc > 0 && !filter_snowc))
+    return CTSM_ERR_BAD_ARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  SnowCappingDev d;
+  const int32_t *dfi = filter_initc, *dfs = filter_snowc;
+  std::vector<StageField> fl;
+#define CTSM_F(name, ctype, sub, lev, intent, us, usn, ref) \
+  d.name = hf->name;                                        \
+  fl.push_back(StageField{(void**)&d.name, (void*)hf->name, (int)sizeof(ctype), SUB_##sub, lev_shape(#lev).n, INTENT_##intent});
+#define CTSM_FIELDS_SNOWCAPPING
+#include "../../include/ctsm_b200_fields.def"
+#undef CTSM_FIELDS_SNOWCAPPING
+#undef CTSM_F
+  for (auto& s : fl) if (!s.host_ptr) return CTSM_ERR_BAD_ARG;
+  if (mem != CTSM_MEM_DEVICE) {
+    int rc = stage_begin(ctx, fl, hf->alloc, *bounds, mem == CTSM_MEM_HOST);
+    if (rc) return rc;
+    rc = stage_filter(ctx, ctx->arena_filter0, filter_initc, num_initc, &dfi);
+    if (rc) return rc;
+    rc = stage_filter(ctx, ctx->arena_filter1, filter_snowc, num_snowc, &dfs);
+    if (rc) return rc;
+  }
+  const ctsm_params_t& p = ctx->prm;
+  // SnowCappingExcess :3447-3454: reset_snow_timesteps_per_layer = 4
+  const int reset_active = ((p.reset_snow || p.reset_snow_glc) && nstep <= 4 * NS) ? 1 : 0;
+  const SnowCapPrm prm{p.dtime, p.h2osno_max, p.reset_snow_glc_ela, p.reset_snow, p.reset_snow_glc, reset_active};
+  const int begc0 = hf->alloc.begc, ldc = hf->alloc.endc - hf->alloc.begc + 1;
+  if (num_initc > 0) {
+    snow_capping_init_kernel<<<grid_for(num_initc, 256), 256, 0, ctx->stream>>>(d, begc0, num_initc, dfi);
+    ctx->launches++;
+  }
+  if (num_snowc > 0) {
+    snow_capping_kernel<<<grid_for(num_snowc, 128), 128, 0, ctx->stream>>>(d, prm, begc0, ldc, num_snowc, dfs, ctx->d_status);
     ctx->launches++;
   }
   if (mem != CTSM_MEM_DEVICE) {

@@ -24,17 +24,17 @@ ROUTINES = ("canopyfluxes", "soiltemperature", "soilfluxes", "patch2col", "plant
 PRE_ROUTINES = ("preflux", "surfacehumidity", "baregroundfluxes")
 # HydrologyNoDrainage's routines in front of the root-water sink (HydrologyNoDrainageMod.F90:297-337): with
 # them SoilWater's icefrac / eff_porosity / qflx_infl are produced on the device instead of being inputs
-HYDRO_ROUTINES = ("snowwater", "infiltration", "watertable", "snowlayers", "hydrodiag")
+HYDRO_ROUTINES = ("snowwater", "infiltration", "watertable", "snowcapping", "snowlayers", "hydrodiag")
 # HydrologyNoDrainage as far as it is built (HydrologyNoDrainageMod.F90:279-757): BuildSnowFilter, SnowWater, the infiltration chain,
 # the root-water sink, SoilWater, PerchedWaterTable / ThetaBasedWaterTable / RenewCondensation, SnowCompaction / CombineSnowLayers /
-# DivideSnowLayers / ZeroEmptySnowLayers, BuildSnowFilter, the closing diagnostics (everything except SnowCapping)
+# SnowCapping, SnowCompaction / CombineSnowLayers / DivideSnowLayers / ZeroEmptySnowLayers, BuildSnowFilter, the closing diagnostics
 ROUTINES_HYDRO = ("canopyfluxes", "soiltemperature", "soilfluxes", "patch2col", "snowwater", "infiltration", "plantsink", "soilwater",
-                  "watertable", "snowlayers", "hydrodiag", "balancecheck")
+                  "watertable", "snowcapping", "snowlayers", "hydrodiag", "balancecheck")
 FILTER_OF = {"preflux": ("nolakec", "nolakep"), "surfacehumidity": ("nolakec",), "baregroundfluxes": ("noexposedvegp",),
              "canopyfluxes": ("exposedvegp",), "soiltemperature": ("nolakep", "nolakec"), "soilfluxes": ("nolakep", "nolakec"),
              "patch2col": ("allc", "nolakec"), "infiltration": ("nolakec", "hydrologyc"), "plantsink": ("hydrologyc",),
              "snowwater": ("nolakec",), "snowlayers": ("nolakec",), "watertable": ("hydrologyc",),
-             "hydrodiag": ("nolakec", "hydrologyc"), "soilwater": ("hydrologyc",), "balancecheck": ("allc",)}
+             "hydrodiag": ("nolakec", "hydrologyc"), "snowcapping": ("nolakec",), "soilwater": ("hydrologyc",), "balancecheck": ("allc",)}
 
 
 class CtsmError(RuntimeError):
@@ -319,12 +319,18 @@ class HotPath:
         n = self.nfilter["nolakec"]
         na, nb = C.c_int32(0), C.c_int32(0)
         snl = self.arrays["snl"]
-        if self.mem == abi.MEM_DEVICE:
-            import torch
-            a = torch.zeros(max(n, 1), dtype=torch.int32, device="cuda")
-            b = torch.zeros(max(n, 1), dtype=torch.int32, device="cuda")
-        else:
-            a, b = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+        bufs = self.filters.get("_snowbufs")                  # the two output lists live as long as the clump (no per-step allocation)
+        if bufs is None:
+            if self.mem == abi.MEM_DEVICE:
+                import torch
+                # torch fills on ITS stream; the library's stream is non-blocking, so an asynchronous fill could land after the
+                # library has written the lists: allocate without a fill and drain torch's stream once
+                bufs = (torch.empty(max(n, 1), dtype=torch.int32, device="cuda"), torch.empty(max(n, 1), dtype=torch.int32, device="cuda"))
+                torch.cuda.current_stream().synchronize()
+            else:
+                bufs = (np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32))
+            self.filters["_snowbufs"] = bufs
+        a, b = bufs
         rc = self.ctx.L.ctsm_b200_build_snow_filter(
             self.ctx.h, C.byref(self.bounds), n, abi.i32p(self.filters["nolakec"]), abi.i32p(snl), self.sg.bounds.begc,
             self.sg.bounds.endc, abi.i32p(a), C.byref(na), abi.i32p(b), C.byref(nb), abi.MEM_DEVICE if self.mem == abi.MEM_DEVICE else abi.MEM_HOST)
@@ -342,6 +348,17 @@ class HotPath:
         rc = self.ctx.L.ctsm_b200_snow_water(
             self.ctx.h, C.byref(self.bounds), self.nfilter["snowc"], abi.i32p(self.filters["snowc"]), self.nfilter["nosnowc"],
             abi.i32p(self.filters["nosnowc"]), C.byref(self.structs["snowwater"]), self.mem, C.byref(st))
+        if rc != 0:
+            raise CtsmError(st, rc)
+
+    def SnowCapping(self, nstep: int = 1000):
+        """SnowCapping over (filter_nolakec, filter_snowc), HydrologyNoDrainageMod.F90:377 (SnowHydrologyMod.F90:3121)"""
+        if "snowc" not in self.filters:
+            self.BuildSnowFilter()
+        st = abi.Status()
+        rc = self.ctx.L.ctsm_b200_snow_capping(
+            self.ctx.h, C.byref(self.bounds), self.nfilter["nolakec"], abi.i32p(self.filters["nolakec"]), self.nfilter["snowc"],
+            abi.i32p(self.filters["snowc"]), C.byref(self.structs["snowcapping"]), int(nstep), self.mem, C.byref(st))
         if rc != 0:
             raise CtsmError(st, rc)
 
@@ -381,7 +398,7 @@ class HotPath:
             raise CtsmError(st, rc)
 
     def call(self, g):
-        {"watertable": self.WaterTable, "hydrodiag": self.HydrologyDiagnostics, "snowwater": self.SnowWater, "snowlayers": self.SnowLayers, "infiltration": self.HydrologyInfiltration, "preflux": self.BiogeophysPreFluxCalcs, "surfacehumidity": self.CalculateSurfaceHumidity, "baregroundfluxes": self.BareGroundFluxes,
+        {"snowcapping": self.SnowCapping, "watertable": self.WaterTable, "hydrodiag": self.HydrologyDiagnostics, "snowwater": self.SnowWater, "snowlayers": self.SnowLayers, "infiltration": self.HydrologyInfiltration, "preflux": self.BiogeophysPreFluxCalcs, "surfacehumidity": self.CalculateSurfaceHumidity, "baregroundfluxes": self.BareGroundFluxes,
          "canopyfluxes": self.CanopyFluxes, "soiltemperature": self.SoilTemperature, "soilwater": self.SoilWater,
          "plantsink": self.VertTranSink, "balancecheck": self.BalanceCheck, "soilfluxes": self.SoilFluxes, "patch2col": self.Patch2Col}[g]()
 

@@ -521,7 +521,7 @@ def snow_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator) 
         S[k] = np.ascontiguousarray(v)
 
 
-def watertable_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator) -> None:
+def watertable_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator, saturate: bool = True) -> None:
     """Inputs of PerchedWaterTable / ThetaBasedWaterTable / RenewCondensation and of the diagnostics that close HydrologyNoDrainage
     (SURVEY.md 8f rank 3).  A third of the columns get nearly saturated layers below a random depth, so that the water tables are
     found by interpolation between layers (perched above a frozen layer, and the theta-based one above bedrock); a few per cent
@@ -530,8 +530,8 @@ def watertable_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Gener
     g = lambda lo, hi, *shape: rng.uniform(lo, hi, shape)
     lo = 11                                                     # row of soil level 1 in SNOSOI arrays is lo + 1
     dz, liq, ice = S["dz"], S["h2osoi_liq"], S["h2osoi_ice"]
-    wet = np.nonzero(rng.random(nc) < 0.35)[0]
-    ktop = rng.integers(2, 16, size=len(wet))
+    wet = np.nonzero(rng.random(nc) < (0.35 if saturate else 0.0))[0]       # (saturate = False: for steps that also run SoilWater,
+    ktop = rng.integers(2, 16, size=len(wet))                              # whose adaptive solve is ill-conditioned on saturated layers)
     for c, k0 in zip(wet, ktop):
         for k in range(int(k0), 21):
             ratio = rng.uniform(0.91, 0.995)

@@ -171,6 +171,10 @@ typedef struct ctsm_params_t {
   double  wimp, ssi, drift_gs, eta0_anderson, eta0_vionnet, rho_max, tau_ref, ceta, snw_rds_min, upplim_destruct_metamorph;
   double  scvng_fct_mlt_sf, scvng_fct_mlt_bcphi, scvng_fct_mlt_bcpho, scvng_fct_mlt_dst1, scvng_fct_mlt_dst2,
           scvng_fct_mlt_dst3, scvng_fct_mlt_dst4;
+  /* SnowCapping: clm_varcon h2osno_max (namelist, 10000 mm for the standard structure), clm_snowhydrology_inparm reset_snow /
+   * reset_snow_glc / reset_snow_glc_ela (SnowHydrologyMod.F90:160-179) */
+  double  h2osno_max, reset_snow_glc_ela;
+  int32_t reset_snow, reset_snow_glc;
 } ctsm_params_t;
 
 typedef struct ctsm_b200_ctx ctsm_b200_ctx;
@@ -253,6 +257,13 @@ typedef struct ctsm_snowlayers_fields_t {
 #include "ctsm_b200_fields.def"
 #undef CTSM_FIELDS_SNOWLAYERS
 } ctsm_snowlayers_fields_t;
+
+typedef struct ctsm_snowcapping_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_SNOWCAPPING
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_SNOWCAPPING
+} ctsm_snowcapping_fields_t;
 
 typedef struct ctsm_watertable_fields_t {
   ctsm_bounds_t alloc;
@@ -540,6 +551,15 @@ int ctsm_b200_build_snow_filter(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds,
 int ctsm_b200_snow_water(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_snowc, const int32_t* filter_snowc,
                          int num_nosnowc, const int32_t* filter_nosnowc, const ctsm_snowwater_fields_t* f, int mem,
                          ctsm_status_t* st);
+
+/* SnowCapping(bounds, num_initc, filter_initc, num_snowc, filter_snowc, topo_inst, aerosol_inst, water_inst):
+ * SnowHydrologyMod.F90:3121-3247 (InitFlux_SnowCapping :3250, BulkFlux_SnowCappingFluxes :3288 with SnowCappingExcess :3397 and
+ * CalculateTotalH2osno WaterStateType.F90:887-897, UpdateState_RemoveSnowCappingFluxes :3575, SnowCappingUpdateDzAndAerosols
+ * :3623); HydrologyNoDrainageMod.F90:377.  nstep = get_nstep() (the snow reset of reset_snow / reset_snow_glc is active during the
+ * first 4 * nlevsno steps).  Fails with CTSM_ERR_SNOW_NEGATIVE (info = 3) on "capping procedure failed (negative mass remaining)". */
+int ctsm_b200_snow_capping(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_initc, const int32_t* filter_initc,
+                           int num_snowc, const int32_t* filter_snowc, const ctsm_snowcapping_fields_t* f, int nstep, int mem,
+                           ctsm_status_t* st);
 
 /* SnowCompaction, CombineSnowLayers, DivideSnowLayers(is_lake = .false.), ZeroEmptySnowLayers over filter_snowc: the call
  * sequence HydrologyNoDrainageMod.F90:381-399 (SnowHydrologyMod.F90:1870, :2083, :2510, :2898).  Lake and urban columns in the

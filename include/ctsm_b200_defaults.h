@@ -66,6 +66,7 @@ static inline void ctsm_default_params_fill(ctsm_params_t* p) {
   p->rho_max = 350.0; p->tau_ref = 172800.0; p->ceta = 250.0; p->snw_rds_min = 54.526; p->upplim_destruct_metamorph = 175.0;
   p->scvng_fct_mlt_sf = 1.0; p->scvng_fct_mlt_bcphi = 0.20; p->scvng_fct_mlt_bcpho = 0.03;
   p->scvng_fct_mlt_dst1 = 0.02; p->scvng_fct_mlt_dst2 = 0.02; p->scvng_fct_mlt_dst3 = 0.01; p->scvng_fct_mlt_dst4 = 0.01;
+  p->h2osno_max = 10000.0; p->reset_snow = 0; p->reset_snow_glc = 0; p->reset_snow_glc_ela = 1.e9;   // namelist_defaults_ctsm.xml:517,546-551
   p->balance_skip_steps = -1;
   p->npft_table = CTSM_MXPFT + 1;
 }

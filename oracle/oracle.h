@@ -86,6 +86,8 @@ void oracle_build_snow_filter(int num_nolakec, const int32_t* filter_nolakec, co
                               int32_t* filter_snowc, int32_t* num_snowc, int32_t* filter_nosnowc, int32_t* num_nosnowc);
 int oracle_snow_water(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_snowc, const int32_t* filter_snowc,
                       int num_nosnowc, const int32_t* filter_nosnowc, const ctsm_snowwater_fields_t* f, ctsm_status_t* st);
+int oracle_snow_capping(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_initc, const int32_t* filter_initc,
+                        int num_snowc, const int32_t* filter_snowc, const ctsm_snowcapping_fields_t* f, int nstep, ctsm_status_t* st);
 int oracle_snow_layers(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_snowc, const int32_t* filter_snowc,
                        const ctsm_snowlayers_fields_t* f, ctsm_status_t* st);
 int oracle_vert_tran_sink_default(const ctsm_bounds_t* bounds, int num_filterc, const int32_t* filterc,

@@ -578,3 +578,64 @@ int oracle_snow_layers(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, in
   return 0;
 #undef MS
 }
+
+/* SnowCapping :3121-3247 with InitFlux_SnowCapping :3273-3283, CalculateTotalH2osno WaterStateType.F90:887-897,
+ * SnowCappingExcess :3425-3472, BulkFlux_SnowCappingFluxes :3344-3392, UpdateState_RemoveSnowCappingFluxes :3601-3618,
+ * SnowCappingUpdateDzAndAerosols :3668-3691.  Bulk water only. */
+int oracle_snow_capping(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_initc, const int32_t* filter_initc,
+                        int num_snowc, const int32_t* filter_snowc, const ctsm_snowcapping_fields_t* f, int nstep, ctsm_status_t* st) {
+  (void)bounds;
+  if (st) memset(st, 0, sizeof *st);
+  const int begc0 = f->alloc.begc;
+  const size_t ldc = (size_t)(f->alloc.endc - f->alloc.begc + 1);
+  const double dtime = prm->dtime;
+  const double reset_snow_h2osno = 35.0, min_snow_to_keep = 1.e-3;
+  const int reset_snow_timesteps_per_layer = 4;
+  double* mss[8] = {f->mss_bcphi, f->mss_bcpho, f->mss_ocphi, f->mss_ocpho, f->mss_dst1, f->mss_dst2, f->mss_dst3, f->mss_dst4};
+  for (int fc = 0; fc < num_initc; ++fc) {
+    const int c = filter_initc[fc];
+    CC(qflx_snwcp_ice, c) = 0.0; CC(qflx_snwcp_liq, c) = 0.0; CC(qflx_snwcp_discarded_ice, c) = 0.0; CC(qflx_snwcp_discarded_liq, c) = 0.0;
+  }
+  int is_reset_snow_active = 0;
+  if (prm->reset_snow || prm->reset_snow_glc) {
+    const int reset_snow_timesteps = reset_snow_timesteps_per_layer * NSNO;
+    if (nstep <= reset_snow_timesteps) is_reset_snow_active = 1;
+  }
+  for (int fc = 0; fc < num_snowc; ++fc) {
+    const int c = filter_snowc[fc], lt = CC(lun_itype, c);
+    double h2osno = CC(h2osno_no_layers, c);
+    for (int j = CC(snl, c) + 1; j <= 0; ++j) h2osno = h2osno + CS(h2osoi_ice, c, j) + CS(h2osoi_liq, c, j);
+    double excess = 0.0;
+    int apply_runoff = 0;
+    if (h2osno > prm->h2osno_max) { excess = h2osno - prm->h2osno_max; apply_runoff = 1; }
+    if (is_reset_snow_active) {
+      if ((lt != CTSM_ISTICE) && prm->reset_snow && (h2osno > reset_snow_h2osno)) {
+        excess = h2osno - reset_snow_h2osno; apply_runoff = 0;
+      } else if ((lt == CTSM_ISTICE) && prm->reset_snow_glc && (h2osno > reset_snow_h2osno) && (CC(topo, c) <= prm->reset_snow_glc_ela)) {
+        excess = h2osno - reset_snow_h2osno; apply_runoff = 0;
+      }
+    }
+    if (!(excess > 0.0)) continue;
+    const double rho_orig_bottom = CS(h2osoi_ice, c, 0) / CS(dz, c, 0);
+    const double mss_snow_bottom_lyr = CS(h2osoi_ice, c, 0) + CS(h2osoi_liq, c, 0);
+    const double mss_snwcp_tot = fmin(excess, mss_snow_bottom_lyr * (1.0 - min_snow_to_keep));
+    const double icefrac = CS(h2osoi_ice, c, 0) / mss_snow_bottom_lyr;
+    const double snwcp_flux_ice = mss_snwcp_tot / dtime * icefrac;
+    const double snwcp_flux_liq = mss_snwcp_tot / dtime * (1.0 - icefrac);
+    if (apply_runoff) { CC(qflx_snwcp_ice, c) = snwcp_flux_ice; CC(qflx_snwcp_liq, c) = snwcp_flux_liq; }
+    else { CC(qflx_snwcp_discarded_ice, c) = snwcp_flux_ice; CC(qflx_snwcp_discarded_liq, c) = snwcp_flux_liq; }
+    const double frac_adjust = (mss_snow_bottom_lyr - mss_snwcp_tot) / mss_snow_bottom_lyr;
+    CS(h2osoi_ice, c, 0) = CS(h2osoi_ice, c, 0) - (CC(qflx_snwcp_ice, c) + CC(qflx_snwcp_discarded_ice, c)) * dtime;
+    CS(h2osoi_liq, c, 0) = CS(h2osoi_liq, c, 0) - (CC(qflx_snwcp_liq, c) + CC(qflx_snwcp_discarded_liq, c)) * dtime;
+    if (CS(h2osoi_ice, c, 0) < 0.0 || CS(h2osoi_liq, c, 0) < 0.0) {
+      if (st) {
+        st->code = CTSM_ERR_SNOW_NEGATIVE; st->subgrid_level = CTSM_SUBGRID_COLUMN; st->subgrid_index = c; st->info = 3;
+        snprintf(st->msg, sizeof st->msg, "ERROR: capping procedure failed (negative mass remaining)");
+      }
+      return CTSM_ERR_SNOW_NEGATIVE;
+    }
+    if (rho_orig_bottom > 1.0) CS(dz, c, 0) = CS(h2osoi_ice, c, 0) / rho_orig_bottom;
+    for (int k = 0; k < 8; ++k) mss[k][(size_t)(0 - SNO_LO) * ldc + (c - begc0)] = mss[k][(size_t)(0 - SNO_LO) * ldc + (c - begc0)] * frac_adjust;
+  }
+  return 0;
+}

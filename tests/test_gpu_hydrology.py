@@ -254,8 +254,15 @@ def test_hydrology_no_drainage_device_resident(oracle_lib):
     SnowWater, infiltration chain, root-water sink, SoilWater, water tables + RenewCondensation, snow-layer update, BuildSnowFilter,
     diagnostics - device-resident through driver.HotPath against the same sequence of the oracle."""
     import torch
-    from tests.test_oracle_snow import snow_filters, run_snow_water, run_snow_layers
-    sg, S = wt_case(3000, 751)
+    from tests.test_oracle_snow import snow_filters, run_snow_water, run_snow_layers, run_snow_capping
+    sg, S = wt_case(3000, 751, saturate=False)
+    rng = np.random.Generator(np.random.PCG64(752))
+    S["topo"] = rng.uniform(0.0, 3000.0, sg.ncol)
+    heavy = np.nonzero(S["snl"] < 0)[0][::9]                    # a few packs above h2osno_max
+    S["h2osoi_ice"][11, heavy] = 11000.0
+    S["dz"][11, heavy] = 11000.0 / 500.0
+    for k in ("qflx_snwcp_ice", "qflx_snwcp_liq", "qflx_snwcp_discarded_ice", "qflx_snwcp_discarded_liq"):
+        S[k] = np.full(sg.ncol, 1.0e36)
     prm = abi.default_params()
     fh = sg.filters["hydrologyc"]
     ref = copy_state(S)
@@ -268,10 +275,11 @@ def test_hydrology_no_drainage_device_resident(oracle_lib):
     fw = abi.make_struct("soilwater", ref, sg.bounds)
     assert oracle_lib.oracle_soilwater(C.byref(prm), C.byref(sg.bounds), len(fh), abi.i32p(fh), C.byref(fw), C.byref(st)) == 0
     assert run_water_table(oracle_lib, prm, sg, ref)[0] == 0
+    assert run_snow_capping(oracle_lib, prm, sg, ref, sg.filters["nolakec"], fs, 1000)[0] == 0
     assert run_snow_layers(oracle_lib, prm, sg, ref, fs)[0] == 0
     fs2, fns2 = snow_filters(oracle_lib, sg, ref)
     assert run_diagnostics(oracle_lib, prm, sg, ref, fs2, fns2)[0] == 0
-    routines = ("snowwater", "infiltration", "plantsink", "soilwater", "watertable", "snowlayers", "hydrodiag")
+    routines = ("snowwater", "infiltration", "plantsink", "soilwater", "watertable", "snowcapping", "snowlayers", "hydrodiag")
     ctx = driver.Context(prm)
     try:
         names = sorted({f.name for g in routines for f in abi.FIELDS[g]})

@@ -251,3 +251,43 @@ def test_snow_sequence_of_hydrology_no_drainage(oracle_lib):
         fin = np.abs(ref[k]) < 1e30
         e = np.max(np.abs(got[k][fin] - ref[k][fin]) / np.maximum(np.abs(ref[k][fin]), 1e-6 * np.max(np.abs(ref[k][fin]))))
         assert e <= RTOL, (k, e)
+
+
+@pytest.mark.parametrize("mem", [abi.MEM_DEVICE, abi.MEM_HOST])
+@pytest.mark.parametrize("reset,reset_glc,nstep", [(0, 0, 100), (1, 1, 10)], ids=["capping", "reset_active"])
+def test_snow_capping_bit_exact(oracle_lib, mem, reset, reset_glc, nstep):
+    """SnowCapping has no transcendentals: identical bits in every field"""
+    from tests.test_oracle_snow import capping_case, run_snow_capping
+    L = abi.lib()
+    sg, S = capping_case(5000, 961)
+    prm = abi.default_params()
+    prm.reset_snow, prm.reset_snow_glc, prm.reset_snow_glc_ela = reset, reset_glc, 1500.0
+    fs, _ = snow_filters(oracle_lib, sg, S)
+    fi = sg.filters["nolakec"]
+    ref, got = copy_state(S), copy_state(S)
+    rc, st = run_snow_capping(oracle_lib, prm, sg, ref, fi, fs, nstep)
+    assert rc == 0
+    ctx = C.c_void_p()
+    assert L.ctsm_b200_init(C.byref(prm), C.byref(ctx)) == 0
+    try:
+        def call(S_, fi_, fs_, bounds=None):
+            b = C.byref(bounds if bounds is not None else sg.bounds)
+            return gpu_call(L, ctx, "snowcapping", sg, S_, mem, [fi_, fs_], lambda f, fl, st: L.ctsm_b200_snow_capping(
+                ctx, b, len(fi_), abi.i32p(fl[0]), len(fs_), abi.i32p(fl[1]), C.byref(f), nstep, mem, C.byref(st)))
+        if mem == abi.MEM_HOST:
+            for kb, fl in driver.make_slabs(sg, 3):
+                rc, st = call(got, fl["nolakec"], fs[(fs >= kb.begc) & (fs <= kb.endc)], kb)
+                assert rc == 0, st.msg
+        else:
+            rc, st = call(got, fi, fs)
+            assert rc == 0, st.msg
+        for f in abi.FIELDS["snowcapping"]:
+            assert np.array_equal(got[f.name], ref[f.name], equal_nan=True), f.name
+        capped = ((ref["qflx_snwcp_ice"] > 0) & (ref["qflx_snwcp_ice"] < 1e30)) | ((ref["qflx_snwcp_discarded_ice"] > 0) & (ref["qflx_snwcp_discarded_ice"] < 1e30))
+        assert capped.sum() > 50
+        bad = copy_state(S)                                     # negative mass remaining: a bottom layer whose liquid is negative
+        bad["h2osoi_liq"][11, np.nonzero(capped)[0][3]] = -1.0
+        rc, st = call(bad, fi, fs)
+        assert rc == 18 and st.subgrid_index == np.nonzero(capped)[0][3] + 1 and b"capping procedure failed" in st.msg
+    finally:
+        L.ctsm_b200_finalize(ctx)

@@ -179,10 +179,10 @@ SAT_LEV = float(np.float32(0.9))            # a default-kind literal in both rou
 LO = 11                                      # row of soil level j in SNOSOI arrays: LO + j; in zi (SNOSOI0): LO + 1 + j
 
 
-def wt_case(n=800, seed=631):
+def wt_case(n=800, seed=631, saturate=True):
     from tests.test_oracle_snow import case as snow_case
     sg, S = snow_case(n, seed)
-    synthetic_canopy.watertable_state(sg, S, np.random.Generator(np.random.PCG64(seed + 6)))
+    synthetic_canopy.watertable_state(sg, S, np.random.Generator(np.random.PCG64(seed + 6)), saturate)
     return sg, S
 
 

@@ -274,3 +274,95 @@ def test_snow_layers_match_python_restatement(oracle_lib, method, wind, subgrid)
         nmerge += col["snl"] > S["snl"][c]
         nsplit += col["snl"] < S["snl"][c]
     assert nmerge > 30 and nsplit > 30
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# SnowCapping
+def capping_case(n=600, seed=881):
+    sg, S = case(n, seed)
+    rng = np.random.Generator(np.random.PCG64(seed + 9))
+    nc = sg.ncol
+    S["topo"] = rng.uniform(0.0, 3000.0, nc)
+    deep = np.nonzero((S["snl"] < 0) & (rng.random(nc) < 0.15))[0]          # packs above h2osno_max: a very heavy bottom layer
+    S["h2osoi_ice"][NSNO - 1, deep] = rng.uniform(9000.0, 14000.0, len(deep))
+    S["dz"][NSNO - 1, deep] = S["h2osoi_ice"][NSNO - 1, deep] / rng.uniform(300.0, 800.0, len(deep))
+    thin = deep[::4]                                                        # ... and some whose excess exceeds the bottom layer
+    S["h2osoi_ice"][NSNO - 1, thin] = 40.0
+    S["h2osoi_ice"][NSNO - 2, thin] = 12000.0
+    S["snl"][thin] = np.minimum(S["snl"][thin], -2)
+    for k in ("qflx_snwcp_ice", "qflx_snwcp_liq", "qflx_snwcp_discarded_ice", "qflx_snwcp_discarded_liq"):
+        S[k] = np.full(nc, 1.0e36)
+    return sg, S
+
+
+def run_snow_capping(OL, prm, sg, S, fi, fs, nstep=100, bounds=None):
+    st = abi.Status()
+    f = abi.make_struct("snowcapping", S, sg.bounds)
+    z = np.zeros(1, np.int32)
+    rc = OL.oracle_snow_capping(C.byref(prm), C.byref(bounds if bounds is not None else sg.bounds), len(fi), abi.i32p(fi if len(fi) else z),
+                                len(fs), abi.i32p(fs if len(fs) else z), C.byref(f), nstep, C.byref(st))
+    return rc, st
+
+
+def capping_np(prm, sg, S0, fi, fs, nstep):
+    """SnowHydrologyMod.F90:3121-3693 in NumPy (bulk water)"""
+    S = copy_state(S0)
+    ci, c = fi - 1, fs - 1
+    for k in ("qflx_snwcp_ice", "qflx_snwcp_liq", "qflx_snwcp_discarded_ice", "qflx_snwcp_discarded_liq"):
+        S[k][ci] = 0.0
+    tot = S["h2osno_no_layers"][c].copy()
+    for j in range(NSNO):                                       # CalculateTotalH2osno: top to bottom over the active layers
+        on = (j - NSNO + 1) >= S["snl"][c] + 1
+        tot = np.where(on, tot + S["h2osoi_ice"][j, c] + S["h2osoi_liq"][j, c], tot)
+    excess = np.where(tot > prm.h2osno_max, tot - prm.h2osno_max, 0.0)
+    runoff = tot > prm.h2osno_max
+    if (prm.reset_snow or prm.reset_snow_glc) and nstep <= 4 * NSNO:
+        ice_lu = S["lun_itype"][c] == 4
+        r1 = ~ice_lu & bool(prm.reset_snow) & (tot > 35.0)
+        r2 = ice_lu & bool(prm.reset_snow_glc) & (tot > 35.0) & (S["topo"][c] <= prm.reset_snow_glc_ela)
+        excess = np.where(r1 | r2, tot - 35.0, excess)
+        runoff = np.where(r1 | r2, False, runoff)
+    cap = excess > 0.0
+    cc, runoff, excess = c[cap], runoff[cap], excess[cap]
+    b = NSNO - 1
+    ice, liq = S["h2osoi_ice"][b, cc], S["h2osoi_liq"][b, cc]
+    rho = ice / S["dz"][b, cc]
+    m = ice + liq
+    take = np.minimum(excess, m * (1.0 - 1.e-3))
+    icefrac = ice / m
+    fi_, fl_ = take / prm.dtime * icefrac, take / prm.dtime * (1.0 - icefrac)
+    S["qflx_snwcp_ice"][cc] = np.where(runoff, fi_, 0.0)
+    S["qflx_snwcp_liq"][cc] = np.where(runoff, fl_, 0.0)
+    S["qflx_snwcp_discarded_ice"][cc] = np.where(runoff, 0.0, fi_)
+    S["qflx_snwcp_discarded_liq"][cc] = np.where(runoff, 0.0, fl_)
+    adj = (m - take) / m
+    S["h2osoi_ice"][b, cc] = ice - (S["qflx_snwcp_ice"][cc] + S["qflx_snwcp_discarded_ice"][cc]) * prm.dtime
+    S["h2osoi_liq"][b, cc] = liq - (S["qflx_snwcp_liq"][cc] + S["qflx_snwcp_discarded_liq"][cc]) * prm.dtime
+    S["dz"][b, cc] = np.where(rho > 1.0, S["h2osoi_ice"][b, cc] / rho, S["dz"][b, cc])
+    for a in AER:
+        S["mss_" + a][b, cc] = S["mss_" + a][b, cc] * adj
+    return S, cap.sum()
+
+
+@pytest.mark.parametrize("reset,reset_glc,nstep", [(0, 0, 100), (1, 1, 10), (1, 0, 100)], ids=["capping", "reset_active", "reset_expired"])
+def test_snow_capping_matches_numpy(oracle_lib, reset, reset_glc, nstep):
+    sg, S = capping_case()
+    prm = abi.default_params()
+    prm.reset_snow, prm.reset_snow_glc, prm.reset_snow_glc_ela = reset, reset_glc, 1500.0
+    fs, _ = snow_filters(oracle_lib, sg, S)
+    fi = sg.filters["nolakec"]
+    ref = copy_state(S)
+    rc, st = run_snow_capping(oracle_lib, prm, sg, ref, fi, fs, nstep)
+    assert rc == 0, st.msg
+    exp, ncap = capping_np(prm, sg, S, fi, fs, nstep)
+    for f in abi.FIELDS["snowcapping"]:
+        assert np.array_equal(ref[f.name], exp[f.name], equal_nan=True), f.name           # no transcendentals: identical bits
+    assert ncap > (200 if (reset and nstep <= 48) else 10)
+    c = fs - 1
+    # what leaves the pack is what the fluxes carry
+    w0 = (S["h2osoi_ice"][:NSNO, c] + S["h2osoi_liq"][:NSNO, c]).sum(0)
+    w1 = (ref["h2osoi_ice"][:NSNO, c] + ref["h2osoi_liq"][:NSNO, c]).sum(0)
+    out = (ref["qflx_snwcp_ice"][c] + ref["qflx_snwcp_liq"][c] + ref["qflx_snwcp_discarded_ice"][c] + ref["qflx_snwcp_discarded_liq"][c]) * prm.dtime
+    assert np.max(np.abs(w0 - w1 - out) / w0) < 1e-12
+    if not reset:
+        assert np.all(ref["qflx_snwcp_discarded_ice"][c] == 0.0) and (ref["qflx_snwcp_ice"][c] > 0).sum() == ncap
