@@ -323,6 +323,9 @@ def lib():
                                                C.POINTER(STRUCTS["baregroundfluxes"]), C.c_int, C.POINTER(Status)]
     L.ctsm_b200_hydrology_infiltration.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p, C.c_int, i32p,
                                                    C.POINTER(STRUCTS["infiltration"]), C.c_int, C.POINTER(Status)]
+    L.ctsm_b200_calc_ozone_uptake.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.POINTER(STRUCTS["ozone"]), C.c_int, C.POINTER(Status)]
+    L.ctsm_b200_calc_ozone_stress.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p, C.c_int, C.c_int, C.POINTER(STRUCTS["ozone"]),
+                                              C.c_int, C.POINTER(Status)]
     L.ctsm_b200_build_snow_filter.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, i32p, C.c_int, C.c_int, i32p, i32p, i32p, i32p, C.c_int]
     L.ctsm_b200_snow_water.argtypes = [vp, C.POINTER(Bounds), C.c_int, i32p, C.c_int, i32p, C.POINTER(STRUCTS["snowwater"]), C.c_int,
                                        C.POINTER(Status)]
@@ -354,7 +357,7 @@ def lib():
     L.ctsm_b200_set_soil_tuning.argtypes = [vp, C.c_int]
     L.ctsm_b200_set_soilwater_tuning.argtypes = [vp, C.c_int]
     for fn in ("vert_tran_sink_hydstress", "vert_tran_sink_default", "biogeophys_pre_flux_calcs", "calculate_surface_humidity",
-               "bare_ground_fluxes", "hydrology_infiltration", "build_snow_filter", "snow_water", "snow_capping", "snow_layers", "water_table", "hydrology_diagnostics", "balancecheck_init", "balancecheck", "soilfluxes", "patch2col"):
+               "bare_ground_fluxes", "hydrology_infiltration", "calc_ozone_uptake", "calc_ozone_stress", "build_snow_filter", "snow_water", "snow_capping", "snow_layers", "water_table", "hydrology_diagnostics", "balancecheck_init", "balancecheck", "soilfluxes", "patch2col"):
         getattr(L, "ctsm_b200_" + fn).restype = C.c_int
     for fn in ("init", "finalize", "sync", "host_register", "host_unregister", "tridiagonal", "banddiagonal",
                "dgtsv_batch", "soilwater", "soiltemperature", "canopyfluxes", "set_exposedvegp_filter"):

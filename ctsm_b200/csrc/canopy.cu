@@ -2444,7 +2444,20 @@ extern "C" int ctsm_b200_set_exposedvegp_filter(ctsm_b200_ctx* ctx, const ctsm_b
 extern "C" int ctsm_b200_build_snow_filter(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_nolakec, const int32_t* filter_nolakec,
                                            const int32_t* snl, int alloc_begc, int alloc_endc, int32_t* filter_snowc, int32_t* num_snowc,
                                            int32_t* filter_nosnowc, int32_t* num_nosnowc, int mem) {
-  if (!bounds || alloc_endc < alloc_begc) return CTSM_ERR_BAD_ARG;
+  if (!ctx || !bounds || !snl || alloc_endc < alloc_begc) return CTSM_ERR_BAD_ARG;
+  // Inside a resident window the host copy of col%snl may be stale (the snow-layer update has written it on the device and its
+  // download is still in flight): where the device mirror of the array is fresh over the call bounds, the split reads the mirror.
+  if (mem != CTSM_MEM_DEVICE && ctx->window_open) {
+    auto it = ctx->mirrors.find((const void*)snl);
+    if (it != ctx->mirrors.end() && it->second.d) {
+      bool covered = false;
+      for (const auto& iv : it->second.fresh)
+        if (iv.first <= bounds->begc && iv.second >= bounds->endc) { covered = true; break; }
+      if (covered)
+        return split_filter(ctx, alloc_begc, alloc_endc, -1, num_nolakec, filter_nolakec, (const int32_t*)it->second.d, filter_snowc,
+                            num_snowc, filter_nosnowc, num_nosnowc, CTSM_MEM_HOST | 0x100);
+    }
+  }
   return split_filter(ctx, alloc_begc, alloc_endc, -1, num_nolakec, filter_nolakec, snl, filter_snowc, num_snowc, filter_nosnowc,
                       num_nosnowc, mem);
 }
@@ -2456,11 +2469,13 @@ static int split_filter(ctsm_b200_ctx* ctx, int beg, int end, int sign, int num_
       (num_nolakeurbanp > 0 && (!filter_nolakeurbanp || !filter_exposedvegp || !filter_noexposedvegp)))
     return CTSM_ERR_BAD_ARG;
   CUDA_TRY(cudaSetDevice(ctx->device));
+  const bool flag_on_device = (mem & 0x100) != 0;            // (host lists, device flags: ctsm_b200_build_snow_filter inside a window)
+  mem &= 0xff;
   const int n = num_nolakeurbanp;
   *num_exposedvegp = 0; *num_noexposedvegp = 0;
   if (n == 0) return CTSM_OK;
   cudaStream_t s = ctx->stream;
-  const int np = end - beg + 1;
+  const int np = flag_on_device ? 0 : end - beg + 1;
   const int nblocks = grid_for(n, SPLIT_BLOCK * SPLIT_ITEMS);
   const int32_t *dfilt = filter_nolakeurbanp, *dfv = frac_veg_nosno;
   int32_t *dyes = filter_exposedvegp, *dno = filter_noexposedvegp;
@@ -2475,8 +2490,8 @@ static int split_filter(ctsm_b200_ctx* ctx, int beg, int end, int sign, int num_
     int32_t* c = ip; ip += n;
     int32_t* e = ip; ip += np;
     CUDA_TRY(cudaMemcpyAsync(a, filter_nolakeurbanp, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(e, frac_veg_nosno, sizeof(int32_t) * (size_t)np, cudaMemcpyHostToDevice, s));
-    dfilt = a; dyes = b; dno = c; dfv = e;
+    if (!flag_on_device) CUDA_TRY(cudaMemcpyAsync(e, frac_veg_nosno, sizeof(int32_t) * (size_t)np, cudaMemcpyHostToDevice, s));
+    dfilt = a; dyes = b; dno = c; dfv = flag_on_device ? frac_veg_nosno : e;
   }
   split_count_kernel<<<nblocks, SPLIT_BLOCK, 0, s>>>(n, dfilt, dfv, beg, sign, blockc);
   split_scan_kernel<<<1, 1024, 0, s>>>(nblocks, blockc, total);

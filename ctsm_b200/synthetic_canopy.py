@@ -552,6 +552,27 @@ def watertable_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Gener
         S[k] = np.ascontiguousarray(v)
 
 
+def ozone_state(sg: Subgrid, S: Dict[str, np.ndarray], rng: np.random.Generator) -> None:
+    """Inputs of CalcOzoneUptake / CalcOzoneStress (OzoneMod.F90): ozone mixing ratio, the accumulated doses,
+    last step's LAI, the three PFT flags.  Resistances CanopyFluxes has not produced yet (spval before a step) get plausible values."""
+    npch, ng = sg.npatch, sg.ngrc
+    g = lambda lo, hi, *shape: rng.uniform(lo, hi, shape)
+    S["forc_o3"] = g(5.0e-9, 9.0e-8, ng)
+    for nm, (lo, hi) in {"rssun": (40.0, 2.0e4), "rssha": (40.0, 2.0e4), "rb1": (5.0, 150.0), "ram1": (5.0, 300.0)}.items():
+        S[nm] = np.where(np.abs(S[nm]) < 1e30, S[nm], g(lo, hi, npch))
+    S["tlai_old"] = S["tlai"] * g(0.8, 1.2, npch)
+    for nm in ("o3uptakesha", "o3uptakesun"):
+        S[nm] = np.where(rng.random(npch) < 0.2, 0.0, g(0.0, 60.0, npch))
+    nt = len(S["pft_z0v_LAImax"])
+    S["pft_evergreen"] = (rng.random(nt) < 0.4).astype(np.float64)
+    S["pft_leaf_long"] = g(0.5, 6.0, nt)
+    S["pft_woody"] = (rng.random(nt) < 0.5).astype(np.float64)
+    for nm in ("o3coefvsha", "o3coefvsun", "o3coefgsha", "o3coefgsun", "o3coefjmaxsha", "o3coefjmaxsun"):
+        S[nm] = np.full(npch, 1.0e36)
+    for k, v in list(S.items()):
+        S[k] = np.ascontiguousarray(v)
+
+
 def make_ensemble(sg: Subgrid, S: Dict[str, np.ndarray], nmember: int, rng: np.random.Generator, spread: float = 0.2):
     """Perturbed-parameter ensemble through the PFT tables (BASELINE config 5): the grid is split into `nmember` equal
     runs of gridcells, member m's patches get itype = m*(mxpft+1) + pft, and every pft_* table is extended to

@@ -244,6 +244,13 @@ typedef struct ctsm_infiltration_fields_t {
 #undef CTSM_FIELDS_INFILTRATION
 } ctsm_infiltration_fields_t;
 
+typedef struct ctsm_ozone_fields_t {
+  ctsm_bounds_t alloc;
+#define CTSM_FIELDS_OZONE
+#include "ctsm_b200_fields.def"
+#undef CTSM_FIELDS_OZONE
+} ctsm_ozone_fields_t;
+
 typedef struct ctsm_snowwater_fields_t {
   ctsm_bounds_t alloc;
 #define CTSM_FIELDS_SNOWWATER
@@ -536,6 +543,17 @@ int ctsm_b200_hydrology_infiltration(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bo
                                      int num_hydrologyc, const int32_t* filter_hydrologyc,
                                      int num_urbanc, const int32_t* filter_urbanc,
                                      const ctsm_infiltration_fields_t* f, int mem, ctsm_status_t* st);
+
+/* ozone_inst%CalcOzoneUptake(bounds, num_exposedvegp, filter_exposedvegp, forc_pbot, forc_th, rssun, rssha, rb, ram, tlai, forc_o3):
+ * OzoneMod.F90:356-511, the call CanopyFluxes makes at CanopyFluxesMod.F90:1690 (the host's CanopyFluxes body issues it right after
+ * ctsm_b200_canopyfluxes, whose outputs rssun / rssha / rb1 / ram1 it reads).  dtime is the integer get_step_size() of the reference. */
+int ctsm_b200_calc_ozone_uptake(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_exposedvegp, const int32_t* filter_exposedvegp,
+                                const ctsm_ozone_fields_t* f, int mem, ctsm_status_t* st);
+/* ozone_inst%CalcOzoneStress(bounds, num_exposedvegp, filter_exposedvegp, num_noexposedvegp, filter_noexposedvegp): OzoneMod.F90:514-782
+ * (clm_driver.F90:690).  stress_method: 1 = Lombardozzi2015 (o3coefv / o3coefg), 2 = Falk (o3coefjmax; only when is_time_to_run_luna). */
+int ctsm_b200_calc_ozone_stress(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_exposedvegp, const int32_t* filter_exposedvegp,
+                                int num_noexposedvegp, const int32_t* filter_noexposedvegp, int stress_method, int is_time_to_run_luna,
+                                const ctsm_ozone_fields_t* f, int mem, ctsm_status_t* st);
 
 /* BuildSnowFilter(bounds, num_nolakec, filter_nolakec, num_snowc, filter_snowc, num_nosnowc, filter_nosnowc):
  * SnowHydrologyMod.F90:3975-4010, called at HydrologyNoDrainageMod.F90:279 and :402.  Order-preserving split of filter_nolakec

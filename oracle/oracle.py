@@ -164,6 +164,8 @@ def _bind(L):
     L.oracle_snow_water.argtypes = [P, B, C.c_int, i32p, C.c_int, i32p, C.POINTER(abi.STRUCTS["snowwater"]), C.POINTER(abi.Status)]
     L.oracle_snow_capping.argtypes = [P, B, C.c_int, i32p, C.c_int, i32p, C.POINTER(abi.STRUCTS["snowcapping"]), C.c_int, C.POINTER(abi.Status)]
     L.oracle_snow_layers.argtypes = [P, B, C.c_int, i32p, C.POINTER(abi.STRUCTS["snowlayers"]), C.POINTER(abi.Status)]
+    L.oracle_calc_ozone_uptake.argtypes = [P, B, C.c_int, i32p, C.POINTER(abi.STRUCTS["ozone"]), C.POINTER(abi.Status)]
+    L.oracle_calc_ozone_stress.argtypes = [B, C.c_int, i32p, C.c_int, i32p, C.c_int, C.c_int, C.POINTER(abi.STRUCTS["ozone"]), C.POINTER(abi.Status)]
     L.oracle_water_table.argtypes = [P, B, C.c_int, i32p, C.c_int, C.POINTER(abi.STRUCTS["watertable"]), C.POINTER(abi.Status)]
     L.oracle_hydrology_diagnostics.argtypes = [P, B, C.c_int, i32p, C.c_int, i32p, C.c_int, i32p, C.c_int, i32p, C.c_int,
                                                C.POINTER(abi.STRUCTS["hydrodiag"]), C.POINTER(abi.Status)]
