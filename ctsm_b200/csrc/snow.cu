@@ -267,7 +267,10 @@ __device__ __forceinline__ void combo(double& dz, double& wliq, double& wice, do
   dz = dzc; wice = wicec; wliq = wliqc; t = tc;
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef SNOW_LAYERS_BLOCKS
+#define SNOW_LAYERS_BLOCKS 4      // resident blocks per SM: 128 registers, 16 warps per SM (2 blocks: 252 registers)
+#endif
+__global__ void __launch_bounds__(128, SNOW_LAYERS_BLOCKS)
 snow_layers_kernel(SnowLayersDev f, SnowGeo geo, SnowLayersPrm prm, int num_snowc, const int32_t* __restrict__ filter_snowc,
                    DevStatus* ds) {
   const int fc = blockIdx.x * blockDim.x + threadIdx.x;
