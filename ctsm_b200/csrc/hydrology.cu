@@ -125,7 +125,7 @@ infiltration_kernel(InfilDev f, InfilPrm prm, int begc0, int ldc_, int numf, con
   } else {
     qflx_h2osfc_surf = 0.0;
   }
-  if (qflx_h2osfc_surf < 1.0e-8) qflx_h2osfc_surf = 0.0;
+  if (qflx_h2osfc_surf < R4(1.0e-8f)) qflx_h2osfc_surf = 0.0;              // SurfaceWaterMod.F90:499: a default-kind (REAL(4)) literal
   f.qflx_h2osfc_surf[cc] = qflx_h2osfc_surf;
   double h2osfc_partial = h2osfc0 + (qflx_in_h2osfc - qflx_h2osfc_surf) * dtime;
   h2osfc_partial = truncate_small(h2osfc_partial, h2osfc0);

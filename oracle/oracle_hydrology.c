@@ -139,7 +139,7 @@ int oracle_hydrology_infiltration(const ctsm_params_t* prm, const ctsm_bounds_t*
     } else {
       CC(qflx_h2osfc_surf, c) = 0.0;
     }
-    if (CC(qflx_h2osfc_surf, c) < 1.0e-8) CC(qflx_h2osfc_surf, c) = 0.0;
+    if (CC(qflx_h2osfc_surf, c) < (double)1.0e-8f) CC(qflx_h2osfc_surf, c) = 0.0;     /* :499, a default-kind literal: REAL(4) 1.0e-8 */
   }
   for (int fc = 0; fc < num_hydrologyc; ++fc) {                       /* :394-397 */
     const int c = filter_hydrologyc[fc];

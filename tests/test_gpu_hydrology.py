@@ -74,6 +74,9 @@ def test_infiltration_matches_oracle(oracle_lib, mem, h2osfcflag, crop0):
         L.ctsm_b200_finalize(ctx)
     worst = {}
     compare(got, ref, S, worst)
+    ck = sg.filters["hydrologyc"][5] - 1                         # SurfaceWaterMod.F90:499's REAL(4) 1.0e-8: this column keeps its runoff
+    if h2osfcflag:
+        assert 9.99999994e-9 < got["qflx_h2osfc_surf"][ck] < 1.0e-8
     print("infiltration chain worst:", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
 
 

@@ -16,6 +16,14 @@ DENICE = 917.0
 def case(n=800, seed=601, wet_every=3):
     sg, S = preflux_case(n, seed, wet_every)
     synthetic_canopy.hydrology_state(sg, S, np.random.Generator(np.random.PCG64(seed + 4)))
+    # one column whose surface-water runoff falls between REAL(4) 1.0e-8 (= 9.99999994e-9, what SurfaceWaterMod.F90:499 compares
+    # with) and the double 1.0e-8: it keeps its runoff (pc = 0.4, mu = 0.13889: the defaults)
+    ck = sg.filters["hydrologyc"][5] - 1
+    S["frac_h2osfc_nosnow"][ck], S["topo_slope"][ck] = 1.0, 30.0
+    kw = 1.0e-4 * np.sin((np.pi / 180.0) * 30.0) * (1.0 - 0.4) ** 0.13889
+    S["h2osfc_thresh"][ck] = 1.0
+    S["h2osfc"][ck] = 1.0 + 9.99999997e-9 / kw
+    S["frac_h2osfc"][ck] = max(S["frac_h2osfc"][ck], 0.05)
     return sg, S
 
 
@@ -92,7 +100,7 @@ def infiltration_np(prm, sg, S0):
     k_wet = 1.0e-4 * np.sin((np.pi / 180.0) * S["topo_slope"][c])
     surf = np.minimum(k_wet * clust * (h0 - thr), (h0 - thr) / dt)
     surf = np.where((h0 > thr) & (prm.h2osfcflag != 0), surf, 0.0)
-    surf = np.where(surf < 1.0e-8, 0.0, surf)
+    surf = np.where(surf < float(np.float32(1.0e-8)), 0.0, surf)          # SurfaceWaterMod.F90:499: REAL(4) literal
     S["qflx_h2osfc_surf"][c] = surf
     part = h0 + (in_sfc - surf) * dt
     part = np.where(np.abs(part) < 1.0e-13 * np.abs(h0), 0.0, part)
@@ -112,8 +120,11 @@ def test_infiltration_matches_numpy(oracle_lib, h2osfcflag, crop0):
     sg, S = case()
     prm = abi.default_params()
     prm.h2osfcflag, prm.crop_fsat_equals_zero = h2osfcflag, crop0
+    ck = sg.filters["hydrologyc"][5] - 1                     # (the column case() places between the REAL(4) and the double 1.0e-8)
     ref = copy_state(S)
     assert run_infiltration(oracle_lib, prm, sg, ref) == 0
+    if h2osfcflag:
+        assert 9.99999994e-9 < ref["qflx_h2osfc_surf"][ck] < 1.0e-8
     exp = infiltration_np(prm, sg, S)
     worst = 0.0
     for fs in abi.FIELDS["infiltration"]:
