@@ -156,3 +156,67 @@ def test_config4_full_step_f02_slab(gpu_ctx, oracle_lib):
             m = ~skip_of["PATCH" if got[name].shape[-1] == sg.npatch else "COL"]
             fin = (np.abs(ref[name]) < 1e30) & m
             assert np.max(np.abs(got[name][fin] - ref[name][fin])) <= 1e-10 * scale * 10, name
+
+
+def test_config2_hydrology_no_drainage_f09(oracle_lib):
+    """HydrologyNoDrainage end to end (SnowWater .. diagnostics, 13 C-ABI calls) on the f09 column set, device-resident,
+    against the same call sequence of the oracle: identical snow-layer counts and SoilWater sub-step counts, reals <= 1e-10."""
+    import torch
+    from tests.test_oracle_hydrology import run_infiltration, run_water_table, run_diagnostics
+    from tests.test_oracle_snow import snow_filters, run_snow_water, run_snow_layers, run_snow_capping
+    seed = 20260104
+    sg, S = synthetic_canopy.make_full_case("f09", seed=seed)
+    synthetic_canopy.balance_state(sg, S, np.random.Generator(np.random.PCG64(seed + 1)), 1.0e-11)
+    synthetic_canopy.soilfluxes_state(sg, S, np.random.Generator(np.random.PCG64(seed + 2)))
+    synthetic_canopy.preflux_state(sg, S, np.random.Generator(np.random.PCG64(seed + 3)))
+    synthetic_canopy.hydrology_state(sg, S, np.random.Generator(np.random.PCG64(seed + 4)))
+    synthetic_canopy.snow_state(sg, S, np.random.Generator(np.random.PCG64(seed + 5)))
+    synthetic_canopy.watertable_state(sg, S, np.random.Generator(np.random.PCG64(seed + 6)), saturate=False)
+    S["topo"] = np.random.Generator(np.random.PCG64(seed + 7)).uniform(0.0, 3000.0, sg.ncol)
+    for k in ("qflx_snwcp_ice", "qflx_snwcp_liq", "qflx_snwcp_discarded_ice", "qflx_snwcp_discarded_liq"):
+        S[k] = np.full(sg.ncol, 1.0e36)
+    assert sg.ngrc == 21000
+    prm = abi.default_params()
+    fh, fn = sg.filters["hydrologyc"], sg.filters["nolakec"]
+    ref = copy_state(S)
+    st = abi.Status()
+    fs, fns = snow_filters(oracle_lib, sg, ref)
+    assert run_snow_water(oracle_lib, prm, sg, ref, fs, fns)[0] == 0
+    assert run_infiltration(oracle_lib, prm, sg, ref) == 0
+    fsk = abi.make_struct("plantsink", ref, sg.bounds)
+    assert oracle_lib.oracle_vert_tran_sink_hydstress(C.byref(sg.bounds), len(fh), abi.i32p(fh), C.byref(fsk)) == 0
+    fw = abi.make_struct("soilwater", ref, sg.bounds)
+    assert oracle_lib.oracle_soilwater(C.byref(prm), C.byref(sg.bounds), len(fh), abi.i32p(fh), C.byref(fw), C.byref(st)) == 0
+    assert run_water_table(oracle_lib, prm, sg, ref)[0] == 0
+    assert run_snow_capping(oracle_lib, prm, sg, ref, fn, fs, 1000)[0] == 0
+    assert run_snow_layers(oracle_lib, prm, sg, ref, fs)[0] == 0
+    fs2, fns2 = snow_filters(oracle_lib, sg, ref)
+    assert run_diagnostics(oracle_lib, prm, sg, ref, fs2, fns2)[0] == 0
+    routines = ("snowwater", "infiltration", "plantsink", "soilwater", "watertable", "snowcapping", "snowlayers", "hydrodiag")
+    ctx = driver.Context(prm)
+    try:
+        names = sorted({f.name for g in routines for f in abi.FIELDS[g]})
+        D = {k: torch.from_numpy(np.ascontiguousarray(S[k])).cuda() for k in names}
+        driver.HotPath(ctx, sg, D, abi.MEM_DEVICE, routines).step()
+        ctx.sync()
+        got = {k: (D[k].cpu().numpy() if k in D else S[k]) for k in S}
+    finally:
+        ctx.close()
+    assert np.array_equal(got["snl"], ref["snl"]) and np.array_equal(got["num_substeps"], ref["num_substeps"])
+    worst = {}
+    for g in routines:
+        for f in abi.FIELDS[g]:
+            if f.intent == "IN" or f.ctype == "int":
+                continue
+            a, b = got[f.name], ref[f.name]
+            fin = np.abs(b) < 1e30
+            assert np.array_equal(fin, np.abs(a) < 1e30), f.name
+            if fin.any():
+                scale = float(np.max(np.abs(b[fin])))
+                worst[f.name] = float(np.max(np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), 1e-6 * scale + 1e-300)))
+    c = fs - 1
+    print("f09 HydrologyNoDrainage: %d snow columns (%d merged, %d split, %d vanished), worst" % (
+        len(fs), int((ref["snl"][c] > S["snl"][c]).sum()), int((ref["snl"][c] < S["snl"][c]).sum()), int((ref["snl"][c] == 0).sum())),
+        sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+    bad = {k: v for k, v in worst.items() if not v <= RTOL}
+    assert not bad, bad
