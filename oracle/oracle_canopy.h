@@ -51,6 +51,12 @@ void oracle_photosynthesis_hydraulic_stress(cf_ctx* x, int fn, const int32_t* fi
                                             const double* eair, const double* oair, const double* cair,
                                             const double* rb, double* bsun, double* bsha, double* btran,
                                             const double* dayl_factor, const double* qsatl, const double* qaf);
+int oracle_phs_calcstress(const ctsm_params_t* prm, const ctsm_canopyfluxes_fields_t* fld, int p, double* xv4, double* bsun,
+                          double* bsha, double gb_mol, double gs_mol_sun, double gs_mol_sha, double qsatl, double qaf);
+int oracle_phs_standalone(const ctsm_params_t* prm, const ctsm_canopyfluxes_fields_t* fld, int fn, const int32_t* filterp,
+                          const double* esat_tv, const double* eair, const double* oair, const double* cair, const double* rb,
+                          double* bsun, double* bsha, double* btran, const double* dayl_factor, const double* qsatl,
+                          const double* qaf);
 void oracle_photosynthesis(cf_ctx* x, int fn, const int32_t* filterp, const double* esat_tv, const double* eair,
                            const double* oair, const double* cair, const double* rb, const double* btran,
                            const double* dayl_factor, int phase);

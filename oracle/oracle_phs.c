@@ -1027,3 +1027,40 @@ void oracle_photosynthesis_hydraulic_stress(cf_ctx* x, int fn, const int32_t* fi
 #undef JMAX
 #undef L
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Stand-alone entry points for the pinning tests (tests/test_oracle_phs.py compares them with an independent Python restatement
+ * written from the Fortran): one calcstress solve of one patch, and PhotosynthesisHydraulicStress over a filter. */
+static void phs_ctx(cf_ctx* x, const ctsm_params_t* prm, const ctsm_canopyfluxes_fields_t* fld) {
+  memset(x, 0, sizeof *x);
+  x->f = fld; x->prm = prm;
+  x->begp0 = fld->alloc.begp; x->begc0 = fld->alloc.begc; x->begg0 = fld->alloc.begg;
+  x->ldp = (size_t)(fld->alloc.endp - fld->alloc.begp + 1);
+  x->ldc = (size_t)(fld->alloc.endc - fld->alloc.begc + 1);
+  x->np = (int)x->ldp;
+}
+
+/* xv: vegwp(sun, sha, xyl, root) in / out (4 values, 0-based) */
+int oracle_phs_calcstress(const ctsm_params_t* prm, const ctsm_canopyfluxes_fields_t* fld, int p, double* xv4, double* bsun,
+                          double* bsha, double gb_mol, double gs_mol_sun, double gs_mol_sha, double qsatl, double qaf) {
+  cf_ctx ctx, *x = &ctx;
+  phs_ctx(x, prm, fld);
+  double xv[5] = {0.0, xv4[0], xv4[1], xv4[2], xv4[3]};
+  calcstress(x, p, P1(column, p), xv, bsun, bsha, gb_mol, gs_mol_sun, gs_mol_sha, qsatl, qaf);
+  for (int i = 0; i < 4; ++i) xv4[i] = xv[i + 1];
+  return x->err_code;
+}
+
+/* the (begp0:endp0) work arrays are the caller's: esat_tv, eair, oair, cair, rb, dayl_factor, qsatl, qaf in; bsun, bsha, btran out */
+int oracle_phs_standalone(const ctsm_params_t* prm, const ctsm_canopyfluxes_fields_t* fld, int fn, const int32_t* filterp,
+                          const double* esat_tv, const double* eair, const double* oair, const double* cair, const double* rb,
+                          double* bsun, double* bsha, double* btran, const double* dayl_factor, const double* qsatl,
+                          const double* qaf) {
+  cf_ctx ctx, *x = &ctx;
+  phs_ctx(x, prm, fld);
+  x->bbb = (double*)calloc((size_t)x->np, sizeof(double));
+  x->mbb = (double*)calloc((size_t)x->np, sizeof(double));
+  oracle_photosynthesis_hydraulic_stress(x, fn, filterp, esat_tv, eair, oair, cair, rb, bsun, bsha, btran, dayl_factor, qsatl, qaf);
+  free(x->bbb); free(x->mbb);
+  return x->err_code;
+}
