@@ -280,3 +280,581 @@ def calcstress(P, x, gb_mol, gs_mol_sun, gs_mol_sha, qsatl, qaf):
         tran = soilflux
     pd = dict(x) if (night and P.local_time_lt_noon) else {i: SPVAL for i in range(1, 5)}
     return SimpleNamespace(bsun=bsun, bsha=bsha, night=night, tran=tran, iters=iters, vegwp_pd=pd)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# PhotosynthesisHydraulicStress and its root finder (PhotosynthesisMod.F90:2704-4486), nlevcan = 1, use_cn = .false.,
+# lnc_opt = .false., vcmax_opt = 0, use_c13 = .false. (the configuration of the hot path)
+# ------------------------------------------------------------------------------------------------------------------------------
+RPI = 3.14159265358979323846
+BBBOPT_C3, BBBOPT_C4 = 10000.0, 40000.0          # :85-86
+MEDLYN_RH_CAN_MAX, MEDLYN_RH_CAN_FACT = 50.0, 0.001   # :87-88
+MAX_CS = 1.e-06                                   # :89
+BB1987, MEDLYN2011 = 1, 2
+EPSILON = 2.220446049250313e-16
+
+
+class EndRun(Exception):
+    pass
+
+
+def quadratic(a, b, c):
+    """src/utils/quadraticMod.F90:17-68; returns (r1, r2)"""
+    if a == 0.0:
+        raise EndRun("quadratic: a = 0")
+    root = b * b - 4.0 * a * c
+    if root < 0.0:
+        if -root < 3.0 * EPSILON:
+            root = 0.0
+        else:
+            raise EndRun("quadratic: b^2 - 4ac is negative")
+    if b >= 0.0:
+        q = -0.5 * (b + math.sqrt(root))
+    else:
+        q = -0.5 * (b - math.sqrt(root))
+    r1 = q / a
+    if q != 0.0:
+        r2 = c / q
+    else:
+        r2 = 1.e36
+    return r1, r2
+
+
+def ft(tl, ha):
+    """:2488-2510"""
+    return math.exp(ha / (RGAS * 1.e-3 * (TFRZ + 25.0)) * (1.0 - (TFRZ + 25.0) / tl))
+
+
+def fth(tl, hd, se, scaleFactor):
+    """:2513-2536"""
+    return scaleFactor / (1.0 + math.exp((-hd + se * tl) / (RGAS * 1.e-3 * tl)))
+
+
+def fth25(hd, se):
+    """:2539-2561"""
+    return 1.0 + math.exp((-hd + se * (TFRZ + 25.0)) / (RGAS * 1.e-3 * (TFRZ + 25.0)))
+
+
+def _gsmin(P, M):
+    if M.stomatalcond_mtd == MEDLYN2011:
+        return P.medlynintercept
+    if M.stomatalcond_mtd == BB1987:
+        return P.bbb
+    raise EndRun("must choose stomatalcond_mtd method")
+
+
+def ci_func_PHS(P, M, W, x, cisun, cisha, bflag, gs0sun, gs0sha, fvalsun, fvalsha):
+    """:4227-4486.  W carries what the routine keeps in photosyns_inst / its inout dummies: ac, aj, ap, ag, an (dicts keyed SUN,
+    SHA), gs_mol (dict), bsun, bsha.  Returns (fvalsun, fvalsha); the incoming values survive where the routine does not assign."""
+    if bflag:
+        r = calcstress(P, x, P.gb_mol, gs0sun, gs0sha, P.qsatl, P.qaf)
+        W.bsun, W.bsha = r.bsun, r.bsha
+        W.vegwp_pd = r.vegwp_pd
+        if r.tran is not None:
+            W.qflx_tran_veg = r.tran
+        W.calcstress_calls += 1
+    bsun, bsha = W.bsun, W.bsha
+    ac, aj, ap, ag, an = W.ac, W.aj, W.ap, W.ag, W.an
+    if P.c3flag:
+        ac[SUN] = bsun * P.vcmax_z[SUN] * max(cisun - P.cp, 0.0) / (cisun + P.kc * (1.0 + P.oair / P.ko))
+        ac[SHA] = bsha * P.vcmax_z[SHA] * max(cisha - P.cp, 0.0) / (cisha + P.kc * (1.0 + P.oair / P.ko))
+        aj[SUN] = P.je[SUN] * max(cisun - P.cp, 0.0) / (4.0 * cisun + 8.0 * P.cp)
+        aj[SHA] = P.je[SHA] * max(cisha - P.cp, 0.0) / (4.0 * cisha + 8.0 * P.cp)
+        ap[SUN] = 3.0 * P.tpu_z[SUN]
+        ap[SHA] = 3.0 * P.tpu_z[SHA]
+    else:
+        ac[SUN] = bsun * P.vcmax_z[SUN]
+        ac[SHA] = bsha * P.vcmax_z[SHA]
+        aj[SUN] = P.qe * P.par_z[SUN] * 4.6
+        aj[SHA] = P.qe * P.par_z[SHA] * 4.6
+        ap[SUN] = P.kp_z[SUN] * max(cisun, 0.0) / P.forc_pbot
+        ap[SHA] = P.kp_z[SHA] * max(cisha, 0.0) / P.forc_pbot
+    for s in (SUN, SHA):
+        r1, r2 = quadratic(P.theta_cj, -(ac[s] + aj[s]), ac[s] * aj[s])
+        ai = min(r1, r2)
+        r1, r2 = quadratic(M.theta_ip, -(ai + ap[s]), ai * ap[s])
+        ag[s] = max(0.0, min(r1, r2))
+    an[SUN] = ag[SUN] - bsun * P.lmr_z[SUN]
+    an[SHA] = ag[SHA] - bsha * P.lmr_z[SHA]
+    gs = W.gs_mol
+    if an[SUN] < 0.0:
+        gs[SUN] = max(bsun * _gsmin(P, M), 1.0)
+        fvalsun = 0.0
+    if an[SHA] < 0.0:
+        gs[SHA] = max(bsha * _gsmin(P, M), 1.0)
+        fvalsha = 0.0
+    if an[SUN] < 0.0 and an[SHA] < 0.0:
+        return fvalsun, fvalsha
+    if an[SUN] >= 0.0:
+        cs_sun = P.cair - 1.4 / P.gb_mol * an[SUN] * P.forc_pbot
+        cs_sun = max(cs_sun, MAX_CS)
+    if M.stomatalcond_mtd == MEDLYN2011:
+        mi, ms = P.medlynintercept, P.medlynslope
+        if an[SUN] >= 0.0:
+            term = 1.6 * an[SUN] / (cs_sun / P.forc_pbot * 1.e06)
+            aquad = 1.0
+            bquad = -(2.0 * (mi * 1.e-06 + term) + (ms * term) * (ms * term) / (P.gb_mol * 1.e-06 * P.rh_can))
+            cquad = mi * mi * 1.e-12 + (2.0 * mi * 1.e-06 + term * (1.0 - ms * ms / P.rh_can)) * term
+            r1, r2 = quadratic(aquad, bquad, cquad)
+            gs[SUN] = max(r1, r2) * 1.e06
+        if an[SHA] >= 0.0:
+            cs_sha = P.cair - 1.4 / P.gb_mol * an[SHA] * P.forc_pbot
+            cs_sha = max(cs_sha, MAX_CS)
+            term = 1.6 * an[SHA] / (cs_sha / P.forc_pbot * 1.e06)
+            aquad = 1.0
+            bquad = -(2.0 * (mi * 1.e-06 + term) + (ms * term) * (ms * term) / (P.gb_mol * 1.e-06 * P.rh_can))
+            cquad = mi * mi * 1.e-12 + (2.0 * mi * 1.e-06 + term * (1.0 - ms * ms / P.rh_can)) * term
+            r1, r2 = quadratic(aquad, bquad, cquad)
+            gs[SHA] = max(r1, r2) * 1.e06
+    elif M.stomatalcond_mtd == BB1987:
+        if an[SUN] >= 0.0:
+            aquad = cs_sun
+            bquad = cs_sun * (P.gb_mol - max(bsun * P.bbb, 1.0)) - P.mbb * an[SUN] * P.forc_pbot
+            cquad = -P.gb_mol * (cs_sun * max(bsun * P.bbb, 1.0) + P.mbb * an[SUN] * P.forc_pbot * P.rh_can)
+            r1, r2 = quadratic(aquad, bquad, cquad)
+            gs[SUN] = max(r1, r2)
+        if an[SHA] >= 0.0:
+            cs_sha = P.cair - 1.4 / P.gb_mol * an[SHA] * P.forc_pbot
+            cs_sha = max(cs_sha, MAX_CS)
+            aquad = cs_sha
+            bquad = cs_sha * (P.gb_mol - max(bsha * P.bbb, 1.0)) - P.mbb * an[SHA] * P.forc_pbot
+            cquad = -P.gb_mol * (cs_sha * max(bsha * P.bbb, 1.0) + P.mbb * an[SHA] * P.forc_pbot * P.rh_can)
+            r1, r2 = quadratic(aquad, bquad, cquad)
+            gs[SHA] = max(r1, r2)
+    if an[SUN] >= 0.0:
+        if gs[SUN] > 0.0:
+            fvalsun = cisun - P.cair + an[SUN] * P.forc_pbot * (1.4 * gs[SUN] + 1.6 * P.gb_mol) / (P.gb_mol * gs[SUN])
+        else:
+            fvalsun = cisun - P.cair
+    if an[SHA] >= 0.0:
+        if gs[SHA] > 0.0:
+            fvalsha = cisha - P.cair + an[SHA] * P.forc_pbot * (1.4 * gs[SHA] + 1.6 * P.gb_mol) / (P.gb_mol * gs[SHA])
+        else:
+            fvalsha = cisha - P.cair
+    return fvalsun, fvalsha
+
+
+def brent_PHS(P, M, W, x1sun, x2sun, f1sun, f2sun, x1sha, x2sha, f1sha, f2sha, tol):
+    """:4068-4223; returns (xsun, xsha).  Arrays are dicts keyed SUN, SHA."""
+    itmax, eps = 20, 1.e-4
+    a = {SUN: x1sun, SHA: x1sha}
+    b = {SUN: x2sun, SHA: x2sha}
+    fa = {SUN: f1sun, SHA: f1sha}
+    fb = {SUN: f2sun, SHA: f2sha}
+    for ph in (SUN, SHA):
+        if (fa[ph] > 0.0 and fb[ph] > 0.0) or (fa[ph] < 0.0 and fb[ph] < 0.0):
+            raise EndRun("root must be bracketed for brent")
+    c, fc = dict(b), dict(fb)
+    d, e, s, pp_, q, r = {}, {}, {}, {}, {}, {}
+    it = 0
+    while True:
+        if it == itmax:
+            break
+        it += 1
+        for ph in (SUN, SHA):
+            if (fb[ph] > 0.0 and fc[ph] > 0.0) or (fb[ph] < 0.0 and fc[ph] < 0.0):
+                c[ph] = a[ph]
+                fc[ph] = fa[ph]
+                d[ph] = b[ph] - a[ph]
+                e[ph] = d[ph]
+            if abs(fc[ph]) < abs(fb[ph]):
+                a[ph] = b[ph]
+                b[ph] = c[ph]
+                c[ph] = a[ph]
+                fa[ph] = fb[ph]
+                fb[ph] = fc[ph]
+                fc[ph] = fa[ph]
+        tol1 = {ph: 2.0 * eps * abs(b[ph]) + 0.5 * tol for ph in (SUN, SHA)}
+        xm = {ph: 0.5 * (c[ph] - b[ph]) for ph in (SUN, SHA)}
+        if abs(xm[SUN]) <= tol1[SUN] or fb[SUN] == 0.0:
+            if abs(xm[SHA]) <= tol1[SHA] or fb[SHA] == 0.0:
+                W.brent_iters += it
+                return b[SUN], b[SHA]
+        for ph in (SUN, SHA):
+            if abs(e[ph]) >= tol1[ph] and abs(fa[ph]) > abs(fb[ph]):
+                s[ph] = fb[ph] / fa[ph]
+                if a[ph] == c[ph]:
+                    pp_[ph] = 2.0 * xm[ph] * s[ph]
+                    q[ph] = 1.0 - s[ph]
+                else:
+                    q[ph] = fa[ph] / fc[ph]
+                    r[ph] = fb[ph] / fc[ph]
+                    pp_[ph] = s[ph] * (2.0 * xm[ph] * q[ph] * (q[ph] - r[ph]) - (b[ph] - a[ph]) * (r[ph] - 1.0))
+                    q[ph] = (q[ph] - 1.0) * (r[ph] - 1.0) * (s[ph] - 1.0)
+                if pp_[ph] > 0.0:
+                    q[ph] = -q[ph]
+                pp_[ph] = abs(pp_[ph])
+                if 2.0 * pp_[ph] < min(3.0 * xm[ph] * q[ph] - abs(tol1[ph] * q[ph]), abs(e[ph] * q[ph])):
+                    e[ph] = d[ph]
+                    d[ph] = pp_[ph] / q[ph]
+                else:
+                    d[ph] = xm[ph]
+                    e[ph] = d[ph]
+            else:
+                d[ph] = xm[ph]
+                e[ph] = d[ph]
+            a[ph] = b[ph]
+            fa[ph] = fb[ph]
+            if abs(d[ph]) > tol1[ph]:
+                b[ph] = b[ph] + d[ph]
+            else:
+                b[ph] = b[ph] + math.copysign(tol1[ph], xm[ph])
+        gs0sun, gs0sha = W.gs_mol[SUN], W.gs_mol[SHA]
+        fb[SUN], fb[SHA] = ci_func_PHS(P, M, W, None, b[SUN], b[SHA], False, gs0sun, gs0sha, fb[SUN], fb[SHA])
+        if fb[SUN] == 0.0 and fb[SHA] == 0.0:
+            break
+    W.brent_iters += it
+    return b[SUN], b[SHA]
+
+
+def hybrid_PHS(P, M, W, x0sun, x0sha):
+    """:3815-4064; returns (x0sun, x0sha) = the converged ci pair.  W.vegwp (dict 1..4) is vegwp(p,:)"""
+    toldb, eps, eps1, itmax = 1.e-2, 1.e-2, 1.e-4, 3
+    x1sun, x1sha = x0sun, x0sha
+    bflag = False
+    b0sun, b0sha = -1.0, -1.0
+    gs0sun, gs0sha = 0.0, 0.0
+    W.bsun, W.bsha = 1.0, 1.0
+    f0sun = f0sha = f1sun = f1sha = float("nan")
+    minf = minxsun = minxsha = float("nan")
+    iter1 = 0
+    while True:
+        x = dict(W.vegwp)
+        iter1 += 1
+        iter2 = 0
+        x0sun = max(0.1, x1sun)
+        x1sun = 0.99 * x1sun
+        x0sha = max(0.1, x1sha)
+        x1sha = 0.99 * x1sha
+        tolsun = abs(x1sun) * eps
+        tolsha = abs(x1sha) * eps
+        f0sun, f0sha = ci_func_PHS(P, M, W, x, x0sun, x0sha, bflag, gs0sun, gs0sha, f0sun, f0sha)
+        dbsun = b0sun - W.bsun
+        dbsha = b0sha - W.bsha
+        b0sun, b0sha = W.bsun, W.bsha
+        bflag = False
+        f1sun, f1sha = ci_func_PHS(P, M, W, x, x1sun, x1sha, bflag, gs0sun, gs0sha, f1sun, f1sha)
+        while True:
+            if abs(f0sun) < eps1 and abs(f0sha) < eps1:
+                x1sun, x1sha = x0sun, x0sha
+                break
+            if abs(f1sun) < eps1 and abs(f1sha) < eps1:
+                break
+            iter2 += 1
+            if (f1sun - f0sun) == 0.0:
+                dxsun = 0.5 * (x1sun + x0sun) - x1sun
+            else:
+                dxsun = -f1sun * (x1sun - x0sun) / (f1sun - f0sun)
+            if (f1sha - f0sha) == 0.0:
+                dxsha = 0.5 * (x1sha + x0sha) - x1sha
+            else:
+                dxsha = -f1sha * (x1sha - x0sha) / (f1sha - f0sha)
+            x0sun = x1sun
+            x1sun = x1sun + dxsun
+            x0sha = x1sha
+            x1sha = x1sha + dxsha
+            f1sun, f1sha = ci_func_PHS(P, M, W, x, x1sun, x1sha, bflag, gs0sun, gs0sha, f1sun, f1sha)
+            if abs(dxsun) < tolsun and abs(dxsha) < tolsha:
+                x0sun, x0sha = x1sun, x1sha
+                break
+            if iter2 == 1:
+                minf = abs(f1sun + f1sha)
+                minxsun, minxsha = x1sun, x1sha
+            else:
+                if abs(f1sun + f1sha) < minf:
+                    minf = abs(f1sun + f1sha)
+                    minxsun, minxsha = x1sun, x1sha
+            if abs(f1sun) < eps1 and abs(f1sha) < eps1:
+                break
+            if f1sun * f0sun < 0.0 and f1sha * f0sha < 0.0:
+                xsun, xsha = brent_PHS(P, M, W, x0sun, x1sun, f0sun, f1sun, x0sha, x1sha, f0sha, f1sha, tolsun)
+                x0sun, x0sha = xsun, xsha
+                W.brent_calls += 1
+                break
+            if iter2 > itmax:
+                x1sun, x1sha = minxsun, minxsha
+                f1sun, f1sha = ci_func_PHS(P, M, W, x, x1sun, x1sha, bflag, gs0sun, gs0sha, f1sun, f1sha)
+                W.itmax_exits += 1
+                break
+        if W.bsun > 0.01:
+            gs0sun = W.gs_mol[SUN] / W.bsun
+        if W.bsha > 0.01:
+            gs0sha = W.gs_mol[SHA] / W.bsha
+        bflag = True
+        if abs(dbsun) < toldb and abs(dbsha) < toldb:
+            break
+        if iter1 > itmax:
+            break
+    x0sun, x0sha = x1sun, x1sha
+    soilflux = getvegwp(P, x, P.gb_mol, W.gs_mol[SUN], W.gs_mol[SHA], P.qsatl, P.qaf)
+    W.vegwp = dict(x)
+    if P.near_local_noon:
+        W.vegwp_ln = dict(W.vegwp)
+    else:
+        W.vegwp_ln = {i: SPVAL for i in range(1, 5)}
+    if soilflux < 0.0:
+        soilflux = 0.0
+    W.qflx_tran_veg = soilflux
+    W.iter1 += iter1
+    return x0sun, x0sha
+
+
+def photosynthesis_hydraulic_stress(P, M):
+    """:2704-3811 for one patch (nlevcan = 1: the canopy-layer loops run iv = 1 .. nrad <= 1).  P: the patch's inputs (see
+    tests/test_oracle_phs.py::phs_patch_inputs); M: the parameter / namelist values.  Returns the namespace W of everything the
+    routine writes for that patch."""
+    croot_lateral_length, c_to_b = 0.25, 2.0
+    W = SimpleNamespace(calcstress_calls=0, brent_calls=0, brent_iters=0, itmax_exits=0, iter1=0, qflx_tran_veg=None, vegwp_pd=None,
+                        vegwp_ln=None, vegwp=dict(P.vegwp))
+    medlyn = M.stomatalcond_mtd == MEDLYN2011
+    lmrc = fth25(M.lmrhd, M.lmrse)
+    # root-soil interface conductance (:3063-3114)
+    W.root_conductance, W.soil_conductance, W.k_soil_root = {}, {}, {}
+    for j in range(1, NLEVSOI + 1):
+        root_biomass_density = c_to_b * P.froot_carbon * P.rootfr[j] / P.dz[j]
+        root_biomass_density = max(c_to_b * 1.0, root_biomass_density)
+        root_cross_sec_area = RPI * (P.root_radius * P.root_radius)        # x**2 is x*x in Fortran
+        root_length_density = root_biomass_density / (P.root_density * root_cross_sec_area)
+        rai = (P.tsai + P.tlai) * P.froot_leaf * P.rootfr[j]
+        croot_average_length = croot_lateral_length
+        r_soil = math.sqrt(1. / (RPI * root_length_density))
+        soil_conductance = min(P.hksat[j], P.hk_l[j]) / (1.e3 * r_soil)
+        fs = plc(P.smp[j], P, ROOT)
+        root_conductance = (fs * rai * P.krmax) / (croot_average_length + P.z[j])
+        soil_conductance = max(soil_conductance, 1.e-16)
+        root_conductance = max(root_conductance, 1.e-16)
+        W.root_conductance[j] = root_conductance
+        W.soil_conductance[j] = soil_conductance
+        rs_resis = 1.0 / soil_conductance + 1.0 / root_conductance
+        if rai * P.rootfr[j] > 0.0 and j > 1:
+            W.k_soil_root[j] = 1.0 / rs_resis
+        else:
+            W.k_soil_root[j] = 0.0
+    P.k = W.k_soil_root
+    # :3118-3164
+    if round(P.c3psn) == 1:
+        P.c3flag = True
+    elif round(P.c3psn) == 0:
+        P.c3flag = False
+    W.c3flag = P.c3flag
+    if P.c3flag:
+        P.qe = 0.0
+        bbbopt = BBBOPT_C3
+    else:
+        P.qe = 0.05
+        bbbopt = BBBOPT_C4
+    if not medlyn:
+        P.bbb = bbbopt
+        P.mbb = P.mbbopt
+    kc25 = M.kc25_coef * P.forc_pbot
+    ko25 = M.ko25_coef * P.forc_pbot
+    sco = 0.5 * 0.209 / M.cp25_yr2000
+    cp25 = 0.5 * P.oair / sco
+    P.kc = kc25 * ft(P.t_veg, M.kcha)
+    P.ko = ko25 * ft(P.t_veg, M.koha)
+    P.cp = cp25 * ft(P.t_veg, M.cpha)
+    W.qe, W.kc, W.ko, W.cp = P.qe, P.kc, P.ko, P.cp
+    # :3170-3469
+    lnc = 1.0 / (P.slatop * P.leafcn)
+    lnc = min(lnc, 10.0)
+    W.lnc = lnc
+    vcmax25top = lnc * P.flnr * M.fnr * M.act25 * P.dayl_factor
+    vcmax25top = vcmax25top * P.fnitr                       # .not. use_cn
+    t10c = min(max((P.t10 - TFRZ), 11.0), 35.0)
+    jmax25top = ((2.59 - 0.035 * t10c) * vcmax25top) * M.jmax25top_sf
+    tpu25top = M.tpu25ratio * vcmax25top
+    kp25top = M.kp25ratio * vcmax25top
+    W.luvcmax25top, W.lujmax25top, W.lutpu25top = vcmax25top, jmax25top, tpu25top
+    if P.c3flag:
+        lmr25top = vcmax25top * M.leaf_mr_vcm
+    else:
+        lmr25top = vcmax25top * 0.025
+    luna = M.use_luna and P.c3flag and P.crop == 0
+    P.vcmax_z, P.tpu_z, P.kp_z, P.lmr_z, jmax_z = {}, {}, {}, {}, {}
+    t_veg = P.t_veg
+    for iv in range(1, P.nrad + 1):
+        nscaler_sun = P.vcmaxcintsun
+        nscaler_sha = P.vcmaxcintsha
+        lmr25_sun = lmr25top * nscaler_sun
+        lmr25_sha = lmr25top * nscaler_sha
+        if luna:
+            lmr25_sun = M.leaf_mr_vcm * P.vcmx25_z
+            lmr25_sha = M.leaf_mr_vcm * P.vcmx25_z
+        if P.c3flag:
+            P.lmr_z[SUN] = lmr25_sun * ft(t_veg, M.lmrha) * fth(t_veg, M.lmrhd, M.lmrse, lmrc)
+            P.lmr_z[SHA] = lmr25_sha * ft(t_veg, M.lmrha) * fth(t_veg, M.lmrhd, M.lmrse, lmrc)
+        else:
+            P.lmr_z[SUN] = lmr25_sun * 2.0 ** ((t_veg - (TFRZ + 25.0)) / 10.0)
+            P.lmr_z[SUN] = P.lmr_z[SUN] / (1.0 + math.exp(1.3 * (t_veg - (TFRZ + 55.0))))
+            P.lmr_z[SHA] = lmr25_sha * 2.0 ** ((t_veg - (TFRZ + 25.0)) / 10.0)
+            P.lmr_z[SHA] = P.lmr_z[SHA] / (1.0 + math.exp(1.3 * (t_veg - (TFRZ + 55.0))))
+        P.lmr_z[SUN] = P.lmr_z[SUN] * min((0.2 * math.exp(3.218 * P.tlai_z)), 1.0)
+        P.lmr_z[SHA] = P.lmr_z[SHA] * min((0.2 * math.exp(3.218 * P.tlai_z)), 1.0)
+        if P.par_z[SUN] <= 0.0:
+            for s in (SUN, SHA):
+                P.vcmax_z[s] = 0.0
+                jmax_z[s] = 0.0
+                P.tpu_z[s] = 0.0
+                P.kp_z[s] = 0.0
+        else:
+            if luna:
+                vcmax25_sun = P.vcmx25_z
+                vcmax25_sha = P.vcmx25_z
+                jmax25_sun = P.jmx25_z
+                jmax25_sha = P.jmx25_z
+                tpu25_sun = M.tpu25ratio * vcmax25_sun
+                tpu25_sha = M.tpu25ratio * vcmax25_sha
+                if P.vcmaxcintsun > 0.0:                      # .and. nlevcan == 1
+                    vcmax25_sha = vcmax25_sun * P.vcmaxcintsha / P.vcmaxcintsun
+                    jmax25_sha = jmax25_sun * P.vcmaxcintsha / P.vcmaxcintsun
+                    tpu25_sha = tpu25_sun * P.vcmaxcintsha / P.vcmaxcintsun
+            else:
+                vcmax25_sun = vcmax25top * nscaler_sun
+                jmax25_sun = jmax25top * nscaler_sun
+                tpu25_sun = tpu25top * nscaler_sun
+                vcmax25_sha = vcmax25top * nscaler_sha
+                jmax25_sha = jmax25top * nscaler_sha
+                tpu25_sha = tpu25top * nscaler_sha
+            kp25_sun = kp25top * nscaler_sun
+            kp25_sha = kp25top * nscaler_sha
+            vcmaxse = (668.39 - 1.07 * t10c) * M.vcmaxse_sf
+            jmaxse = (659.70 - 0.75 * t10c) * M.jmaxse_sf
+            tpuse = (668.39 - 1.07 * t10c) * M.tpuse_sf
+            vcmaxc = fth25(M.vcmaxhd, vcmaxse)
+            jmaxc = fth25(M.jmaxhd, jmaxse)
+            tpuc = fth25(M.tpuhd, tpuse)
+            P.vcmax_z[SUN] = vcmax25_sun * ft(t_veg, M.vcmaxha) * fth(t_veg, M.vcmaxhd, vcmaxse, vcmaxc)
+            jmax_z[SUN] = jmax25_sun * ft(t_veg, M.jmaxha) * fth(t_veg, M.jmaxhd, jmaxse, jmaxc)
+            P.tpu_z[SUN] = tpu25_sun * ft(t_veg, M.tpuha) * fth(t_veg, M.tpuhd, tpuse, tpuc)
+            P.vcmax_z[SHA] = vcmax25_sha * ft(t_veg, M.vcmaxha) * fth(t_veg, M.vcmaxhd, vcmaxse, vcmaxc)
+            jmax_z[SHA] = jmax25_sha * ft(t_veg, M.jmaxha) * fth(t_veg, M.jmaxhd, jmaxse, jmaxc)
+            P.tpu_z[SHA] = tpu25_sha * ft(t_veg, M.tpuha) * fth(t_veg, M.tpuhd, tpuse, tpuc)
+            if not P.c3flag:
+                for s, v25 in ((SUN, vcmax25_sun), (SHA, vcmax25_sha)):
+                    P.vcmax_z[s] = v25 * 2.0 ** ((t_veg - (TFRZ + 25.0)) / 10.0)
+                    P.vcmax_z[s] = P.vcmax_z[s] / (1.0 + math.exp(0.2 * ((TFRZ + 15.0) - t_veg)))
+                    P.vcmax_z[s] = P.vcmax_z[s] / (1.0 + math.exp(0.3 * (t_veg - (TFRZ + 40.0))))
+            P.kp_z[SUN] = kp25_sun * 2.0 ** ((t_veg - (TFRZ + 25.0)) / 10.0)
+            P.kp_z[SHA] = kp25_sha * 2.0 ** ((t_veg - (TFRZ + 25.0)) / 10.0)
+        if M.light_inhibit and P.par_z[SUN] > 0.0:
+            P.lmr_z[SUN] = P.lmr_z[SUN] * 0.67
+        if M.light_inhibit and P.par_z[SHA] > 0.0:
+            P.lmr_z[SHA] = P.lmr_z[SHA] * 0.67
+    W.vcmax_z, W.tpu_z, W.kp_z, W.lmr_z = P.vcmax_z, P.tpu_z, P.kp_z, P.lmr_z
+    # leaf-level photosynthesis and stomatal conductance (:3475-3711)
+    rsmax0 = 2.e4
+    cf = P.forc_pbot / (RGAS * 1.e-3 * P.tgcm) * 1.e06
+    gb = 1.0 / P.rb
+    P.gb_mol = gb * cf
+    W.gb_mol = P.gb_mol
+    W.ac, W.aj, W.ap, W.ag, W.an, W.gs_mol = {}, {}, {}, {}, {}, dict(P.gs_mol)
+    W.bsun, W.bsha = P.bsun_in, P.bsha_in
+    W.psn_z, W.psn_wc_z, W.psn_wj_z, W.psn_wp_z, W.rs_z, W.ci_z, W.gs_mol_ln = {}, {}, {}, {}, {}, {}, None
+    W.vpd_can = None
+    lessen = P.crop == 0 or not M.modifyphoto_and_lmr_forcrop
+    for iv in range(1, P.nrad + 1):
+        if P.par_z[SUN] <= 0.0:
+            W.vegwp[SUN] = 1.0
+            gsminsun = gsminsha = _gsmin(P, M)
+            x = W.vegwp                                               # calcstress works on vegwp(p,:) itself here
+            r = calcstress(P, x, P.gb_mol, gsminsun, gsminsha, P.qsatl, P.qaf)
+            W.calcstress_calls += 1
+            W.bsun, W.bsha, W.vegwp_pd = r.bsun, r.bsha, r.vegwp_pd
+            if r.tran is not None:
+                W.qflx_tran_veg = r.tran
+            for s, b, gsmin in ((SUN, W.bsun, gsminsun), (SHA, W.bsha, gsminsha)):
+                W.ac[s] = W.aj[s] = W.ap[s] = W.ag[s] = 0.0
+                if lessen:
+                    W.an[s] = W.ag[s] - b * P.lmr_z[s]
+                else:
+                    W.an[s] = W.ag[s] - P.lmr_z[s]
+                W.psn_z[s] = W.psn_wc_z[s] = W.psn_wj_z[s] = W.psn_wp_z[s] = 0.0
+                W.rs_z[s] = min(rsmax0, 1.0 / (max(b * gsmin, 1.0)) * cf)
+                W.ci_z[s] = 0.0
+            W.gs_mol[SUN] = cf / W.rs_z[SUN]
+            W.gs_mol[SHA] = cf / W.rs_z[SHA]
+        else:
+            ceair = min(P.eair, P.esat_tv)
+            if not medlyn:
+                P.rh_can = ceair / P.esat_tv
+            else:
+                P.rh_can = max((P.esat_tv - ceair), MEDLYN_RH_CAN_MAX) * MEDLYN_RH_CAN_FACT
+                W.vpd_can = P.rh_can
+            P.je = {}
+            for s in (SUN, SHA):
+                qabs = 0.5 * (1.0 - M.fnps) * P.par_z[s] * 4.6
+                r1, r2 = quadratic(M.theta_psii, -(qabs + jmax_z[s]), qabs * jmax_z[s])
+                P.je[s] = min(r1, r2)
+            ci0 = 0.7 * P.cair if P.c3flag else 0.4 * P.cair
+            hybrid_PHS(P, M, W, ci0, ci0)
+            if medlyn:
+                gsminsun = gsminsha = P.medlynintercept
+                gs_slope = P.medlynslope
+            else:
+                gsminsun = gsminsha = P.bbb
+                gs_slope = P.mbb
+            if W.an[SUN] < 0.0:
+                W.gs_mol[SUN] = max(W.bsun * gsminsun, 1.0)
+            if W.an[SHA] < 0.0:
+                W.gs_mol[SHA] = max(W.bsha * gsminsha, 1.0)
+            if P.near_local_noon:
+                W.gs_mol_ln = dict(W.gs_mol)
+            else:
+                W.gs_mol_ln = {SUN: SPVAL, SHA: SPVAL}
+            cs = {}
+            for s in (SUN, SHA):
+                cs[s] = P.cair - 1.4 / P.gb_mol * W.an[s] * P.forc_pbot
+                cs[s] = max(cs[s], MAX_CS)
+                W.ci_z[s] = P.cair - W.an[s] * P.forc_pbot * (1.4 * W.gs_mol[s] + 1.6 * P.gb_mol) / (P.gb_mol * W.gs_mol[s])
+                W.ci_z[s] = max(W.ci_z[s], 1.e-06)
+            for s in (SUN, SHA):
+                gs = W.gs_mol[s] / cf
+                W.rs_z[s] = min(1.0 / gs, rsmax0)
+                W.rs_z[s] = W.rs_z[s] / P.o3coefg[s]
+            for s in (SUN, SHA):
+                W.psn_z[s] = W.ag[s]
+                W.psn_z[s] = W.psn_z[s] * P.o3coefv[s]
+                W.psn_wc_z[s] = W.psn_wj_z[s] = W.psn_wp_z[s] = 0.0
+                if W.ac[s] <= W.aj[s] and W.ac[s] <= W.ap[s]:
+                    W.psn_wc_z[s] = W.psn_z[s]
+                elif W.aj[s] < W.ac[s] and W.aj[s] <= W.ap[s]:
+                    W.psn_wj_z[s] = W.psn_z[s]
+                elif W.ap[s] < W.ac[s] and W.ap[s] < W.aj[s]:
+                    W.psn_wp_z[s] = W.psn_z[s]
+            if W.gs_mol[SUN] < 0.0 or W.gs_mol[SHA] < 0.0:
+                raise EndRun("Negative stomatal conductance")
+            W.gs_mol_err = {}
+            for s, b, gsmin in ((SUN, W.bsun, gsminsun), (SHA, W.bsha, gsminsha)):
+                hs = (P.gb_mol * ceair + W.gs_mol[s] * P.esat_tv) / ((P.gb_mol + W.gs_mol[s]) * P.esat_tv)
+                W.gs_mol_err[s] = gs_slope * max(W.an[s], 0.0) * hs / cs[s] * P.forc_pbot + max(b * gsmin, 1.0)
+    # canopy sums (:3715-3807)
+    W.psn, W.psn_wc, W.psn_wj, W.psn_wp, W.lmr, W.rs = {}, {}, {}, {}, {}, {}
+    laican = {}
+    for s, b in ((SUN, W.bsun), (SHA, W.bsha)):
+        psncan = psncan_wc = psncan_wj = psncan_wp = lmrcan = gscan = 0.0
+        laican[s] = 0.0
+        for iv in range(1, P.nrad + 1):
+            psncan = psncan + W.psn_z[s] * P.lai_z[s]
+            psncan_wc = psncan_wc + W.psn_wc_z[s] * P.lai_z[s]
+            psncan_wj = psncan_wj + W.psn_wj_z[s] * P.lai_z[s]
+            psncan_wp = psncan_wp + W.psn_wp_z[s] * P.lai_z[s]
+            if P.crop == 0 and M.modifyphoto_and_lmr_forcrop:
+                lmrcan = lmrcan + P.lmr_z[s] * P.lai_z[s] * b
+            else:
+                lmrcan = lmrcan + P.lmr_z[s] * P.lai_z[s]
+            gscan = gscan + P.lai_z[s] / (P.rb + W.rs_z[s])
+            laican[s] = laican[s] + P.lai_z[s]
+        if laican[s] > 0.0:
+            W.psn[s] = psncan / laican[s]
+            W.psn_wc[s] = psncan_wc / laican[s]
+            W.psn_wj[s] = psncan_wj / laican[s]
+            W.psn_wp[s] = psncan_wp / laican[s]
+            W.lmr[s] = lmrcan / laican[s]
+            W.rs[s] = laican[s] / gscan - P.rb
+        else:
+            W.psn[s] = W.psn_wc[s] = W.psn_wj[s] = W.psn_wp[s] = W.lmr[s] = W.rs[s] = 0.0
+    if laican[SHA] + laican[SUN] > 0.0:
+        W.btran = W.bsun * (laican[SUN] / (laican[SUN] + laican[SHA])) + W.bsha * (laican[SHA] / (laican[SUN] + laican[SHA]))
+    else:
+        W.btran = W.bsun
+    return W
