@@ -65,3 +65,94 @@ def test_friction_velocity_monin_obukhov_qsat_match_python(oracle_lib):
         OL.oracle_qsat(T, p, C.byref(qs), C.byref(es), C.byref(qsdT))
         assert (qs.value, es.value, qsdT.value) == cp.qsat(T, p)[:3]
     assert min(regimes.values()) > 300, regimes
+
+
+def canopy_patch_inputs(S, p):
+    """everything CanopyFluxes reads for patch p (0-based) and its column / gridcell, Fortran-indexed, on top of the PHS inputs"""
+    from tests.test_oracle_phs import phs_patch_inputs
+    n = S["itype"].shape[0]
+    dummy = {k: np.zeros(n) for k in ("esat_tv", "eair", "oair", "cair", "rb", "dayl_factor", "qsatl", "qaf", "bsun", "bsha")}
+    P = phs_patch_inputs(S, p, dummy)
+    c, g, t = P.c, P.g, P.t
+    fp, fc, fg, ft = (lambda k: float(S[k][p])), (lambda k: float(S[k][c])), (lambda k: float(S[k][g])), (lambda k: float(S[k][t]))
+    grnd = lambda k, lo=1: {j: float(S[k][j - lo, c]) for j in range(1, 26)}
+    P.__dict__.update(
+        dayl=fg("dayl"), max_dayl=fg("max_dayl"), forc_u=fg("forc_u"), forc_v=fg("forc_v"), forc_pco2=fg("forc_pco2"),
+        forc_po2=fg("forc_po2"), forc_hgt_t=fg("forc_hgt_t"), forc_hgt_u=fg("forc_hgt_u"), forc_hgt_q=fg("forc_hgt_q"),
+        forc_lwrad=fc("forc_lwrad"), forc_th=fc("forc_th"), forc_q=fc("forc_q"), z0mg=fc("z0mg"), t_h2osfc=fc("t_h2osfc"),
+        t_grnd=fc("t_grnd"), thv=fc("thv"), emg=fc("emg"), frac_h2osfc=fc("frac_h2osfc"), frac_sno=fc("frac_sno_eff"),
+        snow_depth=fc("snow_depth"), qg_snow=fc("qg_snow"), qg_soil=fc("qg_soil"), qg_h2osfc=fc("qg_h2osfc"), qg=fc("qg"),
+        dqgdT=fc("dqgdT"), htvp=fc("htvp"), snl=int(S["snl"][c]), soilresis=fc("soilresis"), soilbeta=fc("soilbeta"),
+        t_soisno={j: float(S["t_soisno"][j + 11, c]) for j in range(-11, 26)}, h2osoi_ice=grnd("h2osoi_ice", -11),
+        h2osoi_liq=grnd("h2osoi_liq", -11), watsat=grnd("watsat"), bsw=grnd("bsw"), sucsat=grnd("sucsat"), dz=grnd("dz", -11),
+        rootfr={j: float(S["rootfr"][j - 1, p]) for j in range(1, 26)},
+        frac_veg_nosno=int(S["frac_veg_nosno"][p]), thm=fp("thm"), sabv=fp("sabv"), emv=fp("emv"), fwet=fp("fwet"), t_stem=fp("t_stem"),
+        displa=fp("displa"), z0mv=fp("z0mv"), snocan=fp("snocan"), liqcan=fp("liqcan"), cgrnds=fp("cgrnds"), cgrndl=fp("cgrndl"),
+        stem_biomass=fp("stem_biomass"), leaf_biomass=fp("leaf_biomass"), dleaf=ft("pft_dleaf"), dbh_param=ft("pft_dbh"),
+        fbw=ft("pft_fbw"), nstem=ft("pft_nstem"), rstem_per_dbh=ft("pft_rstem_per_dbh"), wood_density=ft("pft_wood_density"),
+        is_tree=bool(S["pft_is_tree"][t]), is_shrub=bool(S["pft_is_shrub"][t]), z0v_Cr=ft("pft_z0v_Cr"), z0v_Cs=ft("pft_z0v_Cs"),
+        z0v_c=ft("pft_z0v_c"), z0v_cw=ft("pft_z0v_cw"), z0v_LAImax=ft("pft_z0v_LAImax"), smpso=ft("pft_smpso"), smpsc=ft("pft_smpsc"))
+    return P
+
+
+def _canopy_pin(oracle_lib, seed, ngrid, npatch, **switches):
+    from types import SimpleNamespace
+    from ctsm_b200 import abi, synthetic_canopy
+    from tests import phs_python as pp
+    from tests.test_oracle_phs import phs_output_pairs
+    from tests.util import copy_state
+    sg, S = synthetic_canopy.make_full_case(ngrid, seed=seed)
+    prm = abi.default_params()
+    for k, v in switches.items():
+        setattr(prm, k, v)
+    S0 = copy_state(S)
+    fe = sg.filters["exposedvegp"]
+    f = abi.make_struct("canopyfluxes", S, sg.bounds)
+    st = abi.Status()
+    oracle_lib.oracle_canopyfluxes.argtypes = [C.POINTER(abi.Params), C.POINTER(abi.Bounds), C.c_int, C.POINTER(C.c_int32),
+                                               C.POINTER(abi.STRUCTS["canopyfluxes"]), C.POINTER(abi.Status)]
+    assert oracle_lib.oracle_canopyfluxes(C.byref(prm), C.byref(sg.bounds), len(fe), abi.i32p(fe), C.byref(f), C.byref(st)) == 0
+    M = SimpleNamespace(**{k: getattr(prm, k) for k, _ in abi.Params._fields_ if not k.startswith("reserved")})
+    patch_fields = ("t_veg t_stem displa z0mv z0hv z0qv forc_hgt_u_patch forc_hgt_t_patch forc_hgt_q_patch snocan liqcan cgrnds cgrndl "
+                    "cgrnd qflx_tran_veg stem_biomass leaf_biomass dleaf_patch dhsdt_canopy btran taux tauy dlrad ulrad eflx_sh_snow "
+                    "eflx_sh_h2osfc eflx_sh_soil eflx_sh_stem eflx_sh_veg eflx_sh_grnd ram1 rb1 rah1 rah2 raw1 raw2 ustar um uaf taf qaf "
+                    "obu zeta vpd u10 u10_clm fv va vds t_ref2m t_ref2m_r t_skin q_ref2m rh_ref2m rh_ref2m_r rh_af vpd_ref2m iwue_ln "
+                    "qflx_evap_veg qflx_evap_soi qflx_ev_snow qflx_ev_soil qflx_ev_h2osfc fpsn fpsn_wc fpsn_wj fpsn_wp").split()
+    stats = {"patches": 0, "iters": 0, "max_iter": 0, "capped": 0, "clipped": 0}
+    for p1 in fe[:npatch]:
+        p = int(p1) - 1
+        P = canopy_patch_inputs(S0, p)
+        O = cp.canopy_fluxes_patch(P, M, pp.photosynthesis_hydraulic_stress)
+        got = lambda k, *i: float(S[k][(*i, p)])
+        pairs = [(k, getattr(O, k), got(k)) for k in patch_fields]
+        pairs += [("num_iter", O.num_iter, int(S["num_iter"][p])), ("bsun", O.phs.bsun, got("bsun")), ("bsha", O.phs.bsha, got("bsha"))]
+        day = P.par_z[1] > 0.0
+        pairs += phs_output_pairs(O.phs, got, day, prm.stomatalcond_mtd)
+        for j in range(1, 26):
+            pairs += [("rootr", O.rootr[j], got("rootr", j - 1)), ("eff_porosity", O.eff_porosity[j], float(S["eff_porosity"][j - 1, P.c])),
+                      ("h2osoi_liqvol", O.h2osoi_liqvol[j], float(S["h2osoi_liqvol"][j + 11, P.c]))]
+            if O.rresis[j] is not None:
+                pairs.append(("rresis", O.rresis[j], got("rresis", j - 1)))
+        bad = [(k, a, b) for k, a, b in pairs if a != b]
+        assert not bad, (int(p1), day, O.num_iter, bad[:8])
+        stats["patches"] += 1
+        stats["iters"] += O.num_iter
+        stats["max_iter"] = max(stats["max_iter"], O.num_iter)
+        stats["capped"] += O.num_iter > prm.itmax_canopy_fluxes
+    return stats
+
+
+def test_canopyfluxes_matches_python_restatement(oracle_lib):
+    """CanopyFluxes with plant hydraulic stress, clm6_0 switches (Meier2022 roughness, biomass heat storage, SL14 soil resistance,
+    Medlyn): every patch / column array element the routine writes, identical bits, with identical iteration counts"""
+    stats = _canopy_pin(oracle_lib, 1401, 400, 900)
+    print("CanopyFluxes pin:", stats)
+    assert stats["patches"] == 900 and stats["max_iter"] >= 10
+
+
+def test_canopyfluxes_matches_python_restatement_other_switches(oracle_lib):
+    """ZengWang2007 roughness, no biomass heat storage, Lee-Pielke soil beta, under-canopy stability, Ball-Berry"""
+    stats = _canopy_pin(oracle_lib, 1402, 300, 500, z0param_method=1, use_biomass_heat_storage=0, soil_resis_method=0,
+                        use_undercanopy_stability=1, stomatalcond_mtd=1)
+    print("CanopyFluxes pin (other switches):", stats)
+    assert stats["patches"] == 500

@@ -108,6 +108,39 @@ def phs_patch_inputs(S, p, work):
     return P
 
 
+def phs_output_pairs(W, got, day, mtd):
+    """(name, restatement, oracle) for every array element PhotosynthesisHydraulicStress writes for one patch; got(name, *level)
+    reads the oracle's state"""
+    pairs = [("c3flag", float(W.c3flag), got("c3flag")), ("qe", W.qe, got("qe")), ("kc", W.kc, got("kc")), ("ko", W.ko, got("ko")),
+             ("cp", W.cp, got("cp")), ("lnca", W.lnc, got("lnca")), ("luvcmax25top", W.luvcmax25top, got("luvcmax25top")),
+             ("lujmax25top", W.lujmax25top, got("lujmax25top")), ("lutpu25top", W.lutpu25top, got("lutpu25top")),
+             ("gb_mol", W.gb_mol, got("gb_mol")), ("qflx_tran_veg", W.qflx_tran_veg, got("qflx_tran_veg"))]
+    for j in range(1, 21):
+        pairs += [("k_soil_root", W.k_soil_root[j], got("k_soil_root", j - 1)),
+                  ("root_conductance", W.root_conductance[j], got("root_conductance", j - 1)),
+                  ("soil_conductance", W.soil_conductance[j], got("soil_conductance", j - 1))]
+    for i in range(1, 5):
+        pairs += [("vegwp", W.vegwp[i], got("vegwp", i - 1)), ("vegwp_pd", W.vegwp_pd[i], got("vegwp_pd", i - 1))]
+        if day:
+            pairs.append(("vegwp_ln", W.vegwp_ln[i], got("vegwp_ln", i - 1)))
+    for s, sfx in ((1, "sun"), (2, "sha")):
+        pairs += [("ac_phs", W.ac[s], got("ac_phs", s - 1)), ("aj_phs", W.aj[s], got("aj_phs", s - 1)),
+                  ("ap_phs", W.ap[s], got("ap_phs", s - 1)), ("ag_phs", W.ag[s], got("ag_phs", s - 1)),
+                  ("vcmax_z_phs", W.vcmax_z[s], got("vcmax_z_phs", s - 1)), ("tpu_z_phs", W.tpu_z[s], got("tpu_z_phs", s - 1)),
+                  ("kp_z_phs", W.kp_z[s], got("kp_z_phs", s - 1)), ("an_" + sfx, W.an[s], got("an_" + sfx, 0)),
+                  ("lmr%s_z" % sfx, W.lmr_z[s], got("lmr%s_z" % sfx, 0)), ("psn%s_z" % sfx, W.psn_z[s], got("psn%s_z" % sfx, 0)),
+                  ("rs%s_z" % sfx, W.rs_z[s], got("rs%s_z" % sfx, 0)), ("ci%s_z" % sfx, W.ci_z[s], got("ci%s_z" % sfx, 0)),
+                  ("gs_mol_" + sfx, W.gs_mol[s], got("gs_mol_" + sfx, 0)), ("psn" + sfx, W.psn[s], got("psn" + sfx)),
+                  ("psn%s_wc" % sfx, W.psn_wc[s], got("psn%s_wc" % sfx)), ("psn%s_wj" % sfx, W.psn_wj[s], got("psn%s_wj" % sfx)),
+                  ("psn%s_wp" % sfx, W.psn_wp[s], got("psn%s_wp" % sfx)), ("lmr" + sfx, W.lmr[s], got("lmr" + sfx)),
+                  ("rs" + sfx, W.rs[s], got("rs" + sfx))]
+        if day:
+            pairs.append(("gs_mol_%s_ln" % sfx, W.gs_mol_ln[s], got("gs_mol_%s_ln" % sfx, 0)))
+    if day and mtd == 2:
+        pairs.append(("vpd_can", W.vpd_can, got("vpd_can")))
+    return pairs
+
+
 @pytest.mark.parametrize("mtd,seed", [(2, 1201), (1, 1202)])
 def test_photosynthesis_hydraulic_stress_matches_python_restatement(oracle_lib, mtd, seed):
     """the whole of PhotosynthesisHydraulicStress (root-soil conductances, the vcmax / jmax / tpu / lmr temperature response, the
@@ -155,34 +188,8 @@ def test_photosynthesis_hydraulic_stress_matches_python_restatement(oracle_lib, 
         W = pp.photosynthesis_hydraulic_stress(P, M)
         day = P.par_z[1] > 0.0
         got = lambda k, *i: float(S[k][(*i, p)])
-        pairs = [("bsun", W.bsun, work["bsun"][p]), ("bsha", W.bsha, work["bsha"][p]), ("btran", W.btran, work["btran"][p]),
-                 ("c3flag", float(W.c3flag), got("c3flag")), ("qe", W.qe, got("qe")), ("kc", W.kc, got("kc")), ("ko", W.ko, got("ko")),
-                 ("cp", W.cp, got("cp")), ("lnca", W.lnc, got("lnca")), ("luvcmax25top", W.luvcmax25top, got("luvcmax25top")),
-                 ("lujmax25top", W.lujmax25top, got("lujmax25top")), ("lutpu25top", W.lutpu25top, got("lutpu25top")),
-                 ("gb_mol", W.gb_mol, got("gb_mol")), ("qflx_tran_veg", W.qflx_tran_veg, got("qflx_tran_veg"))]
-        for j in range(1, 21):
-            pairs += [("k_soil_root", W.k_soil_root[j], got("k_soil_root", j - 1)),
-                      ("root_conductance", W.root_conductance[j], got("root_conductance", j - 1)),
-                      ("soil_conductance", W.soil_conductance[j], got("soil_conductance", j - 1))]
-        for i in range(1, 5):
-            pairs += [("vegwp", W.vegwp[i], got("vegwp", i - 1)), ("vegwp_pd", W.vegwp_pd[i], got("vegwp_pd", i - 1))]
-            if day:
-                pairs.append(("vegwp_ln", W.vegwp_ln[i], got("vegwp_ln", i - 1)))
-        for s, sfx in ((1, "sun"), (2, "sha")):
-            pairs += [("ac_phs", W.ac[s], got("ac_phs", s - 1)), ("aj_phs", W.aj[s], got("aj_phs", s - 1)),
-                      ("ap_phs", W.ap[s], got("ap_phs", s - 1)), ("ag_phs", W.ag[s], got("ag_phs", s - 1)),
-                      ("vcmax_z_phs", W.vcmax_z[s], got("vcmax_z_phs", s - 1)), ("tpu_z_phs", W.tpu_z[s], got("tpu_z_phs", s - 1)),
-                      ("kp_z_phs", W.kp_z[s], got("kp_z_phs", s - 1)), ("an_" + sfx, W.an[s], got("an_" + sfx, 0)),
-                      ("lmr%s_z" % sfx, W.lmr_z[s], got("lmr%s_z" % sfx, 0)), ("psn%s_z" % sfx, W.psn_z[s], got("psn%s_z" % sfx, 0)),
-                      ("rs%s_z" % sfx, W.rs_z[s], got("rs%s_z" % sfx, 0)), ("ci%s_z" % sfx, W.ci_z[s], got("ci%s_z" % sfx, 0)),
-                      ("gs_mol_" + sfx, W.gs_mol[s], got("gs_mol_" + sfx, 0)), ("psn" + sfx, W.psn[s], got("psn" + sfx)),
-                      ("psn%s_wc" % sfx, W.psn_wc[s], got("psn%s_wc" % sfx)), ("psn%s_wj" % sfx, W.psn_wj[s], got("psn%s_wj" % sfx)),
-                      ("psn%s_wp" % sfx, W.psn_wp[s], got("psn%s_wp" % sfx)), ("lmr" + sfx, W.lmr[s], got("lmr" + sfx)),
-                      ("rs" + sfx, W.rs[s], got("rs" + sfx))]
-            if day:
-                pairs.append(("gs_mol_%s_ln" % sfx, W.gs_mol_ln[s], got("gs_mol_%s_ln" % sfx, 0)))
-        if day and mtd == 2:
-            pairs.append(("vpd_can", W.vpd_can, got("vpd_can")))
+        pairs = phs_output_pairs(W, got, day, mtd)
+        pairs += [("bsun", W.bsun, work["bsun"][p]), ("bsha", W.bsha, work["bsha"][p]), ("btran", W.btran, work["btran"][p])]
         bad = [(k, a, b) for k, a, b in pairs if a != b]
         assert not bad, (int(p1), day, bad[:6])
         stats["day"] += day
