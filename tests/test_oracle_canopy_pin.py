@@ -3,6 +3,7 @@ Python written from FrictionVelocityMod.F90, QSatMod.F90 and CanopyFluxesMod.F90
 import ctypes as C
 
 import numpy as np
+import pytest
 
 from tests import canopy_python as cp
 
@@ -156,3 +157,140 @@ def test_canopyfluxes_matches_python_restatement_other_switches(oracle_lib):
                         use_undercanopy_stability=1, stomatalcond_mtd=1)
     print("CanopyFluxes pin (other switches):", stats)
     assert stats["patches"] == 500
+
+
+def test_vert_tran_sink_hydstress_matches_python_restatement(oracle_lib):
+    """Compute_EffecRootFrac_And_VertTranSink_HydStress (SoilWaterPlantSinkMod.F90:236-328), written from the Fortran column by
+    column: qflx_rootsoi, qflx_phs_neg and qflx_hydr_redist, identical bits"""
+    from ctsm_b200 import abi, synthetic_canopy
+    from tests.util import copy_state
+    sg, S = synthetic_canopy.make_full_case(300, seed=1501)
+    rng = np.random.Generator(np.random.PCG64(1502))
+    synthetic_canopy.balance_state(sg, S, rng, 1e-11)
+    S["k_soil_root"] = rng.uniform(1.0e-9, 2.0e-6, S["k_soil_root"].shape) * (rng.random(S["k_soil_root"].shape) < 0.9)
+    S["vegwp"][3] = rng.uniform(-250000.0, -2000.0, S["vegwp"].shape[1])
+    S["wtcol"][::23] = 0.0
+    S0 = copy_state(S)
+    fh = sg.filters["hydrologyc"]
+    f = abi.make_struct("plantsink", S, sg.bounds)
+    oracle_lib.oracle_vert_tran_sink_hydstress.argtypes = [C.POINTER(abi.Bounds), C.c_int, C.POINTER(C.c_int32),
+                                                          C.POINTER(abi.STRUCTS["plantsink"])]
+    assert oracle_lib.oracle_vert_tran_sink_hydstress(C.byref(sg.bounds), len(fh), abi.i32p(fh), C.byref(f)) == 0
+    neg = 0
+    for c1 in fh:
+        c = int(c1) - 1
+        qflx_phs_neg = 0.0
+        redist = {}
+        for j in range(1, 21):
+            grav2 = float(S0["z"][j + 11, c]) * 1000.0
+            temp = 0.0
+            for p1 in range(int(S0["patchi"][c]), int(S0["patchi"][c]) + int(S0["npatches"][c])):
+                p = p1 - 1
+                if j == 1:
+                    redist[p] = 0.0
+                if S0["patch_active"][p] and S0["frac_veg_nosno"][p] > 0:
+                    if S0["wtcol"][p] > 0.0:
+                        patchflux = float(S0["k_soil_root"][j - 1, p]) * (float(S0["smp_l"][j - 1, c]) - float(S0["vegwp"][3, p]) - grav2)
+                        if patchflux < 0:
+                            redist[p] = redist[p] + patchflux
+                        temp = temp + patchflux * float(S0["wtcol"][p])
+            assert S["qflx_rootsoi"][j - 1, c] == temp, (c1, j)
+            if temp < 0.0:
+                qflx_phs_neg = qflx_phs_neg + temp
+        assert S["qflx_phs_neg"][c] == qflx_phs_neg
+        neg += qflx_phs_neg < 0.0
+        for p, v in redist.items():
+            assert S["qflx_hydr_redist"][p] == v
+    assert neg > 20
+
+
+@pytest.mark.parametrize("with_urban", [False, True])
+def test_balancecheck_residuals_match_numpy(oracle_lib, with_urban):
+    """the residual formulas of BalanceCheck / EnergyBalanceCheck (BalanceCheckMod.F90:565-600 errh2o_col, :648-694 c2g + errh2o_grc,
+    :746-800 snow sources / sinks / errh2osno, :948-1000 errsol / errlon / errseb / netrad), restated in NumPy from the Fortran"""
+    from ctsm_b200 import abi, synthetic_canopy
+    from oracle import oracle
+    from tests.util import copy_state
+    sg, S = synthetic_canopy.make_full_case(500, seed=1601)
+    rng = np.random.Generator(np.random.PCG64(1602))
+    synthetic_canopy.balance_state(sg, S, rng, 1e-6)
+    S["lun_itype"][::13] = 5                                       # some deep-lake columns: the other snow-source form
+    if with_urban:
+        S["lun_itype"][::17] = 7                                   # an urban type: the first (generic) snow form
+    S0 = copy_state(S)
+    prm = abi.default_params()
+    prm.balance_skip_steps = 3                                     # BalanceCheckInit at dtime = 1800 s (test_Balance.pf)
+    L = oracle.lib()
+    rep, st = abi.BalanceReport(), abi.Status()
+    allc = np.arange(1, sg.ncol + 1, dtype=np.int32)
+    f = abi.make_struct("balancecheck", S, sg.bounds)
+    rc = L.oracle_balancecheck(C.byref(prm), C.byref(sg.bounds), len(allc), abi.i32p(allc), C.byref(f), 1, C.byref(rep), C.byref(st))
+    assert rc == 0, st.msg
+    I, dtime = S0, prm.dtime
+    act = I["col_active"] != 0
+    errh2o = np.where(act, I["endwb"] - I["begwb"] - (I["forc_rain"] + I["forc_snow"] + I["qflx_flood"] + I["qflx_sfc_irrig"]
+                      + I["qflx_glcice_dyn_water_flux"] - I["qflx_evap_tot"] - I["qflx_surf"] - I["qflx_qrgwl"] - I["qflx_drain"]
+                      - I["qflx_drain_perched"] - I["qflx_ice_runoff"] - I["qflx_snwcp_discarded_liq"]
+                      - I["qflx_snwcp_discarded_ice"]) * dtime, 0.0)
+    assert np.array_equal(S["errh2o"], errh2o)
+    # snow balance
+    nlevsno = prm.nlevsno
+    lev = np.arange(-nlevsno + 1, 1)[:, None]
+    insnow = lev >= (I["snl"] + 1)[None, :]
+    h2osno_total = I["h2osno_no_layers"].copy()
+    for j in range(nlevsno):                                       # layer order of CalculateTotalH2osno (WaterStateType.F90)
+        h2osno_total = np.where(insnow[j], h2osno_total + I["h2osoi_ice"][j] + I["h2osoi_liq"][j], h2osno_total)
+    lt = I["lun_itype"]
+    src = I["qflx_prec_grnd"] + I["qflx_soliddew_to_top_layer"] + I["qflx_liqdew_to_top_layer"]
+    snk = (I["qflx_solidevap_from_top_layer"] + I["qflx_liqevap_from_top_layer"] + I["qflx_snow_drain"] + I["qflx_snwcp_ice"]
+           + I["qflx_snwcp_liq"] + I["qflx_snwcp_discarded_ice"] + I["qflx_snwcp_discarded_liq"] + I["qflx_sl_top_soil"])
+    lak = lt == 5
+    src = np.where(lak, I["qflx_snow_grnd"] + I["frac_sno_eff"] * (I["qflx_liq_grnd"] + I["qflx_soliddew_to_top_layer"]
+                                                                   + I["qflx_liqdew_to_top_layer"]), src)
+    snk = np.where(lak, I["frac_sno_eff"] * (I["qflx_solidevap_from_top_layer"] + I["qflx_liqevap_from_top_layer"]) + I["qflx_snwcp_ice"]
+                   + I["qflx_snwcp_liq"] + I["qflx_snwcp_discarded_ice"] + I["qflx_snwcp_discarded_liq"] + I["qflx_snow_drain"]
+                   + I["qflx_sl_top_soil"], snk)
+    soil = (lt == 1) | (lt == 2) | (lt == 6) | (lt == 4)
+    src = np.where(soil, (I["qflx_snow_grnd"] - I["qflx_snow_h2osfc"]) + I["frac_sno_eff"] * (I["qflx_liq_grnd"]
+                   + I["qflx_soliddew_to_top_layer"] + I["qflx_liqdew_to_top_layer"]) + I["qflx_h2osfc_to_ice"], src)
+    snk = np.where(soil, I["frac_sno_eff"] * (I["qflx_solidevap_from_top_layer"] + I["qflx_liqevap_from_top_layer"]) + I["qflx_snwcp_ice"]
+                   + I["qflx_snwcp_liq"] + I["qflx_snwcp_discarded_ice"] + I["qflx_snwcp_discarded_liq"] + I["qflx_snow_drain"]
+                   + I["qflx_sl_top_soil"], snk)
+    has = act & (I["snl"] < 0)
+    assert np.array_equal(S["snow_sources"][act], np.where(has, src, 0.0)[act])
+    assert np.array_equal(S["snow_sinks"][act], np.where(has, snk, 0.0)[act])
+    assert np.array_equal(S["errh2osno"], np.where(has, (h2osno_total - I["h2osno_old"]) - (src - snk) * dtime, 0.0))
+    assert has.sum() > 50 and (lak & has).sum() > 3 and (not with_urban or ((lt == 7) & has).sum() > 3)
+    # energy
+    pa = I["patch_active"] != 0
+    c, g = I["column"] - 1, I["gridcell"] - 1
+    urb = (lt[c] >= 7) & (lt[c] <= 9)
+    errsol = I["fsa"] + I["fsr"] - (I["forc_solad"][0, c] + I["forc_solad"][1, c] + I["forc_solai"][0, g] + I["forc_solai"][1, g])
+    errlon = I["eflx_lwrad_out"] - I["eflx_lwrad_net"] - I["forc_lwrad"][c]
+    errseb = (I["sabv"] + I["sabg_chk"] + I["forc_lwrad"][c] - I["eflx_lwrad_out"] - I["eflx_sh_tot"] - I["eflx_lh_tot"]
+              - I["eflx_soil_grnd"] - I["dhsdt_canopy"])
+    sel = pa & ~urb
+    assert np.array_equal(S["errsol"][sel], errsol[sel]) and np.array_equal(S["errlon"][sel], errlon[sel])
+    assert np.array_equal(S["errseb"][sel], errseb[sel])
+    assert np.array_equal(S["netrad"][pa], (I["fsa"] - I["eflx_lwrad_net"])[pa])
+    assert np.all(S["errsol"][~pa] == 0.0) and np.all(S["errseb"][~pa] == 0.0)
+    # gridcell residual with the three c2g averages ('urbanf' / 'unity' scales are 1 off urban landunits)
+    ng = I["begwb_grc"].shape[0]
+    def c2g(x):
+        out, sumwt = np.full(ng, 1.0e36), np.zeros(ng)
+        for ci in range(x.shape[0]):
+            if act[ci] and I["wtgcell"][ci] != 0.0 and x[ci] != 1.0e36:
+                gi = sg.col_gridcell[ci] - 1
+                if sumwt[gi] == 0.0:
+                    out[gi] = 0.0
+                out[gi] = out[gi] + x[ci] * 1.0 * 1.0 * I["wtgcell"][ci]
+                sumwt[gi] = sumwt[gi] + I["wtgcell"][ci]
+        nz = sumwt != 0.0
+        out[nz] = out[nz] / sumwt[nz]
+        return out
+    if not with_urban:
+        errg = I["endwb_grc"] - I["begwb_grc"] - (I["forc_rain_grc"] + I["forc_snow_grc"] + I["forc_flood_grc"] + I["qflx_sfc_irrig_grc"]
+               + c2g(I["qflx_glcice_dyn_water_flux"]) - I["qflx_evap_tot_grc"] - I["qflx_surf_grc"] - I["qflx_qrgwl_grc"]
+               - I["qflx_drain_grc"] - I["qflx_drain_perched_grc"] - I["qflx_ice_runoff_grc"] - c2g(I["qflx_snwcp_discarded_liq"])
+               - c2g(I["qflx_snwcp_discarded_ice"])) * dtime
+        assert np.array_equal(S["errh2o_grc"], errg)
