@@ -252,6 +252,12 @@ void oracle_set_exposedvegp_filter(const ctsm_bounds_t* bounds, int num_nolakeur
   *num_noexposedvegp = fn;
 }
 
+/* Wet_BulbS, HumanIndexMod.F90:987-1030 (Stull 2011); pinned by the reference's own vectors (HumanStress_test/test_humanstress.pf:26-29) */
+double oracle_wet_bulbs(double tc, double rh) {
+  return tc * atan(0.151977 * sqrt(rh + 8.313659)) + atan(tc + rh) - atan(rh - 1.676331)
+         + 0.00391838 * pow(rh, (3.0 / 2.0)) * atan(0.023101 * rh) - 4.686035;
+}
+
 int oracle_canopyfluxes(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, int num_exposedvegp,
                         const int32_t* filter_exposedvegp, const ctsm_canopyfluxes_fields_t* fld, ctsm_status_t* st) {
   cf_ctx ctx, *x = &ctx;
@@ -717,8 +723,7 @@ int oracle_canopyfluxes(const ctsm_params_t* prm, const ctsm_bounds_t* bounds, i
       const double vap = (rh / 100.0) * e_ref2m;                        /* VaporPres :1243 */
       P1(vap_ref2m, p) = vap;
       if ((rh < 0.0 || rh > 100.0) && !ctx.err_code) { ctx.err_code = CTSM_ERR_RH; ctx.err_index = p; }   /* Wet_BulbS :1016-1022 endrun */
-      const double wbt = tc * atan(0.151977 * sqrt(rh + 8.313659)) + atan(tc + rh) - atan(rh - 1.676331)
-                         + 0.00391838 * pow(rh, (3.0 / 2.0)) * atan(0.023101 * rh) - 4.686035;        /* :1024-1027 */
+      const double wbt = oracle_wet_bulbs(tc, rh);                      /* :1024-1027 */
       P1(wbt_ref2m, p) = wbt;
       const double tf = (tc) * 9.0 / 5.0 + 32.0;                        /* HeatIndex :1039-1095 */
       double hi;

@@ -45,6 +45,7 @@ void oracle_moninobukini(double zetamaxstable, double ur, double thv, double dth
 int oracle_quadratic(double a, double b, double c, double* r1, double* r2);
 double oracle_plc(double x, double psi50, double ck);
 double oracle_d1plc(double x, double psi50, double ck);
+double oracle_wet_bulbs(double tc, double rh);
 void oracle_photosyns_timestepinit(cf_ctx* x, const ctsm_bounds_t* bounds);
 void oracle_photosynthesis_total(cf_ctx* x, int fn, const int32_t* filterp);
 void oracle_photosynthesis_hydraulic_stress(cf_ctx* x, int fn, const int32_t* filterp, const double* esat_tv,

@@ -467,8 +467,7 @@ int oracle_bare_ground_fluxes(const ctsm_params_t* prm, const ctsm_bounds_t* bou
       const double vap = (rh / 100.0) * e_ref2m;                               /* VaporPres :1243 */
       PP(vap_ref2m, p) = vap;
       if (rh < 0.0 || rh > 100.0) { rc = CTSM_ERR_RH; if (st) { st->code = rc; st->subgrid_index = p; } goto done; }
-      const double wbt = tc * atan(0.151977 * sqrt(rh + 8.313659)) + atan(tc + rh) - atan(rh - 1.676331)
-                         + 0.00391838 * pow(rh, (3.0 / 2.0)) * atan(0.023101 * rh) - 4.686035;       /* Wet_BulbS :1024-1027 */
+      const double wbt = oracle_wet_bulbs(tc, rh);                             /* Wet_BulbS :1024-1027 */
       PP(wbt_ref2m, p) = wbt;
       const double tf = (tc) * 9.0 / 5.0 + 32.0;                               /* HeatIndex :1039-1095 */
       double hi;

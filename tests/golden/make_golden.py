@@ -30,6 +30,9 @@ gold = {
         {"a": 1.0, "b": 2.0, "c": 5.0, "aborts": True},
         {"a": 1.0, "b": 4.0, "c": 4.0 + 100.0 * 2.220446049250313e-16, "aborts": True},
     ],
+    # HumanStress_test/test_humanstress.pf:26-29 (Wet_BulbS, tolerance 1e-8)
+    "wet_bulbs": [{"tc": 0.0, "rh": 0.0, "wbt": -3.6531108341574, "tol": 1e-8},
+                  {"tc": 0.0, "rh": 100.0, "wbt": -0.13165370616986, "tol": 1e-8}],
     "balance_skip_steps": [[1800, 3], [7200, 3], [300, 13], [36, 101]],
     "truncate_small_values": [
         {"name": "tsv_truncates_correct_points", "eps": 1e-13, "filter": [1, 2, 3],

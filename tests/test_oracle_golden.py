@@ -4,6 +4,7 @@
                    (params from PhotosynthesisMod.F90:929-934 setParamsForTesting)
   quadratic        src/utils/test/quadratic_test/test_quadratic.pf
   truncate_small_values   src/utils/test/numerics_test/
+  Wet_BulbS        src/biogeophys/test/HumanStress_test/test_humanstress.pf:26-29 (fast human-stress indices)
   BalanceCheckInit skip steps   src/biogeophys/test/Balance_test/test_Balance.pf:39-105
   filter order     src/main/test/filter_test/test_filter_col.pf (stable ascending order)
 The vectors are also stored in tests/golden/reference_unit_tests.json (written by
@@ -53,6 +54,17 @@ def test_quadratic_near_zero_discriminant(oracle_lib):
         r1, r2 = C.c_double(), C.c_double()
         assert oracle_lib.oracle_quadratic(1.0, 4.0, 4.0 + d, C.byref(r1), C.byref(r2)) == 0
         assert abs(r1.value + 2.0) < 1e-6 and abs(r2.value + 2.0) < 1e-6
+
+
+def test_wet_bulbs_known_answers(oracle_lib):
+    oracle_lib.oracle_wet_bulbs.argtypes = [C.c_double, C.c_double]
+    oracle_lib.oracle_wet_bulbs.restype = C.c_double
+    for g in GOLD["wet_bulbs"]:
+        assert abs(oracle_lib.oracle_wet_bulbs(g["tc"], g["rh"]) - g["wbt"]) <= g["tol"]
+    tc = 100.0                                                     # the .pf's sweep: never NaN from 100 C down to -50 C at rh = 100
+    while tc > -50.0:
+        assert np.isfinite(oracle_lib.oracle_wet_bulbs(tc, 100.0))
+        tc -= 0.1
 
 
 def test_balancecheck_skip_steps(oracle_lib):
