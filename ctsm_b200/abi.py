@@ -356,6 +356,7 @@ def lib():
                                          C.c_int, C.c_int, C.POINTER(BalanceReport), C.POINTER(Status)]
     L.ctsm_b200_set_soil_tuning.argtypes = [vp, C.c_int]
     L.ctsm_b200_set_soilwater_tuning.argtypes = [vp, C.c_int]
+    L.ctsm_b200_set_sink_tuning.argtypes = [vp, C.c_int]
     for fn in ("vert_tran_sink_hydstress", "vert_tran_sink_default", "biogeophys_pre_flux_calcs", "calculate_surface_humidity",
                "bare_ground_fluxes", "hydrology_infiltration", "calc_ozone_uptake", "calc_ozone_stress", "build_snow_filter", "snow_water", "snow_capping", "snow_layers", "water_table", "hydrology_diagnostics", "balancecheck_init", "balancecheck", "soilfluxes", "patch2col"):
         getattr(L, "ctsm_b200_" + fn).restype = C.c_int

@@ -57,6 +57,7 @@ extern "C" int ctsm_b200_init(const ctsm_params_t* p, ctsm_b200_ctx** out) {
   if (const char* e = getenv("CTSM_B200_NT_SPLIT")) ctx->tune.nt_split = atoi(e);
   if (const char* e = getenv("CTSM_B200_SOIL_STREAM")) ctx->tune.soil_stream = atoi(e);
   if (const char* e = getenv("CTSM_B200_SW_WARP")) ctx->tune.sw_warp = atoi(e);
+  if (const char* e = getenv("CTSM_B200_SINK_WARP")) ctx->tune.sink_warp = atoi(e);
   const int rc = [&]() -> int {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
@@ -106,6 +107,12 @@ extern "C" int ctsm_b200_finalize(ctsm_b200_ctx* ctx) {
 extern "C" int ctsm_b200_set_soil_tuning(ctsm_b200_ctx* ctx, int soil_stream) {
   if (!ctx) return CTSM_ERR_BAD_ARG;
   if (soil_stream >= 0) ctx->tune.soil_stream = soil_stream;
+  return CTSM_OK;
+}
+
+extern "C" int ctsm_b200_set_sink_tuning(ctsm_b200_ctx* ctx, int sink_warp) {
+  if (!ctx) return CTSM_ERR_BAD_ARG;
+  if (sink_warp >= 0) ctx->tune.sink_warp = sink_warp;
   return CTSM_OK;
 }
 

@@ -221,6 +221,83 @@ plantsink_kernel(PlantSinkDev f, int begc0, int ldc, int begp0, int ldp, int num
   f.qflx_phs_neg[cc] = neg;
 }
 
+// The same routine with one WARP per column (default; CTSM_B200_SINK_WARP=0 selects the thread-per-column kernel above, and
+// tests/test_gpu_balance.py proves the two bit-identical).  The routine is a stream over k_soil_root(p, 1:nlevsoi) - 71 % of its
+// bytes - and a thread per column reads it with a stride of the column's patch count (15 doubles) between lanes.  Here lane i owns
+// patch patchi + i: the 20 level loads of a warp are contiguous runs of the column's patches (consecutive warps continue them),
+// all 20 are in flight before the first is used, and the reference's ascending-patch summation order is kept by handing the
+// contributions through shared memory to lane j, which adds level j's terms one by one.
+constexpr int SINK_WARPS = 8;                 // warps per block
+constexpr int SINK_LD = 33;                   // padded lane stride of a level's row (bank-conflict-free transposition)
+constexpr int SINK_HALF = NLEVSOI / 2;        // levels handed over per phase (halves the shared memory: 5 blocks per SM)
+static_assert(NLEVSOI % 2 == 0 && NLEVSOI <= 32, "plantsink_warp_kernel: level halves across the lanes");
+__global__ void __launch_bounds__(SINK_WARPS * 32, 4)
+plantsink_warp_kernel(PlantSinkDev f, int begc0, int ldc, int begp0, int ldp, int numf, const int32_t* __restrict__ filterc) {
+  __shared__ double s_c[SINK_WARPS][SINK_HALF * SINK_LD];     // [level of the half][lane] contributions flux * wtcol
+  __shared__ double s_col[SINK_WARPS][2 * NLEVSOI];           // smp_l(c, j), grav2(j); later temp(j)
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int fc = blockIdx.x * SINK_WARPS + w;
+  if (fc >= numf) return;                                     // warp-uniform
+  const int cc = filterc[fc] - begc0;
+  const int pi = f.patchi[cc], np = f.npatches[cc];
+  if (lane < NLEVSOI) {
+    s_col[w][lane] = f.smp_l[(size_t)lane * ldc + cc];
+    s_col[w][NLEVSOI + lane] = f.z[(size_t)(lane + 1 - SNOSOI_LO) * ldc + cc] * 1000.0;
+  }
+  __syncwarp();
+  double temp = 0.0;                                          // lane j - 1 accumulates level j
+  for (int base = 0; base < np; base += 32) {
+    const bool mine = base + lane < np;
+    const int pp = pi + base + lane - begp0;
+    bool q = false;
+    double wt = 0.0, vw = 0.0, redist = 0.0;
+    double k[NLEVSOI];
+    if (mine) {                                               // the level loads do not wait for the predicate's loads
+#pragma unroll
+      for (int j = 0; j < NLEVSOI; ++j) k[j] = __ldg(&f.k_soil_root[(size_t)j * ldp + pp]);
+      vw = f.vegwp[(size_t)3 * ldp + pp];
+      wt = f.wtcol[pp];
+      q = f.patch_active[pp] && f.frac_veg_nosno[pp] > 0 && wt > 0.0;
+    }
+    unsigned qm = __ballot_sync(FULL, q);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (q) {
+#pragma unroll
+        for (int jj = 0; jj < SINK_HALF; ++jj) {
+          const int j = h * SINK_HALF + jj;
+          const double flux = k[j] * (s_col[w][j] - vw - s_col[w][NLEVSOI + j]);
+          if (flux < 0) redist = redist + flux;
+          s_c[w][jj * SINK_LD + lane] = flux * wt;
+        }
+      }
+      __syncwarp();
+      if (lane >= h * SINK_HALF && lane < (h + 1) * SINK_HALF) {
+        unsigned m = qm;
+        while (m) {                                           // ascending patches: the reference's order
+          const int i = __ffs(m) - 1;
+          m &= m - 1;
+          temp = temp + s_c[w][(lane - h * SINK_HALF) * SINK_LD + i];
+        }
+      }
+      __syncwarp();
+    }
+    if (mine) f.qflx_hydr_redist[pp] = redist;
+  }
+  if (lane < NLEVSOI) {
+    f.qflx_rootsoi[(size_t)lane * ldc + cc] = temp;
+    s_col[w][lane] = temp;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    double neg = 0.0;
+#pragma unroll
+    for (int j = 0; j < NLEVSOI; ++j) { const double t = s_col[w][j]; if (t < 0.0) neg = neg + t; }
+    f.qflx_phs_neg[cc] = neg;
+  }
+}
+
 // Compute_EffecRootFrac_And_VertTranSink_Default (SoilWaterPlantSinkMod.F90:332-424): one thread per column, its contiguous
 // patches inner and ascending (the reference's summation order).  Levels nlevsoi+1..nlevgrnd of rootr_col are not touched.
 __global__ void __launch_bounds__(128)
@@ -695,9 +772,14 @@ extern "C" int ctsm_b200_vert_tran_sink_hydstress(ctsm_b200_ctx* ctx, const ctsm
     if (rc) return rc;
   }
   if (num_filterc > 0) {
-    plantsink_kernel<<<grid_for(num_filterc, 128), 128, 0, ctx->stream>>>(
-        d, hf->alloc.begc, hf->alloc.endc - hf->alloc.begc + 1, hf->alloc.begp, hf->alloc.endp - hf->alloc.begp + 1,
-        num_filterc, dfilter);
+    if (ctx->tune.sink_warp)
+      plantsink_warp_kernel<<<(num_filterc + SINK_WARPS - 1) / SINK_WARPS, SINK_WARPS * 32, 0, ctx->stream>>>(
+          d, hf->alloc.begc, hf->alloc.endc - hf->alloc.begc + 1, hf->alloc.begp, hf->alloc.endp - hf->alloc.begp + 1,
+          num_filterc, dfilter);
+    else
+      plantsink_kernel<<<grid_for(num_filterc, 128), 128, 0, ctx->stream>>>(
+          d, hf->alloc.begc, hf->alloc.endc - hf->alloc.begc + 1, hf->alloc.begp, hf->alloc.endp - hf->alloc.begp + 1,
+          num_filterc, dfilter);
     ctx->launches++;
   }
   if (mem != CTSM_MEM_DEVICE) {

@@ -73,7 +73,7 @@ struct ctsm_b200_ctx {
   std::vector<cudaEvent_t> ev_round, ev_tail;
   cudaEvent_t ev_join = nullptr;
   int* h_counts = nullptr; int h_counts_cap = 0;
-  struct Tuning { int tail_max = 0, nt_budget = 0, tail_lanes = 1, nt_split = 1, soil_stream = 1, sw_warp = 1; } tune;
+  struct Tuning { int tail_max = 0, nt_budget = 0, tail_lanes = 1, nt_split = 1, soil_stream = 1, sw_warp = 1, sink_warp = 1; } tune;
   int* dbg_counts = nullptr; int* dbg_tail_end = nullptr; int dbg_npass = 0;
   // CTSM_MEM_HOST resident window (abi.cu: ctsm_b200_host_window_begin / _end): persistent device mirrors keyed by the
   // host array's base address, what is fresh on the device in the current window, copy streams, event pool

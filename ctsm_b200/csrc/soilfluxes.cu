@@ -197,6 +197,64 @@ patch2col_kernel(Patch2ColDev f, int begc0, int begp0, int numc, const int32_t* 
     f.qflx_liqdew_to_top_layer[cc] = a[7]; f.qflx_solidevap_from_top_layer[cc] = a[8]; f.qflx_soliddew_to_top_layer[cc] = a[9];
   }
 }
+
+// clm_drv_patch2col with one WARP per column (default; CTSM_B200_SINK_WARP=0 selects the thread-per-column kernels above;
+// bit-identical, tests/test_gpu_soilfluxes.py).  Lane i owns patch patchi + i, so every patch field is read in contiguous runs
+// (a thread per column strides by the column's patch count and fetched 9.4 x the algorithmic bytes from DRAM); the weighted
+// terms go through shared memory to lane k, which adds average k's terms in ascending patch order (the reference's order).
+constexpr int P2C_WARPS = 8;
+constexpr int P2C_LD = 33;
+template <bool ALLC>
+__global__ void __launch_bounds__(P2C_WARPS * 32)
+patch2col_warp_kernel(Patch2ColDev f, int begc0, int begp0, int numc, const int32_t* __restrict__ filterc) {
+  __shared__ double s_t[P2C_WARPS][10 * P2C_LD];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int fc = blockIdx.x * P2C_WARPS + w;
+  if (fc >= numc) return;                                     // warp-uniform
+  const int cc = filterc[fc] - begc0;
+  const int pi = f.patchi[cc], np = f.patchf[cc] - pi + 1;
+  double acc = 0.0;                                           // lane k accumulates average k
+  for (int base = 0; base < np; base += 32) {
+    const int pp = pi + base + lane - begp0;
+    const bool q = (base + lane < np) && f.patch_active[pp];
+    if (q) {
+      const double wt = f.wtcol[pp];
+      s_t[w][3 * P2C_LD + lane] = f.qflx_evap_soi[pp] * wt;
+      if (!ALLC) {
+        s_t[w][0 * P2C_LD + lane] = f.qflx_ev_snow[pp] * wt;
+        s_t[w][1 * P2C_LD + lane] = f.qflx_ev_soil[pp] * wt;
+        s_t[w][2 * P2C_LD + lane] = f.qflx_ev_h2osfc[pp] * wt;
+        s_t[w][4 * P2C_LD + lane] = f.qflx_evap_tot_patch[pp] * wt;
+        s_t[w][5 * P2C_LD + lane] = f.qflx_tran_veg[pp] * wt;
+        s_t[w][6 * P2C_LD + lane] = f.qflx_liqevap_from_top_layer_patch[pp] * wt;
+        s_t[w][7 * P2C_LD + lane] = f.qflx_liqdew_to_top_layer_patch[pp] * wt;
+        s_t[w][8 * P2C_LD + lane] = f.qflx_solidevap_from_top_layer_patch[pp] * wt;
+        s_t[w][9 * P2C_LD + lane] = f.qflx_soliddew_to_top_layer_patch[pp] * wt;
+      }
+    }
+    unsigned m = __ballot_sync(FULL, q);
+    __syncwarp();
+    if (lane < 10 && (!ALLC || lane == 3)) {
+      while (m) {
+        const int i = __ffs(m) - 1;
+        m &= m - 1;
+        acc = acc + s_t[w][lane * P2C_LD + i];
+      }
+    }
+    __syncwarp();
+  }
+  if (ALLC) {
+    if (lane == 3) f.qflx_evap_soi_col[cc] = acc;
+    return;
+  }
+  double* const out[10] = {f.qflx_ev_snow_col, f.qflx_ev_soil_col, f.qflx_ev_h2osfc_col, f.qflx_evap_soi_col, f.qflx_evap_tot,
+                           f.qflx_tran_veg_col, f.qflx_liqevap_from_top_layer, f.qflx_liqdew_to_top_layer,
+                           f.qflx_solidevap_from_top_layer, f.qflx_soliddew_to_top_layer};
+#pragma unroll
+  for (int k = 0; k < 10; ++k)
+    if (lane == k) out[k][cc] = acc;
+}
 }  // namespace
 
 extern "C" int ctsm_b200_patch2col(ctsm_b200_ctx* ctx, const ctsm_bounds_t* bounds, int num_allc, const int32_t* filter_allc,
@@ -225,12 +283,21 @@ extern "C" int ctsm_b200_patch2col(ctsm_b200_ctx* ctx, const ctsm_bounds_t* boun
     rc = stage_filter(ctx, ctx->arena_filter1, filter_nolakec, num_nolakec, &dfc);
     if (rc) return rc;
   }
+  const bool warp = ctx->tune.sink_warp != 0;
   if (num_nolakec > 0) {
-    patch2col_kernel<false><<<grid_for(num_nolakec, 128), 128, 0, ctx->stream>>>(d, hf->alloc.begc, hf->alloc.begp, num_nolakec, dfc);
+    if (warp)
+      patch2col_warp_kernel<false><<<(num_nolakec + P2C_WARPS - 1) / P2C_WARPS, P2C_WARPS * 32, 0, ctx->stream>>>(
+          d, hf->alloc.begc, hf->alloc.begp, num_nolakec, dfc);
+    else
+      patch2col_kernel<false><<<grid_for(num_nolakec, 128), 128, 0, ctx->stream>>>(d, hf->alloc.begc, hf->alloc.begp, num_nolakec, dfc);
     ctx->launches++;
   }
   if (num_allc > 0) {
-    patch2col_kernel<true><<<grid_for(num_allc, 128), 128, 0, ctx->stream>>>(d, hf->alloc.begc, hf->alloc.begp, num_allc, dfa);
+    if (warp)
+      patch2col_warp_kernel<true><<<(num_allc + P2C_WARPS - 1) / P2C_WARPS, P2C_WARPS * 32, 0, ctx->stream>>>(
+          d, hf->alloc.begc, hf->alloc.begp, num_allc, dfa);
+    else
+      patch2col_kernel<true><<<grid_for(num_allc, 128), 128, 0, ctx->stream>>>(d, hf->alloc.begc, hf->alloc.begp, num_allc, dfa);
     ctx->launches++;
   }
   if (mem != CTSM_MEM_DEVICE) {

@@ -408,6 +408,10 @@ int  ctsm_b200_set_soil_tuning(ctsm_b200_ctx* ctx, int soil_stream);
  * per column with the soil levels across the lanes (soilwater_retry_warp_kernel), 0 one thread per column (soilwater_kernel<2>).
  * Bit-identical results; a negative value leaves the setting unchanged. */
 int  ctsm_b200_set_soilwater_tuning(ctsm_b200_ctx* ctx, int sw_warp);
+/* Compute_EffecRootFrac_And_VertTranSink_HydStress: sink_warp 1 (default; CTSM_B200_SINK_WARP) runs one warp per column with the
+ * column's patches across the lanes (plantsink_warp_kernel: contiguous reads of k_soil_root), 0 one thread per column
+ * (plantsink_kernel).  Bit-identical results; a negative value leaves the setting unchanged. */
+int  ctsm_b200_set_sink_tuning(ctsm_b200_ctx* ctx, int sink_warp);
 /* Diagnostic of the last ctsm_b200_canopyfluxes call (synchronises the stream): for every ITERATION round r < cap,
  * list_len[r] = patches the round's list kernels served, tail_end[r] = patches handed to the tail kernel up to and
  * including round r.  Returns the number of rounds written. */

@@ -65,10 +65,14 @@ def test_balancecheck_before_init_is_an_error(oracle_lib):
     L.ctsm_b200_finalize(ctx)
 
 
-@pytest.mark.parametrize("mem", [abi.MEM_HOST, abi.MEM_DEVICE])
-def test_vert_tran_sink_matches_oracle(gpu_ctx, oracle_lib, mem):
+@pytest.mark.parametrize("mem,sink_warp", [(abi.MEM_HOST, 1), (abi.MEM_DEVICE, 1), (abi.MEM_HOST, 0)])
+def test_vert_tran_sink_matches_oracle(gpu_ctx, oracle_lib, mem, sink_warp):
+    """both kernels (one warp per column: default; one thread per column) against the oracle, bit for bit; inactive patches,
+    zero-weight patches and patches without exposed vegetation are present"""
     L, ctx, prm = gpu_ctx
+    assert L.ctsm_b200_set_sink_tuning(ctx, sink_warp) == 0
     sg, S = _case(500, 41)
+    S["wtcol"][::19] = 0.0
     # k_soil_root / vegwp as CanopyFluxes leaves them
     from tests.test_gpu_canopy import run_oracle
     assert run_oracle(oracle_lib, prm, sg, S)[0] == 0
@@ -91,3 +95,4 @@ def test_vert_tran_sink_matches_oracle(gpu_ctx, oracle_lib, mem):
     for name in ("qflx_rootsoi", "qflx_phs_neg", "qflx_hydr_redist"):
         assert np.array_equal(got[name], ref[name]), name     # same operations in the same order: bit-identical
     assert np.abs(ref["qflx_rootsoi"][:, fh - 1]).max() > 0
+    assert L.ctsm_b200_set_sink_tuning(ctx, 1) == 0

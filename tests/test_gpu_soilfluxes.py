@@ -106,10 +106,12 @@ def test_soilfluxes_clump_bounds_and_urban_refusal(gpu_ctx, oracle_lib):
     assert rc == 16 and st.subgrid_index == c
 
 
-@pytest.mark.parametrize("mem", [abi.MEM_HOST, abi.MEM_DEVICE])
-def test_patch2col_matches_oracle_bitwise(gpu_ctx, oracle_lib, mem):
-    """clm_drv_patch2col (clm_driver.F90:1655): eleven p2c averages, same accumulation order, bit-identical."""
+@pytest.mark.parametrize("mem,warp", [(abi.MEM_HOST, 1), (abi.MEM_DEVICE, 1), (abi.MEM_DEVICE, 0)])
+def test_patch2col_matches_oracle_bitwise(gpu_ctx, oracle_lib, mem, warp):
+    """clm_drv_patch2col (clm_driver.F90:1655): eleven p2c averages, same accumulation order, bit-identical - the warp-per-column
+    kernels (default) and the thread-per-column ones (ctsm_b200_set_sink_tuning)."""
     L, ctx, prm = gpu_ctx
+    assert L.ctsm_b200_set_sink_tuning(ctx, warp) == 0
     sg, S = _case(oracle_lib, prm, 1500, 57)
     assert _run_oracle(oracle_lib, prm, sg, S)[0] == 0            # SoilFluxes first: its outputs are what gets averaged
     ref, got = copy_state(S), copy_state(S)
@@ -134,3 +136,4 @@ def test_patch2col_matches_oracle_bitwise(gpu_ctx, oracle_lib, mem):
     for fs in abi.FIELDS["patch2col"]:
         assert np.array_equal(got[fs.name], ref[fs.name], equal_nan=True), fs.name
     assert np.abs(ref["qflx_evap_soi_col"][fc - 1]).max() > 0
+    assert L.ctsm_b200_set_sink_tuning(ctx, 1) == 0
