@@ -19,8 +19,10 @@ timeout 400 python bench.py --routines pre,canopyfluxes,soiltemperature,soilflux
 timeout 300 python bench.py --size f09 --steps 5 --no-cpu > $out/${tag}_bench_f09.json 2>> $out/${tag}_bench_f02.err
 timeout 300 python bench.py --size f19 --members 32 --steps 5 --no-cpu > $out/${tag}_bench_f19x32.json 2>> $out/${tag}_bench_f02.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_reference.json 2>> $out/${tag}_bench_f02.err
+timeout 300 python bench.py --routines hydro,canopyfluxes,soiltemperature,soilfluxes,patch2col,plantsink,soilwater,balancecheck --steps 5 --no-cpu --no-e2e > $out/${tag}_bench_f02_hydro.json 2>> $out/${tag}_bench_f02.err
+ROUTINES=plantsink,patch2col timeout 300 bash tools/gpu_ncu.sh $tag "sink:plantsink_warp_kernel|patch2col_warp_kernel:9:3" > $out/${tag}_ncu_sink.log 2>&1
 cat $out/${tag}_pytest.log $out/${tag}_smoke.log; head -34 $out/${tag}_launch_summary_f02.txt; tail -12 $out/${tag}_launch_summary_f02.txt; tail -3 $out/${tag}_bench_f02.err
-for f in f02 f02_pre f09 f19x32 reference; do python - <<PY
+for f in f02 f02_pre f09 f19x32 reference f02_hydro; do python - <<PY
 import json
 try:
     d = json.loads(open("$out/${tag}_bench_$f.json").read().strip().splitlines()[-1])
