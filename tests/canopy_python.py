@@ -354,13 +354,21 @@ def canopy_fluxes_patch(P, M, phs):
         vpd = max((svpts - eah), 50.0) * 0.001
         # photosynthesis with plant hydraulic stress
         P.esat_tv, P.eair, P.rb, P.qsatl, P.qaf, P.t_veg = svpts, eah, rb, qsatl, qaf, t_veg
-        W = phs(P, M)
-        P.vegwp, P.gs_mol = W.vegwp, W.gs_mol
-        P.bsun_in, P.bsha_in = W.bsun, W.bsha
-        btran = W.btran
-        qflx_tran_veg = W.qflx_tran_veg
-        rssun, rssha = W.rs[1], W.rs[2]
-        O.phs = W
+        if M.use_hydrstress:
+            W = phs(P, M)
+            P.vegwp, P.gs_mol = W.vegwp, W.gs_mol
+            P.bsun_in, P.bsha_in = W.bsun, W.bsha
+            btran = W.btran
+            qflx_tran_veg = W.qflx_tran_veg
+            rssun, rssha = W.rs[1], W.rs[2]
+            O.phs = W
+        else:                                                         # Photosynthesis for sunlit, then shaded leaves (:1143-1166)
+            P.gs_mol_in = P.gs_mol_patch
+            O.psn_sun = phs(P, M, 1, btran)
+            P.gs_mol_in = O.psn_sun.gs_mol
+            O.psn_sha = phs(P, M, 2, btran)
+            P.gs_mol_patch = O.psn_sha.gs_mol
+            rssun, rssha = O.psn_sun.rs, O.psn_sha.rs
         # fluxes and the leaf temperature update (:1176-1369)
         wta = 1.0 / rah_above
         wtl = sa_leaf / rb
@@ -381,14 +389,27 @@ def canopy_fluxes_patch(P, M, phs):
             rppdry = 0.0
         efpot = P.forc_rho * ((elai + esai) / rb) * (qsatl - qaf)
         h2ocan = P.liqcan + P.snocan
-        if efpot > 0.0:
-            if btran > btran0:
-                rpp = rppdry + P.fwet
+        if M.use_hydrstress:
+            if efpot > 0.0:
+                if btran > btran0:
+                    rpp = rppdry + P.fwet
+                else:
+                    rpp = P.fwet
+                rpp = min(rpp, (qflx_tran_veg + h2ocan / dtime) / efpot)
             else:
-                rpp = P.fwet
-            rpp = min(rpp, (qflx_tran_veg + h2ocan / dtime) / efpot)
+                rpp = 1.0
         else:
-            rpp = 1.0
+            if efpot > 0.0:
+                if btran > btran0:
+                    qflx_tran_veg = efpot * rppdry
+                    rpp = rppdry + P.fwet
+                else:
+                    rpp = P.fwet
+                    qflx_tran_veg = 0.0
+                rpp = min(rpp, (qflx_tran_veg + h2ocan / dtime) / efpot)
+            else:
+                rpp = 1.0
+                qflx_tran_veg = 0.0
         wtaq = P.frac_veg_nosno / raw_above
         wtlq = P.frac_veg_nosno * (elai + esai) / rb * rpp
         snow_depth_c = M.z_dl
@@ -436,6 +457,11 @@ def canopy_fluxes_patch(P, M, phs):
                    - (efsh + dc1 * wtga * dt_veg) - (efe + dc2 * wtgaq * qsatldT * dt_veg) - (cp_leaf / dtime) * (t_veg - tl_ini))
         efpot = P.forc_rho * ((elai + esai) / rb) * (wtgaq * (qsatl + qsatldT * dt_veg) - wtgq0 * P.qg - wtaq0 * P.forc_q)
         qflx_evap_veg = rpp * efpot
+        if not M.use_hydrstress:
+            if efpot > 0.0 and btran > btran0:
+                qflx_tran_veg = efpot * rppdry
+            else:
+                qflx_tran_veg = 0.0
         ecidif = max(0.0, qflx_evap_veg - qflx_tran_veg - h2ocan / dtime)
         qflx_evap_veg = min(qflx_evap_veg, qflx_tran_veg + h2ocan / dtime)
         eflx_sh_veg = efsh + dc1 * wtga * dt_veg + err + erre + HVAP * ecidif
@@ -538,13 +564,19 @@ def canopy_fluxes_patch(P, M, phs):
     if abs(snocan) < 1.e-10 * abs(snocan_baseline):                  # truncate_small_values (NumericsMod.F90:53-99)
         snocan = 0.0
     O.snocan, O.liqcan = snocan, liqcan
-    W = O.phs
-    O.fpsn = W.psn[1] * P.laisun + W.psn[2] * P.laisha                # PhotosynthesisTotal (PhotosynthesisMod.F90:2065-2151)
-    O.fpsn_wc = W.psn_wc[1] * P.laisun + W.psn_wc[2] * P.laisha
-    O.fpsn_wj = W.psn_wj[1] * P.laisun + W.psn_wj[2] * P.laisha
-    O.fpsn_wp = W.psn_wp[1] * P.laisun + W.psn_wp[2] * P.laisha
+    if M.use_hydrstress:
+        W = O.phs
+        psn, psn_wc, psn_wj, psn_wp, gs_ss = W.psn, W.psn_wc, W.psn_wj, W.psn_wp, W.gs_mol
+    else:
+        A, B = O.psn_sun, O.psn_sha
+        psn, psn_wc, psn_wj, psn_wp = {1: A.psn, 2: B.psn}, {1: A.psn_wc, 2: B.psn_wc}, {1: A.psn_wj, 2: B.psn_wj}, {1: A.psn_wp, 2: B.psn_wp}
+        gs_ss = {1: A.gs_mol_phase, 2: B.gs_mol_phase}
+    O.fpsn = psn[1] * P.laisun + psn[2] * P.laisha                    # PhotosynthesisTotal (PhotosynthesisMod.F90:2065-2151)
+    O.fpsn_wc = psn_wc[1] * P.laisun + psn_wc[2] * P.laisha
+    O.fpsn_wj = psn_wj[1] * P.laisun + psn_wj[2] * P.laisha
+    O.fpsn_wp = psn_wp[1] * P.laisun + psn_wp[2] * P.laisha
     if P.near_local_noon and O.fpsn > 0.0:
-        gs = 1.e-6 * (P.laisun * W.gs_mol[1] + P.laisha * W.gs_mol[2])
+        gs = 1.e-6 * (P.laisun * gs_ss[1] + P.laisha * gs_ss[2])
         O.iwue_ln = O.fpsn / gs if gs > 0.0 else SPVAL
     else:
         O.iwue_ln = SPVAL

@@ -858,3 +858,310 @@ def photosynthesis_hydraulic_stress(P, M):
     else:
         W.btran = W.bsun
     return W
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Photosynthesis without plant hydraulic stress (PhotosynthesisMod.F90:1243-2062) and its root finder hybrid / brent / ci_func
+# (:2251-2485, :2564-2701), one leaf class (phase 'sun' or 'sha') per call, same configuration as above
+# ------------------------------------------------------------------------------------------------------------------------------
+def ci_func(P, M, W, ci):
+    """:2564-2701; W carries ac, aj, ap, ag, an, gs_mol of the patch; returns fval"""
+    if P.c3flag:
+        W.ac = W.vcmax_z * max(ci - P.cp, 0.0) / (ci + P.kc * (1.0 + P.oair / P.ko))
+        W.aj = W.je * max(ci - P.cp, 0.0) / (4.0 * ci + 8.0 * P.cp)
+        W.ap = 3.0 * W.tpu_z
+    else:
+        W.ac = W.vcmax_z
+        W.aj = P.qe * W.par_z * 4.6
+        W.ap = W.kp_z * max(ci, 0.0) / P.forc_pbot
+    r1, r2 = quadratic(P.theta_cj, -(W.ac + W.aj), W.ac * W.aj)
+    ai = min(r1, r2)
+    r1, r2 = quadratic(M.theta_ip, -(ai + W.ap), ai * W.ap)
+    W.ag = max(0.0, min(r1, r2))
+    W.an = W.ag - W.lmr_z
+    W.ci_evals += 1
+    if W.an < 0.0:
+        return 0.0
+    cs = P.cair - 1.4 / P.gb_mol * W.an * P.forc_pbot
+    cs = max(cs, MAX_CS)
+    if M.stomatalcond_mtd == MEDLYN2011:
+        mi, ms = P.medlynintercept, P.medlynslope
+        term = 1.6 * W.an / (cs / P.forc_pbot * 1.e06)
+        aquad = 1.0
+        bquad = -(2.0 * (mi * 1.e-06 + term) + (ms * term) * (ms * term) / (P.gb_mol * 1.e-06 * W.rh_can))
+        cquad = mi * mi * 1.e-12 + (2.0 * mi * 1.e-06 + term * (1.0 - ms * ms / W.rh_can)) * term
+        r1, r2 = quadratic(aquad, bquad, cquad)
+        W.gs_mol = max(r1, r2) * 1.e06
+    elif M.stomatalcond_mtd == BB1987:
+        aquad = cs
+        bquad = cs * (P.gb_mol - P.bbb) - P.mbb * W.an * P.forc_pbot
+        cquad = -P.gb_mol * (cs * P.bbb + P.mbb * W.an * P.forc_pbot * W.rh_can)
+        r1, r2 = quadratic(aquad, bquad, cquad)
+        W.gs_mol = max(r1, r2)
+    return ci - P.cair + W.an * P.forc_pbot * (1.4 * W.gs_mol + 1.6 * P.gb_mol) / (P.gb_mol * W.gs_mol)
+
+
+def brent(P, M, W, x1, x2, f1, f2, tol):
+    """:2371-2485; returns the root"""
+    itmax, eps = 20, 1.e-2
+    a, b, fa, fb = x1, x2, f1, f2
+    if (fa > 0.0 and fb > 0.0) or (fa < 0.0 and fb < 0.0):
+        raise EndRun("root must be bracketed for brent")
+    c, fc = b, fb
+    d = e = None
+    it = 0
+    while True:
+        if it == itmax:
+            break
+        it += 1
+        if (fb > 0.0 and fc > 0.0) or (fb < 0.0 and fc < 0.0):
+            c = a
+            fc = fa
+            d = b - a
+            e = d
+        if abs(fc) < abs(fb):
+            a = b
+            b = c
+            c = a
+            fa = fb
+            fb = fc
+            fc = fa
+        tol1 = 2.0 * eps * abs(b) + 0.5 * tol
+        xm = 0.5 * (c - b)
+        if abs(xm) <= tol1 or fb == 0.0:
+            W.brent_iters += it
+            return b
+        if abs(e) >= tol1 and abs(fa) > abs(fb):
+            s = fb / fa
+            if a == c:
+                p = 2.0 * xm * s
+                q = 1.0 - s
+            else:
+                q = fa / fc
+                r = fb / fc
+                p = s * (2.0 * xm * q * (q - r) - (b - a) * (r - 1.0))
+                q = (q - 1.0) * (r - 1.0) * (s - 1.0)
+            if p > 0.0:
+                q = -q
+            p = abs(p)
+            if 2.0 * p < min(3.0 * xm * q - abs(tol1 * q), abs(e * q)):
+                e = d
+                d = p / q
+            else:
+                d = xm
+                e = d
+        else:
+            d = xm
+            e = d
+        a = b
+        fa = fb
+        if abs(d) > tol1:
+            b = b + d
+        else:
+            b = b + math.copysign(tol1, xm)
+        fb = ci_func(P, M, W, b)
+        if fb == 0.0:
+            break
+    W.brent_iters += it
+    return b
+
+
+def hybrid(P, M, W, x0):
+    """:2251-2368; returns x0 (the ci the routine hands back)"""
+    eps, eps1, itmax = 1.e-2, 1.e-4, 40
+    f0 = ci_func(P, M, W, x0)
+    if f0 == 0.0:
+        return x0
+    minx, minf = x0, f0
+    x1 = x0 * 0.99
+    f1 = ci_func(P, M, W, x1)
+    if f1 == 0.0:
+        return x1
+    if f1 < minf:
+        minx, minf = x1, f1
+    it = 0
+    while True:
+        it += 1
+        dx = -f1 * (x1 - x0) / (f1 - f0)
+        x = x1 + dx
+        tol = abs(x) * eps
+        if abs(dx) < tol:
+            x0 = x
+            break
+        x0 = x1
+        f0 = f1
+        x1 = x
+        f1 = ci_func(P, M, W, x1)
+        if f1 < minf:
+            minx, minf = x1, f1
+        if abs(f1) <= eps1:
+            x0 = x1
+            break
+        if f1 * f0 < 0.0:
+            x = brent(P, M, W, x0, x1, f0, f1, tol)
+            W.brent_calls += 1
+            x0 = x
+            break
+        if it > itmax:
+            f1 = ci_func(P, M, W, minx)
+            W.itmax_exits += 1
+            break
+    return x0
+
+
+def photosynthesis(P, M, phase, btran):
+    """:1243-2062 for one patch and one leaf class (phase SUN or SHA), nlevcan = 1.  Sets the patch-level values both phases share
+    on P (c3flag, qe, kc, ko, cp, bbb, mbb, gb_mol) and returns the namespace W of what the call writes."""
+    W = SimpleNamespace(ci_evals=0, brent_calls=0, brent_iters=0, itmax_exits=0, gs_mol=P.gs_mol_in, vpd_can=None, gs_mol_ln=None)
+    medlyn = M.stomatalcond_mtd == MEDLYN2011
+    W.par_z = P.par_z[phase]
+    lai_z = P.lai_z[phase]
+    vcmaxcint = P.vcmaxcintsun if phase == SUN else P.vcmaxcintsha
+    lmrc = fth25(M.lmrhd, M.lmrse)
+    if round(P.c3psn) == 1:
+        P.c3flag = True
+    elif round(P.c3psn) == 0:
+        P.c3flag = False
+    if P.c3flag:
+        P.qe = 0.0
+        bbbopt = BBBOPT_C3
+    else:
+        P.qe = 0.05
+        bbbopt = BBBOPT_C4
+    if not medlyn:
+        P.bbb = max(bbbopt * btran, 1.0)
+        P.mbb = P.mbbopt
+    kc25 = M.kc25_coef * P.forc_pbot
+    ko25 = M.ko25_coef * P.forc_pbot
+    sco = 0.5 * 0.209 / M.cp25_yr2000
+    cp25 = 0.5 * P.oair / sco
+    P.kc = kc25 * ft(P.t_veg, M.kcha)
+    P.ko = ko25 * ft(P.t_veg, M.koha)
+    P.cp = cp25 * ft(P.t_veg, M.cpha)
+    W.c3flag, W.qe, W.kc, W.ko, W.cp = P.c3flag, P.qe, P.kc, P.ko, P.cp
+    if (P.slatop * P.leafcn) <= 0.0:
+        raise EndRun("slatop or leafcn is zero")
+    lnc = 1.0 / (P.slatop * P.leafcn)
+    lnc = min(lnc, 10.0)
+    W.lnc = lnc
+    vcmax25top = lnc * P.flnr * M.fnr * M.act25 * P.dayl_factor
+    vcmax25top = vcmax25top * P.fnitr
+    t10c = min(max((P.t10 - TFRZ), 11.0), 35.0)
+    jmax25top = ((2.59 - 0.035 * t10c) * vcmax25top) * M.jmax25top_sf
+    tpu25top = M.tpu25ratio * vcmax25top
+    kp25top = M.kp25ratio * vcmax25top
+    lmr25top = vcmax25top * M.leaf_mr_vcm if P.c3flag else vcmax25top * 0.025
+    luna = M.use_luna and P.c3flag and P.crop == 0
+    t_veg = P.t_veg
+    jmax_z = 0.0
+    for iv in range(1, P.nrad + 1):
+        nscaler = vcmaxcint
+        lmr25 = lmr25top * nscaler
+        if luna:
+            lmr25 = M.leaf_mr_vcm * P.vcmx25_z
+        if P.c3flag:
+            W.lmr_z = lmr25 * ft(t_veg, M.lmrha) * fth(t_veg, M.lmrhd, M.lmrse, lmrc)
+        else:
+            W.lmr_z = lmr25 * 2.0 ** ((t_veg - (TFRZ + 25.0)) / 10.0)
+            W.lmr_z = W.lmr_z / (1.0 + math.exp(1.3 * (t_veg - (TFRZ + 55.0))))
+        if W.par_z <= 0.0:
+            W.vcmax_z = jmax_z = W.tpu_z = W.kp_z = 0.0
+        else:
+            if luna:
+                vcmax25 = P.vcmx25_z
+                jmax25 = P.jmx25_z
+                tpu25 = M.tpu25ratio * vcmax25
+                if phase == SHA and P.vcmaxcintsun > 0.0:
+                    vcmax25 = vcmax25 * P.vcmaxcintsha / P.vcmaxcintsun
+                    jmax25 = jmax25 * P.vcmaxcintsha / P.vcmaxcintsun
+                    tpu25 = tpu25 * P.vcmaxcintsha / P.vcmaxcintsun
+            else:
+                vcmax25 = vcmax25top * nscaler
+                jmax25 = jmax25top * nscaler
+                tpu25 = tpu25top * nscaler
+            kp25 = kp25top * nscaler
+            vcmaxse = (668.39 - 1.07 * t10c) * M.vcmaxse_sf
+            jmaxse = (659.70 - 0.75 * t10c) * M.jmaxse_sf
+            tpuse = (668.39 - 1.07 * t10c) * M.tpuse_sf
+            vcmaxc = fth25(M.vcmaxhd, vcmaxse)
+            jmaxc = fth25(M.jmaxhd, jmaxse)
+            tpuc = fth25(M.tpuhd, tpuse)
+            W.vcmax_z = vcmax25 * ft(t_veg, M.vcmaxha) * fth(t_veg, M.vcmaxhd, vcmaxse, vcmaxc)
+            jmax_z = jmax25 * ft(t_veg, M.jmaxha) * fth(t_veg, M.jmaxhd, jmaxse, jmaxc)
+            W.tpu_z = tpu25 * ft(t_veg, M.tpuha) * fth(t_veg, M.tpuhd, tpuse, tpuc)
+            if not P.c3flag:
+                W.vcmax_z = vcmax25 * 2.0 ** ((t_veg - (TFRZ + 25.0)) / 10.0)
+                W.vcmax_z = W.vcmax_z / (1.0 + math.exp(0.2 * ((TFRZ + 15.0) - t_veg)))
+                W.vcmax_z = W.vcmax_z / (1.0 + math.exp(0.3 * (t_veg - (TFRZ + 40.0))))
+            W.kp_z = kp25 * 2.0 ** ((t_veg - (TFRZ + 25.0)) / 10.0)
+        W.vcmax_z = W.vcmax_z * btran
+        W.lmr_z = W.lmr_z * btran
+        if M.light_inhibit and W.par_z > 0.0:
+            W.lmr_z = W.lmr_z * 0.67
+    rsmax0 = 2.e4
+    cf = P.forc_pbot / (RGAS * 1.e-3 * P.tgcm) * 1.e06
+    gb = 1.0 / P.rb
+    P.gb_mol = gb * cf
+    W.gb_mol = P.gb_mol
+    for iv in range(1, P.nrad + 1):
+        if W.par_z <= 0.0:
+            W.ac = W.aj = W.ap = W.ag = 0.0
+            W.an = W.ag - W.lmr_z
+            W.psn_z = W.psn_wc_z = W.psn_wj_z = W.psn_wp_z = 0.0
+            if not medlyn:
+                W.rs_z = min(rsmax0, 1.0 / P.bbb * cf)
+            else:
+                W.rs_z = min(rsmax0, 1.0 / P.medlynintercept * cf)
+            W.ci_z = 0.0
+            W.gs_mol_phase = cf / W.rs_z
+        else:
+            ceair = min(P.eair, P.esat_tv)
+            if not medlyn:
+                W.rh_can = ceair / P.esat_tv
+            else:
+                W.rh_can = max((P.esat_tv - ceair), MEDLYN_RH_CAN_MAX) * MEDLYN_RH_CAN_FACT
+                W.vpd_can = W.rh_can
+            qabs = 0.5 * (1.0 - M.fnps) * W.par_z * 4.6
+            r1, r2 = quadratic(M.theta_psii, -(qabs + jmax_z), qabs * jmax_z)
+            W.je = min(r1, r2)
+            W.ci_z = 0.7 * P.cair if P.c3flag else 0.4 * P.cair
+            ciold = W.ci_z
+            hybrid(P, M, W, ciold)
+            if W.an < 0.0:
+                W.gs_mol = P.bbb if not medlyn else P.medlynintercept
+            W.gs_mol_phase = W.gs_mol
+            W.gs_mol_ln = W.gs_mol if P.near_local_noon else SPVAL
+            cs = P.cair - 1.4 / P.gb_mol * W.an * P.forc_pbot
+            cs = max(cs, MAX_CS)
+            W.ci_z = P.cair - W.an * P.forc_pbot * (1.4 * W.gs_mol + 1.6 * P.gb_mol) / (P.gb_mol * W.gs_mol)
+            W.ci_z = max(W.ci_z, 1.e-06)
+            gs = W.gs_mol / cf
+            W.rs_z = min(1.0 / gs, rsmax0)
+            W.rs_z = W.rs_z / P.o3coefg[phase]
+            W.psn_z = W.ag
+            W.psn_z = W.psn_z * P.o3coefv[phase]
+            W.psn_wc_z = W.psn_wj_z = W.psn_wp_z = 0.0
+            if W.ac <= W.aj and W.ac <= W.ap:
+                W.psn_wc_z = W.psn_z
+            elif W.aj < W.ac and W.aj <= W.ap:
+                W.psn_wj_z = W.psn_z
+            elif W.ap < W.ac and W.ap < W.aj:
+                W.psn_wp_z = W.psn_z
+            if W.gs_mol < 0.0:
+                raise EndRun("Negative stomatal conductance")
+    psncan = psncan_wc = psncan_wj = psncan_wp = lmrcan = gscan = laican = 0.0
+    for iv in range(1, P.nrad + 1):
+        psncan = psncan + W.psn_z * lai_z
+        psncan_wc = psncan_wc + W.psn_wc_z * lai_z
+        psncan_wj = psncan_wj + W.psn_wj_z * lai_z
+        psncan_wp = psncan_wp + W.psn_wp_z * lai_z
+        lmrcan = lmrcan + W.lmr_z * lai_z
+        gscan = gscan + lai_z / (P.rb + W.rs_z)
+        laican = laican + lai_z
+    if laican > 0.0:
+        W.psn, W.psn_wc, W.psn_wj, W.psn_wp = psncan / laican, psncan_wc / laican, psncan_wj / laican, psncan_wp / laican
+        W.lmr = lmrcan / laican
+        W.rs = laican / gscan - P.rb
+    else:
+        W.psn = W.psn_wc = W.psn_wj = W.psn_wp = W.lmr = W.rs = 0.0
+    return W

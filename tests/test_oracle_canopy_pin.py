@@ -123,12 +123,38 @@ def _canopy_pin(oracle_lib, seed, ngrid, npatch, **switches):
     for p1 in fe[:npatch]:
         p = int(p1) - 1
         P = canopy_patch_inputs(S0, p)
-        O = cp.canopy_fluxes_patch(P, M, pp.photosynthesis_hydraulic_stress)
+        P.gs_mol_patch = float(S0["gs_mol"][0, p])
+        O = cp.canopy_fluxes_patch(P, M, pp.photosynthesis_hydraulic_stress if prm.use_hydrstress else pp.photosynthesis)
         got = lambda k, *i: float(S[k][(*i, p)])
         pairs = [(k, getattr(O, k), got(k)) for k in patch_fields]
-        pairs += [("num_iter", O.num_iter, int(S["num_iter"][p])), ("bsun", O.phs.bsun, got("bsun")), ("bsha", O.phs.bsha, got("bsha"))]
+        pairs += [("num_iter", O.num_iter, int(S["num_iter"][p]))]
         day = P.par_z[1] > 0.0
-        pairs += phs_output_pairs(O.phs, got, day, prm.stomatalcond_mtd)
+        if prm.use_hydrstress:
+            pairs += [("bsun", O.phs.bsun, got("bsun")), ("bsha", O.phs.bsha, got("bsha"))]
+            pairs += phs_output_pairs(O.phs, got, day, prm.stomatalcond_mtd)
+        else:
+            for W, sfx in ((O.psn_sun, "sun"), (O.psn_sha, "sha")):
+                pairs += [("lmr%s_z" % sfx, W.lmr_z, got("lmr%s_z" % sfx, 0)), ("psn%s_z" % sfx, W.psn_z, got("psn%s_z" % sfx, 0)),
+                          ("rs%s_z" % sfx, W.rs_z, got("rs%s_z" % sfx, 0)), ("ci%s_z" % sfx, W.ci_z, got("ci%s_z" % sfx, 0)),
+                          ("gs_mol_" + sfx, W.gs_mol_phase, got("gs_mol_" + sfx, 0)), ("psn" + sfx, W.psn, got("psn" + sfx)),
+                          ("psn%s_wc" % sfx, W.psn_wc, got("psn%s_wc" % sfx)), ("psn%s_wj" % sfx, W.psn_wj, got("psn%s_wj" % sfx)),
+                          ("psn%s_wp" % sfx, W.psn_wp, got("psn%s_wp" % sfx)), ("lmr" + sfx, W.lmr, got("lmr" + sfx)),
+                          ("rs" + sfx, W.rs, got("rs" + sfx))]
+                if W.par_z > 0.0:
+                    pairs.append(("gs_mol_%s_ln" % sfx, W.gs_mol_ln, got("gs_mol_%s_ln" % sfx, 0)))
+            W = O.psn_sha                                                 # the arrays both phases share hold the shaded call's values
+            pairs += [("ac", W.ac, got("ac", 0)), ("aj", W.aj, got("aj", 0)), ("ap", W.ap, got("ap", 0)), ("ag", W.ag, got("ag", 0)),
+                      ("an", W.an, got("an", 0)), ("vcmax_z", W.vcmax_z, got("vcmax_z", 0)), ("tpu_z", W.tpu_z, got("tpu_z", 0)),
+                      ("kp_z", W.kp_z, got("kp_z", 0)), ("c3flag", float(W.c3flag), got("c3flag")), ("qe", W.qe, got("qe")),
+                      ("kc", W.kc, got("kc")), ("ko", W.ko, got("ko")), ("cp", W.cp, got("cp")), ("lnca", W.lnc, got("lnca")),
+                      ("gb_mol", W.gb_mol, got("gb_mol")),
+                      # luvcmax25top / lujmax25top / lutpu25top are written by PhotosynthesisHydraulicStress only (:3266-3268)
+                      ("luvcmax25top", float(S0["luvcmax25top"][p]), got("luvcmax25top"))]
+            if W.par_z > 0.0:
+                pairs.append(("gs_mol", W.gs_mol, got("gs_mol", 0)))
+                if prm.stomatalcond_mtd == 2:
+                    pairs.append(("vpd_can", W.vpd_can, got("vpd_can")))
+            stats["brent"] = stats.get("brent", 0) + O.psn_sun.brent_calls + O.psn_sha.brent_calls
         for j in range(1, 26):
             pairs += [("rootr", O.rootr[j], got("rootr", j - 1)), ("eff_porosity", O.eff_porosity[j], float(S["eff_porosity"][j - 1, P.c])),
                       ("h2osoi_liqvol", O.h2osoi_liqvol[j], float(S["h2osoi_liqvol"][j + 11, P.c]))]
@@ -157,6 +183,15 @@ def test_canopyfluxes_matches_python_restatement_other_switches(oracle_lib):
                         use_undercanopy_stability=1, stomatalcond_mtd=1)
     print("CanopyFluxes pin (other switches):", stats)
     assert stats["patches"] == 500
+
+
+@pytest.mark.parametrize("mtd", [2, 1])
+def test_canopyfluxes_without_hydraulic_stress_matches_python_restatement(oracle_lib, mtd):
+    """use_hydrstress = .false.: Photosynthesis / hybrid / brent / ci_func for sunlit then shaded leaves, btran from
+    calc_root_moist_stress, transpiration from the potential evaporation - identical bits, Medlyn and Ball-Berry"""
+    stats = _canopy_pin(oracle_lib, 1403 + mtd, 300, 600, use_hydrstress=0, stomatalcond_mtd=mtd)
+    print("CanopyFluxes pin (no PHS, stomatalcond_mtd=%d):" % mtd, stats)
+    assert stats["patches"] == 600 and stats["brent"] > 0
 
 
 def test_vert_tran_sink_hydstress_matches_python_restatement(oracle_lib):
