@@ -586,3 +586,110 @@ def canopy_fluxes_patch(P, M, phs):
     O.ustar, O.um, O.uaf, O.taf, O.qaf, O.obu, O.zeta, O.vpd, O.rh_af = ustar, um, uaf, taf, qaf, obu, zeta, vpd, rhaf
     O.dleaf_patch = dleaf_patch
     return O
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# BareGroundFluxes for one patch without exposed vegetation (BareGroundFluxesMod.F90:63-579; the human-stress indices are pinned
+# separately, tests/test_oracle_canopy.py)
+# ------------------------------------------------------------------------------------------------------------------------------
+RGAS_SHR = 6.02214e26 * 1.38065e-23
+BETA_PARAM = 7.2
+MEIER_PARAM3 = 70.0
+
+
+def dewpoint(e, t):
+    """BareGroundFluxesMod.F90:549-579"""
+    if t < TKFRZ:
+        d = 273.86 * math.log(e / 611.21) / (22.587 - math.log(e / 611.21))
+    else:
+        d = 243.04 * math.log(e / 610.94) / (17.625 - math.log(e / 610.94))
+    return d + TKFRZ
+
+
+def bare_ground_fluxes_patch(P, M):
+    niters = 3
+    O = SimpleNamespace()
+    O.btran = 0.0
+    O.t_veg = P.forc_t
+    cf_bare = P.forc_pbot / (RGAS_SHR * 0.001 * P.thm) * 1.e06
+    O.rssun = 1.0 / 1.e15 * cf_bare
+    O.rssha = 1.0 / 1.e15 * cf_bare
+    displa = 0.0
+    ur = max(M.wind_min, math.sqrt(P.forc_u * P.forc_u + P.forc_v * P.forc_v))
+    dth = P.thm - P.t_grnd
+    dqh = P.forc_q - P.qg
+    dthv = dth * (1.0 + 0.61 * P.forc_q) + 0.61 * P.forc_th * dqh
+    zldis = P.forc_hgt_u_patch
+    z0mg, z0hg, z0qg = P.z0mg, P.z0hg, P.z0qg
+    um, obu = monin_obuk_ini(M.zetamaxstable, ur, P.thv, dthv, zldis, z0mg)
+    hgt_u, hgt_t, hgt_q = P.forc_hgt_u_patch, P.forc_hgt_t_patch, P.forc_hgt_q_patch
+    fm = None
+    for it in range(1, niters + 1):
+        fv = friction_velocity(hgt_u, hgt_t, hgt_q, displa, z0mg, z0hg, z0qg, obu, it, ur, um, fm)
+        ustar, temp1, temp2, temp12m, temp22m, fm = fv.ustar, fv.temp1, fv.temp2, fv.temp12m, fv.temp22m, fv.fm
+        tstar = temp1 * dth
+        qstar = temp2 * dqh
+        if M.z0param_method == 1:
+            z0hg = z0mg / math.exp(M.a_coef * (ustar * z0mg / NU_PARAM) ** M.a_exp)
+        elif M.z0param_method == 2:
+            z0hg = MEIER_PARAM3 * NU_PARAM / ustar * math.exp(-BETA_PARAM * ustar ** (0.5) * (abs(tstar)) ** (0.25))
+        z0qg = z0hg
+        hgt_u = P.forc_hgt_u + z0mg + displa
+        hgt_t = P.forc_hgt_t + z0hg + displa
+        hgt_q = P.forc_hgt_q + z0qg + displa
+        thvstar = tstar * (1.0 + 0.61 * P.forc_q) + 0.61 * P.forc_th * qstar
+        zeta = zldis * VKC * GRAV * thvstar / (ustar * ustar * P.thv)
+        if zeta >= 0.0:
+            zeta = min(M.zetamaxstable, max(zeta, 0.01))
+            um = max(ur, 0.1)
+        else:
+            zeta = max(-100.0, min(zeta, -0.01))
+            wc = P.beta * (-GRAV * ustar * thvstar * P.zii / P.thv) ** 0.333
+            um = math.sqrt(ur * ur + wc * wc)
+        obu = zldis / zeta
+    O.num_iter = niters
+    O.vds, O.u10, O.u10_clm, O.va, O.fv = fv.vds, fv.u10, fv.u10_clm, fv.va, fv.fv
+    ram = 1.0 / (ustar * ustar / um)
+    rah = 1.0 / (temp1 * ustar)
+    raw = 1.0 / (temp2 * ustar)
+    raih = P.forc_rho * CPAIR / rah
+    _, forc_esat, _, _ = qsat(P.forc_t, P.forc_pbot)
+    forc_e = max((P.forc_q * P.forc_pbot) / (P.forc_q + 0.622), 0.01 * forc_esat)
+    forc_dewpoint = dewpoint(forc_e, P.t_grnd)
+    raiw = None
+    if dqh > 0.0:
+        raiw = 0.0 if P.t_grnd > forc_dewpoint else P.forc_rho / (raw)
+    else:
+        if M.soil_resis_method == 0:
+            raiw = 0.0 if P.t_grnd > forc_dewpoint else P.soilbeta * P.forc_rho / (raw)
+        if M.soil_resis_method == 1:
+            raiw = P.forc_rho / (raw + P.soilresis)
+    O.ram1 = ram
+    O.cgrnds = raih
+    O.cgrndl = raiw * P.dqgdT
+    O.cgrnd = O.cgrnds + P.htvp * O.cgrndl
+    O.taux = -P.forc_rho * P.forc_u / ram
+    O.tauy = -P.forc_rho * P.forc_v / ram
+    O.eflx_sh_grnd = -raih * dth
+    O.eflx_sh_tot = O.eflx_sh_grnd
+    O.eflx_sh_snow = -raih * (P.thm - P.t_soisno[P.snl + 1])
+    O.eflx_sh_soil = -raih * (P.thm - P.t_soisno[1])
+    O.eflx_sh_h2osfc = -raih * (P.thm - P.t_h2osfc)
+    O.qflx_tran_veg = 0.0
+    O.qflx_evap_veg = 0.0
+    O.qflx_evap_soi = -raiw * dqh
+    O.qflx_evap_tot_patch = O.qflx_evap_soi
+    O.qflx_ev_snow = -raiw * (P.forc_q - P.qg_snow)
+    O.qflx_ev_soil = -raiw * (P.forc_q - P.qg_soil)
+    O.qflx_ev_h2osfc = -raiw * (P.forc_q - P.qg_h2osfc)
+    O.t_ref2m = P.thm + temp1 * dth * (1.0 / temp12m - 1.0 / temp1)
+    O.q_ref2m = P.forc_q + temp2 * dqh * (1.0 / temp22m - 1.0 / temp2)
+    qsat_ref2m, _, _, _ = qsat(O.t_ref2m, P.forc_pbot)
+    O.rh_ref2m = min(100.0, O.q_ref2m / qsat_ref2m * 100.0)
+    O.kbm1 = math.log(z0mg / z0hg)
+    O.z0mg_p, O.z0hg_p, O.z0qg_p = z0mg, z0hg, z0qg
+    O.forc_hgt_u_patch, O.forc_hgt_t_patch, O.forc_hgt_q_patch = hgt_u, hgt_t, hgt_q
+    O.um, O.obu, O.zeta, O.ustar = um, obu, zeta, ustar
+    for k in ("displa", "z0mv", "z0hv", "z0qv", "dlrad", "ulrad", "dhsdt_canopy", "eflx_sh_stem"):
+        setattr(O, k, 0.0)
+    return O

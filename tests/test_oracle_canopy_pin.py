@@ -329,3 +329,59 @@ def test_balancecheck_residuals_match_numpy(oracle_lib, with_urban):
                - I["qflx_drain_grc"] - I["qflx_drain_perched_grc"] - I["qflx_ice_runoff_grc"] - c2g(I["qflx_snwcp_discarded_liq"])
                - c2g(I["qflx_snwcp_discarded_ice"])) * dtime
         assert np.array_equal(S["errh2o_grc"], errg)
+
+
+@pytest.mark.parametrize("method,resis", [(2, 1), (1, 0)], ids=["meier2022_sl14", "zengwang2007_leepielke"])
+def test_bare_ground_fluxes_matches_python_restatement(oracle_lib, method, resis):
+    """BareGroundFluxes (three Monin-Obukhov passes, scalar roughness of the ground, the dew-point switch of the latent-heat
+    conductance, fluxes and 2 m diagnostics) for every patch without exposed vegetation: identical bits; the column's z0hg / z0qg
+    take the value of the column's last such patch"""
+    from types import SimpleNamespace
+    from ctsm_b200 import abi
+    from tests.test_oracle_preflux import case, run_preflux, run_humidity, run_bare
+    from tests.util import copy_state
+    sg, S = case(n=500, seed=1701, wet_every=3)
+    prm = abi.default_params()
+    prm.z0param_method, prm.soil_resis_method = method, resis
+    assert run_preflux(oracle_lib, prm, sg, S) == 0
+    assert run_humidity(oracle_lib, sg, S) == 0
+    rng = np.random.Generator(np.random.PCG64(1702))
+    S["t_grnd"] = S["t_grnd"] + rng.uniform(-6.0, 3.0, S["t_grnd"].shape)      # both sides of the dew point and of freezing
+    S0 = copy_state(S)
+    assert run_bare(oracle_lib, prm, sg, S) == 0
+    M = SimpleNamespace(**{k: getattr(prm, k) for k, _ in abi.Params._fields_ if not k.startswith("reserved")})
+    fields = ("btran t_veg rssun rssha displa z0mv z0hv z0qv dlrad ulrad dhsdt_canopy eflx_sh_stem z0mg_p z0hg_p z0qg_p kbm1 um obu zeta "
+              "ustar vds u10 u10_clm va fv ram1 cgrnds cgrndl cgrnd taux tauy eflx_sh_grnd eflx_sh_tot eflx_sh_snow eflx_sh_soil "
+              "eflx_sh_h2osfc qflx_tran_veg qflx_evap_veg qflx_evap_soi qflx_evap_tot_patch qflx_ev_snow qflx_ev_soil qflx_ev_h2osfc "
+              "t_ref2m q_ref2m rh_ref2m forc_hgt_u_patch forc_hgt_t_patch forc_hgt_q_patch").split()
+    fp = sg.filters["noexposedvegp"]
+    last = {}
+    stats = {"dew": 0, "nodew": 0, "stable": 0, "unstable": 0}
+    for p1 in fp:
+        p = int(p1) - 1
+        c, g = int(S0["column"][p]) - 1, int(S0["gridcell"][p]) - 1
+        fc, fg, fpp = (lambda k: float(S0[k][c])), (lambda k: float(S0[k][g])), (lambda k: float(S0[k][p]))
+        P = SimpleNamespace(
+            forc_u=fg("forc_u"), forc_v=fg("forc_v"), forc_hgt_u=fg("forc_hgt_u"), forc_hgt_t=fg("forc_hgt_t"), forc_hgt_q=fg("forc_hgt_q"),
+            snl=int(S0["snl"][c]), forc_t=fc("forc_t"), forc_th=fc("forc_th"), forc_q=fc("forc_q"), forc_pbot=fc("forc_pbot"),
+            forc_rho=fc("forc_rho"), t_grnd=fc("t_grnd"), t_h2osfc=fc("t_h2osfc"), thv=fc("thv"), beta=fc("beta"), zii=fc("zii"),
+            qg=fc("qg"), qg_snow=fc("qg_snow"), qg_soil=fc("qg_soil"), qg_h2osfc=fc("qg_h2osfc"), dqgdT=fc("dqgdT"), htvp=fc("htvp"),
+            soilbeta=fc("soilbeta"), soilresis=fc("soilresis"), z0mg=fc("z0mg"),
+            z0hg=fc("z0hg"), z0qg=fc("z0qg"),                  # every patch starts from the column's value at entry (:309-311)
+            t_soisno={j: float(S0["t_soisno"][j + 11, c]) for j in range(-11, 26)}, thm=fpp("thm"),
+            forc_hgt_u_patch=fpp("forc_hgt_u_patch"), forc_hgt_t_patch=fpp("forc_hgt_t_patch"), forc_hgt_q_patch=fpp("forc_hgt_q_patch"))
+        O = cp.bare_ground_fluxes_patch(P, M)
+        bad = [(k, getattr(O, k), float(S[k][p])) for k in fields if getattr(O, k) != float(S[k][p])]
+        assert not bad, (int(p1), bad[:6])
+        assert S["num_iter"][p] == O.num_iter
+        assert np.all(S["rootr"][:, p] == 0.0) and np.all(S["rresis"][:, p] == 0.0)
+        if S0["lun_itype"][c] in (1, 2):
+            assert S["t_ref2m_r"][p] == O.t_ref2m and S["rh_ref2m_r"][p] == O.rh_ref2m
+        last[c] = (O.z0hg_p, O.z0qg_p)
+        stats["dew"] += O.cgrndl != 0.0
+        stats["nodew"] += O.cgrndl == 0.0
+        stats["stable"] += O.zeta > 0
+        stats["unstable"] += O.zeta < 0
+    for c, (zh, zq) in last.items():
+        assert S["z0hg"][c] == zh and S["z0qg"][c] == zq
+    assert min(stats["stable"], stats["unstable"]) > 50 and (resis == 1 or min(stats["dew"], stats["nodew"]) > 20), stats
