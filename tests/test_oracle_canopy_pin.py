@@ -96,7 +96,7 @@ def canopy_patch_inputs(S, p):
     return P
 
 
-def _canopy_pin(oracle_lib, seed, ngrid, npatch, **switches):
+def _canopy_pin(oracle_lib, seed, ngrid, npatch, crop_every=0, **switches):
     from types import SimpleNamespace
     from ctsm_b200 import abi, synthetic_canopy
     from tests import phs_python as pp
@@ -106,6 +106,8 @@ def _canopy_pin(oracle_lib, seed, ngrid, npatch, **switches):
     prm = abi.default_params()
     for k, v in switches.items():
         setattr(prm, k, v)
+    if crop_every:
+        S["pft_crop"][np.unique(S["itype"])[1::crop_every]] = 1.0
     S0 = copy_state(S)
     fe = sg.filters["exposedvegp"]
     f = abi.make_struct("canopyfluxes", S, sg.bounds)
@@ -166,6 +168,7 @@ def _canopy_pin(oracle_lib, seed, ngrid, npatch, **switches):
         stats["iters"] += O.num_iter
         stats["max_iter"] = max(stats["max_iter"], O.num_iter)
         stats["capped"] += O.num_iter > prm.itmax_canopy_fluxes
+        stats["crop"] = stats.get("crop", 0) + (P.crop != 0)
     return stats
 
 
@@ -183,6 +186,16 @@ def test_canopyfluxes_matches_python_restatement_other_switches(oracle_lib):
                         use_undercanopy_stability=1, stomatalcond_mtd=1)
     print("CanopyFluxes pin (other switches):", stats)
     assert stats["patches"] == 500
+
+
+@pytest.mark.parametrize("hyd", [1, 0])
+def test_canopyfluxes_matches_python_restatement_photosynthesis_switches(oracle_lib, hyd):
+    """use_luna, light_inhibit and modifyphoto_and_lmr_forcrop off, crop types present: the prescribed-Vcmax, uninhibited-respiration
+    and crop branches of both photosynthesis routines inside the restated CanopyFluxes"""
+    stats = _canopy_pin(oracle_lib, 1410 + hyd, 250, 450, use_hydrstress=hyd, use_luna=0, light_inhibit=0, modifyphoto_and_lmr_forcrop=0,
+                        crop_every=3)
+    print("CanopyFluxes pin (photosynthesis switches, use_hydrstress=%d):" % hyd, stats)
+    assert stats["patches"] == 450 and stats["crop"] > 30
 
 
 @pytest.mark.parametrize("mtd", [2, 1])
